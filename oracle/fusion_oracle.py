@@ -1,0 +1,95 @@
+"""oracle/fusion_oracle.py -- TEST INFRASTRUCTURE.
+
+NumPy restatement of the reference's Laplacian-pyramid tile fusion, in the reference's float32 op order:
+  Gaussian pyramid     /root/reference/blending_module.py:217-269
+  Laplacian pyramid    /root/reference/blending_module.py:271-318
+  collapse             /root/reference/blending_module.py:320-363
+  fusion               /root/reference/blending_module.py:369-506
+  distance weight map  /root/reference/blending_module.py:508-561
+
+Per tile t (independent pyramids, tile-local borders):
+    G_0 = f32(tile);  G_{l+1} = pyrDown(G_l)            (stops early if a side < 2)
+    W_0 = weight map; W_{l+1} = pyrDown(W_l)
+    C_top = G_top * W_top;   C_l = pyrUp(C_{l+1}) + (G_l - pyrUp(G_{l+1})) * W_l
+    acc[y:y+h, x:x+w] += C_0 (cropped to the canvas);  wacc += W_0
+out = uint8(trunc(clip(acc / max(wacc, 1e-6), 0, 255)))
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import pyr
+
+WEIGHT_KINDS = ("linear", "cosine", "sigmoid")
+
+
+def weight_profile(feather: int, kind: str) -> np.ndarray:
+    """W as a function of d = min distance to the tile border, d = 0..feather (float64 math, then f32),
+    i.e. blending_module.py:543-561 evaluated on the only values it can take."""
+    d = np.arange(feather + 1)
+    nd = np.clip(d / feather, 0, 1)
+    if kind == "cosine":
+        w = 0.5 * (1 - np.cos(np.pi * nd))
+    elif kind == "sigmoid":
+        w = 1 / (1 + np.exp(-10 * (nd - 0.5)))
+    else:
+        w = nd
+    return w.astype(np.float32)
+
+
+def weight_map(h: int, w: int, kind: str = "cosine", feather=None) -> np.ndarray:
+    if feather is None:
+        feather = min(h, w) // 8
+    y = np.arange(h).reshape(-1, 1)
+    x = np.arange(w).reshape(1, -1)
+    d = np.minimum(np.minimum(y, h - 1 - y), np.minimum(x, w - 1 - x))
+    return weight_profile(feather, kind)[np.minimum(d, feather)]
+
+
+def gaussian_pyramid(img: np.ndarray, levels: int, backend="c"):
+    cur = img.astype(np.float32)
+    out = [cur]
+    for _ in range(levels - 1):
+        if cur.shape[0] < 2 or cur.shape[1] < 2:
+            break
+        cur = pyr.pyr_down(cur, backend)
+        out.append(cur)
+    return out
+
+
+def weighted_collapse(g, wp, backend="c"):
+    """C_0 of one tile from its Gaussian pyramid g and weight pyramid wp."""
+    def ex(a):
+        return a[..., None] if g[0].ndim == 3 else a
+    cur = g[-1] * ex(wp[-1])
+    for l in range(len(g) - 2, -1, -1):
+        hw = g[l].shape[:2]
+        lap = g[l] - pyr.pyr_up(g[l + 1], hw, backend)
+        cur = pyr.pyr_up(cur, hw, backend) + lap * ex(wp[l])
+    return cur
+
+
+def laplacian_fuse(tiles, positions_yx, out_hw, levels=6, kind="cosine", backend="c"):
+    """tiles: list of uint8 (h,w,C) or (h,w); positions_yx: list of (y, x); returns uint8 canvas."""
+    H, W = out_hw
+    ch = tiles[0].shape[2:]
+    acc = np.zeros((H, W) + ch, np.float32)
+    wacc = np.zeros((H, W), np.float32)
+    cache = {}
+    for img, (y, x) in zip(tiles, positions_yx):
+        h, w = img.shape[:2]
+        key = (h, w)
+        if key not in cache:  # identical for same-shape tiles; the reference recomputes it per tile
+            w0 = weight_map(h, w, kind)
+            cache[key] = gaussian_pyramid(w0, levels, backend)
+        wp = cache[key]
+        g = gaussian_pyramid(img, levels, backend)
+        c0 = weighted_collapse(g, wp, backend)
+        ye, xe = min(y + h, H), min(x + w, W)
+        if ye <= y or xe <= x:
+            continue
+        acc[y:ye, x:xe] += c0[:ye - y, :xe - x]
+        wacc[y:ye, x:xe] += wp[0][:ye - y, :xe - x]
+    wacc = np.maximum(wacc, np.float32(1e-6))
+    res = acc / (wacc[..., None] if ch else wacc)
+    return np.clip(res, 0, 255).astype(np.uint8)
