@@ -1,0 +1,155 @@
+/*
+ * srfuse.h -- C ABI of libsrfuse.so: the B200 (sm_100a) tile -> Laplacian-fuse -> PSNR/SSIM path.
+ *
+ * The reference (squellww/super-resolution-system) is pure Python and has no FFI of its own; each entry point
+ * below replaces the body of one reference method and is what a ctypes binding inside that method calls
+ * (INTEGRATION.md shows the stubs).  Reference line numbers are into /root/reference.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; images are uint8, HWC interleaved (C = 1 or 3), row pitch in BYTES;
+ *   - every function returns SRF_OK (0) or a negative srf_status; srf_last_error(ctx) has the text;
+ *   - "_host" entry points take HOST buffers, do the host<->device copies themselves and return when the
+ *     result is in the caller's buffer; the others take DEVICE pointers, enqueue on `stream`
+ *     (a cudaStream_t passed as void*, NULL = the legacy default stream) and do not synchronise;
+ *   - the library owns only the workspace inside srf_ctx; callers own every buffer they pass;
+ *   - one srf_ctx per device per host thread; calls on one ctx must not overlap;
+ *   - there is NO CPU fallback: without a usable sm_100-class device srf_create fails.
+ */
+#ifndef SRFUSE_H_
+#define SRFUSE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SRF_VERSION 100 /* 0.1.0 */
+#define SRF_MAX_LEVELS 16
+
+typedef enum srf_status {
+    SRF_OK = 0,
+    SRF_ERR_ARG = -1,     /* bad argument (the Python mirror raises ValueError) */
+    SRF_ERR_CUDA = -2,    /* a CUDA call failed */
+    SRF_ERR_NO_DEVICE = -3,
+    SRF_ERR_OOM = -4,
+    SRF_ERR_UNSUPPORTED = -5
+} srf_status;
+
+/* tiling_module.py:40-45 PaddingMode */
+typedef enum srf_border {
+    SRF_BORDER_MIRROR = 0,    /* 'mirror'    -> cv2.BORDER_REFLECT_101 */
+    SRF_BORDER_REPLICATE = 1, /* 'replicate' -> cv2.BORDER_REPLICATE   */
+    SRF_BORDER_REFLECT = 2,   /* 'reflect'   -> cv2.BORDER_REFLECT     */
+    SRF_BORDER_CONSTANT = 3   /* 'constant'  -> cv2.BORDER_CONSTANT, value 0 */
+} srf_border;
+
+/* blending_module.py:52-57 WeightType */
+typedef enum srf_weight { SRF_WEIGHT_LINEAR = 0, SRF_WEIGHT_COSINE = 1, SRF_WEIGHT_SIGMOID = 2 } srf_weight;
+
+typedef struct srf_ctx srf_ctx;
+
+/* ---- context ------------------------------------------------------------------------------------------- */
+int srf_version(void);
+const char *srf_status_string(int status);
+const char *srf_last_error(const srf_ctx *ctx);
+int srf_create(int device, srf_ctx **out);
+void srf_destroy(srf_ctx *ctx);
+int srf_sync(srf_ctx *ctx, void *stream);
+/* number of kernels this ctx has launched since creation (bench.py's gpu_launches) */
+int64_t srf_launch_count(const srf_ctx *ctx);
+/* bytes of device workspace currently held */
+size_t srf_workspace_bytes(const srf_ctx *ctx);
+/* CUDA-event time (ms) of the device work of the last *_host / srf_laplacian_fuse / srf_psnr_ssim call,
+ * valid after that call's stream has been synchronised; <0 if none */
+float srf_last_device_ms(srf_ctx *ctx);
+
+/* ---- tiling -------------------------------------------------------------------------------------------- */
+/* replaces TilingModule._calculate_tile_positions (tiling_module.py:572-608).  Host-only, exact.
+ * Writes min(count, cap) quadruples (x, y, w, h), row-major, and returns the count (or <0). */
+int srf_tile_positions(int width, int height, int block, int overlap, int *xywh, int cap);
+/* replaces TilingModule._calculate_overlap_for_tile (tiling_module.py:610-646).  out = top,bottom,left,right */
+int srf_tile_overlaps(int x, int y, int w, int h, int width, int height, int block, int overlap, int *out4);
+/* replaces the crop + cv2.copyMakeBorder loop of TilingModule.split_image (tiling_module.py:713-724, 522-570):
+ * tile i = src[y:y+h, x:x+w] padded bottom/right to (block, block, C); tiles_out is n*block*block*C bytes */
+int srf_tile_extract_pad(srf_ctx *ctx, const uint8_t *d_src, int height, int width, int channels, size_t pitch,
+                         const int *xywh, int n, int block, int border, uint8_t *d_tiles_out, void *stream);
+int srf_tile_extract_pad_host(srf_ctx *ctx, const uint8_t *h_src, int height, int width, int channels,
+                              size_t pitch, const int *xywh, int n, int block, int border, uint8_t *h_tiles_out);
+
+/* ---- pyramids (float32, HWC interleaved, packed rows -- the arrays the reference hands to cv2) ---------- */
+/* replaces cv2.pyrDown in BlendingModule.build_gaussian_pyramid (blending_module.py:263);
+ * dst is ((h+1)/2, (w+1)/2, C) */
+int srf_pyr_down_f32(srf_ctx *ctx, const float *d_src, int h, int w, int channels, float *d_dst, void *stream);
+/* replaces cv2.pyrUp(dstsize=) in build_laplacian_pyramid / collapse_laplacian_pyramid
+ * (blending_module.py:306, 358); dst_h in {2h, 2h-1}, dst_w in {2w, 2w-1} */
+int srf_pyr_up_f32(srf_ctx *ctx, const float *d_src, int h, int w, int channels, float *d_dst, int dst_h,
+                   int dst_w, void *stream);
+int srf_pyr_down_f32_host(srf_ctx *ctx, const float *h_src, int h, int w, int channels, float *h_dst);
+int srf_pyr_up_f32_host(srf_ctx *ctx, const float *h_src, int h, int w, int channels, float *h_dst, int dst_h,
+                        int dst_w);
+
+/* ---- Laplacian fusion ---------------------------------------------------------------------------------- */
+/* one upscaled tile (blending_module.py:96-112 TileInfo: image, x, y) */
+typedef struct srf_tile {
+    const uint8_t *data; /* (h, w, C) uint8; device pointer (host pointer for the _host entry point) */
+    size_t pitch;        /* bytes between rows */
+    int h, w;
+    int y, x;            /* canvas position of the tile's top-left pixel (may overhang the canvas) */
+    int lut;             /* index into the srf_weight_lut array */
+} srf_tile;
+
+/* W_0(y,x) = values[min(d, len-1)], d = min distance to the tile border; the 1-D profile of
+ * BlendingModule._create_distance_weight_map (blending_module.py:508-561), len = feather_width + 1 */
+typedef struct srf_weight_lut {
+    const float *values; /* HOST pointer */
+    int len;
+} srf_weight_lut;
+
+/* helper for C callers: fills feather+1 floats with the reference profile (float64 math, cast to float32) */
+int srf_weight_profile(int weight_type, int feather, float *out);
+
+/* replaces BlendingModule.laplacian_fusion (blending_module.py:369-506): per-tile Gaussian/Laplacian pyramids
+ * (levels arrays, tile-local borders), per-level multiply by the tile's weight pyramid, per-tile collapse,
+ * accumulation in list order, divide by max(sum W_0, 1e-6), clip, TRUNCATING cast to uint8.
+ * Only canvas rows [row_begin, row_end) are produced (band sharding; 0, out_h for everything); rows outside
+ * are left untouched.  canvas is (out_h, out_w, C) with `canvas_pitch` bytes per row. */
+int srf_laplacian_fuse(srf_ctx *ctx, const srf_tile *tiles, int n_tiles, int channels, int levels,
+                       const srf_weight_lut *luts, int n_luts, int out_h, int out_w, uint8_t *d_canvas,
+                       size_t canvas_pitch, int row_begin, int row_end, void *stream);
+int srf_laplacian_fuse_host(srf_ctx *ctx, const srf_tile *tiles, int n_tiles, int channels, int levels,
+                            const srf_weight_lut *luts, int n_luts, int out_h, int out_w, uint8_t *h_canvas,
+                            size_t canvas_pitch, int row_begin, int row_end);
+
+/* ---- full-reference IQA -------------------------------------------------------------------------------- */
+/* partial sums of one image pair over a row band; additive across bands / ranks */
+typedef struct srf_iqa_sums {
+    int64_t sq_err;     /* sum (a-b)^2 over every element of rows [row_begin,row_end)            (PSNR) */
+    int64_t n_elems;    /* elements in that sum                                                         */
+    double ssim_sum;    /* sum of the SSIM map over interior pixels (>=5 from every image edge) whose    */
+    int64_t ssim_count; /*   row lies in [row_begin,row_end); and their number                          */
+    int32_t max_a;      /* max element of a / b over the band: the caller applies the reference's        */
+    int32_t max_b;      /*   `image.max() <= 1.0` rescale rule (quality_assessment_module.py:192-193)    */
+} srf_iqa_sums;
+
+/* replaces calculate_psnr + calculate_ssim(multiscale=True) of QualityAssessmentModule
+ * (quality_assessment_module.py:277-320, 322-376) in ONE pass over the pair: integer sum of squared
+ * differences over all channels, cv2-exact RGB->gray, 11-tap sigma=1.5 Gaussian SSIM (C1 = (0.01 data_range)^2,
+ * C2 = (0.03 data_range)^2, population covariance) summed over the interior.  This call SYNCHRONISES `stream`
+ * before returning (it hands scalars back to the host).  scale_a / scale_b: multiply that image by 255 first
+ * (the preprocess rule above), 0 or 1.  a and b are (h, w, C) views of equal size. */
+int srf_psnr_ssim(srf_ctx *ctx, const uint8_t *d_a, size_t pitch_a, const uint8_t *d_b, size_t pitch_b, int h,
+                  int w, int channels, int scale_a, int scale_b, double data_range, int row_begin, int row_end,
+                  srf_iqa_sums *h_out, void *stream);
+int srf_psnr_ssim_host(srf_ctx *ctx, const uint8_t *h_a, size_t pitch_a, const uint8_t *h_b, size_t pitch_b,
+                       int h, int w, int channels, int scale_a, int scale_b, double data_range, int row_begin,
+                       int row_end, srf_iqa_sums *h_out);
+/* final scalars from (all-reduced) sums: psnr = 10 log10(range^2 / (sq_err / n_elems)) (+inf if sq_err == 0),
+ * ssim = ssim_sum / ssim_count */
+int srf_iqa_finish(const srf_iqa_sums *sums, double data_range, double *psnr, double *ssim);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SRFUSE_H_ */

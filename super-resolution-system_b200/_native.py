@@ -1,0 +1,133 @@
+"""ctypes binding of libsrfuse.so (include/srfuse.h).  No CPU fallback: if the library or a usable device is
+missing, every entry point raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+import numpy as np
+
+from . import build as _build
+
+c_void_p, c_int, c_size_t, c_int64 = C.c_void_p, C.c_int, C.c_size_t, C.c_int64
+
+
+class SrfError(RuntimeError):
+    pass
+
+
+class srf_tile(C.Structure):
+    _fields_ = [("data", c_void_p), ("pitch", c_size_t), ("h", c_int), ("w", c_int), ("y", c_int), ("x", c_int),
+                ("lut", c_int)]
+
+
+class srf_weight_lut(C.Structure):
+    _fields_ = [("values", c_void_p), ("len", c_int)]
+
+
+class srf_iqa_sums(C.Structure):
+    _fields_ = [("sq_err", c_int64), ("n_elems", c_int64), ("ssim_sum", C.c_double), ("ssim_count", c_int64),
+                ("max_a", C.c_int32), ("max_b", C.c_int32)]
+
+
+# every symbol include/srfuse.h declares: name -> (restype, argtypes)
+P = C.POINTER
+SIGNATURES = {
+    "srf_version": (c_int, []),
+    "srf_status_string": (C.c_char_p, [c_int]),
+    "srf_last_error": (C.c_char_p, [c_void_p]),
+    "srf_create": (c_int, [c_int, P(c_void_p)]),
+    "srf_destroy": (None, [c_void_p]),
+    "srf_sync": (c_int, [c_void_p, c_void_p]),
+    "srf_launch_count": (c_int64, [c_void_p]),
+    "srf_workspace_bytes": (c_size_t, [c_void_p]),
+    "srf_last_device_ms": (C.c_float, [c_void_p]),
+    "srf_tile_positions": (c_int, [c_int, c_int, c_int, c_int, c_void_p, c_int]),
+    "srf_tile_overlaps": (c_int, [c_int] * 8 + [c_void_p]),
+    "srf_tile_extract_pad": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_size_t, c_void_p, c_int, c_int, c_int,
+                                     c_void_p, c_void_p]),
+    "srf_tile_extract_pad_host": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_size_t, c_void_p, c_int, c_int,
+                                          c_int, c_void_p]),
+    "srf_pyr_down_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "srf_pyr_up_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p]),
+    "srf_pyr_down_f32_host": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "srf_pyr_up_f32_host": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int]),
+    "srf_weight_profile": (c_int, [c_int, c_int, c_void_p]),
+    "srf_laplacian_fuse": (c_int, [c_void_p, P(srf_tile), c_int, c_int, c_int, P(srf_weight_lut), c_int, c_int, c_int,
+                                   c_void_p, c_size_t, c_int, c_int, c_void_p]),
+    "srf_laplacian_fuse_host": (c_int, [c_void_p, P(srf_tile), c_int, c_int, c_int, P(srf_weight_lut), c_int, c_int,
+                                        c_int, c_void_p, c_size_t, c_int, c_int]),
+    "srf_psnr_ssim": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, c_int, c_int, c_int, c_int, c_int,
+                              C.c_double, c_int, c_int, P(srf_iqa_sums), c_void_p]),
+    "srf_psnr_ssim_host": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, c_int, c_int, c_int, c_int, c_int,
+                                   C.c_double, c_int, c_int, P(srf_iqa_sums)]),
+    "srf_iqa_finish": (c_int, [P(srf_iqa_sums), C.c_double, P(C.c_double), P(C.c_double)]),
+}
+
+_lib = None
+_lock = threading.RLock()
+_ctx = {}
+
+
+def lib_path() -> str:
+    return _build.LIB_PATH
+
+
+def load():
+    """dlopen libsrfuse.so and bind every declared symbol; raises if the library has not been built."""
+    global _lib
+    with _lock:
+        if _lib is None:
+            path = lib_path()
+            if not os.path.exists(path):
+                raise SrfError(f"{path} is missing -- run `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "(libsrfuse has no CPU fallback)")
+            lib = C.CDLL(path)
+            for name, (res, args) in SIGNATURES.items():
+                fn = getattr(lib, name)  # AttributeError if the export is missing
+                fn.restype = res
+                fn.argtypes = args
+            _lib = lib
+    return _lib
+
+
+def last_error(ctx=None) -> str:
+    msg = load().srf_last_error(ctx)
+    return msg.decode("utf-8", "replace") if msg else ""
+
+
+def check(rc: int, ctx=None, exc=None):
+    if rc >= 0:
+        return rc
+    text = last_error(ctx) or load().srf_status_string(rc).decode()
+    if rc == -1:
+        raise (exc or ValueError)(text)
+    if rc == -4:
+        raise MemoryError(text)
+    raise SrfError(f"libsrfuse status {rc}: {text}")
+
+
+def context(device: int = 0):
+    """one srf_ctx per (process, device); raises SrfError when no sm_100 device is usable."""
+    lib = load()
+    with _lock:
+        if device not in _ctx:
+            h = c_void_p()
+            rc = lib.srf_create(device, C.byref(h))
+            if rc != 0:
+                raise SrfError(f"srf_create(device={device}) failed ({rc}): {last_error(None)}")
+            _ctx[device] = h
+    return _ctx[device]
+
+
+def destroy_contexts():
+    lib = load()
+    with _lock:
+        for h in _ctx.values():
+            lib.srf_destroy(h)
+        _ctx.clear()
+
+
+def np_ptr(a: np.ndarray) -> int:
+    return a.ctypes.data

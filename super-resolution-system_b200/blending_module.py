@@ -1,0 +1,237 @@
+"""GPU mirror of the reference's blending module -- the Laplacian-pyramid tile fusion and its pyramid helpers.
+
+Mirrors (names, arguments, error behaviour) /root/reference/blending_module.py:
+  FusionMethod 36-40, WeightType 52-56, TileInfo 96-112, BlendingModule.__init__ 164-190,
+  build_gaussian_pyramid 217-269, build_laplacian_pyramid 271-318, collapse_laplacian_pyramid 320-363,
+  laplacian_fusion 369-506, _create_distance_weight_map 508-561.
+Every pixel is computed by libsrfuse.so (csrc/srf_fuse.cu) through the C ABI; nothing here falls back to the CPU.
+Out of scope: Poisson / weighted / feather / gradient-domain fusion, seam detection and
+repair, colour correction -- those entry points raise NotImplementedError.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import logging
+from dataclasses import dataclass
+from enum import Enum
+from typing import List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+
+from . import _native
+from ._arrays import ImageView, current_stream_ptr, is_cuda_tensor, torch
+
+logger = logging.getLogger(__name__)
+
+
+class FusionMethod(Enum):
+    LAPLACIAN = "laplacian"
+    POISSON = "poisson"
+    WEIGHTED_AVERAGE = "weighted"
+
+
+class WeightType(Enum):
+    LINEAR = "linear"
+    COSINE = "cosine"
+    SIGMOID = "sigmoid"
+
+
+@dataclass
+class TileInfo:
+    """an upscaled tile and where its top-left pixel sits on the canvas"""
+    image: np.ndarray
+    x: int
+    y: int
+    row: int
+    col: int
+
+
+def weight_profile(feather_width: int, weight_type: WeightType) -> np.ndarray:
+    """The distance-weight map only depends on d = min distance to the tile border, and only through
+    min(d, feather_width): this is that 1-D profile, evaluated with the reference's float64 NumPy expressions
+    (blending_module.py:543-561) so the float32 values are the reference's bit for bit."""
+    d = np.arange(feather_width + 1)
+    nd = np.clip(d / feather_width, 0, 1)
+    if weight_type == WeightType.LINEAR:
+        w = nd
+    elif weight_type == WeightType.COSINE:
+        w = 0.5 * (1 - np.cos(np.pi * nd))
+    elif weight_type == WeightType.SIGMOID:
+        w = 1 / (1 + np.exp(-10 * (nd - 0.5)))
+    else:
+        w = nd
+    return np.ascontiguousarray(w.astype(np.float32))
+
+
+class BlendingModule:
+    def __init__(self, method: str = "laplacian", num_levels: int = 6, ssim_threshold: float = 0.95,
+                 use_cuda: bool = False, device: int = 0):
+        self.method = FusionMethod(method)  # ValueError on an unknown method, like the reference
+        self.num_levels = num_levels
+        self.ssim_threshold = ssim_threshold
+        self.use_cuda = True  # the only path there is; the reference's flag selected cv2.cuda and is accepted for compatibility
+        self.device = int(device)
+        self._profiles = {}
+        logger.info("BlendingModule (libsrfuse, sm_100a): method=%s levels=%d device=%d", method, num_levels, self.device)
+
+    # ------------------------------------------------------------------ pyramids (API-compat helpers)
+    def _ctx(self):
+        return _native.context(self.device)
+
+    def _pyr_down(self, img: np.ndarray) -> np.ndarray:
+        lib = _native.load()
+        h, w = img.shape[:2]
+        cn = 1 if img.ndim == 2 else img.shape[2]
+        out = np.empty(((h + 1) // 2, (w + 1) // 2) + img.shape[2:], np.float32)
+        _native.check(lib.srf_pyr_down_f32_host(self._ctx(), img.ctypes.data, h, w, cn, out.ctypes.data), self._ctx())
+        return out
+
+    def _pyr_up(self, img: np.ndarray, dst_hw: Tuple[int, int]) -> np.ndarray:
+        lib = _native.load()
+        h, w = img.shape[:2]
+        cn = 1 if img.ndim == 2 else img.shape[2]
+        out = np.empty((int(dst_hw[0]), int(dst_hw[1])) + img.shape[2:], np.float32)
+        _native.check(lib.srf_pyr_up_f32_host(self._ctx(), img.ctypes.data, h, w, cn, out.ctypes.data, out.shape[0],
+                                              out.shape[1]), self._ctx())
+        return out
+
+    def build_gaussian_pyramid(self, image: np.ndarray, levels: Optional[int] = None) -> List[np.ndarray]:
+        if levels is None:
+            levels = self.num_levels
+        cur = np.ascontiguousarray(image, dtype=np.float32)
+        pyramid = [cur.copy()]
+        for i in range(levels - 1):
+            if cur.shape[0] < 2 or cur.shape[1] < 2:
+                logger.warning("Stopping pyramid at level %d: image too small", i + 1)
+                break
+            cur = self._pyr_down(cur)
+            pyramid.append(cur)
+        return pyramid
+
+    def build_laplacian_pyramid(self, gaussian_pyramid: Sequence[np.ndarray]) -> List[np.ndarray]:
+        out = []
+        for cur, nxt in zip(gaussian_pyramid[:-1], gaussian_pyramid[1:]):
+            up = self._pyr_up(np.ascontiguousarray(nxt, dtype=np.float32), cur.shape[:2])
+            out.append(cur - up)
+        out.append(gaussian_pyramid[-1])
+        return out
+
+    def collapse_laplacian_pyramid(self, laplacian_pyramid: Sequence[np.ndarray]) -> np.ndarray:
+        cur = np.array(laplacian_pyramid[-1], dtype=np.float32, copy=True)
+        for layer in reversed(laplacian_pyramid[:-1]):
+            cur = self._pyr_up(np.ascontiguousarray(cur), layer.shape[:2]) + layer
+        return cur
+
+    # ------------------------------------------------------------------ weights
+    def _profile(self, h: int, w: int, weight_type: WeightType, feather_width: Optional[int] = None) -> np.ndarray:
+        if feather_width is None:
+            feather_width = min(h, w) // 8
+        if feather_width < 1:
+            raise ValueError(f"tile {h}x{w} is too small for a distance weight map (feather width {feather_width})")
+        key = (feather_width, weight_type)
+        if key not in self._profiles:
+            self._profiles[key] = weight_profile(feather_width, weight_type)
+        return self._profiles[key]
+
+    def _create_distance_weight_map(self, height: int, width: int, weight_type: WeightType,
+                                    feather_width: Optional[int] = None) -> np.ndarray:
+        """(H, W) float32 map in [0, 1]: the profile indexed by border distance (host-side table lookup; the fusion
+        kernels index the same profile on the fly and never materialise this map)."""
+        prof = self._profile(height, width, weight_type, feather_width)
+        y = np.arange(height).reshape(-1, 1)
+        x = np.arange(width).reshape(1, -1)
+        d = np.minimum(np.minimum(y, height - 1 - y), np.minimum(x, width - 1 - x))
+        return prof[np.minimum(d, len(prof) - 1)]
+
+    # ------------------------------------------------------------------ fusion
+    def laplacian_fusion(self, tiles: List[Union[np.ndarray, TileInfo]], overlap_map=None,
+                         output_shape: Optional[Tuple[int, int]] = None,
+                         weight_type: WeightType = WeightType.COSINE, row_range: Optional[Tuple[int, int]] = None):
+        """Fuse upscaled tiles into one uint8 canvas (see include/srfuse.h: srf_laplacian_fuse).
+
+        tiles: TileInfo objects (image + x, y) or bare arrays (grid layout, needs output_shape).  Images are uint8
+        NumPy arrays (host path: H2D, kernels, D2H inside the call) or uint8 torch CUDA tensors (device path: the
+        result is a CUDA tensor and stays on the device).  `overlap_map` is accepted and ignored, as in the
+        reference (blending_module.py:369-506 never reads it).  `row_range` (extension) restricts the produced
+        canvas rows for band sharding across GPUs.
+        """
+        images, positions = [], []
+        for i, t in enumerate(tiles):
+            if isinstance(t, TileInfo):
+                images.append(t.image)
+                positions.append((int(t.y), int(t.x)))
+            else:
+                images.append(t)
+                if output_shape:
+                    grid = int(np.ceil(np.sqrt(len(tiles))))
+                    r, c = i // grid, i % grid
+                    positions.append((r * t.shape[0], c * t.shape[1]))
+        if not images:
+            raise ValueError("laplacian_fusion: no tiles")
+        if len(positions) != len(images):
+            # the reference dies in max() over an empty sequence here (ValueError); same exception type
+            raise ValueError("laplacian_fusion: bare-array tiles need output_shape to derive a grid layout")
+        views = [ImageView(im, f"tile {i}") for i, im in enumerate(images)]
+        on_dev = views[0].on_device
+        if any(v.on_device != on_dev for v in views):
+            raise ValueError("laplacian_fusion: mix of host and device tiles")
+        chans = views[0].c
+        if any(v.c != chans for v in views):
+            raise ValueError("laplacian_fusion: tiles disagree on the channel count")
+        if output_shape is None:
+            out_h = max(y + v.h for v, (y, _) in zip(views, positions))
+            out_w = max(x + v.w for v, (_, x) in zip(views, positions))
+        else:
+            out_h, out_w = int(output_shape[0]), int(output_shape[1])
+        r0, r1 = (0, out_h) if row_range is None else (int(row_range[0]), int(row_range[1]))
+
+        lut_index, luts = {}, []
+        c_tiles = (_native.srf_tile * len(views))()
+        for i, (v, (y, x)) in enumerate(zip(views, positions)):
+            prof = self._profile(v.h, v.w, weight_type)
+            if id(prof) not in lut_index:
+                lut_index[id(prof)] = len(luts)
+                luts.append(prof)
+            c_tiles[i] = _native.srf_tile(v.ptr, v.pitch, v.h, v.w, y, x, lut_index[id(prof)])
+        c_luts = (_native.srf_weight_lut * len(luts))(*[_native.srf_weight_lut(p.ctypes.data, len(p)) for p in luts])
+
+        lib, ctx = _native.load(), self._ctx()
+        shape = (out_h, out_w) if views[0].keep.ndim == 2 else (out_h, out_w, chans)
+        if on_dev:
+            dev = views[0].device
+            if dev != self.device:
+                raise ValueError(f"tiles live on cuda:{dev} but this BlendingModule is bound to cuda:{self.device}")
+            staged = []
+            for i, v in enumerate(views):  # the kernels want 16-byte aligned rows
+                if v.ptr % 16 or (v.pitch % 16 and v.h > 1):
+                    pitch = (v.w * chans + 15) // 16 * 16
+                    buf = torch.empty((v.h, pitch), dtype=torch.uint8, device=v.keep.device)
+                    buf[:, : v.w * chans] = v.keep.reshape(v.h, v.w * chans)
+                    staged.append(buf)
+                    c_tiles[i].data, c_tiles[i].pitch = buf.data_ptr(), pitch
+            canvas = torch.zeros(shape, dtype=torch.uint8, device=views[0].keep.device) if (r0, r1) != (0, out_h) \
+                else torch.empty(shape, dtype=torch.uint8, device=views[0].keep.device)
+            rc = lib.srf_laplacian_fuse(ctx, c_tiles, len(views), chans, self.num_levels, c_luts, len(luts), out_h,
+                                        out_w, canvas.data_ptr(), out_w * chans, r0, r1, current_stream_ptr(dev))
+            _native.check(rc, ctx)
+            del staged
+            return canvas
+        canvas = np.zeros(shape, np.uint8) if (r0, r1) != (0, out_h) else np.empty(shape, np.uint8)
+        rc = lib.srf_laplacian_fuse_host(ctx, c_tiles, len(views), chans, self.num_levels, c_luts, len(luts), out_h,
+                                         out_w, canvas.ctypes.data, out_w * chans, r0, r1)
+        _native.check(rc, ctx)
+        return canvas
+
+    # ------------------------------------------------------------------ explicitly out of scope
+    def _out_of_scope(self, name):
+        raise NotImplementedError(f"BlendingModule.{name} is outside the B200 hot path (SURVEY.md section 8); "
+                                  "only laplacian_fusion and the pyramid helpers are provided")
+
+    def poisson_fusion(self, *a, **k):
+        self._out_of_scope("poisson_fusion")
+
+    def weighted_average_fusion(self, *a, **k):
+        self._out_of_scope("weighted_average_fusion")
+
+    def detect_seams(self, *a, **k):
+        self._out_of_scope("detect_seams")

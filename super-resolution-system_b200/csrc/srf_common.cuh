@@ -1,0 +1,143 @@
+// srf_common.cuh -- shared declarations for libsrfuse (sm_100a).
+//
+// Float32 op ORDER is part of the contract: the reference path (cv2.pyrDown / cv2.pyrUp on float32 followed by a
+// truncating uint8 cast, /root/reference/blending_module.py:263, 306, 358, 504-506) is reproduced rounding for
+// rounding, so every arithmetic step below is an explicit __f*_rn intrinsic (never contracted into an FMA).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include <map>
+
+#include "../../include/srfuse.h"
+
+#define SRF_CHECK_CUDA(ctx, expr)                                                                   \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess) {                                                                    \
+            srf_set_error((ctx), "%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            return (_e == cudaErrorMemoryAllocation) ? SRF_ERR_OOM : SRF_ERR_CUDA;                  \
+        }                                                                                           \
+    } while (0)
+
+#define SRF_REQUIRE(ctx, cond, ...)           \
+    do {                                      \
+        if (!(cond)) {                        \
+            srf_set_error((ctx), __VA_ARGS__); \
+            return SRF_ERR_ARG;               \
+        }                                     \
+    } while (0)
+
+struct srf_buffer {
+    void *ptr = nullptr;
+    size_t bytes = 0;
+};
+
+struct srf_ctx {
+    int device = 0;
+    int sm_count = 148;
+    std::string last_error;
+    int64_t launches = 0;
+    // grow-only device workspaces, by role
+    srf_buffer ws_pyr;      // per-tile G/C pyramids + weight pyramids
+    srf_buffer ws_desc;     // device copies of descriptor arrays
+    srf_buffer ws_stage_in; // *_host entry points: device staging of inputs
+    srf_buffer ws_stage_out;
+    srf_buffer ws_misc;     // weight profiles
+    srf_buffer ws_iqa;      // IQA reduction partials
+    void *pinned = nullptr; // small pinned host block for result read-back
+    size_t pinned_bytes = 0;
+    cudaStream_t own_stream = nullptr; // used by the *_host entry points
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool ev_valid = false;
+    std::vector<cudaEvent_t> ev_pool;
+};
+
+void srf_set_error(srf_ctx *ctx, const char *fmt, ...);
+void srf_set_error(const srf_ctx *ctx, const char *fmt, ...);
+int srf_reserve(srf_ctx *ctx, srf_buffer &b, size_t bytes);
+int srf_reserve_pinned(srf_ctx *ctx, size_t bytes);
+
+static inline int srf_ceil_div(int a, int b) { return (a + b - 1) / b; }
+static inline size_t srf_align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ---- index maps -------------------------------------------------------------------------------------------
+// cv2 BORDER_REFLECT_101 with multi-bounce (index i on an axis of length n)
+__host__ __device__ __forceinline__ int srf_reflect101(int i, int n)
+{
+    if (n == 1) return 0;
+    while (i < 0 || i >= n) i = (i < 0) ? -i : 2 * (n - 1) - i;
+    return i;
+}
+
+// ---- pyrDown / pyrUp arithmetic, in OpenCV's float32 op order (see oracle/pyr_oracle.c) -------------------
+#ifdef __CUDACC__
+// horizontal 5-tap, SIMD-body order: r2*6 + ((r1+r3)*4 + (r0+r4))
+__device__ __forceinline__ float dn_h_vec(float r0, float r1, float r2, float r3, float r4)
+{
+    float a = __fmul_rn(__fadd_rn(r1, r3), 4.f);
+    float b = __fadd_rn(r0, r4);
+    return __fadd_rn(__fmul_rn(r2, 6.f), __fadd_rn(a, b));
+}
+// horizontal 5-tap, scalar order (border columns and SIMD tail): ((r2*6 + (r1+r3)*4) + r0) + r4
+__device__ __forceinline__ float dn_h_sca(float r0, float r1, float r2, float r3, float r4)
+{
+    float a = __fmul_rn(r2, 6.f);
+    float b = __fmul_rn(__fadd_rn(r1, r3), 4.f);
+    return __fadd_rn(__fadd_rn(__fadd_rn(a, b), r0), r4);
+}
+// vertical 5-tap, SIMD-body order: (((r1+r3)+r2)*4 + ((r0+r4)+(r2+r2))) * 1/256
+__device__ __forceinline__ float dn_v_vec(float r0, float r1, float r2, float r3, float r4)
+{
+    float a = __fmul_rn(__fadd_rn(__fadd_rn(r1, r3), r2), 4.f);
+    float b = __fadd_rn(__fadd_rn(r0, r4), __fadd_rn(r2, r2));
+    return __fmul_rn(__fadd_rn(a, b), 1.f / 256.f);
+}
+__device__ __forceinline__ float dn_v_sca(float r0, float r1, float r2, float r3, float r4)
+{
+    return __fmul_rn(dn_h_sca(r0, r1, r2, r3, r4), 1.f / 256.f);
+}
+// pyrUp 1-D forms (un-normalised: each pass leaves a factor 8)
+__device__ __forceinline__ float up_even(float m, float p, float n) { return __fadd_rn(__fadd_rn(__fmul_rn(p, 6.f), m), n); }
+__device__ __forceinline__ float up_even_left(float p, float n) { return __fadd_rn(__fmul_rn(p, 6.f), __fmul_rn(n, 2.f)); }
+__device__ __forceinline__ float up_even_right(float m, float p) { return __fadd_rn(m, __fmul_rn(p, 7.f)); }
+__device__ __forceinline__ float up_odd(float p, float n) { return __fmul_rn(__fadd_rn(p, n), 4.f); }
+__device__ __forceinline__ float up_odd_right(float p) { return __fmul_rn(p, 8.f); }
+
+// horizontal pyrUp sample `tx` (0 .. 2*w-1) of a source row addressed through `at(i)`, i in [0, w)
+template <class At>
+__device__ __forceinline__ float up_h_sample(int tx, int w, At at)
+{
+    const int i = tx >> 1;
+    const float p = at(i);
+    if (w == 1) return __fmul_rn(p, 8.f);
+    if (tx & 1) return (i == w - 1) ? up_odd_right(p) : up_odd(p, at(i + 1));
+    if (i == 0) return up_even_left(p, at(1));
+    if (i == w - 1) return up_even_right(at(i - 1), p);
+    return up_even(at(i - 1), p, at(i + 1));
+}
+#endif
+
+// number of output columns (pixels) of a pyrDown row that OpenCV's 4-lane SIMD body covers: columns
+// [1, vec_end) use the vector op order, all others the scalar one (cn = channels of the REFERENCE's
+// interleaved array: 3 for image pyramids, 1 for weight pyramids)
+__host__ __device__ __forceinline__ int srf_down_vec_end(int w, int ow, int cn)
+{
+    int width0 = (w - 3) / 2 + 1;
+    if (width0 > ow) width0 = ow;
+    if (width0 < 1) return 1;
+    if (cn == 1) return 1 + 4 * ((width0 - 1) / 4);
+    if (cn == 3) return (width0 - 1 > 1) ? width0 - 1 : 1;
+    if (cn == 2) return 1 + 2 * ((width0 - 1) / 2);
+    if (cn == 4) return width0;
+    return 1;
+}
+
+// ---- internal entry points shared between translation units ------------------------------------------------
+int srf_launch_pyr_down_hwc(srf_ctx *ctx, const float *src, int h, int w, int cn, float *dst, cudaStream_t st);
+int srf_launch_pyr_up_hwc(srf_ctx *ctx, const float *src, int h, int w, int cn, float *dst, int dh, int dw,
+                          cudaStream_t st);

@@ -1,0 +1,958 @@
+// srf_fuse.cu -- Laplacian-pyramid tile fusion (replaces BlendingModule.laplacian_fusion,
+// /root/reference/blending_module.py:369-506) as five planar-float32 kernels:
+//
+//   k_down_u8    tile uint8 HWC            -> G_1 (planar f32)                 integer-exact 5x5 / 256
+//   k_down_f32   G_l / W_l (planar f32)    -> G_{l+1} / W_{l+1}                cv2.pyrDown op order
+//                (W_0 is never materialised: the level-0 weight is a 1-D profile looked up by border distance)
+//   k_up_level   C_l = pyrUp(C_{l+1}) + (G_l - pyrUp(G_{l+1})) * W_l          l = n-2 .. 1, one pass per level;
+//                the top level's C = G*W product is folded into the first pass
+//   k_final      canvas gather: for every canvas pixel, in tile-list order, C_0 of each covering tile is rebuilt
+//                from (C_1, G_1, the uint8 tile, W_0) and summed; divide by max(sum W_0, 1e-6), clip, truncate
+//
+// Nothing canvas-sized is ever held in float32: the reference's two float accumulators (16 B per canvas pixel,
+// read-modify-written once per tile) become registers in k_final.
+//
+// Data layout: every pyramid level is stored planar, one (h_l x pitch_l) float plane per channel, pitch_l = w_l
+// rounded up to 4 floats so every row is 16-byte aligned.  Tiles that share (h, w, weight profile) form a group;
+// a group shares one weight pyramid and one launch per level (grid.z = tile).
+#include "srf_common.cuh"
+
+#include <algorithm>
+#include <string.h>
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int DN_BH = 16, DN_BW = 64;               // pyrDown output block
+constexpr int DN_IN_ROWS = 2 * DN_BH + 3;           // 35 input rows
+constexpr int DN_IN_COLS_F32 = 2 * DN_BW + 8;       // staged f32 cols: [2*ox0-4, 2*ox0+132)
+constexpr int DN_IN_BYTES_U8 = 416;                 // staged bytes per row for the uint8 source
+constexpr int UP_BH = 32, UP_BW = 64;               // pyrUp / final output block
+constexpr int UP_SRC_ROWS = UP_BH / 2 + 3;          // 19 source rows (odd start + both halos)
+constexpr int UP_SRC_COLS = 44;                     // staged source cols (11 float4)
+
+struct LevelGeom {
+    int h, w, pitch;  // pitch in floats
+    size_t plane;     // floats between channel planes
+    int vec_end;      // pyrDown op-order bookkeeping for the level ABOVE (this level as destination)
+    int vtail;
+};
+
+struct GroupDev {
+    int n_levels;            // levels actually built (<= requested)
+    int cn;                  // channels (1 or 3)
+    int lut_len;
+    const float *lut;        // device copy of the weight profile
+    LevelGeom lv[SRF_MAX_LEVELS];
+    float *W[SRF_MAX_LEVELS]; // W[l], l >= 1 (single plane); W[0] unused
+};
+
+struct TileDev {
+    const uint8_t *src;
+    size_t pitch;
+    int h, w, y, x;
+    float *G[SRF_MAX_LEVELS]; // l >= 1
+    float *C[SRF_MAX_LEVELS]; // 1 <= l <= n-2
+    int g0[SRF_MAX_LEVELS], g1[SRF_MAX_LEVELS]; // rows of G_l to produce
+    int c0[SRF_MAX_LEVELS], c1[SRF_MAX_LEVELS]; // rows of C_l to produce
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// cooperative staging helpers
+// ------------------------------------------------------------------------------------------------------------
+// Copy bytes [b0, b0 + nbytes) of a global row (valid bytes [0, valid)) into smem; b0 is a multiple of 16, the
+// row base is 16-byte aligned, smem dst is 16-byte aligned.  Out-of-range bytes become 0.
+__device__ __forceinline__ void stage_u8_chunk(uint8_t *sdst, const uint8_t *grow, int b0, int chunk, int valid)
+{
+    const int o = b0 + chunk * 16;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (grow != nullptr) {
+        if (o >= 0 && o + 16 <= valid) {
+            v = *reinterpret_cast<const uint4 *>(grow + o);
+        } else if (o + 16 > 0 && o < valid) {
+            uint8_t *b = reinterpret_cast<uint8_t *>(&v);
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+                const int p = o + e;
+                b[e] = (p >= 0 && p < valid) ? grow[p] : (uint8_t)0;
+            }
+        }
+    }
+    *reinterpret_cast<uint4 *>(sdst + chunk * 16) = v;
+}
+
+// same for float planes: cols [c0, c0+4) of a row with `w` valid floats (pitch multiple of 4, c0 multiple of 4)
+__device__ __forceinline__ float4 load_f32_chunk(const float *grow, int c0, int w)
+{
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (grow != nullptr && c0 >= 0 && c0 < w) {
+        if (c0 + 4 <= w) {
+            v = *reinterpret_cast<const float4 *>(grow + c0);
+        } else {
+            v.x = grow[c0];
+            if (c0 + 1 < w) v.y = grow[c0 + 1];
+            if (c0 + 2 < w) v.z = grow[c0 + 2];
+        }
+    }
+    return v;
+}
+
+__device__ __forceinline__ float lut_weight(const float *__restrict__ lut, int lut_len, int y, int x, int h, int w)
+{
+    int d = min(min(y, h - 1 - y), min(x, w - 1 - x));
+    d = min(d, lut_len - 1);
+    return __ldg(lut + d);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// k_down_u8: uint8 HWC tile -> G_1 planar.  All sums are exact integers (<= 65280), so OpenCV's float op order
+// is irrelevant here; the result is (int) * 2^-8, bit-identical to cv2.pyrDown(float32(tile)).
+// grid = (ceil(ow/64), ceil(rows/16), tiles in group)
+// ------------------------------------------------------------------------------------------------------------
+template <int C>
+__global__ void __launch_bounds__(kThreads) k_down_u8(const TileDev *__restrict__ tiles, const int *__restrict__ tile_ids, GroupDev g)
+{
+    __shared__ __align__(16) uint8_t s_in[DN_IN_ROWS][DN_IN_BYTES_U8];
+    __shared__ int s_h[DN_IN_ROWS][C][DN_BW];
+
+    const TileDev &t = tiles[tile_ids[blockIdx.z]];
+    const int h = t.h, w = t.w;
+    const int oh = g.lv[1].h, ow = g.lv[1].w;
+    const int oy0 = t.g0[1] + blockIdx.y * DN_BH;
+    const int ox0 = blockIdx.x * DN_BW;
+    if (oy0 >= t.g1[1] || ox0 >= ow) return;
+    const int oy1 = min(oy0 + DN_BH, t.g1[1]);
+    const int in_y0 = 2 * oy0 - 2;
+    const int px0 = 2 * ox0 - 2;
+    const int byte0 = px0 * C;
+    const int a0 = (byte0 >= 0) ? (byte0 & ~15) : -(((-byte0) + 15) & ~15);
+    const int boff = byte0 - a0;
+    const int n_in_rows = 2 * (oy1 - oy0) + 3;
+
+    for (int i = threadIdx.x; i < n_in_rows * (DN_IN_BYTES_U8 / 16); i += kThreads) {
+        const int r = i / (DN_IN_BYTES_U8 / 16), ch = i - r * (DN_IN_BYTES_U8 / 16);
+        const int gy = in_y0 + r;
+        const uint8_t *grow = (gy >= 0 && gy < h) ? t.src + (size_t)gy * t.pitch : nullptr;
+        stage_u8_chunk(&s_in[r][0], grow, a0, ch, w * C);
+    }
+    __syncthreads();
+
+    const bool x_interior = (px0 >= 0) && (px0 + 2 * DN_BW + 2 < w);
+    for (int i = threadIdx.x; i < n_in_rows * C * DN_BW; i += kThreads) {
+        const int x = i % DN_BW;
+        const int c = (i / DN_BW) % C;
+        const int r = i / (DN_BW * C);
+        const int gy = in_y0 + r;
+        if (gy < 0 || gy >= h || ox0 + x >= ow) continue;
+        const uint8_t *row = &s_in[r][boff + c];
+        int b0, b1, b2, b3, b4;
+        if (x_interior) {
+            const uint8_t *p = row + 2 * x * C;
+            b0 = p[0]; b1 = p[C]; b2 = p[2 * C]; b3 = p[3 * C]; b4 = p[4 * C];
+        } else {
+            const int gx = 2 * (ox0 + x);
+            b0 = row[(srf_reflect101(gx - 2, w) - px0) * C];
+            b1 = row[(srf_reflect101(gx - 1, w) - px0) * C];
+            b2 = row[(srf_reflect101(gx, w) - px0) * C];
+            b3 = row[(srf_reflect101(gx + 1, w) - px0) * C];
+            b4 = row[(srf_reflect101(gx + 2, w) - px0) * C];
+        }
+        s_h[r][c][x] = b0 + b4 + 4 * (b1 + b3) + 6 * b2;
+    }
+    __syncthreads();
+
+    const int n_out_rows = oy1 - oy0;
+    const LevelGeom L1 = g.lv[1];
+    for (int i = threadIdx.x; i < n_out_rows * C * DN_BW; i += kThreads) {
+        const int x = i % DN_BW;
+        const int c = (i / DN_BW) % C;
+        const int ry = i / (DN_BW * C);
+        const int ox = ox0 + x;
+        if (ox >= ow) continue;
+        const int oy = oy0 + ry;
+        int rr[5];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) rr[k] = srf_reflect101(2 * oy + k - 2, h) - in_y0;
+        const int v = s_h[rr[0]][c][x] + s_h[rr[4]][c][x] + 4 * (s_h[rr[1]][c][x] + s_h[rr[3]][c][x]) + 6 * s_h[rr[2]][c][x];
+        t.G[1][(size_t)c * L1.plane + (size_t)oy * L1.pitch + ox] = __fmul_rn((float)v, 1.f / 256.f);
+    }
+    (void)oh;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// k_down_f32: one planar f32 level -> the next (cv2.pyrDown op order incl. the SIMD-body / scalar split).
+// WEIGHT=false: source = tile G_l planes (grid.z = tile * C + c);
+// WEIGHT=true : source = group weight plane W_l, or the border-distance profile when l == 0 (grid.z = 1).
+// ------------------------------------------------------------------------------------------------------------
+template <bool WEIGHT>
+__global__ void __launch_bounds__(kThreads) k_down_f32(const TileDev *__restrict__ tiles, const int *__restrict__ tile_ids, GroupDev g,
+                                                       int l /* source level */)
+{
+    __shared__ __align__(16) float s_in[DN_IN_ROWS][DN_IN_COLS_F32];
+    __shared__ float s_h[DN_IN_ROWS][DN_BW];
+
+    const LevelGeom Ls = g.lv[l], Ld = g.lv[l + 1];
+    const int h = Ls.h, w = Ls.w, ow = Ld.w;
+    const float *src = nullptr;
+    float *dst;
+    int r0, r1, c = 0, cn_ref;
+    if (WEIGHT) {
+        if (l > 0) src = g.W[l];
+        dst = g.W[l + 1];
+        r0 = 0;
+        r1 = Ld.h;
+        cn_ref = 1;
+    } else {
+        const int z = blockIdx.z;
+        const TileDev &t = tiles[tile_ids[z / g.cn]];
+        c = z % g.cn;
+        src = t.G[l] + (size_t)c * Ls.plane;
+        dst = t.G[l + 1] + (size_t)c * Ld.plane;
+        r0 = t.g0[l + 1];
+        r1 = t.g1[l + 1];
+        cn_ref = g.cn;
+    }
+    const int oy0 = r0 + blockIdx.y * DN_BH;
+    const int ox0 = blockIdx.x * DN_BW;
+    if (oy0 >= r1 || ox0 >= ow) return;
+    const int oy1 = min(oy0 + DN_BH, r1);
+    const int in_y0 = 2 * oy0 - 2;
+    const int in_x0 = 2 * ox0 - 4; // multiple of 4
+    const int n_in_rows = 2 * (oy1 - oy0) + 3;
+
+    for (int i = threadIdx.x; i < n_in_rows * (DN_IN_COLS_F32 / 4); i += kThreads) {
+        const int r = i / (DN_IN_COLS_F32 / 4), ch = i - r * (DN_IN_COLS_F32 / 4);
+        const int gy = in_y0 + r;
+        const int c0 = in_x0 + ch * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gy >= 0 && gy < h) {
+            if (WEIGHT && l == 0) {
+                float *e = reinterpret_cast<float *>(&v);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (c0 + k >= 0 && c0 + k < w) e[k] = lut_weight(g.lut, g.lut_len, gy, c0 + k, h, w);
+            } else {
+                v = load_f32_chunk(src + (size_t)gy * Ls.pitch, c0, w);
+            }
+        }
+        *reinterpret_cast<float4 *>(&s_in[r][ch * 4]) = v;
+    }
+    __syncthreads();
+
+    const bool x_interior = (ox0 > 0) && (2 * (ox0 + DN_BW) + 2 < w);
+    const int vec_end = Ld.vec_end;
+    for (int i = threadIdx.x; i < n_in_rows * DN_BW; i += kThreads) {
+        const int x = i % DN_BW, r = i / DN_BW;
+        const int gy = in_y0 + r;
+        const int ox = ox0 + x;
+        if (gy < 0 || gy >= h || ox >= ow) continue;
+        const float *row = &s_in[r][0];
+        float a0, a1, a2, a3, a4;
+        if (x_interior) {
+            const float2 p0 = *reinterpret_cast<const float2 *>(row + 2 * x + 2);
+            const float2 p1 = *reinterpret_cast<const float2 *>(row + 2 * x + 4);
+            a0 = p0.x; a1 = p0.y; a2 = p1.x; a3 = p1.y; a4 = row[2 * x + 6];
+        } else {
+            const int gx = 2 * ox;
+            a0 = row[srf_reflect101(gx - 2, w) - in_x0];
+            a1 = row[srf_reflect101(gx - 1, w) - in_x0];
+            a2 = row[srf_reflect101(gx, w) - in_x0];
+            a3 = row[srf_reflect101(gx + 1, w) - in_x0];
+            a4 = row[srf_reflect101(gx + 2, w) - in_x0];
+        }
+        const bool sca = (ox < 1) || (ox >= vec_end);
+        s_h[r][x] = sca ? dn_h_sca(a0, a1, a2, a3, a4) : dn_h_vec(a0, a1, a2, a3, a4);
+    }
+    __syncthreads();
+
+    const int n_out_rows = oy1 - oy0;
+    const int vtail = Ld.vtail;
+    for (int i = threadIdx.x; i < n_out_rows * DN_BW; i += kThreads) {
+        const int x = i % DN_BW, ry = i / DN_BW;
+        const int ox = ox0 + x;
+        if (ox >= ow) continue;
+        const int oy = oy0 + ry;
+        float rv[5];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) rv[k] = s_h[srf_reflect101(2 * oy + k - 2, h) - in_y0][x];
+        const bool sca = (ox * cn_ref + c) >= vtail;
+        dst[(size_t)oy * Ld.pitch + ox] = sca ? dn_v_sca(rv[0], rv[1], rv[2], rv[3], rv[4]) : dn_v_vec(rv[0], rv[1], rv[2], rv[3], rv[4]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// pyrUp building blocks shared by k_up_level and k_final.
+// A "source block" is rows [jb, jb + nrows) x cols [ib, ib + UP_SRC_COLS) of a level-(l+1) plane staged in smem.
+// ------------------------------------------------------------------------------------------------------------
+struct SrcWin {
+    int jb, nrows; // first staged source row, count
+    int ib;        // first staged source col (multiple of 4)
+};
+
+// rows/cols of level l+1 needed to up-sample output rows [ty0, ty1) x cols [tx0, tx1) of level l
+__device__ __forceinline__ SrcWin src_window(int ty0, int ty1, int tx0, int h1)
+{
+    SrcWin s;
+    const int jlo = max((ty0 >> 1) - 1, 0);
+    const int jhi = min(((ty1 - 1) >> 1) + 1, h1 - 1);
+    s.jb = jlo;
+    s.nrows = jhi - jlo + 1;
+    s.ib = (max((tx0 >> 1) - 1, 0)) & ~3;
+    return s;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// k_up_level: C_l = pyrUp(C_{l+1}) + (G_l - pyrUp(G_{l+1})) * W_l for 1 <= l <= n-2.
+// TOP: C_{l+1} is not stored; it is G_{l+1} * W_{l+1} (the coarsest Laplacian level is the Gaussian one).
+// grid = (ceil(w_l/64), ceil(rows/32), tile * C + c)
+// ------------------------------------------------------------------------------------------------------------
+template <bool TOP>
+__global__ void __launch_bounds__(kThreads) k_up_level(const TileDev *__restrict__ tiles, const int *__restrict__ tile_ids, GroupDev g, int l)
+{
+    __shared__ __align__(16) float s_c[UP_SRC_ROWS][UP_SRC_COLS];
+    __shared__ __align__(16) float s_g[UP_SRC_ROWS][UP_SRC_COLS];
+    __shared__ __align__(16) float s_hc[UP_SRC_ROWS][UP_BW];
+    __shared__ __align__(16) float s_hg[UP_SRC_ROWS][UP_BW];
+
+    const int z = blockIdx.z;
+    const TileDev &t = tiles[tile_ids[z / g.cn]];
+    const int c = z % g.cn;
+    const LevelGeom L0 = g.lv[l], L1 = g.lv[l + 1];
+    const int ty0 = t.c0[l] + blockIdx.y * UP_BH;
+    const int tx0 = blockIdx.x * UP_BW;
+    if (ty0 >= t.c1[l] || tx0 >= L0.w) return;
+    const int ty1 = min(ty0 + UP_BH, t.c1[l]);
+    const int tx1 = min(tx0 + UP_BW, L0.w);
+    const SrcWin sw = src_window(ty0, ty1, tx0, L1.h);
+    const float *G1 = t.G[l + 1] + (size_t)c * L1.plane;
+    const float *C1 = TOP ? nullptr : t.C[l + 1] + (size_t)c * L1.plane;
+    const float *W1 = TOP ? g.W[l + 1] : nullptr;
+
+    for (int i = threadIdx.x; i < sw.nrows * (UP_SRC_COLS / 4); i += kThreads) {
+        const int r = i / (UP_SRC_COLS / 4), ch = i - r * (UP_SRC_COLS / 4);
+        const int gy = sw.jb + r, c0 = sw.ib + ch * 4;
+        const float4 gv = load_f32_chunk(G1 + (size_t)gy * L1.pitch, c0, L1.w);
+        float4 cv;
+        if (TOP) {
+            const float4 wv = load_f32_chunk(W1 + (size_t)gy * L1.pitch, c0, L1.w);
+            cv = make_float4(__fmul_rn(gv.x, wv.x), __fmul_rn(gv.y, wv.y), __fmul_rn(gv.z, wv.z), __fmul_rn(gv.w, wv.w));
+        } else {
+            cv = load_f32_chunk(C1 + (size_t)gy * L1.pitch, c0, L1.w);
+        }
+        *reinterpret_cast<float4 *>(&s_g[r][ch * 4]) = gv;
+        *reinterpret_cast<float4 *>(&s_c[r][ch * 4]) = cv;
+    }
+    __syncthreads();
+
+    for (int i = threadIdx.x; i < sw.nrows * UP_BW; i += kThreads) {
+        const int x = i % UP_BW, r = i / UP_BW;
+        const int tx = tx0 + x;
+        if (tx >= tx1) continue;
+        const float *rc = &s_c[r][0] - sw.ib;
+        const float *rg = &s_g[r][0] - sw.ib;
+        s_hc[r][x] = up_h_sample(tx, L1.w, [&](int ii) { return rc[ii]; });
+        s_hg[r][x] = up_h_sample(tx, L1.w, [&](int ii) { return rg[ii]; });
+    }
+    __syncthreads();
+
+    const float *G0 = t.G[l] + (size_t)c * L0.plane;
+    const float *W0 = g.W[l];
+    float *C0 = t.C[l] + (size_t)c * L0.plane;
+    const int n_rows = ty1 - ty0;
+    for (int i = threadIdx.x; i < n_rows * (UP_BW / 4); i += kThreads) {
+        const int xg = i % (UP_BW / 4), ry = i / (UP_BW / 4);
+        const int tx = tx0 + xg * 4;
+        if (tx >= tx1) continue;
+        const int ty = ty0 + ry;
+        const int j = ty >> 1;
+        const int rj = j - sw.jb;
+        const int rm = srf_reflect101(j - 1, L1.h) - sw.jb;
+        const int rn = min(j + 1, L1.h - 1) - sw.jb;
+        const float4 pc = *reinterpret_cast<const float4 *>(&s_hc[rj][xg * 4]);
+        const float4 nc = *reinterpret_cast<const float4 *>(&s_hc[rn][xg * 4]);
+        const float4 pg = *reinterpret_cast<const float4 *>(&s_hg[rj][xg * 4]);
+        const float4 ng = *reinterpret_cast<const float4 *>(&s_hg[rn][xg * 4]);
+        float uc[4], ug[4];
+        if (ty & 1) {
+            uc[0] = up_odd(pc.x, nc.x); uc[1] = up_odd(pc.y, nc.y); uc[2] = up_odd(pc.z, nc.z); uc[3] = up_odd(pc.w, nc.w);
+            ug[0] = up_odd(pg.x, ng.x); ug[1] = up_odd(pg.y, ng.y); ug[2] = up_odd(pg.z, ng.z); ug[3] = up_odd(pg.w, ng.w);
+        } else {
+            const float4 mc = *reinterpret_cast<const float4 *>(&s_hc[rm][xg * 4]);
+            const float4 mg = *reinterpret_cast<const float4 *>(&s_hg[rm][xg * 4]);
+            uc[0] = up_even(mc.x, pc.x, nc.x); uc[1] = up_even(mc.y, pc.y, nc.y); uc[2] = up_even(mc.z, pc.z, nc.z); uc[3] = up_even(mc.w, pc.w, nc.w);
+            ug[0] = up_even(mg.x, pg.x, ng.x); ug[1] = up_even(mg.y, pg.y, ng.y); ug[2] = up_even(mg.z, pg.z, ng.z); ug[3] = up_even(mg.w, pg.w, ng.w);
+        }
+        const size_t off = (size_t)ty * L0.pitch + tx;
+        const float4 g0 = load_f32_chunk(G0 + (size_t)ty * L0.pitch, tx, L0.w);
+        const float4 w0 = load_f32_chunk(W0 + (size_t)ty * L0.pitch, tx, L0.w);
+        const float gg[4] = {g0.x, g0.y, g0.z, g0.w}, ww[4] = {w0.x, w0.y, w0.z, w0.w};
+        float o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float upc = __fmul_rn(uc[k], 1.f / 64.f), upg = __fmul_rn(ug[k], 1.f / 64.f);
+            o[k] = __fadd_rn(upc, __fmul_rn(__fsub_rn(gg[k], upg), ww[k]));
+        }
+        if (tx + 4 <= L0.w) {
+            *reinterpret_cast<float4 *>(C0 + off) = make_float4(o[0], o[1], o[2], o[3]);
+        } else {
+            for (int k = 0; k < 4 && tx + k < L0.w; ++k) C0[off + k] = o[k];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// k_final: one CTA per 32 x 64 canvas block.  Per covering tile (list order = the reference's accumulation order):
+// stage C_1/G_1 source windows and the uint8 tile block, horizontal pyrUp into smem, then each thread finishes
+// its 2 x 4 pixels x C channels in registers.  MODE: 0 = tiles have >= 3 levels (C_1 stored), 1 = exactly 2 levels
+// (C_1 = G_1 * W_1 on the fly), 2 = single level (C_0 = G_0 * W_0, no pyramid at all).
+// ------------------------------------------------------------------------------------------------------------
+constexpr int FN_U8_STRIDE = UP_BW * 3 + 32; // staged uint8 row: 192 payload bytes + 16 B misalignment + slack
+
+template <int C>
+struct FinalSmem {
+    float sc[C][UP_SRC_ROWS][UP_SRC_COLS];
+    float sg[C][UP_SRC_ROWS][UP_SRC_COLS];
+    float hc[C][UP_SRC_ROWS][UP_BW];
+    float hg[C][UP_SRC_ROWS][UP_BW];
+    uint8_t u8[UP_BH][FN_U8_STRIDE];
+};
+
+struct FinalParams {
+    const TileDev *tiles;
+    const GroupDev *groups;
+    const int *tile_group; // group index per tile
+    int n_tiles;
+    int out_h, out_w;
+    uint8_t *canvas;
+    size_t canvas_pitch;
+    int row_begin, row_end;
+};
+
+template <int C>
+__global__ void __launch_bounds__(kThreads) k_final(FinalParams P)
+{
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    FinalSmem<C> &S = *reinterpret_cast<FinalSmem<C> *>(smem_raw);
+
+    const int cy0 = P.row_begin + blockIdx.y * UP_BH;
+    const int cx0 = blockIdx.x * UP_BW;
+    const int cy1 = min(cy0 + UP_BH, P.row_end);
+    const int cx1 = min(cx0 + UP_BW, P.out_w);
+    const int cg = threadIdx.x & 15; // 4-pixel column group
+    const int rp = threadIdx.x >> 4; // row pair
+    float acc[2][4][C];
+    float wacc[2][4];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            wacc[a][b] = 0.f;
+#pragma unroll
+            for (int c = 0; c < C; ++c) acc[a][b][c] = 0.f;
+        }
+
+    for (int ti = 0; ti < P.n_tiles; ++ti) {
+        const TileDev &t = P.tiles[ti];
+        // intersection of this block with the tile, in canvas coordinates (uniform across the CTA)
+        const int iy0 = max(cy0, t.y), iy1 = min(cy1, t.y + t.h);
+        const int ix0 = max(cx0, t.x), ix1 = min(cx1, t.x + t.w);
+        if (iy0 >= iy1 || ix0 >= ix1) continue;
+        const GroupDev &g = P.groups[P.tile_group[ti]];
+        const int mode = (g.n_levels >= 3) ? 0 : (g.n_levels == 2 ? 1 : 2);
+        const int ty0 = iy0 - t.y, ty1 = iy1 - t.y, tx0 = ix0 - t.x, tx1 = ix1 - t.x;
+        const LevelGeom L1 = g.lv[1];
+        SrcWin sw;
+        sw.jb = 0; sw.nrows = 0; sw.ib = 0;
+        __syncthreads(); // previous tile's smem fully consumed
+
+        // ---- stage the uint8 tile block (congruent 16-byte chunks) ----
+        const int u8_bytes = (tx1 - tx0) * C;
+        for (int i = threadIdx.x; i < (iy1 - iy0) * (FN_U8_STRIDE / 16); i += kThreads) {
+            const int r = i / (FN_U8_STRIDE / 16), ch = i - r * (FN_U8_STRIDE / 16);
+            const uint8_t *grow = t.src + (size_t)(ty0 + r) * t.pitch;
+            const int first = tx0 * C;
+            const int a0 = first & ~15;
+            if (a0 + ch * 16 < first + u8_bytes) stage_u8_chunk(&S.u8[r][0], grow, a0, ch, t.w * C);
+        }
+        if (mode != 2) {
+            sw = src_window(ty0, ty1, tx0, L1.h);
+            for (int i = threadIdx.x; i < C * sw.nrows * (UP_SRC_COLS / 4); i += kThreads) {
+                const int ch = i % (UP_SRC_COLS / 4);
+                const int r = (i / (UP_SRC_COLS / 4)) % sw.nrows;
+                const int c = i / ((UP_SRC_COLS / 4) * sw.nrows);
+                const int gy = sw.jb + r, c0 = sw.ib + ch * 4;
+                const float4 gv = load_f32_chunk(t.G[1] + (size_t)c * L1.plane + (size_t)gy * L1.pitch, c0, L1.w);
+                float4 cv;
+                if (mode == 1) {
+                    const float4 wv = load_f32_chunk(g.W[1] + (size_t)gy * L1.pitch, c0, L1.w);
+                    cv = make_float4(__fmul_rn(gv.x, wv.x), __fmul_rn(gv.y, wv.y), __fmul_rn(gv.z, wv.z), __fmul_rn(gv.w, wv.w));
+                } else {
+                    cv = load_f32_chunk(t.C[1] + (size_t)c * L1.plane + (size_t)gy * L1.pitch, c0, L1.w);
+                }
+                *reinterpret_cast<float4 *>(&S.sg[c][r][ch * 4]) = gv;
+                *reinterpret_cast<float4 *>(&S.sc[c][r][ch * 4]) = cv;
+            }
+        }
+        __syncthreads();
+
+        // ---- horizontal pyrUp of the staged rows, for the columns this block covers ----
+        if (mode != 2) {
+            const int ncols = tx1 - tx0;
+            for (int i = threadIdx.x; i < C * sw.nrows * UP_BW; i += kThreads) {
+                const int x = i % UP_BW;
+                const int r = (i / UP_BW) % sw.nrows;
+                const int c = i / (UP_BW * sw.nrows);
+                if (x >= ncols) continue;
+                const int tx = tx0 + x;
+                const float *rc = &S.sc[c][r][0] - sw.ib;
+                const float *rg = &S.sg[c][r][0] - sw.ib;
+                S.hc[c][r][x] = up_h_sample(tx, L1.w, [&](int ii) { return rc[ii]; });
+                S.hg[c][r][x] = up_h_sample(tx, L1.w, [&](int ii) { return rg[ii]; });
+            }
+            __syncthreads();
+        }
+
+        // ---- vertical pyrUp + Laplacian weighting + accumulation, 2 x 4 pixels per thread ----
+        const int u8_off = (tx0 * C) & 15;
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+            const int cy = cy0 + rp * 2 + a;
+            if (cy < iy0 || cy >= iy1) continue;
+            const int ty = cy - t.y;
+            const int j = ty >> 1;
+            int rj = 0, rm = 0, rn = 0;
+            if (mode != 2) {
+                rj = j - sw.jb;
+                rm = srf_reflect101(j - 1, L1.h) - sw.jb;
+                rn = min(j + 1, L1.h - 1) - sw.jb;
+            }
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const int cx = cx0 + cg * 4 + b;
+                if (cx < ix0 || cx >= ix1) continue;
+                const int tx = cx - t.x;
+                const int x = tx - tx0; // column inside hc/hg and the u8 block
+                const float w0 = lut_weight(g.lut, g.lut_len, ty, tx, t.h, t.w);
+                const uint8_t *px = &S.u8[ty - ty0][u8_off + x * C];
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    const float g0 = (float)px[c];
+                    float c0v;
+                    if (mode == 2) {
+                        c0v = __fmul_rn(g0, w0);
+                    } else {
+                        float uc, ug;
+                        if (ty & 1) {
+                            uc = up_odd(S.hc[c][rj][x], S.hc[c][rn][x]);
+                            ug = up_odd(S.hg[c][rj][x], S.hg[c][rn][x]);
+                        } else {
+                            uc = up_even(S.hc[c][rm][x], S.hc[c][rj][x], S.hc[c][rn][x]);
+                            ug = up_even(S.hg[c][rm][x], S.hg[c][rj][x], S.hg[c][rn][x]);
+                        }
+                        const float upc = __fmul_rn(uc, 1.f / 64.f), upg = __fmul_rn(ug, 1.f / 64.f);
+                        c0v = __fadd_rn(upc, __fmul_rn(__fsub_rn(g0, upg), w0));
+                    }
+                    acc[a][b][c] = __fadd_rn(acc[a][b][c], c0v);
+                }
+                wacc[a][b] = __fadd_rn(wacc[a][b], w0);
+            }
+        }
+    }
+
+    // ---- normalise, clip, truncate; stage the block as bytes congruent (mod 16) with the canvas rows ----
+    __syncthreads();
+    const int row_bytes = (cx1 - cx0) * C;
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+        const int r = rp * 2 + a;
+        const int cy = cy0 + r;
+        if (cy >= cy1) continue;
+        const int mis = (int)((reinterpret_cast<uintptr_t>(P.canvas) + (size_t)cy * P.canvas_pitch + (size_t)cx0 * C) & 15);
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int x = cg * 4 + b;
+            if (cx0 + x >= cx1) continue;
+            const float wsum = fmaxf(wacc[a][b], 1e-6f);
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                float v = __fdiv_rn(acc[a][b][c], wsum);
+                v = fminf(fmaxf(v, 0.f), 255.f);
+                S.u8[r][mis + x * C + c] = (uint8_t)(int)v; // clip then truncate (blending_module.py:504-506)
+            }
+        }
+    }
+    __syncthreads();
+    const int n_rows = cy1 - cy0;
+    constexpr int kChunks = (UP_BW * 3 + 15 + 15) / 16; // chunks that can touch a row's payload
+    for (int i = threadIdx.x; i < n_rows * kChunks; i += kThreads) {
+        const int r = i / kChunks, ch = i - r * kChunks;
+        uint8_t *grow = P.canvas + (size_t)(cy0 + r) * P.canvas_pitch + (size_t)cx0 * C;
+        const int mis = (int)(reinterpret_cast<uintptr_t>(grow) & 15);
+        const int lo = ch * 16, hi = lo + 16; // byte range inside the staged row
+        const int p0 = mis, p1 = mis + row_bytes; // payload range
+        if (hi <= p0 || lo >= p1) continue;
+        uint8_t *gdst = grow - mis + lo; // 16-byte aligned
+        if (lo >= p0 && hi <= p1) {
+            *reinterpret_cast<uint4 *>(gdst) = *reinterpret_cast<const uint4 *>(&S.u8[r][lo]);
+        } else {
+            for (int e = max(lo, p0); e < min(hi, p1); ++e) gdst[e - lo] = S.u8[r][e];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------------
+struct HostGroup {
+    int h, w, lut;
+    std::vector<int> tiles;
+    GroupDev dev;
+};
+
+struct RowRange {
+    int a, b;
+    void merge(int lo, int hi)
+    {
+        if (lo >= hi) return;
+        if (a >= b) {
+            a = lo;
+            b = hi;
+        } else {
+            a = std::min(a, lo);
+            b = std::max(b, hi);
+        }
+    }
+};
+
+} // namespace
+
+static int fuse_device(srf_ctx *ctx, const srf_tile *tiles, int n_tiles, int C, int levels, const srf_weight_lut *luts, int n_luts,
+                       int out_h, int out_w, uint8_t *d_canvas, size_t canvas_pitch, int row_begin, int row_end, cudaStream_t st)
+{
+    // ---- group tiles by (h, w, lut) ----
+    std::vector<HostGroup> groups;
+    std::vector<int> tile_group(n_tiles);
+    for (int i = 0; i < n_tiles; ++i) {
+        int gi = -1;
+        for (size_t k = 0; k < groups.size(); ++k)
+            if (groups[k].h == tiles[i].h && groups[k].w == tiles[i].w && groups[k].lut == tiles[i].lut) gi = (int)k;
+        if (gi < 0) {
+            HostGroup hg;
+            hg.h = tiles[i].h;
+            hg.w = tiles[i].w;
+            hg.lut = tiles[i].lut;
+            memset(&hg.dev, 0, sizeof hg.dev);
+            groups.push_back(hg);
+            gi = (int)groups.size() - 1;
+        }
+        groups[gi].tiles.push_back(i);
+        tile_group[i] = gi;
+    }
+
+    // ---- geometry + workspace plan ----
+    size_t lut_floats = 0;
+    for (int k = 0; k < n_luts; ++k) lut_floats += srf_align_up((size_t)luts[k].len, 4);
+    std::vector<size_t> lut_off(n_luts);
+    {
+        size_t o = 0;
+        for (int k = 0; k < n_luts; ++k) {
+            lut_off[k] = o;
+            o += srf_align_up((size_t)luts[k].len, 4);
+        }
+    }
+    size_t pyr_floats = 0;
+    auto take = [&](size_t n) {
+        size_t o = pyr_floats;
+        pyr_floats += srf_align_up(n, 32);
+        return o;
+    };
+    std::vector<std::vector<size_t>> w_off(groups.size());
+    for (size_t k = 0; k < groups.size(); ++k) {
+        GroupDev &g = groups[k].dev;
+        g.cn = C;
+        g.lut_len = luts[groups[k].lut].len;
+        int h = groups[k].h, w = groups[k].w, n = 1;
+        g.lv[0] = LevelGeom{h, w, 0, 0, 0, 0};
+        while (n < levels && h >= 2 && w >= 2) {
+            const int oh = (h + 1) / 2, ow = (w + 1) / 2;
+            LevelGeom L;
+            L.h = oh;
+            L.w = ow;
+            L.pitch = (int)srf_align_up((size_t)ow, 4);
+            L.plane = srf_align_up((size_t)L.pitch * oh, 32);
+            L.vec_end = 0;
+            L.vtail = 0;
+            g.lv[n] = L;
+            h = oh;
+            w = ow;
+            ++n;
+        }
+        g.n_levels = n;
+        w_off[k].assign(SRF_MAX_LEVELS, 0);
+        for (int l = 1; l < n; ++l) w_off[k][l] = take(g.lv[l].plane);
+    }
+    std::vector<TileDev> tdev(n_tiles);
+    std::vector<std::vector<size_t>> g_off(n_tiles, std::vector<size_t>(SRF_MAX_LEVELS, 0)), c_off = g_off;
+    for (int i = 0; i < n_tiles; ++i) {
+        const GroupDev &g = groups[tile_group[i]].dev;
+        for (int l = 1; l < g.n_levels; ++l) g_off[i][l] = take(g.lv[l].plane * C);
+        for (int l = 1; l <= g.n_levels - 2; ++l) c_off[i][l] = take(g.lv[l].plane * C);
+    }
+    int rc;
+    if ((rc = srf_reserve(ctx, ctx->ws_pyr, pyr_floats * sizeof(float) + 256))) return rc;
+    const size_t desc_bytes = srf_align_up(sizeof(TileDev) * n_tiles, 256) + srf_align_up(sizeof(GroupDev) * groups.size(), 256) +
+                              srf_align_up(sizeof(int) * n_tiles * 2, 256);
+    if ((rc = srf_reserve(ctx, ctx->ws_desc, desc_bytes))) return rc;
+    if ((rc = srf_reserve(ctx, ctx->ws_misc, lut_floats * sizeof(float) + 256))) return rc;
+    float *pyr = (float *)ctx->ws_pyr.ptr;
+    float *d_lut = (float *)ctx->ws_misc.ptr;
+    for (int k = 0; k < n_luts; ++k)
+        SRF_CHECK_CUDA(ctx, cudaMemcpyAsync(d_lut + lut_off[k], luts[k].values, sizeof(float) * luts[k].len, cudaMemcpyHostToDevice, st));
+
+    // ---- row ranges per tile and level (band mode computes only what canvas rows [row_begin,row_end) need) ----
+    for (int i = 0; i < n_tiles; ++i) {
+        const GroupDev &g = groups[tile_group[i]].dev;
+        TileDev &t = tdev[i];
+        memset(&t, 0, sizeof t);
+        t.src = tiles[i].data;
+        t.pitch = tiles[i].pitch;
+        t.h = tiles[i].h;
+        t.w = tiles[i].w;
+        t.y = tiles[i].y;
+        t.x = tiles[i].x;
+        const int n = g.n_levels;
+        for (int l = 1; l < n; ++l) t.G[l] = pyr + g_off[i][l];
+        for (int l = 1; l <= n - 2; ++l) t.C[l] = pyr + c_off[i][l];
+        RowRange needC[SRF_MAX_LEVELS], needG[SRF_MAX_LEVELS];
+        for (int l = 0; l < SRF_MAX_LEVELS; ++l) needC[l] = needG[l] = RowRange{0, 0};
+        const bool x_overlap = std::max(0, t.x) < std::min(out_w, t.x + t.w);
+        const int a0 = std::max(row_begin, t.y) - t.y, b0 = std::min(std::min(row_end, out_h), t.y + t.h) - t.y;
+        if (x_overlap && a0 < b0) {
+            needC[0].merge(a0, b0);
+            for (int l = 1; l < n; ++l) {
+                const int h1 = g.lv[l].h;
+                const int lo = std::max((needC[l - 1].a >> 1) - 1, 0), hi = std::min(((needC[l - 1].b - 1) >> 1) + 2, h1);
+                needC[l].merge(lo, std::max(hi, std::min(2, h1))); // row 1 is the reflection of row -1
+                needG[l].merge(needC[l].a, needC[l].b);
+            }
+            for (int l = n - 1; l >= 2; --l) {
+                const int hs = g.lv[l - 1].h;
+                int lo = std::max(2 * needG[l].a - 2, 0), hi = std::min(2 * needG[l].b + 1, hs);
+                if (needG[l].a <= 0) hi = std::max(hi, std::min(3, hs));      // reflections of rows -1, -2
+                if (2 * needG[l].b + 1 > hs) lo = std::min(lo, std::max(hs - 3, 0)); // reflections past the bottom
+                needG[l - 1].merge(lo, hi);
+            }
+        }
+        for (int l = 1; l < n; ++l) {
+            t.g0[l] = needG[l].a;
+            t.g1[l] = needG[l].b;
+            t.c0[l] = needC[l].a;
+            t.c1[l] = needC[l].b;
+        }
+    }
+    for (size_t k = 0; k < groups.size(); ++k) {
+        GroupDev &g = groups[k].dev;
+        g.lut = d_lut + lut_off[groups[k].lut];
+        for (int l = 1; l < g.n_levels; ++l) {
+            g.W[l] = pyr + w_off[k][l];
+            g.lv[l].vec_end = 0; // set per launch below (depends on the reference's channel count)
+        }
+    }
+
+    // ---- upload descriptors ----
+    uint8_t *dbase = (uint8_t *)ctx->ws_desc.ptr;
+    TileDev *d_tiles = (TileDev *)dbase;
+    GroupDev *d_groups = (GroupDev *)(dbase + srf_align_up(sizeof(TileDev) * n_tiles, 256));
+    int *d_tile_group = (int *)((uint8_t *)d_groups + srf_align_up(sizeof(GroupDev) * groups.size(), 256));
+    int *d_tile_ids = d_tile_group + n_tiles;
+    std::vector<int> ids;
+    std::vector<int> ids_off(groups.size());
+    for (size_t k = 0; k < groups.size(); ++k) {
+        ids_off[k] = (int)ids.size();
+        ids.insert(ids.end(), groups[k].tiles.begin(), groups[k].tiles.end());
+    }
+    std::vector<GroupDev> gdev_img(groups.size());
+    for (size_t k = 0; k < groups.size(); ++k) {
+        gdev_img[k] = groups[k].dev;
+        for (int l = 1; l < gdev_img[k].n_levels; ++l) {
+            gdev_img[k].lv[l].vec_end = srf_down_vec_end(gdev_img[k].lv[l - 1].w, gdev_img[k].lv[l].w, C);
+            gdev_img[k].lv[l].vtail = 4 * ((gdev_img[k].lv[l].w * C) / 4);
+        }
+    }
+    SRF_CHECK_CUDA(ctx, cudaMemcpyAsync(d_tiles, tdev.data(), sizeof(TileDev) * n_tiles, cudaMemcpyHostToDevice, st));
+    SRF_CHECK_CUDA(ctx, cudaMemcpyAsync(d_groups, gdev_img.data(), sizeof(GroupDev) * groups.size(), cudaMemcpyHostToDevice, st));
+    SRF_CHECK_CUDA(ctx, cudaMemcpyAsync(d_tile_group, tile_group.data(), sizeof(int) * n_tiles, cudaMemcpyHostToDevice, st));
+    SRF_CHECK_CUDA(ctx, cudaMemcpyAsync(d_tile_ids, ids.data(), sizeof(int) * n_tiles, cudaMemcpyHostToDevice, st));
+
+    // ---- launches ----
+    for (size_t k = 0; k < groups.size(); ++k) {
+        const GroupDev &gi = gdev_img[k];
+        GroupDev gw = gi; // weight pyramid: the reference's array is single-channel
+        for (int l = 1; l < gw.n_levels; ++l) {
+            gw.lv[l].vec_end = srf_down_vec_end(gw.lv[l - 1].w, gw.lv[l].w, 1);
+            gw.lv[l].vtail = 4 * (gw.lv[l].w / 4);
+        }
+        const int n = gi.n_levels;
+        const int nt = (int)groups[k].tiles.size();
+        const int *ids_k = d_tile_ids + ids_off[k];
+        // rows to launch = max over the group's tiles
+        auto max_rows = [&](int l, bool cc) {
+            int m = 0;
+            for (int ti : groups[k].tiles) m = std::max(m, cc ? tdev[ti].c1[l] - tdev[ti].c0[l] : tdev[ti].g1[l] - tdev[ti].g0[l]);
+            return m;
+        };
+        // weight pyramid (full planes; tiny next to the image work, and shared by the whole group)
+        for (int l = 0; l + 1 < n; ++l) {
+            dim3 grid(srf_ceil_div(gw.lv[l + 1].w, DN_BW), srf_ceil_div(gw.lv[l + 1].h, DN_BH), 1);
+            k_down_f32<true><<<grid, kThreads, 0, st>>>(d_tiles, ids_k, gw, l);
+            ctx->launches++;
+        }
+        // image pyramids, down
+        if (n >= 2) {
+            const int rows = max_rows(1, false);
+            if (rows > 0) {
+                dim3 grid(srf_ceil_div(gi.lv[1].w, DN_BW), srf_ceil_div(rows, DN_BH), nt);
+                if (C == 3)
+                    k_down_u8<3><<<grid, kThreads, 0, st>>>(d_tiles, ids_k, gi);
+                else
+                    k_down_u8<1><<<grid, kThreads, 0, st>>>(d_tiles, ids_k, gi);
+                ctx->launches++;
+            }
+        }
+        for (int l = 1; l + 1 < n; ++l) {
+            const int rows = max_rows(l + 1, false);
+            if (rows <= 0) continue;
+            dim3 grid(srf_ceil_div(gi.lv[l + 1].w, DN_BW), srf_ceil_div(rows, DN_BH), nt * C);
+            k_down_f32<false><<<grid, kThreads, 0, st>>>(d_tiles, ids_k, gi, l);
+            ctx->launches++;
+        }
+        // up: l = n-2 .. 1
+        for (int l = n - 2; l >= 1; --l) {
+            const int rows = max_rows(l, true);
+            if (rows <= 0) continue;
+            dim3 grid(srf_ceil_div(gi.lv[l].w, UP_BW), srf_ceil_div(rows, UP_BH), nt * C);
+            if (l == n - 2)
+                k_up_level<true><<<grid, kThreads, 0, st>>>(d_tiles, ids_k, gi, l);
+            else
+                k_up_level<false><<<grid, kThreads, 0, st>>>(d_tiles, ids_k, gi, l);
+            ctx->launches++;
+        }
+    }
+    SRF_CHECK_CUDA(ctx, cudaGetLastError());
+
+    // ---- canvas gather ----
+    const int rb = std::max(row_begin, 0), re = std::min(row_end, out_h);
+    if (rb < re) {
+        FinalParams P;
+        P.tiles = d_tiles;
+        P.groups = d_groups;
+        P.tile_group = d_tile_group;
+        P.n_tiles = n_tiles;
+        P.out_h = out_h;
+        P.out_w = out_w;
+        P.canvas = d_canvas;
+        P.canvas_pitch = canvas_pitch;
+        P.row_begin = rb;
+        P.row_end = re;
+        dim3 grid(srf_ceil_div(out_w, UP_BW), srf_ceil_div(re - rb, UP_BH), 1);
+        if (C == 3) {
+            const size_t sm = sizeof(FinalSmem<3>);
+            SRF_CHECK_CUDA(ctx, cudaFuncSetAttribute(k_final<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            k_final<3><<<grid, kThreads, sm, st>>>(P);
+        } else {
+            const size_t sm = sizeof(FinalSmem<1>);
+            SRF_CHECK_CUDA(ctx, cudaFuncSetAttribute(k_final<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            k_final<1><<<grid, kThreads, sm, st>>>(P);
+        }
+        ctx->launches++;
+        SRF_CHECK_CUDA(ctx, cudaGetLastError());
+    }
+    return SRF_OK;
+}
+
+static int check_fuse_args(srf_ctx *ctx, const srf_tile *tiles, int n_tiles, int C, int levels, const srf_weight_lut *luts, int n_luts,
+                           int out_h, int out_w, const void *canvas, size_t canvas_pitch, int row_begin, int row_end)
+{
+    SRF_REQUIRE(ctx, tiles && n_tiles >= 1, "laplacian_fuse: no tiles");
+    SRF_REQUIRE(ctx, C == 1 || C == 3, "laplacian_fuse: channels must be 1 or 3 (got %d)", C);
+    SRF_REQUIRE(ctx, levels >= 1 && levels <= SRF_MAX_LEVELS, "laplacian_fuse: levels must be 1..%d (got %d)", SRF_MAX_LEVELS, levels);
+    SRF_REQUIRE(ctx, luts && n_luts >= 1, "laplacian_fuse: no weight profiles");
+    SRF_REQUIRE(ctx, out_h >= 1 && out_w >= 1 && canvas, "laplacian_fuse: empty canvas");
+    SRF_REQUIRE(ctx, canvas_pitch >= (size_t)out_w * C, "laplacian_fuse: canvas pitch < row bytes");
+    SRF_REQUIRE(ctx, row_begin >= 0 && row_begin <= row_end && row_end <= out_h, "laplacian_fuse: bad row band [%d,%d) of %d", row_begin,
+                row_end, out_h);
+    for (int k = 0; k < n_luts; ++k) SRF_REQUIRE(ctx, luts[k].values && luts[k].len >= 1, "laplacian_fuse: weight profile %d empty", k);
+    for (int i = 0; i < n_tiles; ++i) {
+        const srf_tile &t = tiles[i];
+        SRF_REQUIRE(ctx, t.data, "laplacian_fuse: tile %d has no data", i);
+        SRF_REQUIRE(ctx, t.h >= 1 && t.w >= 1, "laplacian_fuse: tile %d is empty (%dx%d)", i, t.h, t.w);
+        SRF_REQUIRE(ctx, t.pitch >= (size_t)t.w * C, "laplacian_fuse: tile %d pitch < row bytes", i);
+        SRF_REQUIRE(ctx, t.y >= 0 && t.x >= 0, "laplacian_fuse: tile %d has a negative position (%d,%d)", i, t.y, t.x);
+        SRF_REQUIRE(ctx, t.lut >= 0 && t.lut < n_luts, "laplacian_fuse: tile %d weight profile index %d out of range", i, t.lut);
+    }
+    return SRF_OK;
+}
+
+extern "C" int srf_laplacian_fuse(srf_ctx *ctx, const srf_tile *tiles, int n_tiles, int channels, int levels, const srf_weight_lut *luts,
+                                  int n_luts, int out_h, int out_w, uint8_t *d_canvas, size_t canvas_pitch, int row_begin, int row_end,
+                                  void *stream)
+{
+    if (!ctx) return SRF_ERR_ARG;
+    int rc = check_fuse_args(ctx, tiles, n_tiles, channels, levels, luts, n_luts, out_h, out_w, d_canvas, canvas_pitch, row_begin, row_end);
+    if (rc) return rc;
+    for (int i = 0; i < n_tiles; ++i)
+        SRF_REQUIRE(ctx, ((uintptr_t)tiles[i].data % 16 == 0) && (tiles[i].pitch % 16 == 0 || tiles[i].h == 1),
+                    "srf_laplacian_fuse: device tile %d must be 16-byte aligned with a 16-byte-multiple pitch "
+                    "(use srf_laplacian_fuse_host, or copy into an aligned buffer)", i);
+    SRF_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    SRF_CHECK_CUDA(ctx, cudaEventRecord(ctx->ev0, st));
+    rc = fuse_device(ctx, tiles, n_tiles, channels, levels, luts, n_luts, out_h, out_w, d_canvas, canvas_pitch, row_begin, row_end, st);
+    if (rc) return rc;
+    SRF_CHECK_CUDA(ctx, cudaEventRecord(ctx->ev1, st));
+    ctx->ev_valid = true;
+    return SRF_OK;
+}
+
+extern "C" int srf_laplacian_fuse_host(srf_ctx *ctx, const srf_tile *tiles, int n_tiles, int channels, int levels,
+                                       const srf_weight_lut *luts, int n_luts, int out_h, int out_w, uint8_t *h_canvas, size_t canvas_pitch,
+                                       int row_begin, int row_end)
+{
+    if (!ctx) return SRF_ERR_ARG;
+    int rc = check_fuse_args(ctx, tiles, n_tiles, channels, levels, luts, n_luts, out_h, out_w, h_canvas, canvas_pitch, row_begin, row_end);
+    if (rc) return rc;
+    SRF_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+    // device staging: every tile at a 256-byte aligned offset with a 16-byte-multiple pitch, then the canvas band
+    std::vector<srf_tile> dt(tiles, tiles + n_tiles);
+    std::vector<size_t> off(n_tiles);
+    size_t total = 0;
+    for (int i = 0; i < n_tiles; ++i) {
+        const size_t p = srf_align_up((size_t)tiles[i].w * channels, 16);
+        off[i] = total;
+        dt[i].pitch = p;
+        total += srf_align_up(p * tiles[i].h, 256);
+    }
+    const size_t cpitch = srf_align_up((size_t)out_w * channels, 256);
+    const int band = row_end - row_begin;
+    if ((rc = srf_reserve(ctx, ctx->ws_stage_in, total))) return rc;
+    if ((rc = srf_reserve(ctx, ctx->ws_stage_out, cpitch * (size_t)std::max(band, 1)))) return rc;
+    cudaStream_t st = ctx->own_stream;
+    uint8_t *din = (uint8_t *)ctx->ws_stage_in.ptr;
+    for (int i = 0; i < n_tiles; ++i) {
+        dt[i].data = din + off[i];
+        SRF_CHECK_CUDA(ctx, cudaMemcpy2DAsync(din + off[i], dt[i].pitch, tiles[i].data, tiles[i].pitch, (size_t)tiles[i].w * channels,
+                                              tiles[i].h, cudaMemcpyHostToDevice, st));
+    }
+    SRF_CHECK_CUDA(ctx, cudaEventRecord(ctx->ev0, st));
+    // the staged canvas holds only the band: shift the base so canvas row `row_begin` lands on staged row 0
+    uint8_t *dcanvas = (uint8_t *)ctx->ws_stage_out.ptr - (size_t)row_begin * cpitch;
+    rc = fuse_device(ctx, dt.data(), n_tiles, channels, levels, luts, n_luts, out_h, out_w, dcanvas, cpitch, row_begin, row_end, st);
+    if (rc) return rc;
+    SRF_CHECK_CUDA(ctx, cudaEventRecord(ctx->ev1, st));
+    ctx->ev_valid = true;
+    if (band > 0)
+        SRF_CHECK_CUDA(ctx, cudaMemcpy2DAsync(h_canvas + (size_t)row_begin * canvas_pitch, canvas_pitch, ctx->ws_stage_out.ptr, cpitch,
+                                              (size_t)out_w * channels, band, cudaMemcpyDeviceToHost, st));
+    SRF_CHECK_CUDA(ctx, cudaStreamSynchronize(st));
+    return SRF_OK;
+}

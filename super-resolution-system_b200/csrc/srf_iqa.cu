@@ -1,0 +1,381 @@
+// srf_iqa.cu -- full-reference PSNR + Gaussian SSIM in one pass over an image pair (replaces
+// QualityAssessmentModule.calculate_psnr / calculate_ssim(multiscale=True),
+// /root/reference/quality_assessment_module.py:277-320, 322-376; arithmetic of scikit-image's
+// peak_signal_noise_ratio / structural_similarity(gaussian_weights=True, sigma=1.5, use_sample_covariance=False)).
+//
+// Each CTA owns a 128-column strip x IQ_RB rows of the S map and streams DOWN the rows: per input row it
+//   * reads the RGB bytes of both images once (sum of squared differences and the running max are taken here),
+//   * converts to gray with cv2's 15-bit fixed point, keeps (gray - 128) as float in a double-buffered smem row,
+//   * runs the horizontal 11-tap pass for 4 signals {a, b, a^2 + b^2, a*b} (SSIM needs vx + vy, never each alone),
+//   * pushes the 4 results into an 11-deep register ring and runs the vertical 11-tap pass from registers.
+// 6 B/px of HBM traffic against ~120 FP32 instructions/px: FP32-issue bound, not HBM bound.
+// Per-CTA partials are reduced by a second single-CTA kernel in a fixed order, so results are deterministic.
+#include "srf_common.cuh"
+
+namespace {
+
+constexpr int IQ_THREADS = 128;
+constexpr int IQ_RB = 64;    // S-map rows per CTA
+constexpr int IQ_R = 5;      // filter radius
+constexpr int IQ_TAPS = 11;
+constexpr int IQ_SROW = IQ_THREADS + 2 * IQ_R + 2; // staged gray columns (+2 keeps rows 16-byte multiples)
+
+// exp(-k^2 / (2 * 1.5^2)) normalised, k = -5..5 (scipy.ndimage._gaussian_kernel1d(1.5, 0, 5))
+#define IQ_T0 1.028380084e-03f
+#define IQ_T1 7.598758135e-03f
+#define IQ_T2 3.600077213e-02f
+#define IQ_T3 1.093606895e-01f
+#define IQ_T4 2.130055377e-01f
+#define IQ_T5 2.660117249e-01f
+
+struct IqaPartial {
+    double ssim;
+    unsigned long long sq;
+    unsigned long long cnt;
+    int max_a, max_b;
+};
+
+struct IqaParams {
+    const uint8_t *a, *b;
+    size_t pitch_a, pitch_b;
+    int h, w;
+    int scale_a, scale_b;
+    float c1, c2;
+    int row_begin, row_end;
+    IqaPartial *partials;
+};
+
+template <int C>
+__device__ __forceinline__ void load_px(const uint8_t *row, int col, bool ok, int scale, int (&v)[C])
+{
+#pragma unroll
+    for (int c = 0; c < C; ++c) v[c] = 0;
+    if (ok) {
+        const uint8_t *p = row + (size_t)col * C;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            int t = p[c];
+            if (scale) t = (t * 255) & 0xFF; // (image * 255).astype(uint8), quality_assessment_module.py:192-193
+            v[c] = t;
+        }
+    }
+}
+
+template <int C>
+__device__ __forceinline__ int to_gray(const int (&v)[C])
+{
+    if (C == 1) return v[0];
+    return (v[0] * 9798 + v[C > 1 ? 1 : 0] * 19235 + v[C > 2 ? 2 : 0] * 3735 + 16384) >> 15; // cv2 COLOR_RGB2GRAY, uint8
+}
+
+__device__ __forceinline__ float tap11(const float (&x)[IQ_TAPS])
+{
+    float s = x[5] * IQ_T5;
+    s = fmaf(x[4] + x[6], IQ_T4, s);
+    s = fmaf(x[3] + x[7], IQ_T3, s);
+    s = fmaf(x[2] + x[8], IQ_T2, s);
+    s = fmaf(x[1] + x[9], IQ_T1, s);
+    s = fmaf(x[0] + x[10], IQ_T0, s);
+    return s;
+}
+
+template <int C>
+__global__ void __launch_bounds__(IQ_THREADS) k_psnr_ssim(IqaParams P)
+{
+    __shared__ float s_a[2][IQ_SROW];
+    __shared__ float s_b[2][IQ_SROW];
+    __shared__ double s_red[IQ_THREADS / 32];
+    __shared__ unsigned long long s_sq[IQ_THREADS / 32];
+    __shared__ unsigned long long s_cnt[IQ_THREADS / 32];
+    __shared__ int s_mx[2][IQ_THREADS / 32];
+
+    const int t = threadIdx.x;
+    const int cx0 = blockIdx.x * IQ_THREADS;
+    const int ry0 = P.row_begin + blockIdx.y * IQ_RB;
+    const int ry1 = min(ry0 + IQ_RB, P.row_end);
+    const int h = P.h, w = P.w;
+    const int col1 = cx0 - IQ_R + t;           // every thread's first pixel
+    const int col2 = cx0 + IQ_THREADS - IQ_R + t; // threads 0..9: the right halo
+    const bool has2 = t < 2 * IQ_R;
+    const bool own1 = col1 >= cx0 && col1 < w;  // owned = inside this CTA's strip (for the PSNR sum)
+    const bool own2 = has2 && col2 < cx0 + IQ_THREADS && col2 < w;
+
+    unsigned int sq = 0; // <= 64 rows * 2 px * 3 * 65025 < 2^32
+    int mxa = 0, mxb = 0;
+
+    auto fetch = [&](int r, int (&a1)[C], int (&b1)[C], int (&a2)[C], int (&b2)[C]) {
+        const bool rok = r >= 0 && r < h;
+        const uint8_t *ra = P.a + (size_t)(rok ? r : 0) * P.pitch_a;
+        const uint8_t *rb = P.b + (size_t)(rok ? r : 0) * P.pitch_b;
+        load_px<C>(ra, col1, rok && col1 >= 0 && col1 < w, P.scale_a, a1);
+        load_px<C>(rb, col1, rok && col1 >= 0 && col1 < w, P.scale_b, b1);
+        load_px<C>(ra, col2, rok && has2 && col2 < w, P.scale_a, a2);
+        load_px<C>(rb, col2, rok && has2 && col2 < w, P.scale_b, b2);
+    };
+    auto stash = [&](int r, int buf, const int (&a1)[C], const int (&b1)[C], const int (&a2)[C], const int (&b2)[C]) {
+        const bool rown = r >= ry0 && r < ry1;
+        if (rown) {
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                if (own1) {
+                    const int d = a1[c] - b1[c];
+                    sq += (unsigned)(d * d);
+                    mxa = max(mxa, a1[c]);
+                    mxb = max(mxb, b1[c]);
+                }
+                if (own2) {
+                    const int d = a2[c] - b2[c];
+                    sq += (unsigned)(d * d);
+                    mxa = max(mxa, a2[c]);
+                    mxb = max(mxb, b2[c]);
+                }
+            }
+        }
+        s_a[buf][t] = (float)(to_gray<C>(a1) - 128);
+        s_b[buf][t] = (float)(to_gray<C>(b1) - 128);
+        if (has2) {
+            s_a[buf][IQ_THREADS + t] = (float)(to_gray<C>(a2) - 128);
+            s_b[buf][IQ_THREADS + t] = (float)(to_gray<C>(b2) - 128);
+        }
+    };
+
+    float ring[4][IQ_TAPS];
+#pragma unroll
+    for (int s = 0; s < 4; ++s)
+#pragma unroll
+        for (int k = 0; k < IQ_TAPS; ++k) ring[s][k] = 0.f;
+
+    float ssum = 0.f;
+    unsigned int scount = 0;
+    const int col = cx0 + t; // this thread's S-map column
+    const bool col_interior = col >= IQ_R && col < w - IQ_R;
+
+    const int r_first = ry0 - IQ_R, r_last = ry1 + IQ_R; // input rows [r_first, r_last)
+    {
+        int a1[C], b1[C], a2[C], b2[C];
+        fetch(r_first, a1, b1, a2, b2);
+        stash(r_first, 0, a1, b1, a2, b2);
+    }
+    __syncthreads();
+
+    int buf = 0;
+    for (int base = r_first; base < r_last; base += IQ_TAPS) {
+#pragma unroll
+        for (int ph = 0; ph < IQ_TAPS; ++ph) {
+            const int r_in = base + ph;
+            if (r_in >= r_last) break;
+            int a1[C], b1[C], a2[C], b2[C];
+            const bool more = r_in + 1 < r_last;
+            if (more) fetch(r_in + 1, a1, b1, a2, b2);
+
+            // horizontal pass on row r_in
+            float xa[IQ_TAPS], xb[IQ_TAPS], xs[IQ_TAPS], xp[IQ_TAPS];
+#pragma unroll
+            for (int k = 0; k < IQ_TAPS; ++k) {
+                xa[k] = s_a[buf][t + k];
+                xb[k] = s_b[buf][t + k];
+                xs[k] = fmaf(xa[k], xa[k], xb[k] * xb[k]);
+                xp[k] = xa[k] * xb[k];
+            }
+            ring[0][ph] = tap11(xa);
+            ring[1][ph] = tap11(xb);
+            ring[2][ph] = tap11(xs);
+            ring[3][ph] = tap11(xp);
+
+            // vertical pass: output row r = r_in - 5 uses input rows r_in-10 .. r_in = ring slots (ph+1+k) % 11
+            const int r = r_in - IQ_R;
+            if (r >= ry0) {
+                float f[4];
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {
+                    float v[IQ_TAPS];
+#pragma unroll
+                    for (int k = 0; k < IQ_TAPS; ++k) v[k] = ring[s][(ph + 1 + k) % IQ_TAPS];
+                    f[s] = tap11(v);
+                }
+                const float ua = f[0], ub = f[1];
+                const float ux = ua + 128.f, uy = ub + 128.f;
+                const float vsum = f[2] - fmaf(ua, ua, ub * ub); // vx + vy (shift invariant)
+                const float vxy = f[3] - ua * ub;
+                const float C1 = P.c1, C2 = P.c2;
+                const float A1 = fmaf(2.f * ux, uy, C1), A2 = fmaf(2.f, vxy, C2);
+                const float B1 = fmaf(ux, ux, fmaf(uy, uy, C1)), B2 = vsum + C2;
+                const float S = __fdividef(A1 * A2, B1 * B2);
+                if (col_interior && r >= IQ_R && r < h - IQ_R) {
+                    ssum += S;
+                    scount++;
+                }
+            }
+            if (more) stash(r_in + 1, buf ^ 1, a1, b1, a2, b2);
+            __syncthreads();
+            buf ^= 1;
+        }
+    }
+
+    // ---- block reduction (fixed order) ----
+    double ds = (double)ssum;
+    unsigned long long dsq = sq, dcnt = scount;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        ds += __shfl_down_sync(0xffffffffu, ds, o);
+        dsq += __shfl_down_sync(0xffffffffu, dsq, o);
+        dcnt += __shfl_down_sync(0xffffffffu, dcnt, o);
+        mxa = max(mxa, __shfl_down_sync(0xffffffffu, mxa, o));
+        mxb = max(mxb, __shfl_down_sync(0xffffffffu, mxb, o));
+    }
+    if ((t & 31) == 0) {
+        s_red[t >> 5] = ds;
+        s_sq[t >> 5] = dsq;
+        s_cnt[t >> 5] = dcnt;
+        s_mx[0][t >> 5] = mxa;
+        s_mx[1][t >> 5] = mxb;
+    }
+    __syncthreads();
+    if (t == 0) {
+        IqaPartial p;
+        p.ssim = 0;
+        p.sq = 0;
+        p.cnt = 0;
+        p.max_a = 0;
+        p.max_b = 0;
+        for (int k = 0; k < IQ_THREADS / 32; ++k) {
+            p.ssim += s_red[k];
+            p.sq += s_sq[k];
+            p.cnt += s_cnt[k];
+            p.max_a = max(p.max_a, s_mx[0][k]);
+            p.max_b = max(p.max_b, s_mx[1][k]);
+        }
+        P.partials[blockIdx.y * gridDim.x + blockIdx.x] = p;
+    }
+}
+
+// single CTA, fixed summation order: thread k sums partials k, k+256, ... then a shared-memory tree
+__global__ void __launch_bounds__(256) k_iqa_reduce(const IqaPartial *__restrict__ parts, int n, IqaPartial *__restrict__ out)
+{
+    __shared__ IqaPartial s[256];
+    IqaPartial p;
+    p.ssim = 0;
+    p.sq = 0;
+    p.cnt = 0;
+    p.max_a = 0;
+    p.max_b = 0;
+    for (int i = threadIdx.x; i < n; i += 256) {
+        const IqaPartial q = parts[i];
+        p.ssim += q.ssim;
+        p.sq += q.sq;
+        p.cnt += q.cnt;
+        p.max_a = max(p.max_a, q.max_a);
+        p.max_b = max(p.max_b, q.max_b);
+    }
+    s[threadIdx.x] = p;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) {
+            IqaPartial &x = s[threadIdx.x];
+            const IqaPartial &y = s[threadIdx.x + o];
+            x.ssim += y.ssim;
+            x.sq += y.sq;
+            x.cnt += y.cnt;
+            x.max_a = max(x.max_a, y.max_a);
+            x.max_b = max(x.max_b, y.max_b);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *out = s[0];
+}
+
+} // namespace
+
+static int iqa_device(srf_ctx *ctx, const uint8_t *a, size_t pa, const uint8_t *b, size_t pb, int h, int w, int C, int scale_a, int scale_b,
+                      double data_range, int row_begin, int row_end, srf_iqa_sums *out, cudaStream_t st, bool record_events)
+{
+    int rc;
+    const int gx = srf_ceil_div(w, IQ_THREADS), gy = srf_ceil_div(row_end - row_begin, IQ_RB);
+    const size_t nparts = (size_t)gx * gy;
+    if ((rc = srf_reserve(ctx, ctx->ws_iqa, (nparts + 1) * sizeof(IqaPartial)))) return rc;
+    if ((rc = srf_reserve_pinned(ctx, 4096))) return rc;
+    IqaPartial *parts = (IqaPartial *)ctx->ws_iqa.ptr;
+    IqaPartial *final_d = parts + nparts;
+    IqaParams P;
+    P.a = a;
+    P.b = b;
+    P.pitch_a = pa;
+    P.pitch_b = pb;
+    P.h = h;
+    P.w = w;
+    P.scale_a = scale_a;
+    P.scale_b = scale_b;
+    P.c1 = (float)((0.01 * data_range) * (0.01 * data_range));
+    P.c2 = (float)((0.03 * data_range) * (0.03 * data_range));
+    P.row_begin = row_begin;
+    P.row_end = row_end;
+    P.partials = parts;
+    if (record_events) SRF_CHECK_CUDA(ctx, cudaEventRecord(ctx->ev0, st));
+    if (nparts > 0) {
+        dim3 grid(gx, gy);
+        if (C == 3)
+            k_psnr_ssim<3><<<grid, IQ_THREADS, 0, st>>>(P);
+        else
+            k_psnr_ssim<1><<<grid, IQ_THREADS, 0, st>>>(P);
+        ctx->launches++;
+    }
+    k_iqa_reduce<<<1, 256, 0, st>>>(parts, (int)nparts, final_d);
+    ctx->launches++;
+    SRF_CHECK_CUDA(ctx, cudaGetLastError());
+    if (record_events) {
+        SRF_CHECK_CUDA(ctx, cudaEventRecord(ctx->ev1, st));
+        ctx->ev_valid = true;
+    }
+    SRF_CHECK_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, final_d, sizeof(IqaPartial), cudaMemcpyDeviceToHost, st));
+    SRF_CHECK_CUDA(ctx, cudaStreamSynchronize(st));
+    const IqaPartial *f = (const IqaPartial *)ctx->pinned;
+    out->sq_err = (int64_t)f->sq;
+    out->n_elems = (int64_t)(row_end - row_begin) * w * C;
+    out->ssim_sum = f->ssim;
+    out->ssim_count = (int64_t)f->cnt;
+    out->max_a = f->max_a;
+    out->max_b = f->max_b;
+    return SRF_OK;
+}
+
+static int check_iqa_args(srf_ctx *ctx, const void *a, size_t pa, const void *b, size_t pb, int h, int w, int C, int row_begin, int row_end,
+                          const void *out)
+{
+    SRF_REQUIRE(ctx, a && b && out, "psnr_ssim: null pointer");
+    SRF_REQUIRE(ctx, C == 1 || C == 3, "psnr_ssim: channels must be 1 or 3 (got %d)", C);
+    SRF_REQUIRE(ctx, h >= 1 && w >= 1, "psnr_ssim: empty image");
+    SRF_REQUIRE(ctx, pa >= (size_t)w * C && pb >= (size_t)w * C, "psnr_ssim: pitch < row bytes");
+    SRF_REQUIRE(ctx, row_begin >= 0 && row_begin <= row_end && row_end <= h, "psnr_ssim: bad row band [%d,%d) of %d", row_begin, row_end, h);
+    return SRF_OK;
+}
+
+extern "C" int srf_psnr_ssim(srf_ctx *ctx, const uint8_t *d_a, size_t pitch_a, const uint8_t *d_b, size_t pitch_b, int h, int w,
+                             int channels, int scale_a, int scale_b, double data_range, int row_begin, int row_end, srf_iqa_sums *h_out, void *stream)
+{
+    if (!ctx) return SRF_ERR_ARG;
+    int rc = check_iqa_args(ctx, d_a, pitch_a, d_b, pitch_b, h, w, channels, row_begin, row_end, h_out);
+    if (rc) return rc;
+    SRF_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+    return iqa_device(ctx, d_a, pitch_a, d_b, pitch_b, h, w, channels, scale_a, scale_b, data_range, row_begin, row_end, h_out, (cudaStream_t)stream, true);
+}
+
+extern "C" int srf_psnr_ssim_host(srf_ctx *ctx, const uint8_t *h_a, size_t pitch_a, const uint8_t *h_b, size_t pitch_b, int h, int w,
+                                  int channels, int scale_a, int scale_b, double data_range, int row_begin, int row_end, srf_iqa_sums *h_out)
+{
+    if (!ctx) return SRF_ERR_ARG;
+    int rc = check_iqa_args(ctx, h_a, pitch_a, h_b, pitch_b, h, w, channels, row_begin, row_end, h_out);
+    if (rc) return rc;
+    SRF_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+    // stage only the rows the band reads: [row_begin - 5, row_end + 5) clipped
+    const int r0 = row_begin - IQ_R < 0 ? 0 : row_begin - IQ_R, r1 = row_end + IQ_R > h ? h : row_end + IQ_R;
+    const size_t dp = srf_align_up((size_t)w * channels, 256);
+    const size_t one = dp * (size_t)(r1 - r0 > 0 ? r1 - r0 : 1);
+    if ((rc = srf_reserve(ctx, ctx->ws_stage_in, 2 * one))) return rc;
+    cudaStream_t st = ctx->own_stream;
+    uint8_t *da = (uint8_t *)ctx->ws_stage_in.ptr, *db = da + one;
+    if (r1 > r0) {
+        SRF_CHECK_CUDA(ctx, cudaMemcpy2DAsync(da, dp, h_a + (size_t)r0 * pitch_a, pitch_a, (size_t)w * channels, r1 - r0, cudaMemcpyHostToDevice, st));
+        SRF_CHECK_CUDA(ctx, cudaMemcpy2DAsync(db, dp, h_b + (size_t)r0 * pitch_b, pitch_b, (size_t)w * channels, r1 - r0, cudaMemcpyHostToDevice, st));
+    }
+    return iqa_device(ctx, da - (size_t)r0 * dp, dp, db - (size_t)r0 * dp, dp, h, w, channels, scale_a, scale_b, data_range, row_begin, row_end, h_out, st, true);
+}

@@ -1,0 +1,183 @@
+"""GPU mirror of the reference's full-reference metrics: PSNR and 11x11-Gaussian SSIM in one pass.
+
+Mirrors /root/reference/quality_assessment_module.py: AssessmentLevel 35-41, QualityThresholds 44-75,
+ScaleConfig 78-86, QualityAssessmentModule.__init__ 107-133, _preprocess_image 169-195, calculate_psnr 277-320,
+calculate_ssim 322-389, evaluate_full_reference 467-516, _assess_* 557-588, _calculate_overall_score 590-609,
+batch_evaluate 1350-1371.  The arithmetic (scikit-image's peak_signal_noise_ratio / structural_similarity) runs in
+csrc/srf_iqa.cu.  Out of scope: LPIPS, NIQE, BRISQUE, commercial metrics, reports; the
+7x7 uniform-window SSIM and the bicubic down-sample comparison are the "next" row N1 and raise until built.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from enum import Enum
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+
+from . import _native
+from ._arrays import ImageView, current_stream_ptr, is_cuda_tensor, torch
+
+
+class AssessmentLevel(Enum):
+    EXCELLENT = "excellent"
+    GOOD = "good"
+    FAIR = "fair"
+    POOR = "poor"
+    BAD = "bad"
+
+
+@dataclass
+class QualityThresholds:
+    PSNR_EXCELLENT: float = 40.0
+    PSNR_GOOD: float = 35.0
+    PSNR_FAIR: float = 30.0
+    SSIM_EXCELLENT: float = 0.98
+    SSIM_GOOD: float = 0.95
+    SSIM_FAIR: float = 0.90
+    LPIPS_EXCELLENT: float = 0.02
+    LPIPS_GOOD: float = 0.05
+    LPIPS_FAIR: float = 0.10
+
+
+@dataclass
+class ScaleConfig:
+    scale_factors: List[float] = field(default_factory=lambda: [0.1, 0.2, 0.4])
+    scale_names: Dict[float, str] = field(default_factory=lambda: {0.1: "structure_color", 0.2: "mid_frequency",
+                                                                   0.4: "high_frequency"})
+
+
+class QualityAssessmentModule:
+    def __init__(self, device: str = "cpu", thresholds: Optional[QualityThresholds] = None,
+                 scale_config: Optional[ScaleConfig] = None):
+        # the reference's `device` picks where LPIPS runs; PSNR/SSIM here always run on a B200.  'cuda:N' selects N.
+        self.device = device
+        self.device_index = int(device.split(":")[1]) if isinstance(device, str) and ":" in device else 0
+        self.thresholds = thresholds or QualityThresholds()
+        self.scale_config = scale_config or ScaleConfig()
+        self.lpips_model_vgg = None  # LPIPS is out of scope; evaluate_full_reference omits its keys exactly as the
+        self.lpips_model_alex = None  # reference does when the models fail to load (q.a.m:508-511)
+
+    # ------------------------------------------------------------------ preprocessing
+    def _preprocess_image(self, image, to_tensor: bool = False):
+        """tensor (C,H,W)/(1,C,H,W) -> HWC; float images in [0, 1] -> uint8 by *255 and truncation.  uint8 images are
+        returned untouched: their `max() <= 1` case is resolved inside the kernel pass (srf_iqa_sums.max_a/max_b)."""
+        if is_cuda_tensor(image) and image.dtype == torch.uint8:
+            return image
+        if torch is not None and isinstance(image, torch.Tensor):
+            if image.dim() == 4:
+                image = image.squeeze(0)
+            if image.dim() == 3:
+                image = image.permute(1, 2, 0)
+            image = image.cpu().numpy()
+        image = np.asarray(image)
+        if image.dtype != np.uint8:
+            if image.max() <= 1.0:
+                image = (image * 255).astype(np.uint8)
+            else:
+                raise TypeError("calculate_psnr/calculate_ssim: images must be uint8 or float in [0, 1]")
+        return image
+
+    @staticmethod
+    def _crop_common(a, b):
+        if tuple(a.shape) != tuple(b.shape):
+            h, w = min(a.shape[0], b.shape[0]), min(a.shape[1], b.shape[1])
+            a, b = a[:h, :w], b[:h, :w]
+        return a, b
+
+    # ------------------------------------------------------------------ the one-pass kernel
+    def psnr_ssim_sums(self, img1, img2, data_range: float = 255.0, row_range: Optional[Tuple[int, int]] = None):
+        """additive partial sums (srf_iqa_sums) of the pair over a row band -- what ranks all-reduce"""
+        a, b = self._crop_common(self._preprocess_image(img1), self._preprocess_image(img2))
+        if len(a.shape) != len(b.shape) or (len(a.shape) == 3 and a.shape[2] != b.shape[2]):
+            raise ValueError("image pair disagrees on channels")
+        va, vb = ImageView(a, "img1"), ImageView(b, "img2")
+        if va.on_device != vb.on_device:
+            raise ValueError("image pair must be both host or both device")
+        h, w = va.h, va.w
+        r0, r1 = (0, h) if row_range is None else (int(row_range[0]), int(row_range[1]))
+        lib, ctx = _native.load(), _native.context(va.device if va.on_device else self.device_index)
+        sums = _native.srf_iqa_sums()
+
+        def run(sa, sb):
+            if va.on_device:
+                rc = lib.srf_psnr_ssim(ctx, va.ptr, va.pitch, vb.ptr, vb.pitch, h, w, va.c, sa, sb, float(data_range),
+                                       r0, r1, C.byref(sums), current_stream_ptr(va.device))
+            else:
+                rc = lib.srf_psnr_ssim_host(ctx, va.ptr, va.pitch, vb.ptr, vb.pitch, h, w, va.c, sa, sb,
+                                            float(data_range), r0, r1, C.byref(sums))
+            _native.check(rc, ctx)
+
+        run(0, 0)
+        if row_range is None and (sums.max_a <= 1 or sums.max_b <= 1):
+            # the reference rescales an image whose max() <= 1.0 by 255 (q.a.m:192-193) -- also an all-0/1 uint8 one
+            run(int(sums.max_a <= 1), int(sums.max_b <= 1))
+        return sums
+
+    @staticmethod
+    def finish(sums, data_range: float = 255.0) -> Tuple[float, float]:
+        p, s = C.c_double(), C.c_double()
+        _native.check(_native.load().srf_iqa_finish(C.byref(sums), float(data_range), C.byref(p), C.byref(s)))
+        return p.value, s.value
+
+    # ------------------------------------------------------------------ reference API
+    def calculate_psnr(self, img1, img2, data_range: float = 255.0) -> float:
+        return float(self.finish(self.psnr_ssim_sums(img1, img2, data_range), data_range)[0])
+
+    def calculate_ssim(self, img1, img2, multiscale: bool = True, data_range: float = 255.0) -> float:
+        if not multiscale:
+            raise NotImplementedError("7x7 uniform-window SSIM (multiscale=False) is row N1 of SURVEY.md section 8(f); "
+                                      "the B200 path provides the 11x11 Gaussian SSIM (multiscale=True)")
+        sums = self.psnr_ssim_sums(img1, img2, data_range)
+        if sums.ssim_count <= 0:
+            raise ValueError("image smaller than the 11x11 SSIM window")
+        return float(self.finish(sums, data_range)[1])
+
+    def calculate_psnr_ssim(self, img1, img2, data_range: float = 255.0) -> Tuple[float, float]:
+        """both metrics from ONE pass over the pair (extension; the reference makes two)"""
+        sums = self.psnr_ssim_sums(img1, img2, data_range)
+        if sums.ssim_count <= 0:
+            raise ValueError("image smaller than the 11x11 SSIM window")
+        return self.finish(sums, data_range)
+
+    def _level(self, value, exc, good, fair) -> str:
+        if value >= exc:
+            return AssessmentLevel.EXCELLENT.value
+        if value >= good:
+            return AssessmentLevel.GOOD.value
+        if value >= fair:
+            return AssessmentLevel.FAIR.value
+        return AssessmentLevel.POOR.value
+
+    def _assess_psnr(self, v: float) -> str:
+        t = self.thresholds
+        return self._level(v, t.PSNR_EXCELLENT, t.PSNR_GOOD, t.PSNR_FAIR)
+
+    def _assess_ssim(self, v: float) -> str:
+        t = self.thresholds
+        return self._level(v, t.SSIM_EXCELLENT, t.SSIM_GOOD, t.SSIM_FAIR)
+
+    def _calculate_overall_score(self, metrics: Dict[str, float]) -> float:
+        scores = []
+        if "psnr" in metrics:
+            scores.append(min(100, max(0, metrics["psnr"])))
+        if "ms_ssim" in metrics:
+            scores.append(metrics["ms_ssim"] * 100)
+        if "lpips_vgg" in metrics:
+            scores.append(max(0, (1 - metrics["lpips_vgg"]) * 100))
+        return float(np.mean(scores)) if scores else 0.0
+
+    def evaluate_full_reference(self, original, upscaled, scale_factor: int = 4) -> Dict[str, float]:
+        """psnr, psnr_level, ms_ssim (= single-scale 11x11 Gaussian SSIM, the reference's naming), ssim_level,
+        overall_score.  The reference's 'ssim' (7x7 uniform) and six down-sample keys are row N1, not produced yet;
+        LPIPS keys are omitted as in the reference when its models are unavailable."""
+        psnr, ssim = self.calculate_psnr_ssim(original, upscaled)
+        metrics = {"psnr": float(psnr), "ms_ssim": float(ssim)}
+        metrics["psnr_level"] = self._assess_psnr(metrics["psnr"])
+        metrics["ssim_level"] = self._assess_ssim(metrics["ms_ssim"])
+        metrics["overall_score"] = self._calculate_overall_score(metrics)
+        return metrics
+
+    def batch_evaluate(self, image_pairs, scale_factor: int = 4) -> List[Dict[str, float]]:
+        return [self.evaluate_full_reference(o, u, scale_factor) for o, u in image_pairs]

@@ -1,0 +1,253 @@
+"""GPU mirror of the reference's tiler: overlap grid, crop, bottom/right padding to block_size.
+
+Mirrors /root/reference/tiling_module.py: PaddingMode 40-45, TileStatus 48-54, TileMetadata 64-125, Tile 128-171,
+TilingModule.__init__ 446-504, _apply_padding 522-570, _calculate_tile_positions 572-608,
+_calculate_overlap_for_tile 610-646, split_image 671-784, neighbour bookkeeping 786-850.
+Grid and overlap arithmetic run in libsrfuse's exact host functions; the crop + pad gather runs on the GPU
+(csrc/srf_api.cu: k_tile_extract_pad).  Out of scope: content analysis (Haar / MSER /
+saliency), the L1/L2/L3 caches, JSON checkpoints and streaming -- metadata decoration and host bookkeeping.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import hashlib
+import logging
+import threading
+import time
+import uuid
+from dataclasses import asdict, dataclass, field
+from enum import Enum, auto
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+
+from . import _native
+from ._arrays import ImageView, current_stream_ptr, torch
+
+logger = logging.getLogger(__name__)
+
+
+class PaddingMode(Enum):
+    MIRROR = "mirror"        # cv2.BORDER_REFLECT_101
+    REPLICATE = "replicate"  # cv2.BORDER_REPLICATE
+    REFLECT = "reflect"      # cv2.BORDER_REFLECT
+    CONSTANT = "constant"    # zeros
+
+
+_BORDER_CODE = {PaddingMode.MIRROR: 0, PaddingMode.REPLICATE: 1, PaddingMode.REFLECT: 2, PaddingMode.CONSTANT: 3}
+
+
+class TileStatus(Enum):
+    PENDING = auto()
+    PROCESSING = auto()
+    COMPLETED = auto()
+    FAILED = auto()
+    CACHED = auto()
+
+
+class CacheLevel(Enum):
+    L1_MEMORY = "L1"
+    L2_DISK = "L2"
+    L3_CLOUD = "L3"
+
+
+@dataclass
+class TileMetadata:
+    block_id: str = field(default_factory=lambda: str(uuid.uuid4()))
+    global_x: int = 0
+    global_y: int = 0
+    input_w: int = 2048
+    input_h: int = 2048
+    output_w: int = 4096
+    output_h: int = 4096
+    overlap_top: int = 0
+    overlap_bottom: int = 0
+    overlap_left: int = 0
+    overlap_right: int = 0
+    roi_flags: Dict[str, bool] = field(default_factory=dict)
+    status: TileStatus = TileStatus.PENDING
+    neighbor_ids: Dict[str, Optional[str]] = field(
+        default_factory=lambda: {"top": None, "bottom": None, "left": None, "right": None})
+    image_hash: str = ""
+    complexity_score: float = 0.0
+    priority: int = 0
+    created_at: float = field(default_factory=time.time)
+    updated_at: float = field(default_factory=time.time)
+
+    def to_dict(self) -> Dict:
+        d = asdict(self)
+        d["status"] = self.status.name
+        return d
+
+    @classmethod
+    def from_dict(cls, data: Dict) -> "TileMetadata":
+        d = dict(data)
+        d["status"] = TileStatus[d["status"]]
+        return cls(**d)
+
+
+@dataclass
+class Tile:
+    metadata: TileMetadata
+    data: Optional[np.ndarray] = None
+    mask: Optional[np.ndarray] = None
+    cache_path: Optional[str] = None
+
+    def get_overlap_region(self) -> Tuple[int, int, int, int]:
+        m = self.metadata
+        return (m.overlap_top, m.overlap_bottom, m.overlap_left, m.overlap_right)
+
+    def get_effective_region(self) -> Tuple[int, int, int, int]:
+        m = self.metadata
+        x1, y1 = m.global_x + m.overlap_left, m.global_y + m.overlap_top
+        return (x1, y1, x1 + m.input_w - m.overlap_left - m.overlap_right,
+                y1 + m.input_h - m.overlap_top - m.overlap_bottom)
+
+
+def _read_rgb(path: str) -> np.ndarray:
+    """decode to HWC uint8 RGB (I/O, not part of the hot path); unreadable -> ValueError like the reference"""
+    img = None
+    try:
+        import cv2
+        bgr = cv2.imread(path)
+        if bgr is not None:
+            img = np.ascontiguousarray(bgr[:, :, ::-1])
+    except ImportError:
+        from PIL import Image
+        try:
+            img = np.asarray(Image.open(path).convert("RGB"))
+        except Exception:
+            img = None
+    if img is None:
+        raise ValueError(f"cannot load image: {path}")
+    return img
+
+
+class TilingModule:
+    def __init__(self, block_size: int = 2048, overlap_ratio: float = 0.2, padding_mode: str = "mirror",
+                 output_scale: float = 2.0, l1_cache_size: int = 50, l2_cache_dir: Optional[str] = None,
+                 enable_content_aware: bool = True, device: int = 0):
+        if not (0.1 <= overlap_ratio <= 0.3):
+            raise ValueError(f"overlap_ratio must be within 0.1-0.3, got {overlap_ratio}")
+        self.block_size = block_size
+        self.overlap_ratio = overlap_ratio
+        self.padding_mode = PaddingMode(padding_mode)  # ValueError on an unknown mode
+        self.output_scale = output_scale
+        self.output_size = int(block_size * output_scale)
+        self.overlap_pixels = int(block_size * overlap_ratio)
+        # content analysis only decorates metadata (roi_flags, complexity_score); it is outside the GPU path
+        self.enable_content_aware = False
+        self.content_analyzer = None
+        if enable_content_aware:
+            logger.debug("content-aware analysis is out of scope for the B200 path; tiles carry no roi_flags")
+        self.l1_cache_size = l1_cache_size
+        self.l2_cache_dir = l2_cache_dir
+        self.device = int(device)
+        self.tile_registry: Dict[str, Tile] = {}
+        self.registry_lock = threading.Lock()
+        self.processing_state: Dict[str, dict] = {}
+
+    # ------------------------------------------------------------------ exact host geometry
+    def _calculate_tile_positions(self, image_width: int, image_height: int) -> List[Tuple[int, int, int, int]]:
+        lib = _native.load()
+        n = _native.check(lib.srf_tile_positions(image_width, image_height, self.block_size, self.overlap_pixels, None, 0),
+                          exc=ValueError)
+        buf = (C.c_int * (4 * n))()
+        _native.check(lib.srf_tile_positions(image_width, image_height, self.block_size, self.overlap_pixels, buf, n))
+        return [tuple(buf[4 * i: 4 * i + 4]) for i in range(n)]
+
+    def _calculate_overlap_for_tile(self, x, y, w, h, image_width, image_height) -> Tuple[int, int, int, int]:
+        out = (C.c_int * 4)()
+        _native.check(_native.load().srf_tile_overlaps(x, y, w, h, image_width, image_height, self.block_size,
+                                                      self.overlap_pixels, out))
+        return tuple(out)
+
+    def _compute_image_hash(self, image_path: str) -> str:
+        md5 = hashlib.md5()
+        with open(image_path, "rb") as f:
+            for chunk in iter(lambda: f.read(1 << 16), b""):
+                md5.update(chunk)
+        return md5.hexdigest()
+
+    # ------------------------------------------------------------------ GPU crop + pad
+    def _extract(self, image, positions) -> "np.ndarray":
+        """(n, block, block, C) uint8 stack of padded tiles; NumPy in -> NumPy out, CUDA tensor in -> CUDA tensor out"""
+        v = ImageView(image, "image")
+        n, b = len(positions), self.block_size
+        xywh = (C.c_int * (4 * n))(*[q for p in positions for q in p])
+        lib, ctx = _native.load(), _native.context(self.device)
+        mode = _BORDER_CODE[self.padding_mode]
+        shape = (n, b, b) if v.keep.ndim == 2 else (n, b, b, v.c)
+        if v.on_device:
+            out = torch.empty(shape, dtype=torch.uint8, device=v.keep.device)
+            rc = lib.srf_tile_extract_pad(ctx, v.ptr, v.h, v.w, v.c, v.pitch, xywh, n, b, mode, out.data_ptr(),
+                                          current_stream_ptr(v.device))
+        else:
+            out = np.empty(shape, np.uint8)
+            rc = lib.srf_tile_extract_pad_host(ctx, v.ptr, v.h, v.w, v.c, v.pitch, xywh, n, b, mode, out.ctypes.data)
+        _native.check(rc, ctx)
+        return out
+
+    def _apply_padding(self, image: np.ndarray, pad_top: int, pad_bottom: int, pad_left: int, pad_right: int) -> np.ndarray:
+        """bottom/right padding of one crop on the GPU; split_image never pads top/left (tiling_module.py:718-724)"""
+        if pad_top or pad_left:
+            raise NotImplementedError("only bottom/right padding is on the tiling path")
+        h, w = image.shape[:2]
+        if h + pad_bottom != w + pad_right:
+            raise NotImplementedError("the GPU pad kernel produces square block_size tiles")
+        saved = self.block_size
+        try:
+            self.block_size = h + pad_bottom
+            return self._extract(image, [(0, 0, w, h)])[0]
+        finally:
+            self.block_size = saved
+
+    # ------------------------------------------------------------------ public API
+    def split_array(self, image, image_hash: str = "", save_metadata: bool = True) -> List[Tile]:
+        """split an in-memory HWC uint8 RGB image (NumPy or CUDA tensor); split_image = decode + this"""
+        height, width = int(image.shape[0]), int(image.shape[1])
+        positions = self._calculate_tile_positions(width, height)
+        stack = self._extract(image, positions)
+        tiles = []
+        for i, (x, y, w, h) in enumerate(positions):
+            top, bottom, left, right = self._calculate_overlap_for_tile(x, y, w, h, width, height)
+            meta = TileMetadata(global_x=x, global_y=y, input_w=w, input_h=h, output_w=int(w * self.output_scale),
+                                output_h=int(h * self.output_scale), overlap_top=top, overlap_bottom=bottom,
+                                overlap_left=left, overlap_right=right, image_hash=image_hash, status=TileStatus.PENDING)
+            tile = Tile(metadata=meta, data=stack[i])
+            tiles.append(tile)
+            if save_metadata:
+                with self.registry_lock:
+                    self.tile_registry[meta.block_id] = tile
+        self._build_neighbor_relationships(tiles)
+        self.processing_state[image_hash] = {"image_width": width, "image_height": height, "num_tiles": len(tiles),
+                                             "tile_ids": [t.metadata.block_id for t in tiles], "timestamp": time.time()}
+        return tiles
+
+    def split_image(self, image_path: str, save_metadata: bool = True) -> List[Tile]:
+        image = _read_rgb(image_path)
+        image_hash = self._compute_image_hash(image_path)
+        tiles = self.split_array(image, image_hash, save_metadata)
+        self.processing_state[image_hash]["image_path"] = image_path
+        return tiles
+
+    def _build_neighbor_relationships(self, tiles: List[Tile]) -> None:
+        at = {(t.metadata.global_x, t.metadata.global_y): t.metadata.block_id for t in tiles}
+        step = self.block_size - self.overlap_pixels
+        for t in tiles:
+            x, y = t.metadata.global_x, t.metadata.global_y
+            for name, key in (("top", (x, y - step)), ("bottom", (x, y + step)), ("left", (x - step, y)),
+                              ("right", (x + step, y))):
+                if key in at:
+                    t.metadata.neighbor_ids[name] = at[key]
+
+    def get_neighbor_tiles(self, tile_id: str) -> List[Tile]:
+        with self.registry_lock:
+            tile = self.tile_registry.get(tile_id)
+            if tile is None:
+                return []
+            return [self.tile_registry[n] for n in tile.metadata.neighbor_ids.values() if n and n in self.tile_registry]
+
+    def restore_from_cache(self, image_hash: str):
+        """the reference's checkpoint restore (tiling_module.py:1040-1072) is host bookkeeping, out of scope"""
+        return None

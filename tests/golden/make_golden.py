@@ -1,0 +1,147 @@
+"""Generate the golden vectors in this directory by running the REFERENCE modules themselves
+(/root/reference, importable only in the build container -- the vectors travel, the reference does not).
+
+    python tests/golden/make_golden.py
+
+tiling_module and blending_module import as shipped (cv2 + numpy).  quality_assessment_module imports lpips and
+scikit-image at module level; neither is installed, so both are stubbed with functions that RAISE, which makes the
+reference take its own manual fallbacks: PSNR formula (quality_assessment_module.py:313-318) and
+_calculate_ssim_simple (391-417).  Inputs are stored next to the outputs so nothing depends on RNG stability.
+"""
+import logging
+import os
+import sys
+import tempfile
+import types
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = "/root/reference"
+
+
+def synth(rng, h, w, c=3):
+    """textured, non-saturated, non-flat uint8 image (blurred noise, contrast-stretched, + N(0,4))"""
+    import cv2
+    f = cv2.GaussianBlur(rng.random((h, w, c), dtype=np.float32) * 255, (0, 0), 3)
+    f = (f - f.mean()) * 4 + 128 + rng.normal(0, 4, f.shape)
+    return np.clip(f, 0, 255).astype(np.uint8).reshape((h, w, c) if c > 1 else (h, w))
+
+
+def main():
+    os.chdir(tempfile.mkdtemp())
+    logging.disable(logging.CRITICAL)
+    lp = types.ModuleType("lpips")
+
+    class _NoLpips:
+        def __init__(self, *a, **k):
+            raise RuntimeError("lpips absent")
+
+    lp.LPIPS = _NoLpips
+    sys.modules["lpips"] = lp
+    sk, skm = types.ModuleType("skimage"), types.ModuleType("skimage.metrics")
+
+    def _absent(*a, **k):
+        raise RuntimeError("skimage absent")
+
+    skm.peak_signal_noise_ratio = skm.structural_similarity = _absent
+    sk.metrics = skm
+    sys.modules["skimage"], sys.modules["skimage.metrics"] = sk, skm
+    sys.path.insert(0, REF)
+    import blending_module as rb
+    import quality_assessment_module as rq
+    import tiling_module as rt
+    import cv2
+
+    rng = np.random.default_rng(20261018)
+    out = {}
+
+    # ---- tiling: grid, overlaps, padded tiles for every padding mode -------------------------------------
+    geo = []
+    for (W, H, block, ratio) in [(8660, 5773, 2048, 0.2), (7500, 5000, 2048, 0.3), (6122, 4081, 2048, 0.1),
+                                 (6122, 3443, 2048, 0.2), (1280, 720, 2048, 0.2), (300, 200, 128, 0.25),
+                                 (129, 513, 128, 0.1), (100, 50, 64, 0.3)]:
+        tm = rt.TilingModule(block, ratio, "mirror", enable_content_aware=False, l2_cache_dir=tempfile.mkdtemp())
+        pos = tm._calculate_tile_positions(W, H)
+        ov = [tm._calculate_overlap_for_tile(x, y, w, h, W, H) for (x, y, w, h) in pos]
+        geo.append((W, H, block, ratio, len(pos)))
+        out[f"tiling_pos_{W}x{H}_{block}_{ratio}"] = np.array(pos, np.int32)
+        out[f"tiling_ov_{W}x{H}_{block}_{ratio}"] = np.array(ov, np.int32)
+    out["tiling_cases"] = np.array(geo, np.float64)
+    src = synth(rng, 150, 217)
+    out["tiling_src"] = src
+    png = os.path.join(tempfile.mkdtemp(), "src.png")
+    cv2.imwrite(png, src[:, :, ::-1])
+    for mode in ("mirror", "replicate", "reflect", "constant"):
+        tm = rt.TilingModule(96, 0.2, mode, enable_content_aware=False, l2_cache_dir=tempfile.mkdtemp())
+        tiles = tm.split_image(png)
+        out[f"tiling_tiles_{mode}"] = np.stack([t.data for t in tiles])
+        out[f"tiling_meta_{mode}"] = np.array([[t.metadata.global_x, t.metadata.global_y, t.metadata.input_w,
+                                                t.metadata.input_h, t.metadata.output_w, t.metadata.output_h,
+                                                t.metadata.overlap_top, t.metadata.overlap_bottom,
+                                                t.metadata.overlap_left, t.metadata.overlap_right] for t in tiles], np.int32)
+    # a crop much smaller than the block: multi-bounce reflection (pad > size - 1)
+    tiny = synth(rng, 5, 7)
+    out["tiling_tiny_src"] = tiny
+    for mode in ("mirror", "replicate", "reflect", "constant"):
+        tm = rt.TilingModule(32, 0.2, mode, enable_content_aware=False, l2_cache_dir=tempfile.mkdtemp())
+        out[f"tiling_tiny_{mode}"] = tm._apply_padding(tiny, 0, 32 - 5, 0, 32 - 7)
+
+    # ---- pyramids: the reference's own helpers ---------------------------------------------------------------
+    bm = rb.BlendingModule(num_levels=5)
+    img = synth(rng, 77, 101)
+    out["pyr_src"] = img
+    gp = bm.build_gaussian_pyramid(img, 5)
+    lp_ = bm.build_laplacian_pyramid(gp)
+    for i, (g, l) in enumerate(zip(gp, lp_)):
+        out[f"pyr_g{i}"] = g
+        out[f"pyr_l{i}"] = l
+    out["pyr_collapse"] = bm.collapse_laplacian_pyramid(lp_)
+    for kind in ("linear", "cosine", "sigmoid"):
+        out[f"weight_{kind}_64x80"] = bm._create_distance_weight_map(64, 80, rb.WeightType(kind))
+
+    # ---- fusion: 2x3 ragged grid with overhang, three weight types, odd sizes ------------------------------
+    def fuse_case(name, shapes_pos, out_hw, levels, kind="cosine", c=3):
+        tiles = [synth(rng, h, w, c) for (h, w, _, _) in shapes_pos]
+        infos = [rb.TileInfo(t, x, y, 0, 0) for t, (_, _, y, x) in zip(tiles, shapes_pos)]
+        res = rb.BlendingModule(num_levels=levels).laplacian_fusion(infos, output_shape=out_hw, weight_type=rb.WeightType(kind))
+        out[f"fuse_{name}_n"] = np.array([len(tiles), levels, out_hw[0], out_hw[1]], np.int32)
+        out[f"fuse_{name}_pos"] = np.array([(y, x) for (_, _, y, x) in shapes_pos], np.int32)
+        for i, t in enumerate(tiles):
+            out[f"fuse_{name}_t{i}"] = t
+        out[f"fuse_{name}_kind"] = np.array(kind)
+        out[f"fuse_{name}_out"] = res
+
+    grid = [(128, 128, y, x) for y in (0, 96) for x in (0, 96, 192)]
+    fuse_case("grid", grid, (210, 300), 5)                       # bottom/right tiles overhang and are cropped
+    fuse_case("ragged", [(100, 141, 0, 0), (77, 90, 11, 120), (130, 64, 60, 40)], (160, 215), 4, "sigmoid")
+    fuse_case("linear6", [(64, 64, 0, 0), (64, 64, 0, 40), (64, 64, 40, 0), (64, 64, 40, 40)], (104, 104), 6, "linear")
+    fuse_case("gray", [(96, 96, 0, 0), (96, 96, 0, 64)], (96, 160), 3, "cosine", c=1)
+    fuse_case("single1", [(72, 88, 3, 5)], (80, 100), 1)         # levels=1: no pyramid, hole around the tile
+    fuse_case("deep", [(48, 40, 0, 0), (48, 40, 0, 24)], (48, 64), 9)  # asks for more levels than the tile supports
+
+    # ---- IQA: the reference's manual fallbacks ------------------------------------------------------------
+    qa = rq.QualityAssessmentModule()
+    a = synth(rng, 211, 307)
+    b = np.clip(a.astype(np.float64) + rng.normal(0, 5, a.shape), 0, 255).astype(np.uint8)
+    out["iqa_a"], out["iqa_b"] = a, b
+    out["iqa_psnr"] = np.array(qa.calculate_psnr(a, b))
+    out["iqa_ssim_fallback"] = np.array(qa.calculate_ssim(a, b, multiscale=True))
+    out["iqa_gray_a"] = cv2.cvtColor(a, cv2.COLOR_RGB2GRAY)
+    out["iqa_psnr_crop"] = np.array(qa.calculate_psnr(a, b[:200, :300]))
+    out["iqa_psnr_same"] = np.array(qa.calculate_psnr(a, a))
+    # the seeded demo of the reference's own __main__ (quality_assessment_module.py:1394-1400)
+    np.random.seed(42)
+    hr = np.random.randint(0, 255, (512, 512, 3), dtype=np.uint8)
+    noise = np.random.normal(0, 5, hr.shape).astype(np.int16)
+    sr = np.clip(hr.astype(np.int16) + noise, 0, 255).astype(np.uint8)
+    out["iqa_demo_psnr"] = np.array(qa.calculate_psnr(hr, sr))
+    out["iqa_demo_ssim_fallback"] = np.array(qa.calculate_ssim(hr, sr, multiscale=True))
+
+    np.savez_compressed(os.path.join(HERE, "reference_vectors.npz"), **out)
+    print("wrote", os.path.join(HERE, "reference_vectors.npz"), os.path.getsize(os.path.join(HERE, "reference_vectors.npz")) // 1024, "KiB")
+    print("cv2", cv2.__version__, "numpy", np.__version__)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,137 @@
+"""CPU suite, part 2: the drop-in boundary -- the C-ABI library loads and exports everything include/srfuse.h
+declares, the host-exact entry points agree with the reference's golden vectors, the host-side mirrors keep the
+reference's argument/error behaviour, and the product never routes through the oracle or a CPU fallback."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "super-resolution-system_b200")
+
+
+def declared_functions():
+    text = open(os.path.join(ROOT, "include", "srfuse.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(srf_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(srs):
+    lib = ctypes.CDLL(srs._native.lib_path())
+    names = declared_functions()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/srfuse.h but not exported"
+    assert set(names) == set(srs._native.SIGNATURES), "ctypes binding and header disagree"
+    assert srs._native.load().srf_version() == 100
+
+
+def test_no_oracle_or_cpu_fallback_in_product():
+    for dirpath, _, files in os.walk(PKG):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, re.M), f"{f} imports the oracle"
+                assert "libsrf_oracle" not in text, f"{f} loads the oracle library"
+    for f in ("blending_module.py", "quality_assessment_module.py"):
+        text = open(os.path.join(PKG, f)).read()
+        assert not re.search(r"^\s*(from|import)\s+(cv2|scipy|skimage)\b", text, re.M), f"{f} must not compute on the CPU"
+
+
+def test_context_creation_fails_loudly_without_gpu(srs):
+    if os.path.exists("/dev/nvidiactl"):
+        pytest.skip("a GPU is present")
+    with pytest.raises(srs._native.SrfError, match="no CPU fallback"):
+        srs._native.context(0)
+    bm = srs.BlendingModule(num_levels=3)
+    with pytest.raises(srs._native.SrfError):
+        bm.laplacian_fusion([srs.TileInfo(np.zeros((64, 64, 3), np.uint8), 0, 0, 0, 0)], output_shape=(64, 64))
+
+
+def test_tile_geometry_is_exact(srs, golden):
+    for W, H, block, ratio, n in golden["tiling_cases"]:
+        W, H, block, n = int(W), int(H), int(block), int(n)
+        tm = srs.TilingModule(block, float(ratio), "mirror", enable_content_aware=False)
+        pos = tm._calculate_tile_positions(W, H)
+        assert len(pos) == n
+        assert np.array_equal(np.array(pos, np.int32), golden[f"tiling_pos_{W}x{H}_{block}_{ratio}"])
+        ov = [tm._calculate_overlap_for_tile(x, y, w, h, W, H) for (x, y, w, h) in pos]
+        assert np.array_equal(np.array(ov, np.int32), golden[f"tiling_ov_{W}x{H}_{block}_{ratio}"])
+
+
+def test_tile_geometry_property(srs, oracle):
+    rng = np.random.default_rng(11)
+    for _ in range(300):
+        block = int(rng.integers(16, 3000))
+        ratio = float(rng.uniform(0.1, 0.3))
+        W, H = int(rng.integers(1, 20000)), int(rng.integers(1, 20000))
+        tm = srs.TilingModule(block, ratio, enable_content_aware=False)
+        assert tm.overlap_pixels == oracle.tiling_oracle.overlap_pixels(block, ratio)
+        assert tm._calculate_tile_positions(W, H) == oracle.tiling_oracle.tile_positions(W, H, block, tm.overlap_pixels)
+
+
+def test_constructor_errors_match_reference(srs):
+    with pytest.raises(ValueError):
+        srs.TilingModule(overlap_ratio=0.05)
+    with pytest.raises(ValueError):
+        srs.TilingModule(overlap_ratio=0.31)
+    with pytest.raises(ValueError):
+        srs.TilingModule(padding_mode="wrap")
+    with pytest.raises(ValueError):
+        srs.BlendingModule(method="nope")
+    with pytest.raises(ValueError):
+        srs.TilingModule(enable_content_aware=False).split_image("/nonexistent/image.png")
+    tm = srs.TilingModule(2048, 0.2)
+    assert (tm.overlap_pixels, tm.output_size) == (409, 4096)
+    assert srs.TilingModule(2048, 0.1).overlap_pixels == 204 and srs.TilingModule(2048, 0.3).overlap_pixels == 614
+
+
+def test_fusion_argument_errors(srs):
+    bm = srs.BlendingModule(num_levels=4)
+    with pytest.raises(ValueError):
+        bm.laplacian_fusion([])
+    with pytest.raises(ValueError):  # bare arrays without output_shape: the reference raises ValueError too
+        bm.laplacian_fusion([np.zeros((64, 64, 3), np.uint8)])
+    with pytest.raises(TypeError):
+        bm.laplacian_fusion([srs.TileInfo(np.zeros((64, 64, 3), np.float32), 0, 0, 0, 0)], output_shape=(64, 64))
+    with pytest.raises(ValueError):
+        bm.laplacian_fusion([srs.TileInfo(np.zeros((4, 64, 3), np.uint8), 0, 0, 0, 0)], output_shape=(64, 64))
+
+
+def test_weight_profile_is_the_reference_map(srs, golden):
+    bm = srs.BlendingModule()
+    for kind in ("linear", "cosine", "sigmoid"):
+        got = bm._create_distance_weight_map(64, 80, srs.WeightType(kind))
+        assert got.dtype == np.float32 and np.array_equal(got, golden[f"weight_{kind}_64x80"])
+    # C helper for non-Python callers agrees with the NumPy profile to 1 ulp
+    buf = (ctypes.c_float * 513)()
+    assert srs._native.load().srf_weight_profile(1, 512, buf) == 0
+    prof = srs.blending_module.weight_profile(512, srs.WeightType.COSINE)
+    assert np.max(np.abs(np.frombuffer(buf, np.float32) - prof)) <= 6e-8
+
+
+def test_pipeline_api_surface(srs):
+    cfg = srs.PipelineConfig()
+    assert (cfg.block_size, cfg.overlap_ratio, cfg.padding_mode, cfg.num_pyramid_levels, cfg.blend_method) == \
+        (2048, 0.2, "mirror", 6, "laplacian")
+    pipe = srs.SuperResolutionPipeline(cfg)
+    assert pipe._calculate_target_size((1280, 720), "100MP") == (12245, 6887)
+    assert pipe._calculate_target_size((3000, 2000), "200MP") == (17320, 11546)
+    assert pipe._calculate_target_size((100, 100), "640x480") == (640, 480)
+    tc = srs.TilingConfig()
+    assert (tc.block_size, tc.output_block_size, tc.overlap_ratio, tc.min_overlap_ratio, tc.max_overlap_ratio) == \
+        (2048, 4096, 0.2, 0.1, 0.3)
+    md = srs.TileMetadata(global_x=3)
+    assert srs.TileMetadata.from_dict(md.to_dict()).global_x == 3
+    res = srs.PipelineResult(True, "x", 0.1, 1, 1, 0, None, None, None)
+    assert res.success
+
+
+def test_iqa_finish_matches_oracle_formula(srs, oracle):
+    s = srs._native.srf_iqa_sums(sq_err=123456, n_elems=3000, ssim_sum=87.5, ssim_count=100, max_a=255, max_b=255)
+    p, q = srs.QualityAssessmentModule.finish(s)
+    assert p == pytest.approx(10 * np.log10(255.0 ** 2 / (123456 / 3000)), rel=1e-15) and q == 0.875
+    s.sq_err = 0
+    assert srs.QualityAssessmentModule.finish(s)[0] == float("inf")

@@ -1,0 +1,272 @@
+"""GPU suite: every kernel of the hot path, called through the C ABI, against the oracle and the reference's golden
+vectors.  Bars (BASELINE.json north_star): tiles bit-exact; canvas within +-1 LSB with >= 99.9 % exact; PSNR / SSIM
+within 1e-4 relative."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from helpers import FUSE_CASES, canvas_agreement, fuse_case, synth
+
+pytestmark = pytest.mark.gpu
+REL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def bm5(srs):
+    return srs.BlendingModule(num_levels=5)
+
+
+# ------------------------------------------------------------------ tiling
+@pytest.mark.parametrize("mode", ["mirror", "replicate", "reflect", "constant"])
+def test_tiles_bit_exact_vs_reference(srs, golden, mode):
+    tm = srs.TilingModule(96, 0.2, mode, enable_content_aware=False)
+    tiles = tm.split_array(golden["tiling_src"])
+    want, meta = golden[f"tiling_tiles_{mode}"], golden[f"tiling_meta_{mode}"]
+    assert len(tiles) == len(want)
+    for t, w, m in zip(tiles, want, meta):
+        md = t.metadata
+        assert [md.global_x, md.global_y, md.input_w, md.input_h, md.output_w, md.output_h, md.overlap_top,
+                md.overlap_bottom, md.overlap_left, md.overlap_right] == [int(v) for v in m]
+        assert t.data.dtype == np.uint8 and np.array_equal(t.data, w)
+    tm32 = srs.TilingModule(32, 0.2, mode, enable_content_aware=False)
+    got = tm32._apply_padding(golden["tiling_tiny_src"], 0, 27, 0, 25)  # multi-bounce: pad >> size
+    assert np.array_equal(got, golden[f"tiling_tiny_{mode}"])
+
+
+def test_tiles_vs_oracle_large_and_gray(srs, oracle):
+    rng = np.random.default_rng(5)
+    for shape, block, ratio in [((1500, 2300, 3), 1024, 0.2), ((700, 333), 256, 0.3), ((64, 64, 3), 64, 0.1)]:
+        img = rng.integers(0, 256, shape, dtype=np.uint8)
+        tm = srs.TilingModule(block, ratio, "mirror", enable_content_aware=False)
+        for t in tm.split_array(img):
+            m = t.metadata
+            assert np.array_equal(t.data, oracle.tiling_oracle.extract_tile(img, m.global_x, m.global_y, m.input_w,
+                                                                          m.input_h, block, "mirror"))
+
+
+def test_tiles_device_path(srs):
+    import torch
+    rng = np.random.default_rng(6)
+    img = rng.integers(0, 256, (500, 700, 3), dtype=np.uint8)
+    tm = srs.TilingModule(256, 0.2, "reflect", enable_content_aware=False)
+    host = tm.split_array(img)
+    dev = tm.split_array(torch.from_numpy(img).cuda())
+    for a, b in zip(host, dev):
+        assert b.data.is_cuda and np.array_equal(a.data, b.data.cpu().numpy())
+
+
+# ------------------------------------------------------------------ pyramids (API-compat entry points)
+def test_pyramid_helpers_bit_exact_vs_reference(bm5, golden):
+    gp = bm5.build_gaussian_pyramid(golden["pyr_src"], 5)
+    assert len(gp) == 5
+    for i, g in enumerate(gp):
+        assert np.array_equal(g, golden[f"pyr_g{i}"]), i
+    lp = bm5.build_laplacian_pyramid(gp)
+    for i, l in enumerate(lp):
+        assert np.array_equal(l, golden[f"pyr_l{i}"]), i
+    assert np.array_equal(bm5.collapse_laplacian_pyramid(lp), golden["pyr_collapse"])
+
+
+def test_pyr_down_up_vs_oracle_shapes(bm5, oracle):
+    rng = np.random.default_rng(8)
+    for h, w in [(1, 1), (1, 5), (2, 2), (3, 7), (16, 16), (37, 53), (128, 130), (257, 64)]:
+        for cn in (1, 3):
+            x = (rng.random((h, w, cn)) * 255 + rng.random((h, w, cn))).astype(np.float32)
+            x = np.ascontiguousarray(x[:, :, 0] if cn == 1 else x)
+            assert np.array_equal(bm5._pyr_down(x), oracle.pyr.pyr_down(x, "c")), (h, w, cn)
+            for dh, dw in ((2 * h, 2 * w), (2 * h - 1, 2 * w - 1)):
+                if dh >= 1 and dw >= 1:
+                    assert np.array_equal(bm5._pyr_up(x, (dh, dw)), oracle.pyr.pyr_up(x, (dh, dw), "c")), (h, w, cn, dh, dw)
+    with pytest.raises(ValueError):
+        bm5._pyr_up(np.zeros((4, 4), np.float32), (9, 9))
+
+
+# ------------------------------------------------------------------ fusion
+@pytest.mark.parametrize("name", FUSE_CASES)
+def test_fusion_vs_reference_golden(srs, golden, name):
+    tiles, pos, out_hw, levels, kind, want = fuse_case(golden, name)
+    infos = [srs.TileInfo(np.ascontiguousarray(t), x, y, 0, 0) for t, (y, x) in zip(tiles, pos)]
+    got = srs.BlendingModule(num_levels=levels).laplacian_fusion(infos, output_shape=out_hw, weight_type=srs.WeightType(kind))
+    assert got.shape == want.shape and got.dtype == np.uint8
+    mx, exact = canvas_agreement(got, want)
+    assert mx <= 1 and exact >= 0.999, (name, mx, exact)
+
+
+def _grid_case(rng, th, tw, ny, nx, sy, sx, c=3):
+    tiles, pos = [], []
+    for j in range(ny):
+        for i in range(nx):
+            tiles.append(synth(rng, th, tw, c))
+            pos.append((j * sy, i * sx))
+    return tiles, pos
+
+
+@pytest.mark.parametrize("levels", [1, 2, 3, 5, 7])
+def test_fusion_vs_oracle_levels(srs, oracle, levels):
+    rng = np.random.default_rng(100 + levels)
+    tiles, pos = _grid_case(rng, 256, 320, 2, 3, 200, 250)
+    out_hw = (440, 800)  # bottom/right tiles overhang the canvas
+    infos = [srs.TileInfo(t, x, y, 0, 0) for t, (y, x) in zip(tiles, pos)]
+    got = srs.BlendingModule(num_levels=levels).laplacian_fusion(infos, output_shape=out_hw)
+    want = oracle.fusion_oracle.laplacian_fuse(tiles, pos, out_hw, levels, "cosine", "c")
+    mx, exact = canvas_agreement(got, want)
+    assert mx <= 1 and exact >= 0.999, (levels, mx, exact)
+
+
+def test_fusion_odd_positions_and_sizes(srs, oracle):
+    """odd tile origins flip the pyrUp phase relative to the canvas blocks; odd sizes hit the 2n-1 pyrUp case"""
+    rng = np.random.default_rng(21)
+    shapes = [(201, 333), (201, 333), (157, 129), (96, 415)]
+    pos = [(3, 5), (101, 207), (150, 1), (7, 300)]
+    tiles = [synth(rng, h, w) for h, w in shapes]
+    out_hw = (330, 560)
+    infos = [srs.TileInfo(t, x, y, 0, 0) for t, (y, x) in zip(tiles, pos)]
+    for kind in ("cosine", "linear", "sigmoid"):
+        got = srs.BlendingModule(num_levels=6).laplacian_fusion(infos, output_shape=out_hw, weight_type=srs.WeightType(kind))
+        want = oracle.fusion_oracle.laplacian_fuse(tiles, pos, out_hw, 6, kind, "c")
+        mx, exact = canvas_agreement(got, want)
+        assert mx <= 1 and exact >= 0.999, (kind, mx, exact)
+
+
+def test_fusion_default_output_shape_and_grid_layout(srs, oracle):
+    rng = np.random.default_rng(22)
+    tiles = [synth(rng, 128, 128) for _ in range(4)]
+    bm = srs.BlendingModule(num_levels=4)
+    got = bm.laplacian_fusion(tiles, output_shape=(256, 256))  # bare arrays: sqrt-grid layout
+    pos = [(0, 0), (0, 128), (128, 0), (128, 128)]
+    want = oracle.fusion_oracle.laplacian_fuse(tiles, pos, (256, 256), 4, "cosine", "c")
+    assert canvas_agreement(got, want)[0] <= 1
+    infos = [srs.TileInfo(t, x, y, 0, 0) for t, (y, x) in zip(tiles, [(0, 0), (0, 100), (90, 0), (90, 100)])]
+    got = bm.laplacian_fusion(infos)  # output_shape=None -> max extents
+    assert got.shape == (218, 228, 3)
+
+
+def test_fusion_device_path_equals_host_path(srs):
+    import torch
+    rng = np.random.default_rng(23)
+    tiles, pos = _grid_case(rng, 192, 192, 2, 2, 150, 150)
+    bm = srs.BlendingModule(num_levels=5)
+    host = bm.laplacian_fusion([srs.TileInfo(t, x, y, 0, 0) for t, (y, x) in zip(tiles, pos)], output_shape=(342, 342))
+    dev = bm.laplacian_fusion([srs.TileInfo(torch.from_numpy(t).cuda(), x, y, 0, 0) for t, (y, x) in zip(tiles, pos)],
+                              output_shape=(342, 342))
+    assert dev.is_cuda and np.array_equal(dev.cpu().numpy(), host)
+
+
+def test_fusion_row_bands_reassemble(srs):
+    """band sharding: any split of the canvas rows gives the same bytes as the single pass"""
+    rng = np.random.default_rng(24)
+    tiles, pos = _grid_case(rng, 256, 256, 3, 2, 190, 200)
+    infos = [srs.TileInfo(t, x, y, 0, 0) for t, (y, x) in zip(tiles, pos)]
+    bm = srs.BlendingModule(num_levels=6)
+    out_hw = (636, 456)
+    full = bm.laplacian_fusion(infos, output_shape=out_hw)
+    for cuts in ([0, 318, 636], [0, 101, 333, 500, 636], [0, 1, 635, 636]):
+        acc = np.zeros_like(full)
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            part = bm.laplacian_fusion(infos, output_shape=out_hw, row_range=(a, b))
+            assert not part[:a].any() and not part[b:].any()
+            acc[a:b] = part[a:b]
+        assert np.array_equal(acc, full), cuts
+
+
+def test_fusion_full_size_tile_properties(srs, oracle):
+    """one 4096^2 tile at BASELINE size: compared with the oracle on a band, plus idempotence of the call"""
+    rng = np.random.default_rng(25)
+    small = synth(rng, 512, 512)
+    tile = np.ascontiguousarray(np.kron(small, np.ones((8, 8, 1), np.uint8)))
+    tile = np.clip(tile.astype(np.int16) + rng.integers(-5, 6, tile.shape), 0, 255).astype(np.uint8)
+    bm = srs.BlendingModule(num_levels=7)
+    info = [srs.TileInfo(tile, 0, 0, 0, 0)]
+    a = bm.laplacian_fusion(info, output_shape=(4096, 4096))
+    b = bm.laplacian_fusion(info, output_shape=(4096, 4096))
+    assert np.array_equal(a, b)
+    want = oracle.fusion_oracle.laplacian_fuse([tile], [(0, 0)], (4096, 4096), 7, "cosine", "cv2" if oracle.pyr.have_cv2() else "c")
+    mx, exact = canvas_agreement(a, want)
+    assert mx <= 1 and exact >= 0.999, (mx, exact)
+
+
+# ------------------------------------------------------------------ IQA
+def test_iqa_vs_reference_golden(srs, golden, oracle):
+    qa = srs.QualityAssessmentModule()
+    a, b = golden["iqa_a"], golden["iqa_b"]
+    assert qa.calculate_psnr(a, b) == pytest.approx(float(golden["iqa_psnr"]), rel=1e-12)
+    assert qa.calculate_psnr(a, b[:200, :300]) == pytest.approx(float(golden["iqa_psnr_crop"]), rel=1e-12)
+    assert qa.calculate_psnr(a, a) == float("inf")
+    assert qa.calculate_ssim(a, b) == pytest.approx(oracle.iqa_oracle.ssim(a, b), rel=REL)
+    assert qa.calculate_ssim(a, b) == pytest.approx(float(golden["iqa_ssim_fallback"]), rel=3e-4)
+    assert qa.calculate_ssim(a, a) == pytest.approx(1.0, rel=1e-6)
+
+
+@pytest.mark.parametrize("shape", [(11, 11, 3), (12, 300, 3), (300, 13, 3), (129, 257, 3), (640, 480), (1000, 1500, 3)])
+def test_iqa_vs_oracle_shapes(srs, oracle, shape):
+    rng = np.random.default_rng(sum(shape))
+    a = synth(rng, shape[0], shape[1], shape[2] if len(shape) == 3 else 1)
+    b = np.clip(a.astype(np.int16) + rng.integers(-12, 13, a.shape), 0, 255).astype(np.uint8)
+    qa = srs.QualityAssessmentModule()
+    p, s = qa.calculate_psnr_ssim(a, b)
+    assert p == pytest.approx(oracle.iqa_oracle.psnr(a, b), rel=1e-12)
+    assert s == pytest.approx(oracle.iqa_oracle.ssim(a, b), rel=REL)
+    sums = qa.psnr_ssim_sums(a, b)
+    assert sums.sq_err == oracle.iqa_oracle.sq_err_sum(a, b)
+    assert sums.ssim_count == (shape[0] - 10) * (shape[1] - 10)
+
+
+def test_iqa_hard_cases(srs, oracle):
+    qa = srs.QualityAssessmentModule()
+    rng = np.random.default_rng(31)
+    flat = np.full((200, 260, 3), 201, np.uint8)
+    near = flat.copy()
+    near[::7, ::5] -= 1  # near-flat pair: worst case for float32 cancellation in the variances
+    assert qa.calculate_ssim(flat, near) == pytest.approx(oracle.iqa_oracle.ssim(flat, near), rel=REL)
+    sat = rng.choice(np.array([0, 255], np.uint8), (150, 170, 3))
+    assert qa.calculate_ssim(sat, 255 - sat) == pytest.approx(oracle.iqa_oracle.ssim(sat, 255 - sat), rel=REL, abs=1e-6)
+    with pytest.raises(ValueError):
+        qa.calculate_ssim(np.zeros((8, 40, 3), np.uint8), np.zeros((8, 40, 3), np.uint8))
+    # the reference's max() <= 1 rule: an all-0/1 uint8 image is multiplied by 255 first
+    bits = rng.integers(0, 2, (64, 64, 3), dtype=np.uint8)
+    other = rng.integers(0, 256, (64, 64, 3), dtype=np.uint8)
+    assert qa.calculate_psnr(bits, other) == pytest.approx(oracle.iqa_oracle.psnr(bits, other), rel=1e-12)
+    f01 = rng.random((64, 64, 3))
+    assert qa.calculate_psnr(f01, other) == pytest.approx(oracle.iqa_oracle.psnr(f01, other), rel=1e-12)
+
+
+def test_iqa_bands_add_up(srs):
+    rng = np.random.default_rng(32)
+    a = synth(rng, 700, 900)
+    b = np.clip(a.astype(np.int16) + rng.integers(-9, 10, a.shape), 0, 255).astype(np.uint8)
+    qa = srs.QualityAssessmentModule()
+    full = qa.psnr_ssim_sums(a, b)
+    sq = cnt = 0
+    ss = 0.0
+    for r0, r1 in [(0, 3), (3, 64), (64, 350), (350, 699), (699, 700)]:
+        s = qa.psnr_ssim_sums(a, b, row_range=(r0, r1))
+        sq, cnt, ss = sq + s.sq_err, cnt + s.ssim_count, ss + s.ssim_sum
+    assert sq == full.sq_err and cnt == full.ssim_count
+    assert ss == pytest.approx(full.ssim_sum, rel=1e-9)
+
+
+def test_iqa_device_path_and_evaluate(srs, oracle):
+    import torch
+    rng = np.random.default_rng(33)
+    a = synth(rng, 400, 520)
+    b = np.clip(a.astype(np.int16) + rng.integers(-9, 10, a.shape), 0, 255).astype(np.uint8)
+    qa = srs.QualityAssessmentModule()
+    host = qa.calculate_psnr_ssim(a, b)
+    dev = qa.calculate_psnr_ssim(torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda())
+    assert host == dev
+    rep = qa.evaluate_full_reference(a, b)
+    assert set(rep) >= {"psnr", "psnr_level", "ms_ssim", "ssim_level", "overall_score"}
+    assert rep["overall_score"] == pytest.approx(np.mean([min(100, rep["psnr"]), rep["ms_ssim"] * 100]))
+    assert len(qa.batch_evaluate([(a, b), (b, a)])) == 2
+
+
+# ------------------------------------------------------------------ end to end
+def test_pipeline_run_small(srs, oracle):
+    rng = np.random.default_rng(40)
+    src = synth(rng, 90, 160)
+    cfg = srs.PipelineConfig(block_size=128, overlap_ratio=0.25, target_resolution="640x360", num_pyramid_levels=4)
+    pipe = srs.SuperResolutionPipeline(cfg)
+    res = pipe.run(src)
+    assert res["canvas"].shape == (360, 640, 3) and res["tiles"] >= 2
+    assert 0 < res["report"]["ms_ssim"] <= 1

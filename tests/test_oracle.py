@@ -1,0 +1,118 @@
+"""CPU suite, part 1: the oracle against the reference's golden vectors (tests/golden/reference_vectors.npz, made by
+tests/golden/make_golden.py from the reference modules themselves) and against cv2 where cv2 is importable."""
+import numpy as np
+import pytest
+
+from helpers import FUSE_CASES, fuse_case, synth
+
+
+def test_pyr_c_matches_reference_pyramids(golden, oracle):
+    fo = oracle.fusion_oracle
+    g = fo.gaussian_pyramid(golden["pyr_src"], 5, "c")
+    for i, lvl in enumerate(g):
+        assert np.array_equal(lvl, golden[f"pyr_g{i}"]), f"gaussian level {i}"
+    for i in range(len(g) - 1):
+        lap = g[i] - oracle.pyr.pyr_up(g[i + 1], g[i].shape[:2], "c")
+        assert np.array_equal(lap, golden[f"pyr_l{i}"]), f"laplacian level {i}"
+    cur = g[-1]
+    for i in range(len(g) - 2, -1, -1):
+        cur = oracle.pyr.pyr_up(cur, g[i].shape[:2], "c") + golden[f"pyr_l{i}"]
+    assert np.array_equal(cur, golden["pyr_collapse"])
+
+
+@pytest.mark.skipif(not __import__("oracle").pyr.have_cv2(), reason="cv2 not importable")
+def test_pyr_c_bit_equals_cv2(oracle):
+    rng = np.random.default_rng(7)
+    for h in (1, 2, 3, 5, 8, 17, 64, 65):
+        for w in (1, 2, 3, 4, 7, 16, 33, 130):
+            for cn in (1, 3):
+                x = (rng.random((h, w, cn)) * 255 + rng.random((h, w, cn))).astype(np.float32)
+                x = x[:, :, 0] if cn == 1 else x
+                assert np.array_equal(oracle.pyr.pyr_down(x, "c"), oracle.pyr.pyr_down(x, "cv2")), (h, w, cn)
+                for dh, dw in ((2 * h, 2 * w), (2 * h - 1, 2 * w - 1), (2 * h, 2 * w - 1), (2 * h - 1, 2 * w)):
+                    if dh < 1 or dw < 1:
+                        continue
+                    assert np.array_equal(oracle.pyr.pyr_up(x, (dh, dw), "c"), oracle.pyr.pyr_up(x, (dh, dw), "cv2")), (h, w, cn, dh, dw)
+
+
+def test_pyr_up_rejects_sizes_off_the_path(oracle):
+    with pytest.raises(ValueError):
+        oracle.pyr.pyr_up(np.zeros((4, 4), np.float32), (9, 9), "c")
+
+
+@pytest.mark.parametrize("kind", ["linear", "cosine", "sigmoid"])
+def test_weight_map(golden, oracle, kind):
+    assert np.array_equal(oracle.fusion_oracle.weight_map(64, 80, kind), golden[f"weight_{kind}_64x80"])
+
+
+@pytest.mark.parametrize("name", FUSE_CASES)
+def test_fusion_oracle_matches_reference(golden, oracle, name):
+    tiles, pos, out_hw, levels, kind, want = fuse_case(golden, name)
+    got = oracle.fusion_oracle.laplacian_fuse(tiles, pos, out_hw, levels, kind, "c")
+    assert got.shape == want.shape and got.dtype == np.uint8
+    assert np.array_equal(got, want)
+
+
+def test_tiling_oracle_matches_reference(golden, oracle):
+    to = oracle.tiling_oracle
+    for W, H, block, ratio, n in golden["tiling_cases"]:
+        W, H, block, n = int(W), int(H), int(block), int(n)
+        ov = to.overlap_pixels(block, float(ratio))
+        pos = to.tile_positions(W, H, block, ov)
+        assert len(pos) == n
+        assert np.array_equal(np.array(pos, np.int32), golden[f"tiling_pos_{W}x{H}_{block}_{ratio}"])
+        got = [to.tile_overlaps(x, y, w, h, W, H, block, ov) for (x, y, w, h) in pos]
+        assert np.array_equal(np.array(got, np.int32), golden[f"tiling_ov_{W}x{H}_{block}_{ratio}"])
+    src = golden["tiling_src"]
+    for mode in to.MODES:
+        meta = golden[f"tiling_meta_{mode}"]
+        for i, m in enumerate(meta):
+            t = to.extract_tile(src, int(m[0]), int(m[1]), int(m[2]), int(m[3]), 96, mode)
+            assert np.array_equal(t, golden[f"tiling_tiles_{mode}"][i]), (mode, i)
+        tiny = golden["tiling_tiny_src"]
+        assert np.array_equal(to.extract_tile(tiny, 0, 0, 7, 5, 32, mode), golden[f"tiling_tiny_{mode}"]), mode
+
+
+def test_iqa_oracle_matches_reference(golden, oracle):
+    io = oracle.iqa_oracle
+    a, b = golden["iqa_a"], golden["iqa_b"]
+    assert io.psnr(a, b) == pytest.approx(float(golden["iqa_psnr"]), rel=1e-13)
+    assert io.psnr(a, b[:200, :300]) == pytest.approx(float(golden["iqa_psnr_crop"]), rel=1e-13)
+    assert io.psnr(a, a) == float("inf") == float(golden["iqa_psnr_same"])
+    assert np.array_equal(io.rgb_to_gray(a), golden["iqa_gray_a"])
+    # the reference's fallback blurs with reflect-101 borders and averages the whole map; scikit-image's algorithm
+    # (the oracle) averages the interior -- they agree to ~1e-4 at this size and better as images grow
+    assert io.ssim(a, b) == pytest.approx(float(golden["iqa_ssim_fallback"]), rel=3e-4)
+    np.random.seed(42)
+    hr = np.random.randint(0, 255, (512, 512, 3), dtype=np.uint8)
+    noise = np.random.normal(0, 5, hr.shape).astype(np.int16)
+    sr = np.clip(hr.astype(np.int16) + noise, 0, 255).astype(np.uint8)
+    assert io.psnr(hr, sr) == pytest.approx(float(golden["iqa_demo_psnr"]), rel=1e-13)
+    assert io.ssim(hr, sr) == pytest.approx(float(golden["iqa_demo_ssim_fallback"]), rel=1e-4)
+
+
+def test_iqa_oracle_equals_scipy_restatement_of_skimage(oracle):
+    ndimage = pytest.importorskip("scipy.ndimage")
+    io = oracle.iqa_oracle
+    rng = np.random.default_rng(3)
+    a = synth(rng, 90, 120)
+    b = np.clip(a.astype(np.int16) + rng.integers(-9, 10, a.shape), 0, 255).astype(np.uint8)
+    x, y = io.rgb_to_gray(a).astype(np.float64), io.rgb_to_gray(b).astype(np.float64)
+
+    def f(z):
+        return ndimage.gaussian_filter(z, 1.5, truncate=3.5, mode="reflect")
+
+    ux, uy, uxx, uyy, uxy = f(x), f(y), f(x * x), f(y * y), f(x * y)
+    vx, vy, vxy = uxx - ux * ux, uyy - uy * uy, uxy - ux * uy
+    c1, c2 = 6.5025, 58.5225
+    s = ((2 * ux * uy + c1) * (2 * vxy + c2)) / ((ux ** 2 + uy ** 2 + c1) * (vx + vy + c2))
+    assert io.ssim(a, b) == pytest.approx(s[5:-5, 5:-5].mean(dtype=np.float64), rel=1e-12)
+
+
+def test_iqa_preprocess_rule(oracle):
+    io = oracle.iqa_oracle
+    ones = np.ones((20, 20, 3), np.uint8)
+    assert io.preprocess(ones).max() == 255  # an all-<=1 uint8 image is rescaled too (q.a.m:192-193)
+    assert io.preprocess(np.full((4, 4), 0.5)).dtype == np.uint8
+    with pytest.raises(ValueError):
+        io.ssim(np.zeros((8, 30), np.uint8), np.zeros((8, 30), np.uint8))
