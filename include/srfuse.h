@@ -65,6 +65,17 @@ size_t srf_workspace_bytes(const srf_ctx *ctx);
  * valid after that call's stream has been synchronised; <0 if none */
 float srf_last_device_ms(srf_ctx *ctx);
 
+/* per-kernel CUDA-event timing (bench.py's roofline leg).  While enabled every kernel launch is bracketed by two
+ * events on its stream; srf_profile_read synchronises the device, writes up to `cap` entries in launch order,
+ * clears the log and returns the number of entries it held. */
+typedef struct srf_profile_entry {
+    char name[40];
+    float ms;     /* device time of this launch */
+    double bytes; /* algorithmic bytes of this launch (compulsory reads + writes), 0 if not tracked */
+} srf_profile_entry;
+int srf_profile_enable(srf_ctx *ctx, int on);
+int srf_profile_read(srf_ctx *ctx, srf_profile_entry *out, int cap);
+
 /* ---- tiling -------------------------------------------------------------------------------------------- */
 /* replaces TilingModule._calculate_tile_positions (tiling_module.py:572-608).  Host-only, exact.
  * Writes min(count, cap) quadruples (x, y, w, h), row-major, and returns the count (or <0). */
@@ -145,6 +156,14 @@ int srf_psnr_ssim(srf_ctx *ctx, const uint8_t *d_a, size_t pitch_a, const uint8_
 int srf_psnr_ssim_host(srf_ctx *ctx, const uint8_t *h_a, size_t pitch_a, const uint8_t *h_b, size_t pitch_b,
                        int h, int w, int channels, int scale_a, int scale_b, double data_range, int row_begin,
                        int row_end, srf_iqa_sums *h_out);
+/* stage 3 + stage 4 of the reference pipeline in one call (main.py:347 laplacian_fusion, :369
+ * evaluate_full_reference): host tiles -> fused canvas (host) + PSNR/SSIM sums of the canvas against a host
+ * comparison image of the same size.  The canvas stays on the device between the two stages; uploads, kernels and
+ * the canvas download overlap on two streams. */
+int srf_fuse_assess_host(srf_ctx *ctx, const srf_tile *tiles, int n_tiles, int channels, int levels,
+                         const srf_weight_lut *luts, int n_luts, int out_h, int out_w, uint8_t *h_canvas,
+                         size_t canvas_pitch, const uint8_t *h_reference, size_t reference_pitch, double data_range,
+                         srf_iqa_sums *h_out);
 /* final scalars from (all-reduced) sums: psnr = 10 log10(range^2 / (sq_err / n_elems)) (+inf if sq_err == 0),
  * ssim = ssim_sum / ssim_count */
 int srf_iqa_finish(const srf_iqa_sums *sums, double data_range, double *psnr, double *ssim);

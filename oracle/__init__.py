@@ -16,4 +16,4 @@ Parity status (see DESIGN.md "Oracle"):
     against scipy.ndimage.gaussian_filter (what scikit-image calls) -- "parity pinned to the fallback, not to
     scikit-image itself".
 """
-from . import pyr, tiling_oracle, fusion_oracle, iqa_oracle  # noqa: F401
+from . import pyr, tiling_oracle, fusion_oracle, iqa_oracle, reference_port  # noqa: F401

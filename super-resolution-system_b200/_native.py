@@ -26,6 +26,10 @@ class srf_weight_lut(C.Structure):
     _fields_ = [("values", c_void_p), ("len", c_int)]
 
 
+class srf_profile_entry(C.Structure):
+    _fields_ = [("name", C.c_char * 40), ("ms", C.c_float), ("bytes", C.c_double)]
+
+
 class srf_iqa_sums(C.Structure):
     _fields_ = [("sq_err", c_int64), ("n_elems", c_int64), ("ssim_sum", C.c_double), ("ssim_count", c_int64),
                 ("max_a", C.c_int32), ("max_b", C.c_int32)]
@@ -43,6 +47,8 @@ SIGNATURES = {
     "srf_launch_count": (c_int64, [c_void_p]),
     "srf_workspace_bytes": (c_size_t, [c_void_p]),
     "srf_last_device_ms": (C.c_float, [c_void_p]),
+    "srf_profile_enable": (c_int, [c_void_p, c_int]),
+    "srf_profile_read": (c_int, [c_void_p, P(srf_profile_entry), c_int]),
     "srf_tile_positions": (c_int, [c_int, c_int, c_int, c_int, c_void_p, c_int]),
     "srf_tile_overlaps": (c_int, [c_int] * 8 + [c_void_p]),
     "srf_tile_extract_pad": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_size_t, c_void_p, c_int, c_int, c_int,
@@ -62,6 +68,8 @@ SIGNATURES = {
                               C.c_double, c_int, c_int, P(srf_iqa_sums), c_void_p]),
     "srf_psnr_ssim_host": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, c_int, c_int, c_int, c_int, c_int,
                                    C.c_double, c_int, c_int, P(srf_iqa_sums)]),
+    "srf_fuse_assess_host": (c_int, [c_void_p, P(srf_tile), c_int, c_int, c_int, P(srf_weight_lut), c_int, c_int, c_int,
+                                     c_void_p, c_size_t, c_void_p, c_size_t, C.c_double, P(srf_iqa_sums)]),
     "srf_iqa_finish": (c_int, [P(srf_iqa_sums), C.c_double, P(C.c_double), P(C.c_double)]),
 }
 
@@ -129,5 +137,12 @@ def destroy_contexts():
         _ctx.clear()
 
 
-def np_ptr(a: np.ndarray) -> int:
-    return a.ctypes.data
+def profile_enable(ctx, on: bool) -> None:
+    check(load().srf_profile_enable(ctx, int(on)), ctx)
+
+
+def profile_read(ctx, cap: int = 4096):
+    """[(kernel name, ms, algorithmic bytes)] in launch order since the last read"""
+    buf = (srf_profile_entry * cap)()
+    n = check(load().srf_profile_read(ctx, buf, cap), ctx)
+    return [(buf[i].name.decode(), float(buf[i].ms), float(buf[i].bytes)) for i in range(min(n, cap))]

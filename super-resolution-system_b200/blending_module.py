@@ -144,17 +144,8 @@ class BlendingModule:
         return prof[np.minimum(d, len(prof) - 1)]
 
     # ------------------------------------------------------------------ fusion
-    def laplacian_fusion(self, tiles: List[Union[np.ndarray, TileInfo]], overlap_map=None,
-                         output_shape: Optional[Tuple[int, int]] = None,
-                         weight_type: WeightType = WeightType.COSINE, row_range: Optional[Tuple[int, int]] = None):
-        """Fuse upscaled tiles into one uint8 canvas (see include/srfuse.h: srf_laplacian_fuse).
-
-        tiles: TileInfo objects (image + x, y) or bare arrays (grid layout, needs output_shape).  Images are uint8
-        NumPy arrays (host path: H2D, kernels, D2H inside the call) or uint8 torch CUDA tensors (device path: the
-        result is a CUDA tensor and stays on the device).  `overlap_map` is accepted and ignored, as in the
-        reference (blending_module.py:369-506 never reads it).  `row_range` (extension) restricts the produced
-        canvas rows for band sharding across GPUs.
-        """
+    def _marshal(self, tiles, output_shape, weight_type):
+        """TileInfo / array list -> (views, srf_tile[], srf_weight_lut[], keepalive, out_h, out_w, channels)"""
         images, positions = [], []
         for i, t in enumerate(tiles):
             if isinstance(t, TileInfo):
@@ -183,8 +174,6 @@ class BlendingModule:
             out_w = max(x + v.w for v, (_, x) in zip(views, positions))
         else:
             out_h, out_w = int(output_shape[0]), int(output_shape[1])
-        r0, r1 = (0, out_h) if row_range is None else (int(row_range[0]), int(row_range[1]))
-
         lut_index, luts = {}, []
         c_tiles = (_native.srf_tile * len(views))()
         for i, (v, (y, x)) in enumerate(zip(views, positions)):
@@ -194,7 +183,24 @@ class BlendingModule:
                 luts.append(prof)
             c_tiles[i] = _native.srf_tile(v.ptr, v.pitch, v.h, v.w, y, x, lut_index[id(prof)])
         c_luts = (_native.srf_weight_lut * len(luts))(*[_native.srf_weight_lut(p.ctypes.data, len(p)) for p in luts])
+        return views, c_tiles, c_luts, luts, out_h, out_w, chans
 
+    def laplacian_fusion(self, tiles: List[Union[np.ndarray, TileInfo]], overlap_map=None,
+                         output_shape: Optional[Tuple[int, int]] = None,
+                         weight_type: WeightType = WeightType.COSINE, row_range: Optional[Tuple[int, int]] = None,
+                         out=None):
+        """Fuse upscaled tiles into one uint8 canvas (see include/srfuse.h: srf_laplacian_fuse).
+
+        tiles: TileInfo objects (image + x, y) or bare arrays (grid layout, needs output_shape).  Images are uint8
+        NumPy arrays (host path: H2D, kernels, D2H inside the call) or uint8 torch CUDA tensors (device path: the
+        result is a CUDA tensor and stays on the device).  `overlap_map` is accepted and ignored, as in the
+        reference (blending_module.py:369-506 never reads it).  Extensions: `row_range` restricts the produced
+        canvas rows (band sharding across GPUs; other rows are zero / left as they are in `out`), `out` reuses a
+        caller-owned canvas.
+        """
+        views, c_tiles, c_luts, keep, out_h, out_w, chans = self._marshal(tiles, output_shape, weight_type)
+        on_dev = views[0].on_device
+        r0, r1 = (0, out_h) if row_range is None else (int(row_range[0]), int(row_range[1]))
         lib, ctx = _native.load(), self._ctx()
         shape = (out_h, out_w) if views[0].keep.ndim == 2 else (out_h, out_w, chans)
         if on_dev:
@@ -209,18 +215,54 @@ class BlendingModule:
                     buf[:, : v.w * chans] = v.keep.reshape(v.h, v.w * chans)
                     staged.append(buf)
                     c_tiles[i].data, c_tiles[i].pitch = buf.data_ptr(), pitch
-            canvas = torch.zeros(shape, dtype=torch.uint8, device=views[0].keep.device) if (r0, r1) != (0, out_h) \
-                else torch.empty(shape, dtype=torch.uint8, device=views[0].keep.device)
-            rc = lib.srf_laplacian_fuse(ctx, c_tiles, len(views), chans, self.num_levels, c_luts, len(luts), out_h,
+            if out is not None:
+                if not is_cuda_tensor(out) or tuple(out.shape) != shape or out.dtype != torch.uint8 or not out.is_contiguous():
+                    raise ValueError("out must be a contiguous uint8 CUDA tensor of the canvas shape")
+                canvas = out
+            elif (r0, r1) != (0, out_h):
+                canvas = torch.zeros(shape, dtype=torch.uint8, device=views[0].keep.device)
+            else:
+                canvas = torch.empty(shape, dtype=torch.uint8, device=views[0].keep.device)
+            rc = lib.srf_laplacian_fuse(ctx, c_tiles, len(views), chans, self.num_levels, c_luts, len(c_luts), out_h,
                                         out_w, canvas.data_ptr(), out_w * chans, r0, r1, current_stream_ptr(dev))
             _native.check(rc, ctx)
             del staged
             return canvas
-        canvas = np.zeros(shape, np.uint8) if (r0, r1) != (0, out_h) else np.empty(shape, np.uint8)
-        rc = lib.srf_laplacian_fuse_host(ctx, c_tiles, len(views), chans, self.num_levels, c_luts, len(luts), out_h,
+        if out is not None:
+            if not isinstance(out, np.ndarray) or out.shape != shape or out.dtype != np.uint8 or not out.flags.c_contiguous:
+                raise ValueError("out must be a C-contiguous uint8 array of the canvas shape")
+            canvas = out
+        else:
+            canvas = np.zeros(shape, np.uint8) if (r0, r1) != (0, out_h) else np.empty(shape, np.uint8)
+        rc = lib.srf_laplacian_fuse_host(ctx, c_tiles, len(views), chans, self.num_levels, c_luts, len(c_luts), out_h,
                                          out_w, canvas.ctypes.data, out_w * chans, r0, r1)
         _native.check(rc, ctx)
         return canvas
+
+    def fuse_and_assess(self, tiles, reference: np.ndarray, output_shape=None,
+                        weight_type: WeightType = WeightType.COSINE, data_range: float = 255.0, out=None):
+        """Host tiles -> (fused canvas, srf_iqa_sums of canvas vs `reference`) in one library call: stage 3 + stage 4
+        of the reference pipeline with the canvas kept on the device in between (include/srfuse.h:
+        srf_fuse_assess_host)."""
+        views, c_tiles, c_luts, keep, out_h, out_w, chans = self._marshal(tiles, output_shape, weight_type)
+        if views[0].on_device:
+            raise ValueError("fuse_and_assess takes host arrays; use laplacian_fusion + psnr_ssim_sums for CUDA tensors")
+        shape = (out_h, out_w) if views[0].keep.ndim == 2 else (out_h, out_w, chans)
+        ref = ImageView(reference, "reference")
+        if (ref.h, ref.w, ref.c) != (out_h, out_w, chans) or ref.on_device:
+            raise ValueError(f"reference must be a host image of the canvas shape {shape}")
+        if out is not None:
+            if not isinstance(out, np.ndarray) or out.shape != shape or out.dtype != np.uint8 or not out.flags.c_contiguous:
+                raise ValueError("out must be a C-contiguous uint8 array of the canvas shape")
+            canvas = out
+        else:
+            canvas = np.empty(shape, np.uint8)
+        sums = _native.srf_iqa_sums()
+        lib, ctx = _native.load(), self._ctx()
+        rc = lib.srf_fuse_assess_host(ctx, c_tiles, len(views), chans, self.num_levels, c_luts, len(c_luts), out_h, out_w,
+                                      canvas.ctypes.data, out_w * chans, ref.ptr, ref.pitch, float(data_range), C.byref(sums))
+        _native.check(rc, ctx)
+        return canvas, sums
 
     # ------------------------------------------------------------------ explicitly out of scope
     def _out_of_scope(self, name):

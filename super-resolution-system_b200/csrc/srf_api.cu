@@ -123,6 +123,7 @@ extern "C" int srf_create(int device, srf_ctx **out)
     SRF_CHECK_CUDA(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     SRF_CHECK_CUDA(c, cudaEventCreate(&c->ev0));
     SRF_CHECK_CUDA(c, cudaEventCreate(&c->ev1));
+    for (cudaEvent_t &e : c->ev_aux) SRF_CHECK_CUDA(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     *out = c;
     return SRF_OK;
 }
@@ -137,6 +138,8 @@ extern "C" void srf_destroy(srf_ctx *c)
         if (b->ptr) cudaFree(b->ptr);
     if (c->pinned) cudaFreeHost(c->pinned);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->ev_aux)
+        if (e) cudaEventDestroy(e);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -158,6 +161,39 @@ extern "C" size_t srf_workspace_bytes(const srf_ctx *c)
 {
     if (!c) return 0;
     return c->ws_pyr.bytes + c->ws_desc.bytes + c->ws_stage_in.bytes + c->ws_stage_out.bytes + c->ws_misc.bytes + c->ws_iqa.bytes;
+}
+
+extern "C" int srf_profile_enable(srf_ctx *c, int on)
+{
+    if (!c) return SRF_ERR_ARG;
+    c->profile = on != 0;
+    return SRF_OK;
+}
+
+extern "C" int srf_profile_read(srf_ctx *c, srf_profile_entry *out, int cap)
+{
+    if (!c) return SRF_ERR_ARG;
+    SRF_CHECK_CUDA(c, cudaSetDevice(c->device));
+    SRF_CHECK_CUDA(c, cudaDeviceSynchronize());
+    const int n = (int)c->prof.size();
+    for (int i = 0; i < n; ++i) {
+        srf_ctx::ProfRec &r = c->prof[i];
+        if (out && i < cap) {
+            memset(&out[i], 0, sizeof out[i]);
+            strncpy(out[i].name, r.name, sizeof(out[i].name) - 1);
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, r.e0, r.e1) != cudaSuccess) {
+                (void)cudaGetLastError();
+                ms = -1.f;
+            }
+            out[i].ms = ms;
+            out[i].bytes = r.bytes;
+        }
+        c->ev_pool.push_back(r.e0);
+        c->ev_pool.push_back(r.e1);
+    }
+    c->prof.clear();
+    return n;
 }
 
 extern "C" float srf_last_device_ms(srf_ctx *c)
@@ -313,11 +349,15 @@ extern "C" int srf_tile_extract_pad(srf_ctx *ctx, const uint8_t *d_src, int heig
     SRF_CHECK_CUDA(ctx, cudaMemcpyAsync(ctx->ws_desc.ptr, xywh, (size_t)n * sizeof(int4), cudaMemcpyHostToDevice, st));
     const int vec_ok = ((block * channels) % 16 == 0) && (((uintptr_t)d_out) % 16 == 0);
     dim3 grid(block, n);
-    if (channels == 3)
-        k_tile_extract_pad<3><<<grid, 256, 0, st>>>(d_src, pitch, (const int4 *)ctx->ws_desc.ptr, block, border, d_out, vec_ok);
-    else
-        k_tile_extract_pad<1><<<grid, 256, 0, st>>>(d_src, pitch, (const int4 *)ctx->ws_desc.ptr, block, border, d_out, vec_ok);
-    ctx->launches++;
+    {
+        double bytes = (double)n * block * block * channels;
+        for (int i = 0; i < n; ++i) bytes += (double)xywh[4 * i + 2] * xywh[4 * i + 3] * channels;
+        srf_launch_scope scope(ctx, "tile_extract_pad", bytes, st);
+        if (channels == 3)
+            k_tile_extract_pad<3><<<grid, 256, 0, st>>>(d_src, pitch, (const int4 *)ctx->ws_desc.ptr, block, border, d_out, vec_ok);
+        else
+            k_tile_extract_pad<1><<<grid, 256, 0, st>>>(d_src, pitch, (const int4 *)ctx->ws_desc.ptr, block, border, d_out, vec_ok);
+    }
     SRF_CHECK_CUDA(ctx, cudaGetLastError());
     return SRF_OK;
 }
@@ -403,8 +443,10 @@ int srf_launch_pyr_down_hwc(srf_ctx *ctx, const float *src, int h, int w, int cn
 {
     const int oh = (h + 1) / 2, ow = (w + 1) / 2;
     dim3 grid(srf_ceil_div(ow * cn, 256), oh);
-    k_pyr_down_hwc<<<grid, 256, 0, st>>>(src, h, w, cn, dst, oh, ow, srf_down_vec_end(w, ow, cn), 4 * ((ow * cn) / 4));
-    ctx->launches++;
+    {
+        srf_launch_scope scope(ctx, "pyr_down_hwc", 4.0 * cn * ((double)h * w + (double)oh * ow), st);
+        k_pyr_down_hwc<<<grid, 256, 0, st>>>(src, h, w, cn, dst, oh, ow, srf_down_vec_end(w, ow, cn), 4 * ((ow * cn) / 4));
+    }
     SRF_CHECK_CUDA(ctx, cudaGetLastError());
     return SRF_OK;
 }
@@ -412,8 +454,10 @@ int srf_launch_pyr_down_hwc(srf_ctx *ctx, const float *src, int h, int w, int cn
 int srf_launch_pyr_up_hwc(srf_ctx *ctx, const float *src, int h, int w, int cn, float *dst, int dh, int dw, cudaStream_t st)
 {
     dim3 grid(srf_ceil_div(dw * cn, 256), dh);
-    k_pyr_up_hwc<<<grid, 256, 0, st>>>(src, h, w, cn, dst, dh, dw);
-    ctx->launches++;
+    {
+        srf_launch_scope scope(ctx, "pyr_up_hwc", 4.0 * cn * ((double)h * w + (double)dh * dw), st);
+        k_pyr_up_hwc<<<grid, 256, 0, st>>>(src, h, w, cn, dst, dh, dw);
+    }
     SRF_CHECK_CUDA(ctx, cudaGetLastError());
     return SRF_OK;
 }

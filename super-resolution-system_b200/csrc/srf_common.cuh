@@ -53,8 +53,48 @@ struct srf_ctx {
     cudaStream_t own_stream = nullptr; // used by the *_host entry points
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev_aux[3] = {nullptr, nullptr, nullptr};
     bool ev_valid = false;
     std::vector<cudaEvent_t> ev_pool;
+    // per-kernel profiling (srf_profile_enable)
+    bool profile = false;
+    struct ProfRec {
+        const char *name;
+        cudaEvent_t e0, e1;
+        double bytes;
+    };
+    std::vector<ProfRec> prof;
+};
+
+// brackets one kernel launch with events when profiling is on; always counts the launch
+struct srf_launch_scope {
+    srf_ctx *ctx;
+    cudaStream_t st;
+    cudaEvent_t e1 = nullptr;
+    srf_launch_scope(srf_ctx *c, const char *name, double bytes, cudaStream_t s) : ctx(c), st(s)
+    {
+        ctx->launches++;
+        if (!ctx->profile) return;
+        cudaEvent_t e0;
+        auto get = [&]() {
+            cudaEvent_t e;
+            if (!ctx->ev_pool.empty()) {
+                e = ctx->ev_pool.back();
+                ctx->ev_pool.pop_back();
+            } else {
+                cudaEventCreate(&e);
+            }
+            return e;
+        };
+        e0 = get();
+        e1 = get();
+        cudaEventRecord(e0, st);
+        ctx->prof.push_back(srf_ctx::ProfRec{name, e0, e1, bytes});
+    }
+    ~srf_launch_scope()
+    {
+        if (e1) cudaEventRecord(e1, st);
+    }
 };
 
 void srf_set_error(srf_ctx *ctx, const char *fmt, ...);
@@ -141,3 +181,13 @@ __host__ __device__ __forceinline__ int srf_down_vec_end(int w, int ow, int cn)
 int srf_launch_pyr_down_hwc(srf_ctx *ctx, const float *src, int h, int w, int cn, float *dst, cudaStream_t st);
 int srf_launch_pyr_up_hwc(srf_ctx *ctx, const float *src, int h, int w, int cn, float *dst, int dh, int dw,
                           cudaStream_t st);
+
+// fusion of device-resident tiles into a device canvas (srf_fuse.cu) and the IQA pass over device images (srf_iqa.cu)
+int srf_fuse_device(srf_ctx *ctx, const srf_tile *tiles, int n_tiles, int C, int levels, const srf_weight_lut *luts, int n_luts, int out_h,
+                    int out_w, uint8_t *d_canvas, size_t canvas_pitch, int row_begin, int row_end, cudaStream_t st);
+int srf_check_fuse_args(srf_ctx *ctx, const srf_tile *tiles, int n_tiles, int C, int levels, const srf_weight_lut *luts, int n_luts,
+                        int out_h, int out_w, const void *canvas, size_t canvas_pitch, int row_begin, int row_end);
+// enqueue only: the sums land in ctx->pinned after the stream is synchronised; srf_iqa_collect converts them
+int srf_iqa_enqueue(srf_ctx *ctx, const uint8_t *a, size_t pa, const uint8_t *b, size_t pb, int h, int w, int C, int scale_a, int scale_b,
+                    double data_range, int row_begin, int row_end, cudaStream_t st);
+void srf_iqa_collect(srf_ctx *ctx, int w, int C, int row_begin, int row_end, srf_iqa_sums *out);

@@ -626,7 +626,7 @@ struct RowRange {
 
 } // namespace
 
-static int fuse_device(srf_ctx *ctx, const srf_tile *tiles, int n_tiles, int C, int levels, const srf_weight_lut *luts, int n_luts,
+int srf_fuse_device(srf_ctx *ctx, const srf_tile *tiles, int n_tiles, int C, int levels, const srf_weight_lut *luts, int n_luts,
                        int out_h, int out_w, uint8_t *d_canvas, size_t canvas_pitch, int row_begin, int row_end, cudaStream_t st)
 {
     // ---- group tiles by (h, w, lut) ----
@@ -804,38 +804,45 @@ static int fuse_device(srf_ctx *ctx, const srf_tile *tiles, int n_tiles, int C, 
         // weight pyramid (full planes; tiny next to the image work, and shared by the whole group)
         for (int l = 0; l + 1 < n; ++l) {
             dim3 grid(srf_ceil_div(gw.lv[l + 1].w, DN_BW), srf_ceil_div(gw.lv[l + 1].h, DN_BH), 1);
+            srf_launch_scope scope(ctx, "down_weight", 4.0 * ((l ? (double)gw.lv[l].h * gw.lv[l].w : 0.0) + (double)gw.lv[l + 1].h * gw.lv[l + 1].w), st);
             k_down_f32<true><<<grid, kThreads, 0, st>>>(d_tiles, ids_k, gw, l);
-            ctx->launches++;
         }
         // image pyramids, down
         if (n >= 2) {
             const int rows = max_rows(1, false);
             if (rows > 0) {
                 dim3 grid(srf_ceil_div(gi.lv[1].w, DN_BW), srf_ceil_div(rows, DN_BH), nt);
+                double px1 = 0; // level-1 pixels produced
+                for (int ti : groups[k].tiles) px1 += (double)(tdev[ti].g1[1] - tdev[ti].g0[1]) * gi.lv[1].w;
+                srf_launch_scope scope(ctx, "down_u8", px1 * C * (4.0 /*u8 in*/ + 4.0 /*f32 out*/), st);
                 if (C == 3)
                     k_down_u8<3><<<grid, kThreads, 0, st>>>(d_tiles, ids_k, gi);
                 else
                     k_down_u8<1><<<grid, kThreads, 0, st>>>(d_tiles, ids_k, gi);
-                ctx->launches++;
             }
         }
         for (int l = 1; l + 1 < n; ++l) {
             const int rows = max_rows(l + 1, false);
             if (rows <= 0) continue;
             dim3 grid(srf_ceil_div(gi.lv[l + 1].w, DN_BW), srf_ceil_div(rows, DN_BH), nt * C);
+            double pxo = 0;
+            for (int ti : groups[k].tiles) pxo += (double)(tdev[ti].g1[l + 1] - tdev[ti].g0[l + 1]) * gi.lv[l + 1].w;
+            srf_launch_scope scope(ctx, "down_f32", pxo * C * (16.0 + 4.0), st);
             k_down_f32<false><<<grid, kThreads, 0, st>>>(d_tiles, ids_k, gi, l);
-            ctx->launches++;
         }
         // up: l = n-2 .. 1
         for (int l = n - 2; l >= 1; --l) {
             const int rows = max_rows(l, true);
             if (rows <= 0) continue;
             dim3 grid(srf_ceil_div(gi.lv[l].w, UP_BW), srf_ceil_div(rows, UP_BH), nt * C);
+            double pxo = 0;
+            for (int ti : groups[k].tiles) pxo += (double)(tdev[ti].c1[l] - tdev[ti].c0[l]) * gi.lv[l].w;
+            // per output element: G_l + W_l/C read, C_l written, C_{l+1} (or W_{l+1}/C) + G_{l+1} at quarter density
+            srf_launch_scope scope(ctx, "up_level", pxo * C * (4.0 + 4.0 / C + 4.0 + 2.0), st);
             if (l == n - 2)
                 k_up_level<true><<<grid, kThreads, 0, st>>>(d_tiles, ids_k, gi, l);
             else
                 k_up_level<false><<<grid, kThreads, 0, st>>>(d_tiles, ids_k, gi, l);
-            ctx->launches++;
         }
     }
     SRF_CHECK_CUDA(ctx, cudaGetLastError());
@@ -855,6 +862,14 @@ static int fuse_device(srf_ctx *ctx, const srf_tile *tiles, int n_tiles, int C, 
         P.row_begin = rb;
         P.row_end = re;
         dim3 grid(srf_ceil_div(out_w, UP_BW), srf_ceil_div(re - rb, UP_BH), 1);
+        double cov = 0; // tile pixels inside the band
+        for (int i = 0; i < n_tiles; ++i) {
+            const int a = std::max(rb, tiles[i].y), b = std::min(re, tiles[i].y + tiles[i].h);
+            const int c0 = std::max(0, tiles[i].x), c1 = std::min(out_w, tiles[i].x + tiles[i].w);
+            if (a < b && c0 < c1) cov += (double)(b - a) * (c1 - c0);
+        }
+        // per covered tile pixel: u8 in + C_1, G_1 at quarter density; per canvas pixel: u8 out
+        srf_launch_scope scope(ctx, "final_gather", cov * C * (1.0 + 2.0) + (double)(re - rb) * out_w * C, st);
         if (C == 3) {
             const size_t sm = sizeof(FinalSmem<3>);
             SRF_CHECK_CUDA(ctx, cudaFuncSetAttribute(k_final<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
@@ -864,13 +879,12 @@ static int fuse_device(srf_ctx *ctx, const srf_tile *tiles, int n_tiles, int C, 
             SRF_CHECK_CUDA(ctx, cudaFuncSetAttribute(k_final<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
             k_final<1><<<grid, kThreads, sm, st>>>(P);
         }
-        ctx->launches++;
         SRF_CHECK_CUDA(ctx, cudaGetLastError());
     }
     return SRF_OK;
 }
 
-static int check_fuse_args(srf_ctx *ctx, const srf_tile *tiles, int n_tiles, int C, int levels, const srf_weight_lut *luts, int n_luts,
+int srf_check_fuse_args(srf_ctx *ctx, const srf_tile *tiles, int n_tiles, int C, int levels, const srf_weight_lut *luts, int n_luts,
                            int out_h, int out_w, const void *canvas, size_t canvas_pitch, int row_begin, int row_end)
 {
     SRF_REQUIRE(ctx, tiles && n_tiles >= 1, "laplacian_fuse: no tiles");
@@ -898,7 +912,7 @@ extern "C" int srf_laplacian_fuse(srf_ctx *ctx, const srf_tile *tiles, int n_til
                                   void *stream)
 {
     if (!ctx) return SRF_ERR_ARG;
-    int rc = check_fuse_args(ctx, tiles, n_tiles, channels, levels, luts, n_luts, out_h, out_w, d_canvas, canvas_pitch, row_begin, row_end);
+    int rc = srf_check_fuse_args(ctx, tiles, n_tiles, channels, levels, luts, n_luts, out_h, out_w, d_canvas, canvas_pitch, row_begin, row_end);
     if (rc) return rc;
     for (int i = 0; i < n_tiles; ++i)
         SRF_REQUIRE(ctx, ((uintptr_t)tiles[i].data % 16 == 0) && (tiles[i].pitch % 16 == 0 || tiles[i].h == 1),
@@ -907,7 +921,7 @@ extern "C" int srf_laplacian_fuse(srf_ctx *ctx, const srf_tile *tiles, int n_til
     SRF_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
     SRF_CHECK_CUDA(ctx, cudaEventRecord(ctx->ev0, st));
-    rc = fuse_device(ctx, tiles, n_tiles, channels, levels, luts, n_luts, out_h, out_w, d_canvas, canvas_pitch, row_begin, row_end, st);
+    rc = srf_fuse_device(ctx, tiles, n_tiles, channels, levels, luts, n_luts, out_h, out_w, d_canvas, canvas_pitch, row_begin, row_end, st);
     if (rc) return rc;
     SRF_CHECK_CUDA(ctx, cudaEventRecord(ctx->ev1, st));
     ctx->ev_valid = true;
@@ -919,7 +933,7 @@ extern "C" int srf_laplacian_fuse_host(srf_ctx *ctx, const srf_tile *tiles, int 
                                        int row_begin, int row_end)
 {
     if (!ctx) return SRF_ERR_ARG;
-    int rc = check_fuse_args(ctx, tiles, n_tiles, channels, levels, luts, n_luts, out_h, out_w, h_canvas, canvas_pitch, row_begin, row_end);
+    int rc = srf_check_fuse_args(ctx, tiles, n_tiles, channels, levels, luts, n_luts, out_h, out_w, h_canvas, canvas_pitch, row_begin, row_end);
     if (rc) return rc;
     SRF_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
     // device staging: every tile at a 256-byte aligned offset with a 16-byte-multiple pitch, then the canvas band
@@ -946,7 +960,7 @@ extern "C" int srf_laplacian_fuse_host(srf_ctx *ctx, const srf_tile *tiles, int 
     SRF_CHECK_CUDA(ctx, cudaEventRecord(ctx->ev0, st));
     // the staged canvas holds only the band: shift the base so canvas row `row_begin` lands on staged row 0
     uint8_t *dcanvas = (uint8_t *)ctx->ws_stage_out.ptr - (size_t)row_begin * cpitch;
-    rc = fuse_device(ctx, dt.data(), n_tiles, channels, levels, luts, n_luts, out_h, out_w, dcanvas, cpitch, row_begin, row_end, st);
+    rc = srf_fuse_device(ctx, dt.data(), n_tiles, channels, levels, luts, n_luts, out_h, out_w, dcanvas, cpitch, row_begin, row_end, st);
     if (rc) return rc;
     SRF_CHECK_CUDA(ctx, cudaEventRecord(ctx->ev1, st));
     ctx->ev_valid = true;

@@ -286,8 +286,8 @@ __global__ void __launch_bounds__(256) k_iqa_reduce(const IqaPartial *__restrict
 
 } // namespace
 
-static int iqa_device(srf_ctx *ctx, const uint8_t *a, size_t pa, const uint8_t *b, size_t pb, int h, int w, int C, int scale_a, int scale_b,
-                      double data_range, int row_begin, int row_end, srf_iqa_sums *out, cudaStream_t st, bool record_events)
+int srf_iqa_enqueue(srf_ctx *ctx, const uint8_t *a, size_t pa, const uint8_t *b, size_t pb, int h, int w, int C, int scale_a, int scale_b,
+                    double data_range, int row_begin, int row_end, cudaStream_t st)
 {
     int rc;
     const int gx = srf_ceil_div(w, IQ_THREADS), gy = srf_ceil_div(row_end - row_begin, IQ_RB);
@@ -310,24 +310,25 @@ static int iqa_device(srf_ctx *ctx, const uint8_t *a, size_t pa, const uint8_t *
     P.row_begin = row_begin;
     P.row_end = row_end;
     P.partials = parts;
-    if (record_events) SRF_CHECK_CUDA(ctx, cudaEventRecord(ctx->ev0, st));
     if (nparts > 0) {
         dim3 grid(gx, gy);
+        srf_launch_scope scope(ctx, "psnr_ssim", 2.0 * (double)(row_end - row_begin) * w * C, st);
         if (C == 3)
             k_psnr_ssim<3><<<grid, IQ_THREADS, 0, st>>>(P);
         else
             k_psnr_ssim<1><<<grid, IQ_THREADS, 0, st>>>(P);
-        ctx->launches++;
     }
-    k_iqa_reduce<<<1, 256, 0, st>>>(parts, (int)nparts, final_d);
-    ctx->launches++;
+    {
+        srf_launch_scope scope(ctx, "iqa_reduce", 0.0, st);
+        k_iqa_reduce<<<1, 256, 0, st>>>(parts, (int)nparts, final_d);
+    }
     SRF_CHECK_CUDA(ctx, cudaGetLastError());
-    if (record_events) {
-        SRF_CHECK_CUDA(ctx, cudaEventRecord(ctx->ev1, st));
-        ctx->ev_valid = true;
-    }
     SRF_CHECK_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, final_d, sizeof(IqaPartial), cudaMemcpyDeviceToHost, st));
-    SRF_CHECK_CUDA(ctx, cudaStreamSynchronize(st));
+    return SRF_OK;
+}
+
+void srf_iqa_collect(srf_ctx *ctx, int w, int C, int row_begin, int row_end, srf_iqa_sums *out)
+{
     const IqaPartial *f = (const IqaPartial *)ctx->pinned;
     out->sq_err = (int64_t)f->sq;
     out->n_elems = (int64_t)(row_end - row_begin) * w * C;
@@ -335,6 +336,20 @@ static int iqa_device(srf_ctx *ctx, const uint8_t *a, size_t pa, const uint8_t *
     out->ssim_count = (int64_t)f->cnt;
     out->max_a = f->max_a;
     out->max_b = f->max_b;
+}
+
+static int iqa_device(srf_ctx *ctx, const uint8_t *a, size_t pa, const uint8_t *b, size_t pb, int h, int w, int C, int scale_a, int scale_b,
+                      double data_range, int row_begin, int row_end, srf_iqa_sums *out, cudaStream_t st, bool record_events)
+{
+    if (record_events) SRF_CHECK_CUDA(ctx, cudaEventRecord(ctx->ev0, st));
+    int rc = srf_iqa_enqueue(ctx, a, pa, b, pb, h, w, C, scale_a, scale_b, data_range, row_begin, row_end, st);
+    if (rc) return rc;
+    if (record_events) {
+        SRF_CHECK_CUDA(ctx, cudaEventRecord(ctx->ev1, st));
+        ctx->ev_valid = true;
+    }
+    SRF_CHECK_CUDA(ctx, cudaStreamSynchronize(st));
+    srf_iqa_collect(ctx, w, C, row_begin, row_end, out);
     return SRF_OK;
 }
 

@@ -114,12 +114,27 @@ class SuperResolutionPipeline:
             up = self.upscaler(t.data, (out, out))
             infos.append(TileInfo(up, 2 * m.global_x, 2 * m.global_y, m.global_y // step, m.global_x // step))
         canvas_hw = (2 * half.shape[0], 2 * half.shape[1])
-        canvas = self.blending_module.laplacian_fusion(infos, output_shape=canvas_hw)
-        report = None
         if cfg.enable_qa:
             ref = reference if reference is not None else bicubic_stub(image, canvas_hw)
-            report = self.quality_module.evaluate_full_reference(ref, canvas, scale_factor=2)
+            canvas, report = self.fuse_and_assess(infos, ref, canvas_hw)
+        else:
+            canvas, report = self.blending_module.laplacian_fusion(infos, output_shape=canvas_hw), None
         return {"canvas": canvas, "report": report, "tiles": len(tiles)}
+
+    def fuse_and_assess(self, tile_infos: List[TileInfo], reference: np.ndarray, output_shape=None, out=None):
+        """stages 3 + 4 in one device round trip: fused canvas + the full-reference report against `reference`"""
+        canvas, sums = self.blending_module.fuse_and_assess(tile_infos, np.ascontiguousarray(reference), output_shape, out=out)
+        if sums.max_a <= 1 or sums.max_b <= 1:  # the reference's max() <= 1 rescale rule: take the two-pass route
+            return canvas, self.quality_module.evaluate_full_reference(reference, canvas, scale_factor=2)
+        if sums.ssim_count <= 0:
+            raise ValueError("canvas smaller than the 11x11 SSIM window")
+        qm = self.quality_module
+        psnr, ssim = qm.finish(sums)
+        report = {"psnr": float(psnr), "ms_ssim": float(ssim)}
+        report["psnr_level"] = qm._assess_psnr(report["psnr"])
+        report["ssim_level"] = qm._assess_ssim(report["ms_ssim"])
+        report["overall_score"] = qm._calculate_overall_score(report)
+        return canvas, report
 
     async def process(self, input_path: str, output_path: str, prompt: str = "",
                       roi_regions: Optional[List[Dict]] = None) -> PipelineResult:

@@ -243,7 +243,7 @@ def test_iqa_bands_add_up(srs):
         s = qa.psnr_ssim_sums(a, b, row_range=(r0, r1))
         sq, cnt, ss = sq + s.sq_err, cnt + s.ssim_count, ss + s.ssim_sum
     assert sq == full.sq_err and cnt == full.ssim_count
-    assert ss == pytest.approx(full.ssim_sum, rel=1e-9)
+    assert ss == pytest.approx(full.ssim_sum, rel=1e-7)  # float32 per-thread partial sums regroup with the band split
 
 
 def test_iqa_device_path_and_evaluate(srs, oracle):

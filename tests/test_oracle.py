@@ -116,3 +116,13 @@ def test_iqa_preprocess_rule(oracle):
     assert io.preprocess(np.full((4, 4), 0.5)).dtype == np.uint8
     with pytest.raises(ValueError):
         io.ssim(np.zeros((8, 30), np.uint8), np.zeros((8, 30), np.uint8))
+
+
+def test_reference_port_equals_oracle(golden, oracle):
+    """the cost-faithful port timed as the CPU baseline computes exactly what the oracle computes"""
+    for name in ("grid", "ragged"):
+        tiles, pos, out_hw, levels, kind, want = fuse_case(golden, name)
+        for threads in (1, 3):
+            assert np.array_equal(oracle.reference_port.laplacian_fuse(tiles, pos, out_hw, levels, kind, threads), want)
+    a, b = golden["iqa_a"], golden["iqa_b"]
+    assert oracle.reference_port.ssim(a, b) == pytest.approx(oracle.iqa_oracle.ssim(a, b), rel=1e-12)
