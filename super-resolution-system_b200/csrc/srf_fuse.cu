@@ -401,20 +401,27 @@ __global__ void __launch_bounds__(kThreads) k_up_level(const TileDev *__restrict
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// k_final: one CTA per 32 x 64 canvas block.  Per covering tile (list order = the reference's accumulation order):
-// stage C_1/G_1 source windows and the uint8 tile block, horizontal pyrUp into smem, then each thread finishes
-// its 2 x 4 pixels x C channels in registers.  MODE: 0 = tiles have >= 3 levels (C_1 stored), 1 = exactly 2 levels
-// (C_1 = G_1 * W_1 on the fly), 2 = single level (C_0 = G_0 * W_0, no pyramid at all).
+// k_final: canvas gather.  One CTA per 256 x 16 canvas block, 128*C threads: thread (p, c) owns canvas columns
+// cx0+2p, cx0+2p+1 of channel c for all 16 rows -- 32 accumulators in registers; the sum of W_0 lives in smem.
+// Per covering tile (list order = the reference's accumulation order) the CTA stages the C_1 / G_1 source windows
+// (<= 11 rows x 136 cols per channel) and the uint8 tile block, then every thread slides DOWN the rows with a
+// 3-row register ring of horizontally up-sampled values: one new source row per canvas row pair, 3 LDS per array
+// for two columns, vertical pass + Laplacian weighting + accumulation straight from registers.
+// Tile origins of either parity are handled by shifting the window (xpar / ypar are uniform per CTA and tile).
+// MODE per tile: 0 = >= 3 levels (C_1 stored), 1 = exactly 2 levels (C_1 = G_1 * W_1 on the fly), 2 = single level
+// (C_0 = G_0 * W_0, no pyramid).
 // ------------------------------------------------------------------------------------------------------------
-constexpr int FN_U8_STRIDE = UP_BW * 3 + 32; // staged uint8 row: 192 payload bytes + 16 B misalignment + slack
+constexpr int FB_W = 256, FB_H = 16, FB_PAIRS = FB_W / 2, FB_STEPS = FB_H / 2;
+constexpr int FB_SRC_ROWS = FB_STEPS + 3;   // 11
+constexpr int FB_SRC_COLS = FB_PAIRS + 8;   // 136
+constexpr int FB_U8_STRIDE = FB_W * 3 + 32; // 800: payload + 16 B misalignment + slack
 
 template <int C>
 struct FinalSmem {
-    float sc[C][UP_SRC_ROWS][UP_SRC_COLS];
-    float sg[C][UP_SRC_ROWS][UP_SRC_COLS];
-    float hc[C][UP_SRC_ROWS][UP_BW];
-    float hg[C][UP_SRC_ROWS][UP_BW];
-    uint8_t u8[UP_BH][FN_U8_STRIDE];
+    float sc[C][FB_SRC_ROWS][FB_SRC_COLS];
+    float sg[C][FB_SRC_ROWS][FB_SRC_COLS];
+    float wsum[FB_H][FB_W];
+    uint8_t u8[FB_H][FB_U8_STRIDE];
 };
 
 struct FinalParams {
@@ -428,134 +435,193 @@ struct FinalParams {
     int row_begin, row_end;
 };
 
+struct HPair {
+    float a, b; // horizontally up-sampled values (x8, un-normalised) for the thread's two columns
+};
+
+// horizontal pass for the thread's column pair from source samples s0,s1,s2 = s[i0+p .. i0+p+2] (interior form)
+__device__ __forceinline__ HPair h_pair_fast(float s0, float s1, float s2, int xpar)
+{
+    HPair r;
+    if (xpar == 0) { // columns (2i, 2i+1), i = window centre
+        r.a = up_even(s0, s1, s2);
+        r.b = up_odd(s1, s2);
+    } else {         // columns (2i+1, 2i+2), i = window start
+        r.a = up_odd(s0, s1);
+        r.b = up_even(s0, s1, s2);
+    }
+    return r;
+}
+
 template <int C>
-__global__ void __launch_bounds__(kThreads) k_final(FinalParams P)
+__global__ void __launch_bounds__(128 * C, (C == 3) ? 2 : 5) k_final(FinalParams P)
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     FinalSmem<C> &S = *reinterpret_cast<FinalSmem<C> *>(smem_raw);
+    constexpr int NT = 128 * C;
 
-    const int cy0 = P.row_begin + blockIdx.y * UP_BH;
-    const int cx0 = blockIdx.x * UP_BW;
-    const int cy1 = min(cy0 + UP_BH, P.row_end);
-    const int cx1 = min(cx0 + UP_BW, P.out_w);
-    const int cg = threadIdx.x & 15; // 4-pixel column group
-    const int rp = threadIdx.x >> 4; // row pair
-    float acc[2][4][C];
-    float wacc[2][4];
+    const int cy0 = P.row_begin + blockIdx.y * FB_H;
+    const int cx0 = blockIdx.x * FB_W;
+    const int cy1 = min(cy0 + FB_H, P.row_end);
+    const int cx1 = min(cx0 + FB_W, P.out_w);
+    const int c = threadIdx.x / FB_PAIRS; // warp-uniform
+    const int p = threadIdx.x % FB_PAIRS;
+
+    float acc[FB_STEPS][2][2];
 #pragma unroll
-    for (int a = 0; a < 2; ++a)
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-            wacc[a][b] = 0.f;
-#pragma unroll
-            for (int c = 0; c < C; ++c) acc[a][b][c] = 0.f;
-        }
+    for (int k = 0; k < FB_STEPS; ++k) acc[k][0][0] = acc[k][0][1] = acc[k][1][0] = acc[k][1][1] = 0.f;
+    for (int i = threadIdx.x; i < FB_H * FB_W; i += NT) (&S.wsum[0][0])[i] = 0.f;
 
     for (int ti = 0; ti < P.n_tiles; ++ti) {
         const TileDev &t = P.tiles[ti];
-        // intersection of this block with the tile, in canvas coordinates (uniform across the CTA)
         const int iy0 = max(cy0, t.y), iy1 = min(cy1, t.y + t.h);
         const int ix0 = max(cx0, t.x), ix1 = min(cx1, t.x + t.w);
-        if (iy0 >= iy1 || ix0 >= ix1) continue;
+        if (iy0 >= iy1 || ix0 >= ix1) continue; // uniform across the CTA
         const GroupDev &g = P.groups[P.tile_group[ti]];
         const int mode = (g.n_levels >= 3) ? 0 : (g.n_levels == 2 ? 1 : 2);
-        const int ty0 = iy0 - t.y, ty1 = iy1 - t.y, tx0 = ix0 - t.x, tx1 = ix1 - t.x;
         const LevelGeom L1 = g.lv[1];
-        SrcWin sw;
-        sw.jb = 0; sw.nrows = 0; sw.ib = 0;
-        __syncthreads(); // previous tile's smem fully consumed
+        const int h1 = L1.h, w1 = L1.w;
+        const int tyf = cy0 - t.y, txf = cx0 - t.x; // tile coordinates of the block origin (may be negative)
+        const int xpar = txf & 1, ypar = tyf & 1;
+        const int i0 = (txf >> 1) - (1 - xpar); // window start column for pair 0
+        const int ws0 = (tyf >> 1) - (1 - ypar); // window start row for step 0
+        // staged source window
+        const int sx0 = max(i0, 0) & ~3;
+        const int srow0 = max(min(ws0, h1 - 1), 0);
+        const int srow1 = max(min(ws0 + FB_STEPS + 1, h1 - 1), 0);
+        const int n_srows = srow1 - srow0 + 1; // <= 10
+        __syncthreads(); // everyone is done with the previous tile's smem (and wsum is initialised)
 
-        // ---- stage the uint8 tile block (congruent 16-byte chunks) ----
-        const int u8_bytes = (tx1 - tx0) * C;
-        for (int i = threadIdx.x; i < (iy1 - iy0) * (FN_U8_STRIDE / 16); i += kThreads) {
-            const int r = i / (FN_U8_STRIDE / 16), ch = i - r * (FN_U8_STRIDE / 16);
-            const uint8_t *grow = t.src + (size_t)(ty0 + r) * t.pitch;
-            const int first = tx0 * C;
-            const int a0 = first & ~15;
-            if (a0 + ch * 16 < first + u8_bytes) stage_u8_chunk(&S.u8[r][0], grow, a0, ch, t.w * C);
+        // ---- stage the uint8 tile block: rows iy0..iy1, bytes congruent mod 16 with the tile rows ----
+        const int u8_first = (ix0 - t.x) * C;
+        const int u8_a0 = u8_first & ~15;
+        const int u8_chunks = ((ix1 - t.x) * C - u8_a0 + 15) >> 4;
+        for (int i = threadIdx.x; i < (iy1 - iy0) * u8_chunks; i += NT) {
+            const int r = i / u8_chunks, ch = i - r * u8_chunks;
+            const uint8_t *grow = t.src + (size_t)(iy0 - t.y + r) * t.pitch;
+            stage_u8_chunk(&S.u8[iy0 - cy0 + r][0], grow, u8_a0, ch, t.w * C);
         }
         if (mode != 2) {
-            sw = src_window(ty0, ty1, tx0, L1.h);
-            for (int i = threadIdx.x; i < C * sw.nrows * (UP_SRC_COLS / 4); i += kThreads) {
-                const int ch = i % (UP_SRC_COLS / 4);
-                const int r = (i / (UP_SRC_COLS / 4)) % sw.nrows;
-                const int c = i / ((UP_SRC_COLS / 4) * sw.nrows);
-                const int gy = sw.jb + r, c0 = sw.ib + ch * 4;
-                const float4 gv = load_f32_chunk(t.G[1] + (size_t)c * L1.plane + (size_t)gy * L1.pitch, c0, L1.w);
+            for (int i = threadIdx.x; i < C * n_srows * (FB_SRC_COLS / 4); i += NT) {
+                const int ch = i % (FB_SRC_COLS / 4);
+                const int r = (i / (FB_SRC_COLS / 4)) % n_srows;
+                const int cc = i / ((FB_SRC_COLS / 4) * n_srows);
+                const int gy = srow0 + r, c0 = sx0 + ch * 4;
+                const float4 gv = load_f32_chunk(t.G[1] + (size_t)cc * L1.plane + (size_t)gy * L1.pitch, c0, w1);
                 float4 cv;
                 if (mode == 1) {
-                    const float4 wv = load_f32_chunk(g.W[1] + (size_t)gy * L1.pitch, c0, L1.w);
+                    const float4 wv = load_f32_chunk(g.W[1] + (size_t)gy * L1.pitch, c0, w1);
                     cv = make_float4(__fmul_rn(gv.x, wv.x), __fmul_rn(gv.y, wv.y), __fmul_rn(gv.z, wv.z), __fmul_rn(gv.w, wv.w));
                 } else {
-                    cv = load_f32_chunk(t.C[1] + (size_t)c * L1.plane + (size_t)gy * L1.pitch, c0, L1.w);
+                    cv = load_f32_chunk(t.C[1] + (size_t)cc * L1.plane + (size_t)gy * L1.pitch, c0, w1);
                 }
-                *reinterpret_cast<float4 *>(&S.sg[c][r][ch * 4]) = gv;
-                *reinterpret_cast<float4 *>(&S.sc[c][r][ch * 4]) = cv;
+                *reinterpret_cast<float4 *>(&S.sg[cc][r][ch * 4]) = gv;
+                *reinterpret_cast<float4 *>(&S.sc[cc][r][ch * 4]) = cv;
             }
         }
         __syncthreads();
 
-        // ---- horizontal pyrUp of the staged rows, for the columns this block covers ----
-        if (mode != 2) {
-            const int ncols = tx1 - tx0;
-            for (int i = threadIdx.x; i < C * sw.nrows * UP_BW; i += kThreads) {
-                const int x = i % UP_BW;
-                const int r = (i / UP_BW) % sw.nrows;
-                const int c = i / (UP_BW * sw.nrows);
-                if (x >= ncols) continue;
-                const int tx = tx0 + x;
-                const float *rc = &S.sc[c][r][0] - sw.ib;
-                const float *rg = &S.sg[c][r][0] - sw.ib;
-                S.hc[c][r][x] = up_h_sample(tx, L1.w, [&](int ii) { return rc[ii]; });
-                S.hg[c][r][x] = up_h_sample(tx, L1.w, [&](int ii) { return rg[ii]; });
+        // ---- per-thread geometry for this tile ----
+        const int txa = txf + 2 * p, txb = txa + 1; // tile columns of the thread's two canvas columns
+        const bool ina = (txa >= 0) && (txa < t.w) && (cx0 + 2 * p < cx1);
+        const bool inb = (txb >= 0) && (txb < t.w) && (cx0 + 2 * p + 1 < cx1);
+        const int lmax = g.lut_len - 1;
+        const int dxa = min(min(txa, t.w - 1 - txa), lmax), dxb = min(min(txb, t.w - 1 - txb), lmax);
+        const int u8_col = txa * C + c - u8_a0; // byte offset of (txa, c) inside a staged row
+        // horizontal fast path: the whole 130-sample window of this CTA lies strictly inside the source row
+        const bool hfast = (i0 >= 0) && (i0 + FB_PAIRS + 1 <= w1 - 1) && (w1 > 1);
+        const int scol = i0 + p - sx0; // smem column of s0
+
+        auto hrow = [&](int r_logical, HPair &oc, HPair &og) {
+            int r = (r_logical == -1) ? min(1, h1 - 1) : max(min(r_logical, h1 - 1), 0);
+            r -= srow0;
+            r = max(min(r, n_srows - 1), 0);
+            const float *rc = &S.sc[c][r][0];
+            const float *rg = &S.sg[c][r][0];
+            if (hfast) {
+                oc = h_pair_fast(rc[scol], rc[scol + 1], rc[scol + 2], xpar);
+                og = h_pair_fast(rg[scol], rg[scol + 1], rg[scol + 2], xpar);
+            } else {
+                oc.a = oc.b = og.a = og.b = 0.f;
+                if (ina) {
+                    oc.a = up_h_sample(txa, w1, [&](int ii) { return rc[ii - sx0]; });
+                    og.a = up_h_sample(txa, w1, [&](int ii) { return rg[ii - sx0]; });
+                }
+                if (inb) {
+                    oc.b = up_h_sample(txb, w1, [&](int ii) { return rc[ii - sx0]; });
+                    og.b = up_h_sample(txb, w1, [&](int ii) { return rg[ii - sx0]; });
+                }
             }
-            __syncthreads();
+        };
+
+        if (mode == 2) {
+#pragma unroll
+            for (int k = 0; k < FB_STEPS; ++k) {
+#pragma unroll
+                for (int a = 0; a < 2; ++a) {
+                    const int cy = cy0 + 2 * k + a;
+                    if (cy < iy0 || cy >= iy1) continue;
+                    const int ty = cy - t.y;
+                    const int dy = min(min(ty, t.h - 1 - ty), lmax);
+                    const uint8_t *px = &S.u8[2 * k + a][u8_col];
+                    if (ina) {
+                        const float w0 = __ldg(g.lut + min(dy, dxa));
+                        acc[k][a][0] = __fadd_rn(acc[k][a][0], __fmul_rn((float)px[0], w0));
+                        if (c == 0) S.wsum[2 * k + a][2 * p] = __fadd_rn(S.wsum[2 * k + a][2 * p], w0);
+                    }
+                    if (inb) {
+                        const float w0 = __ldg(g.lut + min(dy, dxb));
+                        acc[k][a][1] = __fadd_rn(acc[k][a][1], __fmul_rn((float)px[C], w0));
+                        if (c == 0) S.wsum[2 * k + a][2 * p + 1] = __fadd_rn(S.wsum[2 * k + a][2 * p + 1], w0);
+                    }
+                }
+            }
+            continue;
         }
 
-        // ---- vertical pyrUp + Laplacian weighting + accumulation, 2 x 4 pixels per thread ----
-        const int u8_off = (tx0 * C) & 15;
+        HPair rc0, rg0, rc1, rg1, rc2, rg2; // ring: logical rows ws0+k, ws0+k+1, ws0+k+2
+        hrow(ws0, rc0, rg0);
+        hrow(ws0 + 1, rc1, rg1);
 #pragma unroll
-        for (int a = 0; a < 2; ++a) {
-            const int cy = cy0 + rp * 2 + a;
-            if (cy < iy0 || cy >= iy1) continue;
-            const int ty = cy - t.y;
-            const int j = ty >> 1;
-            int rj = 0, rm = 0, rn = 0;
-            if (mode != 2) {
-                rj = j - sw.jb;
-                rm = srf_reflect101(j - 1, L1.h) - sw.jb;
-                rn = min(j + 1, L1.h - 1) - sw.jb;
+        for (int k = 0; k < FB_STEPS; ++k) {
+            hrow(ws0 + k + 2, rc2, rg2);
+            // vertical pass for canvas rows cy0+2k (a=0) and cy0+2k+1 (a=1)
+            float uc[2][2], ug[2][2];
+            if (ypar == 0) { // tile rows (2j, 2j+1), j = ws0+k+1: even uses (m,p,n), odd uses (p,n)
+                uc[0][0] = up_even(rc0.a, rc1.a, rc2.a); uc[0][1] = up_even(rc0.b, rc1.b, rc2.b);
+                ug[0][0] = up_even(rg0.a, rg1.a, rg2.a); ug[0][1] = up_even(rg0.b, rg1.b, rg2.b);
+                uc[1][0] = up_odd(rc1.a, rc2.a); uc[1][1] = up_odd(rc1.b, rc2.b);
+                ug[1][0] = up_odd(rg1.a, rg2.a); ug[1][1] = up_odd(rg1.b, rg2.b);
+            } else {         // tile rows (2j+1, 2j+2), j = ws0+k: odd uses (p,n) = ring 0,1; even uses ring 0,1,2
+                uc[0][0] = up_odd(rc0.a, rc1.a); uc[0][1] = up_odd(rc0.b, rc1.b);
+                ug[0][0] = up_odd(rg0.a, rg1.a); ug[0][1] = up_odd(rg0.b, rg1.b);
+                uc[1][0] = up_even(rc0.a, rc1.a, rc2.a); uc[1][1] = up_even(rc0.b, rc1.b, rc2.b);
+                ug[1][0] = up_even(rg0.a, rg1.a, rg2.a); ug[1][1] = up_even(rg0.b, rg1.b, rg2.b);
             }
 #pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                const int cx = cx0 + cg * 4 + b;
-                if (cx < ix0 || cx >= ix1) continue;
-                const int tx = cx - t.x;
-                const int x = tx - tx0; // column inside hc/hg and the u8 block
-                const float w0 = lut_weight(g.lut, g.lut_len, ty, tx, t.h, t.w);
-                const uint8_t *px = &S.u8[ty - ty0][u8_off + x * C];
-#pragma unroll
-                for (int c = 0; c < C; ++c) {
-                    const float g0 = (float)px[c];
-                    float c0v;
-                    if (mode == 2) {
-                        c0v = __fmul_rn(g0, w0);
-                    } else {
-                        float uc, ug;
-                        if (ty & 1) {
-                            uc = up_odd(S.hc[c][rj][x], S.hc[c][rn][x]);
-                            ug = up_odd(S.hg[c][rj][x], S.hg[c][rn][x]);
-                        } else {
-                            uc = up_even(S.hc[c][rm][x], S.hc[c][rj][x], S.hc[c][rn][x]);
-                            ug = up_even(S.hg[c][rm][x], S.hg[c][rj][x], S.hg[c][rn][x]);
-                        }
-                        const float upc = __fmul_rn(uc, 1.f / 64.f), upg = __fmul_rn(ug, 1.f / 64.f);
-                        c0v = __fadd_rn(upc, __fmul_rn(__fsub_rn(g0, upg), w0));
+            for (int a = 0; a < 2; ++a) {
+                const int cy = cy0 + 2 * k + a;
+                if (cy >= iy0 && cy < iy1) {
+                    const int ty = cy - t.y;
+                    const int dy = min(min(ty, t.h - 1 - ty), lmax);
+                    const uint8_t *px = &S.u8[2 * k + a][u8_col];
+                    if (ina) {
+                        const float w0 = __ldg(g.lut + min(dy, dxa));
+                        const float upc = __fmul_rn(uc[a][0], 1.f / 64.f), upg = __fmul_rn(ug[a][0], 1.f / 64.f);
+                        const float v = __fadd_rn(upc, __fmul_rn(__fsub_rn((float)px[0], upg), w0));
+                        acc[k][a][0] = __fadd_rn(acc[k][a][0], v);
+                        if (c == 0) S.wsum[2 * k + a][2 * p] = __fadd_rn(S.wsum[2 * k + a][2 * p], w0);
                     }
-                    acc[a][b][c] = __fadd_rn(acc[a][b][c], c0v);
+                    if (inb) {
+                        const float w0 = __ldg(g.lut + min(dy, dxb));
+                        const float upc = __fmul_rn(uc[a][1], 1.f / 64.f), upg = __fmul_rn(ug[a][1], 1.f / 64.f);
+                        const float v = __fadd_rn(upc, __fmul_rn(__fsub_rn((float)px[C], upg), w0));
+                        acc[k][a][1] = __fadd_rn(acc[k][a][1], v);
+                        if (c == 0) S.wsum[2 * k + a][2 * p + 1] = __fadd_rn(S.wsum[2 * k + a][2 * p + 1], w0);
+                    }
                 }
-                wacc[a][b] = __fadd_rn(wacc[a][b], w0);
             }
+            rc0 = rc1; rg0 = rg1; rc1 = rc2; rg1 = rg2;
         }
     }
 
@@ -563,19 +629,19 @@ __global__ void __launch_bounds__(kThreads) k_final(FinalParams P)
     __syncthreads();
     const int row_bytes = (cx1 - cx0) * C;
 #pragma unroll
-    for (int a = 0; a < 2; ++a) {
-        const int r = rp * 2 + a;
-        const int cy = cy0 + r;
-        if (cy >= cy1) continue;
-        const int mis = (int)((reinterpret_cast<uintptr_t>(P.canvas) + (size_t)cy * P.canvas_pitch + (size_t)cx0 * C) & 15);
+    for (int k = 0; k < FB_STEPS; ++k) {
 #pragma unroll
-        for (int b = 0; b < 4; ++b) {
-            const int x = cg * 4 + b;
-            if (cx0 + x >= cx1) continue;
-            const float wsum = fmaxf(wacc[a][b], 1e-6f);
+        for (int a = 0; a < 2; ++a) {
+            const int r = 2 * k + a;
+            const int cy = cy0 + r;
+            if (cy >= cy1) continue;
+            const int mis = (int)((reinterpret_cast<uintptr_t>(P.canvas) + (size_t)cy * P.canvas_pitch + (size_t)cx0 * C) & 15);
 #pragma unroll
-            for (int c = 0; c < C; ++c) {
-                float v = __fdiv_rn(acc[a][b][c], wsum);
+            for (int b = 0; b < 2; ++b) {
+                const int x = 2 * p + b;
+                if (cx0 + x >= cx1) continue;
+                const float wsum = fmaxf(S.wsum[r][x], 1e-6f);
+                float v = __fdiv_rn(acc[k][a][b], wsum);
                 v = fminf(fmaxf(v, 0.f), 255.f);
                 S.u8[r][mis + x * C + c] = (uint8_t)(int)v; // clip then truncate (blending_module.py:504-506)
             }
@@ -583,8 +649,8 @@ __global__ void __launch_bounds__(kThreads) k_final(FinalParams P)
     }
     __syncthreads();
     const int n_rows = cy1 - cy0;
-    constexpr int kChunks = (UP_BW * 3 + 15 + 15) / 16; // chunks that can touch a row's payload
-    for (int i = threadIdx.x; i < n_rows * kChunks; i += kThreads) {
+    constexpr int kChunks = (FB_W * 3 + 15 + 15) / 16; // chunks that can touch a row's payload
+    for (int i = threadIdx.x; i < n_rows * kChunks; i += NT) {
         const int r = i / kChunks, ch = i - r * kChunks;
         uint8_t *grow = P.canvas + (size_t)(cy0 + r) * P.canvas_pitch + (size_t)cx0 * C;
         const int mis = (int)(reinterpret_cast<uintptr_t>(grow) & 15);
@@ -861,7 +927,7 @@ int srf_fuse_device(srf_ctx *ctx, const srf_tile *tiles, int n_tiles, int C, int
         P.canvas_pitch = canvas_pitch;
         P.row_begin = rb;
         P.row_end = re;
-        dim3 grid(srf_ceil_div(out_w, UP_BW), srf_ceil_div(re - rb, UP_BH), 1);
+        dim3 grid(srf_ceil_div(out_w, FB_W), srf_ceil_div(re - rb, FB_H), 1);
         double cov = 0; // tile pixels inside the band
         for (int i = 0; i < n_tiles; ++i) {
             const int a = std::max(rb, tiles[i].y), b = std::min(re, tiles[i].y + tiles[i].h);
@@ -873,11 +939,11 @@ int srf_fuse_device(srf_ctx *ctx, const srf_tile *tiles, int n_tiles, int C, int
         if (C == 3) {
             const size_t sm = sizeof(FinalSmem<3>);
             SRF_CHECK_CUDA(ctx, cudaFuncSetAttribute(k_final<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-            k_final<3><<<grid, kThreads, sm, st>>>(P);
+            k_final<3><<<grid, 128 * 3, sm, st>>>(P);
         } else {
             const size_t sm = sizeof(FinalSmem<1>);
             SRF_CHECK_CUDA(ctx, cudaFuncSetAttribute(k_final<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-            k_final<1><<<grid, kThreads, sm, st>>>(P);
+            k_final<1><<<grid, 128, sm, st>>>(P);
         }
         SRF_CHECK_CUDA(ctx, cudaGetLastError());
     }
