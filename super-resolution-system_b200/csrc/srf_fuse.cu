@@ -26,7 +26,6 @@ constexpr int kThreads = 256;
 constexpr int DN_BH = 16, DN_BW = 64;               // pyrDown output block
 constexpr int DN_IN_ROWS = 2 * DN_BH + 3;           // 35 input rows
 constexpr int DN_IN_COLS_F32 = 2 * DN_BW + 8;       // staged f32 cols: [2*ox0-4, 2*ox0+132)
-constexpr int DN_IN_BYTES_U8 = 416;                 // staged bytes per row for the uint8 source
 constexpr int UP_BH = 32, UP_BW = 64;               // pyrUp / final output block
 constexpr int UP_SRC_ROWS = UP_BH / 2 + 3;          // 19 source rows (odd start + both halos)
 constexpr int UP_SRC_COLS = 44;                     // staged source cols (11 float4)
@@ -107,76 +106,134 @@ __device__ __forceinline__ float lut_weight(const float *__restrict__ lut, int l
 // ------------------------------------------------------------------------------------------------------------
 // k_down_u8: uint8 HWC tile -> G_1 planar.  All sums are exact integers (<= 65280), so OpenCV's float op order
 // is irrelevant here; the result is (int) * 2^-8, bit-identical to cv2.pyrDown(float32(tile)).
-// grid = (ceil(ow/64), ceil(rows/16), tiles in group)
+//
+// One CTA = 128 output columns x 32 output rows of one tile, 128*C threads: thread (x, c) owns output column x of
+// channel c and streams DOWN the input rows.  Input rows are staged 8 at a time (double buffered, one 16-pixel
+// group = C 16-byte loads per staging thread) and DE-INTERLEAVED into per-channel byte planes on the way in, so the
+// horizontal 5-tap is two aligned 32-bit LDS + two DP4A per value; the five most recent horizontal sums live in a
+// register shift ring and every second row emits one output row (coalesced 128-byte stores per warp).
+// grid = (ceil(ow/128), ceil(rows/32), tiles in group)
 // ------------------------------------------------------------------------------------------------------------
-template <int C>
-__global__ void __launch_bounds__(kThreads) k_down_u8(const TileDev *__restrict__ tiles, const int *__restrict__ tile_ids, GroupDev g)
+constexpr int D8_BW = 128, D8_ROWS = 32, D8_BATCH = 8;
+constexpr int D8_GROUPS = 18;           // 16-pixel groups staged per row: pixels [2*ox0-16, 2*ox0+272)
+constexpr int D8_PSTRIDE = D8_GROUPS * 16;
+
+__device__ __forceinline__ uint4 load_u8_chunk(const uint8_t *grow, int o, int valid)
 {
-    __shared__ __align__(16) uint8_t s_in[DN_IN_ROWS][DN_IN_BYTES_U8];
-    __shared__ int s_h[DN_IN_ROWS][C][DN_BW];
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (o >= 0 && o + 16 <= valid) {
+        v = *reinterpret_cast<const uint4 *>(grow + o);
+    } else if (o + 16 > 0 && o < valid) {
+        uint8_t *b = reinterpret_cast<uint8_t *>(&v);
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+            const int p = o + e;
+            b[e] = (p >= 0 && p < valid) ? grow[p] : (uint8_t)0;
+        }
+    }
+    return v;
+}
+
+template <int C>
+__global__ void __launch_bounds__(128 * C) k_down_u8(const TileDev *__restrict__ tiles, const int *__restrict__ tile_ids, GroupDev g)
+{
+    __shared__ __align__(16) uint8_t s_pl[2][D8_BATCH][C][D8_PSTRIDE];
+    constexpr int NT = 128 * C;
 
     const TileDev &t = tiles[tile_ids[blockIdx.z]];
     const int h = t.h, w = t.w;
-    const int oh = g.lv[1].h, ow = g.lv[1].w;
-    const int oy0 = t.g0[1] + blockIdx.y * DN_BH;
-    const int ox0 = blockIdx.x * DN_BW;
-    if (oy0 >= t.g1[1] || ox0 >= ow) return;
-    const int oy1 = min(oy0 + DN_BH, t.g1[1]);
-    const int in_y0 = 2 * oy0 - 2;
-    const int px0 = 2 * ox0 - 2;
-    const int byte0 = px0 * C;
-    const int a0 = (byte0 >= 0) ? (byte0 & ~15) : -(((-byte0) + 15) & ~15);
-    const int boff = byte0 - a0;
-    const int n_in_rows = 2 * (oy1 - oy0) + 3;
-
-    for (int i = threadIdx.x; i < n_in_rows * (DN_IN_BYTES_U8 / 16); i += kThreads) {
-        const int r = i / (DN_IN_BYTES_U8 / 16), ch = i - r * (DN_IN_BYTES_U8 / 16);
-        const int gy = in_y0 + r;
-        const uint8_t *grow = (gy >= 0 && gy < h) ? t.src + (size_t)gy * t.pitch : nullptr;
-        stage_u8_chunk(&s_in[r][0], grow, a0, ch, w * C);
-    }
-    __syncthreads();
-
-    const bool x_interior = (px0 >= 0) && (px0 + 2 * DN_BW + 2 < w);
-    for (int i = threadIdx.x; i < n_in_rows * C * DN_BW; i += kThreads) {
-        const int x = i % DN_BW;
-        const int c = (i / DN_BW) % C;
-        const int r = i / (DN_BW * C);
-        const int gy = in_y0 + r;
-        if (gy < 0 || gy >= h || ox0 + x >= ow) continue;
-        const uint8_t *row = &s_in[r][boff + c];
-        int b0, b1, b2, b3, b4;
-        if (x_interior) {
-            const uint8_t *p = row + 2 * x * C;
-            b0 = p[0]; b1 = p[C]; b2 = p[2 * C]; b3 = p[3 * C]; b4 = p[4 * C];
-        } else {
-            const int gx = 2 * (ox0 + x);
-            b0 = row[(srf_reflect101(gx - 2, w) - px0) * C];
-            b1 = row[(srf_reflect101(gx - 1, w) - px0) * C];
-            b2 = row[(srf_reflect101(gx, w) - px0) * C];
-            b3 = row[(srf_reflect101(gx + 1, w) - px0) * C];
-            b4 = row[(srf_reflect101(gx + 2, w) - px0) * C];
-        }
-        s_h[r][c][x] = b0 + b4 + 4 * (b1 + b3) + 6 * b2;
-    }
-    __syncthreads();
-
-    const int n_out_rows = oy1 - oy0;
     const LevelGeom L1 = g.lv[1];
-    for (int i = threadIdx.x; i < n_out_rows * C * DN_BW; i += kThreads) {
-        const int x = i % DN_BW;
-        const int c = (i / DN_BW) % C;
-        const int ry = i / (DN_BW * C);
-        const int ox = ox0 + x;
-        if (ox >= ow) continue;
-        const int oy = oy0 + ry;
-        int rr[5];
+    const int ow = L1.w;
+    const int oy0 = t.g0[1] + blockIdx.y * D8_ROWS;
+    const int ox0 = blockIdx.x * D8_BW;
+    if (oy0 >= t.g1[1] || ox0 >= ow) return;
+    const int oy1 = min(oy0 + D8_ROWS, t.g1[1]);
+    const int in_y0 = 2 * oy0 - 2;
+    const int px_g0 = 2 * ox0 - 16;                 // first staged pixel (multiple of 16 -> 16-byte aligned bytes)
+    const int n_in_rows = 2 * (oy1 - oy0) + 3;
+    const int n_batches = (n_in_rows + D8_BATCH - 1) / D8_BATCH;
+    const uint8_t *src = t.src;
+    const size_t pitch = t.pitch;
+    const int valid = w * C;
+
+    // staging role: (row j of the batch, group q)
+    const bool stager = threadIdx.x < D8_BATCH * D8_GROUPS;
+    const int sj = threadIdx.x / D8_GROUPS, sq = threadIdx.x % D8_GROUPS;
+    uint4 pre[C];
+    auto stage_load = [&](int b) {
+        if (!stager) return;
+        const int gy = srf_reflect101(in_y0 + b * D8_BATCH + sj, h);
+        const uint8_t *grow = src + (size_t)gy * pitch;
+        const int o = (px_g0 + 16 * sq) * C;
 #pragma unroll
-        for (int k = 0; k < 5; ++k) rr[k] = srf_reflect101(2 * oy + k - 2, h) - in_y0;
-        const int v = s_h[rr[0]][c][x] + s_h[rr[4]][c][x] + 4 * (s_h[rr[1]][c][x] + s_h[rr[3]][c][x]) + 6 * s_h[rr[2]][c][x];
-        t.G[1][(size_t)c * L1.plane + (size_t)oy * L1.pitch + ox] = __fmul_rn((float)v, 1.f / 256.f);
+        for (int k = 0; k < C; ++k) pre[k] = load_u8_chunk(grow, o + 16 * k, valid);
+    };
+    auto stage_store = [&](int buf) {
+        if (!stager) return;
+        if (C == 3) {
+            const uint32_t *wv = reinterpret_cast<const uint32_t *>(&pre[0]);
+            uint32_t o0[4], o1[4], o2[4];
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                const uint32_t A = wv[3 * m], B = wv[3 * m + 1], Cw = wv[3 * m + 2];
+                o0[m] = __byte_perm(__byte_perm(A, B, 0x0630), Cw, 0x5210);
+                o1[m] = __byte_perm(__byte_perm(A, B, 0x0741), Cw, 0x6210);
+                o2[m] = __byte_perm(__byte_perm(A, B, 0x0052), Cw, 0x7410);
+            }
+            *reinterpret_cast<uint4 *>(&s_pl[buf][sj][0][16 * sq]) = make_uint4(o0[0], o0[1], o0[2], o0[3]);
+            *reinterpret_cast<uint4 *>(&s_pl[buf][sj][C > 1 ? 1 : 0][16 * sq]) = make_uint4(o1[0], o1[1], o1[2], o1[3]);
+            *reinterpret_cast<uint4 *>(&s_pl[buf][sj][C > 2 ? 2 : 0][16 * sq]) = make_uint4(o2[0], o2[1], o2[2], o2[3]);
+        } else {
+            *reinterpret_cast<uint4 *>(&s_pl[buf][sj][0][16 * sq]) = pre[0];
+        }
+    };
+
+    // compute role: output column x of channel c
+    const int x = threadIdx.x % D8_BW, c = threadIdx.x / D8_BW;
+    const int ox = ox0 + x;
+    const bool x_edge = (2 * ox0 - 2 < 0) || (2 * (ox0 + D8_BW - 1) + 2 >= w); // some tap of this strip is reflected
+    const int pb = 14 + 2 * x;                      // planar index of tap 0 (pixel 2*ox - 2)
+    const int wo = (pb >> 2) * 4, sh = pb & 3;      // aligned word offset; sh is 0 or 2
+    const uint32_t wA = sh ? 0x04010000u : 0x04060401u, wB = sh ? 0x00010406u : 0x00000001u;
+    int ti[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        int q = srf_reflect101(2 * min(ox, ow - 1) + k - 2, w) - px_g0;
+        ti[k] = max(min(q, D8_PSTRIDE - 1), 0);
     }
-    (void)oh;
+    float *dst = t.G[1] + (size_t)c * L1.plane;
+
+    int h0 = 0, h1 = 0, h2 = 0, h3 = 0, h4 = 0;
+    stage_load(0);
+    stage_store(0);
+    __syncthreads();
+    for (int b = 0; b < n_batches; ++b) {
+        const int buf = b & 1;
+        if (b + 1 < n_batches) stage_load(b + 1);
+#pragma unroll
+        for (int j = 0; j < D8_BATCH; ++j) {
+            const uint8_t *row = &s_pl[buf][j][c][0];
+            int hv;
+            if (!x_edge) {
+                const uint32_t w0 = *reinterpret_cast<const uint32_t *>(row + wo);
+                const uint32_t w1 = *reinterpret_cast<const uint32_t *>(row + wo + 4);
+                hv = (int)__dp4a(w0, wA, __dp4a(w1, wB, 0u));
+            } else {
+                hv = (int)row[ti[0]] + (int)row[ti[4]] + 4 * ((int)row[ti[1]] + (int)row[ti[3]]) + 6 * (int)row[ti[2]];
+            }
+            h0 = h1; h1 = h2; h2 = h3; h3 = h4; h4 = hv;
+            const int r = b * D8_BATCH + j; // stream position; rows r-4..r are in the ring
+            if ((j & 1) == 0 && r >= 4) {
+                const int oy = oy0 + ((r - 4) >> 1);
+                if (oy < oy1 && ox < ow) {
+                    const int v = h0 + h4 + 4 * (h1 + h3) + 6 * h2;
+                    dst[(size_t)oy * L1.pitch + ox] = __fmul_rn((float)v, 1.f / 256.f);
+                }
+            }
+        }
+        if (b + 1 < n_batches) stage_store(buf ^ 1);
+        __syncthreads();
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -428,6 +485,7 @@ struct FinalParams {
     const TileDev *tiles;
     const GroupDev *groups;
     const int *tile_group; // group index per tile
+    const int4 *rects;     // (y, x, h, w) per tile, compact copy for the coverage test
     int n_tiles;
     int out_h, out_w;
     uint8_t *canvas;
@@ -453,12 +511,130 @@ __device__ __forceinline__ HPair h_pair_fast(float s0, float s1, float s2, int x
     return r;
 }
 
+// All arithmetic of the gather runs in the "x64 domain": pyrUp's two un-normalised passes leave a factor 64 that the
+// reference removes right away (x 1/64).  Scaling by a power of two commutes with every IEEE rounding, so
+// 64*(upC + (g - upG)*w) == up64C + (64 g - up64G)*w bit for bit; the factor is taken out once, before the divide.
+template <int C, bool FULL>
+__device__ __forceinline__ void final_accumulate_tile(FinalSmem<C> &S, float (&acc)[FB_STEPS][2][2], const TileDev &t, const GroupDev &g,
+                                                      int cy0, int cx0, int iy0, int iy1, int ix0, int ix1, int c, int p, int u8_a0,
+                                                      int srow0, int n_srows, int sx0, int i0, int ws0, int xpar, int ypar, int mode)
+{
+    const int h1 = g.lv[1].h, w1 = g.lv[1].w;
+    const int tyf = cy0 - t.y, txf = cx0 - t.x;
+    const int txa = txf + 2 * p, txb = txa + 1; // tile columns of the thread's two canvas columns
+    const bool ina = FULL || ((cx0 + 2 * p >= ix0) && (cx0 + 2 * p < ix1));
+    const bool inb = FULL || ((cx0 + 2 * p + 1 >= ix0) && (cx0 + 2 * p + 1 < ix1));
+    const int lmax = g.lut_len - 1;
+    const float wflat = __ldg(g.lut + lmax);
+    const int dxa = min(txa, t.w - 1 - txa), dxb = min(txb, t.w - 1 - txb);
+    const int u8_col = txa * C + c - u8_a0; // byte offset of (txa, c) inside a staged row
+    const bool hfast = FULL || ((i0 >= 0) && (i0 + FB_PAIRS + 1 <= w1 - 1) && (w1 > 1));
+    const int scol = i0 + p - sx0; // smem column of s0
+
+    auto weight = [&](int dy, int dx) {
+        const int d = min(dy, dx);
+        return (d >= lmax) ? wflat : __ldg(g.lut + d);
+    };
+    auto hrow = [&](int r_logical, HPair &oc, HPair &og) {
+        int r = (r_logical == -1) ? min(1, h1 - 1) : max(min(r_logical, h1 - 1), 0);
+        r -= srow0;
+        r = max(min(r, n_srows - 1), 0);
+        const float *rc = &S.sc[c][r][0];
+        const float *rg = &S.sg[c][r][0];
+        if (hfast) {
+            oc = h_pair_fast(rc[scol], rc[scol + 1], rc[scol + 2], xpar);
+            og = h_pair_fast(rg[scol], rg[scol + 1], rg[scol + 2], xpar);
+        } else {
+            oc.a = oc.b = og.a = og.b = 0.f;
+            if (ina) {
+                oc.a = up_h_sample(txa, w1, [&](int ii) { return rc[ii - sx0]; });
+                og.a = up_h_sample(txa, w1, [&](int ii) { return rg[ii - sx0]; });
+            }
+            if (inb) {
+                oc.b = up_h_sample(txb, w1, [&](int ii) { return rc[ii - sx0]; });
+                og.b = up_h_sample(txb, w1, [&](int ii) { return rg[ii - sx0]; });
+            }
+        }
+    };
+
+    if (mode == 2) { // single level: C_0 = G_0 * W_0
+#pragma unroll
+        for (int k = 0; k < FB_STEPS; ++k) {
+#pragma unroll
+            for (int a = 0; a < 2; ++a) {
+                const int cy = cy0 + 2 * k + a;
+                if (cy < iy0 || cy >= iy1) continue;
+                const int ty = cy - t.y;
+                const int dy = min(ty, t.h - 1 - ty);
+                const uint8_t *px = &S.u8[2 * k + a][u8_col];
+                if (ina) {
+                    const float w0 = weight(dy, dxa);
+                    acc[k][a][0] = __fadd_rn(acc[k][a][0], __fmul_rn((float)((int)px[0] << 6), w0));
+                    if (c == 0) S.wsum[2 * k + a][2 * p] = __fadd_rn(S.wsum[2 * k + a][2 * p], w0);
+                }
+                if (inb) {
+                    const float w0 = weight(dy, dxb);
+                    acc[k][a][1] = __fadd_rn(acc[k][a][1], __fmul_rn((float)((int)px[C] << 6), w0));
+                    if (c == 0) S.wsum[2 * k + a][2 * p + 1] = __fadd_rn(S.wsum[2 * k + a][2 * p + 1], w0);
+                }
+            }
+        }
+        return;
+    }
+
+    HPair rc0, rg0, rc1, rg1, rc2, rg2; // ring: logical rows ws0+k, ws0+k+1, ws0+k+2
+    hrow(ws0, rc0, rg0);
+    hrow(ws0 + 1, rc1, rg1);
+#pragma unroll
+    for (int k = 0; k < FB_STEPS; ++k) {
+        hrow(ws0 + k + 2, rc2, rg2);
+        float uc[2][2], ug[2][2]; // x64
+        if (ypar == 0) { // tile rows (2j, 2j+1), j = ws0+k+1: even uses (m,p,n), odd uses (p,n)
+            uc[0][0] = up_even(rc0.a, rc1.a, rc2.a); uc[0][1] = up_even(rc0.b, rc1.b, rc2.b);
+            ug[0][0] = up_even(rg0.a, rg1.a, rg2.a); ug[0][1] = up_even(rg0.b, rg1.b, rg2.b);
+            uc[1][0] = up_odd(rc1.a, rc2.a); uc[1][1] = up_odd(rc1.b, rc2.b);
+            ug[1][0] = up_odd(rg1.a, rg2.a); ug[1][1] = up_odd(rg1.b, rg2.b);
+        } else {         // tile rows (2j+1, 2j+2), j = ws0+k: odd uses ring 0,1; even uses ring 0,1,2
+            uc[0][0] = up_odd(rc0.a, rc1.a); uc[0][1] = up_odd(rc0.b, rc1.b);
+            ug[0][0] = up_odd(rg0.a, rg1.a); ug[0][1] = up_odd(rg0.b, rg1.b);
+            uc[1][0] = up_even(rc0.a, rc1.a, rc2.a); uc[1][1] = up_even(rc0.b, rc1.b, rc2.b);
+            ug[1][0] = up_even(rg0.a, rg1.a, rg2.a); ug[1][1] = up_even(rg0.b, rg1.b, rg2.b);
+        }
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+            const int cy = cy0 + 2 * k + a;
+            if (FULL || (cy >= iy0 && cy < iy1)) {
+                const int ty = tyf + 2 * k + a;
+                const int dy = min(ty, t.h - 1 - ty);
+                const uint8_t *px = &S.u8[2 * k + a][u8_col];
+                if (ina) {
+                    const float w0 = weight(dy, dxa);
+                    const float g64 = (float)((int)px[0] << 6);
+                    const float v = __fadd_rn(uc[a][0], __fmul_rn(__fsub_rn(g64, ug[a][0]), w0));
+                    acc[k][a][0] = __fadd_rn(acc[k][a][0], v);
+                    if (c == 0) S.wsum[2 * k + a][2 * p] = __fadd_rn(S.wsum[2 * k + a][2 * p], w0);
+                }
+                if (inb) {
+                    const float w0 = weight(dy, dxb);
+                    const float g64 = (float)((int)px[C] << 6);
+                    const float v = __fadd_rn(uc[a][1], __fmul_rn(__fsub_rn(g64, ug[a][1]), w0));
+                    acc[k][a][1] = __fadd_rn(acc[k][a][1], v);
+                    if (c == 0) S.wsum[2 * k + a][2 * p + 1] = __fadd_rn(S.wsum[2 * k + a][2 * p + 1], w0);
+                }
+            }
+        }
+        rc0 = rc1; rg0 = rg1; rc1 = rc2; rg1 = rg2;
+    }
+}
+
 template <int C>
 __global__ void __launch_bounds__(128 * C, (C == 3) ? 2 : 5) k_final(FinalParams P)
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     FinalSmem<C> &S = *reinterpret_cast<FinalSmem<C> *>(smem_raw);
     constexpr int NT = 128 * C;
+    __shared__ int s_list[NT];
+    __shared__ int s_wcnt[NT / 32];
 
     const int cy0 = P.row_begin + blockIdx.y * FB_H;
     const int cx0 = blockIdx.x * FB_W;
@@ -466,162 +642,93 @@ __global__ void __launch_bounds__(128 * C, (C == 3) ? 2 : 5) k_final(FinalParams
     const int cx1 = min(cx0 + FB_W, P.out_w);
     const int c = threadIdx.x / FB_PAIRS; // warp-uniform
     const int p = threadIdx.x % FB_PAIRS;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
     float acc[FB_STEPS][2][2];
 #pragma unroll
     for (int k = 0; k < FB_STEPS; ++k) acc[k][0][0] = acc[k][0][1] = acc[k][1][0] = acc[k][1][1] = 0.f;
     for (int i = threadIdx.x; i < FB_H * FB_W; i += NT) (&S.wsum[0][0])[i] = 0.f;
 
-    for (int ti = 0; ti < P.n_tiles; ++ti) {
-        const TileDev &t = P.tiles[ti];
-        const int iy0 = max(cy0, t.y), iy1 = min(cy1, t.y + t.h);
-        const int ix0 = max(cx0, t.x), ix1 = min(cx1, t.x + t.w);
-        if (iy0 >= iy1 || ix0 >= ix1) continue; // uniform across the CTA
-        const GroupDev &g = P.groups[P.tile_group[ti]];
-        const int mode = (g.n_levels >= 3) ? 0 : (g.n_levels == 2 ? 1 : 2);
-        const LevelGeom L1 = g.lv[1];
-        const int h1 = L1.h, w1 = L1.w;
-        const int tyf = cy0 - t.y, txf = cx0 - t.x; // tile coordinates of the block origin (may be negative)
-        const int xpar = txf & 1, ypar = tyf & 1;
-        const int i0 = (txf >> 1) - (1 - xpar); // window start column for pair 0
-        const int ws0 = (tyf >> 1) - (1 - ypar); // window start row for step 0
-        // staged source window
-        const int sx0 = max(i0, 0) & ~3;
-        const int srow0 = max(min(ws0, h1 - 1), 0);
-        const int srow1 = max(min(ws0 + FB_STEPS + 1, h1 - 1), 0);
-        const int n_srows = srow1 - srow0 + 1; // <= 10
-        __syncthreads(); // everyone is done with the previous tile's smem (and wsum is initialised)
-
-        // ---- stage the uint8 tile block: rows iy0..iy1, bytes congruent mod 16 with the tile rows ----
-        const int u8_first = (ix0 - t.x) * C;
-        const int u8_a0 = u8_first & ~15;
-        const int u8_chunks = ((ix1 - t.x) * C - u8_a0 + 15) >> 4;
-        for (int i = threadIdx.x; i < (iy1 - iy0) * u8_chunks; i += NT) {
-            const int r = i / u8_chunks, ch = i - r * u8_chunks;
-            const uint8_t *grow = t.src + (size_t)(iy0 - t.y + r) * t.pitch;
-            stage_u8_chunk(&S.u8[iy0 - cy0 + r][0], grow, u8_a0, ch, t.w * C);
+    for (int base = 0; base < P.n_tiles; base += NT) {
+        // ---- ordered list of the tiles (of this chunk) that touch the block: one tile per thread, ballot-compacted ----
+        const int cand = base + threadIdx.x;
+        bool hit = false;
+        if (cand < P.n_tiles) {
+            const int4 rct = P.rects[cand]; // y, x, h, w
+            hit = max(cy0, rct.x) < min(cy1, rct.x + rct.z) && max(cx0, rct.y) < min(cx1, rct.y + rct.w);
         }
-        if (mode != 2) {
-            for (int i = threadIdx.x; i < C * n_srows * (FB_SRC_COLS / 4); i += NT) {
-                const int ch = i % (FB_SRC_COLS / 4);
-                const int r = (i / (FB_SRC_COLS / 4)) % n_srows;
-                const int cc = i / ((FB_SRC_COLS / 4) * n_srows);
-                const int gy = srow0 + r, c0 = sx0 + ch * 4;
-                const float4 gv = load_f32_chunk(t.G[1] + (size_t)cc * L1.plane + (size_t)gy * L1.pitch, c0, w1);
-                float4 cv;
-                if (mode == 1) {
-                    const float4 wv = load_f32_chunk(g.W[1] + (size_t)gy * L1.pitch, c0, w1);
-                    cv = make_float4(__fmul_rn(gv.x, wv.x), __fmul_rn(gv.y, wv.y), __fmul_rn(gv.z, wv.z), __fmul_rn(gv.w, wv.w));
-                } else {
-                    cv = load_f32_chunk(t.C[1] + (size_t)cc * L1.plane + (size_t)gy * L1.pitch, c0, w1);
-                }
-                *reinterpret_cast<float4 *>(&S.sg[cc][r][ch * 4]) = gv;
-                *reinterpret_cast<float4 *>(&S.sc[cc][r][ch * 4]) = cv;
-            }
+        const unsigned bal = __ballot_sync(0xffffffffu, hit);
+        __syncthreads(); // previous chunk's list fully consumed
+        if (lane == 0) s_wcnt[warp] = __popc(bal);
+        __syncthreads();
+        int off = 0, total = 0;
+#pragma unroll
+        for (int k = 0; k < NT / 32; ++k) {
+            const int n = s_wcnt[k];
+            if (k < warp) off += n;
+            total += n;
         }
+        if (hit) s_list[off + __popc(bal & ((1u << lane) - 1u))] = cand;
         __syncthreads();
 
-        // ---- per-thread geometry for this tile ----
-        const int txa = txf + 2 * p, txb = txa + 1; // tile columns of the thread's two canvas columns
-        const bool ina = (txa >= 0) && (txa < t.w) && (cx0 + 2 * p < cx1);
-        const bool inb = (txb >= 0) && (txb < t.w) && (cx0 + 2 * p + 1 < cx1);
-        const int lmax = g.lut_len - 1;
-        const int dxa = min(min(txa, t.w - 1 - txa), lmax), dxb = min(min(txb, t.w - 1 - txb), lmax);
-        const int u8_col = txa * C + c - u8_a0; // byte offset of (txa, c) inside a staged row
-        // horizontal fast path: the whole 130-sample window of this CTA lies strictly inside the source row
-        const bool hfast = (i0 >= 0) && (i0 + FB_PAIRS + 1 <= w1 - 1) && (w1 > 1);
-        const int scol = i0 + p - sx0; // smem column of s0
+        for (int li = 0; li < total; ++li) {
+            const int ti = s_list[li];
+            const TileDev &t = P.tiles[ti];
+            const int iy0 = max(cy0, t.y), iy1 = min(cy1, t.y + t.h);
+            const int ix0 = max(cx0, t.x), ix1 = min(cx1, t.x + t.w);
+            const GroupDev &g = P.groups[P.tile_group[ti]];
+            const int mode = (g.n_levels >= 3) ? 0 : (g.n_levels == 2 ? 1 : 2);
+            const LevelGeom L1 = g.lv[1];
+            const int h1 = L1.h, w1 = L1.w;
+            const int tyf = cy0 - t.y, txf = cx0 - t.x; // tile coordinates of the block origin (may be negative)
+            const int xpar = txf & 1, ypar = tyf & 1;
+            const int i0 = (txf >> 1) - (1 - xpar);  // window start column for pair 0
+            const int ws0 = (tyf >> 1) - (1 - ypar); // window start row for step 0
+            const int sx0 = max(i0, 0) & ~3;
+            const int srow0 = max(min(ws0, h1 - 1), 0);
+            const int srow1 = max(min(ws0 + FB_STEPS + 1, h1 - 1), 0);
+            const int n_srows = srow1 - srow0 + 1; // <= 10
+            __syncthreads(); // everyone is done with the previous tile's smem (and wsum is initialised)
 
-        auto hrow = [&](int r_logical, HPair &oc, HPair &og) {
-            int r = (r_logical == -1) ? min(1, h1 - 1) : max(min(r_logical, h1 - 1), 0);
-            r -= srow0;
-            r = max(min(r, n_srows - 1), 0);
-            const float *rc = &S.sc[c][r][0];
-            const float *rg = &S.sg[c][r][0];
-            if (hfast) {
-                oc = h_pair_fast(rc[scol], rc[scol + 1], rc[scol + 2], xpar);
-                og = h_pair_fast(rg[scol], rg[scol + 1], rg[scol + 2], xpar);
-            } else {
-                oc.a = oc.b = og.a = og.b = 0.f;
-                if (ina) {
-                    oc.a = up_h_sample(txa, w1, [&](int ii) { return rc[ii - sx0]; });
-                    og.a = up_h_sample(txa, w1, [&](int ii) { return rg[ii - sx0]; });
-                }
-                if (inb) {
-                    oc.b = up_h_sample(txb, w1, [&](int ii) { return rc[ii - sx0]; });
-                    og.b = up_h_sample(txb, w1, [&](int ii) { return rg[ii - sx0]; });
+            // ---- stage the uint8 tile block: rows iy0..iy1, bytes congruent mod 16 with the tile rows ----
+            const int u8_first = (ix0 - t.x) * C;
+            const int u8_a0 = u8_first & ~15;
+            const int u8_chunks = ((ix1 - t.x) * C - u8_a0 + 15) >> 4;
+            for (int i = threadIdx.x; i < (iy1 - iy0) * u8_chunks; i += NT) {
+                const int r = i / u8_chunks, ch = i - r * u8_chunks;
+                const uint8_t *grow = t.src + (size_t)(iy0 - t.y + r) * t.pitch;
+                stage_u8_chunk(&S.u8[iy0 - cy0 + r][0], grow, u8_a0, ch, t.w * C);
+            }
+            if (mode != 2) {
+                const int per_c = n_srows * (FB_SRC_COLS / 4);
+                for (int i = threadIdx.x; i < C * per_c; i += NT) {
+                    const int cc = i / per_c;
+                    const int rem = i - cc * per_c;
+                    const int r = rem / (FB_SRC_COLS / 4), ch = rem - r * (FB_SRC_COLS / 4);
+                    const int gy = srow0 + r, c0 = sx0 + ch * 4;
+                    const float4 gv = load_f32_chunk(t.G[1] + (size_t)cc * L1.plane + (size_t)gy * L1.pitch, c0, w1);
+                    float4 cv;
+                    if (mode == 1) {
+                        const float4 wv = load_f32_chunk(g.W[1] + (size_t)gy * L1.pitch, c0, w1);
+                        cv = make_float4(__fmul_rn(gv.x, wv.x), __fmul_rn(gv.y, wv.y), __fmul_rn(gv.z, wv.z), __fmul_rn(gv.w, wv.w));
+                    } else {
+                        cv = load_f32_chunk(t.C[1] + (size_t)cc * L1.plane + (size_t)gy * L1.pitch, c0, w1);
+                    }
+                    *reinterpret_cast<float4 *>(&S.sg[cc][r][ch * 4]) = gv;
+                    *reinterpret_cast<float4 *>(&S.sc[cc][r][ch * 4]) = cv;
                 }
             }
-        };
+            __syncthreads();
 
-        if (mode == 2) {
-#pragma unroll
-            for (int k = 0; k < FB_STEPS; ++k) {
-#pragma unroll
-                for (int a = 0; a < 2; ++a) {
-                    const int cy = cy0 + 2 * k + a;
-                    if (cy < iy0 || cy >= iy1) continue;
-                    const int ty = cy - t.y;
-                    const int dy = min(min(ty, t.h - 1 - ty), lmax);
-                    const uint8_t *px = &S.u8[2 * k + a][u8_col];
-                    if (ina) {
-                        const float w0 = __ldg(g.lut + min(dy, dxa));
-                        acc[k][a][0] = __fadd_rn(acc[k][a][0], __fmul_rn((float)px[0], w0));
-                        if (c == 0) S.wsum[2 * k + a][2 * p] = __fadd_rn(S.wsum[2 * k + a][2 * p], w0);
-                    }
-                    if (inb) {
-                        const float w0 = __ldg(g.lut + min(dy, dxb));
-                        acc[k][a][1] = __fadd_rn(acc[k][a][1], __fmul_rn((float)px[C], w0));
-                        if (c == 0) S.wsum[2 * k + a][2 * p + 1] = __fadd_rn(S.wsum[2 * k + a][2 * p + 1], w0);
-                    }
-                }
-            }
-            continue;
-        }
-
-        HPair rc0, rg0, rc1, rg1, rc2, rg2; // ring: logical rows ws0+k, ws0+k+1, ws0+k+2
-        hrow(ws0, rc0, rg0);
-        hrow(ws0 + 1, rc1, rg1);
-#pragma unroll
-        for (int k = 0; k < FB_STEPS; ++k) {
-            hrow(ws0 + k + 2, rc2, rg2);
-            // vertical pass for canvas rows cy0+2k (a=0) and cy0+2k+1 (a=1)
-            float uc[2][2], ug[2][2];
-            if (ypar == 0) { // tile rows (2j, 2j+1), j = ws0+k+1: even uses (m,p,n), odd uses (p,n)
-                uc[0][0] = up_even(rc0.a, rc1.a, rc2.a); uc[0][1] = up_even(rc0.b, rc1.b, rc2.b);
-                ug[0][0] = up_even(rg0.a, rg1.a, rg2.a); ug[0][1] = up_even(rg0.b, rg1.b, rg2.b);
-                uc[1][0] = up_odd(rc1.a, rc2.a); uc[1][1] = up_odd(rc1.b, rc2.b);
-                ug[1][0] = up_odd(rg1.a, rg2.a); ug[1][1] = up_odd(rg1.b, rg2.b);
-            } else {         // tile rows (2j+1, 2j+2), j = ws0+k: odd uses (p,n) = ring 0,1; even uses ring 0,1,2
-                uc[0][0] = up_odd(rc0.a, rc1.a); uc[0][1] = up_odd(rc0.b, rc1.b);
-                ug[0][0] = up_odd(rg0.a, rg1.a); ug[0][1] = up_odd(rg0.b, rg1.b);
-                uc[1][0] = up_even(rc0.a, rc1.a, rc2.a); uc[1][1] = up_even(rc0.b, rc1.b, rc2.b);
-                ug[1][0] = up_even(rg0.a, rg1.a, rg2.a); ug[1][1] = up_even(rg0.b, rg1.b, rg2.b);
-            }
-#pragma unroll
-            for (int a = 0; a < 2; ++a) {
-                const int cy = cy0 + 2 * k + a;
-                if (cy >= iy0 && cy < iy1) {
-                    const int ty = cy - t.y;
-                    const int dy = min(min(ty, t.h - 1 - ty), lmax);
-                    const uint8_t *px = &S.u8[2 * k + a][u8_col];
-                    if (ina) {
-                        const float w0 = __ldg(g.lut + min(dy, dxa));
-                        const float upc = __fmul_rn(uc[a][0], 1.f / 64.f), upg = __fmul_rn(ug[a][0], 1.f / 64.f);
-                        const float v = __fadd_rn(upc, __fmul_rn(__fsub_rn((float)px[0], upg), w0));
-                        acc[k][a][0] = __fadd_rn(acc[k][a][0], v);
-                        if (c == 0) S.wsum[2 * k + a][2 * p] = __fadd_rn(S.wsum[2 * k + a][2 * p], w0);
-                    }
-                    if (inb) {
-                        const float w0 = __ldg(g.lut + min(dy, dxb));
-                        const float upc = __fmul_rn(uc[a][1], 1.f / 64.f), upg = __fmul_rn(ug[a][1], 1.f / 64.f);
-                        const float v = __fadd_rn(upc, __fmul_rn(__fsub_rn((float)px[C], upg), w0));
-                        acc[k][a][1] = __fadd_rn(acc[k][a][1], v);
-                        if (c == 0) S.wsum[2 * k + a][2 * p + 1] = __fadd_rn(S.wsum[2 * k + a][2 * p + 1], w0);
-                    }
-                }
-            }
-            rc0 = rc1; rg0 = rg1; rc1 = rc2; rg1 = rg2;
+            // block entirely inside the tile and every horizontal window strictly inside the source row: no predicates
+            const bool full = (mode != 2) && (iy0 == cy0) && (iy1 == cy0 + FB_H) && (ix0 == cx0) && (ix1 == cx0 + FB_W) && (i0 >= 0) &&
+                              (i0 + FB_PAIRS + 1 <= w1 - 1);
+            if (full)
+                final_accumulate_tile<C, true>(S, acc, t, g, cy0, cx0, iy0, iy1, ix0, ix1, c, p, u8_a0, srow0, n_srows, sx0, i0, ws0, xpar,
+                                               ypar, mode);
+            else
+                final_accumulate_tile<C, false>(S, acc, t, g, cy0, cx0, iy0, iy1, ix0, ix1, c, p, u8_a0, srow0, n_srows, sx0, i0, ws0, xpar,
+                                                ypar, mode);
         }
     }
 
@@ -641,7 +748,7 @@ __global__ void __launch_bounds__(128 * C, (C == 3) ? 2 : 5) k_final(FinalParams
                 const int x = 2 * p + b;
                 if (cx0 + x >= cx1) continue;
                 const float wsum = fmaxf(S.wsum[r][x], 1e-6f);
-                float v = __fdiv_rn(acc[k][a][b], wsum);
+                float v = __fdiv_rn(__fmul_rn(acc[k][a][b], 1.f / 64.f), wsum);
                 v = fminf(fmaxf(v, 0.f), 255.f);
                 S.u8[r][mis + x * C + c] = (uint8_t)(int)v; // clip then truncate (blending_module.py:504-506)
             }
@@ -767,7 +874,7 @@ int srf_fuse_device(srf_ctx *ctx, const srf_tile *tiles, int n_tiles, int C, int
     int rc;
     if ((rc = srf_reserve(ctx, ctx->ws_pyr, pyr_floats * sizeof(float) + 256))) return rc;
     const size_t desc_bytes = srf_align_up(sizeof(TileDev) * n_tiles, 256) + srf_align_up(sizeof(GroupDev) * groups.size(), 256) +
-                              srf_align_up(sizeof(int) * n_tiles * 2, 256);
+                              srf_align_up(sizeof(int) * n_tiles * 2, 256) + srf_align_up(sizeof(int4) * n_tiles, 256);
     if ((rc = srf_reserve(ctx, ctx->ws_desc, desc_bytes))) return rc;
     if ((rc = srf_reserve(ctx, ctx->ws_misc, lut_floats * sizeof(float) + 256))) return rc;
     float *pyr = (float *)ctx->ws_pyr.ptr;
@@ -831,6 +938,9 @@ int srf_fuse_device(srf_ctx *ctx, const srf_tile *tiles, int n_tiles, int C, int
     GroupDev *d_groups = (GroupDev *)(dbase + srf_align_up(sizeof(TileDev) * n_tiles, 256));
     int *d_tile_group = (int *)((uint8_t *)d_groups + srf_align_up(sizeof(GroupDev) * groups.size(), 256));
     int *d_tile_ids = d_tile_group + n_tiles;
+    int4 *d_rects = (int4 *)((uint8_t *)d_tile_group + srf_align_up(sizeof(int) * n_tiles * 2, 256));
+    std::vector<int4> rects(n_tiles);
+    for (int i = 0; i < n_tiles; ++i) rects[i] = make_int4(tiles[i].y, tiles[i].x, tiles[i].h, tiles[i].w);
     std::vector<int> ids;
     std::vector<int> ids_off(groups.size());
     for (size_t k = 0; k < groups.size(); ++k) {
@@ -849,6 +959,7 @@ int srf_fuse_device(srf_ctx *ctx, const srf_tile *tiles, int n_tiles, int C, int
     SRF_CHECK_CUDA(ctx, cudaMemcpyAsync(d_groups, gdev_img.data(), sizeof(GroupDev) * groups.size(), cudaMemcpyHostToDevice, st));
     SRF_CHECK_CUDA(ctx, cudaMemcpyAsync(d_tile_group, tile_group.data(), sizeof(int) * n_tiles, cudaMemcpyHostToDevice, st));
     SRF_CHECK_CUDA(ctx, cudaMemcpyAsync(d_tile_ids, ids.data(), sizeof(int) * n_tiles, cudaMemcpyHostToDevice, st));
+    SRF_CHECK_CUDA(ctx, cudaMemcpyAsync(d_rects, rects.data(), sizeof(int4) * n_tiles, cudaMemcpyHostToDevice, st));
 
     // ---- launches ----
     for (size_t k = 0; k < groups.size(); ++k) {
@@ -877,14 +988,14 @@ int srf_fuse_device(srf_ctx *ctx, const srf_tile *tiles, int n_tiles, int C, int
         if (n >= 2) {
             const int rows = max_rows(1, false);
             if (rows > 0) {
-                dim3 grid(srf_ceil_div(gi.lv[1].w, DN_BW), srf_ceil_div(rows, DN_BH), nt);
+                dim3 grid(srf_ceil_div(gi.lv[1].w, D8_BW), srf_ceil_div(rows, D8_ROWS), nt);
                 double px1 = 0; // level-1 pixels produced
                 for (int ti : groups[k].tiles) px1 += (double)(tdev[ti].g1[1] - tdev[ti].g0[1]) * gi.lv[1].w;
                 srf_launch_scope scope(ctx, "down_u8", px1 * C * (4.0 /*u8 in*/ + 4.0 /*f32 out*/), st);
                 if (C == 3)
-                    k_down_u8<3><<<grid, kThreads, 0, st>>>(d_tiles, ids_k, gi);
+                    k_down_u8<3><<<grid, 128 * 3, 0, st>>>(d_tiles, ids_k, gi);
                 else
-                    k_down_u8<1><<<grid, kThreads, 0, st>>>(d_tiles, ids_k, gi);
+                    k_down_u8<1><<<grid, 128, 0, st>>>(d_tiles, ids_k, gi);
             }
         }
         for (int l = 1; l + 1 < n; ++l) {
@@ -920,6 +1031,7 @@ int srf_fuse_device(srf_ctx *ctx, const srf_tile *tiles, int n_tiles, int C, int
         P.tiles = d_tiles;
         P.groups = d_groups;
         P.tile_group = d_tile_group;
+        P.rects = d_rects;
         P.n_tiles = n_tiles;
         P.out_h = out_h;
         P.out_w = out_w;
