@@ -140,8 +140,8 @@ typedef struct srf_iqa_sums {
     int64_t n_elems;    /* elements in that sum                                                         */
     double ssim_sum;    /* sum of the SSIM map over interior pixels (>=5 from every image edge) whose    */
     int64_t ssim_count; /*   row lies in [row_begin,row_end); and their number                          */
-    int32_t max_a;      /* max element of a / b over the band: the caller applies the reference's        */
-    int32_t max_b;      /*   `image.max() <= 1.0` rescale rule (quality_assessment_module.py:192-193)    */
+    int32_t bits_a;     /* bitwise OR of every byte of a / b over the band: max() <= 1 exactly when bits <= 1 -- */
+    int32_t bits_b;     /*   the caller applies the reference's `image.max() <= 1.0` rescale rule (q.a.m:192-193) */
 } srf_iqa_sums;
 
 /* replaces calculate_psnr + calculate_ssim(multiscale=True) of QualityAssessmentModule

@@ -32,7 +32,7 @@ class srf_profile_entry(C.Structure):
 
 class srf_iqa_sums(C.Structure):
     _fields_ = [("sq_err", c_int64), ("n_elems", c_int64), ("ssim_sum", C.c_double), ("ssim_count", c_int64),
-                ("max_a", C.c_int32), ("max_b", C.c_int32)]
+                ("bits_a", C.c_int32), ("bits_b", C.c_int32)]
 
 
 # every symbol include/srfuse.h declares: name -> (restype, argtypes)

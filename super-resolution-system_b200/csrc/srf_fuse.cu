@@ -156,35 +156,45 @@ __global__ void __launch_bounds__(128 * C) k_down_u8(const TileDev *__restrict__
     const size_t pitch = t.pitch;
     const int valid = w * C;
 
-    // staging role: (row j of the batch, group q)
-    const bool stager = threadIdx.x < D8_BATCH * D8_GROUPS;
-    const int sj = threadIdx.x / D8_GROUPS, sq = threadIdx.x % D8_GROUPS;
-    uint4 pre[C];
+    // staging role: task = (row j of the batch, group q); 144 tasks over NT threads
+    constexpr int N_TASKS = D8_BATCH * D8_GROUPS;
+    constexpr int TPT = (N_TASKS + NT - 1) / NT; // tasks per thread: 1 (C = 3) or 2 (C = 1)
+    uint4 pre[TPT][C];
     auto stage_load = [&](int b) {
-        if (!stager) return;
-        const int gy = srf_reflect101(in_y0 + b * D8_BATCH + sj, h);
-        const uint8_t *grow = src + (size_t)gy * pitch;
-        const int o = (px_g0 + 16 * sq) * C;
 #pragma unroll
-        for (int k = 0; k < C; ++k) pre[k] = load_u8_chunk(grow, o + 16 * k, valid);
+        for (int u = 0; u < TPT; ++u) {
+            const int task = threadIdx.x + u * NT;
+            if (task >= N_TASKS) continue;
+            const int sj = task / D8_GROUPS, sq = task % D8_GROUPS;
+            const int gy = srf_reflect101(in_y0 + b * D8_BATCH + sj, h);
+            const uint8_t *grow = src + (size_t)gy * pitch;
+            const int o = (px_g0 + 16 * sq) * C;
+#pragma unroll
+            for (int k = 0; k < C; ++k) pre[u][k] = load_u8_chunk(grow, o + 16 * k, valid);
+        }
     };
     auto stage_store = [&](int buf) {
-        if (!stager) return;
-        if (C == 3) {
-            const uint32_t *wv = reinterpret_cast<const uint32_t *>(&pre[0]);
-            uint32_t o0[4], o1[4], o2[4];
 #pragma unroll
-            for (int m = 0; m < 4; ++m) {
-                const uint32_t A = wv[3 * m], B = wv[3 * m + 1], Cw = wv[3 * m + 2];
-                o0[m] = __byte_perm(__byte_perm(A, B, 0x0630), Cw, 0x5210);
-                o1[m] = __byte_perm(__byte_perm(A, B, 0x0741), Cw, 0x6210);
-                o2[m] = __byte_perm(__byte_perm(A, B, 0x0052), Cw, 0x7410);
+        for (int u = 0; u < TPT; ++u) {
+            const int task = threadIdx.x + u * NT;
+            if (task >= N_TASKS) continue;
+            const int sj = task / D8_GROUPS, sq = task % D8_GROUPS;
+            if (C == 3) {
+                const uint32_t *wv = reinterpret_cast<const uint32_t *>(&pre[u][0]);
+                uint32_t o0[4], o1[4], o2[4];
+#pragma unroll
+                for (int m = 0; m < 4; ++m) {
+                    const uint32_t A = wv[3 * m], B = wv[3 * m + 1], Cw = wv[3 * m + 2];
+                    o0[m] = __byte_perm(__byte_perm(A, B, 0x0630), Cw, 0x5210);
+                    o1[m] = __byte_perm(__byte_perm(A, B, 0x0741), Cw, 0x6210);
+                    o2[m] = __byte_perm(__byte_perm(A, B, 0x0052), Cw, 0x7410);
+                }
+                *reinterpret_cast<uint4 *>(&s_pl[buf][sj][0][16 * sq]) = make_uint4(o0[0], o0[1], o0[2], o0[3]);
+                *reinterpret_cast<uint4 *>(&s_pl[buf][sj][C > 1 ? 1 : 0][16 * sq]) = make_uint4(o1[0], o1[1], o1[2], o1[3]);
+                *reinterpret_cast<uint4 *>(&s_pl[buf][sj][C > 2 ? 2 : 0][16 * sq]) = make_uint4(o2[0], o2[1], o2[2], o2[3]);
+            } else {
+                *reinterpret_cast<uint4 *>(&s_pl[buf][sj][0][16 * sq]) = pre[u][0];
             }
-            *reinterpret_cast<uint4 *>(&s_pl[buf][sj][0][16 * sq]) = make_uint4(o0[0], o0[1], o0[2], o0[3]);
-            *reinterpret_cast<uint4 *>(&s_pl[buf][sj][C > 1 ? 1 : 0][16 * sq]) = make_uint4(o1[0], o1[1], o1[2], o1[3]);
-            *reinterpret_cast<uint4 *>(&s_pl[buf][sj][C > 2 ? 2 : 0][16 * sq]) = make_uint4(o2[0], o2[1], o2[2], o2[3]);
-        } else {
-            *reinterpret_cast<uint4 *>(&s_pl[buf][sj][0][16 * sq]) = pre[0];
         }
     };
 

@@ -19,6 +19,7 @@ constexpr int IQ_RB = 64;    // S-map rows per CTA
 constexpr int IQ_R = 5;      // filter radius
 constexpr int IQ_TAPS = 11;
 constexpr int IQ_SROW = IQ_THREADS + 2 * IQ_R + 2; // staged gray columns (+2 keeps rows 16-byte multiples)
+constexpr int IQ_RAW = 448;                         // staged raw bytes per row and image: 15 + 138 * 3 rounded up to 16
 
 // exp(-k^2 / (2 * 1.5^2)) normalised, k = -5..5 (scipy.ndimage._gaussian_kernel1d(1.5, 0, 5))
 #define IQ_T0 1.028380084e-03f
@@ -32,7 +33,7 @@ struct IqaPartial {
     double ssim;
     unsigned long long sq;
     unsigned long long cnt;
-    int max_a, max_b;
+    int max_a, max_b; // bitwise OR of every owned byte: <= 1 exactly when the image's max() <= 1
 };
 
 struct IqaParams {
@@ -45,26 +46,34 @@ struct IqaParams {
     IqaPartial *partials;
 };
 
-template <int C>
-__device__ __forceinline__ void load_px(const uint8_t *row, int col, bool ok, int scale, int (&v)[C])
+// 16-byte chunk at absolute address q (16-byte aligned), clipped to the image's byte range [lo, hi)
+__device__ __forceinline__ uint4 load_chunk_abs(const uint8_t *q, const uint8_t *lo, const uint8_t *hi)
 {
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (q >= lo && q + 16 <= hi) {
+        v = *reinterpret_cast<const uint4 *>(q);
+    } else if (q + 16 > lo && q < hi) {
+        uint8_t *b = reinterpret_cast<uint8_t *>(&v);
 #pragma unroll
-    for (int c = 0; c < C; ++c) v[c] = 0;
-    if (ok) {
-        const uint8_t *p = row + (size_t)col * C;
-#pragma unroll
-        for (int c = 0; c < C; ++c) {
-            int t = p[c];
-            if (scale) t = (t * 255) & 0xFF; // (image * 255).astype(uint8), quality_assessment_module.py:192-193
-            v[c] = t;
-        }
+        for (int e = 0; e < 16; ++e) b[e] = (q + e >= lo && q + e < hi) ? q[e] : (uint8_t)0;
     }
+    return v;
 }
 
 template <int C>
-__device__ __forceinline__ int to_gray(const int (&v)[C])
+__device__ __forceinline__ int gray_of(const uint8_t *p, int scale, int &bits, int (&v)[C])
 {
-    if (C == 1) return v[0];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        int t = p[c];
+        if (scale) t = (t * 255) & 0xFF; // (image * 255).astype(uint8), quality_assessment_module.py:192-193
+        v[c] = t;
+    }
+    if (C == 1) {
+        bits |= v[0];
+        return v[0];
+    }
+    bits |= v[0] | v[C > 1 ? 1 : 0] | v[C > 2 ? 2 : 0];
     return (v[0] * 9798 + v[C > 1 ? 1 : 0] * 19235 + v[C > 2 ? 2 : 0] * 3735 + 16384) >> 15; // cv2 COLOR_RGB2GRAY, uint8
 }
 
@@ -79,9 +88,14 @@ __device__ __forceinline__ float tap11(const float (&x)[IQ_TAPS])
     return s;
 }
 
+// Per CTA: 128 S-map columns x IQ_RB rows.  A four-stage software pipeline over the input rows, one barrier per
+// row:  L(r+4) 16-byte global loads of the raw RGB bytes into registers (56 loader threads, both images)
+//       S(r+2) registers -> raw smem row        G(r+1) raw bytes -> gray float row (+ squared error, OR of bytes)
+//       H(r)   horizontal 11-tap from the gray row into the register ring, vertical 11-tap, SSIM, accumulate
 template <int C>
 __global__ void __launch_bounds__(IQ_THREADS) k_psnr_ssim(IqaParams P)
 {
+    __shared__ __align__(16) uint8_t s_raw[2][2][IQ_RAW];
     __shared__ float s_a[2][IQ_SROW];
     __shared__ float s_b[2][IQ_SROW];
     __shared__ double s_red[IQ_THREADS / 32];
@@ -94,48 +108,77 @@ __global__ void __launch_bounds__(IQ_THREADS) k_psnr_ssim(IqaParams P)
     const int ry0 = P.row_begin + blockIdx.y * IQ_RB;
     const int ry1 = min(ry0 + IQ_RB, P.row_end);
     const int h = P.h, w = P.w;
-    const int col1 = cx0 - IQ_R + t;           // every thread's first pixel
+    const int col1 = cx0 - IQ_R + t;              // every thread's first pixel
     const int col2 = cx0 + IQ_THREADS - IQ_R + t; // threads 0..9: the right halo
     const bool has2 = t < 2 * IQ_R;
-    const bool own1 = col1 >= cx0 && col1 < w;  // owned = inside this CTA's strip (for the PSNR sum)
+    const bool own1 = col1 >= cx0 && col1 < w; // owned = inside this CTA's strip (for the PSNR sum)
     const bool own2 = has2 && col2 < cx0 + IQ_THREADS && col2 < w;
 
-    unsigned int sq = 0; // <= 64 rows * 2 px * 3 * 65025 < 2^32
-    int mxa = 0, mxb = 0;
+    // loader role: warp 0 lanes 0..27 -> image a, warp 1 lanes 0..27 -> image b
+    const int limg = t >> 5, lchunk = t & 31;
+    const bool loader = (limg < 2) && (lchunk < IQ_RAW / 16);
+    const uint8_t *lbase = limg ? P.b : P.a;
+    const size_t lpitch = limg ? P.pitch_b : P.pitch_a;
+    const uint8_t *llo = lbase, *lhi = lbase + (size_t)(h - 1) * lpitch + (size_t)w * C;
+    const long long col_off = (long long)(cx0 - IQ_R) * C;
 
-    auto fetch = [&](int r, int (&a1)[C], int (&b1)[C], int (&a2)[C], int (&b2)[C]) {
-        const bool rok = r >= 0 && r < h;
-        const uint8_t *ra = P.a + (size_t)(rok ? r : 0) * P.pitch_a;
-        const uint8_t *rb = P.b + (size_t)(rok ? r : 0) * P.pitch_b;
-        load_px<C>(ra, col1, rok && col1 >= 0 && col1 < w, P.scale_a, a1);
-        load_px<C>(rb, col1, rok && col1 >= 0 && col1 < w, P.scale_b, b1);
-        load_px<C>(ra, col2, rok && has2 && col2 < w, P.scale_a, a2);
-        load_px<C>(rb, col2, rok && has2 && col2 < w, P.scale_b, b2);
+    auto row_mis = [&](const uint8_t *base, size_t pitch, int r) {
+        return (int)(reinterpret_cast<uintptr_t>(base + (long long)r * (long long)pitch + col_off) & 15);
     };
-    auto stash = [&](int r, int buf, const int (&a1)[C], const int (&b1)[C], const int (&a2)[C], const int (&b2)[C]) {
-        const bool rown = r >= ry0 && r < ry1;
-        if (rown) {
+    auto L = [&](int r) {
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (loader && r >= 0 && r < h) {
+            const uint8_t *A = lbase + (long long)r * (long long)lpitch + col_off;
+            const uint8_t *q = A - (reinterpret_cast<uintptr_t>(A) & 15) + 16 * lchunk;
+            v = load_chunk_abs(q, llo, lhi);
+        }
+        return v;
+    };
+    auto Sst = [&](int r, const uint4 &v) {
+        if (loader) *reinterpret_cast<uint4 *>(&s_raw[r & 1][limg][16 * lchunk]) = v;
+    };
+
+    unsigned int sq = 0; // <= 64 rows * 2 px * 3 * 65025 < 2^32
+    int bits_a = 0, bits_b = 0;
+    auto G = [&](int r) {
+        const int buf = r & 1;
+        float ga1 = 0.f, gb1 = 0.f, ga2 = 0.f, gb2 = 0.f;
+        if (r >= 0 && r < h) {
+            const uint8_t *ra = &s_raw[buf][0][row_mis(P.a, P.pitch_a, r)];
+            const uint8_t *rb = &s_raw[buf][1][row_mis(P.b, P.pitch_b, r)];
+            const bool rown = r >= ry0 && r < ry1;
+            int va[C], vb[C], da = 0, db = 0;
+            ga1 = (float)(gray_of<C>(ra + t * C, P.scale_a, da, va) - 128);
+            gb1 = (float)(gray_of<C>(rb + t * C, P.scale_b, db, vb) - 128);
+            if (rown && own1) {
+                bits_a |= da;
+                bits_b |= db;
 #pragma unroll
-            for (int c = 0; c < C; ++c) {
-                if (own1) {
-                    const int d = a1[c] - b1[c];
+                for (int c = 0; c < C; ++c) {
+                    const int d = va[c] - vb[c];
                     sq += (unsigned)(d * d);
-                    mxa = max(mxa, a1[c]);
-                    mxb = max(mxb, b1[c]);
                 }
-                if (own2) {
-                    const int d = a2[c] - b2[c];
-                    sq += (unsigned)(d * d);
-                    mxa = max(mxa, a2[c]);
-                    mxb = max(mxb, b2[c]);
+            }
+            if (has2) {
+                da = db = 0;
+                ga2 = (float)(gray_of<C>(ra + (IQ_THREADS + t) * C, P.scale_a, da, va) - 128);
+                gb2 = (float)(gray_of<C>(rb + (IQ_THREADS + t) * C, P.scale_b, db, vb) - 128);
+                if (rown && own2) {
+                    bits_a |= da;
+                    bits_b |= db;
+#pragma unroll
+                    for (int c = 0; c < C; ++c) {
+                        const int d = va[c] - vb[c];
+                        sq += (unsigned)(d * d);
+                    }
                 }
             }
         }
-        s_a[buf][t] = (float)(to_gray<C>(a1) - 128);
-        s_b[buf][t] = (float)(to_gray<C>(b1) - 128);
+        s_a[buf][t] = ga1;
+        s_b[buf][t] = gb1;
         if (has2) {
-            s_a[buf][IQ_THREADS + t] = (float)(to_gray<C>(a2) - 128);
-            s_b[buf][IQ_THREADS + t] = (float)(to_gray<C>(b2) - 128);
+            s_a[buf][IQ_THREADS + t] = ga2;
+            s_b[buf][IQ_THREADS + t] = gb2;
         }
     };
 
@@ -149,26 +192,27 @@ __global__ void __launch_bounds__(IQ_THREADS) k_psnr_ssim(IqaParams P)
     unsigned int scount = 0;
     const int col = cx0 + t; // this thread's S-map column
     const bool col_interior = col >= IQ_R && col < w - IQ_R;
+    const float C1 = P.c1, C2 = P.c2;
 
     const int r_first = ry0 - IQ_R, r_last = ry1 + IQ_R; // input rows [r_first, r_last)
-    {
-        int a1[C], b1[C], a2[C], b2[C];
-        fetch(r_first, a1, b1, a2, b2);
-        stash(r_first, 0, a1, b1, a2, b2);
-    }
+    // prologue: gray(r_first) ready, raw(r_first+1) staged, rows r_first+2 / +3 in flight
+    Sst(r_first, L(r_first));
+    Sst(r_first + 1, L(r_first + 1));
+    __syncthreads();
+    G(r_first);
+    uint4 cur = L(r_first + 2), nxt = L(r_first + 3);
     __syncthreads();
 
-    int buf = 0;
     for (int base = r_first; base < r_last; base += IQ_TAPS) {
 #pragma unroll
         for (int ph = 0; ph < IQ_TAPS; ++ph) {
             const int r_in = base + ph;
             if (r_in >= r_last) break;
-            int a1[C], b1[C], a2[C], b2[C];
-            const bool more = r_in + 1 < r_last;
-            if (more) fetch(r_in + 1, a1, b1, a2, b2);
+            const int buf = r_in & 1;
+            // L(r+4) first: its latency hides behind this row's arithmetic and the next row's
+            const uint4 fresh = L(r_in + 4);
 
-            // horizontal pass on row r_in
+            // H(r): horizontal pass on gray row r_in
             float xa[IQ_TAPS], xb[IQ_TAPS], xs[IQ_TAPS], xp[IQ_TAPS];
 #pragma unroll
             for (int k = 0; k < IQ_TAPS; ++k) {
@@ -197,7 +241,6 @@ __global__ void __launch_bounds__(IQ_THREADS) k_psnr_ssim(IqaParams P)
                 const float ux = ua + 128.f, uy = ub + 128.f;
                 const float vsum = f[2] - fmaf(ua, ua, ub * ub); // vx + vy (shift invariant)
                 const float vxy = f[3] - ua * ub;
-                const float C1 = P.c1, C2 = P.c2;
                 const float A1 = fmaf(2.f * ux, uy, C1), A2 = fmaf(2.f, vxy, C2);
                 const float B1 = fmaf(ux, ux, fmaf(uy, uy, C1)), B2 = vsum + C2;
                 const float S = __fdividef(A1 * A2, B1 * B2);
@@ -206,22 +249,25 @@ __global__ void __launch_bounds__(IQ_THREADS) k_psnr_ssim(IqaParams P)
                     scount++;
                 }
             }
-            if (more) stash(r_in + 1, buf ^ 1, a1, b1, a2, b2);
+            if (r_in + 1 < r_last) G(r_in + 1);
+            Sst(r_in + 2, cur);
+            cur = nxt;
+            nxt = fresh;
             __syncthreads();
-            buf ^= 1;
         }
     }
 
     // ---- block reduction (fixed order) ----
     double ds = (double)ssum;
     unsigned long long dsq = sq, dcnt = scount;
+    int mxa = bits_a, mxb = bits_b;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         ds += __shfl_down_sync(0xffffffffu, ds, o);
         dsq += __shfl_down_sync(0xffffffffu, dsq, o);
         dcnt += __shfl_down_sync(0xffffffffu, dcnt, o);
-        mxa = max(mxa, __shfl_down_sync(0xffffffffu, mxa, o));
-        mxb = max(mxb, __shfl_down_sync(0xffffffffu, mxb, o));
+        mxa |= __shfl_down_sync(0xffffffffu, mxa, o);
+        mxb |= __shfl_down_sync(0xffffffffu, mxb, o);
     }
     if ((t & 31) == 0) {
         s_red[t >> 5] = ds;
@@ -242,8 +288,8 @@ __global__ void __launch_bounds__(IQ_THREADS) k_psnr_ssim(IqaParams P)
             p.ssim += s_red[k];
             p.sq += s_sq[k];
             p.cnt += s_cnt[k];
-            p.max_a = max(p.max_a, s_mx[0][k]);
-            p.max_b = max(p.max_b, s_mx[1][k]);
+            p.max_a |= s_mx[0][k];
+            p.max_b |= s_mx[1][k];
         }
         P.partials[blockIdx.y * gridDim.x + blockIdx.x] = p;
     }
@@ -264,8 +310,8 @@ __global__ void __launch_bounds__(256) k_iqa_reduce(const IqaPartial *__restrict
         p.ssim += q.ssim;
         p.sq += q.sq;
         p.cnt += q.cnt;
-        p.max_a = max(p.max_a, q.max_a);
-        p.max_b = max(p.max_b, q.max_b);
+        p.max_a |= q.max_a;
+        p.max_b |= q.max_b;
     }
     s[threadIdx.x] = p;
     __syncthreads();
@@ -276,8 +322,8 @@ __global__ void __launch_bounds__(256) k_iqa_reduce(const IqaPartial *__restrict
             x.ssim += y.ssim;
             x.sq += y.sq;
             x.cnt += y.cnt;
-            x.max_a = max(x.max_a, y.max_a);
-            x.max_b = max(x.max_b, y.max_b);
+            x.max_a |= y.max_a;
+            x.max_b |= y.max_b;
         }
         __syncthreads();
     }
@@ -334,8 +380,8 @@ void srf_iqa_collect(srf_ctx *ctx, int w, int C, int row_begin, int row_end, srf
     out->n_elems = (int64_t)(row_end - row_begin) * w * C;
     out->ssim_sum = f->ssim;
     out->ssim_count = (int64_t)f->cnt;
-    out->max_a = f->max_a;
-    out->max_b = f->max_b;
+    out->bits_a = f->max_a;
+    out->bits_b = f->max_b;
 }
 
 static int iqa_device(srf_ctx *ctx, const uint8_t *a, size_t pa, const uint8_t *b, size_t pb, int h, int w, int C, int scale_a, int scale_b,

@@ -124,7 +124,7 @@ class SuperResolutionPipeline:
     def fuse_and_assess(self, tile_infos: List[TileInfo], reference: np.ndarray, output_shape=None, out=None):
         """stages 3 + 4 in one device round trip: fused canvas + the full-reference report against `reference`"""
         canvas, sums = self.blending_module.fuse_and_assess(tile_infos, np.ascontiguousarray(reference), output_shape, out=out)
-        if sums.max_a <= 1 or sums.max_b <= 1:  # the reference's max() <= 1 rescale rule: take the two-pass route
+        if sums.bits_a <= 1 or sums.bits_b <= 1:  # the reference's max() <= 1 rescale rule: take the two-pass route
             return canvas, self.quality_module.evaluate_full_reference(reference, canvas, scale_factor=2)
         if sums.ssim_count <= 0:
             raise ValueError("canvas smaller than the 11x11 SSIM window")

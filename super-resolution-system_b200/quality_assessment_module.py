@@ -62,7 +62,7 @@ class QualityAssessmentModule:
     # ------------------------------------------------------------------ preprocessing
     def _preprocess_image(self, image, to_tensor: bool = False):
         """tensor (C,H,W)/(1,C,H,W) -> HWC; float images in [0, 1] -> uint8 by *255 and truncation.  uint8 images are
-        returned untouched: their `max() <= 1` case is resolved inside the kernel pass (srf_iqa_sums.max_a/max_b)."""
+        returned untouched: their `max() <= 1` case is resolved inside the kernel pass (srf_iqa_sums.bits_a/bits_b)."""
         if is_cuda_tensor(image) and image.dtype == torch.uint8:
             return image
         if torch is not None and isinstance(image, torch.Tensor):
@@ -110,9 +110,9 @@ class QualityAssessmentModule:
             _native.check(rc, ctx)
 
         run(0, 0)
-        if row_range is None and (sums.max_a <= 1 or sums.max_b <= 1):
+        if row_range is None and (sums.bits_a <= 1 or sums.bits_b <= 1):
             # the reference rescales an image whose max() <= 1.0 by 255 (q.a.m:192-193) -- also an all-0/1 uint8 one
-            run(int(sums.max_a <= 1), int(sums.max_b <= 1))
+            run(int(sums.bits_a <= 1), int(sums.bits_b <= 1))
         return sums
 
     @staticmethod

@@ -130,7 +130,7 @@ def test_pipeline_api_surface(srs):
 
 
 def test_iqa_finish_matches_oracle_formula(srs, oracle):
-    s = srs._native.srf_iqa_sums(sq_err=123456, n_elems=3000, ssim_sum=87.5, ssim_count=100, max_a=255, max_b=255)
+    s = srs._native.srf_iqa_sums(sq_err=123456, n_elems=3000, ssim_sum=87.5, ssim_count=100, bits_a=255, bits_b=255)
     p, q = srs.QualityAssessmentModule.finish(s)
     assert p == pytest.approx(10 * np.log10(255.0 ** 2 / (123456 / 3000)), rel=1e-15) and q == 0.875
     s.sq_err = 0
