@@ -77,23 +77,12 @@ __device__ __forceinline__ int gray_of(const uint8_t *p, int scale, int &bits, i
     return (v[0] * 9798 + v[C > 1 ? 1 : 0] * 19235 + v[C > 2 ? 2 : 0] * 3735 + 16384) >> 15; // cv2 COLOR_RGB2GRAY, uint8
 }
 
-__device__ __forceinline__ float tap11(const float (&x)[IQ_TAPS])
-{
-    float s = x[5] * IQ_T5;
-    s = fmaf(x[4] + x[6], IQ_T4, s);
-    s = fmaf(x[3] + x[7], IQ_T3, s);
-    s = fmaf(x[2] + x[8], IQ_T2, s);
-    s = fmaf(x[1] + x[9], IQ_T1, s);
-    s = fmaf(x[0] + x[10], IQ_T0, s);
-    return s;
-}
-
 // Per CTA: 128 S-map columns x IQ_RB rows.  A four-stage software pipeline over the input rows, one barrier per
 // row:  L(r+4) 16-byte global loads of the raw RGB bytes into registers (56 loader threads, both images)
 //       S(r+2) registers -> raw smem row        G(r+1) raw bytes -> gray float row (+ squared error, OR of bytes)
 //       H(r)   horizontal 11-tap from the gray row into the register ring, vertical 11-tap, SSIM, accumulate
 template <int C>
-__global__ void __launch_bounds__(IQ_THREADS) k_psnr_ssim(IqaParams P)
+__global__ void __launch_bounds__(IQ_THREADS, 5) k_psnr_ssim(IqaParams P)
 {
     __shared__ __align__(16) uint8_t s_raw[2][2][IQ_RAW];
     __shared__ float s_a[2][IQ_SROW];
@@ -114,6 +103,7 @@ __global__ void __launch_bounds__(IQ_THREADS) k_psnr_ssim(IqaParams P)
     const bool own1 = col1 >= cx0 && col1 < w; // owned = inside this CTA's strip (for the PSNR sum)
     const bool own2 = has2 && col2 < cx0 + IQ_THREADS && col2 < w;
 
+    const int r_first = ry0 - IQ_R, r_last = ry1 + IQ_R; // input rows [r_first, r_last)
     // loader role: warp 0 lanes 0..27 -> image a, warp 1 lanes 0..27 -> image b
     const int limg = t >> 5, lchunk = t & 31;
     const bool loader = (limg < 2) && (lchunk < IQ_RAW / 16);
@@ -127,7 +117,7 @@ __global__ void __launch_bounds__(IQ_THREADS) k_psnr_ssim(IqaParams P)
     };
     auto L = [&](int r) {
         uint4 v = make_uint4(0, 0, 0, 0);
-        if (loader && r >= 0 && r < h) {
+        if (loader && r >= 0 && r < h && r < r_last) {
             const uint8_t *A = lbase + (long long)r * (long long)lpitch + col_off;
             const uint8_t *q = A - (reinterpret_cast<uintptr_t>(A) & 15) + 16 * lchunk;
             v = load_chunk_abs(q, llo, lhi);
@@ -194,7 +184,6 @@ __global__ void __launch_bounds__(IQ_THREADS) k_psnr_ssim(IqaParams P)
     const bool col_interior = col >= IQ_R && col < w - IQ_R;
     const float C1 = P.c1, C2 = P.c2;
 
-    const int r_first = ry0 - IQ_R, r_last = ry1 + IQ_R; // input rows [r_first, r_last)
     // prologue: gray(r_first) ready, raw(r_first+1) staged, rows r_first+2 / +3 in flight
     Sst(r_first, L(r_first));
     Sst(r_first + 1, L(r_first + 1));
@@ -212,19 +201,26 @@ __global__ void __launch_bounds__(IQ_THREADS) k_psnr_ssim(IqaParams P)
             // L(r+4) first: its latency hides behind this row's arithmetic and the next row's
             const uint4 fresh = L(r_in + 4);
 
-            // H(r): horizontal pass on gray row r_in
-            float xa[IQ_TAPS], xb[IQ_TAPS], xs[IQ_TAPS], xp[IQ_TAPS];
-#pragma unroll
-            for (int k = 0; k < IQ_TAPS; ++k) {
-                xa[k] = s_a[buf][t + k];
-                xb[k] = s_b[buf][t + k];
-                xs[k] = fmaf(xa[k], xa[k], xb[k] * xb[k]);
-                xp[k] = xa[k] * xb[k];
+            // H(r): horizontal pass on gray row r_in -- four FMA chains with literal taps, products formed once per tap
+            {
+                float ha = 0.f, hb = 0.f, hs = 0.f, hp = 0.f;
+                const float *pa = &s_a[buf][t], *pb = &s_b[buf][t];
+#define IQ_HTAP(K, T)                          \
+    {                                          \
+        const float a = pa[K], b = pb[K];      \
+        ha = fmaf(a, T, ha);                   \
+        hb = fmaf(b, T, hb);                   \
+        hs = fmaf(fmaf(a, a, b * b), T, hs);   \
+        hp = fmaf(a * b, T, hp);               \
+    }
+                IQ_HTAP(0, IQ_T0) IQ_HTAP(1, IQ_T1) IQ_HTAP(2, IQ_T2) IQ_HTAP(3, IQ_T3) IQ_HTAP(4, IQ_T4) IQ_HTAP(5, IQ_T5)
+                IQ_HTAP(6, IQ_T4) IQ_HTAP(7, IQ_T3) IQ_HTAP(8, IQ_T2) IQ_HTAP(9, IQ_T1) IQ_HTAP(10, IQ_T0)
+#undef IQ_HTAP
+                ring[0][ph] = ha;
+                ring[1][ph] = hb;
+                ring[2][ph] = hs;
+                ring[3][ph] = hp;
             }
-            ring[0][ph] = tap11(xa);
-            ring[1][ph] = tap11(xb);
-            ring[2][ph] = tap11(xs);
-            ring[3][ph] = tap11(xp);
 
             // vertical pass: output row r = r_in - 5 uses input rows r_in-10 .. r_in = ring slots (ph+1+k) % 11
             const int r = r_in - IQ_R;
@@ -232,10 +228,19 @@ __global__ void __launch_bounds__(IQ_THREADS) k_psnr_ssim(IqaParams P)
                 float f[4];
 #pragma unroll
                 for (int s = 0; s < 4; ++s) {
-                    float v[IQ_TAPS];
-#pragma unroll
-                    for (int k = 0; k < IQ_TAPS; ++k) v[k] = ring[s][(ph + 1 + k) % IQ_TAPS];
-                    f[s] = tap11(v);
+                    float v = 0.f;
+                    v = fmaf(ring[s][(ph + 1) % IQ_TAPS], IQ_T0, v);
+                    v = fmaf(ring[s][(ph + 2) % IQ_TAPS], IQ_T1, v);
+                    v = fmaf(ring[s][(ph + 3) % IQ_TAPS], IQ_T2, v);
+                    v = fmaf(ring[s][(ph + 4) % IQ_TAPS], IQ_T3, v);
+                    v = fmaf(ring[s][(ph + 5) % IQ_TAPS], IQ_T4, v);
+                    v = fmaf(ring[s][(ph + 6) % IQ_TAPS], IQ_T5, v);
+                    v = fmaf(ring[s][(ph + 7) % IQ_TAPS], IQ_T4, v);
+                    v = fmaf(ring[s][(ph + 8) % IQ_TAPS], IQ_T3, v);
+                    v = fmaf(ring[s][(ph + 9) % IQ_TAPS], IQ_T2, v);
+                    v = fmaf(ring[s][(ph + 10) % IQ_TAPS], IQ_T1, v);
+                    v = fmaf(ring[s][(ph + 11) % IQ_TAPS], IQ_T0, v);
+                    f[s] = v;
                 }
                 const float ua = f[0], ub = f[1];
                 const float ux = ua + 128.f, uy = ub + 128.f;
