@@ -109,7 +109,11 @@ __global__ void __launch_bounds__(IQ_THREADS, 5) k_psnr_ssim(IqaParams P)
     const bool loader = (limg < 2) && (lchunk < IQ_RAW / 16);
     const uint8_t *lbase = limg ? P.b : P.a;
     const size_t lpitch = limg ? P.pitch_b : P.pitch_a;
-    const uint8_t *llo = lbase, *lhi = lbase + (size_t)(h - 1) * lpitch + (size_t)w * C;
+    // bytes this launch may touch: rows [row_begin - 5, row_end + 5) of the image, clipped (a band-staged image only
+    // holds those rows)
+    const int vr0 = max(P.row_begin - IQ_R, 0), vr1 = min(P.row_end + IQ_R, h);
+    const uint8_t *llo = lbase + (long long)vr0 * (long long)lpitch;
+    const uint8_t *lhi = lbase + (long long)(vr1 - 1) * (long long)lpitch + (long long)w * C;
     const long long col_off = (long long)(cx0 - IQ_R) * C;
 
     auto row_mis = [&](const uint8_t *base, size_t pitch, int r) {
