@@ -168,9 +168,10 @@ def run_b200(args, wl):
     lib = native.load()
 
     H, W = wl.canvas_hw
-    r0, r1 = __import__("workloads").band(rank, world, H)
-    e0, e1 = max(r0 - IQA_HALO, 0), min(r1 + IQA_HALO, H)  # rows this rank fuses (own band + SSIM halo)
-    mine = [i for i, (t, (y, x)) in enumerate(zip(wl.tiles, wl.positions_yx)) if y < e1 and y + t.shape[0] > e0]
+    D = pkg.distributed
+    r0, r1 = D.band(rank, world, H)
+    e0, e1 = D.fuse_rows(rank, world, H)  # rows this rank fuses (own band + SSIM halo)
+    mine = D.tiles_for_rows(wl.positions_yx, [t.shape[0] for t in wl.tiles], e0, e1)
     bm = pkg.BlendingModule(num_levels=wl.levels, device=local)
     qa = pkg.QualityAssessmentModule(device=f"cuda:{local}")
 
@@ -178,17 +179,11 @@ def run_b200(args, wl):
     d_tiles = [pkg.TileInfo(torch.from_numpy(wl.tiles[i]).to(dev), wl.positions_yx[i][1], wl.positions_yx[i][0], 0, 0) for i in mine]
     d_ref = torch.from_numpy(wl.reference).to(dev)
     d_canvas = torch.zeros((H, W, 3), dtype=torch.uint8, device=dev)
-    red = torch.zeros(3, dtype=torch.float64, device=dev)
 
     def step_device():
         bm.laplacian_fusion(d_tiles, output_shape=(H, W), row_range=(e0, e1), out=d_canvas)
         s = qa.psnr_ssim_sums(d_ref, d_canvas, row_range=(r0, r1))
-        if world > 1:
-            red[0], red[1], red[2] = float(s.sq_err), s.ssim_sum, float(s.ssim_count)
-            dist.all_reduce(red)
-            v = red.tolist()
-            s.sq_err, s.ssim_sum, s.ssim_count = int(v[0]), v[1], int(v[2])
-            s.n_elems = H * W * 3
+        s = D.allreduce_sums(s, H * W * 3, device=dev)  # NCCL all-reduce of the partial sums (no-op at N = 1)
         return qa.finish(s)
 
     def timed(fn, steps, sampler=None):

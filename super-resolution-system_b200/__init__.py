@@ -7,7 +7,7 @@ The modules keep the reference's names, so putting this directory on sys.path ma
 `from main import PipelineConfig, SuperResolutionPipeline` resolve to the GPU implementation.
 All compute goes through libsrfuse.so (csrc/, C ABI in include/srfuse.h); there is no CPU fallback.
 """
-from . import _native, build  # noqa: F401
+from . import _native, build, distributed  # noqa: F401
 from .tiling_module import TilingModule, Tile, TileMetadata, PaddingMode, TileStatus  # noqa: F401
 from .blending_module import BlendingModule, TileInfo, WeightType, FusionMethod  # noqa: F401
 from .quality_assessment_module import QualityAssessmentModule, QualityThresholds, ScaleConfig  # noqa: F401

@@ -56,6 +56,9 @@ struct srf_ctx {
     cudaEvent_t ev_aux[3] = {nullptr, nullptr, nullptr};
     bool ev_valid = false;
     std::vector<cudaEvent_t> ev_pool;
+    // weight pyramids of the previous fuse call still valid in ws_pyr: one key per shape group (srf_fuse.cu)
+    std::vector<uint64_t> wcache_keys;
+    const void *wcache_base = nullptr;
     // per-kernel profiling (srf_profile_enable)
     bool profile = false;
     struct ProfRec {

@@ -1,0 +1,52 @@
+"""Band sharding across the GPUs of one box (one process per GPU, torch.distributed).
+
+The canvas is cut into `world` horizontal bands.  A rank fuses its band (plus a 5-row halo each side, so the 11x11
+SSIM window never needs a neighbour's pixels) from the tiles that reach it -- per-tile pyramids have tile-local
+borders, so a rank recomputes the pyramid rows its band depends on (libsrfuse derives those row ranges itself from
+`row_begin/row_end`) and the data path needs NO collective.  The only exchange is the all-reduce of the additive
+PSNR / SSIM partial sums (srf_iqa_sums): three numbers per rank, over NCCL on the GPUs (gloo in the CPU tests).
+"""
+from __future__ import annotations
+
+from typing import List, Sequence, Tuple
+
+from . import _native
+from ._arrays import torch
+
+IQA_HALO = 5  # radius of the 11-tap SSIM window
+
+
+def band(rank: int, world: int, rows: int) -> Tuple[int, int]:
+    """canvas rows [r0, r1) owned by `rank`: ceil(rows / world) rows each, the last band takes what is left"""
+    per = -(-rows // world)
+    return min(rank * per, rows), min((rank + 1) * per, rows)
+
+
+def fuse_rows(rank: int, world: int, rows: int) -> Tuple[int, int]:
+    """rows a rank must FUSE: its band widened by the SSIM halo, clipped to the canvas"""
+    r0, r1 = band(rank, world, rows)
+    if r0 >= r1:
+        return r0, r0
+    return max(r0 - IQA_HALO, 0), min(r1 + IQA_HALO, rows)
+
+
+def tiles_for_rows(positions_yx: Sequence[Tuple[int, int]], heights: Sequence[int], r0: int, r1: int) -> List[int]:
+    """indices (list order kept -- it is the accumulation order) of the tiles that intersect canvas rows [r0, r1)"""
+    return [i for i, ((y, _), h) in enumerate(zip(positions_yx, heights)) if y < r1 and y + h > r0]
+
+
+def allreduce_sums(sums, total_elems: int, group=None, device=None):
+    """sum srf_iqa_sums over the ranks of `group` (in place) and return it.  sq_err and ssim_count are integers below
+    2^53, exact in float64; bits_a / bits_b are OR-ed by a max-reduce of their <=1 / >1 class."""
+    import torch.distributed as dist
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return sums
+    t = torch.tensor([float(sums.sq_err), sums.ssim_sum, float(sums.ssim_count)], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    b = torch.tensor([float(sums.bits_a), float(sums.bits_b)], dtype=torch.float64, device=device)
+    dist.all_reduce(b, op=dist.ReduceOp.MAX, group=group)
+    v, bv = t.tolist(), b.tolist()
+    sums.sq_err, sums.ssim_sum, sums.ssim_count = int(v[0]), v[1], int(v[2])
+    sums.n_elems = int(total_elems)
+    sums.bits_a, sums.bits_b = int(bv[0]), int(bv[1])
+    return sums

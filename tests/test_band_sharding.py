@@ -1,0 +1,80 @@
+"""CPU suite, part 3: the N > 1 host logic under a 2-process gloo group -- band partition, tile selection and the
+all-reduce of the PSNR / SSIM partial sums.  Each rank's partial sums come from the oracle restricted to its band
+(the GPU kernel produces the same sums per band: tests/test_gpu_parity.py::test_iqa_bands_add_up)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+    import oracle
+    import super_resolution_system_b200 as srs
+    from helpers import synth
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(77)  # same image pair on every rank
+        a = synth(rng, 151, 200)
+        b = np.clip(a.astype(np.int16) + rng.integers(-9, 10, a.shape), 0, 255).astype(np.uint8)
+        H, W = a.shape[:2]
+        r0, r1 = srs.distributed.band(rank, world, H)
+        io = oracle.iqa_oracle
+        smap = io.ssim_map_interior(io.rgb_to_gray(a), io.rgb_to_gray(b))  # rows 5 .. H-6
+        lo, hi = max(r0, 5), min(r1, H - 5)
+        part = srs._native.srf_iqa_sums()
+        part.sq_err = io.sq_err_sum(a[r0:r1], b[r0:r1])
+        part.n_elems = (r1 - r0) * W * 3
+        part.ssim_sum = float(smap[lo - 5:hi - 5].sum()) if hi > lo else 0.0
+        part.ssim_count = max(hi - lo, 0) * (W - 10)
+        part.bits_a = part.bits_b = 255
+        total = srs.distributed.allreduce_sums(part, H * W * 3)
+        psnr, ssim = srs.QualityAssessmentModule.finish(total)
+        q.put((rank, (r0, r1), psnr, ssim, io.psnr(a, b), io.ssim(a, b)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_allreduce_matches_single_pass():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    bands = sorted(o[1] for o in out)
+    assert bands == [(0, 76), (76, 151)]
+    for _, _, psnr, ssim, want_p, want_s in out:
+        assert psnr == pytest.approx(want_p, rel=1e-12)
+        assert ssim == pytest.approx(want_s, rel=1e-12)
+
+
+def test_band_partition_and_tile_selection(srs):
+    d = srs.distributed
+    for rows, world in [(11546, 8), (11546, 4), (11546, 2), (11546, 1), (10, 8), (7, 3)]:
+        bands = [d.band(r, world, rows) for r in range(world)]
+        assert bands[0][0] == 0 and bands[-1][1] == rows
+        assert all(a[1] == b[0] for a, b in zip(bands, bands[1:]))
+        for r in range(world):
+            f0, f1 = d.fuse_rows(r, world, rows)
+            b0, b1 = bands[r]
+            assert (f0, f1) == ((max(b0 - 5, 0), min(b1 + 5, rows)) if b1 > b0 else (b0, b0))
+    # the 200 MP grid: 6 x 4 tiles of 4096 rows at y = 0, 3278, 6556, 9834
+    pos = [(y, x) for y in (0, 3278, 6556, 9834) for x in range(0, 6 * 3278, 3278)]
+    hs = [4096] * len(pos)
+    sel = d.tiles_for_rows(pos, hs, *d.fuse_rows(0, 8, 11546))
+    assert sel == list(range(6))                      # band 0 (rows 0..1448) only sees the first tile row
+    sel = d.tiles_for_rows(pos, hs, *d.fuse_rows(2, 8, 11546))
+    assert sel == list(range(12))                     # rows 2883..3897 touch tile rows 0 and 1 (overlap zone)
+    assert d.tiles_for_rows(pos, hs, 0, 11546) == list(range(24))
