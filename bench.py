@@ -41,6 +41,17 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# stdout carries exactly ONE JSON line: park the real stdout and point fd 1 at stderr so that library chatter
+# (NCCL's version banner, for one) cannot get in front of it
+_REAL_STDOUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(line: dict):
+    _REAL_STDOUT.write(json.dumps(line) + "\n")
+    _REAL_STDOUT.flush()
+
+
 # ---------------------------------------------------------------------------------------------- clocks
 class ClockSampler:
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
@@ -298,7 +309,7 @@ def run_b200(args, wl):
             "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
             "clocks": clocks, "ms_per_step_profiled": ms_prof / args.steps,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -323,7 +334,7 @@ def main():
     wl = workloads.build(args.workload, max_tiles=2 if args.impl == "reference" else 0)
     log(f"[bench] workload {wl.name}: {len(wl.tiles)} tiles, canvas {wl.canvas_hw[1]}x{wl.canvas_hw[0]} built in {time.time() - t:.1f}s")
     if args.impl == "reference":
-        print(json.dumps(run_reference(args, wl)), flush=True)
+        emit(run_reference(args, wl))
     else:
         run_b200(args, wl)
     return 0
