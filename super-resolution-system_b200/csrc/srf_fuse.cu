@@ -479,17 +479,57 @@ __global__ void __launch_bounds__(kThreads) k_up_level(const TileDev *__restrict
 // (C_0 = G_0 * W_0, no pyramid).
 // ------------------------------------------------------------------------------------------------------------
 constexpr int FB_W = 256, FB_H = 16, FB_PAIRS = FB_W / 2, FB_STEPS = FB_H / 2;
-constexpr int FB_SRC_ROWS = FB_STEPS + 3;   // 11
+constexpr int FB_SRC_ROWS = FB_STEPS + 2;   // 10
 constexpr int FB_SRC_COLS = FB_PAIRS + 8;   // 136
 constexpr int FB_U8_STRIDE = FB_W * 3 + 32; // 800: payload + 16 B misalignment + slack
 
 template <int C>
-struct FinalSmem {
-    float sc[C][FB_SRC_ROWS][FB_SRC_COLS];
-    float sg[C][FB_SRC_ROWS][FB_SRC_COLS];
-    float wsum[FB_H][FB_W];
-    uint8_t u8[FB_H][FB_U8_STRIDE];
+struct FinalStage { // everything the gather reads of ONE covering tile; double buffered, filled by cp.async
+    float sc[C][FB_SRC_ROWS][FB_SRC_COLS]; // C_1 window (W_1 window when the tile has exactly two levels)
+    float sg[C][FB_SRC_ROWS][FB_SRC_COLS]; // G_1 window
+    uint8_t u8[FB_H][FB_U8_STRIDE];        // uint8 tile block
 };
+template <int C>
+struct FinalSmem {
+    FinalStage<C> st[2];
+    float wsum[FB_H][FB_W];
+};
+
+__device__ __forceinline__ void cp_async_16(void *smem_dst, const void *gsrc)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+// per-(CTA, tile) geometry, uniform across the CTA
+struct FinalGeo {
+    int iy0, iy1, ix0, ix1; // intersection of block and tile, canvas coordinates
+    int mode;               // 0: >= 3 levels, 1: exactly 2 (C_1 = G_1 * W_1), 2: single level
+    int xpar, ypar, i0, ws0;
+    int sx0, srow0, n_srows;
+    int u8_a0, u8_chunks;
+};
+__device__ __forceinline__ FinalGeo final_geo(const TileDev &t, const GroupDev &g, int cy0, int cy1, int cx0, int cx1, int C)
+{
+    FinalGeo q;
+    q.iy0 = max(cy0, t.y); q.iy1 = min(cy1, t.y + t.h);
+    q.ix0 = max(cx0, t.x); q.ix1 = min(cx1, t.x + t.w);
+    q.mode = (g.n_levels >= 3) ? 0 : (g.n_levels == 2 ? 1 : 2);
+    const int h1 = g.lv[1].h;
+    const int tyf = cy0 - t.y, txf = cx0 - t.x; // tile coordinates of the block origin (may be negative)
+    q.xpar = txf & 1; q.ypar = tyf & 1;
+    q.i0 = (txf >> 1) - (1 - q.xpar);  // window start column for pair 0
+    q.ws0 = (tyf >> 1) - (1 - q.ypar); // window start row for step 0
+    q.sx0 = max(q.i0, 0) & ~3;
+    q.srow0 = max(min(q.ws0, h1 - 1), 0);
+    q.n_srows = max(min(q.ws0 + FB_STEPS + 1, h1 - 1), 0) - q.srow0 + 1; // <= 10
+    q.u8_a0 = ((q.ix0 - t.x) * C) & ~15;
+    q.u8_chunks = ((q.ix1 - t.x) * C - q.u8_a0 + 15) >> 4;
+    return q;
+}
 
 struct FinalParams {
     const TileDev *tiles;
@@ -525,10 +565,11 @@ __device__ __forceinline__ HPair h_pair_fast(float s0, float s1, float s2, int x
 // reference removes right away (x 1/64).  Scaling by a power of two commutes with every IEEE rounding, so
 // 64*(upC + (g - upG)*w) == up64C + (64 g - up64G)*w bit for bit; the factor is taken out once, before the divide.
 template <int C, bool FULL>
-__device__ __forceinline__ void final_accumulate_tile(FinalSmem<C> &S, float (&acc)[FB_STEPS][2][2], const TileDev &t, const GroupDev &g,
-                                                      int cy0, int cx0, int iy0, int iy1, int ix0, int ix1, int c, int p, int u8_a0,
-                                                      int srow0, int n_srows, int sx0, int i0, int ws0, int xpar, int ypar, int mode)
+__device__ __forceinline__ void final_accumulate_tile(FinalSmem<C> &S, const FinalStage<C> &B, float (&acc)[FB_STEPS][2][2], const TileDev &t,
+                                                      const GroupDev &g, int cy0, int cx0, const FinalGeo &q, int c, int p)
 {
+    const int iy0 = q.iy0, iy1 = q.iy1, ix0 = q.ix0, ix1 = q.ix1, u8_a0 = q.u8_a0, srow0 = q.srow0, n_srows = q.n_srows, sx0 = q.sx0;
+    const int i0 = q.i0, ws0 = q.ws0, xpar = q.xpar, ypar = q.ypar, mode = q.mode;
     const int h1 = g.lv[1].h, w1 = g.lv[1].w;
     const int tyf = cy0 - t.y, txf = cx0 - t.x;
     const int txa = txf + 2 * p, txb = txa + 1; // tile columns of the thread's two canvas columns
@@ -537,7 +578,7 @@ __device__ __forceinline__ void final_accumulate_tile(FinalSmem<C> &S, float (&a
     const int lmax = g.lut_len - 1;
     const int dxa = min(txa, t.w - 1 - txa), dxb = min(txb, t.w - 1 - txb);
     const int u8_col = txa * C + c - u8_a0; // byte offset of (txa, c) inside a staged row
-    const bool hfast = FULL || ((i0 >= 0) && (i0 + FB_PAIRS + 1 <= w1 - 1) && (w1 > 1));
+    const bool hfast = FULL || ((mode == 0) && (i0 >= 0) && (i0 + FB_PAIRS + 1 <= w1 - 1) && (w1 > 1));
     const int scol = i0 + p - sx0; // smem column of s0
 
     auto weight = [&](int dy, int dx) { return __ldg(g.lut + min(min(dy, dx), lmax)); };
@@ -545,20 +586,22 @@ __device__ __forceinline__ void final_accumulate_tile(FinalSmem<C> &S, float (&a
         int r = (r_logical == -1) ? min(1, h1 - 1) : max(min(r_logical, h1 - 1), 0);
         r -= srow0;
         r = max(min(r, n_srows - 1), 0);
-        const float *rc = &S.sc[c][r][0];
-        const float *rg = &S.sg[c][r][0];
+        const float *rc = &B.sc[c][r][0];
+        const float *rg = &B.sg[c][r][0];
         if (hfast) {
             oc = h_pair_fast(rc[scol], rc[scol + 1], rc[scol + 2], xpar);
             og = h_pair_fast(rg[scol], rg[scol + 1], rg[scol + 2], xpar);
         } else {
             oc.a = oc.b = og.a = og.b = 0.f;
+            auto atg = [&](int ii) { return rg[ii - sx0]; };
+            auto atc = [&](int ii) { return (mode == 1) ? __fmul_rn(rg[ii - sx0], rc[ii - sx0]) : rc[ii - sx0]; };
             if (ina) {
-                oc.a = up_h_sample(txa, w1, [&](int ii) { return rc[ii - sx0]; });
-                og.a = up_h_sample(txa, w1, [&](int ii) { return rg[ii - sx0]; });
+                oc.a = up_h_sample(txa, w1, atc);
+                og.a = up_h_sample(txa, w1, atg);
             }
             if (inb) {
-                oc.b = up_h_sample(txb, w1, [&](int ii) { return rc[ii - sx0]; });
-                og.b = up_h_sample(txb, w1, [&](int ii) { return rg[ii - sx0]; });
+                oc.b = up_h_sample(txb, w1, atc);
+                og.b = up_h_sample(txb, w1, atg);
             }
         }
     };
@@ -572,7 +615,7 @@ __device__ __forceinline__ void final_accumulate_tile(FinalSmem<C> &S, float (&a
                 if (cy < iy0 || cy >= iy1) continue;
                 const int ty = cy - t.y;
                 const int dy = min(ty, t.h - 1 - ty);
-                const uint8_t *px = &S.u8[2 * k + a][u8_col];
+                const uint8_t *px = &B.u8[2 * k + a][u8_col];
                 if (ina) {
                     const float w0 = weight(dy, dxa);
                     acc[k][a][0] = __fadd_rn(acc[k][a][0], __fmul_rn((float)((int)px[0] << 6), w0));
@@ -612,7 +655,7 @@ __device__ __forceinline__ void final_accumulate_tile(FinalSmem<C> &S, float (&a
             if (FULL || (cy >= iy0 && cy < iy1)) {
                 const int ty = tyf + 2 * k + a;
                 const int dy = min(ty, t.h - 1 - ty);
-                const uint8_t *px = &S.u8[2 * k + a][u8_col];
+                const uint8_t *px = &B.u8[2 * k + a][u8_col];
                 if (ina) {
                     const float w0 = weight(dy, dxa);
                     const float g64 = (float)((int)px[0] << 6);
@@ -677,64 +720,67 @@ __global__ void __launch_bounds__(128 * C, (C == 3) ? 2 : 5) k_final(FinalParams
         if (hit) s_list[off + __popc(bal & ((1u << lane) - 1u))] = cand;
         __syncthreads();
 
-        for (int li = 0; li < total; ++li) {
+        // stage(li): cp.async the tile's uint8 block and C_1 / G_1 windows into buffer li & 1 (chunks outside the
+        // arrays are zero-filled with plain stores; everything else lands asynchronously)
+        auto stage = [&](int li) {
             const int ti = s_list[li];
             const TileDev &t = P.tiles[ti];
-            const int iy0 = max(cy0, t.y), iy1 = min(cy1, t.y + t.h);
-            const int ix0 = max(cx0, t.x), ix1 = min(cx1, t.x + t.w);
             const GroupDev &g = P.groups[P.tile_group[ti]];
-            const int mode = (g.n_levels >= 3) ? 0 : (g.n_levels == 2 ? 1 : 2);
-            const LevelGeom L1 = g.lv[1];
-            const int h1 = L1.h, w1 = L1.w;
-            const int tyf = cy0 - t.y, txf = cx0 - t.x; // tile coordinates of the block origin (may be negative)
-            const int xpar = txf & 1, ypar = tyf & 1;
-            const int i0 = (txf >> 1) - (1 - xpar);  // window start column for pair 0
-            const int ws0 = (tyf >> 1) - (1 - ypar); // window start row for step 0
-            const int sx0 = max(i0, 0) & ~3;
-            const int srow0 = max(min(ws0, h1 - 1), 0);
-            const int srow1 = max(min(ws0 + FB_STEPS + 1, h1 - 1), 0);
-            const int n_srows = srow1 - srow0 + 1; // <= 10
-            __syncthreads(); // everyone is done with the previous tile's smem (and wsum is initialised)
-
-            // ---- stage the uint8 tile block: rows iy0..iy1, bytes congruent mod 16 with the tile rows ----
-            const int u8_first = (ix0 - t.x) * C;
-            const int u8_a0 = u8_first & ~15;
-            const int u8_chunks = ((ix1 - t.x) * C - u8_a0 + 15) >> 4;
-            for (int i = threadIdx.x; i < (iy1 - iy0) * u8_chunks; i += NT) {
-                const int r = i / u8_chunks, ch = i - r * u8_chunks;
-                const uint8_t *grow = t.src + (size_t)(iy0 - t.y + r) * t.pitch;
-                stage_u8_chunk(&S.u8[iy0 - cy0 + r][0], grow, u8_a0, ch, t.w * C);
+            const FinalGeo q = final_geo(t, g, cy0, cy1, cx0, cx1, C);
+            FinalStage<C> &B = S.st[li & 1];
+            const int pitch = (int)t.pitch;
+            for (int i = threadIdx.x; i < (q.iy1 - q.iy0) * q.u8_chunks; i += NT) {
+                const int r = i / q.u8_chunks, ch = i - r * q.u8_chunks;
+                const int o = q.u8_a0 + ch * 16;
+                uint8_t *dst = &B.u8[q.iy0 - cy0 + r][ch * 16];
+                if (o >= 0 && o + 16 <= pitch)
+                    cp_async_16(dst, t.src + (size_t)(q.iy0 - t.y + r) * t.pitch + o);
+                else
+                    *reinterpret_cast<uint4 *>(dst) = make_uint4(0, 0, 0, 0);
             }
-            if (mode != 2) {
-                const int per_c = n_srows * (FB_SRC_COLS / 4);
+            if (q.mode != 2) {
+                const LevelGeom L1 = g.lv[1];
+                const int per_c = q.n_srows * (FB_SRC_COLS / 4);
                 for (int i = threadIdx.x; i < C * per_c; i += NT) {
                     const int cc = i / per_c;
                     const int rem = i - cc * per_c;
                     const int r = rem / (FB_SRC_COLS / 4), ch = rem - r * (FB_SRC_COLS / 4);
-                    const int gy = srow0 + r, c0 = sx0 + ch * 4;
-                    const float4 gv = load_f32_chunk(t.G[1] + (size_t)cc * L1.plane + (size_t)gy * L1.pitch, c0, w1);
-                    float4 cv;
-                    if (mode == 1) {
-                        const float4 wv = load_f32_chunk(g.W[1] + (size_t)gy * L1.pitch, c0, w1);
-                        cv = make_float4(__fmul_rn(gv.x, wv.x), __fmul_rn(gv.y, wv.y), __fmul_rn(gv.z, wv.z), __fmul_rn(gv.w, wv.w));
+                    const int c0 = q.sx0 + ch * 4;
+                    const size_t off = (size_t)(q.srow0 + r) * L1.pitch + c0;
+                    float *dg = &B.sg[cc][r][ch * 4], *dc = &B.sc[cc][r][ch * 4];
+                    if (c0 + 4 <= L1.pitch) {
+                        cp_async_16(dg, t.G[1] + (size_t)cc * L1.plane + off);
+                        cp_async_16(dc, (q.mode == 1) ? g.W[1] + off : t.C[1] + (size_t)cc * L1.plane + off);
                     } else {
-                        cv = load_f32_chunk(t.C[1] + (size_t)cc * L1.plane + (size_t)gy * L1.pitch, c0, w1);
+                        *reinterpret_cast<float4 *>(dg) = make_float4(0.f, 0.f, 0.f, 0.f);
+                        *reinterpret_cast<float4 *>(dc) = make_float4(0.f, 0.f, 0.f, 0.f);
                     }
-                    *reinterpret_cast<float4 *>(&S.sg[cc][r][ch * 4]) = gv;
-                    *reinterpret_cast<float4 *>(&S.sc[cc][r][ch * 4]) = cv;
                 }
             }
-            __syncthreads();
+            cp_async_commit();
+        };
 
+        if (total > 0) stage(0);
+        for (int li = 0; li < total; ++li) {
+            if (li + 1 < total) {
+                stage(li + 1); // next tile's copies fly while this tile is consumed
+                cp_async_wait<1>();
+            } else {
+                cp_async_wait<0>();
+            }
+            __syncthreads(); // tile li has landed for every thread
+            const int ti = s_list[li];
+            const TileDev &t = P.tiles[ti];
+            const GroupDev &g = P.groups[P.tile_group[ti]];
+            const FinalGeo q = final_geo(t, g, cy0, cy1, cx0, cx1, C);
             // block entirely inside the tile and every horizontal window strictly inside the source row: no predicates
-            const bool full = (mode != 2) && (iy0 == cy0) && (iy1 == cy0 + FB_H) && (ix0 == cx0) && (ix1 == cx0 + FB_W) && (i0 >= 0) &&
-                              (i0 + FB_PAIRS + 1 <= w1 - 1);
+            const bool full = (q.mode == 0) && (q.iy0 == cy0) && (q.iy1 == cy0 + FB_H) && (q.ix0 == cx0) && (q.ix1 == cx0 + FB_W) &&
+                              (q.i0 >= 0) && (q.i0 + FB_PAIRS + 1 <= g.lv[1].w - 1);
             if (full)
-                final_accumulate_tile<C, true>(S, acc, t, g, cy0, cx0, iy0, iy1, ix0, ix1, c, p, u8_a0, srow0, n_srows, sx0, i0, ws0, xpar,
-                                               ypar, mode);
+                final_accumulate_tile<C, true>(S, S.st[li & 1], acc, t, g, cy0, cx0, q, c, p);
             else
-                final_accumulate_tile<C, false>(S, acc, t, g, cy0, cx0, iy0, iy1, ix0, ix1, c, p, u8_a0, srow0, n_srows, sx0, i0, ws0, xpar,
-                                                ypar, mode);
+                final_accumulate_tile<C, false>(S, S.st[li & 1], acc, t, g, cy0, cx0, q, c, p);
+            __syncthreads(); // buffer li & 1 is free for tile li + 2
         }
     }
 
@@ -756,7 +802,7 @@ __global__ void __launch_bounds__(128 * C, (C == 3) ? 2 : 5) k_final(FinalParams
                 const float wsum = fmaxf(S.wsum[r][x], 1e-6f);
                 float v = __fdiv_rn(__fmul_rn(acc[k][a][b], 1.f / 64.f), wsum);
                 v = fminf(fmaxf(v, 0.f), 255.f);
-                S.u8[r][mis + x * C + c] = (uint8_t)(int)v; // clip then truncate (blending_module.py:504-506)
+                S.st[0].u8[r][mis + x * C + c] = (uint8_t)(int)v; // clip then truncate (blending_module.py:504-506)
             }
         }
     }
@@ -772,9 +818,9 @@ __global__ void __launch_bounds__(128 * C, (C == 3) ? 2 : 5) k_final(FinalParams
         if (hi <= p0 || lo >= p1) continue;
         uint8_t *gdst = grow - mis + lo; // 16-byte aligned
         if (lo >= p0 && hi <= p1) {
-            *reinterpret_cast<uint4 *>(gdst) = *reinterpret_cast<const uint4 *>(&S.u8[r][lo]);
+            *reinterpret_cast<uint4 *>(gdst) = *reinterpret_cast<const uint4 *>(&S.st[0].u8[r][lo]);
         } else {
-            for (int e = max(lo, p0); e < min(hi, p1); ++e) gdst[e - lo] = S.u8[r][e];
+            for (int e = max(lo, p0); e < min(hi, p1); ++e) gdst[e - lo] = S.st[0].u8[r][e];
         }
     }
 }

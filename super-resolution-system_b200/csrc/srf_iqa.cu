@@ -46,27 +46,22 @@ struct IqaParams {
     IqaPartial *partials;
 };
 
-// 16-byte chunk at absolute address q (16-byte aligned), clipped to the image's byte range [lo, hi)
-__device__ __forceinline__ uint4 load_chunk_abs(const uint8_t *q, const uint8_t *lo, const uint8_t *hi)
+__device__ __forceinline__ void cp_async_16(void *smem_dst, const void *gsrc)
 {
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (q >= lo && q + 16 <= hi) {
-        v = *reinterpret_cast<const uint4 *>(q);
-    } else if (q + 16 > lo && q < hi) {
-        uint8_t *b = reinterpret_cast<uint8_t *>(&v);
-#pragma unroll
-        for (int e = 0; e < 16; ++e) b[e] = (q + e >= lo && q + e < hi) ? q[e] : (uint8_t)0;
-    }
-    return v;
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
 }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
-template <int C>
+template <int C, bool ANYSCALE>
 __device__ __forceinline__ int gray_of(const uint8_t *p, int scale, int &bits, int (&v)[C])
 {
 #pragma unroll
     for (int c = 0; c < C; ++c) {
         int t = p[c];
-        if (scale) t = (t * 255) & 0xFF; // (image * 255).astype(uint8), quality_assessment_module.py:192-193
+        if (ANYSCALE && scale) t = (t * 255) & 0xFF; // (image * 255).astype(uint8), quality_assessment_module.py:192-193
         v[c] = t;
     }
     if (C == 1) {
@@ -77,14 +72,17 @@ __device__ __forceinline__ int gray_of(const uint8_t *p, int scale, int &bits, i
     return (v[0] * 9798 + v[C > 1 ? 1 : 0] * 19235 + v[C > 2 ? 2 : 0] * 3735 + 16384) >> 15; // cv2 COLOR_RGB2GRAY, uint8
 }
 
-// Per CTA: 128 S-map columns x IQ_RB rows.  A four-stage software pipeline over the input rows, one barrier per
-// row:  L(r+4) 16-byte global loads of the raw RGB bytes into registers (56 loader threads, both images)
-//       S(r+2) registers -> raw smem row        G(r+1) raw bytes -> gray float row (+ squared error, OR of bytes)
-//       H(r)   horizontal 11-tap from the gray row into the register ring, vertical 11-tap, SSIM, accumulate
-template <int C>
+// Per CTA: 128 S-map columns x IQ_RB rows, streamed DOWN the rows with one barrier per row:
+//   L(r+4) cp.async (LDGSTS) 16-byte copies of the raw RGB bytes of both images into a 4-stage smem ring (56 loader
+//          threads, no registers held across the latency; image-edge chunks take a guarded byte path)
+//   G(r+1) raw bytes -> gray float row (+ exact squared error and the OR of the bytes for the owned pixels)
+//   H(r)   horizontal 11-tap of {a, b, a^2+b^2, ab} into an 11-deep register ring, vertical 11-tap, SSIM, accumulate
+// ANYSCALE: an image is rescaled by 255 first (the reference's max() <= 1 rule, P.scale_a / P.scale_b) -- a separate
+// instantiation so the common case carries no dead arithmetic.
+template <int C, bool ANYSCALE>
 __global__ void __launch_bounds__(IQ_THREADS, 5) k_psnr_ssim(IqaParams P)
 {
-    __shared__ __align__(16) uint8_t s_raw[2][2][IQ_RAW];
+    __shared__ __align__(16) uint8_t s_raw[4][2][IQ_RAW];
     __shared__ float s_a[2][IQ_SROW];
     __shared__ float s_b[2][IQ_SROW];
     __shared__ double s_red[IQ_THREADS / 32];
@@ -102,48 +100,55 @@ __global__ void __launch_bounds__(IQ_THREADS, 5) k_psnr_ssim(IqaParams P)
     const bool has2 = t < 2 * IQ_R;
     const bool own1 = col1 >= cx0 && col1 < w; // owned = inside this CTA's strip (for the PSNR sum)
     const bool own2 = has2 && col2 < cx0 + IQ_THREADS && col2 < w;
-
     const int r_first = ry0 - IQ_R, r_last = ry1 + IQ_R; // input rows [r_first, r_last)
-    // loader role: warp 0 lanes 0..27 -> image a, warp 1 lanes 0..27 -> image b
-    const int limg = t >> 5, lchunk = t & 31;
-    const bool loader = (limg < 2) && (lchunk < IQ_RAW / 16);
+    const long long col_off = (long long)(cx0 - IQ_R) * C;
+
+    // ---- loader role: threads 0..27 -> image a, 28..55 -> image b, one 16-byte chunk each per row ----
+    constexpr int NCH = IQ_RAW / 16;
+    const bool loader = t < 2 * NCH;
+    const int limg = (t >= NCH) ? 1 : 0, lchunk = t - limg * NCH;
     const uint8_t *lbase = limg ? P.b : P.a;
-    const size_t lpitch = limg ? P.pitch_b : P.pitch_a;
+    const long long lpitch = (long long)(limg ? P.pitch_b : P.pitch_a);
     // bytes this launch may touch: rows [row_begin - 5, row_end + 5) of the image, clipped (a band-staged image only
     // holds those rows)
     const int vr0 = max(P.row_begin - IQ_R, 0), vr1 = min(P.row_end + IQ_R, h);
-    const uint8_t *llo = lbase + (long long)vr0 * (long long)lpitch;
-    const uint8_t *lhi = lbase + (long long)(vr1 - 1) * (long long)lpitch + (long long)w * C;
-    const long long col_off = (long long)(cx0 - IQ_R) * C;
-
-    auto row_mis = [&](const uint8_t *base, size_t pitch, int r) {
-        return (int)(reinterpret_cast<uintptr_t>(base + (long long)r * (long long)pitch + col_off) & 15);
-    };
+    const uint8_t *llo = lbase + (long long)vr0 * lpitch;
+    const uint8_t *lhi = lbase + (long long)(vr1 - 1) * lpitch + (long long)w * C;
     auto L = [&](int r) {
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (loader && r >= 0 && r < h && r < r_last) {
-            const uint8_t *A = lbase + (long long)r * (long long)lpitch + col_off;
+        if (loader && r >= vr0 && r < vr1 && r < r_last) {
+            const uint8_t *A = lbase + (long long)r * lpitch + col_off;
             const uint8_t *q = A - (reinterpret_cast<uintptr_t>(A) & 15) + 16 * lchunk;
-            v = load_chunk_abs(q, llo, lhi);
+            uint8_t *dst = &s_raw[(r - r_first) & 3][limg][16 * lchunk];
+            if (q >= llo && q + 16 <= lhi) {
+                cp_async_16(dst, q);
+            } else if (q + 16 > llo && q < lhi) { // image edge: guarded bytes
+                uint4 v = make_uint4(0, 0, 0, 0);
+                uint8_t *bv = reinterpret_cast<uint8_t *>(&v);
+#pragma unroll 1
+                for (int e = 0; e < 16; ++e)
+                    if (q + e >= llo && q + e < lhi) bv[e] = q[e];
+                *reinterpret_cast<uint4 *>(dst) = v;
+            }
         }
-        return v;
-    };
-    auto Sst = [&](int r, const uint4 &v) {
-        if (loader) *reinterpret_cast<uint4 *>(&s_raw[r & 1][limg][16 * lchunk]) = v;
+        cp_async_commit();
     };
 
     unsigned int sq = 0; // <= 64 rows * 2 px * 3 * 65025 < 2^32
     int bits_a = 0, bits_b = 0;
+    const int mis_a0 = (int)((reinterpret_cast<uintptr_t>(P.a) + (unsigned long long)col_off) & 15);
+    const int mis_b0 = (int)((reinterpret_cast<uintptr_t>(P.b) + (unsigned long long)col_off) & 15);
+    const int pa16 = (int)(P.pitch_a & 15), pb16 = (int)(P.pitch_b & 15);
     auto G = [&](int r) {
         const int buf = r & 1;
         float ga1 = 0.f, gb1 = 0.f, ga2 = 0.f, gb2 = 0.f;
         if (r >= 0 && r < h) {
-            const uint8_t *ra = &s_raw[buf][0][row_mis(P.a, P.pitch_a, r)];
-            const uint8_t *rb = &s_raw[buf][1][row_mis(P.b, P.pitch_b, r)];
+            const int st = (r - r_first) & 3;
+            const uint8_t *ra = &s_raw[st][0][(mis_a0 + r * pa16) & 15];
+            const uint8_t *rb = &s_raw[st][1][(mis_b0 + r * pb16) & 15];
             const bool rown = r >= ry0 && r < ry1;
             int va[C], vb[C], da = 0, db = 0;
-            ga1 = (float)(gray_of<C>(ra + t * C, P.scale_a, da, va) - 128);
-            gb1 = (float)(gray_of<C>(rb + t * C, P.scale_b, db, vb) - 128);
+            ga1 = (float)(gray_of<C, ANYSCALE>(ra + t * C, P.scale_a, da, va) - 128);
+            gb1 = (float)(gray_of<C, ANYSCALE>(rb + t * C, P.scale_b, db, vb) - 128);
             if (rown && own1) {
                 bits_a |= da;
                 bits_b |= db;
@@ -155,8 +160,8 @@ __global__ void __launch_bounds__(IQ_THREADS, 5) k_psnr_ssim(IqaParams P)
             }
             if (has2) {
                 da = db = 0;
-                ga2 = (float)(gray_of<C>(ra + (IQ_THREADS + t) * C, P.scale_a, da, va) - 128);
-                gb2 = (float)(gray_of<C>(rb + (IQ_THREADS + t) * C, P.scale_b, db, vb) - 128);
+                ga2 = (float)(gray_of<C, ANYSCALE>(ra + (IQ_THREADS + t) * C, P.scale_a, da, va) - 128);
+                gb2 = (float)(gray_of<C, ANYSCALE>(rb + (IQ_THREADS + t) * C, P.scale_b, db, vb) - 128);
                 if (rown && own2) {
                     bits_a |= da;
                     bits_b |= db;
@@ -188,12 +193,14 @@ __global__ void __launch_bounds__(IQ_THREADS, 5) k_psnr_ssim(IqaParams P)
     const bool col_interior = col >= IQ_R && col < w - IQ_R;
     const float C1 = P.c1, C2 = P.c2;
 
-    // prologue: gray(r_first) ready, raw(r_first+1) staged, rows r_first+2 / +3 in flight
-    Sst(r_first, L(r_first));
-    Sst(r_first + 1, L(r_first + 1));
+    // prologue: rows r_first .. r_first+3 in flight; gray(r_first) ready and raw(r_first+1) published
+    L(r_first);
+    L(r_first + 1);
+    L(r_first + 2);
+    L(r_first + 3);
+    cp_async_wait<2>();
     __syncthreads();
     G(r_first);
-    uint4 cur = L(r_first + 2), nxt = L(r_first + 3);
     __syncthreads();
 
     for (int base = r_first; base < r_last; base += IQ_TAPS) {
@@ -202,8 +209,7 @@ __global__ void __launch_bounds__(IQ_THREADS, 5) k_psnr_ssim(IqaParams P)
             const int r_in = base + ph;
             if (r_in >= r_last) break;
             const int buf = r_in & 1;
-            // L(r+4) first: its latency hides behind this row's arithmetic and the next row's
-            const uint4 fresh = L(r_in + 4);
+            L(r_in + 4);
 
             // H(r): horizontal pass on gray row r_in -- four FMA chains with literal taps, products formed once per tap
             {
@@ -259,12 +265,11 @@ __global__ void __launch_bounds__(IQ_THREADS, 5) k_psnr_ssim(IqaParams P)
                 }
             }
             if (r_in + 1 < r_last) G(r_in + 1);
-            Sst(r_in + 2, cur);
-            cur = nxt;
-            nxt = fresh;
+            cp_async_wait<2>(); // row r_in + 2 has landed (this thread's copies); the barrier publishes it
             __syncthreads();
         }
     }
+    cp_async_wait<0>();
 
     // ---- block reduction (fixed order) ----
     double ds = (double)ssum;
@@ -368,10 +373,16 @@ int srf_iqa_enqueue(srf_ctx *ctx, const uint8_t *a, size_t pa, const uint8_t *b,
     if (nparts > 0) {
         dim3 grid(gx, gy);
         srf_launch_scope scope(ctx, "psnr_ssim", 2.0 * (double)(row_end - row_begin) * w * C, st);
-        if (C == 3)
-            k_psnr_ssim<3><<<grid, IQ_THREADS, 0, st>>>(P);
-        else
-            k_psnr_ssim<1><<<grid, IQ_THREADS, 0, st>>>(P);
+        if (scale_a || scale_b) { // the rare max() <= 1 rescale: generic instantiation
+            if (C == 3)
+                k_psnr_ssim<3, true><<<grid, IQ_THREADS, 0, st>>>(P);
+            else
+                k_psnr_ssim<1, true><<<grid, IQ_THREADS, 0, st>>>(P);
+        } else if (C == 3) {
+            k_psnr_ssim<3, false><<<grid, IQ_THREADS, 0, st>>>(P);
+        } else {
+            k_psnr_ssim<1, false><<<grid, IQ_THREADS, 0, st>>>(P);
+        }
     }
     {
         srf_launch_scope scope(ctx, "iqa_reduce", 0.0, st);
