@@ -46,6 +46,7 @@ SIGNATURES = {
     "srf_sync": (c_int, [c_void_p, c_void_p]),
     "srf_launch_count": (c_int64, [c_void_p]),
     "srf_workspace_bytes": (c_size_t, [c_void_p]),
+    "srf_last_transfer_bytes": (c_int, [c_void_p, P(c_size_t), P(c_size_t)]),
     "srf_last_device_ms": (C.c_float, [c_void_p]),
     "srf_profile_enable": (c_int, [c_void_p, c_int]),
     "srf_profile_read": (c_int, [c_void_p, P(srf_profile_entry), c_int]),
@@ -135,6 +136,12 @@ def destroy_contexts():
         for h in _ctx.values():
             lib.srf_destroy(h)
         _ctx.clear()
+
+
+def last_transfer_bytes(ctx):
+    a, b = c_size_t(), c_size_t()
+    check(load().srf_last_transfer_bytes(ctx, C.byref(a), C.byref(b)), ctx)
+    return int(a.value), int(b.value)
 
 
 def profile_enable(ctx, on: bool) -> None:

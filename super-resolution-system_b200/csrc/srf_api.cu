@@ -121,6 +121,7 @@ extern "C" int srf_create(int device, srf_ctx **out)
     SRF_CHECK_CUDA(c, cudaSetDevice(device));
     SRF_CHECK_CUDA(c, cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     SRF_CHECK_CUDA(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    SRF_CHECK_CUDA(c, cudaStreamCreateWithFlags(&c->down_stream, cudaStreamNonBlocking));
     SRF_CHECK_CUDA(c, cudaEventCreate(&c->ev0));
     SRF_CHECK_CUDA(c, cudaEventCreate(&c->ev1));
     for (cudaEvent_t &e : c->ev_aux) SRF_CHECK_CUDA(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -144,6 +145,7 @@ extern "C" void srf_destroy(srf_ctx *c)
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->down_stream) cudaStreamDestroy(c->down_stream);
     delete c;
 }
 
@@ -156,6 +158,14 @@ extern "C" int srf_sync(srf_ctx *ctx, void *stream)
 }
 
 extern "C" int64_t srf_launch_count(const srf_ctx *ctx) { return ctx ? ctx->launches : -1; }
+
+extern "C" int srf_last_transfer_bytes(const srf_ctx *c, size_t *h2d, size_t *d2h)
+{
+    if (!c) return SRF_ERR_ARG;
+    if (h2d) *h2d = c->last_h2d;
+    if (d2h) *d2h = c->last_d2h;
+    return SRF_OK;
+}
 
 extern "C" size_t srf_workspace_bytes(const srf_ctx *c)
 {

@@ -41,6 +41,7 @@ struct srf_ctx {
     int sm_count = 148;
     std::string last_error;
     int64_t launches = 0;
+    size_t last_h2d = 0, last_d2h = 0; // bytes the last *_host entry point moved over PCIe
     // grow-only device workspaces, by role
     srf_buffer ws_pyr;      // per-tile G/C pyramids + weight pyramids
     srf_buffer ws_desc;     // device copies of descriptor arrays
@@ -52,6 +53,7 @@ struct srf_ctx {
     size_t pinned_bytes = 0;
     cudaStream_t own_stream = nullptr; // used by the *_host entry points
     cudaStream_t copy_stream = nullptr;
+    cudaStream_t down_stream = nullptr; // device->host copies of the pipelined host entry point
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaEvent_t ev_aux[3] = {nullptr, nullptr, nullptr};
     bool ev_valid = false;
@@ -190,7 +192,9 @@ int srf_fuse_device(srf_ctx *ctx, const srf_tile *tiles, int n_tiles, int C, int
                     int out_w, uint8_t *d_canvas, size_t canvas_pitch, int row_begin, int row_end, cudaStream_t st);
 int srf_check_fuse_args(srf_ctx *ctx, const srf_tile *tiles, int n_tiles, int C, int levels, const srf_weight_lut *luts, int n_luts,
                         int out_h, int out_w, const void *canvas, size_t canvas_pitch, int row_begin, int row_end);
-// enqueue only: the sums land in ctx->pinned after the stream is synchronised; srf_iqa_collect converts them
+void srf_fuse_input_extent(const srf_tile &t, int levels, int out_h, int out_w, int row_begin, int row_end, int *rows, int *cols);
+// enqueue only: the sums land in slot `slot` (0..63) of ctx->pinned once the stream is synchronised; srf_iqa_collect
+// converts them
 int srf_iqa_enqueue(srf_ctx *ctx, const uint8_t *a, size_t pa, const uint8_t *b, size_t pb, int h, int w, int C, int scale_a, int scale_b,
-                    double data_range, int row_begin, int row_end, cudaStream_t st);
-void srf_iqa_collect(srf_ctx *ctx, int w, int C, int row_begin, int row_end, srf_iqa_sums *out);
+                    double data_range, int row_begin, int row_end, cudaStream_t st, int slot);
+void srf_iqa_collect(srf_ctx *ctx, int w, int C, int row_begin, int row_end, srf_iqa_sums *out, int slot);

@@ -54,6 +54,7 @@ struct TileDev {
     float *C[SRF_MAX_LEVELS]; // 1 <= l <= n-2
     int g0[SRF_MAX_LEVELS], g1[SRF_MAX_LEVELS]; // rows of G_l to produce
     int c0[SRF_MAX_LEVELS], c1[SRF_MAX_LEVELS]; // rows of C_l to produce
+    int gx1[SRF_MAX_LEVELS], cx1[SRF_MAX_LEVELS]; // columns [0, gx1) of G_l / [0, cx1) of C_l are needed (canvas crop)
 };
 
 // ------------------------------------------------------------------------------------------------------------
@@ -146,7 +147,7 @@ __global__ void __launch_bounds__(128 * C) k_down_u8(const TileDev *__restrict__
     const int ow = L1.w;
     const int oy0 = t.g0[1] + blockIdx.y * D8_ROWS;
     const int ox0 = blockIdx.x * D8_BW;
-    if (oy0 >= t.g1[1] || ox0 >= ow) return;
+    if (oy0 >= t.g1[1] || ox0 >= ow || ox0 >= t.gx1[1]) return;
     const int oy1 = min(oy0 + D8_ROWS, t.g1[1]);
     const int in_y0 = 2 * oy0 - 2;
     const int px_g0 = 2 * ox0 - 16;                 // first staged pixel (multiple of 16 -> 16-byte aligned bytes)
@@ -262,7 +263,7 @@ __global__ void __launch_bounds__(kThreads) k_down_f32(const TileDev *__restrict
     const int h = Ls.h, w = Ls.w, ow = Ld.w;
     const float *src = nullptr;
     float *dst;
-    int r0, r1, c = 0, cn_ref;
+    int r0, r1, c = 0, cn_ref, xlim = ow;
     if (WEIGHT) {
         if (l > 0) src = g.W[l];
         dst = g.W[l + 1];
@@ -278,10 +279,11 @@ __global__ void __launch_bounds__(kThreads) k_down_f32(const TileDev *__restrict
         r0 = t.g0[l + 1];
         r1 = t.g1[l + 1];
         cn_ref = g.cn;
+        xlim = t.gx1[l + 1];
     }
     const int oy0 = r0 + blockIdx.y * DN_BH;
     const int ox0 = blockIdx.x * DN_BW;
-    if (oy0 >= r1 || ox0 >= ow) return;
+    if (oy0 >= r1 || ox0 >= ow || ox0 >= xlim) return;
     const int oy1 = min(oy0 + DN_BH, r1);
     const int in_y0 = 2 * oy0 - 2;
     const int in_x0 = 2 * ox0 - 4; // multiple of 4
@@ -387,7 +389,7 @@ __global__ void __launch_bounds__(kThreads) k_up_level(const TileDev *__restrict
     const LevelGeom L0 = g.lv[l], L1 = g.lv[l + 1];
     const int ty0 = t.c0[l] + blockIdx.y * UP_BH;
     const int tx0 = blockIdx.x * UP_BW;
-    if (ty0 >= t.c1[l] || tx0 >= L0.w) return;
+    if (ty0 >= t.c1[l] || tx0 >= L0.w || tx0 >= t.cx1[l]) return;
     const int ty1 = min(ty0 + UP_BH, t.c1[l]);
     const int tx1 = min(tx0 + UP_BW, L0.w);
     const SrcWin sw = src_window(ty0, ty1, tx0, L1.h);
@@ -851,6 +853,53 @@ struct RowRange {
 
 } // namespace
 
+// Which rows (or columns) of every pyramid level does an interval [a0, b0) of level-0 outputs depend on?
+//   up pass  : C_{l-1}[r] reads C_l, G_l at r/2 - 1 .. r/2 + 1 (row -1 is the reflection of row 1)
+//   down pass: G_l[r] reads G_{l-1} at 2r-2 .. 2r+2 (reflect-101 at both ends)
+// needG[0] is what must be present of the INPUT tile.  dim[l] = extent of level l.  Exact (a dependency cone), so
+// restricting work or uploads to these ranges cannot change a needed output.
+static void srf_propagate_need(int a0, int b0, const int *dim, int n, RowRange *needC, RowRange *needG)
+{
+    for (int l = 0; l < SRF_MAX_LEVELS; ++l) needC[l] = needG[l] = RowRange{0, 0};
+    if (a0 >= b0) return;
+    needC[0].merge(a0, b0);
+    needG[0].merge(a0, b0);
+    for (int l = 1; l < n; ++l) {
+        const int h1 = dim[l];
+        const int lo = std::max((needC[l - 1].a >> 1) - 1, 0), hi = std::min(((needC[l - 1].b - 1) >> 1) + 2, h1);
+        needC[l].merge(lo, std::max(hi, std::min(2, h1))); // row 1 is the reflection of row -1
+        needG[l].merge(needC[l].a, needC[l].b);
+    }
+    for (int l = n - 1; l >= 1; --l) {
+        const int hs = dim[l - 1];
+        int lo = std::max(2 * needG[l].a - 2, 0), hi = std::min(2 * needG[l].b + 1, hs);
+        if (needG[l].a <= 0) hi = std::max(hi, std::min(3, hs));             // reflections of rows -1, -2
+        if (2 * needG[l].b + 1 > hs) lo = std::min(lo, std::max(hs - 3, 0)); // reflections past the end
+        needG[l - 1].merge(lo, hi);
+    }
+}
+
+// rows / columns [0, rows) x [0, cols) of an input tile that canvas rows [row_begin, row_end) can depend on
+void srf_fuse_input_extent(const srf_tile &t, int levels, int out_h, int out_w, int row_begin, int row_end, int *rows, int *cols)
+{
+    int hs[SRF_MAX_LEVELS], ws[SRF_MAX_LEVELS], n = 1;
+    hs[0] = t.h;
+    ws[0] = t.w;
+    while (n < levels && hs[n - 1] >= 2 && ws[n - 1] >= 2) {
+        hs[n] = (hs[n - 1] + 1) / 2;
+        ws[n] = (ws[n - 1] + 1) / 2;
+        ++n;
+    }
+    RowRange nc[SRF_MAX_LEVELS], ng[SRF_MAX_LEVELS], cc[SRF_MAX_LEVELS], cg[SRF_MAX_LEVELS];
+    const int xa0 = std::max(0, -t.x), xb0 = std::min(out_w, t.x + t.w) - t.x;
+    const int a0 = std::max(row_begin, t.y) - t.y, b0 = std::min(std::min(row_end, out_h), t.y + t.h) - t.y;
+    const bool live = (xa0 < xb0) && (a0 < b0);
+    srf_propagate_need(live ? a0 : 0, live ? b0 : 0, hs, n, nc, ng);
+    srf_propagate_need(live ? xa0 : 0, live ? xb0 : 0, ws, n, cc, cg);
+    *rows = ng[0].b;
+    *cols = cg[0].b;
+}
+
 int srf_fuse_device(srf_ctx *ctx, const srf_tile *tiles, int n_tiles, int C, int levels, const srf_weight_lut *luts, int n_luts,
                        int out_h, int out_w, uint8_t *d_canvas, size_t canvas_pitch, int row_begin, int row_end, cudaStream_t st)
 {
@@ -948,31 +997,24 @@ int srf_fuse_device(srf_ctx *ctx, const srf_tile *tiles, int n_tiles, int C, int
         const int n = g.n_levels;
         for (int l = 1; l < n; ++l) t.G[l] = pyr + g_off[i][l];
         for (int l = 1; l <= n - 2; ++l) t.C[l] = pyr + c_off[i][l];
-        RowRange needC[SRF_MAX_LEVELS], needG[SRF_MAX_LEVELS];
-        for (int l = 0; l < SRF_MAX_LEVELS; ++l) needC[l] = needG[l] = RowRange{0, 0};
-        const bool x_overlap = std::max(0, t.x) < std::min(out_w, t.x + t.w);
-        const int a0 = std::max(row_begin, t.y) - t.y, b0 = std::min(std::min(row_end, out_h), t.y + t.h) - t.y;
-        if (x_overlap && a0 < b0) {
-            needC[0].merge(a0, b0);
-            for (int l = 1; l < n; ++l) {
-                const int h1 = g.lv[l].h;
-                const int lo = std::max((needC[l - 1].a >> 1) - 1, 0), hi = std::min(((needC[l - 1].b - 1) >> 1) + 2, h1);
-                needC[l].merge(lo, std::max(hi, std::min(2, h1))); // row 1 is the reflection of row -1
-                needG[l].merge(needC[l].a, needC[l].b);
-            }
-            for (int l = n - 1; l >= 2; --l) {
-                const int hs = g.lv[l - 1].h;
-                int lo = std::max(2 * needG[l].a - 2, 0), hi = std::min(2 * needG[l].b + 1, hs);
-                if (needG[l].a <= 0) hi = std::max(hi, std::min(3, hs));      // reflections of rows -1, -2
-                if (2 * needG[l].b + 1 > hs) lo = std::min(lo, std::max(hs - 3, 0)); // reflections past the bottom
-                needG[l - 1].merge(lo, hi);
-            }
+        RowRange needC[SRF_MAX_LEVELS], needG[SRF_MAX_LEVELS], colC[SRF_MAX_LEVELS], colG[SRF_MAX_LEVELS];
+        int hs[SRF_MAX_LEVELS], ws[SRF_MAX_LEVELS];
+        for (int l = 0; l < n; ++l) {
+            hs[l] = g.lv[l].h;
+            ws[l] = g.lv[l].w;
         }
+        const int xa0 = std::max(0, -t.x), xb0 = std::min(out_w, t.x + t.w) - t.x;
+        const int a0 = std::max(row_begin, t.y) - t.y, b0 = std::min(std::min(row_end, out_h), t.y + t.h) - t.y;
+        const bool live = (xa0 < xb0) && (a0 < b0);
+        srf_propagate_need(live ? a0 : 0, live ? b0 : 0, hs, n, needC, needG);
+        srf_propagate_need(live ? xa0 : 0, live ? xb0 : 0, ws, n, colC, colG);
         for (int l = 1; l < n; ++l) {
             t.g0[l] = needG[l].a;
             t.g1[l] = needG[l].b;
             t.c0[l] = needC[l].a;
             t.c1[l] = needC[l].b;
+            t.gx1[l] = colG[l].b;
+            t.cx1[l] = colC[l].b;
         }
     }
     for (size_t k = 0; k < groups.size(); ++k) {
@@ -1063,7 +1105,7 @@ int srf_fuse_device(srf_ctx *ctx, const srf_tile *tiles, int n_tiles, int C, int
             if (rows > 0) {
                 dim3 grid(srf_ceil_div(gi.lv[1].w, D8_BW), srf_ceil_div(rows, D8_ROWS), nt);
                 double px1 = 0; // level-1 pixels produced
-                for (int ti : groups[k].tiles) px1 += (double)(tdev[ti].g1[1] - tdev[ti].g0[1]) * gi.lv[1].w;
+                for (int ti : groups[k].tiles) px1 += (double)(tdev[ti].g1[1] - tdev[ti].g0[1]) * std::min(gi.lv[1].w, tdev[ti].gx1[1]);
                 srf_launch_scope scope(ctx, "down_u8", px1 * C * (4.0 /*u8 in*/ + 4.0 /*f32 out*/), st);
                 if (C == 3)
                     k_down_u8<3><<<grid, 128 * 3, 0, st>>>(d_tiles, ids_k, gi);
@@ -1076,7 +1118,7 @@ int srf_fuse_device(srf_ctx *ctx, const srf_tile *tiles, int n_tiles, int C, int
             if (rows <= 0) continue;
             dim3 grid(srf_ceil_div(gi.lv[l + 1].w, DN_BW), srf_ceil_div(rows, DN_BH), nt * C);
             double pxo = 0;
-            for (int ti : groups[k].tiles) pxo += (double)(tdev[ti].g1[l + 1] - tdev[ti].g0[l + 1]) * gi.lv[l + 1].w;
+            for (int ti : groups[k].tiles) pxo += (double)(tdev[ti].g1[l + 1] - tdev[ti].g0[l + 1]) * std::min(gi.lv[l + 1].w, tdev[ti].gx1[l + 1]);
             srf_launch_scope scope(ctx, "down_f32", pxo * C * (16.0 + 4.0), st);
             k_down_f32<false><<<grid, kThreads, 0, st>>>(d_tiles, ids_k, gi, l);
         }
@@ -1086,7 +1128,7 @@ int srf_fuse_device(srf_ctx *ctx, const srf_tile *tiles, int n_tiles, int C, int
             if (rows <= 0) continue;
             dim3 grid(srf_ceil_div(gi.lv[l].w, UP_BW), srf_ceil_div(rows, UP_BH), nt * C);
             double pxo = 0;
-            for (int ti : groups[k].tiles) pxo += (double)(tdev[ti].c1[l] - tdev[ti].c0[l]) * gi.lv[l].w;
+            for (int ti : groups[k].tiles) pxo += (double)(tdev[ti].c1[l] - tdev[ti].c0[l]) * std::min(gi.lv[l].w, tdev[ti].cx1[l]);
             // per output element: G_l + W_l/C read, C_l written, C_{l+1} (or W_{l+1}/C) + G_{l+1} at quarter density
             srf_launch_scope scope(ctx, "up_level", pxo * C * (4.0 + 4.0 / C + 4.0 + 2.0), st);
             if (l == n - 2)
@@ -1203,11 +1245,19 @@ extern "C" int srf_laplacian_fuse_host(srf_ctx *ctx, const srf_tile *tiles, int 
     if ((rc = srf_reserve(ctx, ctx->ws_stage_out, cpitch * (size_t)std::max(band, 1)))) return rc;
     cudaStream_t st = ctx->own_stream;
     uint8_t *din = (uint8_t *)ctx->ws_stage_in.ptr;
+    size_t h2d = 0;
     for (int i = 0; i < n_tiles; ++i) {
         dt[i].data = din + off[i];
-        SRF_CHECK_CUDA(ctx, cudaMemcpy2DAsync(din + off[i], dt[i].pitch, tiles[i].data, tiles[i].pitch, (size_t)tiles[i].w * channels,
-                                              tiles[i].h, cudaMemcpyHostToDevice, st));
+        int rows = 0, cols = 0; // only the part of the tile the requested canvas rows can depend on travels
+        srf_fuse_input_extent(tiles[i], levels, out_h, out_w, row_begin, row_end, &rows, &cols);
+        if (rows > 0 && cols > 0) {
+            h2d += (size_t)cols * channels * rows;
+            SRF_CHECK_CUDA(ctx, cudaMemcpy2DAsync(din + off[i], dt[i].pitch, tiles[i].data, tiles[i].pitch, (size_t)cols * channels, rows,
+                                                  cudaMemcpyHostToDevice, st));
+        }
     }
+    ctx->last_h2d = h2d;
+    ctx->last_d2h = (size_t)out_w * channels * (size_t)std::max(band, 0);
     SRF_CHECK_CUDA(ctx, cudaEventRecord(ctx->ev0, st));
     // the staged canvas holds only the band: shift the base so canvas row `row_begin` lands on staged row 0
     uint8_t *dcanvas = (uint8_t *)ctx->ws_stage_out.ptr - (size_t)row_begin * cpitch;

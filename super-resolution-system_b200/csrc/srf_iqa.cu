@@ -347,7 +347,7 @@ __global__ void __launch_bounds__(256) k_iqa_reduce(const IqaPartial *__restrict
 } // namespace
 
 int srf_iqa_enqueue(srf_ctx *ctx, const uint8_t *a, size_t pa, const uint8_t *b, size_t pb, int h, int w, int C, int scale_a, int scale_b,
-                    double data_range, int row_begin, int row_end, cudaStream_t st)
+                    double data_range, int row_begin, int row_end, cudaStream_t st, int slot)
 {
     int rc;
     const int gx = srf_ceil_div(w, IQ_THREADS), gy = srf_ceil_div(row_end - row_begin, IQ_RB);
@@ -389,13 +389,13 @@ int srf_iqa_enqueue(srf_ctx *ctx, const uint8_t *a, size_t pa, const uint8_t *b,
         k_iqa_reduce<<<1, 256, 0, st>>>(parts, (int)nparts, final_d);
     }
     SRF_CHECK_CUDA(ctx, cudaGetLastError());
-    SRF_CHECK_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, final_d, sizeof(IqaPartial), cudaMemcpyDeviceToHost, st));
+    SRF_CHECK_CUDA(ctx, cudaMemcpyAsync((IqaPartial *)ctx->pinned + slot, final_d, sizeof(IqaPartial), cudaMemcpyDeviceToHost, st));
     return SRF_OK;
 }
 
-void srf_iqa_collect(srf_ctx *ctx, int w, int C, int row_begin, int row_end, srf_iqa_sums *out)
+void srf_iqa_collect(srf_ctx *ctx, int w, int C, int row_begin, int row_end, srf_iqa_sums *out, int slot)
 {
-    const IqaPartial *f = (const IqaPartial *)ctx->pinned;
+    const IqaPartial *f = (const IqaPartial *)ctx->pinned + slot;
     out->sq_err = (int64_t)f->sq;
     out->n_elems = (int64_t)(row_end - row_begin) * w * C;
     out->ssim_sum = f->ssim;
@@ -408,14 +408,14 @@ static int iqa_device(srf_ctx *ctx, const uint8_t *a, size_t pa, const uint8_t *
                       double data_range, int row_begin, int row_end, srf_iqa_sums *out, cudaStream_t st, bool record_events)
 {
     if (record_events) SRF_CHECK_CUDA(ctx, cudaEventRecord(ctx->ev0, st));
-    int rc = srf_iqa_enqueue(ctx, a, pa, b, pb, h, w, C, scale_a, scale_b, data_range, row_begin, row_end, st);
+    int rc = srf_iqa_enqueue(ctx, a, pa, b, pb, h, w, C, scale_a, scale_b, data_range, row_begin, row_end, st, 0);
     if (rc) return rc;
     if (record_events) {
         SRF_CHECK_CUDA(ctx, cudaEventRecord(ctx->ev1, st));
         ctx->ev_valid = true;
     }
     SRF_CHECK_CUDA(ctx, cudaStreamSynchronize(st));
-    srf_iqa_collect(ctx, w, C, row_begin, row_end, out);
+    srf_iqa_collect(ctx, w, C, row_begin, row_end, out, 0);
     return SRF_OK;
 }
 

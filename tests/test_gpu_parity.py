@@ -270,3 +270,27 @@ def test_pipeline_run_small(srs, oracle):
     res = pipe.run(src)
     assert res["canvas"].shape == (360, 640, 3) and res["tiles"] >= 2
     assert 0 < res["report"]["ms_ssim"] <= 1
+
+
+def test_fuse_and_assess_band_pipeline_equals_two_calls(srs):
+    """the pipelined host entry point (several bands, three streams) returns the bytes and sums of the plain calls"""
+    rng = np.random.default_rng(41)
+    tiles, pos = [], []
+    for j in range(4):
+        for i in range(2):
+            tiles.append(synth(rng, 1024, 512))
+            pos.append((j * 820, i * 400))
+    out_hw = (3400, 900)  # 3 bands of ~1134 rows; the last tile row overhangs
+    infos = [srs.TileInfo(t, x, y, 0, 0) for t, (y, x) in zip(tiles, pos)]
+    ref = synth(rng, out_hw[0], out_hw[1])
+    bm = srs.BlendingModule(num_levels=6)
+    qa = srs.QualityAssessmentModule()
+    canvas, sums = bm.fuse_and_assess(infos, ref, out_hw)
+    want = bm.laplacian_fusion(infos, output_shape=out_hw)
+    assert np.array_equal(canvas, want)
+    s2 = qa.psnr_ssim_sums(ref, want)
+    assert (sums.sq_err, sums.ssim_count, sums.n_elems) == (s2.sq_err, s2.ssim_count, s2.n_elems)
+    assert sums.ssim_sum == pytest.approx(s2.ssim_sum, rel=1e-7)
+    pipe = srs.SuperResolutionPipeline(srs.PipelineConfig(num_pyramid_levels=6))
+    c2, rep = pipe.fuse_and_assess(infos, ref, out_hw)
+    assert np.array_equal(c2, want) and rep["psnr"] == pytest.approx(qa.finish(s2)[0], rel=1e-12)
