@@ -46,6 +46,13 @@ class TileInfo:
     col: int
 
 
+class FusionPlan:
+    """a marshalled tile list (see BlendingModule.plan_fusion)"""
+
+    def __init__(self, *parts):
+        self.parts = parts
+
+
 def weight_profile(feather_width: int, weight_type: WeightType) -> np.ndarray:
     """The distance-weight map only depends on d = min distance to the tile border, and only through
     min(d, feather_width): this is that 1-D profile, evaluated with the reference's float64 NumPy expressions
@@ -183,7 +190,23 @@ class BlendingModule:
                 luts.append(prof)
             c_tiles[i] = _native.srf_tile(v.ptr, v.pitch, v.h, v.w, y, x, lut_index[id(prof)])
         c_luts = (_native.srf_weight_lut * len(luts))(*[_native.srf_weight_lut(p.ctypes.data, len(p)) for p in luts])
-        return views, c_tiles, c_luts, luts, out_h, out_w, chans
+        keep = list(luts)
+        if on_dev:  # the kernels want 16-byte aligned rows: re-stage a misaligned tensor (the copy lives as long as `keep`)
+            for i, v in enumerate(views):
+                if v.ptr % 16 or (v.pitch % 16 and v.h > 1):
+                    pitch = (v.w * chans + 15) // 16 * 16
+                    buf = torch.empty((v.h, pitch), dtype=torch.uint8, device=v.keep.device)
+                    buf[:, : v.w * chans] = v.keep.reshape(v.h, v.w * chans)
+                    keep.append(buf)
+                    c_tiles[i].data, c_tiles[i].pitch = buf.data_ptr(), pitch
+        return views, c_tiles, c_luts, keep, out_h, out_w, chans
+
+    def plan_fusion(self, tiles, output_shape=None, weight_type: WeightType = WeightType.COSINE):
+        """Marshal a tile list once (extension): the returned plan can be passed to laplacian_fusion in place of the
+        tile list any number of times -- the per-call Python work drops to one ctypes call.  The plan keeps the tile
+        arrays alive; their contents may change between calls, their addresses may not (a CUDA tile that had to be
+        re-staged for alignment is snapshotted in the plan)."""
+        return FusionPlan(*self._marshal(tiles, output_shape, weight_type))
 
     def laplacian_fusion(self, tiles: List[Union[np.ndarray, TileInfo]], overlap_map=None,
                          output_shape: Optional[Tuple[int, int]] = None,
@@ -198,7 +221,10 @@ class BlendingModule:
         canvas rows (band sharding across GPUs; other rows are zero / left as they are in `out`), `out` reuses a
         caller-owned canvas.
         """
-        views, c_tiles, c_luts, keep, out_h, out_w, chans = self._marshal(tiles, output_shape, weight_type)
+        if isinstance(tiles, FusionPlan):
+            views, c_tiles, c_luts, keep, out_h, out_w, chans = tiles.parts
+        else:
+            views, c_tiles, c_luts, keep, out_h, out_w, chans = self._marshal(tiles, output_shape, weight_type)
         on_dev = views[0].on_device
         r0, r1 = (0, out_h) if row_range is None else (int(row_range[0]), int(row_range[1]))
         lib, ctx = _native.load(), self._ctx()
@@ -207,14 +233,6 @@ class BlendingModule:
             dev = views[0].device
             if dev != self.device:
                 raise ValueError(f"tiles live on cuda:{dev} but this BlendingModule is bound to cuda:{self.device}")
-            staged = []
-            for i, v in enumerate(views):  # the kernels want 16-byte aligned rows
-                if v.ptr % 16 or (v.pitch % 16 and v.h > 1):
-                    pitch = (v.w * chans + 15) // 16 * 16
-                    buf = torch.empty((v.h, pitch), dtype=torch.uint8, device=v.keep.device)
-                    buf[:, : v.w * chans] = v.keep.reshape(v.h, v.w * chans)
-                    staged.append(buf)
-                    c_tiles[i].data, c_tiles[i].pitch = buf.data_ptr(), pitch
             if out is not None:
                 if not is_cuda_tensor(out) or tuple(out.shape) != shape or out.dtype != torch.uint8 or not out.is_contiguous():
                     raise ValueError("out must be a contiguous uint8 CUDA tensor of the canvas shape")
@@ -226,7 +244,6 @@ class BlendingModule:
             rc = lib.srf_laplacian_fuse(ctx, c_tiles, len(views), chans, self.num_levels, c_luts, len(c_luts), out_h,
                                         out_w, canvas.data_ptr(), out_w * chans, r0, r1, current_stream_ptr(dev))
             _native.check(rc, ctx)
-            del staged
             return canvas
         if out is not None:
             if not isinstance(out, np.ndarray) or out.shape != shape or out.dtype != np.uint8 or not out.flags.c_contiguous:

@@ -974,14 +974,17 @@ int srf_fuse_device(srf_ctx *ctx, const srf_tile *tiles, int n_tiles, int C, int
     }
     int rc;
     if ((rc = srf_reserve(ctx, ctx->ws_pyr, pyr_floats * sizeof(float) + 256))) return rc;
-    const size_t desc_bytes = srf_align_up(sizeof(TileDev) * n_tiles, 256) + srf_align_up(sizeof(GroupDev) * groups.size(), 256) +
-                              srf_align_up(sizeof(int) * n_tiles * 2, 256) + srf_align_up(sizeof(int4) * n_tiles, 256);
+    // every descriptor and the weight profiles travel as ONE blob: [tiles | groups | tile_group, tile_ids | rects | luts]
+    const size_t o_groups = srf_align_up(sizeof(TileDev) * n_tiles, 256);
+    const size_t o_ints = o_groups + srf_align_up(sizeof(GroupDev) * groups.size(), 256);
+    const size_t o_rects = o_ints + srf_align_up(sizeof(int) * n_tiles * 2, 256);
+    const size_t o_luts = o_rects + srf_align_up(sizeof(int4) * n_tiles, 256);
+    const size_t desc_bytes = o_luts + srf_align_up(lut_floats * sizeof(float), 256);
     if ((rc = srf_reserve(ctx, ctx->ws_desc, desc_bytes))) return rc;
-    if ((rc = srf_reserve(ctx, ctx->ws_misc, lut_floats * sizeof(float) + 256))) return rc;
     float *pyr = (float *)ctx->ws_pyr.ptr;
-    float *d_lut = (float *)ctx->ws_misc.ptr;
-    for (int k = 0; k < n_luts; ++k)
-        SRF_CHECK_CUDA(ctx, cudaMemcpyAsync(d_lut + lut_off[k], luts[k].values, sizeof(float) * luts[k].len, cudaMemcpyHostToDevice, st));
+    float *d_lut = (float *)((uint8_t *)ctx->ws_desc.ptr + o_luts);
+    std::vector<uint8_t> blob(desc_bytes, 0);
+    for (int k = 0; k < n_luts; ++k) memcpy(blob.data() + o_luts + lut_off[k] * sizeof(float), luts[k].values, sizeof(float) * luts[k].len);
 
     // ---- row ranges per tile and level (band mode computes only what canvas rows [row_begin,row_end) need) ----
     for (int i = 0; i < n_tiles; ++i) {
@@ -1029,10 +1032,10 @@ int srf_fuse_device(srf_ctx *ctx, const srf_tile *tiles, int n_tiles, int C, int
     // ---- upload descriptors ----
     uint8_t *dbase = (uint8_t *)ctx->ws_desc.ptr;
     TileDev *d_tiles = (TileDev *)dbase;
-    GroupDev *d_groups = (GroupDev *)(dbase + srf_align_up(sizeof(TileDev) * n_tiles, 256));
-    int *d_tile_group = (int *)((uint8_t *)d_groups + srf_align_up(sizeof(GroupDev) * groups.size(), 256));
+    GroupDev *d_groups = (GroupDev *)(dbase + o_groups);
+    int *d_tile_group = (int *)(dbase + o_ints);
     int *d_tile_ids = d_tile_group + n_tiles;
-    int4 *d_rects = (int4 *)((uint8_t *)d_tile_group + srf_align_up(sizeof(int) * n_tiles * 2, 256));
+    int4 *d_rects = (int4 *)(dbase + o_rects);
     std::vector<int4> rects(n_tiles);
     for (int i = 0; i < n_tiles; ++i) rects[i] = make_int4(tiles[i].y, tiles[i].x, tiles[i].h, tiles[i].w);
     std::vector<int> ids;
@@ -1049,11 +1052,12 @@ int srf_fuse_device(srf_ctx *ctx, const srf_tile *tiles, int n_tiles, int C, int
             gdev_img[k].lv[l].vtail = 4 * ((gdev_img[k].lv[l].w * C) / 4);
         }
     }
-    SRF_CHECK_CUDA(ctx, cudaMemcpyAsync(d_tiles, tdev.data(), sizeof(TileDev) * n_tiles, cudaMemcpyHostToDevice, st));
-    SRF_CHECK_CUDA(ctx, cudaMemcpyAsync(d_groups, gdev_img.data(), sizeof(GroupDev) * groups.size(), cudaMemcpyHostToDevice, st));
-    SRF_CHECK_CUDA(ctx, cudaMemcpyAsync(d_tile_group, tile_group.data(), sizeof(int) * n_tiles, cudaMemcpyHostToDevice, st));
-    SRF_CHECK_CUDA(ctx, cudaMemcpyAsync(d_tile_ids, ids.data(), sizeof(int) * n_tiles, cudaMemcpyHostToDevice, st));
-    SRF_CHECK_CUDA(ctx, cudaMemcpyAsync(d_rects, rects.data(), sizeof(int4) * n_tiles, cudaMemcpyHostToDevice, st));
+    memcpy(blob.data(), tdev.data(), sizeof(TileDev) * n_tiles);
+    memcpy(blob.data() + o_groups, gdev_img.data(), sizeof(GroupDev) * groups.size());
+    memcpy(blob.data() + o_ints, tile_group.data(), sizeof(int) * n_tiles);
+    memcpy(blob.data() + o_ints + sizeof(int) * n_tiles, ids.data(), sizeof(int) * n_tiles);
+    memcpy(blob.data() + o_rects, rects.data(), sizeof(int4) * n_tiles);
+    SRF_CHECK_CUDA(ctx, cudaMemcpyAsync(dbase, blob.data(), desc_bytes, cudaMemcpyHostToDevice, st));
 
     // ---- weight pyramids depend only on (shape, levels, profile): keep them across calls while ws_pyr is unchanged ----
     std::vector<uint64_t> wkeys(groups.size());

@@ -37,16 +37,17 @@ def tiles_for_rows(positions_yx: Sequence[Tuple[int, int]], heights: Sequence[in
 
 def allreduce_sums(sums, total_elems: int, group=None, device=None):
     """sum srf_iqa_sums over the ranks of `group` (in place) and return it.  sq_err and ssim_count are integers below
-    2^53, exact in float64; bits_a / bits_b are OR-ed by a max-reduce of their <=1 / >1 class."""
+    2^53, exact in float64; bits_a / bits_b travel as their <= 1 / > 1 class."""
     import torch.distributed as dist
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return sums
-    t = torch.tensor([float(sums.sq_err), sums.ssim_sum, float(sums.ssim_count)], dtype=torch.float64, device=device)
+    # one collective: the two OR-of-bytes fields only matter through "is any byte > 1", which sums fine
+    t = torch.tensor([float(sums.sq_err), sums.ssim_sum, float(sums.ssim_count), float(sums.bits_a > 1), float(sums.bits_b > 1)],
+                     dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
-    b = torch.tensor([float(sums.bits_a), float(sums.bits_b)], dtype=torch.float64, device=device)
-    dist.all_reduce(b, op=dist.ReduceOp.MAX, group=group)
-    v, bv = t.tolist(), b.tolist()
+    v = t.tolist()
     sums.sq_err, sums.ssim_sum, sums.ssim_count = int(v[0]), v[1], int(v[2])
     sums.n_elems = int(total_elems)
-    sums.bits_a, sums.bits_b = int(bv[0]), int(bv[1])
+    sums.bits_a = 255 if v[3] > 0 else min(int(sums.bits_a), 1)
+    sums.bits_b = 255 if v[4] > 0 else min(int(sums.bits_b), 1)
     return sums

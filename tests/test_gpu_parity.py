@@ -294,3 +294,19 @@ def test_fuse_and_assess_band_pipeline_equals_two_calls(srs):
     pipe = srs.SuperResolutionPipeline(srs.PipelineConfig(num_pyramid_levels=6))
     c2, rep = pipe.fuse_and_assess(infos, ref, out_hw)
     assert np.array_equal(c2, want) and rep["psnr"] == pytest.approx(qa.finish(s2)[0], rel=1e-12)
+
+
+def test_fusion_plan_reuse_and_misaligned_device_tiles(srs):
+    import torch
+    rng = np.random.default_rng(42)
+    tiles, pos = _grid_case(rng, 130, 131, 2, 2, 100, 100)  # 131*3 bytes per row: misaligned pitch on the device
+    bm = srs.BlendingModule(num_levels=4)
+    host = bm.laplacian_fusion([srs.TileInfo(t, x, y, 0, 0) for t, (y, x) in zip(tiles, pos)], output_shape=(230, 231))
+    dev_infos = [srs.TileInfo(torch.from_numpy(t).cuda(), x, y, 0, 0) for t, (y, x) in zip(tiles, pos)]
+    plan = bm.plan_fusion(dev_infos, output_shape=(230, 231))
+    out = torch.empty((230, 231, 3), dtype=torch.uint8, device="cuda")
+    for _ in range(3):
+        got = bm.laplacian_fusion(plan, out=out)
+        assert got is out and np.array_equal(got.cpu().numpy(), host)
+    hplan = bm.plan_fusion([srs.TileInfo(t, x, y, 0, 0) for t, (y, x) in zip(tiles, pos)], output_shape=(230, 231))
+    assert np.array_equal(bm.laplacian_fusion(hplan), host)
