@@ -158,6 +158,12 @@ int srf_psnr_ssim(srf_ctx *ctx, const uint8_t *d_a, size_t pitch_a, const uint8_
 int srf_psnr_ssim_host(srf_ctx *ctx, const uint8_t *h_a, size_t pitch_a, const uint8_t *h_b, size_t pitch_b,
                        int h, int w, int channels, int scale_a, int scale_b, double data_range, int row_begin,
                        int row_end, srf_iqa_sums *h_out);
+/* enqueue-only variant for multi-GPU use: no synchronisation, the band's sums are written to DEVICE memory as five
+ * doubles {sq_err, ssim_sum, ssim_count, any byte of a > 1, any byte of b > 1} -- additive, so the caller can
+ * ncclAllReduce(sum) them in place and read the totals back with one copy */
+int srf_psnr_ssim_enqueue(srf_ctx *ctx, const uint8_t *d_a, size_t pitch_a, const uint8_t *d_b, size_t pitch_b, int h,
+                          int w, int channels, int scale_a, int scale_b, double data_range, int row_begin, int row_end,
+                          double *d_sums5, void *stream);
 /* stage 3 + stage 4 of the reference pipeline in one call (main.py:347 laplacian_fusion, :369
  * evaluate_full_reference): host tiles -> fused canvas (host) + PSNR/SSIM sums of the canvas against a host
  * comparison image of the same size.  The canvas stays on the device between the two stages; uploads, kernels and

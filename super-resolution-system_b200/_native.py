@@ -67,6 +67,8 @@ SIGNATURES = {
                                         c_int, c_void_p, c_size_t, c_int, c_int]),
     "srf_psnr_ssim": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, c_int, c_int, c_int, c_int, c_int,
                               C.c_double, c_int, c_int, P(srf_iqa_sums), c_void_p]),
+    "srf_psnr_ssim_enqueue": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, c_int, c_int, c_int, c_int, c_int,
+                                      C.c_double, c_int, c_int, c_void_p, c_void_p]),
     "srf_psnr_ssim_host": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, c_int, c_int, c_int, c_int, c_int,
                                    C.c_double, c_int, c_int, P(srf_iqa_sums)]),
     "srf_fuse_assess_host": (c_int, [c_void_p, P(srf_tile), c_int, c_int, c_int, P(srf_weight_lut), c_int, c_int, c_int,

@@ -37,6 +37,8 @@ void srf_set_error(const srf_ctx *ctx, const char *fmt, ...)
 int srf_reserve(srf_ctx *ctx, srf_buffer &b, size_t bytes)
 {
     if (bytes <= b.bytes) return SRF_OK;
+    ctx->ws_epoch++; // pointers handed to captured graphs / cached descriptors are about to change
+    ctx->desc_sig = 0;
     if (b.ptr) {
         SRF_CHECK_CUDA(ctx, cudaDeviceSynchronize());
         SRF_CHECK_CUDA(ctx, cudaFree(b.ptr));
@@ -137,6 +139,7 @@ extern "C" void srf_destroy(srf_ctx *c)
     srf_buffer *bs[] = {&c->ws_pyr, &c->ws_desc, &c->ws_stage_in, &c->ws_stage_out, &c->ws_misc, &c->ws_iqa};
     for (srf_buffer *b : bs)
         if (b->ptr) cudaFree(b->ptr);
+    if (c->fuse_graph) cudaGraphExecDestroy(c->fuse_graph);
     if (c->pinned) cudaFreeHost(c->pinned);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     for (cudaEvent_t e : c->ev_aux)
@@ -356,6 +359,8 @@ extern "C" int srf_tile_extract_pad(srf_ctx *ctx, const uint8_t *d_src, int heig
         const int rc = srf_reserve(ctx, ctx->ws_desc, (size_t)n * sizeof(int4));
         if (rc) return rc;
     }
+    ctx->desc_sig = 0; // ws_desc is shared with the fusion descriptors
+    ctx->fuse_sig = 0;
     SRF_CHECK_CUDA(ctx, cudaMemcpyAsync(ctx->ws_desc.ptr, xywh, (size_t)n * sizeof(int4), cudaMemcpyHostToDevice, st));
     const int vec_ok = ((block * channels) % 16 == 0) && (((uintptr_t)d_out) % 16 == 0);
     dim3 grid(block, n);

@@ -61,6 +61,13 @@ struct srf_ctx {
     // weight pyramids of the previous fuse call still valid in ws_pyr: one key per shape group (srf_fuse.cu)
     std::vector<uint64_t> wcache_keys;
     const void *wcache_base = nullptr;
+    // CUDA-graph replay of a repeated srf_laplacian_fuse call (same tiles, canvas, band, stream): the second identical
+    // call is captured, later ones are one cudaGraphLaunch.  Any workspace reallocation bumps ws_epoch and drops it.
+    uint64_t fuse_sig = 0;        // signature of the last srf_laplacian_fuse call
+    uint64_t desc_sig = 0;        // signature whose descriptors currently sit in ws_desc
+    uint64_t ws_epoch = 0, graph_epoch = 0;
+    cudaGraphExec_t fuse_graph = nullptr;
+    int64_t fuse_graph_launches = 0;
     // per-kernel profiling (srf_profile_enable)
     bool profile = false;
     struct ProfRec {
@@ -196,5 +203,5 @@ void srf_fuse_input_extent(const srf_tile &t, int levels, int out_h, int out_w, 
 // enqueue only: the sums land in slot `slot` (0..63) of ctx->pinned once the stream is synchronised; srf_iqa_collect
 // converts them
 int srf_iqa_enqueue(srf_ctx *ctx, const uint8_t *a, size_t pa, const uint8_t *b, size_t pb, int h, int w, int C, int scale_a, int scale_b,
-                    double data_range, int row_begin, int row_end, cudaStream_t st, int slot);
+                    double data_range, int row_begin, int row_end, cudaStream_t st, int slot, double *d_sums = nullptr);
 void srf_iqa_collect(srf_ctx *ctx, int w, int C, int row_begin, int row_end, srf_iqa_sums *out, int slot);

@@ -900,6 +900,29 @@ void srf_fuse_input_extent(const srf_tile &t, int levels, int out_h, int out_w, 
     *cols = cg[0].b;
 }
 
+static uint64_t fuse_signature(const srf_tile *tiles, int n_tiles, int C, int levels, const srf_weight_lut *luts, int n_luts, int out_h,
+                               int out_w, const void *canvas, size_t canvas_pitch, int row_begin, int row_end, const void *stream)
+{
+    uint64_t hsh = 1469598103934665603ull;
+    auto mix = [&](const void *ptr, size_t nb) {
+        const uint8_t *b = (const uint8_t *)ptr;
+        for (size_t i = 0; i < nb; ++i) hsh = (hsh ^ b[i]) * 1099511628211ull;
+    };
+    for (int i = 0; i < n_tiles; ++i) { // field by field: struct padding is not defined
+        mix(&tiles[i].data, sizeof(void *));
+        mix(&tiles[i].pitch, sizeof(size_t));
+        const int v[5] = {tiles[i].h, tiles[i].w, tiles[i].y, tiles[i].x, tiles[i].lut};
+        mix(v, sizeof v);
+    }
+    for (int k = 0; k < n_luts; ++k) mix(luts[k].values, sizeof(float) * luts[k].len);
+    const int geo[7] = {n_tiles, C, levels, out_h, out_w, row_begin, row_end};
+    mix(geo, sizeof geo);
+    mix(&canvas, sizeof canvas);
+    mix(&canvas_pitch, sizeof canvas_pitch);
+    mix(&stream, sizeof stream);
+    return hsh ? hsh : 1;
+}
+
 int srf_fuse_device(srf_ctx *ctx, const srf_tile *tiles, int n_tiles, int C, int levels, const srf_weight_lut *luts, int n_luts,
                        int out_h, int out_w, uint8_t *d_canvas, size_t canvas_pitch, int row_begin, int row_end, cudaStream_t st)
 {
@@ -1057,7 +1080,14 @@ int srf_fuse_device(srf_ctx *ctx, const srf_tile *tiles, int n_tiles, int C, int
     memcpy(blob.data() + o_ints, tile_group.data(), sizeof(int) * n_tiles);
     memcpy(blob.data() + o_ints + sizeof(int) * n_tiles, ids.data(), sizeof(int) * n_tiles);
     memcpy(blob.data() + o_rects, rects.data(), sizeof(int4) * n_tiles);
-    SRF_CHECK_CUDA(ctx, cudaMemcpyAsync(dbase, blob.data(), desc_bytes, cudaMemcpyHostToDevice, st));
+    {
+        const cudaStream_t st_id = st;
+        const uint64_t sig = fuse_signature(tiles, n_tiles, C, levels, luts, n_luts, out_h, out_w, d_canvas, canvas_pitch, row_begin, row_end, &st_id);
+        if (ctx->desc_sig != sig) { // identical call as last time: the descriptors are already in ws_desc
+            SRF_CHECK_CUDA(ctx, cudaMemcpyAsync(dbase, blob.data(), desc_bytes, cudaMemcpyHostToDevice, st));
+            ctx->desc_sig = sig;
+        }
+    }
 
     // ---- weight pyramids depend only on (shape, levels, profile): keep them across calls while ws_pyr is unchanged ----
     std::vector<uint64_t> wkeys(groups.size());
@@ -1217,6 +1247,44 @@ extern "C" int srf_laplacian_fuse(srf_ctx *ctx, const srf_tile *tiles, int n_til
                     "(use srf_laplacian_fuse_host, or copy into an aligned buffer)", i);
     SRF_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
+    const cudaStream_t st_id = st;
+    const uint64_t sig = fuse_signature(tiles, n_tiles, channels, levels, luts, n_luts, out_h, out_w, d_canvas, canvas_pitch, row_begin, row_end, &st_id);
+    const bool repeat = !ctx->profile && st != nullptr && sig == ctx->fuse_sig && ctx->desc_sig == sig;
+    if (repeat && ctx->fuse_graph && ctx->graph_epoch == ctx->ws_epoch) { // third and later identical calls: replay
+        SRF_CHECK_CUDA(ctx, cudaGraphLaunch(ctx->fuse_graph, st));
+        ctx->launches += ctx->fuse_graph_launches;
+        ctx->ev_valid = false;
+        return SRF_OK;
+    }
+    if (ctx->fuse_graph) {
+        cudaGraphExecDestroy(ctx->fuse_graph);
+        ctx->fuse_graph = nullptr;
+    }
+    if (repeat) { // second identical call: every workspace is sized and the descriptors are resident -> capture it
+        const int64_t l0 = ctx->launches;
+        const uint64_t epoch = ctx->ws_epoch;
+        cudaGraph_t graph = nullptr;
+        if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+            rc = srf_fuse_device(ctx, tiles, n_tiles, channels, levels, luts, n_luts, out_h, out_w, d_canvas, canvas_pitch, row_begin, row_end, st);
+            const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+            if (rc == SRF_OK && ce == cudaSuccess && graph && epoch == ctx->ws_epoch &&
+                cudaGraphInstantiate(&ctx->fuse_graph, graph, 0) == cudaSuccess) {
+                ctx->fuse_graph_launches = ctx->launches - l0;
+                ctx->graph_epoch = epoch;
+                cudaGraphDestroy(graph);
+                SRF_CHECK_CUDA(ctx, cudaGraphLaunch(ctx->fuse_graph, st));
+                ctx->ev_valid = false;
+                return SRF_OK;
+            }
+            if (graph) cudaGraphDestroy(graph);
+            ctx->fuse_graph = nullptr;
+            ctx->launches = l0;
+            (void)cudaGetLastError(); // capture failed: fall through to a plain enqueue
+        } else {
+            (void)cudaGetLastError();
+        }
+    }
+    ctx->fuse_sig = sig;
     SRF_CHECK_CUDA(ctx, cudaEventRecord(ctx->ev0, st));
     rc = srf_fuse_device(ctx, tiles, n_tiles, channels, levels, luts, n_luts, out_h, out_w, d_canvas, canvas_pitch, row_begin, row_end, st);
     if (rc) return rc;

@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(IQ_THREADS, 5) k_psnr_ssim(IqaParams P)
 }
 
 // single CTA, fixed summation order: thread k sums partials k, k+256, ... then a shared-memory tree
-__global__ void __launch_bounds__(256) k_iqa_reduce(const IqaPartial *__restrict__ parts, int n, IqaPartial *__restrict__ out)
+__global__ void __launch_bounds__(256) k_iqa_reduce(const IqaPartial *__restrict__ parts, int n, IqaPartial *__restrict__ out, double *__restrict__ dsum)
 {
     __shared__ IqaPartial s[256];
     IqaPartial p;
@@ -341,13 +341,22 @@ __global__ void __launch_bounds__(256) k_iqa_reduce(const IqaPartial *__restrict
         }
         __syncthreads();
     }
-    if (threadIdx.x == 0) *out = s[0];
+    if (threadIdx.x == 0) {
+        *out = s[0];
+        if (dsum) { // additive form for a device-side all-reduce: {sq_err, ssim_sum, ssim_count, any byte of a > 1, of b > 1}
+            dsum[0] = (double)s[0].sq;
+            dsum[1] = s[0].ssim;
+            dsum[2] = (double)s[0].cnt;
+            dsum[3] = s[0].max_a > 1 ? 1.0 : 0.0;
+            dsum[4] = s[0].max_b > 1 ? 1.0 : 0.0;
+        }
+    }
 }
 
 } // namespace
 
 int srf_iqa_enqueue(srf_ctx *ctx, const uint8_t *a, size_t pa, const uint8_t *b, size_t pb, int h, int w, int C, int scale_a, int scale_b,
-                    double data_range, int row_begin, int row_end, cudaStream_t st, int slot)
+                    double data_range, int row_begin, int row_end, cudaStream_t st, int slot, double *d_sums)
 {
     int rc;
     const int gx = srf_ceil_div(w, IQ_THREADS), gy = srf_ceil_div(row_end - row_begin, IQ_RB);
@@ -386,10 +395,11 @@ int srf_iqa_enqueue(srf_ctx *ctx, const uint8_t *a, size_t pa, const uint8_t *b,
     }
     {
         srf_launch_scope scope(ctx, "iqa_reduce", 0.0, st);
-        k_iqa_reduce<<<1, 256, 0, st>>>(parts, (int)nparts, final_d);
+        k_iqa_reduce<<<1, 256, 0, st>>>(parts, (int)nparts, final_d, d_sums);
     }
     SRF_CHECK_CUDA(ctx, cudaGetLastError());
-    SRF_CHECK_CUDA(ctx, cudaMemcpyAsync((IqaPartial *)ctx->pinned + slot, final_d, sizeof(IqaPartial), cudaMemcpyDeviceToHost, st));
+    if (slot >= 0)
+        SRF_CHECK_CUDA(ctx, cudaMemcpyAsync((IqaPartial *)ctx->pinned + slot, final_d, sizeof(IqaPartial), cudaMemcpyDeviceToHost, st));
     return SRF_OK;
 }
 
@@ -408,7 +418,7 @@ static int iqa_device(srf_ctx *ctx, const uint8_t *a, size_t pa, const uint8_t *
                       double data_range, int row_begin, int row_end, srf_iqa_sums *out, cudaStream_t st, bool record_events)
 {
     if (record_events) SRF_CHECK_CUDA(ctx, cudaEventRecord(ctx->ev0, st));
-    int rc = srf_iqa_enqueue(ctx, a, pa, b, pb, h, w, C, scale_a, scale_b, data_range, row_begin, row_end, st, 0);
+    int rc = srf_iqa_enqueue(ctx, a, pa, b, pb, h, w, C, scale_a, scale_b, data_range, row_begin, row_end, st, 0, nullptr);
     if (rc) return rc;
     if (record_events) {
         SRF_CHECK_CUDA(ctx, cudaEventRecord(ctx->ev1, st));
@@ -459,4 +469,16 @@ extern "C" int srf_psnr_ssim_host(srf_ctx *ctx, const uint8_t *h_a, size_t pitch
         SRF_CHECK_CUDA(ctx, cudaMemcpy2DAsync(db, dp, h_b + (size_t)r0 * pitch_b, pitch_b, (size_t)w * channels, r1 - r0, cudaMemcpyHostToDevice, st));
     }
     return iqa_device(ctx, da - (size_t)r0 * dp, dp, db - (size_t)r0 * dp, dp, h, w, channels, scale_a, scale_b, data_range, row_begin, row_end, h_out, st, true);
+}
+
+extern "C" int srf_psnr_ssim_enqueue(srf_ctx *ctx, const uint8_t *d_a, size_t pitch_a, const uint8_t *d_b, size_t pitch_b, int h, int w,
+                                     int channels, int scale_a, int scale_b, double data_range, int row_begin, int row_end, double *d_sums5,
+                                     void *stream)
+{
+    if (!ctx) return SRF_ERR_ARG;
+    int rc = check_iqa_args(ctx, d_a, pitch_a, d_b, pitch_b, h, w, channels, row_begin, row_end, d_sums5);
+    if (rc) return rc;
+    SRF_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+    return srf_iqa_enqueue(ctx, d_a, pitch_a, d_b, pitch_b, h, w, channels, scale_a, scale_b, data_range, row_begin, row_end,
+                           (cudaStream_t)stream, -1, d_sums5);
 }

@@ -51,3 +51,16 @@ def allreduce_sums(sums, total_elems: int, group=None, device=None):
     sums.bits_a = 255 if v[3] > 0 else min(int(sums.bits_a), 1)
     sums.bits_b = 255 if v[4] > 0 else min(int(sums.bits_b), 1)
     return sums
+
+
+def allreduce_device_sums(d_sums, total_elems: int, group=None):
+    """`d_sums`: the 5-double CUDA tensor QualityAssessmentModule.psnr_ssim_sums_device filled.  One NCCL all-reduce
+    (skipped at world size 1), ONE device->host read; returns an srf_iqa_sums with the job-wide totals."""
+    import torch.distributed as dist
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(d_sums, op=dist.ReduceOp.SUM, group=group)
+    v = d_sums.tolist()
+    s = _native.srf_iqa_sums()
+    s.sq_err, s.ssim_sum, s.ssim_count, s.n_elems = int(v[0]), v[1], int(v[2]), int(total_elems)
+    s.bits_a, s.bits_b = (255 if v[3] > 0 else 1), (255 if v[4] > 0 else 1)
+    return s

@@ -115,6 +115,24 @@ class QualityAssessmentModule:
             run(int(sums.bits_a <= 1), int(sums.bits_b <= 1))
         return sums
 
+    def psnr_ssim_sums_device(self, img1, img2, out, data_range: float = 255.0, row_range=None):
+        """Enqueue-only form for CUDA tensors (extension): the band's additive sums {sq_err, ssim_sum, ssim_count,
+        any byte of img1 > 1, any byte of img2 > 1} are written into `out` (float64 CUDA tensor, 5 elements) on the
+        current stream, with no host synchronisation -- all-reduce `out` and read it back once
+        (see distributed.allreduce_device_sums)."""
+        va, vb = ImageView(img1, "img1"), ImageView(img2, "img2")
+        if not (va.on_device and vb.on_device) or (va.h, va.w, va.c) != (vb.h, vb.w, vb.c):
+            raise ValueError("psnr_ssim_sums_device takes two CUDA uint8 images of equal shape")
+        if out.dtype != torch.float64 or out.numel() < 5 or not out.is_cuda:
+            raise ValueError("out must be a float64 CUDA tensor with 5 elements")
+        h, w = va.h, va.w
+        r0, r1 = (0, h) if row_range is None else (int(row_range[0]), int(row_range[1]))
+        lib, ctx = _native.load(), _native.context(va.device)
+        rc = lib.srf_psnr_ssim_enqueue(ctx, va.ptr, va.pitch, vb.ptr, vb.pitch, h, w, va.c, 0, 0, float(data_range), r0, r1,
+                                       out.data_ptr(), current_stream_ptr(va.device))
+        _native.check(rc, ctx)
+        return out
+
     @staticmethod
     def finish(sums, data_range: float = 255.0) -> Tuple[float, float]:
         p, s = C.c_double(), C.c_double()

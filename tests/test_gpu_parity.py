@@ -310,3 +310,37 @@ def test_fusion_plan_reuse_and_misaligned_device_tiles(srs):
         assert got is out and np.array_equal(got.cpu().numpy(), host)
     hplan = bm.plan_fusion([srs.TileInfo(t, x, y, 0, 0) for t, (y, x) in zip(tiles, pos)], output_shape=(230, 231))
     assert np.array_equal(bm.laplacian_fusion(hplan), host)
+
+
+def test_fusion_graph_replay_and_device_sums(srs):
+    """a repeated device call on a side stream is captured into a CUDA graph and replayed; it must track the tile
+    CONTENTS (same addresses, new pixels) and agree with the host path; the enqueue-only IQA agrees with the sync one"""
+    import torch
+    rng = np.random.default_rng(43)
+    tiles, pos = _grid_case(rng, 256, 256, 2, 2, 200, 200)
+    bm = srs.BlendingModule(num_levels=5)
+    qa = srs.QualityAssessmentModule()
+    out_hw = (456, 456)
+    dev_tiles = [torch.from_numpy(t).cuda() for t in tiles]
+    plan = bm.plan_fusion([srs.TileInfo(d, x, y, 0, 0) for d, (y, x) in zip(dev_tiles, pos)], output_shape=out_hw)
+    out = torch.empty(out_hw + (3,), dtype=torch.uint8, device="cuda")
+    ctx = srs._native.context(0)
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        for rep in range(5):
+            if rep == 3:  # new pixels behind the same pointers
+                tiles = [np.ascontiguousarray(t[::-1, ::-1]) for t in tiles]
+                for d, t in zip(dev_tiles, tiles):
+                    d.copy_(torch.from_numpy(t), non_blocking=False)
+            l0 = srs._native.load().srf_launch_count(ctx)
+            bm.laplacian_fusion(plan, out=out)
+            side.synchronize()
+            assert srs._native.load().srf_launch_count(ctx) > l0
+            want = bm.laplacian_fusion([srs.TileInfo(t, x, y, 0, 0) for t, (y, x) in zip(tiles, pos)], output_shape=out_hw)
+            assert np.array_equal(out.cpu().numpy(), want), rep
+        ref = torch.from_numpy(synth(rng, *out_hw)).cuda()
+        d_sums = torch.zeros(5, dtype=torch.float64, device="cuda")
+        qa.psnr_ssim_sums_device(ref, out, d_sums, row_range=(10, 400))
+        got = srs.distributed.allreduce_device_sums(d_sums, 390 * 456 * 3)
+        s = qa.psnr_ssim_sums(ref, out, row_range=(10, 400))
+    assert (got.sq_err, got.ssim_count) == (s.sq_err, s.ssim_count) and got.ssim_sum == s.ssim_sum
