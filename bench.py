@@ -180,8 +180,9 @@ def run_b200(args, wl):
 
     H, W = wl.canvas_hw
     D = pkg.distributed
-    r0, r1 = D.band(rank, world, H)
-    e0, e1 = D.fuse_rows(rank, world, H)  # rows this rank fuses (own band + SSIM halo)
+    bands = D.balanced_bands(world, H, W, wl.positions_yx, [t.shape[:2] for t in wl.tiles])  # equal cost, not equal height
+    r0, r1 = bands[rank]
+    e0, e1 = D.widen(bands[rank], H)  # rows this rank fuses (own band + SSIM halo)
     mine = D.tiles_for_rows(wl.positions_yx, [t.shape[0] for t in wl.tiles], e0, e1)
     bm = pkg.BlendingModule(num_levels=wl.levels, device=local)
     qa = pkg.QualityAssessmentModule(device=f"cuda:{local}")

@@ -22,12 +22,36 @@ def band(rank: int, world: int, rows: int) -> Tuple[int, int]:
     return min(rank * per, rows), min((rank + 1) * per, rows)
 
 
-def fuse_rows(rank: int, world: int, rows: int) -> Tuple[int, int]:
-    """rows a rank must FUSE: its band widened by the SSIM halo, clipped to the canvas"""
-    r0, r1 = band(rank, world, rows)
+def balanced_bands(world: int, rows: int, cols: int, positions_yx, sizes_hw) -> List[Tuple[int, int]]:
+    """Cut the canvas rows into `world` contiguous bands of equal COST rather than equal height.  A canvas row costs
+    one unit of per-pixel work (assessment + canvas write) plus one unit per covering tile (gather + that tile's
+    pyramid rows); with 20-30 % tile overlap the doubly covered rows are ~60 % dearer, and equal-height bands leave
+    the ranks that own an overlap zone ~20 % slower than the rest.  0.65 : 1 is the measured ratio of the two terms
+    on B200 (profiles/README.md)."""
+    import numpy as np
+    cost = np.full(rows, 0.65)
+    for (y, x), (h, w) in zip(positions_yx, sizes_hw):
+        wfrac = max(0, min(cols, x + w) - max(0, x)) / cols
+        cost[max(0, y):min(rows, y + h)] += wfrac
+    cum = np.concatenate([[0.0], np.cumsum(cost)])
+    cuts = [0]
+    for k in range(1, world):
+        cuts.append(max(int(np.searchsorted(cum, cum[-1] * k / world)), cuts[-1]))
+    cuts.append(rows)
+    return [(min(a, rows), min(b, rows)) for a, b in zip(cuts[:-1], cuts[1:])]
+
+
+def widen(band_rows: Tuple[int, int], rows: int) -> Tuple[int, int]:
+    """rows a rank must FUSE for a band: the band plus the SSIM halo, clipped to the canvas"""
+    r0, r1 = band_rows
     if r0 >= r1:
         return r0, r0
     return max(r0 - IQA_HALO, 0), min(r1 + IQA_HALO, rows)
+
+
+def fuse_rows(rank: int, world: int, rows: int) -> Tuple[int, int]:
+    """rows a rank must FUSE: its (equal-height) band widened by the SSIM halo, clipped to the canvas"""
+    return widen(band(rank, world, rows), rows)
 
 
 def tiles_for_rows(positions_yx: Sequence[Tuple[int, int]], heights: Sequence[int], r0: int, r1: int) -> List[int]:

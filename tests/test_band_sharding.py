@@ -78,3 +78,22 @@ def test_band_partition_and_tile_selection(srs):
     sel = d.tiles_for_rows(pos, hs, *d.fuse_rows(2, 8, 11546))
     assert sel == list(range(12))                     # rows 2883..3897 touch tile rows 0 and 1 (overlap zone)
     assert d.tiles_for_rows(pos, hs, 0, 11546) == list(range(24))
+
+
+def test_balanced_bands_cover_and_balance(srs):
+    d = srs.distributed
+    pos = [(y, x) for y in (0, 3278, 6556, 9834) for x in range(0, 6 * 3278, 3278)]
+    sizes = [(4096, 4096)] * len(pos)
+    H, W = 11546, 17320
+    for world in (1, 2, 3, 4, 8):
+        bands = d.balanced_bands(world, H, W, pos, sizes)
+        assert len(bands) == world and bands[0][0] == 0 and bands[-1][1] == H
+        assert all(a[1] == b[0] for a, b in zip(bands, bands[1:]))
+        cov = np.full(H, 0.65)
+        for (y, x), (h, w) in zip(pos, sizes):
+            cov[y:min(H, y + h)] += max(0, min(W, x + w) - x) / W
+        costs = [cov[a:b].sum() for a, b in bands]
+        assert max(costs) <= 1.02 * (sum(costs) / world)          # balanced to 2 %
+        equal = [cov[slice(*d.band(r, world, H))].sum() for r in range(world)]
+        assert max(costs) <= max(equal) + 1e-9                     # never worse than equal-height bands
+    assert d.balanced_bands(4, 3, 10, [(0, 0)], [(3, 10)])[-1][1] == 3  # more ranks than rows: empty bands allowed
