@@ -149,21 +149,24 @@ typedef struct srf_iqa_sums {
 /* replaces calculate_psnr + calculate_ssim(multiscale=True) of QualityAssessmentModule
  * (quality_assessment_module.py:277-320, 322-376) in ONE pass over the pair: integer sum of squared
  * differences over all channels, cv2-exact RGB->gray, 11-tap sigma=1.5 Gaussian SSIM (C1 = (0.01 data_range)^2,
- * C2 = (0.03 data_range)^2, population covariance) summed over the interior.  This call SYNCHRONISES `stream`
+ * C2 = (0.03 data_range)^2, population covariance) summed over the interior.
+ * window: 0 = that 11x11 Gaussian window (calculate_ssim(multiscale=True), the pipeline's 'ms_ssim');
+ *         1 = scikit-image's default 7x7 uniform window with sample covariance, interior = 3 px in
+ *             (calculate_ssim(multiscale=False), quality_assessment_module.py:378-384, the 'ssim' key).  This call SYNCHRONISES `stream`
  * before returning (it hands scalars back to the host).  scale_a / scale_b: multiply that image by 255 first
  * (the preprocess rule above), 0 or 1.  a and b are (h, w, C) views of equal size. */
 int srf_psnr_ssim(srf_ctx *ctx, const uint8_t *d_a, size_t pitch_a, const uint8_t *d_b, size_t pitch_b, int h,
-                  int w, int channels, int scale_a, int scale_b, double data_range, int row_begin, int row_end,
-                  srf_iqa_sums *h_out, void *stream);
+                  int w, int channels, int scale_a, int scale_b, double data_range, int window, int row_begin,
+                  int row_end, srf_iqa_sums *h_out, void *stream);
 int srf_psnr_ssim_host(srf_ctx *ctx, const uint8_t *h_a, size_t pitch_a, const uint8_t *h_b, size_t pitch_b,
-                       int h, int w, int channels, int scale_a, int scale_b, double data_range, int row_begin,
-                       int row_end, srf_iqa_sums *h_out);
+                       int h, int w, int channels, int scale_a, int scale_b, double data_range, int window,
+                       int row_begin, int row_end, srf_iqa_sums *h_out);
 /* enqueue-only variant for multi-GPU use: no synchronisation, the band's sums are written to DEVICE memory as five
  * doubles {sq_err, ssim_sum, ssim_count, any byte of a > 1, any byte of b > 1} -- additive, so the caller can
  * ncclAllReduce(sum) them in place and read the totals back with one copy */
 int srf_psnr_ssim_enqueue(srf_ctx *ctx, const uint8_t *d_a, size_t pitch_a, const uint8_t *d_b, size_t pitch_b, int h,
-                          int w, int channels, int scale_a, int scale_b, double data_range, int row_begin, int row_end,
-                          double *d_sums5, void *stream);
+                          int w, int channels, int scale_a, int scale_b, double data_range, int window, int row_begin,
+                          int row_end, double *d_sums5, void *stream);
 /* stage 3 + stage 4 of the reference pipeline in one call (main.py:347 laplacian_fusion, :369
  * evaluate_full_reference): host tiles -> fused canvas (host) + PSNR/SSIM sums of the canvas against a host
  * comparison image of the same size.  The canvas stays on the device between the two stages; uploads, kernels and

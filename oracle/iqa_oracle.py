@@ -90,3 +90,24 @@ def ssim(a, b, data_range=255.0) -> float:
     if min(a.shape) < 2 * RADIUS + 1:
         raise ValueError("image smaller than the 11x11 window")
     return float(ssim_map_interior(a, b, data_range).mean(dtype=np.float64))
+
+
+def ssim_uniform(a, b, data_range=255.0) -> float:
+    """scikit-image's DEFAULT structural_similarity (what calculate_ssim(multiscale=False) calls,
+    quality_assessment_module.py:378-384): 7x7 uniform window (scipy.ndimage.uniform_filter), SAMPLE covariance
+    (cov_norm = 49/48), mean over the map cropped by 3.  Parity for this key is pinned to the published algorithm and
+    to SciPy only -- the reference has no fallback of its own for it."""
+    a, b = common_crop(preprocess(a), preprocess(b))
+    if a.ndim == 3:
+        a, b = rgb_to_gray(a), rgb_to_gray(b)
+    if min(a.shape) < 7:
+        raise ValueError("image smaller than the 7x7 window")
+    x, y = a.astype(np.float64), b.astype(np.float64)
+    t = np.full(7, 1.0 / 7.0)
+    ux, uy = _valid_filter(x, t), _valid_filter(y, t)
+    uxx, uyy, uxy = _valid_filter(x * x, t), _valid_filter(y * y, t), _valid_filter(x * y, t)
+    cn = 49.0 / 48.0
+    vx, vy, vxy = cn * (uxx - ux * ux), cn * (uyy - uy * uy), cn * (uxy - ux * uy)
+    c1, c2 = (0.01 * data_range) ** 2, (0.03 * data_range) ** 2
+    s = ((2 * ux * uy + c1) * (2 * vxy + c2)) / ((ux ** 2 + uy ** 2 + c1) * (vx + vy + c2))
+    return float(s.mean(dtype=np.float64))

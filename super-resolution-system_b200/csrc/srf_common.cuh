@@ -203,5 +203,5 @@ void srf_fuse_input_extent(const srf_tile &t, int levels, int out_h, int out_w, 
 // enqueue only: the sums land in slot `slot` (0..63) of ctx->pinned once the stream is synchronised; srf_iqa_collect
 // converts them
 int srf_iqa_enqueue(srf_ctx *ctx, const uint8_t *a, size_t pa, const uint8_t *b, size_t pb, int h, int w, int C, int scale_a, int scale_b,
-                    double data_range, int row_begin, int row_end, cudaStream_t st, int slot, double *d_sums = nullptr);
+                    double data_range, int row_begin, int row_end, cudaStream_t st, int slot, double *d_sums = nullptr, int window = 0);
 void srf_iqa_collect(srf_ctx *ctx, int w, int C, int row_begin, int row_end, srf_iqa_sums *out, int slot);

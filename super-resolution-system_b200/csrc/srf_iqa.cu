@@ -16,8 +16,7 @@ namespace {
 
 constexpr int IQ_THREADS = 128;
 constexpr int IQ_RB = 64;    // S-map rows per CTA
-constexpr int IQ_R = 5;      // filter radius
-constexpr int IQ_TAPS = 11;
+constexpr int IQ_R = 5;      // staging halo = radius of the widest window (11-tap Gaussian)
 constexpr int IQ_SROW = IQ_THREADS + 2 * IQ_R + 2; // staged gray columns (+2 keeps rows 16-byte multiples)
 constexpr int IQ_RAW = 448;                         // staged raw bytes per row and image: 15 + 138 * 3 rounded up to 16
 
@@ -28,6 +27,15 @@ constexpr int IQ_RAW = 448;                         // staged raw bytes per row 
 #define IQ_T3 1.093606895e-01f
 #define IQ_T4 2.130055377e-01f
 #define IQ_T5 2.660117249e-01f
+
+// window taps: R = 5 -> exp(-k^2 / (2 * 1.5^2)) normalised (the literals above); R = 3 -> uniform 1/7
+template <int R>
+__device__ __forceinline__ constexpr float iq_tap(int k)
+{
+    if (R == 3) return 1.f / 7.f;
+    const int d = k < 5 ? 5 - k : k - 5;
+    return d == 0 ? IQ_T5 : d == 1 ? IQ_T4 : d == 2 ? IQ_T3 : d == 3 ? IQ_T2 : d == 4 ? IQ_T1 : IQ_T0;
+}
 
 struct IqaPartial {
     double ssim;
@@ -42,6 +50,7 @@ struct IqaParams {
     int h, w;
     int scale_a, scale_b;
     float c1, c2;
+    float cov_norm; // 1 (population covariance, Gaussian window) or 49/48 (sample covariance, uniform 7x7 window)
     int row_begin, row_end;
     IqaPartial *partials;
 };
@@ -79,7 +88,7 @@ __device__ __forceinline__ int gray_of(const uint8_t *p, int scale, int &bits, i
 //   H(r)   horizontal 11-tap of {a, b, a^2+b^2, ab} into an 11-deep register ring, vertical 11-tap, SSIM, accumulate
 // ANYSCALE: an image is rescaled by 255 first (the reference's max() <= 1 rule, P.scale_a / P.scale_b) -- a separate
 // instantiation so the common case carries no dead arithmetic.
-template <int C, bool ANYSCALE>
+template <int C, bool ANYSCALE, int R>
 __global__ void __launch_bounds__(IQ_THREADS, 5) k_psnr_ssim(IqaParams P)
 {
     __shared__ __align__(16) uint8_t s_raw[4][2][IQ_RAW];
@@ -90,6 +99,7 @@ __global__ void __launch_bounds__(IQ_THREADS, 5) k_psnr_ssim(IqaParams P)
     __shared__ unsigned long long s_cnt[IQ_THREADS / 32];
     __shared__ int s_mx[2][IQ_THREADS / 32];
 
+    constexpr int TAPS = 2 * R + 1;
     const int t = threadIdx.x;
     const int cx0 = blockIdx.x * IQ_THREADS;
     const int ry0 = P.row_begin + blockIdx.y * IQ_RB;
@@ -100,7 +110,7 @@ __global__ void __launch_bounds__(IQ_THREADS, 5) k_psnr_ssim(IqaParams P)
     const bool has2 = t < 2 * IQ_R;
     const bool own1 = col1 >= cx0 && col1 < w; // owned = inside this CTA's strip (for the PSNR sum)
     const bool own2 = has2 && col2 < cx0 + IQ_THREADS && col2 < w;
-    const int r_first = ry0 - IQ_R, r_last = ry1 + IQ_R; // input rows [r_first, r_last)
+    const int r_first = ry0 - R, r_last = ry1 + R; // input rows [r_first, r_last)
     const long long col_off = (long long)(cx0 - IQ_R) * C;
 
     // ---- loader role: threads 0..27 -> image a, 28..55 -> image b, one 16-byte chunk each per row ----
@@ -181,16 +191,16 @@ __global__ void __launch_bounds__(IQ_THREADS, 5) k_psnr_ssim(IqaParams P)
         }
     };
 
-    float ring[4][IQ_TAPS];
+    float ring[4][TAPS];
 #pragma unroll
     for (int s = 0; s < 4; ++s)
 #pragma unroll
-        for (int k = 0; k < IQ_TAPS; ++k) ring[s][k] = 0.f;
+        for (int k = 0; k < TAPS; ++k) ring[s][k] = 0.f;
 
     float ssum = 0.f;
     unsigned int scount = 0;
     const int col = cx0 + t; // this thread's S-map column
-    const bool col_interior = col >= IQ_R && col < w - IQ_R;
+    const bool col_interior = col >= R && col < w - R;
     const float C1 = P.c1, C2 = P.c2;
 
     // prologue: rows r_first .. r_first+3 in flight; gray(r_first) ready and raw(r_first+1) published
@@ -203,9 +213,9 @@ __global__ void __launch_bounds__(IQ_THREADS, 5) k_psnr_ssim(IqaParams P)
     G(r_first);
     __syncthreads();
 
-    for (int base = r_first; base < r_last; base += IQ_TAPS) {
+    for (int base = r_first; base < r_last; base += TAPS) {
 #pragma unroll
-        for (int ph = 0; ph < IQ_TAPS; ++ph) {
+        for (int ph = 0; ph < TAPS; ++ph) {
             const int r_in = base + ph;
             if (r_in >= r_last) break;
             const int buf = r_in & 1;
@@ -214,52 +224,40 @@ __global__ void __launch_bounds__(IQ_THREADS, 5) k_psnr_ssim(IqaParams P)
             // H(r): horizontal pass on gray row r_in -- four FMA chains with literal taps, products formed once per tap
             {
                 float ha = 0.f, hb = 0.f, hs = 0.f, hp = 0.f;
-                const float *pa = &s_a[buf][t], *pb = &s_b[buf][t];
-#define IQ_HTAP(K, T)                          \
-    {                                          \
-        const float a = pa[K], b = pb[K];      \
-        ha = fmaf(a, T, ha);                   \
-        hb = fmaf(b, T, hb);                   \
-        hs = fmaf(fmaf(a, a, b * b), T, hs);   \
-        hp = fmaf(a * b, T, hp);               \
-    }
-                IQ_HTAP(0, IQ_T0) IQ_HTAP(1, IQ_T1) IQ_HTAP(2, IQ_T2) IQ_HTAP(3, IQ_T3) IQ_HTAP(4, IQ_T4) IQ_HTAP(5, IQ_T5)
-                IQ_HTAP(6, IQ_T4) IQ_HTAP(7, IQ_T3) IQ_HTAP(8, IQ_T2) IQ_HTAP(9, IQ_T1) IQ_HTAP(10, IQ_T0)
-#undef IQ_HTAP
+                const float *pa = &s_a[buf][t + (IQ_R - R)], *pb = &s_b[buf][t + (IQ_R - R)];
+#pragma unroll
+                for (int k = 0; k < TAPS; ++k) {
+                    const float a = pa[k], b = pb[k];
+                    ha = fmaf(a, iq_tap<R>(k), ha);
+                    hb = fmaf(b, iq_tap<R>(k), hb);
+                    hs = fmaf(fmaf(a, a, b * b), iq_tap<R>(k), hs);
+                    hp = fmaf(a * b, iq_tap<R>(k), hp);
+                }
                 ring[0][ph] = ha;
                 ring[1][ph] = hb;
                 ring[2][ph] = hs;
                 ring[3][ph] = hp;
             }
 
-            // vertical pass: output row r = r_in - 5 uses input rows r_in-10 .. r_in = ring slots (ph+1+k) % 11
-            const int r = r_in - IQ_R;
+            // vertical pass: output row r = r_in - R uses input rows r_in-2R .. r_in = ring slots (ph+1+k) % TAPS
+            const int r = r_in - R;
             if (r >= ry0) {
                 float f[4];
 #pragma unroll
                 for (int s = 0; s < 4; ++s) {
                     float v = 0.f;
-                    v = fmaf(ring[s][(ph + 1) % IQ_TAPS], IQ_T0, v);
-                    v = fmaf(ring[s][(ph + 2) % IQ_TAPS], IQ_T1, v);
-                    v = fmaf(ring[s][(ph + 3) % IQ_TAPS], IQ_T2, v);
-                    v = fmaf(ring[s][(ph + 4) % IQ_TAPS], IQ_T3, v);
-                    v = fmaf(ring[s][(ph + 5) % IQ_TAPS], IQ_T4, v);
-                    v = fmaf(ring[s][(ph + 6) % IQ_TAPS], IQ_T5, v);
-                    v = fmaf(ring[s][(ph + 7) % IQ_TAPS], IQ_T4, v);
-                    v = fmaf(ring[s][(ph + 8) % IQ_TAPS], IQ_T3, v);
-                    v = fmaf(ring[s][(ph + 9) % IQ_TAPS], IQ_T2, v);
-                    v = fmaf(ring[s][(ph + 10) % IQ_TAPS], IQ_T1, v);
-                    v = fmaf(ring[s][(ph + 11) % IQ_TAPS], IQ_T0, v);
+#pragma unroll
+                    for (int k = 0; k < TAPS; ++k) v = fmaf(ring[s][(ph + 1 + k) % TAPS], iq_tap<R>(k), v);
                     f[s] = v;
                 }
                 const float ua = f[0], ub = f[1];
                 const float ux = ua + 128.f, uy = ub + 128.f;
-                const float vsum = f[2] - fmaf(ua, ua, ub * ub); // vx + vy (shift invariant)
-                const float vxy = f[3] - ua * ub;
+                const float vsum = P.cov_norm * (f[2] - fmaf(ua, ua, ub * ub)); // vx + vy (shift invariant)
+                const float vxy = P.cov_norm * (f[3] - ua * ub);
                 const float A1 = fmaf(2.f * ux, uy, C1), A2 = fmaf(2.f, vxy, C2);
                 const float B1 = fmaf(ux, ux, fmaf(uy, uy, C1)), B2 = vsum + C2;
                 const float S = __fdividef(A1 * A2, B1 * B2);
-                if (col_interior && r >= IQ_R && r < h - IQ_R) {
+                if (col_interior && r >= R && r < h - R) {
                     ssum += S;
                     scount++;
                 }
@@ -356,7 +354,7 @@ __global__ void __launch_bounds__(256) k_iqa_reduce(const IqaPartial *__restrict
 } // namespace
 
 int srf_iqa_enqueue(srf_ctx *ctx, const uint8_t *a, size_t pa, const uint8_t *b, size_t pb, int h, int w, int C, int scale_a, int scale_b,
-                    double data_range, int row_begin, int row_end, cudaStream_t st, int slot, double *d_sums)
+                    double data_range, int row_begin, int row_end, cudaStream_t st, int slot, double *d_sums, int window)
 {
     int rc;
     const int gx = srf_ceil_div(w, IQ_THREADS), gy = srf_ceil_div(row_end - row_begin, IQ_RB);
@@ -376,22 +374,23 @@ int srf_iqa_enqueue(srf_ctx *ctx, const uint8_t *a, size_t pa, const uint8_t *b,
     P.scale_b = scale_b;
     P.c1 = (float)((0.01 * data_range) * (0.01 * data_range));
     P.c2 = (float)((0.03 * data_range) * (0.03 * data_range));
+    P.cov_norm = window ? (float)(49.0 / 48.0) : 1.f;
     P.row_begin = row_begin;
     P.row_end = row_end;
     P.partials = parts;
     if (nparts > 0) {
         dim3 grid(gx, gy);
         srf_launch_scope scope(ctx, "psnr_ssim", 2.0 * (double)(row_end - row_begin) * w * C, st);
-        if (scale_a || scale_b) { // the rare max() <= 1 rescale: generic instantiation
-            if (C == 3)
-                k_psnr_ssim<3, true><<<grid, IQ_THREADS, 0, st>>>(P);
-            else
-                k_psnr_ssim<1, true><<<grid, IQ_THREADS, 0, st>>>(P);
-        } else if (C == 3) {
-            k_psnr_ssim<3, false><<<grid, IQ_THREADS, 0, st>>>(P);
+        const bool any = scale_a || scale_b; // the rare max() <= 1 rescale: generic instantiation
+#define IQ_LAUNCH(CC, ANY, RR) k_psnr_ssim<CC, ANY, RR><<<grid, IQ_THREADS, 0, st>>>(P)
+        if (window == 0) {
+            if (C == 3) { if (any) IQ_LAUNCH(3, true, 5); else IQ_LAUNCH(3, false, 5); }
+            else        { if (any) IQ_LAUNCH(1, true, 5); else IQ_LAUNCH(1, false, 5); }
         } else {
-            k_psnr_ssim<1, false><<<grid, IQ_THREADS, 0, st>>>(P);
+            if (C == 3) { if (any) IQ_LAUNCH(3, true, 3); else IQ_LAUNCH(3, false, 3); }
+            else        { if (any) IQ_LAUNCH(1, true, 3); else IQ_LAUNCH(1, false, 3); }
         }
+#undef IQ_LAUNCH
     }
     {
         srf_launch_scope scope(ctx, "iqa_reduce", 0.0, st);
@@ -415,10 +414,10 @@ void srf_iqa_collect(srf_ctx *ctx, int w, int C, int row_begin, int row_end, srf
 }
 
 static int iqa_device(srf_ctx *ctx, const uint8_t *a, size_t pa, const uint8_t *b, size_t pb, int h, int w, int C, int scale_a, int scale_b,
-                      double data_range, int row_begin, int row_end, srf_iqa_sums *out, cudaStream_t st, bool record_events)
+                      double data_range, int row_begin, int row_end, srf_iqa_sums *out, cudaStream_t st, bool record_events, int window)
 {
     if (record_events) SRF_CHECK_CUDA(ctx, cudaEventRecord(ctx->ev0, st));
-    int rc = srf_iqa_enqueue(ctx, a, pa, b, pb, h, w, C, scale_a, scale_b, data_range, row_begin, row_end, st, 0, nullptr);
+    int rc = srf_iqa_enqueue(ctx, a, pa, b, pb, h, w, C, scale_a, scale_b, data_range, row_begin, row_end, st, 0, nullptr, window);
     if (rc) return rc;
     if (record_events) {
         SRF_CHECK_CUDA(ctx, cudaEventRecord(ctx->ev1, st));
@@ -430,31 +429,32 @@ static int iqa_device(srf_ctx *ctx, const uint8_t *a, size_t pa, const uint8_t *
 }
 
 static int check_iqa_args(srf_ctx *ctx, const void *a, size_t pa, const void *b, size_t pb, int h, int w, int C, int row_begin, int row_end,
-                          const void *out)
+                          const void *out, int window)
 {
     SRF_REQUIRE(ctx, a && b && out, "psnr_ssim: null pointer");
     SRF_REQUIRE(ctx, C == 1 || C == 3, "psnr_ssim: channels must be 1 or 3 (got %d)", C);
     SRF_REQUIRE(ctx, h >= 1 && w >= 1, "psnr_ssim: empty image");
     SRF_REQUIRE(ctx, pa >= (size_t)w * C && pb >= (size_t)w * C, "psnr_ssim: pitch < row bytes");
+    SRF_REQUIRE(ctx, window == 0 || window == 1, "psnr_ssim: window must be 0 (11x11 Gaussian) or 1 (7x7 uniform), got %d", window);
     SRF_REQUIRE(ctx, row_begin >= 0 && row_begin <= row_end && row_end <= h, "psnr_ssim: bad row band [%d,%d) of %d", row_begin, row_end, h);
     return SRF_OK;
 }
 
 extern "C" int srf_psnr_ssim(srf_ctx *ctx, const uint8_t *d_a, size_t pitch_a, const uint8_t *d_b, size_t pitch_b, int h, int w,
-                             int channels, int scale_a, int scale_b, double data_range, int row_begin, int row_end, srf_iqa_sums *h_out, void *stream)
+                             int channels, int scale_a, int scale_b, double data_range, int window, int row_begin, int row_end, srf_iqa_sums *h_out, void *stream)
 {
     if (!ctx) return SRF_ERR_ARG;
-    int rc = check_iqa_args(ctx, d_a, pitch_a, d_b, pitch_b, h, w, channels, row_begin, row_end, h_out);
+    int rc = check_iqa_args(ctx, d_a, pitch_a, d_b, pitch_b, h, w, channels, row_begin, row_end, h_out, window);
     if (rc) return rc;
     SRF_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
-    return iqa_device(ctx, d_a, pitch_a, d_b, pitch_b, h, w, channels, scale_a, scale_b, data_range, row_begin, row_end, h_out, (cudaStream_t)stream, true);
+    return iqa_device(ctx, d_a, pitch_a, d_b, pitch_b, h, w, channels, scale_a, scale_b, data_range, row_begin, row_end, h_out, (cudaStream_t)stream, true, window);
 }
 
 extern "C" int srf_psnr_ssim_host(srf_ctx *ctx, const uint8_t *h_a, size_t pitch_a, const uint8_t *h_b, size_t pitch_b, int h, int w,
-                                  int channels, int scale_a, int scale_b, double data_range, int row_begin, int row_end, srf_iqa_sums *h_out)
+                                  int channels, int scale_a, int scale_b, double data_range, int window, int row_begin, int row_end, srf_iqa_sums *h_out)
 {
     if (!ctx) return SRF_ERR_ARG;
-    int rc = check_iqa_args(ctx, h_a, pitch_a, h_b, pitch_b, h, w, channels, row_begin, row_end, h_out);
+    int rc = check_iqa_args(ctx, h_a, pitch_a, h_b, pitch_b, h, w, channels, row_begin, row_end, h_out, window);
     if (rc) return rc;
     SRF_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
     // stage only the rows the band reads: [row_begin - 5, row_end + 5) clipped
@@ -468,17 +468,17 @@ extern "C" int srf_psnr_ssim_host(srf_ctx *ctx, const uint8_t *h_a, size_t pitch
         SRF_CHECK_CUDA(ctx, cudaMemcpy2DAsync(da, dp, h_a + (size_t)r0 * pitch_a, pitch_a, (size_t)w * channels, r1 - r0, cudaMemcpyHostToDevice, st));
         SRF_CHECK_CUDA(ctx, cudaMemcpy2DAsync(db, dp, h_b + (size_t)r0 * pitch_b, pitch_b, (size_t)w * channels, r1 - r0, cudaMemcpyHostToDevice, st));
     }
-    return iqa_device(ctx, da - (size_t)r0 * dp, dp, db - (size_t)r0 * dp, dp, h, w, channels, scale_a, scale_b, data_range, row_begin, row_end, h_out, st, true);
+    return iqa_device(ctx, da - (size_t)r0 * dp, dp, db - (size_t)r0 * dp, dp, h, w, channels, scale_a, scale_b, data_range, row_begin, row_end, h_out, st, true, window);
 }
 
 extern "C" int srf_psnr_ssim_enqueue(srf_ctx *ctx, const uint8_t *d_a, size_t pitch_a, const uint8_t *d_b, size_t pitch_b, int h, int w,
-                                     int channels, int scale_a, int scale_b, double data_range, int row_begin, int row_end, double *d_sums5,
-                                     void *stream)
+                                     int channels, int scale_a, int scale_b, double data_range, int window, int row_begin, int row_end,
+                                     double *d_sums5, void *stream)
 {
     if (!ctx) return SRF_ERR_ARG;
-    int rc = check_iqa_args(ctx, d_a, pitch_a, d_b, pitch_b, h, w, channels, row_begin, row_end, d_sums5);
+    int rc = check_iqa_args(ctx, d_a, pitch_a, d_b, pitch_b, h, w, channels, row_begin, row_end, d_sums5, window);
     if (rc) return rc;
     SRF_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
     return srf_iqa_enqueue(ctx, d_a, pitch_a, d_b, pitch_b, h, w, channels, scale_a, scale_b, data_range, row_begin, row_end,
-                           (cudaStream_t)stream, -1, d_sums5);
+                           (cudaStream_t)stream, -1, d_sums5, window);
 }

@@ -4,8 +4,9 @@ Mirrors /root/reference/quality_assessment_module.py: AssessmentLevel 35-41, Qua
 ScaleConfig 78-86, QualityAssessmentModule.__init__ 107-133, _preprocess_image 169-195, calculate_psnr 277-320,
 calculate_ssim 322-389, evaluate_full_reference 467-516, _assess_* 557-588, _calculate_overall_score 590-609,
 batch_evaluate 1350-1371.  The arithmetic (scikit-image's peak_signal_noise_ratio / structural_similarity) runs in
-csrc/srf_iqa.cu.  Out of scope: LPIPS, NIQE, BRISQUE, commercial metrics, reports; the
-7x7 uniform-window SSIM and the bicubic down-sample comparison are the "next" row N1 and raise until built.
+csrc/srf_iqa.cu (both SSIM windows: 11x11 Gaussian and scikit-image's default 7x7 uniform).  Out of scope (SURVEY.md
+section 8): LPIPS, NIQE, BRISQUE, commercial metrics, reports; the bicubic down-sample comparison keys are the rest
+of the "next" row N1.
 """
 from __future__ import annotations
 
@@ -87,8 +88,10 @@ class QualityAssessmentModule:
         return a, b
 
     # ------------------------------------------------------------------ the one-pass kernel
-    def psnr_ssim_sums(self, img1, img2, data_range: float = 255.0, row_range: Optional[Tuple[int, int]] = None):
-        """additive partial sums (srf_iqa_sums) of the pair over a row band -- what ranks all-reduce"""
+    def psnr_ssim_sums(self, img1, img2, data_range: float = 255.0, row_range: Optional[Tuple[int, int]] = None,
+                       window: int = 0):
+        """additive partial sums (srf_iqa_sums) of the pair over a row band -- what ranks all-reduce.
+        window: 0 = 11x11 Gaussian (multiscale=True), 1 = 7x7 uniform with sample covariance (multiscale=False)"""
         a, b = self._crop_common(self._preprocess_image(img1), self._preprocess_image(img2))
         if len(a.shape) != len(b.shape) or (len(a.shape) == 3 and a.shape[2] != b.shape[2]):
             raise ValueError("image pair disagrees on channels")
@@ -103,10 +106,10 @@ class QualityAssessmentModule:
         def run(sa, sb):
             if va.on_device:
                 rc = lib.srf_psnr_ssim(ctx, va.ptr, va.pitch, vb.ptr, vb.pitch, h, w, va.c, sa, sb, float(data_range),
-                                       r0, r1, C.byref(sums), current_stream_ptr(va.device))
+                                       int(window), r0, r1, C.byref(sums), current_stream_ptr(va.device))
             else:
                 rc = lib.srf_psnr_ssim_host(ctx, va.ptr, va.pitch, vb.ptr, vb.pitch, h, w, va.c, sa, sb,
-                                            float(data_range), r0, r1, C.byref(sums))
+                                            float(data_range), int(window), r0, r1, C.byref(sums))
             _native.check(rc, ctx)
 
         run(0, 0)
@@ -128,7 +131,7 @@ class QualityAssessmentModule:
         h, w = va.h, va.w
         r0, r1 = (0, h) if row_range is None else (int(row_range[0]), int(row_range[1]))
         lib, ctx = _native.load(), _native.context(va.device)
-        rc = lib.srf_psnr_ssim_enqueue(ctx, va.ptr, va.pitch, vb.ptr, vb.pitch, h, w, va.c, 0, 0, float(data_range), r0, r1,
+        rc = lib.srf_psnr_ssim_enqueue(ctx, va.ptr, va.pitch, vb.ptr, vb.pitch, h, w, va.c, 0, 0, float(data_range), 0, r0, r1,
                                        out.data_ptr(), current_stream_ptr(va.device))
         _native.check(rc, ctx)
         return out
@@ -144,12 +147,11 @@ class QualityAssessmentModule:
         return float(self.finish(self.psnr_ssim_sums(img1, img2, data_range), data_range)[0])
 
     def calculate_ssim(self, img1, img2, multiscale: bool = True, data_range: float = 255.0) -> float:
-        if not multiscale:
-            raise NotImplementedError("7x7 uniform-window SSIM (multiscale=False) is row N1 of SURVEY.md section 8(f); "
-                                      "the B200 path provides the 11x11 Gaussian SSIM (multiscale=True)")
-        sums = self.psnr_ssim_sums(img1, img2, data_range)
+        # multiscale=True: 11x11 Gaussian window (the reference's "ms_ssim" is single-scale, q.a.m:366-376);
+        # multiscale=False: scikit-image's default 7x7 uniform window with sample covariance (q.a.m:378-384)
+        sums = self.psnr_ssim_sums(img1, img2, data_range, window=0 if multiscale else 1)
         if sums.ssim_count <= 0:
-            raise ValueError("image smaller than the 11x11 SSIM window")
+            raise ValueError("image smaller than the SSIM window")
         return float(self.finish(sums, data_range)[1])
 
     def calculate_psnr_ssim(self, img1, img2, data_range: float = 255.0) -> Tuple[float, float]:
@@ -187,11 +189,13 @@ class QualityAssessmentModule:
         return float(np.mean(scores)) if scores else 0.0
 
     def evaluate_full_reference(self, original, upscaled, scale_factor: int = 4) -> Dict[str, float]:
-        """psnr, psnr_level, ms_ssim (= single-scale 11x11 Gaussian SSIM, the reference's naming), ssim_level,
-        overall_score.  The reference's 'ssim' (7x7 uniform) and six down-sample keys are row N1, not produced yet;
-        LPIPS keys are omitted as in the reference when its models are unavailable."""
+        """psnr, psnr_level, ssim (7x7 uniform window), ms_ssim (= single-scale 11x11 Gaussian SSIM, the reference's
+        naming), ssim_level, overall_score.  The six bicubic down-sample comparison keys (q.a.m:518-555) are row N1
+        of SURVEY.md section 8(f), not produced yet; LPIPS keys are omitted as in the reference when its models are
+        unavailable."""
         psnr, ssim = self.calculate_psnr_ssim(original, upscaled)
-        metrics = {"psnr": float(psnr), "ms_ssim": float(ssim)}
+        metrics = {"psnr": float(psnr), "ssim": self.calculate_ssim(original, upscaled, multiscale=False),
+                   "ms_ssim": float(ssim)}
         metrics["psnr_level"] = self._assess_psnr(metrics["psnr"])
         metrics["ssim_level"] = self._assess_ssim(metrics["ms_ssim"])
         metrics["overall_score"] = self._calculate_overall_score(metrics)

@@ -256,7 +256,8 @@ def test_iqa_device_path_and_evaluate(srs, oracle):
     dev = qa.calculate_psnr_ssim(torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda())
     assert host == dev
     rep = qa.evaluate_full_reference(a, b)
-    assert set(rep) >= {"psnr", "psnr_level", "ms_ssim", "ssim_level", "overall_score"}
+    assert set(rep) >= {"psnr", "psnr_level", "ssim", "ms_ssim", "ssim_level", "overall_score"}
+    assert rep["ssim"] == pytest.approx(oracle.iqa_oracle.ssim_uniform(a, b), rel=REL)
     assert rep["overall_score"] == pytest.approx(np.mean([min(100, rep["psnr"]), rep["ms_ssim"] * 100]))
     assert len(qa.batch_evaluate([(a, b), (b, a)])) == 2
 
@@ -344,3 +345,17 @@ def test_fusion_graph_replay_and_device_sums(srs):
         got = srs.distributed.allreduce_device_sums(d_sums, 390 * 456 * 3)
         s = qa.psnr_ssim_sums(ref, out, row_range=(10, 400))
     assert (got.sq_err, got.ssim_count) == (s.sq_err, s.ssim_count) and got.ssim_sum == s.ssim_sum
+
+
+@pytest.mark.parametrize("shape", [(7, 7, 3), (9, 300, 3), (257, 129, 3), (480, 640)])
+def test_uniform_window_ssim_vs_oracle(srs, oracle, shape):
+    """calculate_ssim(multiscale=False): scikit-image's default 7x7 uniform window, sample covariance"""
+    rng = np.random.default_rng(1000 + sum(shape))
+    a = synth(rng, shape[0], shape[1], shape[2] if len(shape) == 3 else 1)
+    b = np.clip(a.astype(np.int16) + rng.integers(-12, 13, a.shape), 0, 255).astype(np.uint8)
+    qa = srs.QualityAssessmentModule()
+    assert qa.calculate_ssim(a, b, multiscale=False) == pytest.approx(oracle.iqa_oracle.ssim_uniform(a, b), rel=REL)
+    s = qa.psnr_ssim_sums(a, b, window=1)
+    assert s.ssim_count == (shape[0] - 6) * (shape[1] - 6) and s.sq_err == oracle.iqa_oracle.sq_err_sum(a, b)
+    with pytest.raises(ValueError):
+        qa.calculate_ssim(np.zeros((6, 40, 3), np.uint8), np.zeros((6, 40, 3), np.uint8), multiscale=False)

@@ -126,3 +126,22 @@ def test_reference_port_equals_oracle(golden, oracle):
             assert np.array_equal(oracle.reference_port.laplacian_fuse(tiles, pos, out_hw, levels, kind, threads), want)
     a, b = golden["iqa_a"], golden["iqa_b"]
     assert oracle.reference_port.ssim(a, b) == pytest.approx(oracle.iqa_oracle.ssim(a, b), rel=1e-12)
+
+
+def test_uniform_ssim_oracle_equals_scipy_restatement(oracle):
+    ndimage = pytest.importorskip("scipy.ndimage")
+    io = oracle.iqa_oracle
+    rng = np.random.default_rng(4)
+    a = synth(rng, 70, 95)
+    b = np.clip(a.astype(np.int16) + rng.integers(-9, 10, a.shape), 0, 255).astype(np.uint8)
+    x, y = io.rgb_to_gray(a).astype(np.float64), io.rgb_to_gray(b).astype(np.float64)
+
+    def f(z):
+        return ndimage.uniform_filter(z, size=7, mode="reflect")
+
+    ux, uy, uxx, uyy, uxy = f(x), f(y), f(x * x), f(y * y), f(x * y)
+    cn = 49 / 48
+    vx, vy, vxy = cn * (uxx - ux * ux), cn * (uyy - uy * uy), cn * (uxy - ux * uy)
+    c1, c2 = 6.5025, 58.5225
+    s = ((2 * ux * uy + c1) * (2 * vxy + c2)) / ((ux ** 2 + uy ** 2 + c1) * (vx + vy + c2))
+    assert io.ssim_uniform(a, b) == pytest.approx(s[3:-3, 3:-3].mean(dtype=np.float64), rel=1e-12)
