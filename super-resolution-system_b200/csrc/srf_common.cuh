@@ -172,6 +172,16 @@ __device__ __forceinline__ float up_h_sample(int tx, int w, At at)
     if (i == w - 1) return up_even_right(at(i - 1), p);
     return up_even(at(i - 1), p, at(i + 1));
 }
+
+// ---- cp.async (LDGSTS) helpers: 16-byte global -> shared copies that need no registers across the latency ------
+__device__ __forceinline__ void cp_async_16(void *smem_dst, const void *gsrc)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 #endif
 
 // number of output columns (pixels) of a pyrDown row that OpenCV's 4-lane SIMD body covers: columns

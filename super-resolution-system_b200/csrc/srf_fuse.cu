@@ -469,6 +469,249 @@ __global__ void __launch_bounds__(kThreads) k_up_level(const TileDev *__restrict
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// k_down_f32s: the streaming form of k_down_f32 for image planes (and W_l, l >= 1).  One CTA = 128 output columns x
+// 32 output rows of one plane, 128 threads: thread x owns output column x and streams DOWN the input rows.  Input
+// rows arrive 8 at a time through cp.async into a double-buffered smem ring; the horizontal 5-tap reads 5 adjacent
+// floats (two LDS.64 + one LDS.32, conflict free), the five most recent horizontal sums live in a register shift
+// ring, every second row emits one output row (128-byte coalesced stores per warp).  Same OpenCV op-order split
+// (SIMD body / scalar border + tail columns) as k_down_f32.
+// grid = (ceil(ow/128), ceil(rows/32), planes)
+// ------------------------------------------------------------------------------------------------------------
+constexpr int DF_BW = 128, DF_ROWS = 32, DF_BATCH = 8;
+constexpr int DF_COLS = 2 * DF_BW + 8; // staged floats per row: columns [2*ox0 - 4, 2*ox0 + 260)
+
+template <bool WEIGHT>
+__global__ void __launch_bounds__(DF_BW) k_down_f32s(const TileDev *__restrict__ tiles, const int *__restrict__ tile_ids, GroupDev g, int l)
+{
+    __shared__ __align__(16) float s_in[2][DF_BATCH][DF_COLS];
+
+    const LevelGeom Ls = g.lv[l], Ld = g.lv[l + 1];
+    const int h = Ls.h, w = Ls.w, ow = Ld.w;
+    const float *src;
+    float *dst;
+    int r0, r1, c = 0, cn_ref, xlim = ow;
+    if (WEIGHT) {
+        src = g.W[l];
+        dst = g.W[l + 1];
+        r0 = 0;
+        r1 = Ld.h;
+        cn_ref = 1;
+    } else {
+        const int z = blockIdx.z;
+        const TileDev &t = tiles[tile_ids[z / g.cn]];
+        c = z % g.cn;
+        src = t.G[l] + (size_t)c * Ls.plane;
+        dst = t.G[l + 1] + (size_t)c * Ld.plane;
+        r0 = t.g0[l + 1];
+        r1 = t.g1[l + 1];
+        cn_ref = g.cn;
+        xlim = t.gx1[l + 1];
+    }
+    const int oy0 = r0 + blockIdx.y * DF_ROWS;
+    const int ox0 = blockIdx.x * DF_BW;
+    if (oy0 >= r1 || ox0 >= ow || ox0 >= xlim) return;
+    const int oy1 = min(oy0 + DF_ROWS, r1);
+    const int in_y0 = 2 * oy0 - 2;
+    const int in_x0 = 2 * ox0 - 4; // multiple of 4
+    const int n_in_rows = 2 * (oy1 - oy0) + 3;
+    const int n_batches = (n_in_rows + DF_BATCH - 1) / DF_BATCH;
+    const int pitch = Ls.pitch;
+
+    auto stage = [&](int b) {
+        float(*buf)[DF_COLS] = s_in[b & 1];
+        for (int i = threadIdx.x; i < DF_BATCH * (DF_COLS / 4); i += DF_BW) {
+            const int j = i / (DF_COLS / 4), ch = i - j * (DF_COLS / 4);
+            const int gy = srf_reflect101(in_y0 + b * DF_BATCH + j, h);
+            const int c0 = in_x0 + ch * 4;
+            float *d = &buf[j][ch * 4];
+            if (c0 >= 0 && c0 + 4 <= pitch)
+                cp_async_16(d, src + (size_t)gy * pitch + c0);
+            else
+                *reinterpret_cast<float4 *>(d) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        cp_async_commit();
+    };
+
+    const int x = threadIdx.x;
+    const int ox = ox0 + x;
+    const bool x_edge = (ox0 == 0) || (2 * (ox0 + DF_BW - 1) + 2 >= w); // some tap of this strip is reflected
+    int ti[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        const int q = srf_reflect101(2 * min(ox, ow - 1) + k - 2, w) - in_x0;
+        ti[k] = max(min(q, DF_COLS - 1), 0);
+    }
+    const bool hsca = (ox < 1) || (ox >= Ld.vec_end);
+    const bool vsca = (ox * cn_ref + c) >= Ld.vtail;
+
+    float h0 = 0.f, h1 = 0.f, h2 = 0.f, h3 = 0.f, h4 = 0.f;
+    stage(0);
+    cp_async_wait<0>();
+    __syncthreads();
+    for (int b = 0; b < n_batches; ++b) {
+        if (b + 1 < n_batches) stage(b + 1);
+        const float(*buf)[DF_COLS] = s_in[b & 1];
+#pragma unroll
+        for (int j = 0; j < DF_BATCH; ++j) {
+            const float *row = buf[j];
+            float a0, a1, a2, a3, a4;
+            if (!x_edge) {
+                const float2 p0 = *reinterpret_cast<const float2 *>(row + 2 * x + 2);
+                const float2 p1 = *reinterpret_cast<const float2 *>(row + 2 * x + 4);
+                a0 = p0.x; a1 = p0.y; a2 = p1.x; a3 = p1.y; a4 = row[2 * x + 6];
+            } else {
+                a0 = row[ti[0]]; a1 = row[ti[1]]; a2 = row[ti[2]]; a3 = row[ti[3]]; a4 = row[ti[4]];
+            }
+            const float hv = hsca ? dn_h_sca(a0, a1, a2, a3, a4) : dn_h_vec(a0, a1, a2, a3, a4);
+            h0 = h1; h1 = h2; h2 = h3; h3 = h4; h4 = hv;
+            const int r = b * DF_BATCH + j; // stream position; rows r-4..r are in the ring
+            if ((j & 1) == 0 && r >= 4) {
+                const int oy = oy0 + ((r - 4) >> 1);
+                if (oy < oy1 && ox < ow) dst[(size_t)oy * Ld.pitch + ox] = vsca ? dn_v_sca(h0, h1, h2, h3, h4) : dn_v_vec(h0, h1, h2, h3, h4);
+            }
+        }
+        cp_async_wait<0>();
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// k_up_levels: the streaming form of k_up_level for the stored-C case (TOP = false).  One CTA = 256 x 32 outputs of
+// one plane, 128 threads: thread p owns output columns 2p, 2p+1 and slides down the rows with a 3-row register ring
+// of horizontally up-sampled (C_{l+1}, G_{l+1}) pairs, exactly like k_final; the <= 19 x 136 source windows arrive by
+// cp.async; G_l, W_l are read and C_l written as float2 (256 contiguous bytes per warp and row).
+// grid = (ceil(w_l/256), ceil(rows/32), planes)
+// ------------------------------------------------------------------------------------------------------------
+constexpr int UL_W = 256, UL_H = 32, UL_PAIRS = UL_W / 2, UL_STEPS = UL_H / 2;
+constexpr int UL_SRC_ROWS = UL_STEPS + 2; // 18
+constexpr int UL_SRC_COLS = UL_PAIRS + 8; // 136
+
+struct HPair2 {
+    float a, b;
+};
+__device__ __forceinline__ HPair2 up_pair_even_origin(float s0, float s1, float s2)
+{
+    HPair2 r;
+    r.a = up_even(s0, s1, s2); // column 2i, i = window centre
+    r.b = up_odd(s1, s2);      // column 2i + 1
+    return r;
+}
+
+__global__ void __launch_bounds__(UL_PAIRS) k_up_levels(const TileDev *__restrict__ tiles, const int *__restrict__ tile_ids, GroupDev g, int l)
+{
+    __shared__ __align__(16) float s_c[UL_SRC_ROWS][UL_SRC_COLS];
+    __shared__ __align__(16) float s_g[UL_SRC_ROWS][UL_SRC_COLS];
+
+    const int z = blockIdx.z;
+    const TileDev &t = tiles[tile_ids[z / g.cn]];
+    const int c = z % g.cn;
+    const LevelGeom L0 = g.lv[l], L1 = g.lv[l + 1];
+    const int h1 = L1.h, w1 = L1.w;
+    const int ty0 = t.c0[l] + blockIdx.y * UL_H;
+    const int tx0 = blockIdx.x * UL_W;
+    if (ty0 >= t.c1[l] || tx0 >= L0.w || tx0 >= t.cx1[l]) return;
+    const int ty1 = min(ty0 + UL_H, t.c1[l]);
+    const int ypar = ty0 & 1;
+    const int i0 = (tx0 >> 1) - 1;           // window start column for pair 0 (tx0 is even)
+    const int ws0 = (ty0 >> 1) - (1 - ypar); // window start row for step 0
+    const int sx0 = max(i0, 0) & ~3;
+    const int srow0 = max(min(ws0, h1 - 1), 0);
+    const int n_srows = max(min(ws0 + UL_STEPS + 1, h1 - 1), 0) - srow0 + 1; // <= 18
+    const float *G1 = t.G[l + 1] + (size_t)c * L1.plane;
+    const float *C1 = t.C[l + 1] + (size_t)c * L1.plane;
+
+    for (int i = threadIdx.x; i < n_srows * (UL_SRC_COLS / 4); i += UL_PAIRS) {
+        const int r = i / (UL_SRC_COLS / 4), ch = i - r * (UL_SRC_COLS / 4);
+        const int c0 = sx0 + ch * 4;
+        const size_t off = (size_t)(srow0 + r) * L1.pitch + c0;
+        if (c0 + 4 <= L1.pitch) {
+            cp_async_16(&s_g[r][ch * 4], G1 + off);
+            cp_async_16(&s_c[r][ch * 4], C1 + off);
+        } else {
+            *reinterpret_cast<float4 *>(&s_g[r][ch * 4]) = make_float4(0.f, 0.f, 0.f, 0.f);
+            *reinterpret_cast<float4 *>(&s_c[r][ch * 4]) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+    cp_async_commit();
+
+    const int p = threadIdx.x;
+    const int txa = tx0 + 2 * p, txb = txa + 1;
+    const bool ina = txa < L0.w, inb = txb < L0.w;
+    const bool hfast = (i0 >= 0) && (i0 + UL_PAIRS + 1 <= w1 - 1) && (w1 > 1);
+    const int scol = i0 + p - sx0;
+    const float *G0 = t.G[l] + (size_t)c * L0.plane;
+    const float *W0 = g.W[l];
+    float *C0 = t.C[l] + (size_t)c * L0.plane;
+
+    auto hrow = [&](int r_logical, HPair2 &oc, HPair2 &og) {
+        int r = (r_logical == -1) ? min(1, h1 - 1) : max(min(r_logical, h1 - 1), 0);
+        r = max(min(r - srow0, n_srows - 1), 0);
+        const float *rc = &s_c[r][0];
+        const float *rg = &s_g[r][0];
+        if (hfast) {
+            oc = up_pair_even_origin(rc[scol], rc[scol + 1], rc[scol + 2]);
+            og = up_pair_even_origin(rg[scol], rg[scol + 1], rg[scol + 2]);
+        } else {
+            oc.a = oc.b = og.a = og.b = 0.f;
+            if (ina) {
+                oc.a = up_h_sample(txa, w1, [&](int ii) { return rc[ii - sx0]; });
+                og.a = up_h_sample(txa, w1, [&](int ii) { return rg[ii - sx0]; });
+            }
+            if (inb) {
+                oc.b = up_h_sample(txb, w1, [&](int ii) { return rc[ii - sx0]; });
+                og.b = up_h_sample(txb, w1, [&](int ii) { return rg[ii - sx0]; });
+            }
+        }
+    };
+
+    cp_async_wait<0>();
+    __syncthreads();
+
+    HPair2 rc0, rg0, rc1, rg1, rc2, rg2;
+    hrow(ws0, rc0, rg0);
+    hrow(ws0 + 1, rc1, rg1);
+#pragma unroll 4
+    for (int k = 0; k < UL_STEPS; ++k) {
+        hrow(ws0 + k + 2, rc2, rg2);
+        float uc[2][2], ug[2][2];
+        if (ypar == 0) {
+            uc[0][0] = up_even(rc0.a, rc1.a, rc2.a); uc[0][1] = up_even(rc0.b, rc1.b, rc2.b);
+            ug[0][0] = up_even(rg0.a, rg1.a, rg2.a); ug[0][1] = up_even(rg0.b, rg1.b, rg2.b);
+            uc[1][0] = up_odd(rc1.a, rc2.a); uc[1][1] = up_odd(rc1.b, rc2.b);
+            ug[1][0] = up_odd(rg1.a, rg2.a); ug[1][1] = up_odd(rg1.b, rg2.b);
+        } else {
+            uc[0][0] = up_odd(rc0.a, rc1.a); uc[0][1] = up_odd(rc0.b, rc1.b);
+            ug[0][0] = up_odd(rg0.a, rg1.a); ug[0][1] = up_odd(rg0.b, rg1.b);
+            uc[1][0] = up_even(rc0.a, rc1.a, rc2.a); uc[1][1] = up_even(rc0.b, rc1.b, rc2.b);
+            ug[1][0] = up_even(rg0.a, rg1.a, rg2.a); ug[1][1] = up_even(rg0.b, rg1.b, rg2.b);
+        }
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+            const int ty = ty0 + 2 * k + a;
+            if (ty >= ty1 || !ina) continue;
+            const size_t off = (size_t)ty * L0.pitch + txa;
+            float g0a, g0b = 0.f, w0a, w0b = 0.f;
+            if (inb) {
+                const float2 gv = *reinterpret_cast<const float2 *>(G0 + off);
+                const float2 wv = *reinterpret_cast<const float2 *>(W0 + off);
+                g0a = gv.x; g0b = gv.y; w0a = wv.x; w0b = wv.y;
+            } else {
+                g0a = G0[off];
+                w0a = W0[off];
+            }
+            const float oa = __fadd_rn(__fmul_rn(uc[a][0], 1.f / 64.f), __fmul_rn(__fsub_rn(g0a, __fmul_rn(ug[a][0], 1.f / 64.f)), w0a));
+            const float ob = __fadd_rn(__fmul_rn(uc[a][1], 1.f / 64.f), __fmul_rn(__fsub_rn(g0b, __fmul_rn(ug[a][1], 1.f / 64.f)), w0b));
+            if (inb)
+                *reinterpret_cast<float2 *>(C0 + off) = make_float2(oa, ob);
+            else
+                C0[off] = oa;
+        }
+        rc0 = rc1; rg0 = rg1; rc1 = rc2; rg1 = rg2;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // k_final: canvas gather.  One CTA per 256 x 16 canvas block, 128*C threads: thread (p, c) owns canvas columns
 // cx0+2p, cx0+2p+1 of channel c for all 16 rows -- 32 accumulators in registers; the sum of W_0 lives in smem.
@@ -497,14 +740,6 @@ struct FinalSmem {
     float wsum[FB_H][FB_W];
 };
 
-__device__ __forceinline__ void cp_async_16(void *smem_dst, const void *gsrc)
-{
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
 // per-(CTA, tile) geometry, uniform across the CTA
 struct FinalGeo {
@@ -1129,6 +1364,12 @@ int srf_fuse_device(srf_ctx *ctx, const srf_tile *tiles, int n_tiles, int C, int
         };
         // weight pyramid (full planes; tiny next to the image work, and shared by the whole group)
         for (int l = 0; l + 1 < n && !w_valid[k]; ++l) {
+            if (l >= 1) { // W_l -> W_{l+1}: the streaming kernel; W_0 -> W_1 reads the profile, not a plane
+                dim3 sgrid(srf_ceil_div(gw.lv[l + 1].w, DF_BW), srf_ceil_div(gw.lv[l + 1].h, DF_ROWS), 1);
+                srf_launch_scope scope(ctx, "down_weight", 4.0 * ((double)gw.lv[l].h * gw.lv[l].w + (double)gw.lv[l + 1].h * gw.lv[l + 1].w), st);
+                k_down_f32s<true><<<sgrid, DF_BW, 0, st>>>(d_tiles, ids_k, gw, l);
+                continue;
+            }
             dim3 grid(srf_ceil_div(gw.lv[l + 1].w, DN_BW), srf_ceil_div(gw.lv[l + 1].h, DN_BH), 1);
             srf_launch_scope scope(ctx, "down_weight", 4.0 * ((l ? (double)gw.lv[l].h * gw.lv[l].w : 0.0) + (double)gw.lv[l + 1].h * gw.lv[l + 1].w), st);
             k_down_f32<true><<<grid, kThreads, 0, st>>>(d_tiles, ids_k, gw, l);
@@ -1150,11 +1391,11 @@ int srf_fuse_device(srf_ctx *ctx, const srf_tile *tiles, int n_tiles, int C, int
         for (int l = 1; l + 1 < n; ++l) {
             const int rows = max_rows(l + 1, false);
             if (rows <= 0) continue;
-            dim3 grid(srf_ceil_div(gi.lv[l + 1].w, DN_BW), srf_ceil_div(rows, DN_BH), nt * C);
+            dim3 grid(srf_ceil_div(gi.lv[l + 1].w, DF_BW), srf_ceil_div(rows, DF_ROWS), nt * C);
             double pxo = 0;
             for (int ti : groups[k].tiles) pxo += (double)(tdev[ti].g1[l + 1] - tdev[ti].g0[l + 1]) * std::min(gi.lv[l + 1].w, tdev[ti].gx1[l + 1]);
             srf_launch_scope scope(ctx, "down_f32", pxo * C * (16.0 + 4.0), st);
-            k_down_f32<false><<<grid, kThreads, 0, st>>>(d_tiles, ids_k, gi, l);
+            k_down_f32s<false><<<grid, DF_BW, 0, st>>>(d_tiles, ids_k, gi, l);
         }
         // up: l = n-2 .. 1
         for (int l = n - 2; l >= 1; --l) {
@@ -1165,10 +1406,12 @@ int srf_fuse_device(srf_ctx *ctx, const srf_tile *tiles, int n_tiles, int C, int
             for (int ti : groups[k].tiles) pxo += (double)(tdev[ti].c1[l] - tdev[ti].c0[l]) * std::min(gi.lv[l].w, tdev[ti].cx1[l]);
             // per output element: G_l + W_l/C read, C_l written, C_{l+1} (or W_{l+1}/C) + G_{l+1} at quarter density
             srf_launch_scope scope(ctx, "up_level", pxo * C * (4.0 + 4.0 / C + 4.0 + 2.0), st);
-            if (l == n - 2)
+            if (l == n - 2) {
                 k_up_level<true><<<grid, kThreads, 0, st>>>(d_tiles, ids_k, gi, l);
-            else
-                k_up_level<false><<<grid, kThreads, 0, st>>>(d_tiles, ids_k, gi, l);
+            } else {
+                dim3 sgrid(srf_ceil_div(gi.lv[l].w, UL_W), srf_ceil_div(rows, UL_H), nt * C);
+                k_up_levels<<<sgrid, UL_PAIRS, 0, st>>>(d_tiles, ids_k, gi, l);
+            }
         }
     }
     SRF_CHECK_CUDA(ctx, cudaGetLastError());

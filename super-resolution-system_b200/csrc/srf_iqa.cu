@@ -55,14 +55,6 @@ struct IqaParams {
     IqaPartial *partials;
 };
 
-__device__ __forceinline__ void cp_async_16(void *smem_dst, const void *gsrc)
-{
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
 template <int C, bool ANYSCALE>
 __device__ __forceinline__ int gray_of(const uint8_t *p, int scale, int &bits, int (&v)[C])
