@@ -519,17 +519,23 @@ __global__ void __launch_bounds__(DF_BW) k_down_f32s(const TileDev *__restrict__
     const int n_batches = (n_in_rows + DF_BATCH - 1) / DF_BATCH;
     const int pitch = Ls.pitch;
 
+    // staging: lanes 0..65 of the CTA own one 16-byte chunk column each; the row loop is uniform
+    const int sch = threadIdx.x;
+    const int sc0 = in_x0 + sch * 4;
+    const bool s_on = sch < DF_COLS / 4;
+    const bool s_ok = s_on && sc0 >= 0 && sc0 + 4 <= pitch;
     auto stage = [&](int b) {
         float(*buf)[DF_COLS] = s_in[b & 1];
-        for (int i = threadIdx.x; i < DF_BATCH * (DF_COLS / 4); i += DF_BW) {
-            const int j = i / (DF_COLS / 4), ch = i - j * (DF_COLS / 4);
-            const int gy = srf_reflect101(in_y0 + b * DF_BATCH + j, h);
-            const int c0 = in_x0 + ch * 4;
-            float *d = &buf[j][ch * 4];
-            if (c0 >= 0 && c0 + 4 <= pitch)
-                cp_async_16(d, src + (size_t)gy * pitch + c0);
-            else
-                *reinterpret_cast<float4 *>(d) = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (s_on) {
+#pragma unroll
+            for (int j = 0; j < DF_BATCH; ++j) {
+                const int gy = srf_reflect101(in_y0 + b * DF_BATCH + j, h); // uniform
+                float *d = &buf[j][sch * 4];
+                if (s_ok)
+                    cp_async_16(d, src + (size_t)gy * pitch + sc0);
+                else
+                    *reinterpret_cast<float4 *>(d) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
         }
         cp_async_commit();
     };
@@ -666,6 +672,28 @@ __global__ void __launch_bounds__(UL_PAIRS) k_up_levels(const TileDev *__restric
         }
     };
 
+    // software prefetch of the per-output operands (G_l, W_l): one step (two rows) ahead, in registers
+    float2 gnext[2], wnext[2];
+    auto fetch_gw = [&](int k) {
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+            const int ty = ty0 + 2 * k + a;
+            gnext[a] = make_float2(0.f, 0.f);
+            wnext[a] = make_float2(0.f, 0.f);
+            if (ty < ty1 && ina) {
+                const size_t off = (size_t)ty * L0.pitch + txa;
+                if (inb) {
+                    gnext[a] = __ldg(reinterpret_cast<const float2 *>(G0 + off));
+                    wnext[a] = __ldg(reinterpret_cast<const float2 *>(W0 + off));
+                } else {
+                    gnext[a].x = __ldg(G0 + off);
+                    wnext[a].x = __ldg(W0 + off);
+                }
+            }
+        }
+    };
+    fetch_gw(0); // in flight while the source window lands
+
     cp_async_wait<0>();
     __syncthreads();
 
@@ -687,20 +715,15 @@ __global__ void __launch_bounds__(UL_PAIRS) k_up_levels(const TileDev *__restric
             uc[1][0] = up_even(rc0.a, rc1.a, rc2.a); uc[1][1] = up_even(rc0.b, rc1.b, rc2.b);
             ug[1][0] = up_even(rg0.a, rg1.a, rg2.a); ug[1][1] = up_even(rg0.b, rg1.b, rg2.b);
         }
+        // this step's G_l / W_l were fetched one step ago; fetch the next step's now
+        float2 gcur[2] = {gnext[0], gnext[1]}, wcur[2] = {wnext[0], wnext[1]};
+        if (k + 1 < UL_STEPS) fetch_gw(k + 1);
 #pragma unroll
         for (int a = 0; a < 2; ++a) {
             const int ty = ty0 + 2 * k + a;
             if (ty >= ty1 || !ina) continue;
             const size_t off = (size_t)ty * L0.pitch + txa;
-            float g0a, g0b = 0.f, w0a, w0b = 0.f;
-            if (inb) {
-                const float2 gv = *reinterpret_cast<const float2 *>(G0 + off);
-                const float2 wv = *reinterpret_cast<const float2 *>(W0 + off);
-                g0a = gv.x; g0b = gv.y; w0a = wv.x; w0b = wv.y;
-            } else {
-                g0a = G0[off];
-                w0a = W0[off];
-            }
+            const float g0a = gcur[a].x, g0b = gcur[a].y, w0a = wcur[a].x, w0b = wcur[a].y;
             const float oa = __fadd_rn(__fmul_rn(uc[a][0], 1.f / 64.f), __fmul_rn(__fsub_rn(g0a, __fmul_rn(ug[a][0], 1.f / 64.f)), w0a));
             const float ob = __fadd_rn(__fmul_rn(uc[a][1], 1.f / 64.f), __fmul_rn(__fsub_rn(g0b, __fmul_rn(ug[a][1], 1.f / 64.f)), w0b));
             if (inb)

@@ -205,59 +205,65 @@ __global__ void __launch_bounds__(IQ_THREADS, 5) k_psnr_ssim(IqaParams P)
     G(r_first);
     __syncthreads();
 
-    for (int base = r_first; base < r_last; base += TAPS) {
-#pragma unroll
-        for (int ph = 0; ph < TAPS; ++ph) {
-            const int r_in = base + ph;
-            if (r_in >= r_last) break;
-            const int buf = r_in & 1;
-            L(r_in + 4);
+    // The ring is a register SHIFT ring (slot 0 = oldest row): 4 x (TAPS-1) moves per row buy a loop body that exists
+    // once instead of TAPS times -- the phase-unrolled form overflowed the instruction cache (ncu: `no_instruction`
+    // was the top stall).
+#pragma unroll 1
+    for (int r_in = r_first; r_in < r_last; ++r_in) {
+        const int buf = r_in & 1;
+        L(r_in + 4);
 
-            // H(r): horizontal pass on gray row r_in -- four FMA chains with literal taps, products formed once per tap
-            {
-                float ha = 0.f, hb = 0.f, hs = 0.f, hp = 0.f;
-                const float *pa = &s_a[buf][t + (IQ_R - R)], *pb = &s_b[buf][t + (IQ_R - R)];
+        // H(r): horizontal pass on gray row r_in -- four FMA chains with literal taps, products formed once per tap
+        {
+            float ha = 0.f, hb = 0.f, hs = 0.f, hp = 0.f;
+            const float *pa = &s_a[buf][t + (IQ_R - R)], *pb = &s_b[buf][t + (IQ_R - R)];
 #pragma unroll
-                for (int k = 0; k < TAPS; ++k) {
-                    const float a = pa[k], b = pb[k];
-                    ha = fmaf(a, iq_tap<R>(k), ha);
-                    hb = fmaf(b, iq_tap<R>(k), hb);
-                    hs = fmaf(fmaf(a, a, b * b), iq_tap<R>(k), hs);
-                    hp = fmaf(a * b, iq_tap<R>(k), hp);
-                }
-                ring[0][ph] = ha;
-                ring[1][ph] = hb;
-                ring[2][ph] = hs;
-                ring[3][ph] = hp;
+            for (int k = 0; k < TAPS; ++k) {
+                const float a = pa[k], b = pb[k];
+                ha = fmaf(a, iq_tap<R>(k), ha);
+                hb = fmaf(b, iq_tap<R>(k), hb);
+                hs = fmaf(fmaf(a, a, b * b), iq_tap<R>(k), hs);
+                hp = fmaf(a * b, iq_tap<R>(k), hp);
             }
-
-            // vertical pass: output row r = r_in - R uses input rows r_in-2R .. r_in = ring slots (ph+1+k) % TAPS
-            const int r = r_in - R;
-            if (r >= ry0) {
-                float f[4];
 #pragma unroll
-                for (int s = 0; s < 4; ++s) {
-                    float v = 0.f;
-#pragma unroll
-                    for (int k = 0; k < TAPS; ++k) v = fmaf(ring[s][(ph + 1 + k) % TAPS], iq_tap<R>(k), v);
-                    f[s] = v;
-                }
-                const float ua = f[0], ub = f[1];
-                const float ux = ua + 128.f, uy = ub + 128.f;
-                const float vsum = P.cov_norm * (f[2] - fmaf(ua, ua, ub * ub)); // vx + vy (shift invariant)
-                const float vxy = P.cov_norm * (f[3] - ua * ub);
-                const float A1 = fmaf(2.f * ux, uy, C1), A2 = fmaf(2.f, vxy, C2);
-                const float B1 = fmaf(ux, ux, fmaf(uy, uy, C1)), B2 = vsum + C2;
-                const float S = __fdividef(A1 * A2, B1 * B2);
-                if (col_interior && r >= R && r < h - R) {
-                    ssum += S;
-                    scount++;
-                }
+            for (int k = 0; k < TAPS - 1; ++k) {
+                ring[0][k] = ring[0][k + 1];
+                ring[1][k] = ring[1][k + 1];
+                ring[2][k] = ring[2][k + 1];
+                ring[3][k] = ring[3][k + 1];
             }
-            if (r_in + 1 < r_last) G(r_in + 1);
-            cp_async_wait<2>(); // row r_in + 2 has landed (this thread's copies); the barrier publishes it
-            __syncthreads();
+            ring[0][TAPS - 1] = ha;
+            ring[1][TAPS - 1] = hb;
+            ring[2][TAPS - 1] = hs;
+            ring[3][TAPS - 1] = hp;
         }
+
+        // vertical pass: output row r = r_in - R uses input rows r_in-2R .. r_in = ring slots 0 .. TAPS-1
+        const int r = r_in - R;
+        if (r >= ry0) {
+            float f[4];
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                float v = 0.f;
+#pragma unroll
+                for (int k = 0; k < TAPS; ++k) v = fmaf(ring[s][k], iq_tap<R>(k), v);
+                f[s] = v;
+            }
+            const float ua = f[0], ub = f[1];
+            const float ux = ua + 128.f, uy = ub + 128.f;
+            const float vsum = P.cov_norm * (f[2] - fmaf(ua, ua, ub * ub)); // vx + vy (shift invariant)
+            const float vxy = P.cov_norm * (f[3] - ua * ub);
+            const float A1 = fmaf(2.f * ux, uy, C1), A2 = fmaf(2.f, vxy, C2);
+            const float B1 = fmaf(ux, ux, fmaf(uy, uy, C1)), B2 = vsum + C2;
+            const float S = __fdividef(A1 * A2, B1 * B2);
+            if (col_interior && r >= R && r < h - R) {
+                ssum += S;
+                scount++;
+            }
+        }
+        if (r_in + 1 < r_last) G(r_in + 1);
+        cp_async_wait<2>(); // row r_in + 2 has landed (this thread's copies); the barrier publishes it
+        __syncthreads();
     }
     cp_async_wait<0>();
 
