@@ -783,7 +783,7 @@ __device__ __forceinline__ FinalGeo final_geo(const TileDev &t, const GroupDev &
     q.xpar = txf & 1; q.ypar = tyf & 1;
     q.i0 = (txf >> 1) - (1 - q.xpar);  // window start column for pair 0
     q.ws0 = (tyf >> 1) - (1 - q.ypar); // window start row for step 0
-    q.sx0 = max(q.i0, 0) & ~3;
+    q.sx0 = (q.i0 >> 2) * 4; // floor to a multiple of 4 (may be negative: those columns are staged as zeros)
     q.srow0 = max(min(q.ws0, h1 - 1), 0);
     q.n_srows = max(min(q.ws0 + FB_STEPS + 1, h1 - 1), 0) - q.srow0 + 1; // <= 10
     q.u8_a0 = ((q.ix0 - t.x) * C) & ~15;
@@ -838,8 +838,10 @@ __device__ __forceinline__ void final_accumulate_tile(FinalSmem<C> &S, const Fin
     const int lmax = g.lut_len - 1;
     const int dxa = min(txa, t.w - 1 - txa), dxb = min(txb, t.w - 1 - txb);
     const int u8_col = txa * C + c - u8_a0; // byte offset of (txa, c) inside a staged row
-    const bool hfast = FULL || ((mode == 0) && (i0 >= 0) && (i0 + FB_PAIRS + 1 <= w1 - 1) && (w1 > 1));
-    const int scol = i0 + p - sx0; // smem column of s0
+    const int scol = i0 + p - sx0; // smem column of s0 (>= 0: the staged window starts at floor4(i0), zero-filled left of 0)
+    // columns whose horizontal sample needs an edge formula (tx = 0, the last source column, a 1-wide source)
+    const bool spa = !FULL && ((txa <= 0) || ((txa >> 1) >= w1 - 1));
+    const bool spb = !FULL && ((txb <= 0) || ((txb >> 1) >= w1 - 1));
 
     auto weight = [&](int dy, int dx) { return __ldg(g.lut + min(min(dy, dx), lmax)); };
     auto hrow = [&](int r_logical, HPair &oc, HPair &og) {
@@ -848,13 +850,25 @@ __device__ __forceinline__ void final_accumulate_tile(FinalSmem<C> &S, const Fin
         r = max(min(r, n_srows - 1), 0);
         const float *rc = &B.sc[c][r][0];
         const float *rg = &B.sg[c][r][0];
-        if (hfast) {
+        if (FULL || mode == 0) {
+            // interior formula for everyone (windows that poke outside the source row read staged zeros / padding and
+            // only ever feed columns that are outside the tile or patched right below)
             oc = h_pair_fast(rc[scol], rc[scol + 1], rc[scol + 2], xpar);
             og = h_pair_fast(rg[scol], rg[scol + 1], rg[scol + 2], xpar);
-        } else {
+            if (!FULL) {
+                if (spa && ina) {
+                    oc.a = up_h_sample(txa, w1, [&](int ii) { return rc[ii - sx0]; });
+                    og.a = up_h_sample(txa, w1, [&](int ii) { return rg[ii - sx0]; });
+                }
+                if (spb && inb) {
+                    oc.b = up_h_sample(txb, w1, [&](int ii) { return rc[ii - sx0]; });
+                    og.b = up_h_sample(txb, w1, [&](int ii) { return rg[ii - sx0]; });
+                }
+            }
+        } else { // exactly two levels: C_1 = G_1 * W_1 formed on the fly (sc holds the W_1 window)
             oc.a = oc.b = og.a = og.b = 0.f;
             auto atg = [&](int ii) { return rg[ii - sx0]; };
-            auto atc = [&](int ii) { return (mode == 1) ? __fmul_rn(rg[ii - sx0], rc[ii - sx0]) : rc[ii - sx0]; };
+            auto atc = [&](int ii) { return __fmul_rn(rg[ii - sx0], rc[ii - sx0]); };
             if (ina) {
                 oc.a = up_h_sample(txa, w1, atc);
                 og.a = up_h_sample(txa, w1, atg);
@@ -989,31 +1003,39 @@ __global__ void __launch_bounds__(128 * C, (C == 3) ? 2 : 5) k_final(FinalParams
             const FinalGeo q = final_geo(t, g, cy0, cy1, cx0, cx1, C);
             FinalStage<C> &B = S.st[li & 1];
             const int pitch = (int)t.pitch;
-            for (int i = threadIdx.x; i < (q.iy1 - q.iy0) * q.u8_chunks; i += NT) {
-                const int r = i / q.u8_chunks, ch = i - r * q.u8_chunks;
-                const int o = q.u8_a0 + ch * 16;
-                uint8_t *dst = &B.u8[q.iy0 - cy0 + r][ch * 16];
-                if (o >= 0 && o + 16 <= pitch)
-                    cp_async_16(dst, t.src + (size_t)(q.iy0 - t.y + r) * t.pitch + o);
-                else
-                    *reinterpret_cast<uint4 *>(dst) = make_uint4(0, 0, 0, 0);
+            constexpr int NW = NT / 32;
+            // one warp per row, one lane per 16-byte chunk (+ a second pass for the chunks beyond 32): no div / mod
+            for (int r = warp; r < q.iy1 - q.iy0; r += NW) {
+                const uint8_t *grow = t.src + (size_t)(q.iy0 - t.y + r) * t.pitch + q.u8_a0;
+                uint8_t *drow = &B.u8[q.iy0 - cy0 + r][0];
+                for (int ch = lane; ch < q.u8_chunks; ch += 32) {
+                    const int o = q.u8_a0 + ch * 16;
+                    if (o >= 0 && o + 16 <= pitch)
+                        cp_async_16(drow + ch * 16, grow + ch * 16);
+                    else
+                        *reinterpret_cast<uint4 *>(drow + ch * 16) = make_uint4(0, 0, 0, 0);
+                }
             }
             if (q.mode != 2) {
                 const LevelGeom L1 = g.lv[1];
-                const int per_c = q.n_srows * (FB_SRC_COLS / 4);
-                for (int i = threadIdx.x; i < C * per_c; i += NT) {
-                    const int cc = i / per_c;
-                    const int rem = i - cc * per_c;
-                    const int r = rem / (FB_SRC_COLS / 4), ch = rem - r * (FB_SRC_COLS / 4);
-                    const int c0 = q.sx0 + ch * 4;
-                    const size_t off = (size_t)(q.srow0 + r) * L1.pitch + c0;
-                    float *dg = &B.sg[cc][r][ch * 4], *dc = &B.sc[cc][r][ch * 4];
-                    if (c0 + 4 <= L1.pitch) {
-                        cp_async_16(dg, t.G[1] + (size_t)cc * L1.plane + off);
-                        cp_async_16(dc, (q.mode == 1) ? g.W[1] + off : t.C[1] + (size_t)cc * L1.plane + off);
-                    } else {
-                        *reinterpret_cast<float4 *>(dg) = make_float4(0.f, 0.f, 0.f, 0.f);
-                        *reinterpret_cast<float4 *>(dc) = make_float4(0.f, 0.f, 0.f, 0.f);
+                const float *csrc = (q.mode == 1) ? g.W[1] : t.C[1];
+                const size_t cplane = (q.mode == 1) ? 0 : L1.plane;
+                for (int r = warp; r < q.n_srows; r += NW) {
+                    const ptrdiff_t roff = (ptrdiff_t)(q.srow0 + r) * L1.pitch + q.sx0;
+                    for (int ch = lane; ch < FB_SRC_COLS / 4; ch += 32) {
+                        const int c0 = q.sx0 + ch * 4;
+                        const bool ok = c0 >= 0 && c0 + 4 <= L1.pitch;
+#pragma unroll
+                        for (int cc = 0; cc < C; ++cc) {
+                            float *dg = &B.sg[cc][r][ch * 4], *dc = &B.sc[cc][r][ch * 4];
+                            if (ok) {
+                                cp_async_16(dg, t.G[1] + (size_t)cc * L1.plane + roff + ch * 4);
+                                cp_async_16(dc, csrc + (size_t)cc * cplane + roff + ch * 4);
+                            } else {
+                                *reinterpret_cast<float4 *>(dg) = make_float4(0.f, 0.f, 0.f, 0.f);
+                                *reinterpret_cast<float4 *>(dc) = make_float4(0.f, 0.f, 0.f, 0.f);
+                            }
+                        }
                     }
                 }
             }
