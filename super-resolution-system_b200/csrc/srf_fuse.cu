@@ -485,7 +485,8 @@ constexpr int DF_COLS = 2 * DF_BW + 8; // staged floats per row: columns [2*ox0 
 template <bool WEIGHT>
 __global__ void __launch_bounds__(DF_BW) k_down_f32s(const TileDev *__restrict__ tiles, const int *__restrict__ tile_ids, GroupDev g, int l)
 {
-    __shared__ __align__(16) float s_in[2][DF_BATCH][DF_COLS];
+    __shared__ __align__(128) float s_in[2][DF_BATCH][DF_COLS];
+    __shared__ __align__(8) uint64_t s_bar[2];
 
     const LevelGeom Ls = g.lv[l], Ld = g.lv[l + 1];
     const int h = Ls.h, w = Ls.w, ow = Ld.w;
@@ -518,6 +519,30 @@ __global__ void __launch_bounds__(DF_BW) k_down_f32s(const TileDev *__restrict__
     const int n_in_rows = 2 * (oy1 - oy0) + 3;
     const int n_batches = (n_in_rows + DF_BATCH - 1) / DF_BATCH;
     const int pitch = Ls.pitch;
+
+    // Interior strips (the whole 1056-byte row segment lies inside the plane row) are staged by TMA bulk copies: ONE
+    // thread issues 8 cp.async.bulk per batch, completion on an mbarrier.  Edge strips keep the per-chunk cp.async path
+    // below (their out-of-row chunks must be zero-filled).
+    const bool use_tma = (in_x0 >= 0) && (in_x0 + DF_COLS <= pitch);
+    if (use_tma) {
+        if (threadIdx.x == 0) {
+            mbar_init(&s_bar[0], 1);
+            mbar_init(&s_bar[1], 1);
+            mbar_fence_init();
+        }
+        __syncthreads();
+    }
+    auto stage_tma = [&](int b) {
+        if (threadIdx.x == 0) {
+            uint64_t *bar = &s_bar[b & 1];
+            mbar_expect_tx(bar, DF_BATCH * DF_COLS * (unsigned)sizeof(float));
+#pragma unroll
+            for (int j = 0; j < DF_BATCH; ++j) {
+                const int gy = srf_reflect101(in_y0 + b * DF_BATCH + j, h);
+                tma_bulk_g2s(&s_in[b & 1][j][0], src + (size_t)gy * pitch + in_x0, DF_COLS * (unsigned)sizeof(float), bar);
+            }
+        }
+    };
 
     // staging: lanes 0..65 of the CTA own one 16-byte chunk column each; the row loop is uniform
     const int sch = threadIdx.x;
@@ -553,11 +578,21 @@ __global__ void __launch_bounds__(DF_BW) k_down_f32s(const TileDev *__restrict__
     const bool vsca = (ox * cn_ref + c) >= Ld.vtail;
 
     float h0 = 0.f, h1 = 0.f, h2 = 0.f, h3 = 0.f, h4 = 0.f;
-    stage(0);
-    cp_async_wait<0>();
-    __syncthreads();
+    if (use_tma) {
+        stage_tma(0);
+    } else {
+        stage(0);
+        cp_async_wait<0>();
+        __syncthreads();
+    }
     for (int b = 0; b < n_batches; ++b) {
-        if (b + 1 < n_batches) stage(b + 1);
+        if (b + 1 < n_batches) {
+            if (use_tma)
+                stage_tma(b + 1);
+            else
+                stage(b + 1);
+        }
+        if (use_tma) mbar_wait(&s_bar[b & 1], (b >> 1) & 1); // batch b has landed
         const float(*buf)[DF_COLS] = s_in[b & 1];
 #pragma unroll
         for (int j = 0; j < DF_BATCH; ++j) {
@@ -578,8 +613,8 @@ __global__ void __launch_bounds__(DF_BW) k_down_f32s(const TileDev *__restrict__
                 if (oy < oy1 && ox < ow) dst[(size_t)oy * Ld.pitch + ox] = vsca ? dn_v_sca(h0, h1, h2, h3, h4) : dn_v_vec(h0, h1, h2, h3, h4);
             }
         }
-        cp_async_wait<0>();
-        __syncthreads();
+        if (!use_tma) cp_async_wait<0>();
+        __syncthreads(); // everyone is done with buffer b & 1 before batch b + 2 is copied over it
     }
 }
 
