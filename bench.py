@@ -63,7 +63,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception as e:  # pragma: no cover
             log("clock sampling unavailable:", e)
@@ -275,31 +275,59 @@ def run_b200(args, wl):
 
     # ---- end to end through the public host API (pinned host buffers, copies inside the timed region)
     e2e = None
-    if world == 1 and not args.no_e2e:
+    if not args.no_e2e:
         pipe = pkg.SuperResolutionPipeline(pkg.PipelineConfig(num_pyramid_levels=wl.levels, enable_qa=True))
+        pipe.blending_module.device = local
         h_tiles = []
-        for t, (y, x) in zip(wl.tiles, wl.positions_yx):
-            p = torch.from_numpy(t).pin_memory()
-            h_tiles.append(pkg.TileInfo(p.numpy(), x, y, 0, 0))
+        for i in (range(len(wl.tiles)) if world == 1 else mine):
+            pt = torch.from_numpy(wl.tiles[i]).pin_memory()
+            h_tiles.append(pkg.TileInfo(pt.numpy(), wl.positions_yx[i][1], wl.positions_yx[i][0], 0, 0))
         h_ref = torch.from_numpy(wl.reference).pin_memory().numpy()
         h_out = torch.empty((H, W, 3), dtype=torch.uint8).pin_memory().numpy()
+        moved = [0, 0]
 
-        def step_host():
-            return pipe.fuse_and_assess(h_tiles, h_ref, (H, W), out=h_out)[1]
+        if world == 1:
+            def step_host():  # stage 3 + 4 in one library call (band-pipelined over three streams)
+                rep = pipe.fuse_and_assess(h_tiles, h_ref, (H, W), out=h_out)[1]
+                moved[0], moved[1] = native.last_transfer_bytes(ctx)
+                return rep["psnr"], rep["ms_ssim"]
+        else:
+            hplan = bm.plan_fusion(h_tiles, output_shape=(H, W))
+
+            def step_host():  # every rank: its tiles up, its band fused and down, then its band of both images up for
+                bm.laplacian_fusion(hplan, row_range=(e0, e1), out=h_out)  # the assessment; sums all-reduced
+                a, b = native.last_transfer_bytes(ctx)
+                s = qa.psnr_ssim_sums(h_ref, h_out, row_range=(r0, r1))
+                a2 = 2 * (min(r1 + 5, H) - max(r0 - 5, 0)) * W * 3
+                moved[0], moved[1] = a + a2, b + 48
+                s = D.allreduce_sums(s, H * W * 3, device=dev)
+                return qa.finish(s)
 
         for _ in range(max(1, args.warmup // 2)):
             rep = step_host()
+        n_e2e = max(2, args.steps // 2)
+        if world > 1:
+            dist.barrier()
         torch.cuda.synchronize()
         ta = time.perf_counter()
-        n_e2e = max(2, args.steps // 2)
         for _ in range(n_e2e):
             rep = step_host()
         torch.cuda.synchronize()
         tb = time.perf_counter()
-        h2d_b, d2h_b = native.last_transfer_bytes(ctx)  # what the library really moved (tiles are trimmed to the
-        e2e = {"value": (H * W / 1e6) / ((tb - ta) / n_e2e), "unit": UNIT, "h2d_bytes_per_step": h2d_b,  # canvas's dependency cone)
-               "d2h_bytes_per_step": d2h_b, "h2d_bytes_untrimmed": int(wl.tile_bytes + wl.reference.nbytes), "ms_per_step": 1e3 * (tb - ta) / n_e2e, "steps": n_e2e,
-               "api": "SuperResolutionPipeline.fuse_and_assess (srf_fuse_assess_host)", "psnr": rep["psnr"], "ms_ssim": rep["ms_ssim"]}
+        if world > 1:
+            dist.barrier()
+        tt = torch.tensor([tb - ta, float(moved[0]), float(moved[1])], dtype=torch.float64, device=dev)
+        if world > 1:
+            tmax = tt.clone()
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            dist.all_reduce(tt, op=dist.ReduceOp.SUM)
+            tt[0] = tmax[0]  # time: slowest rank; bytes: summed over ranks
+        secs, h2d_b, d2h_b = tt.tolist()
+        e2e = {"value": (H * W / 1e6) / (secs / n_e2e), "unit": UNIT, "h2d_bytes_per_step": int(h2d_b), "d2h_bytes_per_step": int(d2h_b),
+               "h2d_bytes_untrimmed": int(wl.tile_bytes + wl.reference.nbytes), "ms_per_step": 1e3 * secs / n_e2e, "steps": n_e2e,
+               "api": "SuperResolutionPipeline.fuse_and_assess (srf_fuse_assess_host)" if world == 1 else
+                      "per rank: BlendingModule.laplacian_fusion(row_range=band) + QualityAssessmentModule.psnr_ssim_sums(row_range=band), host arrays",
+               "psnr": rep[0], "ms_ssim": rep[1]}
         del h_tiles, h_ref, h_out
 
     # ---- the reference's CPU path beside it (bounded sample), rank 0 at N = 1 only

@@ -47,7 +47,6 @@ struct srf_ctx {
     srf_buffer ws_desc;     // device copies of descriptor arrays
     srf_buffer ws_stage_in; // *_host entry points: device staging of inputs
     srf_buffer ws_stage_out;
-    srf_buffer ws_misc;     // weight profiles
     srf_buffer ws_iqa;      // IQA reduction partials
     void *pinned = nullptr; // small pinned host block for result read-back
     size_t pinned_bytes = 0;

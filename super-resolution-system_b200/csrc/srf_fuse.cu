@@ -60,28 +60,7 @@ struct TileDev {
 // ------------------------------------------------------------------------------------------------------------
 // cooperative staging helpers
 // ------------------------------------------------------------------------------------------------------------
-// Copy bytes [b0, b0 + nbytes) of a global row (valid bytes [0, valid)) into smem; b0 is a multiple of 16, the
-// row base is 16-byte aligned, smem dst is 16-byte aligned.  Out-of-range bytes become 0.
-__device__ __forceinline__ void stage_u8_chunk(uint8_t *sdst, const uint8_t *grow, int b0, int chunk, int valid)
-{
-    const int o = b0 + chunk * 16;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (grow != nullptr) {
-        if (o >= 0 && o + 16 <= valid) {
-            v = *reinterpret_cast<const uint4 *>(grow + o);
-        } else if (o + 16 > 0 && o < valid) {
-            uint8_t *b = reinterpret_cast<uint8_t *>(&v);
-#pragma unroll
-            for (int e = 0; e < 16; ++e) {
-                const int p = o + e;
-                b[e] = (p >= 0 && p < valid) ? grow[p] : (uint8_t)0;
-            }
-        }
-    }
-    *reinterpret_cast<uint4 *>(sdst + chunk * 16) = v;
-}
-
-// same for float planes: cols [c0, c0+4) of a row with `w` valid floats (pitch multiple of 4, c0 multiple of 4)
+// cols [c0, c0+4) of a float plane row with `w` valid floats (pitch multiple of 4, c0 multiple of 4); zeros outside
 __device__ __forceinline__ float4 load_f32_chunk(const float *grow, int c0, int w)
 {
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
