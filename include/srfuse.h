@@ -169,12 +169,14 @@ int srf_psnr_ssim_enqueue(srf_ctx *ctx, const uint8_t *d_a, size_t pitch_a, cons
                           int row_end, double *d_sums5, void *stream);
 /* stage 3 + stage 4 of the reference pipeline in one call (main.py:347 laplacian_fusion, :369
  * evaluate_full_reference): host tiles -> fused canvas (host) + PSNR/SSIM sums of the canvas against a host
- * comparison image of the same size.  The canvas stays on the device between the two stages; uploads, kernels and
- * the canvas download overlap on two streams. */
+ * comparison image of the same size, for canvas rows [row_begin, row_end) (0, out_h for everything; a rank of a
+ * band-sharded job passes its band -- rows outside are neither written nor scored, and the 5-row SSIM halo is fused
+ * internally).  The canvas stays on the device between the two stages; uploads, kernels and the canvas download
+ * overlap on three streams, band by band. */
 int srf_fuse_assess_host(srf_ctx *ctx, const srf_tile *tiles, int n_tiles, int channels, int levels,
                          const srf_weight_lut *luts, int n_luts, int out_h, int out_w, uint8_t *h_canvas,
                          size_t canvas_pitch, const uint8_t *h_reference, size_t reference_pitch, double data_range,
-                         srf_iqa_sums *h_out);
+                         int row_begin, int row_end, srf_iqa_sums *h_out);
 /* final scalars from (all-reduced) sums: psnr = 10 log10(range^2 / (sq_err / n_elems)) (+inf if sq_err == 0),
  * ssim = ssim_sum / ssim_count */
 int srf_iqa_finish(const srf_iqa_sums *sums, double data_range, double *psnr, double *ssim);

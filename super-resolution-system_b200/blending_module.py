@@ -257,11 +257,15 @@ class BlendingModule:
         return canvas
 
     def fuse_and_assess(self, tiles, reference: np.ndarray, output_shape=None,
-                        weight_type: WeightType = WeightType.COSINE, data_range: float = 255.0, out=None):
+                        weight_type: WeightType = WeightType.COSINE, data_range: float = 255.0, out=None, row_range=None):
         """Host tiles -> (fused canvas, srf_iqa_sums of canvas vs `reference`) in one library call: stage 3 + stage 4
         of the reference pipeline with the canvas kept on the device in between (include/srfuse.h:
         srf_fuse_assess_host)."""
-        views, c_tiles, c_luts, keep, out_h, out_w, chans = self._marshal(tiles, output_shape, weight_type)
+        if isinstance(tiles, FusionPlan):
+            views, c_tiles, c_luts, keep, out_h, out_w, chans = tiles.parts
+        else:
+            views, c_tiles, c_luts, keep, out_h, out_w, chans = self._marshal(tiles, output_shape, weight_type)
+        r0, r1 = (0, out_h) if row_range is None else (int(row_range[0]), int(row_range[1]))
         if views[0].on_device:
             raise ValueError("fuse_and_assess takes host arrays; use laplacian_fusion + psnr_ssim_sums for CUDA tensors")
         shape = (out_h, out_w) if views[0].keep.ndim == 2 else (out_h, out_w, chans)
@@ -273,11 +277,11 @@ class BlendingModule:
                 raise ValueError("out must be a C-contiguous uint8 array of the canvas shape")
             canvas = out
         else:
-            canvas = np.empty(shape, np.uint8)
+            canvas = np.empty(shape, np.uint8) if (r0, r1) == (0, out_h) else np.zeros(shape, np.uint8)
         sums = _native.srf_iqa_sums()
         lib, ctx = _native.load(), self._ctx()
         rc = lib.srf_fuse_assess_host(ctx, c_tiles, len(views), chans, self.num_levels, c_luts, len(c_luts), out_h, out_w,
-                                      canvas.ctypes.data, out_w * chans, ref.ptr, ref.pitch, float(data_range), C.byref(sums))
+                                      canvas.ctypes.data, out_w * chans, ref.ptr, ref.pitch, float(data_range), r0, r1, C.byref(sums))
         _native.check(rc, ctx)
         return canvas, sums
 

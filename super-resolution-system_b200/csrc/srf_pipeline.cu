@@ -31,11 +31,14 @@ cudaEvent_t take_event(srf_ctx *ctx)
 
 extern "C" int srf_fuse_assess_host(srf_ctx *ctx, const srf_tile *tiles, int n_tiles, int channels, int levels,
                                     const srf_weight_lut *luts, int n_luts, int out_h, int out_w, uint8_t *h_canvas, size_t canvas_pitch,
-                                    const uint8_t *h_reference, size_t reference_pitch, double data_range, srf_iqa_sums *h_out)
+                                    const uint8_t *h_reference, size_t reference_pitch, double data_range, int row_begin, int row_end,
+                                    srf_iqa_sums *h_out)
 {
     if (!ctx) return SRF_ERR_ARG;
-    int rc = srf_check_fuse_args(ctx, tiles, n_tiles, channels, levels, luts, n_luts, out_h, out_w, h_canvas, canvas_pitch, 0, out_h);
+    int rc = srf_check_fuse_args(ctx, tiles, n_tiles, channels, levels, luts, n_luts, out_h, out_w, h_canvas, canvas_pitch, row_begin, row_end);
     if (rc) return rc;
+    // rows to FUSE: the requested band plus the SSIM halo (a rank of a band-sharded job needs its neighbours' 5 rows)
+    const int F0 = std::max(row_begin - 5, 0), F1 = (row_end > row_begin) ? std::min(row_end + 5, out_h) : F0;
     SRF_REQUIRE(ctx, h_reference && h_out, "srf_fuse_assess_host: null pointer");
     SRF_REQUIRE(ctx, reference_pitch >= (size_t)out_w * channels, "srf_fuse_assess_host: reference pitch < row bytes");
     SRF_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -61,10 +64,12 @@ extern "C" int srf_fuse_assess_host(srf_ctx *ctx, const srf_tile *tiles, int n_t
     for (int i = 0; i < n_tiles; ++i) dt[i].data = din + off[i];
 
     // ---- bands ----
-    const int nb = std::max(1, std::min(kMaxBands, out_h / 1024));
-    const int per = (out_h + nb - 1) / nb;
-    auto band_lo = [&](int b) { return std::min(b * per, out_h); };
-    auto band_hi = [&](int b) { return std::min((b + 1) * per, out_h); };
+    const int nb = std::max(1, std::min(kMaxBands, (F1 - F0) / 1024));
+    const int per = std::max(1, (F1 - F0 + nb - 1) / nb);
+    auto band_lo = [&](int b) { return std::min(F0 + b * per, F1); };
+    auto band_hi = [&](int b) { return std::min(F0 + (b + 1) * per, F1); };
+    auto own_lo = [&](int b) { return std::max(band_lo(b), row_begin); }; // the part of a sub-band the caller asked for
+    auto own_hi = [&](int b) { return std::min(band_hi(b), row_end); };
     auto touches = [&](int i, int r0, int r1) { return tiles[i].y < r1 && tiles[i].y + tiles[i].h > r0; };
 
     // reserve every workspace for the full tile set up front (and build the shared weight pyramids): an empty band
@@ -85,7 +90,7 @@ extern "C" int srf_fuse_assess_host(srf_ctx *ctx, const srf_tile *tiles, int n_t
             if (uploaded[i] || !touches(i, r0, r1)) continue;
             uploaded[i] = 1;
             int rows = 0, cols = 0; // only the part of the tile the canvas can depend on travels (exact dependency cone)
-            srf_fuse_input_extent(tiles[i], levels, out_h, out_w, 0, out_h, &rows, &cols);
+            srf_fuse_input_extent(tiles[i], levels, out_h, out_w, F0, F1, &rows, &cols);
             if (rows > 0 && cols > 0) {
                 h2d += (size_t)cols * channels * rows;
                 SRF_CHECK_CUDA(ctx, cudaMemcpy2DAsync(din + off[i], dt[i].pitch, tiles[i].data, tiles[i].pitch, (size_t)cols * channels, rows,
@@ -116,17 +121,17 @@ extern "C" int srf_fuse_assess_host(srf_ctx *ctx, const srf_tile *tiles, int n_t
         }
         SRF_CHECK_CUDA(ctx, cudaEventRecord(ev_fused[b], st));
         SRF_CHECK_CUDA(ctx, cudaStreamWaitEvent(dn, ev_fused[b], 0));
-        if (r1 > r0)
-            SRF_CHECK_CUDA(ctx, cudaMemcpy2DAsync(h_canvas + (size_t)r0 * canvas_pitch, canvas_pitch, dcanvas + (size_t)r0 * cpitch, cpitch,
-                                                  (size_t)out_w * channels, r1 - r0, cudaMemcpyDeviceToHost, dn));
-        if (b >= 1 && band_hi(b - 1) > band_lo(b - 1)) {
-            rc = srf_iqa_enqueue(ctx, dref, cpitch, dcanvas, cpitch, out_h, out_w, channels, 0, 0, data_range, band_lo(b - 1), band_hi(b - 1), st,
+        if (own_hi(b) > own_lo(b))
+            SRF_CHECK_CUDA(ctx, cudaMemcpy2DAsync(h_canvas + (size_t)own_lo(b) * canvas_pitch, canvas_pitch, dcanvas + (size_t)own_lo(b) * cpitch,
+                                                  cpitch, (size_t)out_w * channels, own_hi(b) - own_lo(b), cudaMemcpyDeviceToHost, dn));
+        if (b >= 1 && own_hi(b - 1) > own_lo(b - 1)) {
+            rc = srf_iqa_enqueue(ctx, dref, cpitch, dcanvas, cpitch, out_h, out_w, channels, 0, 0, data_range, own_lo(b - 1), own_hi(b - 1), st,
                                  b - 1);
             if (rc) return rc;
         }
     }
-    if (band_hi(nb - 1) > band_lo(nb - 1)) {
-        rc = srf_iqa_enqueue(ctx, dref, cpitch, dcanvas, cpitch, out_h, out_w, channels, 0, 0, data_range, band_lo(nb - 1), band_hi(nb - 1), st,
+    if (own_hi(nb - 1) > own_lo(nb - 1)) {
+        rc = srf_iqa_enqueue(ctx, dref, cpitch, dcanvas, cpitch, out_h, out_w, channels, 0, 0, data_range, own_lo(nb - 1), own_hi(nb - 1), st,
                              nb - 1);
         if (rc) return rc;
     }
@@ -146,9 +151,9 @@ extern "C" int srf_fuse_assess_host(srf_ctx *ctx, const srf_tile *tiles, int n_t
     acc.ssim_count = 0;
     acc.bits_a = acc.bits_b = 0;
     for (int b = 0; b < nb; ++b) {
-        if (band_hi(b) <= band_lo(b)) continue;
+        if (own_hi(b) <= own_lo(b)) continue;
         srf_iqa_sums s;
-        srf_iqa_collect(ctx, out_w, channels, band_lo(b), band_hi(b), &s, b);
+        srf_iqa_collect(ctx, out_w, channels, own_lo(b), own_hi(b), &s, b);
         acc.sq_err += s.sq_err;
         acc.n_elems += s.n_elems;
         acc.ssim_sum += s.ssim_sum; // fixed band order: deterministic
@@ -157,7 +162,7 @@ extern "C" int srf_fuse_assess_host(srf_ctx *ctx, const srf_tile *tiles, int n_t
         acc.bits_b |= s.bits_b;
     }
     *h_out = acc;
-    ctx->last_h2d = h2d + (size_t)out_w * channels * out_h;
-    ctx->last_d2h = (size_t)out_w * channels * out_h + (size_t)nb * 40;
+    ctx->last_h2d = h2d + (size_t)out_w * channels * (size_t)(F1 - F0);
+    ctx->last_d2h = (size_t)out_w * channels * (size_t)std::max(row_end - row_begin, 0) + (size_t)nb * 40;
     return SRF_OK;
 }

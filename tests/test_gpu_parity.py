@@ -359,3 +359,28 @@ def test_uniform_window_ssim_vs_oracle(srs, oracle, shape):
     assert s.ssim_count == (shape[0] - 6) * (shape[1] - 6) and s.sq_err == oracle.iqa_oracle.sq_err_sum(a, b)
     with pytest.raises(ValueError):
         qa.calculate_ssim(np.zeros((6, 40, 3), np.uint8), np.zeros((6, 40, 3), np.uint8), multiscale=False)
+
+
+def test_fuse_and_assess_row_bands_add_up(srs):
+    """band mode of the pipelined host call: bands reassemble the canvas and their sums add up to the full call's"""
+    rng = np.random.default_rng(44)
+    tiles, pos = [], []
+    for j in range(3):
+        for i in range(2):
+            tiles.append(synth(rng, 1024, 600))
+            pos.append((j * 800, i * 450))
+    out_hw = (2600, 1000)
+    infos = [srs.TileInfo(t, x, y, 0, 0) for t, (y, x) in zip(tiles, pos)]
+    ref = synth(rng, out_hw[0], out_hw[1])
+    bm = srs.BlendingModule(num_levels=5)
+    full, fs = bm.fuse_and_assess(infos, ref, out_hw)
+    acc = np.zeros_like(full)
+    sq = cnt = 0
+    ss = 0.0
+    for r0, r1 in [(0, 700), (700, 701), (701, 2000), (2000, 2600)]:
+        part, s = bm.fuse_and_assess(infos, ref, out_hw, row_range=(r0, r1))
+        assert not part[:r0].any() and not part[r1:].any()
+        acc[r0:r1] = part[r0:r1]
+        sq, cnt, ss = sq + s.sq_err, cnt + s.ssim_count, ss + s.ssim_sum
+    assert np.array_equal(acc, full)
+    assert (sq, cnt) == (fs.sq_err, fs.ssim_count) and ss == pytest.approx(fs.ssim_sum, rel=1e-7)
