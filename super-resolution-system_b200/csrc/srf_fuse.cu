@@ -857,7 +857,11 @@ __device__ __forceinline__ void final_accumulate_tile(FinalSmem<C> &S, const Fin
     const bool spa = !FULL && ((txa <= 0) || ((txa >> 1) >= w1 - 1));
     const bool spb = !FULL && ((txb <= 0) || ((txb >> 1) >= w1 - 1));
 
-    auto weight = [&](int dy, int dx) { return __ldg(g.lut + min(min(dy, dx), lmax)); };
+    // The weight profile is monotone non-decreasing in the border distance (linear, cosine and sigmoid all are, and
+    // float32 rounding keeps the order), so lut[min(dy, dx)] == min(lut[dy], lut[dx]) exactly: one lookup per row and
+    // two per tile instead of one per pixel.
+    const float wxa = __ldg(g.lut + max(min(dxa, lmax), 0)), wxb = __ldg(g.lut + max(min(dxb, lmax), 0));
+    auto weight_row = [&](int dy) { return __ldg(g.lut + max(min(dy, lmax), 0)); };
     auto hrow = [&](int r_logical, HPair &oc, HPair &og) {
         int r = (r_logical == -1) ? min(1, h1 - 1) : max(min(r_logical, h1 - 1), 0);
         r -= srow0;
@@ -902,15 +906,15 @@ __device__ __forceinline__ void final_accumulate_tile(FinalSmem<C> &S, const Fin
                 const int cy = cy0 + 2 * k + a;
                 if (cy < iy0 || cy >= iy1) continue;
                 const int ty = cy - t.y;
-                const int dy = min(ty, t.h - 1 - ty);
+                const float wy = weight_row(min(ty, t.h - 1 - ty));
                 const uint8_t *px = &B.u8[2 * k + a][u8_col];
                 if (ina) {
-                    const float w0 = weight(dy, dxa);
+                    const float w0 = fminf(wy, wxa);
                     acc[k][a][0] = __fadd_rn(acc[k][a][0], __fmul_rn((float)((int)px[0] << 6), w0));
                     if (c == 0) S.wsum[2 * k + a][2 * p] = __fadd_rn(S.wsum[2 * k + a][2 * p], w0);
                 }
                 if (inb) {
-                    const float w0 = weight(dy, dxb);
+                    const float w0 = fminf(wy, wxb);
                     acc[k][a][1] = __fadd_rn(acc[k][a][1], __fmul_rn((float)((int)px[C] << 6), w0));
                     if (c == 0) S.wsum[2 * k + a][2 * p + 1] = __fadd_rn(S.wsum[2 * k + a][2 * p + 1], w0);
                 }
@@ -942,19 +946,18 @@ __device__ __forceinline__ void final_accumulate_tile(FinalSmem<C> &S, const Fin
             const int cy = cy0 + 2 * k + a;
             if (FULL || (cy >= iy0 && cy < iy1)) {
                 const int ty = tyf + 2 * k + a;
-                const int dy = min(ty, t.h - 1 - ty);
+                const float wy = weight_row(min(ty, t.h - 1 - ty));
                 const uint8_t *px = &B.u8[2 * k + a][u8_col];
                 if (ina) {
-                    const float w0 = weight(dy, dxa);
-                    const float g64 = (float)((int)px[0] << 6);
-                    const float v = __fadd_rn(uc[a][0], __fmul_rn(__fsub_rn(g64, ug[a][0]), w0));
+                    const float w0 = fminf(wy, wxa);
+                    // fma(g, 64, -up64G) == 64 g - up64G rounded once: 64 g is exact, so this IS the reference's subtraction
+                    const float v = __fadd_rn(uc[a][0], __fmul_rn(__fmaf_rn((float)px[0], 64.f, -ug[a][0]), w0));
                     acc[k][a][0] = __fadd_rn(acc[k][a][0], v);
                     if (c == 0) S.wsum[2 * k + a][2 * p] = __fadd_rn(S.wsum[2 * k + a][2 * p], w0);
                 }
                 if (inb) {
-                    const float w0 = weight(dy, dxb);
-                    const float g64 = (float)((int)px[C] << 6);
-                    const float v = __fadd_rn(uc[a][1], __fmul_rn(__fsub_rn(g64, ug[a][1]), w0));
+                    const float w0 = fminf(wy, wxb);
+                    const float v = __fadd_rn(uc[a][1], __fmul_rn(__fmaf_rn((float)px[C], 64.f, -ug[a][1]), w0));
                     acc[k][a][1] = __fadd_rn(acc[k][a][1], v);
                     if (c == 0) S.wsum[2 * k + a][2 * p + 1] = __fadd_rn(S.wsum[2 * k + a][2 * p + 1], w0);
                 }

@@ -15,7 +15,7 @@
 namespace {
 
 constexpr int IQ_THREADS = 128;
-constexpr int IQ_RB = 64;    // S-map rows per CTA
+constexpr int IQ_RB = 128;   // S-map rows per CTA (the 2R halo rows above/below are re-filtered per CTA: 8 % at R = 5)
 constexpr int IQ_R = 5;      // staging halo = radius of the widest window (11-tap Gaussian)
 constexpr int IQ_SROW = IQ_THREADS + 2 * IQ_R + 2; // staged gray columns (+2 keeps rows 16-byte multiples)
 constexpr int IQ_RAW = 448;                         // staged raw bytes per row and image: 15 + 138 * 3 rounded up to 16
@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(IQ_THREADS, 5) k_psnr_ssim(IqaParams P)
         cp_async_commit();
     };
 
-    unsigned int sq = 0; // <= 64 rows * 2 px * 3 * 65025 < 2^32
+    unsigned int sq = 0; // <= 128 rows * 2 px * 3 * 65025 < 2^32
     int bits_a = 0, bits_b = 0;
     const int mis_a0 = (int)((reinterpret_cast<uintptr_t>(P.a) + (unsigned long long)col_off) & 15);
     const int mis_b0 = (int)((reinterpret_cast<uintptr_t>(P.b) + (unsigned long long)col_off) & 15);
