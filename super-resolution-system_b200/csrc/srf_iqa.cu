@@ -15,7 +15,7 @@
 namespace {
 
 constexpr int IQ_THREADS = 128;
-constexpr int IQ_RB = 128;   // S-map rows per CTA (the 2R halo rows above/below are re-filtered per CTA: 8 % at R = 5)
+constexpr int IQ_RB_MAX = 128; // S-map rows per CTA: 128 (halo re-filtering 8 % at R = 5) or 64 when the grid would be too small
 constexpr int IQ_R = 5;      // staging halo = radius of the widest window (11-tap Gaussian)
 constexpr int IQ_SROW = IQ_THREADS + 2 * IQ_R + 2; // staged gray columns (+2 keeps rows 16-byte multiples)
 constexpr int IQ_RAW = 448;                         // staged raw bytes per row and image: 15 + 138 * 3 rounded up to 16
@@ -50,6 +50,7 @@ struct IqaParams {
     int h, w;
     int scale_a, scale_b;
     float c1, c2;
+    int rb;         // S-map rows per CTA
     float cov_norm; // 1 (population covariance, Gaussian window) or 49/48 (sample covariance, uniform 7x7 window)
     int row_begin, row_end;
     IqaPartial *partials;
@@ -94,8 +95,8 @@ __global__ void __launch_bounds__(IQ_THREADS, 5) k_psnr_ssim(IqaParams P)
     constexpr int TAPS = 2 * R + 1;
     const int t = threadIdx.x;
     const int cx0 = blockIdx.x * IQ_THREADS;
-    const int ry0 = P.row_begin + blockIdx.y * IQ_RB;
-    const int ry1 = min(ry0 + IQ_RB, P.row_end);
+    const int ry0 = P.row_begin + blockIdx.y * P.rb;
+    const int ry1 = min(ry0 + P.rb, P.row_end);
     const int h = P.h, w = P.w;
     const int col1 = cx0 - IQ_R + t;              // every thread's first pixel
     const int col2 = cx0 + IQ_THREADS - IQ_R + t; // threads 0..9: the right halo
@@ -355,7 +356,10 @@ int srf_iqa_enqueue(srf_ctx *ctx, const uint8_t *a, size_t pa, const uint8_t *b,
                     double data_range, int row_begin, int row_end, cudaStream_t st, int slot, double *d_sums, int window)
 {
     int rc;
-    const int gx = srf_ceil_div(w, IQ_THREADS), gy = srf_ceil_div(row_end - row_begin, IQ_RB);
+    // tall CTAs amortise the vertical halo; short ones keep small bands (multi-GPU) from ending in a half-empty wave
+    const int gx = srf_ceil_div(w, IQ_THREADS);
+    const int rb = (gx * srf_ceil_div(row_end - row_begin, IQ_RB_MAX) >= 6 * 5 * ctx->sm_count) ? IQ_RB_MAX : IQ_RB_MAX / 2;
+    const int gy = srf_ceil_div(row_end - row_begin, rb);
     const size_t nparts = (size_t)gx * gy;
     if ((rc = srf_reserve(ctx, ctx->ws_iqa, (nparts + 1) * sizeof(IqaPartial)))) return rc;
     if ((rc = srf_reserve_pinned(ctx, 4096))) return rc;
@@ -372,6 +376,7 @@ int srf_iqa_enqueue(srf_ctx *ctx, const uint8_t *a, size_t pa, const uint8_t *b,
     P.scale_b = scale_b;
     P.c1 = (float)((0.01 * data_range) * (0.01 * data_range));
     P.c2 = (float)((0.03 * data_range) * (0.03 * data_range));
+    P.rb = rb;
     P.cov_norm = window ? (float)(49.0 / 48.0) : 1.f;
     P.row_begin = row_begin;
     P.row_end = row_end;
