@@ -5,8 +5,9 @@ Mirrors (names, arguments, error behaviour) /root/reference/blending_module.py:
   build_gaussian_pyramid 217-269, build_laplacian_pyramid 271-318, collapse_laplacian_pyramid 320-363,
   laplacian_fusion 369-506, _create_distance_weight_map 508-561.
 Every pixel is computed by libsrfuse.so (csrc/srf_fuse.cu) through the C ABI; nothing here falls back to the CPU.
-Out of scope: Poisson / weighted / feather / gradient-domain fusion, seam detection and
-repair, colour correction -- those entry points raise NotImplementedError.
+`weighted_average_fusion` (row N3, "next") maps onto the same gather kernel with one pyramid level.
+Out of scope: Poisson / feather / gradient-domain fusion, seam detection and repair, colour
+correction -- those entry points raise NotImplementedError.
 """
 from __future__ import annotations
 
@@ -211,7 +212,7 @@ class BlendingModule:
     def laplacian_fusion(self, tiles: List[Union[np.ndarray, TileInfo]], overlap_map=None,
                          output_shape: Optional[Tuple[int, int]] = None,
                          weight_type: WeightType = WeightType.COSINE, row_range: Optional[Tuple[int, int]] = None,
-                         out=None):
+                         out=None, _levels: Optional[int] = None):
         """Fuse upscaled tiles into one uint8 canvas (see include/srfuse.h: srf_laplacian_fuse).
 
         tiles: TileInfo objects (image + x, y) or bare arrays (grid layout, needs output_shape).  Images are uint8
@@ -226,6 +227,7 @@ class BlendingModule:
         else:
             views, c_tiles, c_luts, keep, out_h, out_w, chans = self._marshal(tiles, output_shape, weight_type)
         on_dev = views[0].on_device
+        levels = self.num_levels if _levels is None else int(_levels)
         r0, r1 = (0, out_h) if row_range is None else (int(row_range[0]), int(row_range[1]))
         lib, ctx = _native.load(), self._ctx()
         shape = (out_h, out_w) if views[0].keep.ndim == 2 else (out_h, out_w, chans)
@@ -241,7 +243,7 @@ class BlendingModule:
                 canvas = torch.zeros(shape, dtype=torch.uint8, device=views[0].keep.device)
             else:
                 canvas = torch.empty(shape, dtype=torch.uint8, device=views[0].keep.device)
-            rc = lib.srf_laplacian_fuse(ctx, c_tiles, len(views), chans, self.num_levels, c_luts, len(c_luts), out_h,
+            rc = lib.srf_laplacian_fuse(ctx, c_tiles, len(views), chans, levels, c_luts, len(c_luts), out_h,
                                         out_w, canvas.data_ptr(), out_w * chans, r0, r1, current_stream_ptr(dev))
             _native.check(rc, ctx)
             return canvas
@@ -251,7 +253,7 @@ class BlendingModule:
             canvas = out
         else:
             canvas = np.zeros(shape, np.uint8) if (r0, r1) != (0, out_h) else np.empty(shape, np.uint8)
-        rc = lib.srf_laplacian_fuse_host(ctx, c_tiles, len(views), chans, self.num_levels, c_luts, len(c_luts), out_h,
+        rc = lib.srf_laplacian_fuse_host(ctx, c_tiles, len(views), chans, levels, c_luts, len(c_luts), out_h,
                                          out_w, canvas.ctypes.data, out_w * chans, r0, r1)
         _native.check(rc, ctx)
         return canvas
@@ -293,8 +295,21 @@ class BlendingModule:
     def poisson_fusion(self, *a, **k):
         self._out_of_scope("poisson_fusion")
 
-    def weighted_average_fusion(self, *a, **k):
-        self._out_of_scope("weighted_average_fusion")
+    def weighted_average_fusion(self, tiles, weights=None, weight_type: WeightType = WeightType.COSINE,
+                                output_shape: Optional[Tuple[int, int]] = None, row_range=None, out=None):
+        """Mirror of BlendingModule.weighted_average_fusion (blending_module.py:661-760; row N3 of SURVEY.md 8f):
+        sum_t tile_t * W_0^t / max(sum_t W_0^t, 1e-6), clip, truncate -- which is exactly the Laplacian fusion with a
+        single pyramid level (no pyramid at all), so it runs the same gather kernel.  Bare-array tiles always get the
+        sqrt-grid layout here (the reference does not require output_shape for them).  Custom per-tile weight maps
+        (`weights=`) are not supported on the GPU path."""
+        if weights is not None:
+            raise NotImplementedError("weighted_average_fusion(weights=...): custom weight maps are not on the GPU path")
+        tiles = list(tiles)
+        if tiles and not any(isinstance(t, TileInfo) for t in tiles):
+            grid = int(np.ceil(np.sqrt(len(tiles))))
+            tiles = [TileInfo(t, (i % grid) * t.shape[1], (i // grid) * t.shape[0], i // grid, i % grid) for i, t in enumerate(tiles)]
+        return self.laplacian_fusion(tiles, output_shape=output_shape, weight_type=weight_type, row_range=row_range, out=out,
+                                     _levels=1)
 
     def detect_seams(self, *a, **k):
         self._out_of_scope("detect_seams")

@@ -138,6 +138,13 @@ def main():
     out["iqa_demo_psnr"] = np.array(qa.calculate_psnr(hr, sr))
     out["iqa_demo_ssim_fallback"] = np.array(qa.calculate_ssim(hr, sr, multiscale=True))
 
+    # ---- weighted-average fusion (the "next" row N3): same tiles as the ragged Laplacian case ----------------
+    wt = [out[f"fuse_ragged_t{i}"] for i in range(3)]
+    wp = out["fuse_ragged_pos"]
+    winfos = [rb.TileInfo(t, int(x), int(y), 0, 0) for t, (y, x) in zip(wt, wp)]
+    out["wavg_ragged_out"] = rb.BlendingModule().weighted_average_fusion(winfos, weight_type=rb.WeightType.LINEAR, output_shape=(160, 215))
+    out["wavg_grid_out"] = rb.BlendingModule().weighted_average_fusion([out[f"fuse_linear6_t{i}"] for i in range(4)])
+
     np.savez_compressed(os.path.join(HERE, "reference_vectors.npz"), **out)
     print("wrote", os.path.join(HERE, "reference_vectors.npz"), os.path.getsize(os.path.join(HERE, "reference_vectors.npz")) // 1024, "KiB")
     print("cv2", cv2.__version__, "numpy", np.__version__)

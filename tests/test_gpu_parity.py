@@ -384,3 +384,15 @@ def test_fuse_and_assess_row_bands_add_up(srs):
         sq, cnt, ss = sq + s.sq_err, cnt + s.ssim_count, ss + s.ssim_sum
     assert np.array_equal(acc, full)
     assert (sq, cnt) == (fs.sq_err, fs.ssim_count) and ss == pytest.approx(fs.ssim_sum, rel=1e-7)
+
+
+def test_weighted_average_fusion_vs_reference_golden(srs, golden):
+    tiles, pos, out_hw, _, _, _ = fuse_case(golden, "ragged")
+    bm = srs.BlendingModule()
+    infos = [srs.TileInfo(np.ascontiguousarray(t), x, y, 0, 0) for t, (y, x) in zip(tiles, pos)]
+    got = bm.weighted_average_fusion(infos, weight_type=srs.WeightType.LINEAR, output_shape=out_hw)
+    assert np.array_equal(got, golden["wavg_ragged_out"])
+    t4 = [np.ascontiguousarray(golden[f"fuse_linear6_t{i}"]) for i in range(4)]
+    assert np.array_equal(bm.weighted_average_fusion(t4), golden["wavg_grid_out"])  # bare arrays: sqrt-grid, max extents
+    with pytest.raises(NotImplementedError):
+        bm.weighted_average_fusion(t4, weights=[np.ones((64, 64), np.float32)] * 4)

@@ -145,3 +145,13 @@ def test_uniform_ssim_oracle_equals_scipy_restatement(oracle):
     c1, c2 = 6.5025, 58.5225
     s = ((2 * ux * uy + c1) * (2 * vxy + c2)) / ((ux ** 2 + uy ** 2 + c1) * (vx + vy + c2))
     assert io.ssim_uniform(a, b) == pytest.approx(s[3:-3, 3:-3].mean(dtype=np.float64), rel=1e-12)
+
+
+def test_weighted_average_is_single_level_fusion(golden, oracle):
+    """blending_module.py:661-760 == the Laplacian fusion with one level (no pyramid): pinned on the reference's output"""
+    tiles, pos, out_hw, _, _, _ = fuse_case(golden, "ragged")
+    got = oracle.fusion_oracle.laplacian_fuse(tiles, pos, out_hw, 1, "linear", "c")
+    assert np.array_equal(got, golden["wavg_ragged_out"])
+    t4 = [golden[f"fuse_linear6_t{i}"] for i in range(4)]
+    got = oracle.fusion_oracle.laplacian_fuse(t4, [(0, 0), (0, 64), (64, 0), (64, 64)], (128, 128), 1, "cosine", "c")
+    assert np.array_equal(got, golden["wavg_grid_out"])
