@@ -259,7 +259,8 @@ class BlendingModule:
         return canvas
 
     def fuse_and_assess(self, tiles, reference: np.ndarray, output_shape=None,
-                        weight_type: WeightType = WeightType.COSINE, data_range: float = 255.0, out=None, row_range=None):
+                        weight_type: WeightType = WeightType.COSINE, data_range: float = 255.0, out=None, row_range=None,
+                        _levels: Optional[int] = None):
         """Host tiles -> (fused canvas, srf_iqa_sums of canvas vs `reference`) in one library call: stage 3 + stage 4
         of the reference pipeline with the canvas kept on the device in between (include/srfuse.h:
         srf_fuse_assess_host)."""
@@ -282,7 +283,8 @@ class BlendingModule:
             canvas = np.empty(shape, np.uint8) if (r0, r1) == (0, out_h) else np.zeros(shape, np.uint8)
         sums = _native.srf_iqa_sums()
         lib, ctx = _native.load(), self._ctx()
-        rc = lib.srf_fuse_assess_host(ctx, c_tiles, len(views), chans, self.num_levels, c_luts, len(c_luts), out_h, out_w,
+        rc = lib.srf_fuse_assess_host(ctx, c_tiles, len(views), chans, self.num_levels if _levels is None else int(_levels),
+                                      c_luts, len(c_luts), out_h, out_w,
                                       canvas.ctypes.data, out_w * chans, ref.ptr, ref.pitch, float(data_range), r0, r1, C.byref(sums))
         _native.check(rc, ctx)
         return canvas, sums

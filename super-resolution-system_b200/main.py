@@ -118,12 +118,21 @@ class SuperResolutionPipeline:
             ref = reference if reference is not None else bicubic_stub(image, canvas_hw)
             canvas, report = self.fuse_and_assess(infos, ref, canvas_hw)
         else:
-            canvas, report = self.blending_module.laplacian_fusion(infos, output_shape=canvas_hw), None
+            bm = self.blending_module
+            if bm.method.value == "poisson":
+                raise NotImplementedError("blend_method='poisson' is outside the B200 hot path (SURVEY.md section 8)")
+            fuse = bm.weighted_average_fusion if bm.method.value == "weighted" else bm.laplacian_fusion
+            canvas, report = fuse(infos, output_shape=canvas_hw), None
         return {"canvas": canvas, "report": report, "tiles": len(tiles)}
 
     def fuse_and_assess(self, tile_infos: List[TileInfo], reference: np.ndarray, output_shape=None, out=None):
         """stages 3 + 4 in one device round trip: fused canvas + the full-reference report against `reference`"""
-        canvas, sums = self.blending_module.fuse_and_assess(tile_infos, np.ascontiguousarray(reference), output_shape, out=out)
+        method = self.blending_module.method.value  # PipelineConfig.blend_method (main.py:61): laplacian | weighted | poisson
+        if method == "poisson":
+            raise NotImplementedError("blend_method='poisson' is outside the B200 hot path (SURVEY.md section 8)")
+        levels = 1 if method == "weighted" else None  # weighted average == the gather with a single level
+        canvas, sums = self.blending_module.fuse_and_assess(tile_infos, np.ascontiguousarray(reference), output_shape, out=out,
+                                                            _levels=levels)
         if sums.bits_a <= 1 or sums.bits_b <= 1:  # the reference's max() <= 1 rescale rule: take the two-pass route
             return canvas, self.quality_module.evaluate_full_reference(reference, canvas, scale_factor=2)
         if sums.ssim_count <= 0:

@@ -271,6 +271,10 @@ def test_pipeline_run_small(srs, oracle):
     res = pipe.run(src)
     assert res["canvas"].shape == (360, 640, 3) and res["tiles"] >= 2
     assert 0 < res["report"]["ms_ssim"] <= 1
+    cfg_w = srs.PipelineConfig(block_size=128, overlap_ratio=0.25, target_resolution="640x360", blend_method="weighted")
+    res_w = srs.SuperResolutionPipeline(cfg_w).run(src)
+    assert res_w["canvas"].shape == (360, 640, 3) and not np.array_equal(res_w["canvas"], res["canvas"])
+    assert res_w["report"]["psnr"] > res["report"]["psnr"] - 20
 
 
 def test_fuse_and_assess_band_pipeline_equals_two_calls(srs):
