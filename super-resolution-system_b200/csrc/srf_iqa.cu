@@ -12,6 +12,10 @@
 // Per-CTA partials are reduced by a second single-CTA kernel in a fixed order, so results are deterministic.
 #include "srf_common.cuh"
 
+#ifndef SRF_IQA_TWO_COLUMNS
+#define SRF_IQA_TWO_COLUMNS 1 // 1: k_psnr_ssim2 (two S-map columns per thread), 0: k_psnr_ssim (one)
+#endif
+
 namespace {
 
 constexpr int IQ_THREADS = 128;
@@ -306,6 +310,249 @@ __global__ void __launch_bounds__(IQ_THREADS, 5) k_psnr_ssim(IqaParams P)
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// k_psnr_ssim2: same pipeline, TWO S-map columns per thread (256 columns per 128-thread CTA).  The two windows overlap
+// in all but one tap, so the gray samples are read as float2 (6 LDS.64 per image instead of 22 LDS.32 for two pixels)
+// and the per-tap products a^2+b^2, ab are formed once for both columns (36 instead of 66); halo, staging and loop
+// overhead are shared by twice the pixels.  Costs 88 ring registers.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int IQ2_COLS = 2 * IQ_THREADS;                 // 256 S-map columns per CTA
+constexpr int IQ2_PX = IQ2_COLS + 2 * IQ_R;              // 266 staged pixels per row
+constexpr int IQ2_RAW = ((15 + IQ2_PX * 3 + 15) / 16) * 16; // 832 raw bytes per row and image
+constexpr int IQ2_SROW = IQ2_PX + 6;                     // 272 gray floats per row
+
+template <int C, bool ANYSCALE, int R>
+__global__ void __launch_bounds__(IQ_THREADS, 3) k_psnr_ssim2(IqaParams P)
+{
+    __shared__ __align__(16) uint8_t s_raw[4][2][IQ2_RAW];
+    __shared__ __align__(16) float s_a[2][IQ2_SROW];
+    __shared__ __align__(16) float s_b[2][IQ2_SROW];
+    __shared__ double s_red[IQ_THREADS / 32];
+    __shared__ unsigned long long s_sq[IQ_THREADS / 32];
+    __shared__ unsigned long long s_cnt[IQ_THREADS / 32];
+    __shared__ int s_mx[2][IQ_THREADS / 32];
+
+    constexpr int TAPS = 2 * R + 1;
+    const int t = threadIdx.x;
+    const int cx0 = blockIdx.x * IQ2_COLS;
+    const int ry0 = P.row_begin + blockIdx.y * P.rb;
+    const int ry1 = min(ry0 + P.rb, P.row_end);
+    const int h = P.h, w = P.w;
+    const int r_first = ry0 - R, r_last = ry1 + R; // input rows [r_first, r_last)
+    const long long col_off = (long long)(cx0 - IQ_R) * C;
+
+    // ---- loader role: threads 0..51 -> image a, 52..103 -> image b, one 16-byte chunk each per row ----
+    constexpr int NCH = IQ2_RAW / 16;
+    const bool loader = t < 2 * NCH;
+    const int limg = (t >= NCH) ? 1 : 0, lchunk = t - limg * NCH;
+    const uint8_t *lbase = limg ? P.b : P.a;
+    const long long lpitch = (long long)(limg ? P.pitch_b : P.pitch_a);
+    const int vr0 = max(P.row_begin - IQ_R, 0), vr1 = min(P.row_end + IQ_R, h);
+    const uint8_t *llo = lbase + (long long)vr0 * lpitch;
+    const uint8_t *lhi = lbase + (long long)(vr1 - 1) * lpitch + (long long)w * C;
+    auto L = [&](int r) {
+        if (loader && r >= vr0 && r < vr1 && r < r_last) {
+            const uint8_t *A = lbase + (long long)r * lpitch + col_off;
+            const uint8_t *q = A - (reinterpret_cast<uintptr_t>(A) & 15) + 16 * lchunk;
+            uint8_t *dst = &s_raw[(r - r_first) & 3][limg][16 * lchunk];
+            if (q >= llo && q + 16 <= lhi) {
+                cp_async_16(dst, q);
+            } else if (q + 16 > llo && q < lhi) { // image edge: guarded bytes
+                uint4 v = make_uint4(0, 0, 0, 0);
+                uint8_t *bv = reinterpret_cast<uint8_t *>(&v);
+#pragma unroll 1
+                for (int e = 0; e < 16; ++e)
+                    if (q + e >= llo && q + e < lhi) bv[e] = q[e];
+                *reinterpret_cast<uint4 *>(dst) = v;
+            }
+        }
+        cp_async_commit();
+    };
+
+    unsigned int sq = 0; // <= 128 rows * 4 px * 3 * 65025 < 2^32
+    int bits_a = 0, bits_b = 0;
+    const int mis_a0 = (int)((reinterpret_cast<uintptr_t>(P.a) + (unsigned long long)col_off) & 15);
+    const int mis_b0 = (int)((reinterpret_cast<uintptr_t>(P.b) + (unsigned long long)col_off) & 15);
+    const int pa16 = (int)(P.pitch_a & 15), pb16 = (int)(P.pitch_b & 15);
+    // staged pixel i sits at image column cx0 - 5 + i; thread t converts pixels 2t, 2t+1 and (t < 5) 256+2t, 257+2t
+    auto G = [&](int r) {
+        const int buf = r & 1;
+        float ga[4] = {0.f, 0.f, 0.f, 0.f}, gb[4] = {0.f, 0.f, 0.f, 0.f};
+        if (r >= 0 && r < h) {
+            const int st = (r - r_first) & 3;
+            const uint8_t *ra = &s_raw[st][0][(mis_a0 + r * pa16) & 15];
+            const uint8_t *rb = &s_raw[st][1][(mis_b0 + r * pb16) & 15];
+            const bool rown = r >= ry0 && r < ry1;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (u >= 2 && t >= IQ_R) break;
+                const int i = (u < 2) ? 2 * t + u : IQ2_COLS + 2 * t + (u - 2);
+                const int colp = cx0 - IQ_R + i;
+                int va[C], vb[C], da = 0, db = 0;
+                ga[u] = (float)(gray_of<C, ANYSCALE>(ra + i * C, P.scale_a, da, va) - 128);
+                gb[u] = (float)(gray_of<C, ANYSCALE>(rb + i * C, P.scale_b, db, vb) - 128);
+                if (rown && colp >= cx0 && colp < cx0 + IQ2_COLS && colp < w) {
+                    bits_a |= da;
+                    bits_b |= db;
+#pragma unroll
+                    for (int c = 0; c < C; ++c) {
+                        const int d = va[c] - vb[c];
+                        sq += (unsigned)(d * d);
+                    }
+                }
+            }
+        }
+        *reinterpret_cast<float2 *>(&s_a[buf][2 * t]) = make_float2(ga[0], ga[1]);
+        *reinterpret_cast<float2 *>(&s_b[buf][2 * t]) = make_float2(gb[0], gb[1]);
+        if (t < IQ_R) {
+            *reinterpret_cast<float2 *>(&s_a[buf][IQ2_COLS + 2 * t]) = make_float2(ga[2], ga[3]);
+            *reinterpret_cast<float2 *>(&s_b[buf][IQ2_COLS + 2 * t]) = make_float2(gb[2], gb[3]);
+        }
+    };
+
+    float ring[2][4][TAPS];
+#pragma unroll
+    for (int q = 0; q < 2; ++q)
+#pragma unroll
+        for (int s = 0; s < 4; ++s)
+#pragma unroll
+            for (int k = 0; k < TAPS; ++k) ring[q][s][k] = 0.f;
+
+    float ssum = 0.f;
+    unsigned int scount = 0;
+    const int col0 = cx0 + 2 * t; // this thread's two S-map columns: col0, col0 + 1
+    const bool ci0 = col0 >= R && col0 < w - R, ci1 = col0 + 1 >= R && col0 + 1 < w - R;
+    const float C1 = P.c1, C2 = P.c2;
+
+    L(r_first);
+    L(r_first + 1);
+    L(r_first + 2);
+    L(r_first + 3);
+    cp_async_wait<2>();
+    __syncthreads();
+    G(r_first);
+    __syncthreads();
+
+#pragma unroll 1
+    for (int r_in = r_first; r_in < r_last; ++r_in) {
+        const int buf = r_in & 1;
+        L(r_in + 4);
+        {
+            // gray samples 2t + (5 - R) .. + TAPS (TAPS + 1 values, even start -> float2 loads)
+            float xa[TAPS + 1], xb[TAPS + 1];
+            const float2 *pa = reinterpret_cast<const float2 *>(&s_a[buf][2 * t + (IQ_R - R) - ((IQ_R - R) & 1)]);
+            const float2 *pb = reinterpret_cast<const float2 *>(&s_b[buf][2 * t + (IQ_R - R) - ((IQ_R - R) & 1)]);
+            constexpr int OFF = (IQ_R - R) & 1; // 0 for R = 5 and R = 3
+            constexpr int NV = (TAPS + 1 + OFF + 1) / 2;
+            float ta[2 * NV], tb[2 * NV];
+#pragma unroll
+            for (int k = 0; k < NV; ++k) {
+                const float2 va = pa[k], vb = pb[k];
+                ta[2 * k] = va.x; ta[2 * k + 1] = va.y;
+                tb[2 * k] = vb.x; tb[2 * k + 1] = vb.y;
+            }
+#pragma unroll
+            for (int k = 0; k <= TAPS; ++k) {
+                xa[k] = ta[k + OFF];
+                xb[k] = tb[k + OFF];
+            }
+            float h0a = 0.f, h0b = 0.f, h0s = 0.f, h0p = 0.f, h1a = 0.f, h1b = 0.f, h1s = 0.f, h1p = 0.f;
+#pragma unroll
+            for (int k = 0; k <= TAPS; ++k) {
+                const float a = xa[k], b = xb[k];
+                const float ss = fmaf(a, a, b * b), pp = a * b;
+                if (k < TAPS) { // column 0 uses samples 0 .. TAPS-1 with taps 0 .. TAPS-1
+                    h0a = fmaf(a, iq_tap<R>(k), h0a);
+                    h0b = fmaf(b, iq_tap<R>(k), h0b);
+                    h0s = fmaf(ss, iq_tap<R>(k), h0s);
+                    h0p = fmaf(pp, iq_tap<R>(k), h0p);
+                }
+                if (k > 0) { // column 1 uses samples 1 .. TAPS with taps 0 .. TAPS-1
+                    h1a = fmaf(a, iq_tap<R>(k - 1), h1a);
+                    h1b = fmaf(b, iq_tap<R>(k - 1), h1b);
+                    h1s = fmaf(ss, iq_tap<R>(k - 1), h1s);
+                    h1p = fmaf(pp, iq_tap<R>(k - 1), h1p);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 2; ++q)
+#pragma unroll
+                for (int s = 0; s < 4; ++s)
+#pragma unroll
+                    for (int k = 0; k < TAPS - 1; ++k) ring[q][s][k] = ring[q][s][k + 1];
+            ring[0][0][TAPS - 1] = h0a; ring[0][1][TAPS - 1] = h0b; ring[0][2][TAPS - 1] = h0s; ring[0][3][TAPS - 1] = h0p;
+            ring[1][0][TAPS - 1] = h1a; ring[1][1][TAPS - 1] = h1b; ring[1][2][TAPS - 1] = h1s; ring[1][3][TAPS - 1] = h1p;
+        }
+        const int r = r_in - R;
+        if (r >= ry0) {
+            const bool row_ok = r >= R && r < h - R;
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                float f[4];
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {
+                    float v = 0.f;
+#pragma unroll
+                    for (int k = 0; k < TAPS; ++k) v = fmaf(ring[q][s][k], iq_tap<R>(k), v);
+                    f[s] = v;
+                }
+                const float ua = f[0], ub = f[1];
+                const float ux = ua + 128.f, uy = ub + 128.f;
+                const float vsum = P.cov_norm * (f[2] - fmaf(ua, ua, ub * ub));
+                const float vxy = P.cov_norm * (f[3] - ua * ub);
+                const float A1 = fmaf(2.f * ux, uy, C1), A2 = fmaf(2.f, vxy, C2);
+                const float B1 = fmaf(ux, ux, fmaf(uy, uy, C1)), B2 = vsum + C2;
+                const float S = __fdividef(A1 * A2, B1 * B2);
+                if (row_ok && (q ? ci1 : ci0)) {
+                    ssum += S;
+                    scount++;
+                }
+            }
+        }
+        if (r_in + 1 < r_last) G(r_in + 1);
+        cp_async_wait<2>();
+        __syncthreads();
+    }
+    cp_async_wait<0>();
+
+    double ds = (double)ssum;
+    unsigned long long dsq = sq, dcnt = scount;
+    int mxa = bits_a, mxb = bits_b;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        ds += __shfl_down_sync(0xffffffffu, ds, o);
+        dsq += __shfl_down_sync(0xffffffffu, dsq, o);
+        dcnt += __shfl_down_sync(0xffffffffu, dcnt, o);
+        mxa |= __shfl_down_sync(0xffffffffu, mxa, o);
+        mxb |= __shfl_down_sync(0xffffffffu, mxb, o);
+    }
+    if ((t & 31) == 0) {
+        s_red[t >> 5] = ds;
+        s_sq[t >> 5] = dsq;
+        s_cnt[t >> 5] = dcnt;
+        s_mx[0][t >> 5] = mxa;
+        s_mx[1][t >> 5] = mxb;
+    }
+    __syncthreads();
+    if (t == 0) {
+        IqaPartial p;
+        p.ssim = 0;
+        p.sq = 0;
+        p.cnt = 0;
+        p.max_a = 0;
+        p.max_b = 0;
+        for (int k = 0; k < IQ_THREADS / 32; ++k) {
+            p.ssim += s_red[k];
+            p.sq += s_sq[k];
+            p.cnt += s_cnt[k];
+            p.max_a |= s_mx[0][k];
+            p.max_b |= s_mx[1][k];
+        }
+        P.partials[blockIdx.y * gridDim.x + blockIdx.x] = p;
+    }
+}
+
 // single CTA, fixed summation order: thread k sums partials k, k+256, ... then a shared-memory tree
 __global__ void __launch_bounds__(256) k_iqa_reduce(const IqaPartial *__restrict__ parts, int n, IqaPartial *__restrict__ out, double *__restrict__ dsum)
 {
@@ -357,7 +604,7 @@ int srf_iqa_enqueue(srf_ctx *ctx, const uint8_t *a, size_t pa, const uint8_t *b,
 {
     int rc;
     // tall CTAs amortise the vertical halo; short ones keep small bands (multi-GPU) from ending in a half-empty wave
-    const int gx = srf_ceil_div(w, IQ_THREADS);
+    const int gx = srf_ceil_div(w, SRF_IQA_TWO_COLUMNS ? IQ2_COLS : IQ_THREADS);
     const int rb = (gx * srf_ceil_div(row_end - row_begin, IQ_RB_MAX) >= 6 * 5 * ctx->sm_count) ? IQ_RB_MAX : IQ_RB_MAX / 2;
     const int gy = srf_ceil_div(row_end - row_begin, rb);
     const size_t nparts = (size_t)gx * gy;
@@ -385,7 +632,11 @@ int srf_iqa_enqueue(srf_ctx *ctx, const uint8_t *a, size_t pa, const uint8_t *b,
         dim3 grid(gx, gy);
         srf_launch_scope scope(ctx, "psnr_ssim", 2.0 * (double)(row_end - row_begin) * w * C, st);
         const bool any = scale_a || scale_b; // the rare max() <= 1 rescale: generic instantiation
+#if SRF_IQA_TWO_COLUMNS
+#define IQ_LAUNCH(CC, ANY, RR) k_psnr_ssim2<CC, ANY, RR><<<grid, IQ_THREADS, 0, st>>>(P)
+#else
 #define IQ_LAUNCH(CC, ANY, RR) k_psnr_ssim<CC, ANY, RR><<<grid, IQ_THREADS, 0, st>>>(P)
+#endif
         if (window == 0) {
             if (C == 3) { if (any) IQ_LAUNCH(3, true, 5); else IQ_LAUNCH(3, false, 5); }
             else        { if (any) IQ_LAUNCH(1, true, 5); else IQ_LAUNCH(1, false, 5); }
