@@ -1,28 +1,22 @@
-// srf_iqa.cu -- full-reference PSNR + Gaussian SSIM in one pass over an image pair (replaces
-// QualityAssessmentModule.calculate_psnr / calculate_ssim(multiscale=True),
-// /root/reference/quality_assessment_module.py:277-320, 322-376; arithmetic of scikit-image's
-// peak_signal_noise_ratio / structural_similarity(gaussian_weights=True, sigma=1.5, use_sample_covariance=False)).
+// srf_iqa.cu -- full-reference PSNR + SSIM in one pass over an image pair (replaces
+// QualityAssessmentModule.calculate_psnr / calculate_ssim, /root/reference/quality_assessment_module.py:277-320,
+// 322-389; arithmetic of scikit-image's peak_signal_noise_ratio / structural_similarity: 11x11 Gaussian window with
+// population covariance for multiscale=True, the default 7x7 uniform window with sample covariance otherwise).
 //
-// Each CTA owns a 128-column strip x IQ_RB rows of the S map and streams DOWN the rows: per input row it
-//   * reads the RGB bytes of both images once (sum of squared differences and the running max are taken here),
+// Each CTA owns a 256-column strip x P.rb rows of the S map and streams DOWN the rows: per input row it
+//   * reads the RGB bytes of both images once (sum of squared differences and the OR of the bytes are taken here),
 //   * converts to gray with cv2's 15-bit fixed point, keeps (gray - 128) as float in a double-buffered smem row,
-//   * runs the horizontal 11-tap pass for 4 signals {a, b, a^2 + b^2, a*b} (SSIM needs vx + vy, never each alone),
-//   * pushes the 4 results into an 11-deep register ring and runs the vertical 11-tap pass from registers.
-// 6 B/px of HBM traffic against ~120 FP32 instructions/px: FP32-issue bound, not HBM bound.
+//   * runs the horizontal pass for 4 signals {a, b, a^2 + b^2, a*b} (SSIM needs vx + vy, never each alone),
+//   * pushes the 4 results into a register shift ring and runs the vertical pass from registers.
+// 6 B/px of HBM traffic against ~130 FP32 instructions/px: FP32-issue bound, not HBM bound.
 // Per-CTA partials are reduced by a second single-CTA kernel in a fixed order, so results are deterministic.
 #include "srf_common.cuh"
-
-#ifndef SRF_IQA_TWO_COLUMNS
-#define SRF_IQA_TWO_COLUMNS 1 // 1: k_psnr_ssim2 (two S-map columns per thread), 0: k_psnr_ssim (one)
-#endif
 
 namespace {
 
 constexpr int IQ_THREADS = 128;
 constexpr int IQ_RB_MAX = 128; // S-map rows per CTA: 128 (halo re-filtering 8 % at R = 5) or 64 when the grid would be too small
 constexpr int IQ_R = 5;      // staging halo = radius of the widest window (11-tap Gaussian)
-constexpr int IQ_SROW = IQ_THREADS + 2 * IQ_R + 2; // staged gray columns (+2 keeps rows 16-byte multiples)
-constexpr int IQ_RAW = 448;                         // staged raw bytes per row and image: 15 + 138 * 3 rounded up to 16
 
 // exp(-k^2 / (2 * 1.5^2)) normalised, k = -5..5 (scipy.ndimage._gaussian_kernel1d(1.5, 0, 5))
 #define IQ_T0 1.028380084e-03f
@@ -78,244 +72,18 @@ __device__ __forceinline__ int gray_of(const uint8_t *p, int scale, int &bits, i
     return (v[0] * 9798 + v[C > 1 ? 1 : 0] * 19235 + v[C > 2 ? 2 : 0] * 3735 + 16384) >> 15; // cv2 COLOR_RGB2GRAY, uint8
 }
 
-// Per CTA: 128 S-map columns x IQ_RB rows, streamed DOWN the rows with one barrier per row:
-//   L(r+4) cp.async (LDGSTS) 16-byte copies of the raw RGB bytes of both images into a 4-stage smem ring (56 loader
+// ------------------------------------------------------------------------------------------------------------
+// k_psnr_ssim: per CTA 256 S-map columns x P.rb rows, streamed DOWN the rows with one barrier per row:
+//   L(r+4) cp.async (LDGSTS) 16-byte copies of the raw RGB bytes of both images into a 4-stage smem ring (104 loader
 //          threads, no registers held across the latency; image-edge chunks take a guarded byte path)
 //   G(r+1) raw bytes -> gray float row (+ exact squared error and the OR of the bytes for the owned pixels)
-//   H(r)   horizontal 11-tap of {a, b, a^2+b^2, ab} into an 11-deep register ring, vertical 11-tap, SSIM, accumulate
+//   H(r)   horizontal taps of {a, b, a^2+b^2, ab} into a register SHIFT ring (slot 0 = oldest row; a phase-unrolled
+//          ring overflowed the instruction cache), vertical taps, SSIM, accumulate
+// TWO S-map columns per thread: the two windows overlap in all but one tap, so the gray samples are read as float2
+// (6 LDS.64 per image for two pixels) and the per-tap products a^2+b^2, ab are formed once for both columns; halo,
+// staging and loop overhead are shared by twice the pixels.  Costs 88 ring registers (4 CTAs of 128 threads per SM).
 // ANYSCALE: an image is rescaled by 255 first (the reference's max() <= 1 rule, P.scale_a / P.scale_b) -- a separate
-// instantiation so the common case carries no dead arithmetic.
-template <int C, bool ANYSCALE, int R>
-__global__ void __launch_bounds__(IQ_THREADS, 5) k_psnr_ssim(IqaParams P)
-{
-    __shared__ __align__(16) uint8_t s_raw[4][2][IQ_RAW];
-    __shared__ float s_a[2][IQ_SROW];
-    __shared__ float s_b[2][IQ_SROW];
-    __shared__ double s_red[IQ_THREADS / 32];
-    __shared__ unsigned long long s_sq[IQ_THREADS / 32];
-    __shared__ unsigned long long s_cnt[IQ_THREADS / 32];
-    __shared__ int s_mx[2][IQ_THREADS / 32];
-
-    constexpr int TAPS = 2 * R + 1;
-    const int t = threadIdx.x;
-    const int cx0 = blockIdx.x * IQ_THREADS;
-    const int ry0 = P.row_begin + blockIdx.y * P.rb;
-    const int ry1 = min(ry0 + P.rb, P.row_end);
-    const int h = P.h, w = P.w;
-    const int col1 = cx0 - IQ_R + t;              // every thread's first pixel
-    const int col2 = cx0 + IQ_THREADS - IQ_R + t; // threads 0..9: the right halo
-    const bool has2 = t < 2 * IQ_R;
-    const bool own1 = col1 >= cx0 && col1 < w; // owned = inside this CTA's strip (for the PSNR sum)
-    const bool own2 = has2 && col2 < cx0 + IQ_THREADS && col2 < w;
-    const int r_first = ry0 - R, r_last = ry1 + R; // input rows [r_first, r_last)
-    const long long col_off = (long long)(cx0 - IQ_R) * C;
-
-    // ---- loader role: threads 0..27 -> image a, 28..55 -> image b, one 16-byte chunk each per row ----
-    constexpr int NCH = IQ_RAW / 16;
-    const bool loader = t < 2 * NCH;
-    const int limg = (t >= NCH) ? 1 : 0, lchunk = t - limg * NCH;
-    const uint8_t *lbase = limg ? P.b : P.a;
-    const long long lpitch = (long long)(limg ? P.pitch_b : P.pitch_a);
-    // bytes this launch may touch: rows [row_begin - 5, row_end + 5) of the image, clipped (a band-staged image only
-    // holds those rows)
-    const int vr0 = max(P.row_begin - IQ_R, 0), vr1 = min(P.row_end + IQ_R, h);
-    const uint8_t *llo = lbase + (long long)vr0 * lpitch;
-    const uint8_t *lhi = lbase + (long long)(vr1 - 1) * lpitch + (long long)w * C;
-    auto L = [&](int r) {
-        if (loader && r >= vr0 && r < vr1 && r < r_last) {
-            const uint8_t *A = lbase + (long long)r * lpitch + col_off;
-            const uint8_t *q = A - (reinterpret_cast<uintptr_t>(A) & 15) + 16 * lchunk;
-            uint8_t *dst = &s_raw[(r - r_first) & 3][limg][16 * lchunk];
-            if (q >= llo && q + 16 <= lhi) {
-                cp_async_16(dst, q);
-            } else if (q + 16 > llo && q < lhi) { // image edge: guarded bytes
-                uint4 v = make_uint4(0, 0, 0, 0);
-                uint8_t *bv = reinterpret_cast<uint8_t *>(&v);
-#pragma unroll 1
-                for (int e = 0; e < 16; ++e)
-                    if (q + e >= llo && q + e < lhi) bv[e] = q[e];
-                *reinterpret_cast<uint4 *>(dst) = v;
-            }
-        }
-        cp_async_commit();
-    };
-
-    unsigned int sq = 0; // <= 128 rows * 2 px * 3 * 65025 < 2^32
-    int bits_a = 0, bits_b = 0;
-    const int mis_a0 = (int)((reinterpret_cast<uintptr_t>(P.a) + (unsigned long long)col_off) & 15);
-    const int mis_b0 = (int)((reinterpret_cast<uintptr_t>(P.b) + (unsigned long long)col_off) & 15);
-    const int pa16 = (int)(P.pitch_a & 15), pb16 = (int)(P.pitch_b & 15);
-    auto G = [&](int r) {
-        const int buf = r & 1;
-        float ga1 = 0.f, gb1 = 0.f, ga2 = 0.f, gb2 = 0.f;
-        if (r >= 0 && r < h) {
-            const int st = (r - r_first) & 3;
-            const uint8_t *ra = &s_raw[st][0][(mis_a0 + r * pa16) & 15];
-            const uint8_t *rb = &s_raw[st][1][(mis_b0 + r * pb16) & 15];
-            const bool rown = r >= ry0 && r < ry1;
-            int va[C], vb[C], da = 0, db = 0;
-            ga1 = (float)(gray_of<C, ANYSCALE>(ra + t * C, P.scale_a, da, va) - 128);
-            gb1 = (float)(gray_of<C, ANYSCALE>(rb + t * C, P.scale_b, db, vb) - 128);
-            if (rown && own1) {
-                bits_a |= da;
-                bits_b |= db;
-#pragma unroll
-                for (int c = 0; c < C; ++c) {
-                    const int d = va[c] - vb[c];
-                    sq += (unsigned)(d * d);
-                }
-            }
-            if (has2) {
-                da = db = 0;
-                ga2 = (float)(gray_of<C, ANYSCALE>(ra + (IQ_THREADS + t) * C, P.scale_a, da, va) - 128);
-                gb2 = (float)(gray_of<C, ANYSCALE>(rb + (IQ_THREADS + t) * C, P.scale_b, db, vb) - 128);
-                if (rown && own2) {
-                    bits_a |= da;
-                    bits_b |= db;
-#pragma unroll
-                    for (int c = 0; c < C; ++c) {
-                        const int d = va[c] - vb[c];
-                        sq += (unsigned)(d * d);
-                    }
-                }
-            }
-        }
-        s_a[buf][t] = ga1;
-        s_b[buf][t] = gb1;
-        if (has2) {
-            s_a[buf][IQ_THREADS + t] = ga2;
-            s_b[buf][IQ_THREADS + t] = gb2;
-        }
-    };
-
-    float ring[4][TAPS];
-#pragma unroll
-    for (int s = 0; s < 4; ++s)
-#pragma unroll
-        for (int k = 0; k < TAPS; ++k) ring[s][k] = 0.f;
-
-    float ssum = 0.f;
-    unsigned int scount = 0;
-    const int col = cx0 + t; // this thread's S-map column
-    const bool col_interior = col >= R && col < w - R;
-    const float C1 = P.c1, C2 = P.c2;
-
-    // prologue: rows r_first .. r_first+3 in flight; gray(r_first) ready and raw(r_first+1) published
-    L(r_first);
-    L(r_first + 1);
-    L(r_first + 2);
-    L(r_first + 3);
-    cp_async_wait<2>();
-    __syncthreads();
-    G(r_first);
-    __syncthreads();
-
-    // The ring is a register SHIFT ring (slot 0 = oldest row): 4 x (TAPS-1) moves per row buy a loop body that exists
-    // once instead of TAPS times -- the phase-unrolled form overflowed the instruction cache (ncu: `no_instruction`
-    // was the top stall).
-#pragma unroll 1
-    for (int r_in = r_first; r_in < r_last; ++r_in) {
-        const int buf = r_in & 1;
-        L(r_in + 4);
-
-        // H(r): horizontal pass on gray row r_in -- four FMA chains with literal taps, products formed once per tap
-        {
-            float ha = 0.f, hb = 0.f, hs = 0.f, hp = 0.f;
-            const float *pa = &s_a[buf][t + (IQ_R - R)], *pb = &s_b[buf][t + (IQ_R - R)];
-#pragma unroll
-            for (int k = 0; k < TAPS; ++k) {
-                const float a = pa[k], b = pb[k];
-                ha = fmaf(a, iq_tap<R>(k), ha);
-                hb = fmaf(b, iq_tap<R>(k), hb);
-                hs = fmaf(fmaf(a, a, b * b), iq_tap<R>(k), hs);
-                hp = fmaf(a * b, iq_tap<R>(k), hp);
-            }
-#pragma unroll
-            for (int k = 0; k < TAPS - 1; ++k) {
-                ring[0][k] = ring[0][k + 1];
-                ring[1][k] = ring[1][k + 1];
-                ring[2][k] = ring[2][k + 1];
-                ring[3][k] = ring[3][k + 1];
-            }
-            ring[0][TAPS - 1] = ha;
-            ring[1][TAPS - 1] = hb;
-            ring[2][TAPS - 1] = hs;
-            ring[3][TAPS - 1] = hp;
-        }
-
-        // vertical pass: output row r = r_in - R uses input rows r_in-2R .. r_in = ring slots 0 .. TAPS-1
-        const int r = r_in - R;
-        if (r >= ry0) {
-            float f[4];
-#pragma unroll
-            for (int s = 0; s < 4; ++s) {
-                float v = 0.f;
-#pragma unroll
-                for (int k = 0; k < TAPS; ++k) v = fmaf(ring[s][k], iq_tap<R>(k), v);
-                f[s] = v;
-            }
-            const float ua = f[0], ub = f[1];
-            const float ux = ua + 128.f, uy = ub + 128.f;
-            const float vsum = P.cov_norm * (f[2] - fmaf(ua, ua, ub * ub)); // vx + vy (shift invariant)
-            const float vxy = P.cov_norm * (f[3] - ua * ub);
-            const float A1 = fmaf(2.f * ux, uy, C1), A2 = fmaf(2.f, vxy, C2);
-            const float B1 = fmaf(ux, ux, fmaf(uy, uy, C1)), B2 = vsum + C2;
-            const float S = __fdividef(A1 * A2, B1 * B2);
-            if (col_interior && r >= R && r < h - R) {
-                ssum += S;
-                scount++;
-            }
-        }
-        if (r_in + 1 < r_last) G(r_in + 1);
-        cp_async_wait<2>(); // row r_in + 2 has landed (this thread's copies); the barrier publishes it
-        __syncthreads();
-    }
-    cp_async_wait<0>();
-
-    // ---- block reduction (fixed order) ----
-    double ds = (double)ssum;
-    unsigned long long dsq = sq, dcnt = scount;
-    int mxa = bits_a, mxb = bits_b;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        ds += __shfl_down_sync(0xffffffffu, ds, o);
-        dsq += __shfl_down_sync(0xffffffffu, dsq, o);
-        dcnt += __shfl_down_sync(0xffffffffu, dcnt, o);
-        mxa |= __shfl_down_sync(0xffffffffu, mxa, o);
-        mxb |= __shfl_down_sync(0xffffffffu, mxb, o);
-    }
-    if ((t & 31) == 0) {
-        s_red[t >> 5] = ds;
-        s_sq[t >> 5] = dsq;
-        s_cnt[t >> 5] = dcnt;
-        s_mx[0][t >> 5] = mxa;
-        s_mx[1][t >> 5] = mxb;
-    }
-    __syncthreads();
-    if (t == 0) {
-        IqaPartial p;
-        p.ssim = 0;
-        p.sq = 0;
-        p.cnt = 0;
-        p.max_a = 0;
-        p.max_b = 0;
-        for (int k = 0; k < IQ_THREADS / 32; ++k) {
-            p.ssim += s_red[k];
-            p.sq += s_sq[k];
-            p.cnt += s_cnt[k];
-            p.max_a |= s_mx[0][k];
-            p.max_b |= s_mx[1][k];
-        }
-        P.partials[blockIdx.y * gridDim.x + blockIdx.x] = p;
-    }
-}
-
-
-// ------------------------------------------------------------------------------------------------------------
-// k_psnr_ssim2: same pipeline, TWO S-map columns per thread (256 columns per 128-thread CTA).  The two windows overlap
-// in all but one tap, so the gray samples are read as float2 (6 LDS.64 per image instead of 22 LDS.32 for two pixels)
-// and the per-tap products a^2+b^2, ab are formed once for both columns (36 instead of 66); halo, staging and loop
-// overhead are shared by twice the pixels.  Costs 88 ring registers.
+// instantiation so the common case carries no dead arithmetic.  R: window radius (5 Gaussian, 3 uniform).
 // ------------------------------------------------------------------------------------------------------------
 constexpr int IQ2_COLS = 2 * IQ_THREADS;                 // 256 S-map columns per CTA
 constexpr int IQ2_PX = IQ2_COLS + 2 * IQ_R;              // 266 staged pixels per row
@@ -323,7 +91,7 @@ constexpr int IQ2_RAW = ((15 + IQ2_PX * 3 + 15) / 16) * 16; // 832 raw bytes per
 constexpr int IQ2_SROW = IQ2_PX + 6;                     // 272 gray floats per row
 
 template <int C, bool ANYSCALE, int R>
-__global__ void __launch_bounds__(IQ_THREADS, 3) k_psnr_ssim2(IqaParams P)
+__global__ void __launch_bounds__(IQ_THREADS, 4) k_psnr_ssim(IqaParams P)
 {
     __shared__ __align__(16) uint8_t s_raw[4][2][IQ2_RAW];
     __shared__ __align__(16) float s_a[2][IQ2_SROW];
@@ -604,7 +372,7 @@ int srf_iqa_enqueue(srf_ctx *ctx, const uint8_t *a, size_t pa, const uint8_t *b,
 {
     int rc;
     // tall CTAs amortise the vertical halo; short ones keep small bands (multi-GPU) from ending in a half-empty wave
-    const int gx = srf_ceil_div(w, SRF_IQA_TWO_COLUMNS ? IQ2_COLS : IQ_THREADS);
+    const int gx = srf_ceil_div(w, IQ2_COLS);
     const int rb = (gx * srf_ceil_div(row_end - row_begin, IQ_RB_MAX) >= 6 * 5 * ctx->sm_count) ? IQ_RB_MAX : IQ_RB_MAX / 2;
     const int gy = srf_ceil_div(row_end - row_begin, rb);
     const size_t nparts = (size_t)gx * gy;
@@ -632,11 +400,7 @@ int srf_iqa_enqueue(srf_ctx *ctx, const uint8_t *a, size_t pa, const uint8_t *b,
         dim3 grid(gx, gy);
         srf_launch_scope scope(ctx, "psnr_ssim", 2.0 * (double)(row_end - row_begin) * w * C, st);
         const bool any = scale_a || scale_b; // the rare max() <= 1 rescale: generic instantiation
-#if SRF_IQA_TWO_COLUMNS
-#define IQ_LAUNCH(CC, ANY, RR) k_psnr_ssim2<CC, ANY, RR><<<grid, IQ_THREADS, 0, st>>>(P)
-#else
 #define IQ_LAUNCH(CC, ANY, RR) k_psnr_ssim<CC, ANY, RR><<<grid, IQ_THREADS, 0, st>>>(P)
-#endif
         if (window == 0) {
             if (C == 3) { if (any) IQ_LAUNCH(3, true, 5); else IQ_LAUNCH(3, false, 5); }
             else        { if (any) IQ_LAUNCH(1, true, 5); else IQ_LAUNCH(1, false, 5); }
