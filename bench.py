@@ -266,7 +266,7 @@ def run_b200(args, wl):
     roofline = {"bound": "hbm", "kernel": top["kernel"], "achieved": top["GBps"], "peak": peak, "unit": "GB/s",
                 "frac": top["frac_of_peak"], "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": top["algorithmic_GB_per_step"] * 1e9 / max(top["launches_per_step"], 1),
-                "note": "final_gather and psnr_ssim are instruction-issue bound (ncu: issue-active 67-68 %, DRAM 15 % / 5 %): "
+                "note": "final_gather and psnr_ssim are instruction-issue bound (ncu: issue-active 65 % / 87 %, DRAM 15 % / 8 %): "
                         "their DRAM traffic equals the algorithmic bytes, the gap to the HBM roofline is arithmetic, not re-reads",
                 "share_of_step": top["ms_per_step"] / (ms_prof / args.steps),
                 "whole_step": {"algorithmic_GB": (wl.tile_bytes + 3 * H * W + 6 * H * W) / 1e9,
