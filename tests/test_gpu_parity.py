@@ -400,3 +400,23 @@ def test_weighted_average_fusion_vs_reference_golden(srs, golden):
     assert np.array_equal(bm.weighted_average_fusion(t4), golden["wavg_grid_out"])  # bare arrays: sqrt-grid, max extents
     with pytest.raises(NotImplementedError):
         bm.weighted_average_fusion(t4, weights=[np.ones((64, 64), np.float32)] * 4)
+
+
+def test_config_sized_two_tile_fuse_and_iqa_vs_oracle(srs, oracle):
+    """BASELINE config geometry at full tile size: two adjacent bicubic-stub tiles of the 200 MP grid (4096^2 each,
+    818-pixel overlap, 7 levels) fused into their 4096 x 7374 canvas and scored on a 1024-row strip, against the oracle"""
+    import workloads
+    wl = workloads.build("cfg4_200mp", max_tiles=2)
+    tiles, pos = wl.tiles, wl.positions_yx
+    assert pos == [(0, 0), (0, 3278)] and tiles[0].shape == (4096, 4096, 3)
+    out_hw = (4096, 3278 + 4096)
+    bm = srs.BlendingModule(num_levels=wl.levels)
+    got = bm.laplacian_fusion([srs.TileInfo(t, x, y, 0, 0) for t, (y, x) in zip(tiles, pos)], output_shape=out_hw)
+    want = oracle.fusion_oracle.laplacian_fuse(tiles, pos, out_hw, wl.levels, "cosine", "cv2" if oracle.pyr.have_cv2() else "c")
+    mx, exact = canvas_agreement(got, want)
+    assert mx <= 1 and exact >= 0.999, (mx, exact)
+    ref = wl.reference[:1024, :out_hw[1]]
+    qa = srs.QualityAssessmentModule()
+    p, s = qa.calculate_psnr_ssim(ref, got[:1024])
+    assert p == pytest.approx(oracle.iqa_oracle.psnr(ref, want[:1024]), rel=1e-4 if exact < 1 else 1e-12)
+    assert s == pytest.approx(oracle.iqa_oracle.ssim(ref, want[:1024]), rel=REL)
