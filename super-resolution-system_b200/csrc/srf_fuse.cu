@@ -1,13 +1,13 @@
 // srf_fuse.cu -- Laplacian-pyramid tile fusion (replaces BlendingModule.laplacian_fusion,
-// /root/reference/blending_module.py:369-506) as five planar-float32 kernels:
+// /root/reference/blending_module.py:369-506) as planar-float32 kernels:
 //
-//   k_down_u8    tile uint8 HWC            -> G_1 (planar f32)                 integer-exact 5x5 / 256
-//   k_down_f32   G_l / W_l (planar f32)    -> G_{l+1} / W_{l+1}                cv2.pyrDown op order
-//                (W_0 is never materialised: the level-0 weight is a 1-D profile looked up by border distance)
-//   k_up_level   C_l = pyrUp(C_{l+1}) + (G_l - pyrUp(G_{l+1})) * W_l          l = n-2 .. 1, one pass per level;
-//                the top level's C = G*W product is folded into the first pass
-//   k_final      canvas gather: for every canvas pixel, in tile-list order, C_0 of each covering tile is rebuilt
-//                from (C_1, G_1, the uint8 tile, W_0) and summed; divide by max(sum W_0, 1e-6), clip, truncate
+//   k_down_u8       tile uint8 HWC          -> G_1 (planar f32)      integer-exact 5x5 / 256, DP4A, register ring
+//   k_down_f32s     G_l / W_l (l >= 1)      -> G_{l+1} / W_{l+1}     cv2.pyrDown op order, TMA-bulk staged row streaming
+//   k_down_weight0  border-distance profile -> W_1                   (W_0 is never materialised; runs once per shape)
+//   k_up_levels     C_l = pyrUp(C_{l+1}) + (G_l - pyrUp(G_{l+1})) * W_l   l = n-3 .. 1, one streaming pass per level
+//   k_up_level_top  the same for l = n-2, with C_{n-1} = G_{n-1} * W_{n-1} formed on the fly (tiny planes)
+//   k_final         canvas gather: for every canvas pixel, in tile-list order, C_0 of each covering tile is rebuilt
+//                   from (C_1, G_1, the uint8 tile, W_0) and summed; divide by max(sum W_0, 1e-6), clip, truncate
 //
 // Nothing canvas-sized is ever held in float32: the reference's two float accumulators (16 B per canvas pixel,
 // read-modify-written once per tile) become registers in k_final.
@@ -227,12 +227,13 @@ __global__ void __launch_bounds__(128 * C) k_down_u8(const TileDev *__restrict__
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// k_down_f32: one planar f32 level -> the next (cv2.pyrDown op order incl. the SIMD-body / scalar split).
-// WEIGHT=false: source = tile G_l planes (grid.z = tile * C + c);
-// WEIGHT=true : source = group weight plane W_l, or the border-distance profile when l == 0 (grid.z = 1).
+// k_down_weight0: pyrDown of the level-0 weight map into W_1 (cv2.pyrDown op order incl. the SIMD-body / scalar
+// split), with the source generated on the fly from the border-distance profile (l == 0).  Block form (16 x 64
+// outputs per CTA, 2-pass through smem); it runs once per tile shape -- the result is cached across calls -- so it
+// is kept simple.  (It still understands a plane source and tile planes; only the profile source is launched.)
 // ------------------------------------------------------------------------------------------------------------
 template <bool WEIGHT>
-__global__ void __launch_bounds__(kThreads) k_down_f32(const TileDev *__restrict__ tiles, const int *__restrict__ tile_ids, GroupDev g,
+__global__ void __launch_bounds__(kThreads) k_down_weight0(const TileDev *__restrict__ tiles, const int *__restrict__ tile_ids, GroupDev g,
                                                        int l /* source level */)
 {
     __shared__ __align__(16) float s_in[DN_IN_ROWS][DN_IN_COLS_F32];
@@ -329,7 +330,7 @@ __global__ void __launch_bounds__(kThreads) k_down_f32(const TileDev *__restrict
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// pyrUp building blocks shared by k_up_level and k_final.
+// pyrUp building blocks of k_up_level_top.
 // A "source block" is rows [jb, jb + nrows) x cols [ib, ib + UP_SRC_COLS) of a level-(l+1) plane staged in smem.
 // ------------------------------------------------------------------------------------------------------------
 struct SrcWin {
@@ -350,12 +351,13 @@ __device__ __forceinline__ SrcWin src_window(int ty0, int ty1, int tx0, int h1)
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// k_up_level: C_l = pyrUp(C_{l+1}) + (G_l - pyrUp(G_{l+1})) * W_l for 1 <= l <= n-2.
-// TOP: C_{l+1} is not stored; it is G_{l+1} * W_{l+1} (the coarsest Laplacian level is the Gaussian one).
+// k_up_level_top: C_l = pyrUp(C_{l+1}) + (G_l - pyrUp(G_{l+1})) * W_l for l = n-2, where C_{l+1} is not stored: it is
+// G_{l+1} * W_{l+1} (the coarsest Laplacian level is the Gaussian one).  Block form; the planes at this level are tiny
+// (128 x 128 at 7 levels of a 4096 tile).  TOP = false (stored C) is served by the streaming k_up_levels below.
 // grid = (ceil(w_l/64), ceil(rows/32), tile * C + c)
 // ------------------------------------------------------------------------------------------------------------
 template <bool TOP>
-__global__ void __launch_bounds__(kThreads) k_up_level(const TileDev *__restrict__ tiles, const int *__restrict__ tile_ids, GroupDev g, int l)
+__global__ void __launch_bounds__(kThreads) k_up_level_top(const TileDev *__restrict__ tiles, const int *__restrict__ tile_ids, GroupDev g, int l)
 {
     __shared__ __align__(16) float s_c[UP_SRC_ROWS][UP_SRC_COLS];
     __shared__ __align__(16) float s_g[UP_SRC_ROWS][UP_SRC_COLS];
@@ -450,12 +452,12 @@ __global__ void __launch_bounds__(kThreads) k_up_level(const TileDev *__restrict
 
 
 // ------------------------------------------------------------------------------------------------------------
-// k_down_f32s: the streaming form of k_down_f32 for image planes (and W_l, l >= 1).  One CTA = 128 output columns x
+// k_down_f32s: pyrDown of one planar f32 level into the next, for image planes G_l and weight planes W_l (l >= 1).  One CTA = 128 output columns x
 // 32 output rows of one plane, 128 threads: thread x owns output column x and streams DOWN the input rows.  Input
 // rows arrive 8 at a time through cp.async into a double-buffered smem ring; the horizontal 5-tap reads 5 adjacent
 // floats (two LDS.64 + one LDS.32, conflict free), the five most recent horizontal sums live in a register shift
-// ring, every second row emits one output row (128-byte coalesced stores per warp).  Same OpenCV op-order split
-// (SIMD body / scalar border + tail columns) as k_down_f32.
+// ring, every second row emits one output row (128-byte coalesced stores per warp).  OpenCV's op-order split (SIMD
+// body / scalar border + tail columns) is reproduced per column.
 // grid = (ceil(ow/128), ceil(rows/32), planes)
 // ------------------------------------------------------------------------------------------------------------
 constexpr int DF_BW = 128, DF_ROWS = 32, DF_BATCH = 8;
@@ -598,7 +600,7 @@ __global__ void __launch_bounds__(DF_BW) k_down_f32s(const TileDev *__restrict__
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// k_up_levels: the streaming form of k_up_level for the stored-C case (TOP = false).  One CTA = 256 x 32 outputs of
+// k_up_levels: C_l = pyrUp(C_{l+1}) + (G_l - pyrUp(G_{l+1})) * W_l with C_{l+1} stored (every level but the top one).  One CTA = 256 x 32 outputs of
 // one plane, 128 threads: thread p owns output columns 2p, 2p+1 and slides down the rows with a 3-row register ring
 // of horizontally up-sampled (C_{l+1}, G_{l+1}) pairs, exactly like k_final; the <= 19 x 136 source windows arrive by
 // cp.async; G_l, W_l are read and C_l written as float2 (256 contiguous bytes per warp and row).
@@ -1434,7 +1436,7 @@ int srf_fuse_device(srf_ctx *ctx, const srf_tile *tiles, int n_tiles, int C, int
             }
             dim3 grid(srf_ceil_div(gw.lv[l + 1].w, DN_BW), srf_ceil_div(gw.lv[l + 1].h, DN_BH), 1);
             srf_launch_scope scope(ctx, "down_weight", 4.0 * ((l ? (double)gw.lv[l].h * gw.lv[l].w : 0.0) + (double)gw.lv[l + 1].h * gw.lv[l + 1].w), st);
-            k_down_f32<true><<<grid, kThreads, 0, st>>>(d_tiles, ids_k, gw, l);
+            k_down_weight0<true><<<grid, kThreads, 0, st>>>(d_tiles, ids_k, gw, l);
         }
         // image pyramids, down
         if (n >= 2) {
@@ -1469,7 +1471,7 @@ int srf_fuse_device(srf_ctx *ctx, const srf_tile *tiles, int n_tiles, int C, int
             // per output element: G_l + W_l/C read, C_l written, C_{l+1} (or W_{l+1}/C) + G_{l+1} at quarter density
             srf_launch_scope scope(ctx, "up_level", pxo * C * (4.0 + 4.0 / C + 4.0 + 2.0), st);
             if (l == n - 2) {
-                k_up_level<true><<<grid, kThreads, 0, st>>>(d_tiles, ids_k, gi, l);
+                k_up_level_top<true><<<grid, kThreads, 0, st>>>(d_tiles, ids_k, gi, l);
             } else {
                 dim3 sgrid(srf_ceil_div(gi.lv[l].w, UL_W), srf_ceil_div(rows, UL_H), nt * C);
                 k_up_levels<<<sgrid, UL_PAIRS, 0, st>>>(d_tiles, ids_k, gi, l);
