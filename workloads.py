@@ -86,9 +86,3 @@ def build(name: str = "cfg4_200mp", seed: int = 0, max_tiles: int = 0) -> Worklo
     canvas_hw = (2 * half.shape[0], 2 * half.shape[1])
     reference = np.ascontiguousarray(stub_sr(src, canvas_hw))
     return Workload(name, tiles, positions, canvas_hw, levels, reference, grid)
-
-
-def band(rank: int, world: int, rows: int) -> Tuple[int, int]:
-    """horizontal canvas band [r0, r1) owned by `rank`"""
-    per = -(-rows // world)
-    return min(rank * per, rows), min((rank + 1) * per, rows)
