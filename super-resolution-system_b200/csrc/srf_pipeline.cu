@@ -53,8 +53,11 @@ extern "C" int srf_fuse_assess_host(srf_ctx *ctx, const srf_tile *tiles, int n_t
         dt[i].pitch = p;
         total += srf_align_up(p * tiles[i].h, 256);
     }
-    const size_t cpitch = srf_align_up((size_t)out_w * channels, 256);
-    const size_t canvas_bytes = cpitch * (size_t)out_h;
+    // packed device canvas / comparison image when the host side is packed too: the band copies are then plain
+    // contiguous transfers (the gather's congruent 16-byte stores and the IQA loader accept any pitch)
+    const bool packed = canvas_pitch == (size_t)out_w * channels && reference_pitch == (size_t)out_w * channels;
+    const size_t cpitch = packed ? (size_t)out_w * channels : srf_align_up((size_t)out_w * channels, 256);
+    const size_t canvas_bytes = srf_align_up(cpitch * (size_t)out_h, 256);
     if ((rc = srf_reserve(ctx, ctx->ws_stage_in, total))) return rc;
     if ((rc = srf_reserve(ctx, ctx->ws_stage_out, 2 * canvas_bytes))) return rc; // [fused canvas | comparison image]
     if ((rc = srf_reserve_pinned(ctx, 4096))) return rc;
@@ -76,14 +79,26 @@ extern "C" int srf_fuse_assess_host(srf_ctx *ctx, const srf_tile *tiles, int n_t
     rc = srf_fuse_device(ctx, dt.data(), n_tiles, channels, levels, luts, n_luts, out_h, out_w, dcanvas, cpitch, 0, 0, st);
     if (rc) return rc;
 
-    std::vector<cudaEvent_t> ev_up(nb), ev_fused(nb);
+    std::vector<cudaEvent_t> ev_up(nb), ev_fused(nb), ev_ref(nb);
     for (int b = 0; b < nb; ++b) {
         ev_up[b] = take_event(ctx);
         ev_fused[b] = take_event(ctx);
+        ev_ref[b] = take_event(ctx);
     }
-    // ---- upload stream: everything is queued now; the copy engine works through it in band order ----
+    // ---- upload stream: everything is queued now; the copy engine works through it in band order.  Tiles lead, the
+    // comparison image's rows trail by one band: fusing (and downloading) a band only needs its tiles, the assessment
+    // of band b-1 only needs comparison rows up to band b -- so the tail of the call is one small upload + one small
+    // kernel, not a fuse + download.
     std::vector<char> uploaded(n_tiles, 0);
     size_t h2d = 0;
+    auto upload_ref = [&](int b) -> int {
+        const int r0 = band_lo(b), r1 = band_hi(b);
+        if (r1 > r0)
+            SRF_CHECK_CUDA(ctx, cudaMemcpy2DAsync(dref + (size_t)r0 * cpitch, cpitch, h_reference + (size_t)r0 * reference_pitch, reference_pitch,
+                                                  (size_t)out_w * channels, r1 - r0, cudaMemcpyHostToDevice, up));
+        SRF_CHECK_CUDA(ctx, cudaEventRecord(ev_ref[b], up));
+        return SRF_OK;
+    };
     for (int b = 0; b < nb; ++b) {
         const int r0 = band_lo(b), r1 = band_hi(b);
         for (int i = 0; i < n_tiles; ++i) {
@@ -97,11 +112,10 @@ extern "C" int srf_fuse_assess_host(srf_ctx *ctx, const srf_tile *tiles, int n_t
                                                       cudaMemcpyHostToDevice, up));
             }
         }
-        if (r1 > r0)
-            SRF_CHECK_CUDA(ctx, cudaMemcpy2DAsync(dref + (size_t)r0 * cpitch, cpitch, h_reference + (size_t)r0 * reference_pitch, reference_pitch,
-                                                  (size_t)out_w * channels, r1 - r0, cudaMemcpyHostToDevice, up));
         SRF_CHECK_CUDA(ctx, cudaEventRecord(ev_up[b], up));
+        if (b >= 1 && (rc = upload_ref(b - 1))) return rc;
     }
+    if ((rc = upload_ref(nb - 1))) return rc;
     // ---- compute + download ----
     SRF_CHECK_CUDA(ctx, cudaEventRecord(ctx->ev0, st));
     std::vector<srf_tile> sub;
@@ -125,12 +139,14 @@ extern "C" int srf_fuse_assess_host(srf_ctx *ctx, const srf_tile *tiles, int n_t
             SRF_CHECK_CUDA(ctx, cudaMemcpy2DAsync(h_canvas + (size_t)own_lo(b) * canvas_pitch, canvas_pitch, dcanvas + (size_t)own_lo(b) * cpitch,
                                                   cpitch, (size_t)out_w * channels, own_hi(b) - own_lo(b), cudaMemcpyDeviceToHost, dn));
         if (b >= 1 && own_hi(b - 1) > own_lo(b - 1)) {
+            SRF_CHECK_CUDA(ctx, cudaStreamWaitEvent(st, ev_ref[b], 0)); // comparison rows of bands <= b (5-row halo below b-1)
             rc = srf_iqa_enqueue(ctx, dref, cpitch, dcanvas, cpitch, out_h, out_w, channels, 0, 0, data_range, own_lo(b - 1), own_hi(b - 1), st,
                                  b - 1);
             if (rc) return rc;
         }
     }
     if (own_hi(nb - 1) > own_lo(nb - 1)) {
+        SRF_CHECK_CUDA(ctx, cudaStreamWaitEvent(st, ev_ref[nb - 1], 0));
         rc = srf_iqa_enqueue(ctx, dref, cpitch, dcanvas, cpitch, out_h, out_w, channels, 0, 0, data_range, own_lo(nb - 1), own_hi(nb - 1), st,
                              nb - 1);
         if (rc) return rc;
@@ -142,6 +158,7 @@ extern "C" int srf_fuse_assess_host(srf_ctx *ctx, const srf_tile *tiles, int n_t
     for (int b = 0; b < nb; ++b) {
         ctx->ev_pool.push_back(ev_up[b]);
         ctx->ev_pool.push_back(ev_fused[b]);
+        ctx->ev_pool.push_back(ev_ref[b]);
     }
 
     srf_iqa_sums acc;
