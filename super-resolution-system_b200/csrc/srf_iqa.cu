@@ -55,47 +55,71 @@ struct IqaParams {
 };
 
 
+// ---- packed FP32 (sm_100: FFMA2 / FMUL2 issue two IEEE-rounded lanes per instruction; the kernel is issue bound) ----
+__device__ __forceinline__ float2 f2fma(float2 a, float w, float2 c) { return __ffma2_rn(a, make_float2(w, w), c); }
+__device__ __forceinline__ float2 f2mul(float2 a, float w) { return __fmul2_rn(a, make_float2(w, w)); }
+
+// the 2*C bytes of a pixel pair that starts `byte_off` bytes into a 16-byte aligned staged row, shifted down to bit 0:
+// lo = bytes 0..3, hi = bytes 4..7 (C = 3: R0 G0 B0 R1 | G1 B1 x x; C = 1: Y0 Y1 x x | -)
 template <int C, bool ANYSCALE>
-__device__ __forceinline__ int gray_of(const uint8_t *p, int scale, int &bits, int (&v)[C])
+__device__ __forceinline__ void iq_load_pair(const uint8_t *row, int byte_off, int scale, unsigned &lo, unsigned &hi)
 {
-#pragma unroll
-    for (int c = 0; c < C; ++c) {
-        int t = p[c];
-        if (ANYSCALE && scale) t = (t * 255) & 0xFF; // (image * 255).astype(uint8), quality_assessment_module.py:192-193
-        v[c] = t;
+    const unsigned *wp = reinterpret_cast<const unsigned *>(row) + (byte_off >> 2);
+    const int sh = (byte_off & 3) * 8;
+    const unsigned w0 = wp[0], w1 = wp[1];
+    lo = __funnelshift_r(w0, w1, sh);
+    hi = 0u;
+    if (C == 3) hi = __funnelshift_r(w1, wp[2], sh);
+    if (ANYSCALE && scale) { // (image * 255).astype(uint8), quality_assessment_module.py:192-193: (t * 255) & 255 == (-t) & 255
+        lo = __vsub4(0u, lo);
+        hi = __vsub4(0u, hi);
     }
-    if (C == 1) {
-        bits |= v[0];
-        return v[0];
+}
+
+// gray - 128 of both pixels.  cv2 COLOR_RGB2GRAY (uint8): (R*9798 + G*19235 + B*3735 + 16384) >> 15; the coefficients
+// are split into byte halves so that two IDP.4A per pixel form the sum; the -128 rides in the rounding constant
+// (128 << 15 is a multiple of the shift, so the arithmetic shift gives gray - 128 exactly)
+template <int C>
+__device__ __forceinline__ void iq_gray_pair(unsigned lo, unsigned hi, float &g0, float &g1)
+{
+    if (C == 3) {
+        constexpr unsigned CLO = 70u | (35u << 8) | (151u << 16), CHI = 38u | (75u << 8) | (14u << 16);
+        constexpr unsigned K = 16384u - (128u << 15);
+        const unsigned p1 = __funnelshift_r(lo, hi, 24);
+        const int x0 = (int)(__dp4a(lo, CLO, K) + (__dp4a(lo, CHI, 0u) << 8));
+        const int x1 = (int)(__dp4a(p1, CLO, K) + (__dp4a(p1, CHI, 0u) << 8));
+        g0 = (float)(x0 >> 15);
+        g1 = (float)(x1 >> 15);
+    } else {
+        g0 = (float)((int)(lo & 0xFFu) - 128);
+        g1 = (float)((int)((lo >> 8) & 0xFFu) - 128);
     }
-    bits |= v[0] | v[C > 1 ? 1 : 0] | v[C > 2 ? 2 : 0];
-    return (v[0] * 9798 + v[C > 1 ? 1 : 0] * 19235 + v[C > 2 ? 2 : 0] * 3735 + 16384) >> 15; // cv2 COLOR_RGB2GRAY, uint8
 }
 
 // ------------------------------------------------------------------------------------------------------------
 // k_psnr_ssim: per CTA 256 S-map columns x P.rb rows, streamed DOWN the rows with one barrier per row:
-//   L(r+4) cp.async (LDGSTS) 16-byte copies of the raw RGB bytes of both images into a 4-stage smem ring (104 loader
+//   L(r+4) cp.async (LDGSTS) 16-byte copies of the raw bytes of both images into a 4-stage smem ring (104 loader
 //          threads, no registers held across the latency; image-edge chunks take a guarded byte path)
-//   G(r+1) raw bytes -> gray float row (+ exact squared error and the OR of the bytes for the owned pixels)
-//   H(r)   horizontal taps of {a, b, a^2+b^2, ab} into a register SHIFT ring (slot 0 = oldest row; a phase-unrolled
-//          ring overflowed the instruction cache), vertical taps, SSIM, accumulate
-// TWO S-map columns per thread: the two windows overlap in all but one tap, so the gray samples are read as float2
-// (6 LDS.64 per image for two pixels) and the per-tap products a^2+b^2, ab are formed once for both columns; halo,
-// staging and loop overhead are shared by twice the pixels.  Costs 88 ring registers (4 CTAs of 128 threads per SM).
+//   G(r+1) raw bytes -> (gray_a - 128, gray_b - 128) float pairs, one pixel PAIR per thread from packed words (funnel
+//          shifts + IDP.4A); the exact squared error (VABSDIFF4 + IDP.4A) and the OR of the bytes of the owned pixels
+//   H(r)   horizontal taps of the packed signals (a, b) and (a^2+b^2, ab) -- SSIM needs vx + vy, never each alone --
+//          for the thread's TWO S-map columns: FFMA2, two lanes per instruction
+//   V(r)   vertical pass in ACCUMULATE form: the new horizontal row h adds h * tap[k] to the 2R+1 open output rows,
+//          A[j] = fma(h, tap, A[j + 1]) -- the shift of the classic register ring is the FMA's destination, so there
+//          are no moves; per output row the summation order is oldest row first, as in a gather
 // ANYSCALE: an image is rescaled by 255 first (the reference's max() <= 1 rule, P.scale_a / P.scale_b) -- a separate
 // instantiation so the common case carries no dead arithmetic.  R: window radius (5 Gaussian, 3 uniform).
 // ------------------------------------------------------------------------------------------------------------
 constexpr int IQ2_COLS = 2 * IQ_THREADS;                 // 256 S-map columns per CTA
 constexpr int IQ2_PX = IQ2_COLS + 2 * IQ_R;              // 266 staged pixels per row
 constexpr int IQ2_RAW = ((15 + IQ2_PX * 3 + 15) / 16) * 16; // 832 raw bytes per row and image
-constexpr int IQ2_SROW = IQ2_PX + 6;                     // 272 gray floats per row
+constexpr int IQ2_SROW = IQ2_PX + 6;                     // 272 (a, b) pairs per row
 
 template <int C, bool ANYSCALE, int R>
 __global__ void __launch_bounds__(IQ_THREADS, 4) k_psnr_ssim(IqaParams P)
 {
     __shared__ __align__(16) uint8_t s_raw[4][2][IQ2_RAW];
-    __shared__ __align__(16) float s_a[2][IQ2_SROW];
-    __shared__ __align__(16) float s_b[2][IQ2_SROW];
+    __shared__ __align__(16) float2 s_ab[2][IQ2_SROW];
     __shared__ double s_red[IQ_THREADS / 32];
     __shared__ unsigned long long s_sq[IQ_THREADS / 32];
     __shared__ unsigned long long s_cnt[IQ_THREADS / 32];
@@ -119,12 +143,20 @@ __global__ void __launch_bounds__(IQ_THREADS, 4) k_psnr_ssim(IqaParams P)
     const int vr0 = max(P.row_begin - IQ_R, 0), vr1 = min(P.row_end + IQ_R, h);
     const uint8_t *llo = lbase + (long long)vr0 * lpitch;
     const uint8_t *lhi = lbase + (long long)(vr1 - 1) * lpitch + (long long)w * C;
+    // a chunk of row r starts at most 30 bytes before the row and ends at most col_off + IQ2_RAW bytes into it: rows in
+    // [safe_lo, safe_hi] can touch neither end of the readable range [llo, lhi) and skip the per-chunk guards
+    const long long over = col_off + IQ2_RAW - (long long)w * C;
+    const int safe_lo = vr0 + (int)((32 + lpitch - 1) / lpitch);
+    const int safe_hi = vr1 - 1 - (over > 0 ? (int)((over + lpitch - 1) / lpitch) : 0);
+    // L is called for consecutive rows starting at r_first: l_ptr tracks the thread's chunk of the next row
+    const uint8_t *l_ptr = lbase + (long long)r_first * lpitch + col_off + 16 * lchunk;
     auto L = [&](int r) {
         if (loader && r >= vr0 && r < vr1 && r < r_last) {
-            const uint8_t *A = lbase + (long long)r * lpitch + col_off;
-            const uint8_t *q = A - (reinterpret_cast<uintptr_t>(A) & 15) + 16 * lchunk;
+            const uint8_t *q = l_ptr - (reinterpret_cast<uintptr_t>(l_ptr) & 15);
             uint8_t *dst = &s_raw[(r - r_first) & 3][limg][16 * lchunk];
-            if (q >= llo && q + 16 <= lhi) {
+            if (r >= safe_lo && r <= safe_hi) {
+                cp_async_16(dst, q);
+            } else if (q >= llo && q + 16 <= lhi) {
                 cp_async_16(dst, q);
             } else if (q + 16 > llo && q < lhi) { // image edge: guarded bytes
                 uint4 v = make_uint4(0, 0, 0, 0);
@@ -135,57 +167,72 @@ __global__ void __launch_bounds__(IQ_THREADS, 4) k_psnr_ssim(IqaParams P)
                 *reinterpret_cast<uint4 *>(dst) = v;
             }
         }
+        l_ptr += lpitch;
         cp_async_commit();
     };
 
-    unsigned int sq = 0; // <= 128 rows * 4 px * 3 * 65025 < 2^32
-    int bits_a = 0, bits_b = 0;
+    unsigned int sq = 0; // <= 138 rows * 4 px * 3 * 65025 < 2^32
+    unsigned int bits_a = 0, bits_b = 0;
     const int mis_a0 = (int)((reinterpret_cast<uintptr_t>(P.a) + (unsigned long long)col_off) & 15);
     const int mis_b0 = (int)((reinterpret_cast<uintptr_t>(P.b) + (unsigned long long)col_off) & 15);
     const int pa16 = (int)(P.pitch_a & 15), pb16 = (int)(P.pitch_b & 15);
-    // staged pixel i sits at image column cx0 - 5 + i; thread t converts pixels 2t, 2t+1 and (t < 5) 256+2t, 257+2t
-    auto G = [&](int r) {
-        const int buf = r & 1;
-        float ga[4] = {0.f, 0.f, 0.f, 0.f}, gb[4] = {0.f, 0.f, 0.f, 0.f};
-        if (r >= 0 && r < h) {
-            const int st = (r - r_first) & 3;
-            const uint8_t *ra = &s_raw[st][0][(mis_a0 + r * pa16) & 15];
-            const uint8_t *rb = &s_raw[st][1][(mis_b0 + r * pb16) & 15];
-            const bool rown = r >= ry0 && r < ry1;
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                if (u >= 2 && t >= IQ_R) break;
-                const int i = (u < 2) ? 2 * t + u : IQ2_COLS + 2 * t + (u - 2);
-                const int colp = cx0 - IQ_R + i;
-                int va[C], vb[C], da = 0, db = 0;
-                ga[u] = (float)(gray_of<C, ANYSCALE>(ra + i * C, P.scale_a, da, va) - 128);
-                gb[u] = (float)(gray_of<C, ANYSCALE>(rb + i * C, P.scale_b, db, vb) - 128);
-                if (rown && colp >= cx0 && colp < cx0 + IQ2_COLS && colp < w) {
-                    bits_a |= da;
-                    bits_b |= db;
-#pragma unroll
-                    for (int c = 0; c < C; ++c) {
-                        const int d = va[c] - vb[c];
-                        sq += (unsigned)(d * d);
-                    }
-                }
-            }
-        }
-        *reinterpret_cast<float2 *>(&s_a[buf][2 * t]) = make_float2(ga[0], ga[1]);
-        *reinterpret_cast<float2 *>(&s_b[buf][2 * t]) = make_float2(gb[0], gb[1]);
-        if (t < IQ_R) {
-            *reinterpret_cast<float2 *>(&s_a[buf][IQ2_COLS + 2 * t]) = make_float2(ga[2], ga[3]);
-            *reinterpret_cast<float2 *>(&s_b[buf][IQ2_COLS + 2 * t]) = make_float2(gb[2], gb[3]);
+    // staged pixel i sits at image column cx0 - 5 + i; thread t converts the pairs (2t, 2t+1) and, t < 5, (256+2t, 257+2t).
+    // byte masks of the pixels this CTA OWNS (columns [cx0, cx0 + 256) inside the image) within a pair's lo / hi words
+    auto own = [&](int i) { const int colp = cx0 - IQ_R + i; return colp >= cx0 && colp < cx0 + IQ2_COLS && colp < w; };
+    auto pair_masks = [&](int i, unsigned &mlo, unsigned &mhi) {
+        const bool o0 = own(i), o1 = own(i + 1);
+        if (C == 3) {
+            mlo = (o0 ? 0x00FFFFFFu : 0u) | (o1 ? 0xFF000000u : 0u);
+            mhi = o1 ? 0x0000FFFFu : 0u;
+        } else {
+            mlo = (o0 ? 0x000000FFu : 0u) | (o1 ? 0x0000FF00u : 0u);
+            mhi = 0u;
         }
     };
+    unsigned mlo0, mhi0, mlo1 = 0u, mhi1 = 0u;
+    pair_masks(2 * t, mlo0, mhi0);
+    if (t < IQ_R) pair_masks(IQ2_COLS + 2 * t, mlo1, mhi1);
+    auto G = [&](int r) {
+        const int buf = r & 1;
+        float4 o0 = make_float4(0.f, 0.f, 0.f, 0.f), o1 = o0; // (a, b) of the pair's two pixels
+        if (r >= 0 && r < h) {
+            const int st = (r - r_first) & 3;
+            const int ma = (mis_a0 + r * pa16) & 15, mb = (mis_b0 + r * pb16) & 15;
+            const bool rown = r >= ry0 && r < ry1;
+            auto pair = [&](int i, unsigned mlo, unsigned mhi, float4 &o) {
+                unsigned alo, ahi, blo, bhi;
+                iq_load_pair<C, ANYSCALE>(s_raw[st][0], ma + i * C, P.scale_a, alo, ahi);
+                iq_load_pair<C, ANYSCALE>(s_raw[st][1], mb + i * C, P.scale_b, blo, bhi);
+                iq_gray_pair<C>(alo, ahi, o.x, o.z);
+                iq_gray_pair<C>(blo, bhi, o.y, o.w);
+                if (rown) {
+                    const unsigned dlo = __vabsdiffu4(alo, blo) & mlo;
+                    sq = __dp4a(dlo, dlo, sq);
+                    bits_a |= alo & mlo;
+                    bits_b |= blo & mlo;
+                    if (C == 3) {
+                        const unsigned dhi = __vabsdiffu4(ahi, bhi) & mhi;
+                        sq = __dp4a(dhi, dhi, sq);
+                        bits_a |= ahi & mhi;
+                        bits_b |= bhi & mhi;
+                    }
+                }
+            };
+            pair(2 * t, mlo0, mhi0, o0);
+            if (t < IQ_R) pair(IQ2_COLS + 2 * t, mlo1, mhi1, o1);
+        }
+        *reinterpret_cast<float4 *>(&s_ab[buf][2 * t]) = o0;
+        if (t < IQ_R) *reinterpret_cast<float4 *>(&s_ab[buf][IQ2_COLS + 2 * t]) = o1;
+    };
 
-    float ring[2][4][TAPS];
+    // open output rows: A[q][0][j] = partial (a, b) sums, A[q][1][j] = partial (a^2+b^2, ab) sums of S-map column q
+    float2 A[2][2][TAPS - 1];
 #pragma unroll
     for (int q = 0; q < 2; ++q)
 #pragma unroll
-        for (int s = 0; s < 4; ++s)
+        for (int s = 0; s < 2; ++s)
 #pragma unroll
-            for (int k = 0; k < TAPS; ++k) ring[q][s][k] = 0.f;
+            for (int k = 0; k < TAPS - 1; ++k) A[q][s][k] = make_float2(0.f, 0.f);
 
     float ssum = 0.f;
     unsigned int scount = 0;
@@ -206,69 +253,56 @@ __global__ void __launch_bounds__(IQ_THREADS, 4) k_psnr_ssim(IqaParams P)
     for (int r_in = r_first; r_in < r_last; ++r_in) {
         const int buf = r_in & 1;
         L(r_in + 4);
+        float2 hn[2][2]; // this row's horizontal sums: [q][(a, b) | (a^2+b^2, ab)]
         {
-            // gray samples 2t + (5 - R) .. + TAPS (TAPS + 1 values, even start -> float2 loads)
-            float xa[TAPS + 1], xb[TAPS + 1];
-            const float2 *pa = reinterpret_cast<const float2 *>(&s_a[buf][2 * t + (IQ_R - R) - ((IQ_R - R) & 1)]);
-            const float2 *pb = reinterpret_cast<const float2 *>(&s_b[buf][2 * t + (IQ_R - R) - ((IQ_R - R) & 1)]);
-            constexpr int OFF = (IQ_R - R) & 1; // 0 for R = 5 and R = 3
-            constexpr int NV = (TAPS + 1 + OFF + 1) / 2;
-            float ta[2 * NV], tb[2 * NV];
+            // staged pixels 2t + (5 - R) .. + TAPS (TAPS + 1 of them, two per LDS.128): column 0 takes samples
+            // 0 .. TAPS-1, column 1 samples 1 .. TAPS, both with taps 0 .. TAPS-1
+            const float4 *pv = reinterpret_cast<const float4 *>(&s_ab[buf][2 * t + (IQ_R - R)]);
+            static_assert(((IQ_R - R) & 1) == 0 && ((TAPS + 1) & 1) == 0, "pairs must stay 16-byte aligned");
 #pragma unroll
-            for (int k = 0; k < NV; ++k) {
-                const float2 va = pa[k], vb = pb[k];
-                ta[2 * k] = va.x; ta[2 * k + 1] = va.y;
-                tb[2 * k] = vb.x; tb[2 * k + 1] = vb.y;
-            }
+            for (int j = 0; j < (TAPS + 1) / 2; ++j) {
+                const float4 v = pv[j];
 #pragma unroll
-            for (int k = 0; k <= TAPS; ++k) {
-                xa[k] = ta[k + OFF];
-                xb[k] = tb[k + OFF];
-            }
-            float h0a = 0.f, h0b = 0.f, h0s = 0.f, h0p = 0.f, h1a = 0.f, h1b = 0.f, h1s = 0.f, h1p = 0.f;
-#pragma unroll
-            for (int k = 0; k <= TAPS; ++k) {
-                const float a = xa[k], b = xb[k];
-                const float ss = fmaf(a, a, b * b), pp = a * b;
-                if (k < TAPS) { // column 0 uses samples 0 .. TAPS-1 with taps 0 .. TAPS-1
-                    h0a = fmaf(a, iq_tap<R>(k), h0a);
-                    h0b = fmaf(b, iq_tap<R>(k), h0b);
-                    h0s = fmaf(ss, iq_tap<R>(k), h0s);
-                    h0p = fmaf(pp, iq_tap<R>(k), h0p);
-                }
-                if (k > 0) { // column 1 uses samples 1 .. TAPS with taps 0 .. TAPS-1
-                    h1a = fmaf(a, iq_tap<R>(k - 1), h1a);
-                    h1b = fmaf(b, iq_tap<R>(k - 1), h1b);
-                    h1s = fmaf(ss, iq_tap<R>(k - 1), h1s);
-                    h1p = fmaf(pp, iq_tap<R>(k - 1), h1p);
+                for (int e = 0; e < 2; ++e) {
+                    const int k = 2 * j + e;
+                    const float a = e ? v.z : v.x, b = e ? v.w : v.y;
+                    const float2 ab = make_float2(a, b);
+                    const float2 sp = make_float2(fmaf(a, a, b * b), a * b);
+                    if (k == 0) {
+                        hn[0][0] = f2mul(ab, iq_tap<R>(0));
+                        hn[0][1] = f2mul(sp, iq_tap<R>(0));
+                    } else if (k < TAPS) {
+                        hn[0][0] = f2fma(ab, iq_tap<R>(k), hn[0][0]);
+                        hn[0][1] = f2fma(sp, iq_tap<R>(k), hn[0][1]);
+                    }
+                    if (k == 1) {
+                        hn[1][0] = f2mul(ab, iq_tap<R>(0));
+                        hn[1][1] = f2mul(sp, iq_tap<R>(0));
+                    } else if (k > 1) {
+                        hn[1][0] = f2fma(ab, iq_tap<R>(k - 1), hn[1][0]);
+                        hn[1][1] = f2fma(sp, iq_tap<R>(k - 1), hn[1][1]);
+                    }
                 }
             }
-#pragma unroll
-            for (int q = 0; q < 2; ++q)
-#pragma unroll
-                for (int s = 0; s < 4; ++s)
-#pragma unroll
-                    for (int k = 0; k < TAPS - 1; ++k) ring[q][s][k] = ring[q][s][k + 1];
-            ring[0][0][TAPS - 1] = h0a; ring[0][1][TAPS - 1] = h0b; ring[0][2][TAPS - 1] = h0s; ring[0][3][TAPS - 1] = h0p;
-            ring[1][0][TAPS - 1] = h1a; ring[1][1][TAPS - 1] = h1b; ring[1][2][TAPS - 1] = h1s; ring[1][3][TAPS - 1] = h1p;
         }
         const int r = r_in - R;
-        if (r >= ry0) {
-            const bool row_ok = r >= R && r < h - R;
+        const bool emit = r >= ry0;
+        const bool row_ok = r >= R && r < h - R;
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                float f[4];
+        for (int q = 0; q < 2; ++q) {
+            float2 f[2];
 #pragma unroll
-                for (int s = 0; s < 4; ++s) {
-                    float v = 0.f;
+            for (int s = 0; s < 2; ++s) {
+                f[s] = f2fma(hn[q][s], iq_tap<R>(TAPS - 1), A[q][s][0]);
 #pragma unroll
-                    for (int k = 0; k < TAPS; ++k) v = fmaf(ring[q][s][k], iq_tap<R>(k), v);
-                    f[s] = v;
-                }
-                const float ua = f[0], ub = f[1];
+                for (int j = 0; j < TAPS - 2; ++j) A[q][s][j] = f2fma(hn[q][s], iq_tap<R>(TAPS - 2 - j), A[q][s][j + 1]);
+                A[q][s][TAPS - 2] = f2mul(hn[q][s], iq_tap<R>(0));
+            }
+            if (emit) {
+                const float ua = f[0].x, ub = f[0].y;
                 const float ux = ua + 128.f, uy = ub + 128.f;
-                const float vsum = P.cov_norm * (f[2] - fmaf(ua, ua, ub * ub));
-                const float vxy = P.cov_norm * (f[3] - ua * ub);
+                const float vsum = P.cov_norm * (f[1].x - fmaf(ua, ua, ub * ub));
+                const float vxy = P.cov_norm * (f[1].y - ua * ub);
                 const float A1 = fmaf(2.f * ux, uy, C1), A2 = fmaf(2.f, vxy, C2);
                 const float B1 = fmaf(ux, ux, fmaf(uy, uy, C1)), B2 = vsum + C2;
                 const float S = __fdividef(A1 * A2, B1 * B2);
@@ -286,7 +320,8 @@ __global__ void __launch_bounds__(IQ_THREADS, 4) k_psnr_ssim(IqaParams P)
 
     double ds = (double)ssum;
     unsigned long long dsq = sq, dcnt = scount;
-    int mxa = bits_a, mxb = bits_b;
+    int mxa = (int)((bits_a | (bits_a >> 8) | (bits_a >> 16) | (bits_a >> 24)) & 0xFFu);
+    int mxb = (int)((bits_b | (bits_b >> 8) | (bits_b >> 16) | (bits_b >> 24)) & 0xFFu);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         ds += __shfl_down_sync(0xffffffffu, ds, o);
