@@ -772,6 +772,7 @@ struct FinalStage { // everything the gather reads of ONE covering tile; double 
     float sc[C][FB_SRC_ROWS][FB_SRC_COLS]; // C_1 window (W_1 window when the tile has exactly two levels)
     float sg[C][FB_SRC_ROWS][FB_SRC_COLS]; // G_1 window
     uint8_t u8[FB_H][FB_U8_STRIDE];        // uint8 tile block
+    float nwy[FB_H];                       // -W_0 profile of the block's 16 rows (negated: see final_accumulate_tile)
 };
 template <int C>
 struct FinalSmem {
@@ -841,7 +842,7 @@ __device__ __forceinline__ HPair h_pair_fast(float s0, float s1, float s2, int x
 // reference removes right away (x 1/64).  Scaling by a power of two commutes with every IEEE rounding, so
 // 64*(upC + (g - upG)*w) == up64C + (64 g - up64G)*w bit for bit; the factor is taken out once, before the divide.
 template <int C, bool FULL>
-__device__ __forceinline__ void final_accumulate_tile(FinalSmem<C> &S, const FinalStage<C> &B, float (&acc)[FB_STEPS][2][2], const TileDev &t,
+__device__ __forceinline__ void final_accumulate_tile(FinalSmem<C> &S, const FinalStage<C> &B, float2 (&acc)[FB_STEPS][2], const TileDev &t,
                                                       const GroupDev &g, int cy0, int cx0, const FinalGeo &q, int c, int p)
 {
     const int iy0 = q.iy0, iy1 = q.iy1, ix0 = q.ix0, ix1 = q.ix1, u8_a0 = q.u8_a0, srow0 = q.srow0, n_srows = q.n_srows, sx0 = q.sx0;
@@ -862,8 +863,8 @@ __device__ __forceinline__ void final_accumulate_tile(FinalSmem<C> &S, const Fin
     // The weight profile is monotone non-decreasing in the border distance (linear, cosine and sigmoid all are, and
     // float32 rounding keeps the order), so lut[min(dy, dx)] == min(lut[dy], lut[dx]) exactly: one lookup per row and
     // two per tile instead of one per pixel.
+    // The row values come from a 16-entry table the staging step leaves in smem (B.nwy, negated).
     const float wxa = __ldg(g.lut + max(min(dxa, lmax), 0)), wxb = __ldg(g.lut + max(min(dxb, lmax), 0));
-    auto weight_row = [&](int dy) { return __ldg(g.lut + max(min(dy, lmax), 0)); };
     auto hrow = [&](int r_logical, HPair &oc, HPair &og) {
         int r = (r_logical == -1) ? min(1, h1 - 1) : max(min(r_logical, h1 - 1), 0);
         r -= srow0;
@@ -907,20 +908,77 @@ __device__ __forceinline__ void final_accumulate_tile(FinalSmem<C> &S, const Fin
             for (int a = 0; a < 2; ++a) {
                 const int cy = cy0 + 2 * k + a;
                 if (cy < iy0 || cy >= iy1) continue;
-                const int ty = cy - t.y;
-                const float wy = weight_row(min(ty, t.h - 1 - ty));
+                const float wy = -B.nwy[2 * k + a];
                 const uint8_t *px = &B.u8[2 * k + a][u8_col];
+                const bool wsum_mine = c == (2 * k + a) % C; // the block's rows are dealt round-robin to the channel threads
                 if (ina) {
                     const float w0 = fminf(wy, wxa);
-                    acc[k][a][0] = __fadd_rn(acc[k][a][0], __fmul_rn((float)((int)px[0] << 6), w0));
-                    if (c == 0) S.wsum[2 * k + a][2 * p] = __fadd_rn(S.wsum[2 * k + a][2 * p], w0);
+                    acc[k][a].x = __fadd_rn(acc[k][a].x, __fmul_rn((float)((int)px[0] << 6), w0));
+                    if (wsum_mine) S.wsum[2 * k + a][2 * p] = __fadd_rn(S.wsum[2 * k + a][2 * p], w0);
                 }
                 if (inb) {
                     const float w0 = fminf(wy, wxb);
-                    acc[k][a][1] = __fadd_rn(acc[k][a][1], __fmul_rn((float)((int)px[C] << 6), w0));
-                    if (c == 0) S.wsum[2 * k + a][2 * p + 1] = __fadd_rn(S.wsum[2 * k + a][2 * p + 1], w0);
+                    acc[k][a].y = __fadd_rn(acc[k][a].y, __fmul_rn((float)((int)px[C] << 6), w0));
+                    if (wsum_mine) S.wsum[2 * k + a][2 * p + 1] = __fadd_rn(S.wsum[2 * k + a][2 * p + 1], w0);
                 }
             }
+        }
+        return;
+    }
+
+    if (FULL) {
+        // Interior block: no predicates, and the column pair is carried as one packed float2 (FADD2 / FMUL2 / FFMA2 round
+        // each lane like the scalar instruction, so the reference's op order is kept).  ptxas contracts a packed multiply
+        // into a following packed add even for .rn, so every INEXACT product that feeds an add (6 p, d * w) is formed with
+        // scalar FMULs; the exact ones (x 4) may fuse freely.  The pixel stage runs on negated values:
+        // nd = fma(g, -64, up64G) = -(64 g - up64G) and nw = -w0, whose product is the reference's (64 g - up64G) * w0.
+        const float nwxa = -wxa, nwxb = -wxb;
+        auto hrow2 = [&](int r_logical, float2 &oc, float2 &og) {
+            int r = (r_logical == -1) ? min(1, h1 - 1) : max(min(r_logical, h1 - 1), 0);
+            r -= srow0;
+            r = max(min(r, n_srows - 1), 0);
+            const float *rc = &B.sc[c][r][scol];
+            const float *rg = &B.sg[c][r][scol];
+            const HPair hc = h_pair_fast(rc[0], rc[1], rc[2], xpar), hg = h_pair_fast(rg[0], rg[1], rg[2], xpar);
+            oc = make_float2(hc.a, hc.b);
+            og = make_float2(hg.a, hg.b);
+        };
+        auto up_even2 = [](float2 m, float2 p6, float2 n) {
+            return __fadd2_rn(__fadd2_rn(make_float2(__fmul_rn(p6.x, 6.f), __fmul_rn(p6.y, 6.f)), m), n);
+        };
+        auto up_odd2 = [](float2 p4, float2 n) { return __fmul2_rn(__fadd2_rn(p4, n), make_float2(4.f, 4.f)); };
+        float2 rc0, rg0, rc1, rg1, rc2, rg2; // ring: logical rows ws0+k, ws0+k+1, ws0+k+2
+        hrow2(ws0, rc0, rg0);
+        hrow2(ws0 + 1, rc1, rg1);
+#pragma unroll
+        for (int k = 0; k < FB_STEPS; ++k) {
+            hrow2(ws0 + k + 2, rc2, rg2);
+            float2 uc[2], ug[2]; // x64, rows 2k and 2k+1
+            if (ypar == 0) {
+                uc[0] = up_even2(rc0, rc1, rc2); ug[0] = up_even2(rg0, rg1, rg2);
+                uc[1] = up_odd2(rc1, rc2);       ug[1] = up_odd2(rg1, rg2);
+            } else {
+                uc[0] = up_odd2(rc0, rc1);       ug[0] = up_odd2(rg0, rg1);
+                uc[1] = up_even2(rc0, rc1, rc2); ug[1] = up_even2(rg0, rg1, rg2);
+            }
+#pragma unroll
+            for (int a = 0; a < 2; ++a) {
+                const int r = 2 * k + a;
+                const float nwy = B.nwy[r];
+                const uint8_t *px = &B.u8[r][u8_col];
+                const float2 nw = make_float2(fmaxf(nwy, nwxa), fmaxf(nwy, nwxb)); // -min(wy, wx)
+                const float2 nd = __ffma2_rn(make_float2((float)px[0], (float)px[C]), make_float2(-64.f, -64.f), ug[a]);
+                const float2 dw = make_float2(__fmul_rn(nd.x, nw.x), __fmul_rn(nd.y, nw.y));
+                acc[k][a] = __fadd2_rn(acc[k][a], __fadd2_rn(uc[a], dw));
+                if (c == r % C) {
+                    float2 *wp = reinterpret_cast<float2 *>(&S.wsum[r][2 * p]);
+                    float2 ws = *wp;
+                    ws.x = __fadd_rn(ws.x, -nw.x);
+                    ws.y = __fadd_rn(ws.y, -nw.y);
+                    *wp = ws;
+                }
+            }
+            rc0 = rc1; rg0 = rg1; rc1 = rc2; rg1 = rg2;
         }
         return;
     }
@@ -947,26 +1005,35 @@ __device__ __forceinline__ void final_accumulate_tile(FinalSmem<C> &S, const Fin
         for (int a = 0; a < 2; ++a) {
             const int cy = cy0 + 2 * k + a;
             if (FULL || (cy >= iy0 && cy < iy1)) {
-                const int ty = tyf + 2 * k + a;
-                const float wy = weight_row(min(ty, t.h - 1 - ty));
+                const float wy = -B.nwy[2 * k + a];
                 const uint8_t *px = &B.u8[2 * k + a][u8_col];
+                const bool wsum_mine = c == (2 * k + a) % C;
                 if (ina) {
                     const float w0 = fminf(wy, wxa);
                     // fma(g, 64, -up64G) == 64 g - up64G rounded once: 64 g is exact, so this IS the reference's subtraction
                     const float v = __fadd_rn(uc[a][0], __fmul_rn(__fmaf_rn((float)px[0], 64.f, -ug[a][0]), w0));
-                    acc[k][a][0] = __fadd_rn(acc[k][a][0], v);
-                    if (c == 0) S.wsum[2 * k + a][2 * p] = __fadd_rn(S.wsum[2 * k + a][2 * p], w0);
+                    acc[k][a].x = __fadd_rn(acc[k][a].x, v);
+                    if (wsum_mine) S.wsum[2 * k + a][2 * p] = __fadd_rn(S.wsum[2 * k + a][2 * p], w0);
                 }
                 if (inb) {
                     const float w0 = fminf(wy, wxb);
                     const float v = __fadd_rn(uc[a][1], __fmul_rn(__fmaf_rn((float)px[C], 64.f, -ug[a][1]), w0));
-                    acc[k][a][1] = __fadd_rn(acc[k][a][1], v);
-                    if (c == 0) S.wsum[2 * k + a][2 * p + 1] = __fadd_rn(S.wsum[2 * k + a][2 * p + 1], w0);
+                    acc[k][a].y = __fadd_rn(acc[k][a].y, v);
+                    if (wsum_mine) S.wsum[2 * k + a][2 * p + 1] = __fadd_rn(S.wsum[2 * k + a][2 * p + 1], w0);
                 }
             }
         }
         rc0 = rc1; rg0 = rg1; rc1 = rc2; rg1 = rg2;
     }
+}
+
+constexpr float FINAL_NEAR = 2.5e-4f;
+// trunc(clip(v, 0, 255)): float -> u8 conversion rounds toward zero and saturates (NaN -> 0)
+__device__ __forceinline__ unsigned f2u8_trunc_sat(float v)
+{
+    unsigned r;
+    asm("cvt.rzi.u8.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return r;
 }
 
 template <int C>
@@ -986,9 +1053,9 @@ __global__ void __launch_bounds__(128 * C, (C == 3) ? 2 : 5) k_final(FinalParams
     const int p = threadIdx.x % FB_PAIRS;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
-    float acc[FB_STEPS][2][2];
+    float2 acc[FB_STEPS][2];
 #pragma unroll
-    for (int k = 0; k < FB_STEPS; ++k) acc[k][0][0] = acc[k][0][1] = acc[k][1][0] = acc[k][1][1] = 0.f;
+    for (int k = 0; k < FB_STEPS; ++k) acc[k][0] = acc[k][1] = make_float2(0.f, 0.f);
     for (int i = threadIdx.x; i < FB_H * FB_W; i += NT) (&S.wsum[0][0])[i] = 0.f;
 
     for (int base = 0; base < P.n_tiles; base += NT) {
@@ -1021,6 +1088,10 @@ __global__ void __launch_bounds__(128 * C, (C == 3) ? 2 : 5) k_final(FinalParams
             const GroupDev &g = P.groups[P.tile_group[ti]];
             const FinalGeo q = final_geo(t, g, cy0, cy1, cx0, cx1, C);
             FinalStage<C> &B = S.st[li & 1];
+            if (threadIdx.x < FB_H) { // W_0 row profile of the block (blending_module.py:508-561 through the host LUT), negated
+                const int ty = cy0 + (int)threadIdx.x - t.y;
+                B.nwy[threadIdx.x] = -__ldg(g.lut + max(min(min(ty, t.h - 1 - ty), g.lut_len - 1), 0));
+            }
             const int pitch = (int)t.pitch;
             constexpr int NW = NT / 32;
             // one warp per row, one lane per 16-byte chunk (+ a second pass for the chunks beyond 32): no div / mod
@@ -1086,24 +1157,35 @@ __global__ void __launch_bounds__(128 * C, (C == 3) ? 2 : 5) k_final(FinalParams
     }
 
     // ---- normalise, clip, truncate; stage the block as bytes congruent (mod 16) with the canvas rows ----
+    // The reference's out = trunc(clip(RN(acc / wsum), 0, 255)) only needs the correctly rounded quotient where it lies
+    // next to an integer: q ~ acc * rcp(wsum) is within 8e-5 of RN(acc / wsum) for q < 256 (MUFU.RCP + FMUL: 2 ulp, plus
+    // the half ulp of the exact rounding), so unless q is within FINAL_NEAR of an integer both truncate to the same byte.
+    // The IEEE division (~15 instructions per value) runs only for those rare pairs; cvt.rzi.u8 saturates, i.e. clips.
     __syncthreads();
     const int row_bytes = (cx1 - cx0) * C;
+    {
+        const uintptr_t cbase = reinterpret_cast<uintptr_t>(P.canvas) + (size_t)cy0 * P.canvas_pitch + (size_t)cx0 * C;
+        const int mis0 = (int)(cbase & 15), pit16 = (int)(P.canvas_pitch & 15);
+        const bool px_a = cx0 + 2 * p < cx1, px_b = cx0 + 2 * p + 1 < cx1;
+        uint8_t *out0 = &S.st[0].u8[0][2 * p * C + c];
 #pragma unroll
-    for (int k = 0; k < FB_STEPS; ++k) {
+        for (int k = 0; k < FB_STEPS; ++k) {
 #pragma unroll
-        for (int a = 0; a < 2; ++a) {
-            const int r = 2 * k + a;
-            const int cy = cy0 + r;
-            if (cy >= cy1) continue;
-            const int mis = (int)((reinterpret_cast<uintptr_t>(P.canvas) + (size_t)cy * P.canvas_pitch + (size_t)cx0 * C) & 15);
-#pragma unroll
-            for (int b = 0; b < 2; ++b) {
-                const int x = 2 * p + b;
-                if (cx0 + x >= cx1) continue;
-                const float wsum = fmaxf(S.wsum[r][x], 1e-6f);
-                float v = __fdiv_rn(__fmul_rn(acc[k][a][b], 1.f / 64.f), wsum);
-                v = fminf(fmaxf(v, 0.f), 255.f);
-                S.st[0].u8[r][mis + x * C + c] = (uint8_t)(int)v; // clip then truncate (blending_module.py:504-506)
+            for (int a = 0; a < 2; ++a) {
+                const int r = 2 * k + a;
+                if (cy0 + r >= cy1) continue;
+                const int mis = (mis0 + r * pit16) & 15;
+                const float2 ws = *reinterpret_cast<const float2 *>(&S.wsum[r][2 * p]);
+                const float b0 = fmaxf(ws.x, 1e-6f), b1 = fmaxf(ws.y, 1e-6f);
+                const float a0 = __fmul_rn(acc[k][a].x, 1.f / 64.f), a1 = __fmul_rn(acc[k][a].y, 1.f / 64.f);
+                float q0 = __fdividef(a0, b0), q1 = __fdividef(a1, b1);
+                if (fabsf(q0 - rintf(q0)) < FINAL_NEAR || fabsf(q1 - rintf(q1)) < FINAL_NEAR) {
+                    q0 = __fdiv_rn(a0, b0);
+                    q1 = __fdiv_rn(a1, b1);
+                }
+                uint8_t *dst = out0 + r * FB_U8_STRIDE + mis;
+                if (px_a) dst[0] = (uint8_t)f2u8_trunc_sat(q0); // clip then truncate (blending_module.py:504-506)
+                if (px_b) dst[C] = (uint8_t)f2u8_trunc_sat(q1);
             }
         }
     }
