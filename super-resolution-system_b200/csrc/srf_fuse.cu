@@ -18,6 +18,7 @@
 #include "srf_common.cuh"
 
 #include <algorithm>
+#include <type_traits>
 #include <string.h>
 
 namespace {
@@ -927,47 +928,42 @@ __device__ __forceinline__ void final_accumulate_tile(FinalSmem<C> &S, const Fin
     }
 
     if (FULL) {
-        // Interior block: no predicates, and the column pair is carried as one packed float2 (FADD2 / FMUL2 / FFMA2 round
-        // each lane like the scalar instruction, so the reference's op order is kept).  ptxas contracts a packed multiply
-        // into a following packed add even for .rn, so every INEXACT product that feeds an add (6 p, d * w) is formed with
-        // scalar FMULs; the exact ones (x 4) may fuse freely.  The pixel stage runs on negated values:
-        // nd = fma(g, -64, up64G) = -(64 g - up64G) and nw = -w0, whose product is the reference's (64 g - up64G) * w0.
+        // Interior block of even parity (the caller checked: block inside the tile, every source window strictly inside
+        // the level-1 plane in both axes, xpar == ypar == 0): no predicates, staged source row j is logical row ws0 + j,
+        // and the column pair is carried as one packed float2 (FADD2 / FMUL2 / FFMA2 round each lane like the scalar
+        // instruction, so the reference's op order is kept).  ptxas contracts a packed multiply into a following packed
+        // add even for .rn, so every INEXACT product that feeds an add (6 p, d * w) is formed with scalar FMULs; the exact
+        // ones (x 4) may fuse freely.  The pixel stage runs on negated values: nd = fma(g, -64, up64G) = -(64 g - up64G)
+        // and nw = -w0, whose product is the reference's (64 g - up64G) * w0.
         const float nwxa = -wxa, nwxb = -wxb;
-        auto hrow2 = [&](int r_logical, float2 &oc, float2 &og) {
-            int r = (r_logical == -1) ? min(1, h1 - 1) : max(min(r_logical, h1 - 1), 0);
-            r -= srow0;
-            r = max(min(r, n_srows - 1), 0);
-            const float *rc = &B.sc[c][r][scol];
-            const float *rg = &B.sg[c][r][scol];
-            const HPair hc = h_pair_fast(rc[0], rc[1], rc[2], xpar), hg = h_pair_fast(rg[0], rg[1], rg[2], xpar);
-            oc = make_float2(hc.a, hc.b);
-            og = make_float2(hg.a, hg.b);
+        const float *rcb = &B.sc[c][0][scol];
+        const float *rgb = &B.sg[c][0][scol];
+        auto hrow2 = [&](int j, float2 &oc, float2 &og) { // columns (2i, 2i+1), i = window centre: even form, odd form
+            const float *rc = rcb + j * FB_SRC_COLS, *rg = rgb + j * FB_SRC_COLS;
+            const float c0 = rc[0], c1 = rc[1], c2 = rc[2], g0 = rg[0], g1 = rg[1], g2 = rg[2];
+            oc = make_float2(up_even(c0, c1, c2), up_odd(c1, c2));
+            og = make_float2(up_even(g0, g1, g2), up_odd(g1, g2));
         };
         auto up_even2 = [](float2 m, float2 p6, float2 n) {
             return __fadd2_rn(__fadd2_rn(make_float2(__fmul_rn(p6.x, 6.f), __fmul_rn(p6.y, 6.f)), m), n);
         };
         auto up_odd2 = [](float2 p4, float2 n) { return __fmul2_rn(__fadd2_rn(p4, n), make_float2(4.f, 4.f)); };
-        float2 rc0, rg0, rc1, rg1, rc2, rg2; // ring: logical rows ws0+k, ws0+k+1, ws0+k+2
-        hrow2(ws0, rc0, rg0);
-        hrow2(ws0 + 1, rc1, rg1);
+        float2 rc0, rg0, rc1, rg1, rc2, rg2; // ring: source rows k, k+1, k+2
+        hrow2(0, rc0, rg0);
+        hrow2(1, rc1, rg1);
 #pragma unroll
         for (int k = 0; k < FB_STEPS; ++k) {
-            hrow2(ws0 + k + 2, rc2, rg2);
-            float2 uc[2], ug[2]; // x64, rows 2k and 2k+1
-            if (ypar == 0) {
-                uc[0] = up_even2(rc0, rc1, rc2); ug[0] = up_even2(rg0, rg1, rg2);
-                uc[1] = up_odd2(rc1, rc2);       ug[1] = up_odd2(rg1, rg2);
-            } else {
-                uc[0] = up_odd2(rc0, rc1);       ug[0] = up_odd2(rg0, rg1);
-                uc[1] = up_even2(rc0, rc1, rc2); ug[1] = up_even2(rg0, rg1, rg2);
-            }
+            hrow2(k + 2, rc2, rg2);
+            float2 uc[2], ug[2]; // x64, tile rows (2j, 2j+1), j = ws0 + k + 1: even uses the whole ring, odd its last two rows
+            uc[0] = up_even2(rc0, rc1, rc2); ug[0] = up_even2(rg0, rg1, rg2);
+            uc[1] = up_odd2(rc1, rc2);       ug[1] = up_odd2(rg1, rg2);
 #pragma unroll
             for (int a = 0; a < 2; ++a) {
                 const int r = 2 * k + a;
                 const float nwy = B.nwy[r];
                 const uint8_t *px = &B.u8[r][u8_col];
                 const float2 nw = make_float2(fmaxf(nwy, nwxa), fmaxf(nwy, nwxb)); // -min(wy, wx)
-                const float2 nd = __ffma2_rn(make_float2((float)px[0], (float)px[C]), make_float2(-64.f, -64.f), ug[a]);
+                const float2 nd = __ffma2_rn(make_float2(__int2float_rn((int)px[0]), __int2float_rn((int)px[C])), make_float2(-64.f, -64.f), ug[a]);
                 const float2 dw = make_float2(__fmul_rn(nd.x, nw.x), __fmul_rn(nd.y, nw.y));
                 acc[k][a] = __fadd2_rn(acc[k][a], __fadd2_rn(uc[a], dw));
                 if (c == r % C) {
@@ -1028,6 +1024,13 @@ __device__ __forceinline__ void final_accumulate_tile(FinalSmem<C> &S, const Fin
 }
 
 constexpr float FINAL_NEAR = 2.5e-4f;
+// MUFU.RCP: <= 1 ulp, exact for powers of two
+__device__ __forceinline__ float rcp_approx(float x)
+{
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 // trunc(clip(v, 0, 255)): float -> u8 conversion rounds toward zero and saturates (NaN -> 0)
 __device__ __forceinline__ unsigned f2u8_trunc_sat(float v)
 {
@@ -1145,9 +1148,11 @@ __global__ void __launch_bounds__(128 * C, (C == 3) ? 2 : 5) k_final(FinalParams
             const TileDev &t = P.tiles[ti];
             const GroupDev &g = P.groups[P.tile_group[ti]];
             const FinalGeo q = final_geo(t, g, cy0, cy1, cx0, cx1, C);
-            // block entirely inside the tile and every horizontal window strictly inside the source row: no predicates
+            // block entirely inside the tile, every source window strictly inside the level-1 plane (columns and rows) and
+            // even parity in both axes (tile origins are 2 * the low-resolution origin in the pipeline): no predicates
             const bool full = (q.mode == 0) && (q.iy0 == cy0) && (q.iy1 == cy0 + FB_H) && (q.ix0 == cx0) && (q.ix1 == cx0 + FB_W) &&
-                              (q.i0 >= 0) && (q.i0 + FB_PAIRS + 1 <= g.lv[1].w - 1);
+                              (q.i0 >= 0) && (q.i0 + FB_PAIRS + 1 <= g.lv[1].w - 1) && (q.xpar == 0) && (q.ypar == 0) && (q.ws0 >= 0) &&
+                              (q.ws0 + FB_STEPS + 1 <= g.lv[1].h - 1);
             if (full)
                 final_accumulate_tile<C, true>(S, S.st[li & 1], acc, t, g, cy0, cx0, q, c, p);
             else
@@ -1166,28 +1171,39 @@ __global__ void __launch_bounds__(128 * C, (C == 3) ? 2 : 5) k_final(FinalParams
     {
         const uintptr_t cbase = reinterpret_cast<uintptr_t>(P.canvas) + (size_t)cy0 * P.canvas_pitch + (size_t)cx0 * C;
         const int mis0 = (int)(cbase & 15), pit16 = (int)(P.canvas_pitch & 15);
-        const bool px_a = cx0 + 2 * p < cx1, px_b = cx0 + 2 * p + 1 < cx1;
         uint8_t *out0 = &S.st[0].u8[0][2 * p * C + c];
+        auto quantise = [&](auto whole) { // whole: the block lies entirely inside the band / canvas, no row or column tests
+            constexpr bool WHOLE = decltype(whole)::value;
+            const bool px_a = WHOLE || cx0 + 2 * p < cx1, px_b = WHOLE || cx0 + 2 * p + 1 < cx1;
 #pragma unroll
-        for (int k = 0; k < FB_STEPS; ++k) {
+            for (int k = 0; k < FB_STEPS; ++k) {
 #pragma unroll
-            for (int a = 0; a < 2; ++a) {
-                const int r = 2 * k + a;
-                if (cy0 + r >= cy1) continue;
-                const int mis = (mis0 + r * pit16) & 15;
-                const float2 ws = *reinterpret_cast<const float2 *>(&S.wsum[r][2 * p]);
-                const float b0 = fmaxf(ws.x, 1e-6f), b1 = fmaxf(ws.y, 1e-6f);
-                const float a0 = __fmul_rn(acc[k][a].x, 1.f / 64.f), a1 = __fmul_rn(acc[k][a].y, 1.f / 64.f);
-                float q0 = __fdividef(a0, b0), q1 = __fdividef(a1, b1);
-                if (fabsf(q0 - rintf(q0)) < FINAL_NEAR || fabsf(q1 - rintf(q1)) < FINAL_NEAR) {
-                    q0 = __fdiv_rn(a0, b0);
-                    q1 = __fdiv_rn(a1, b1);
+                for (int a = 0; a < 2; ++a) {
+                    const int r = 2 * k + a;
+                    if (!WHOLE && cy0 + r >= cy1) continue;
+                    const int mis = (mis0 + r * pit16) & 15;
+                    const float2 ws = *reinterpret_cast<const float2 *>(&S.wsum[r][2 * p]);
+                    const float b0 = fmaxf(ws.x, 1e-6f), b1 = fmaxf(ws.y, 1e-6f);
+                    const float a0 = __fmul_rn(acc[k][a].x, 1.f / 64.f), a1 = __fmul_rn(acc[k][a].y, 1.f / 64.f);
+                    float q0 = a0 * rcp_approx(b0), q1 = a1 * rcp_approx(b1);
+                    // a power-of-two divisor (1 where one tile covers the pixel, 2 / 4 where fully weighted tiles overlap) makes
+                    // q exact -- those are also the pixels whose quotient IS an integer, so they must not take the slow path
+                    const bool n0 = fabsf(q0 - rintf(q0)) < FINAL_NEAR && (__float_as_uint(b0) & 0x007FFFFFu) != 0u;
+                    const bool n1 = fabsf(q1 - rintf(q1)) < FINAL_NEAR && (__float_as_uint(b1) & 0x007FFFFFu) != 0u;
+                    if (n0 || n1) {
+                        q0 = __fdiv_rn(a0, b0);
+                        q1 = __fdiv_rn(a1, b1);
+                    }
+                    uint8_t *dst = out0 + r * FB_U8_STRIDE + mis;
+                    if (px_a) dst[0] = (uint8_t)f2u8_trunc_sat(q0); // clip then truncate (blending_module.py:504-506)
+                    if (px_b) dst[C] = (uint8_t)f2u8_trunc_sat(q1);
                 }
-                uint8_t *dst = out0 + r * FB_U8_STRIDE + mis;
-                if (px_a) dst[0] = (uint8_t)f2u8_trunc_sat(q0); // clip then truncate (blending_module.py:504-506)
-                if (px_b) dst[C] = (uint8_t)f2u8_trunc_sat(q1);
             }
-        }
+        };
+        if (cy1 - cy0 == FB_H && cx1 - cx0 == FB_W)
+            quantise(std::true_type{});
+        else
+            quantise(std::false_type{});
     }
     __syncthreads();
     const int n_rows = cy1 - cy0;
