@@ -17,6 +17,8 @@
 // a group shares one weight pyramid and one launch per level (grid.z = tile).
 #include "srf_common.cuh"
 
+#include <cuda.h> // CUtensorMap (types only; cuTensorMapEncodeTiled is fetched through cudaGetDriverEntryPoint)
+
 #include <algorithm>
 #include <type_traits>
 #include <string.h>
@@ -769,14 +771,15 @@ constexpr int FB_SRC_COLS = FB_PAIRS + 8;   // 136
 constexpr int FB_U8_STRIDE = FB_W * 3 + 32; // 800: payload + 16 B misalignment + slack
 
 template <int C>
-struct FinalStage { // everything the gather reads of ONE covering tile; double buffered, filled by cp.async
-    float sc[C][FB_SRC_ROWS][FB_SRC_COLS]; // C_1 window (W_1 window when the tile has exactly two levels)
-    float sg[C][FB_SRC_ROWS][FB_SRC_COLS]; // G_1 window
-    uint8_t u8[FB_H][FB_U8_STRIDE];        // uint8 tile block
+struct alignas(128) FinalStage { // everything the gather reads of ONE covering tile; double buffered; each array is the
+                                 // dense box of one TMA tensor copy (128-byte aligned) or is filled by cp.async
+    alignas(128) float sc[C][FB_SRC_ROWS][FB_SRC_COLS]; // C_1 window (W_1 window when the tile has exactly two levels)
+    alignas(128) float sg[C][FB_SRC_ROWS][FB_SRC_COLS]; // G_1 window
+    alignas(128) uint8_t u8[FB_H][FB_U8_STRIDE];        // uint8 tile block
     float nwy[FB_H];                       // -W_0 profile of the block's 16 rows (negated: see final_accumulate_tile)
 };
 template <int C>
-struct FinalSmem {
+struct alignas(128) FinalSmem {
     FinalStage<C> st[2];
     float wsum[FB_H][FB_W];
 };
@@ -809,6 +812,51 @@ __device__ __forceinline__ FinalGeo final_geo(const TileDev &t, const GroupDev &
     return q;
 }
 
+// Tiles with >= 3 levels are staged by TMA tensor copies when the launch carries their descriptors (bit ti of
+// tma_mask): one 3-D box (136 x 10 x C floats) each for the C_1 and G_1 windows and one 2-D box (800 bytes x 16 rows)
+// for the uint8 block; whatever part of a box lies outside its array arrives as zeros, which is what the gather expects
+// of out-of-array columns.  Other tiles (1 or 2 levels, no descriptor) keep the per-chunk cp.async path.
+constexpr int FINAL_TMA_TILES = 48; // descriptors travel as kernel parameters: 48 x 3 x 128 B = 18 KB of the 32 KB limit
+struct FinalTmaps {
+    CUtensorMap m[FINAL_TMA_TILES][3]; // [tile][C_1 | G_1 | uint8]
+};
+__device__ __forceinline__ bool final_tma_ok(const FinalGeo &q, unsigned long long tma_mask, int ti)
+{
+    return q.mode == 0 && ti < FINAL_TMA_TILES && ((tma_mask >> ti) & 1ull);
+}
+__device__ __forceinline__ void tma_tensor_3d_g2s(void *smem_dst, const CUtensorMap *map, int x, int y, int z, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(reinterpret_cast<unsigned long long>(map)), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tma_tensor_2d_g2s(void *smem_dst, const CUtensorMap *map, int x, int y, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(reinterpret_cast<unsigned long long>(map)), "r"(x), "r"(y), "r"(smem_u32(bar))
+                 : "memory");
+}
+// mbarrier wait that traps instead of hanging the GPU should a copy never land
+__device__ __forceinline__ void mbar_wait_or_trap(uint64_t *bar, unsigned parity)
+{
+    for (unsigned spin = 0; spin < (1u << 22); ++spin) {
+        unsigned ok;
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (ok) return;
+    }
+    __trap();
+}
+
 struct FinalParams {
     const TileDev *tiles;
     const GroupDev *groups;
@@ -819,6 +867,7 @@ struct FinalParams {
     uint8_t *canvas;
     size_t canvas_pitch;
     int row_begin, row_end;
+    unsigned long long tma_mask; // tiles whose FinalTmaps entries are valid
 };
 
 struct HPair {
@@ -849,7 +898,7 @@ __device__ __forceinline__ void final_accumulate_tile(FinalSmem<C> &S, const Fin
     const int iy0 = q.iy0, iy1 = q.iy1, ix0 = q.ix0, ix1 = q.ix1, u8_a0 = q.u8_a0, srow0 = q.srow0, n_srows = q.n_srows, sx0 = q.sx0;
     const int i0 = q.i0, ws0 = q.ws0, xpar = q.xpar, ypar = q.ypar, mode = q.mode;
     const int h1 = g.lv[1].h, w1 = g.lv[1].w;
-    const int tyf = cy0 - t.y, txf = cx0 - t.x;
+    const int txf = cx0 - t.x;
     const int txa = txf + 2 * p, txb = txa + 1; // tile columns of the thread's two canvas columns
     const bool ina = FULL || ((cx0 + 2 * p >= ix0) && (cx0 + 2 * p < ix1));
     const bool inb = FULL || ((cx0 + 2 * p + 1 >= ix0) && (cx0 + 2 * p + 1 < ix1));
@@ -1040,13 +1089,20 @@ __device__ __forceinline__ unsigned f2u8_trunc_sat(float v)
 }
 
 template <int C>
-__global__ void __launch_bounds__(128 * C, (C == 3) ? 2 : 5) k_final(FinalParams P)
+__global__ void __launch_bounds__(128 * C, (C == 3) ? 2 : 5) k_final(const __grid_constant__ FinalParams P, const __grid_constant__ FinalTmaps TM)
 {
-    extern __shared__ __align__(16) uint8_t smem_raw[];
-    FinalSmem<C> &S = *reinterpret_cast<FinalSmem<C> *>(smem_raw);
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    FinalSmem<C> &S = *reinterpret_cast<FinalSmem<C> *>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127); // +128 B are allocated
     constexpr int NT = 128 * C;
     __shared__ int s_list[NT];
     __shared__ int s_wcnt[NT / 32];
+    __shared__ __align__(8) uint64_t s_bar[2]; // completion of the TMA-staged tile in buffer 0 / 1
+    unsigned tma_phase = 0;                    // bit b: parity of the next completion of s_bar[b]
+    if (threadIdx.x == 0) {
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+        mbar_fence_init();
+    }
 
     const int cy0 = P.row_begin + blockIdx.y * FB_H;
     const int cx0 = blockIdx.x * FB_W;
@@ -1055,6 +1111,7 @@ __global__ void __launch_bounds__(128 * C, (C == 3) ? 2 : 5) k_final(FinalParams
     const int c = threadIdx.x / FB_PAIRS; // warp-uniform
     const int p = threadIdx.x % FB_PAIRS;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
 
     float2 acc[FB_STEPS][2];
 #pragma unroll
@@ -1094,6 +1151,18 @@ __global__ void __launch_bounds__(128 * C, (C == 3) ? 2 : 5) k_final(FinalParams
             if (threadIdx.x < FB_H) { // W_0 row profile of the block (blending_module.py:508-561 through the host LUT), negated
                 const int ty = cy0 + (int)threadIdx.x - t.y;
                 B.nwy[threadIdx.x] = -__ldg(g.lut + max(min(min(ty, t.h - 1 - ty), g.lut_len - 1), 0));
+            }
+            if (final_tma_ok(q, P.tma_mask, ti)) {
+                if (threadIdx.x == 0) {
+                    uint64_t *bar = &s_bar[li & 1];
+                    fence_proxy_async(); // the buffer's earlier generic-proxy accesses (ordered by the CTA barrier) before the async writes
+                    mbar_expect_tx(bar, (unsigned)(sizeof(B.sc) + sizeof(B.sg) + sizeof(B.u8)));
+                    tma_tensor_3d_g2s(&B.sc[0][0][0], &TM.m[ti][0], q.sx0, q.srow0, 0, bar);
+                    tma_tensor_3d_g2s(&B.sg[0][0][0], &TM.m[ti][1], q.sx0, q.srow0, 0, bar);
+                    tma_tensor_2d_g2s(&B.u8[0][0], &TM.m[ti][2], q.u8_a0 >> 2, cy0 - t.y, bar);
+                }
+                cp_async_commit(); // an empty group keeps the cp.async group count of the fallback path in step
+                return;
             }
             const int pitch = (int)t.pitch;
             constexpr int NW = NT / 32;
@@ -1135,19 +1204,22 @@ __global__ void __launch_bounds__(128 * C, (C == 3) ? 2 : 5) k_final(FinalParams
             cp_async_commit();
         };
 
-        if (total > 0) stage(0);
-        for (int li = 0; li < total; ++li) {
-            if (li + 1 < total) {
-                stage(li + 1); // next tile's copies fly while this tile is consumed
+        for (int li = -1; li < total; ++li) { // li = -1: prologue, stages tile 0 only (one inlined copy of the staging code)
+            if (li + 1 < total) stage(li + 1); // next tile's copies fly while this tile is consumed
+            if (li < 0) continue;
+            if (li + 1 < total)
                 cp_async_wait<1>();
-            } else {
+            else
                 cp_async_wait<0>();
-            }
-            __syncthreads(); // tile li has landed for every thread
             const int ti = s_list[li];
             const TileDev &t = P.tiles[ti];
             const GroupDev &g = P.groups[P.tile_group[ti]];
             const FinalGeo q = final_geo(t, g, cy0, cy1, cx0, cx1, C);
+            if (final_tma_ok(q, P.tma_mask, ti)) {
+                mbar_wait_or_trap(&s_bar[li & 1], (tma_phase >> (li & 1)) & 1u);
+                tma_phase ^= 1u << (li & 1);
+            }
+            __syncthreads(); // tile li has landed for every thread (cp.async groups, TMA bytes, the row-weight table)
             // block entirely inside the tile, every source window strictly inside the level-1 plane (columns and rows) and
             // even parity in both axes (tile origins are 2 * the low-resolution origin in the pipeline): no predicates
             const bool full = (q.mode == 0) && (q.iy0 == cy0) && (q.iy1 == cy0 + FB_H) && (q.ix0 == cx0) && (q.ix1 == cx0 + FB_W) &&
@@ -1222,6 +1294,24 @@ __global__ void __launch_bounds__(128 * C, (C == 3) ? 2 : 5) k_final(FinalParams
             for (int e = max(lo, p0); e < min(hi, p1); ++e) gdst[e - lo] = S.st[0].u8[r][e];
         }
     }
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point lookup (libsrfuse does not link libcuda)
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                    const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled srf_tensor_map_encoder()
+{
+    static PFN_encodeTiled fn = []() -> PFN_encodeTiled {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) != cudaSuccess || qr != cudaDriverEntryPointSuccess) {
+            (void)cudaGetLastError();
+            return nullptr;
+        }
+        return (PFN_encodeTiled)p;
+    }();
+    return fn;
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -1602,14 +1692,40 @@ int srf_fuse_device(srf_ctx *ctx, const srf_tile *tiles, int n_tiles, int C, int
         }
         // per covered tile pixel: u8 in + C_1, G_1 at quarter density; per canvas pixel: u8 out
         srf_launch_scope scope(ctx, "final_gather", cov * C * (1.0 + 2.0) + (double)(re - rb) * out_w * C, st);
+        // TMA descriptors of the level-1 planes and the uint8 source of every tile with >= 3 levels (kernel parameters)
+        static thread_local FinalTmaps TM; // 18 KB: kept off the stack; filled below before every launch
+        P.tma_mask = 0;
+        if (PFN_encodeTiled enc = srf_tensor_map_encoder()) {
+            for (int i = 0; i < n_tiles && i < FINAL_TMA_TILES; ++i) {
+                const GroupDev &g = gdev_img[tile_group[i]];
+                const TileDev &t = tdev[i];
+                if (g.n_levels < 3 || t.pitch % 16 != 0 || ((uintptr_t)t.src & 15)) continue;
+                const LevelGeom &L1 = g.lv[1];
+                const cuuint64_t dims3[3] = {(cuuint64_t)L1.pitch, (cuuint64_t)L1.h, (cuuint64_t)C};
+                const cuuint64_t str3[2] = {(cuuint64_t)L1.pitch * sizeof(float), (cuuint64_t)L1.plane * sizeof(float)};
+                const cuuint32_t box3[3] = {FB_SRC_COLS, FB_SRC_ROWS, (cuuint32_t)C}, one3[3] = {1, 1, 1};
+                const cuuint64_t dims2[2] = {(cuuint64_t)(t.pitch / 4), (cuuint64_t)t.h};
+                const cuuint64_t str2[1] = {(cuuint64_t)t.pitch};
+                const cuuint32_t box2[2] = {FB_U8_STRIDE / 4, FB_H}, one2[2] = {1, 1};
+                const bool ok =
+                    enc(&TM.m[i][0], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, t.C[1], dims3, str3, box3, one3, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS &&
+                    enc(&TM.m[i][1], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, t.G[1], dims3, str3, box3, one3, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS &&
+                    enc(&TM.m[i][2], CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<uint8_t *>(t.src), dims2, str2, box2, one2,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+                if (ok) P.tma_mask |= 1ull << i;
+            }
+        }
         if (C == 3) {
-            const size_t sm = sizeof(FinalSmem<3>);
+            const size_t sm = sizeof(FinalSmem<3>) + 128;
             SRF_CHECK_CUDA(ctx, cudaFuncSetAttribute(k_final<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-            k_final<3><<<grid, 128 * 3, sm, st>>>(P);
+            k_final<3><<<grid, 128 * 3, sm, st>>>(P, TM);
         } else {
-            const size_t sm = sizeof(FinalSmem<1>);
+            const size_t sm = sizeof(FinalSmem<1>) + 128;
             SRF_CHECK_CUDA(ctx, cudaFuncSetAttribute(k_final<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-            k_final<1><<<grid, 128, sm, st>>>(P);
+            k_final<1><<<grid, 128, sm, st>>>(P, TM);
         }
         SRF_CHECK_CUDA(ctx, cudaGetLastError());
     }
