@@ -765,10 +765,14 @@ __global__ void __launch_bounds__(UL_PAIRS) k_up_levels(const TileDev *__restric
 // MODE per tile: 0 = >= 3 levels (C_1 stored), 1 = exactly 2 levels (C_1 = G_1 * W_1 on the fly), 2 = single level
 // (C_0 = G_0 * W_0, no pyramid).
 // ------------------------------------------------------------------------------------------------------------
-constexpr int FB_W = 256, FB_H = 16, FB_PAIRS = FB_W / 2, FB_STEPS = FB_H / 2;
+#ifndef SRF_FB_W
+#define SRF_FB_W 128
+#endif
+constexpr int FB_W = SRF_FB_W, FB_H = 16, FB_PAIRS = FB_W / 2, FB_STEPS = FB_H / 2;
+constexpr int FB_CTAS_3 = (FB_W == 128) ? 4 : 2, FB_CTAS_1 = (FB_W == 128) ? 8 : 5; // resident CTAs per SM the smem / registers allow
 constexpr int FB_SRC_ROWS = FB_STEPS + 2;   // 10
 constexpr int FB_SRC_COLS = FB_PAIRS + 8;   // 136
-constexpr int FB_U8_STRIDE = FB_W * 3 + 32; // 800: payload + 16 B misalignment + slack
+constexpr int FB_U8_STRIDE = FB_W * 3 + 16; // payload + up to 15 B misalignment, a multiple of 16
 
 template <int C>
 struct alignas(128) FinalStage { // everything the gather reads of ONE covering tile; double buffered; each array is the
@@ -1089,11 +1093,11 @@ __device__ __forceinline__ unsigned f2u8_trunc_sat(float v)
 }
 
 template <int C>
-__global__ void __launch_bounds__(128 * C, (C == 3) ? 2 : 5) k_final(const __grid_constant__ FinalParams P, const __grid_constant__ FinalTmaps TM)
+__global__ void __launch_bounds__(FB_PAIRS * C, (C == 3) ? FB_CTAS_3 : FB_CTAS_1) k_final(const __grid_constant__ FinalParams P, const __grid_constant__ FinalTmaps TM)
 {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     FinalSmem<C> &S = *reinterpret_cast<FinalSmem<C> *>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127); // +128 B are allocated
-    constexpr int NT = 128 * C;
+    constexpr int NT = FB_PAIRS * C;
     __shared__ int s_list[NT];
     __shared__ int s_wcnt[NT / 32];
     __shared__ __align__(8) uint64_t s_bar[2]; // completion of the TMA-staged tile in buffer 0 / 1
@@ -1721,11 +1725,13 @@ int srf_fuse_device(srf_ctx *ctx, const srf_tile *tiles, int n_tiles, int C, int
         if (C == 3) {
             const size_t sm = sizeof(FinalSmem<3>) + 128;
             SRF_CHECK_CUDA(ctx, cudaFuncSetAttribute(k_final<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-            k_final<3><<<grid, 128 * 3, sm, st>>>(P, TM);
+            SRF_CHECK_CUDA(ctx, cudaFuncSetAttribute(k_final<3>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            k_final<3><<<grid, FB_PAIRS * 3, sm, st>>>(P, TM);
         } else {
             const size_t sm = sizeof(FinalSmem<1>) + 128;
             SRF_CHECK_CUDA(ctx, cudaFuncSetAttribute(k_final<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-            k_final<1><<<grid, 128, sm, st>>>(P, TM);
+            SRF_CHECK_CUDA(ctx, cudaFuncSetAttribute(k_final<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            k_final<1><<<grid, FB_PAIRS, sm, st>>>(P, TM);
         }
         SRF_CHECK_CUDA(ctx, cudaGetLastError());
     }
