@@ -40,7 +40,8 @@ def is_stale() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not is_stale():
         return LIB_PATH
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH + ".tmp"] + [
+    extra = os.environ.get("SRF_NVCC_EXTRA", "").split()  # tuning experiments: -DSRF_FB_W=..., -DSRF_FB_H=...
+    cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH + ".tmp"] + [
         os.path.join(CSRC, s) for s in SOURCES
     ]
     res = subprocess.run(cmd, capture_output=True, text=True)

@@ -768,8 +768,14 @@ __global__ void __launch_bounds__(UL_PAIRS) k_up_levels(const TileDev *__restric
 #ifndef SRF_FB_W
 #define SRF_FB_W 128
 #endif
-constexpr int FB_W = SRF_FB_W, FB_H = 16, FB_PAIRS = FB_W / 2, FB_STEPS = FB_H / 2;
-constexpr int FB_CTAS_3 = (FB_W == 128) ? 4 : 2, FB_CTAS_1 = (FB_W == 128) ? 8 : 5; // resident CTAs per SM the smem / registers allow
+#ifndef SRF_FB_H
+#define SRF_FB_H 16
+#endif
+#ifndef SRF_FB_CTAS
+#define SRF_FB_CTAS ((SRF_FB_W == 128) ? 4 : 2)
+#endif
+constexpr int FB_W = SRF_FB_W, FB_H = SRF_FB_H, FB_PAIRS = FB_W / 2, FB_STEPS = FB_H / 2;
+constexpr int FB_CTAS_3 = SRF_FB_CTAS, FB_CTAS_1 = 2 * SRF_FB_CTAS; // resident CTAs per SM the smem / registers allow
 constexpr int FB_SRC_ROWS = FB_STEPS + 2;   // 10
 constexpr int FB_SRC_COLS = FB_PAIRS + 8;   // 136
 constexpr int FB_U8_STRIDE = FB_W * 3 + 16; // payload + up to 15 B misalignment, a multiple of 16
