@@ -146,6 +146,18 @@ typedef struct srf_iqa_sums {
     int32_t bits_b;     /*   the caller applies the reference's `image.max() <= 1.0` rescale rule (q.a.m:192-193) */
 } srf_iqa_sums;
 
+/* ---- bicubic resize: cv2.resize(img, (dst_w, dst_h), interpolation=cv2.INTER_CUBIC) on uint8 ---------------------
+ * replaces QualityAssessmentModule.downsample_bicubic (quality_assessment_module.py:226-253) and upsample_bicubic
+ * (255-275); _evaluate_downsample_comparison (518-555) applies it to both images at 0.1x / 0.2x / 0.4x before PSNR and
+ * the 7x7-window SSIM.  Keys cubic (a = -0.75) at float64 sample positions, rounded half-to-even and saturated --
+ * what the opencv-python wheel (Intel IPP) computes; see oracle/resize_oracle.py for the pinning. */
+/* host only, exact: for each of the dst indices of one axis the 4 clamped source indices and their float32 weights */
+int srf_resize_cubic_taps(int src, int dst, int *idx4, float *w4);
+int srf_resize_cubic_u8(srf_ctx *ctx, const uint8_t *d_src, size_t src_pitch, int h, int w, int channels, uint8_t *d_dst,
+                        size_t dst_pitch, int dst_h, int dst_w, void *stream);
+int srf_resize_cubic_u8_host(srf_ctx *ctx, const uint8_t *h_src, size_t src_pitch, int h, int w, int channels,
+                             uint8_t *h_dst, size_t dst_pitch, int dst_h, int dst_w);
+
 /* replaces calculate_psnr + calculate_ssim(multiscale=True) of QualityAssessmentModule
  * (quality_assessment_module.py:277-320, 322-376) in ONE pass over the pair: integer sum of squared
  * differences over all channels, cv2-exact RGB->gray, 11-tap sigma=1.5 Gaussian SSIM (C1 = (0.01 data_range)^2,

@@ -15,5 +15,9 @@ Parity status (see DESIGN.md "Oracle"):
     reference's own fallback `_calculate_ssim_simple` (quality_assessment_module.py:391-417) and exactly
     against scipy.ndimage.gaussian_filter (what scikit-image calls) -- "parity pinned to the fallback, not to
     scikit-image itself".
+  * bicubic resize (cv2.resize INTER_CUBIC, uint8): the opencv-python wheel calls Intel IPP (closed source); restated
+    as the Keys cubic at float64 sample positions with half-to-even rounding.  PINNED against outputs of the
+    reference's own downsample_bicubic / upsample_bicubic (tests/golden) and against cv2 directly: equal on all
+    but ~4e-6 of the pixels, never more than 1 LSB apart, bit-exact for the 2x up-scale.
 """
-from . import pyr, tiling_oracle, fusion_oracle, iqa_oracle, reference_port  # noqa: F401
+from . import pyr, tiling_oracle, fusion_oracle, iqa_oracle, reference_port, resize_oracle  # noqa: F401

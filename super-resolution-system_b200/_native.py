@@ -74,6 +74,11 @@ SIGNATURES = {
     "srf_fuse_assess_host": (c_int, [c_void_p, P(srf_tile), c_int, c_int, c_int, P(srf_weight_lut), c_int, c_int, c_int,
                                      c_void_p, c_size_t, c_void_p, c_size_t, C.c_double, c_int, c_int, P(srf_iqa_sums)]),
     "srf_iqa_finish": (c_int, [P(srf_iqa_sums), C.c_double, P(C.c_double), P(C.c_double)]),
+    "srf_resize_cubic_taps": (c_int, [c_int, c_int, c_void_p, c_void_p]),
+    "srf_resize_cubic_u8": (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_int, c_int, c_void_p, c_size_t, c_int, c_int,
+                                    c_void_p]),
+    "srf_resize_cubic_u8_host": (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_int, c_int, c_void_p, c_size_t, c_int,
+                                         c_int]),
 }
 
 _lib = None

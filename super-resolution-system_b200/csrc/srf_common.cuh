@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <algorithm>
 #include <string>
 #include <vector>
 #include <map>
@@ -48,6 +49,7 @@ struct srf_ctx {
     srf_buffer ws_stage_in; // *_host entry points: device staging of inputs
     srf_buffer ws_stage_out;
     srf_buffer ws_iqa;      // IQA reduction partials
+    srf_buffer ws_tab;      // per-axis tap tables of the bicubic resize
     void *pinned = nullptr; // small pinned host block for result read-back
     size_t pinned_bytes = 0;
     cudaStream_t own_stream = nullptr; // used by the *_host entry points

@@ -2,11 +2,11 @@
 
 Mirrors /root/reference/quality_assessment_module.py: AssessmentLevel 35-41, QualityThresholds 44-75,
 ScaleConfig 78-86, QualityAssessmentModule.__init__ 107-133, _preprocess_image 169-195, calculate_psnr 277-320,
-calculate_ssim 322-389, evaluate_full_reference 467-516, _assess_* 557-588, _calculate_overall_score 590-609,
-batch_evaluate 1350-1371.  The arithmetic (scikit-image's peak_signal_noise_ratio / structural_similarity) runs in
-csrc/srf_iqa.cu (both SSIM windows: 11x11 Gaussian and scikit-image's default 7x7 uniform).  Out of scope (SURVEY.md
-section 8): LPIPS, NIQE, BRISQUE, commercial metrics, reports; the bicubic down-sample comparison keys are the rest
-of the "next" row N1.
+downsample_bicubic 226-253, upsample_bicubic 255-275, calculate_ssim 322-389, evaluate_full_reference 467-516,
+_evaluate_downsample_comparison 518-555, _assess_* 557-588, _calculate_overall_score 590-609, batch_evaluate 1350-1371.
+The arithmetic (scikit-image's peak_signal_noise_ratio / structural_similarity) runs in csrc/srf_iqa.cu (both SSIM
+windows: 11x11 Gaussian and scikit-image's default 7x7 uniform); cv2.resize(INTER_CUBIC) runs in csrc/srf_resize.cu.
+Out of scope: LPIPS, NIQE, BRISQUE, commercial metrics, reports.
 """
 from __future__ import annotations
 
@@ -188,15 +188,65 @@ class QualityAssessmentModule:
             scores.append(max(0, (1 - metrics["lpips_vgg"]) * 100))
         return float(np.mean(scores)) if scores else 0.0
 
+    # ------------------------------------------------------------------ bicubic resize (cv2.resize INTER_CUBIC)
+    def _resize_cubic(self, image, dst_w: int, dst_h: int):
+        v = ImageView(image, "image")
+        if dst_w < 1 or dst_h < 1:
+            raise ValueError(f"resize to an empty size ({dst_w}x{dst_h})")  # cv2.resize raises on an empty dsize
+        two_d = len(image.shape) == 2
+        shape = (dst_h, dst_w) if two_d else (dst_h, dst_w, v.c)
+        lib, ctx = _native.load(), _native.context(v.device if v.on_device else self.device_index)
+        if v.on_device:
+            out = torch.empty(shape, dtype=torch.uint8, device=v.keep.device)
+            rc = lib.srf_resize_cubic_u8(ctx, v.ptr, v.pitch, v.h, v.w, v.c, out.data_ptr(), dst_w * v.c, dst_h, dst_w,
+                                         current_stream_ptr(v.device))
+        else:
+            out = np.empty(shape, np.uint8)
+            rc = lib.srf_resize_cubic_u8_host(ctx, v.ptr, v.pitch, v.h, v.w, v.c, out.ctypes.data, dst_w * v.c, dst_h, dst_w)
+        _native.check(rc, ctx)
+        return out
+
+    def downsample_bicubic(self, image, scale_factor: float):
+        """cv2.resize(image, (int(w*s), int(h*s)), INTER_CUBIC) (q.a.m:226-253); uint8 NumPy array or CUDA tensor"""
+        if scale_factor >= 1.0 or scale_factor <= 0:
+            raise ValueError(f"scale_factor must lie in (0, 1), got {scale_factor}")
+        h, w = int(image.shape[0]), int(image.shape[1])
+        return self._resize_cubic(image, int(w * scale_factor), int(h * scale_factor))
+
+    def upsample_bicubic(self, image, target_size: Tuple[int, int]):
+        """cv2.resize(image, (target_size[1], target_size[0]), INTER_CUBIC) (q.a.m:255-275)"""
+        return self._resize_cubic(image, int(target_size[1]), int(target_size[0]))
+
+    def _evaluate_downsample_comparison(self, original, upscaled, scale_factor: int) -> Dict[str, float]:
+        """both images down-sampled to each scale of scale_config, then PSNR and the 7x7-window SSIM (q.a.m:518-555)"""
+        metrics = {}
+        for scale in self.scale_config.scale_factors:
+            name = self.scale_config.scale_names.get(scale, f"scale_{scale}")
+            sr, hr = self.downsample_bicubic(upscaled, scale), self.downsample_bicubic(original, scale)
+            mh, mw = min(sr.shape[0], hr.shape[0]), min(sr.shape[1], hr.shape[1])
+            sr, hr = sr[:mh, :mw], hr[:mh, :mw]
+            metrics[f"psnr_{name}"] = self.calculate_psnr(hr, sr)
+            metrics[f"ssim_{name}"] = self.calculate_ssim(hr, sr, multiscale=False)
+        return metrics
+
     def evaluate_full_reference(self, original, upscaled, scale_factor: int = 4) -> Dict[str, float]:
-        """psnr, psnr_level, ssim (7x7 uniform window), ms_ssim (= single-scale 11x11 Gaussian SSIM, the reference's
-        naming), ssim_level, overall_score.  The six bicubic down-sample comparison keys (q.a.m:518-555) are row N1
-        of SURVEY.md section 8(f), not produced yet; LPIPS keys are omitted as in the reference when its models are
-        unavailable."""
-        psnr, ssim = self.calculate_psnr_ssim(original, upscaled)
-        metrics = {"psnr": float(psnr), "ssim": self.calculate_ssim(original, upscaled, multiscale=False),
-                   "ms_ssim": float(ssim)}
+        """the reference's dict (q.a.m:467-516): psnr_/ssim_ of the three down-sampled pairs, psnr, psnr_level, ssim (7x7
+        uniform window), ms_ssim (= single-scale 11x11 Gaussian SSIM, the reference's naming), ssim_level, overall_score.
+        LPIPS keys are omitted as in the reference when its models are unavailable.  Host images are uploaded ONCE and
+        every kernel then runs on the device copies."""
+        a, b = self._preprocess_image(original), self._preprocess_image(upscaled)
+        if not is_cuda_tensor(a) and not is_cuda_tensor(b):
+            if torch is None or not torch.cuda.is_available():
+                raise _native.SrfError("evaluate_full_reference needs a CUDA device (there is no CPU fallback)")
+            dev = torch.device("cuda", self.device_index)
+            a = torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+            b = torch.from_numpy(np.ascontiguousarray(b)).to(dev)
+        metrics = dict(self._evaluate_downsample_comparison(a, b, scale_factor))
+        psnr, ssim = self.calculate_psnr_ssim(a, b)
+        metrics["psnr"] = float(psnr)
         metrics["psnr_level"] = self._assess_psnr(metrics["psnr"])
+        metrics["ssim"] = self.calculate_ssim(a, b, multiscale=False)
+        metrics["ms_ssim"] = float(ssim)
         metrics["ssim_level"] = self._assess_ssim(metrics["ms_ssim"])
         metrics["overall_score"] = self._calculate_overall_score(metrics)
         return metrics

@@ -145,6 +145,25 @@ def main():
     out["wavg_ragged_out"] = rb.BlendingModule().weighted_average_fusion(winfos, weight_type=rb.WeightType.LINEAR, output_shape=(160, 215))
     out["wavg_grid_out"] = rb.BlendingModule().weighted_average_fusion([out[f"fuse_linear6_t{i}"] for i in range(4)])
 
+    # ---- bicubic down-/up-sampling and the down-sample comparison (row N1; appended last so that the draws above
+    # keep their values).  downsample_bicubic / upsample_bicubic are cv2.resize(INTER_CUBIC), which this wheel routes to
+    # Intel IPP; the PSNR keys come from the reference's manual formula.  Its SSIM keys would come from the 11x11
+    # fallback (scikit-image is stubbed out), which is NOT the 7x7 window of multiscale=False, so they are not stored.
+    ra = synth(rng, 157, 203)
+    out["resize_src"] = ra
+    for s_ in (0.1, 0.2, 0.4):
+        out[f"resize_down_{s_}"] = qa.downsample_bicubic(ra, s_)
+    out["resize_up_2x"] = qa.upsample_bicubic(ra[:60, :70], (120, 140))
+    out["resize_up_odd"] = qa.upsample_bicubic(ra[:60, :70], (101, 93))
+    out["resize_gray_down_0.4"] = qa.downsample_bicubic(np.ascontiguousarray(ra[:, :, 1]), 0.4)
+    da = synth(rng, 300, 420)
+    db = np.clip(da.astype(np.float64) + rng.normal(0, 5, da.shape), 0, 255).astype(np.uint8)
+    out["dsc_a"], out["dsc_b"] = da, db
+    dsc = qa._evaluate_downsample_comparison(da, db, 4)
+    for k_, v_ in dsc.items():
+        if k_.startswith("psnr_"):
+            out[f"dsc_{k_}"] = np.array(v_)
+
     np.savez_compressed(os.path.join(HERE, "reference_vectors.npz"), **out)
     print("wrote", os.path.join(HERE, "reference_vectors.npz"), os.path.getsize(os.path.join(HERE, "reference_vectors.npz")) // 1024, "KiB")
     print("cv2", cv2.__version__, "numpy", np.__version__)

@@ -135,3 +135,22 @@ def test_iqa_finish_matches_oracle_formula(srs, oracle):
     assert p == pytest.approx(10 * np.log10(255.0 ** 2 / (123456 / 3000)), rel=1e-15) and q == 0.875
     s.sq_err = 0
     assert srs.QualityAssessmentModule.finish(s)[0] == float("inf")
+
+
+def test_resize_tap_tables_equal_oracle(srs, oracle):
+    """host side of srf_resize_cubic_u8: the per-axis tap tables (float64 sample positions, Keys weights) bit for bit"""
+    lib = srs._native.load()
+    for src, dst in [(1531, 153), (1013, 405), (17320, 6928), (11546, 1154), (2048, 4096), (720, 1224), (5, 20), (7, 1), (1, 3)]:
+        idx, w = np.zeros((dst, 4), np.int32), np.zeros((dst, 4), np.float32)
+        assert lib.srf_resize_cubic_taps(src, dst, idx.ctypes.data, w.ctypes.data) == 0
+        i2, w2 = oracle.resize_oracle.axis_table(src, dst)
+        assert np.array_equal(idx, i2) and np.array_equal(w.view(np.uint32), w2.view(np.uint32))
+    assert lib.srf_resize_cubic_taps(0, 4, idx.ctypes.data, w.ctypes.data) < 0
+
+
+def test_downsample_argument_errors(srs):
+    qa = srs.QualityAssessmentModule()
+    img = np.zeros((20, 20, 3), np.uint8)
+    for bad in (1.0, 0.0, -0.5, 1.5):
+        with pytest.raises(ValueError):  # quality_assessment_module.py:240-241
+            qa.downsample_bicubic(img, bad)

@@ -262,6 +262,48 @@ def test_iqa_device_path_and_evaluate(srs, oracle):
     assert len(qa.batch_evaluate([(a, b), (b, a)])) == 2
 
 
+# ------------------------------------------------------------------ bicubic resize + down-sample comparison (row N1)
+def test_resize_cubic_bit_equals_oracle_and_reference(srs, golden, oracle):
+    import torch
+    qa = srs.QualityAssessmentModule()
+    ro = oracle.resize_oracle
+    src = golden["resize_src"]
+    for s in (0.1, 0.2, 0.4):
+        got = qa.downsample_bicubic(src, s)
+        assert np.array_equal(got, ro.downsample_bicubic(src, s))          # the restatement, bit for bit
+        d = np.abs(got.astype(np.int16) - golden[f"resize_down_{s}"])      # the reference's own output (cv2 -> IPP)
+        assert d.max() <= 1 and (d != 0).mean() <= 1e-3
+    assert np.array_equal(qa.upsample_bicubic(src[:60, :70], (120, 140)), golden["resize_up_2x"])
+    assert np.array_equal(qa.upsample_bicubic(src[:60, :70], (101, 93)), ro.resize_cubic_u8(src[:60, :70], 93, 101))
+    g = np.ascontiguousarray(src[:, :, 1])
+    assert np.array_equal(qa.downsample_bicubic(g, 0.4), ro.downsample_bicubic(g, 0.4))
+    rng = np.random.default_rng(77)
+    big = synth(rng, 1500, 2100)
+    dev = qa.downsample_bicubic(torch.from_numpy(big).cuda(), 0.4)          # device path, strided views included
+    assert np.array_equal(dev.cpu().numpy(), ro.downsample_bicubic(big, 0.4))
+    view = big[3:1203, 5:1805]
+    assert np.array_equal(qa.downsample_bicubic(view, 0.2), ro.downsample_bicubic(np.ascontiguousarray(view), 0.2))
+    assert np.array_equal(qa.upsample_bicubic(big[:300, :400], (600, 800)), ro.resize_cubic_u8(big[:300, :400], 800, 600))
+    with pytest.raises(ValueError):
+        qa.downsample_bicubic(np.zeros((5, 5, 3), np.uint8), 0.1)            # int(5 * 0.1) == 0: cv2 rejects an empty dsize
+
+
+def test_evaluate_full_reference_has_every_key(srs, golden, oracle):
+    qa = srs.QualityAssessmentModule()
+    a, b = golden["dsc_a"], golden["dsc_b"]
+    rep = qa.evaluate_full_reference(a, b)
+    want = oracle.resize_oracle.downsample_comparison(a, b)
+    assert list(rep)[:6] == ["psnr_structure_color", "ssim_structure_color", "psnr_mid_frequency", "ssim_mid_frequency",
+                             "psnr_high_frequency", "ssim_high_frequency"]          # the reference's key order
+    for k, v in want.items():
+        assert rep[k] == pytest.approx(v, rel=REL), k
+    for name in ("structure_color", "mid_frequency", "high_frequency"):              # the reference's own numbers
+        assert rep[f"psnr_{name}"] == pytest.approx(float(golden[f"dsc_psnr_{name}"]), rel=REL)
+    assert rep["psnr"] == pytest.approx(oracle.iqa_oracle.psnr(a, b), rel=1e-12)
+    assert rep["ms_ssim"] == pytest.approx(oracle.iqa_oracle.ssim(a, b), rel=REL)
+    assert rep["ssim"] == pytest.approx(oracle.iqa_oracle.ssim_uniform(a, b), rel=REL)
+
+
 # ------------------------------------------------------------------ end to end
 def test_pipeline_run_small(srs, oracle):
     rng = np.random.default_rng(40)

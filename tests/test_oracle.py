@@ -155,3 +155,56 @@ def test_weighted_average_is_single_level_fusion(golden, oracle):
     t4 = [golden[f"fuse_linear6_t{i}"] for i in range(4)]
     got = oracle.fusion_oracle.laplacian_fuse(t4, [(0, 0), (0, 64), (64, 0), (64, 64)], (128, 128), 1, "cosine", "c")
     assert np.array_equal(got, golden["wavg_grid_out"])
+
+
+# ------------------------------------------------------------------ bicubic resize (cv2.resize INTER_CUBIC; row N1)
+def _resize_agreement(got, want):
+    d = np.abs(got.astype(np.int16) - want.astype(np.int16))
+    return int(d.max()), float((d != 0).mean())
+
+
+def test_resize_oracle_matches_reference_vectors(golden, oracle):
+    """downsample_bicubic / upsample_bicubic outputs of the reference module (cv2 4.13 -> Intel IPP): the restatement
+    may differ by one LSB on a handful of rounding ties (IPP's internal order is unknown), nowhere by more"""
+    ro = oracle.resize_oracle
+    src = golden["resize_src"]
+    total = bad = 0
+    cases = [(ro.downsample_bicubic(src, s), golden[f"resize_down_{s}"]) for s in (0.1, 0.2, 0.4)]
+    cases.append((ro.resize_cubic_u8(src[:60, :70], 140, 120), golden["resize_up_2x"]))
+    cases.append((ro.resize_cubic_u8(src[:60, :70], 93, 101), golden["resize_up_odd"]))
+    cases.append((ro.downsample_bicubic(np.ascontiguousarray(src[:, :, 1]), 0.4), golden["resize_gray_down_0.4"]))
+    for got, want in cases:
+        assert got.shape == want.shape and got.dtype == np.uint8
+        mx, frac = _resize_agreement(got, want)
+        assert mx <= 1
+        total += want.size
+        bad += int(round(frac * want.size))
+    assert bad / total <= 2e-4
+    assert np.array_equal(cases[3][0], cases[3][1])  # the 2x up-scale (the SR stand-in) is exact
+
+
+def test_resize_oracle_vs_cv2_shapes(oracle):
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(12)
+    total = bad = 0
+    for (h, w, c) in [(233, 317, 3), (120, 90, 1), (64, 48, 3), (19, 400, 3)]:
+        img = synth(rng, h, w, c)
+        for sc in (0.1, 0.2, 0.4, 2.0, 1.3):
+            dh, dw = int(h * sc), int(w * sc)
+            if dh < 1 or dw < 1:
+                continue
+            want = cv2.resize(img, (dw, dh), interpolation=cv2.INTER_CUBIC)
+            got = oracle.resize_oracle.resize_cubic_u8(img, dw, dh)
+            mx, frac = _resize_agreement(got, want)
+            assert mx <= 1, (h, w, c, sc)
+            total += want.size
+            bad += int(round(frac * want.size))
+    assert bad / total <= 1e-4
+
+
+def test_downsample_comparison_psnr_matches_reference(golden, oracle):
+    """the psnr_* keys of _evaluate_downsample_comparison (q.a.m:518-555), produced by the reference itself"""
+    got = oracle.resize_oracle.downsample_comparison(golden["dsc_a"], golden["dsc_b"])
+    for name in ("structure_color", "mid_frequency", "high_frequency"):
+        assert got[f"psnr_{name}"] == pytest.approx(float(golden[f"dsc_psnr_{name}"]), rel=1e-5)
+        assert 0 < got[f"ssim_{name}"] <= 1
