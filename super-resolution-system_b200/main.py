@@ -1,10 +1,11 @@
 """Pipeline facade with the reference's API surface (/root/reference/main.py: PipelineConfig 47-75,
 PipelineResult 78-89, SuperResolutionPipeline 92-441).
 
-Stages 1 (tiling), 3 (Laplacian fusion) and 4 (PSNR / SSIM) run on the B200 through libsrfuse.  Stage 2 -- the remote
-Seedream / Volcano Ark super-resolution call -- is out of scope and replaced by the deterministic bicubic stub the
-benchmark contract prescribes (cv2.resize INTER_CUBIC, the reference's own `upsample_bicubic`,
-quality_assessment_module.py:255-275).  The reference's agent scheduler, HTTP clients, caches and UI are not part of
+Stages 1 (tiling), 3 (Laplacian fusion) and 4 (the full-reference report) run on the B200 through libsrfuse.  Stage 2 --
+the remote Seedream / Volcano Ark super-resolution call -- is out of scope and replaced by the deterministic bicubic
+stub the benchmark contract prescribes (cv2.resize INTER_CUBIC, the reference's own `upsample_bicubic`,
+quality_assessment_module.py:255-275), which also runs on the GPU (csrc/srf_resize.cu); with the stub in place `run`
+uploads the source image once and every stage works on device-resident tensors.  The reference's agent scheduler, HTTP clients, caches and UI are not part of
 this package.  As shipped the reference's main.py cannot be imported; the data flow below is
 the one its three algorithm modules support: tile positions x2, TileInfo(image, x, y, row, col), ndarray canvases.
 """
@@ -20,6 +21,7 @@ from typing import Any, Callable, Dict, List, Optional
 
 import numpy as np
 
+from ._arrays import is_cuda_tensor, torch
 from .blending_module import BlendingModule, TileInfo
 from .quality_assessment_module import QualityAssessmentModule
 from .tiling_module import Tile, TilingModule, _read_rgb
@@ -57,10 +59,17 @@ class PipelineResult:
     error_message: Optional[str]
 
 
-def bicubic_stub(image: np.ndarray, size_hw) -> np.ndarray:
-    """deterministic stand-in for the remote super-resolution call"""
-    import cv2
-    return cv2.resize(image, (int(size_hw[1]), int(size_hw[0])), interpolation=cv2.INTER_CUBIC)
+_stub_qm: Optional[QualityAssessmentModule] = None
+
+
+def bicubic_stub(image, size_hw):
+    """deterministic stand-in for the remote super-resolution call: cv2.resize(image, (w, h), INTER_CUBIC) computed on
+    the GPU (srf_resize_cubic_u8; bit-identical to cv2 for the 2x tile up-scale).  NumPy in -> NumPy out, CUDA tensor
+    in -> CUDA tensor out."""
+    global _stub_qm
+    if _stub_qm is None:
+        _stub_qm = QualityAssessmentModule()
+    return _stub_qm.upsample_bicubic(image, (int(size_hw[0]), int(size_hw[1])))
 
 
 class SuperResolutionPipeline:
@@ -101,9 +110,20 @@ class SuperResolutionPipeline:
 
     # ------------------------------------------------------------------ the five stages, synchronous
     def run(self, image: np.ndarray, reference: Optional[np.ndarray] = None) -> Dict[str, Any]:
-        """tile -> stub-upscale -> fuse -> assess on an in-memory RGB image; returns canvas + metrics + tile count"""
+        """tile -> stub-upscale -> fuse -> assess on an in-memory RGB image; returns canvas + metrics + tile count.
+        With the built-in bicubic stub the image is uploaded once and all four stages run on device tensors (the report
+        is then the complete evaluate_full_reference dict); a user-supplied `upscaler` works on host arrays."""
         cfg = self.config
-        tw, th = self._calculate_target_size((image.shape[1], image.shape[0]), cfg.target_resolution)
+        bm = self.blending_module
+        if bm.method.value == "poisson":
+            raise NotImplementedError("blend_method='poisson' is outside the B200 hot path (SURVEY.md section 8)")
+        on_device = self.upscaler is bicubic_stub and torch is not None and torch.cuda.is_available()
+        if on_device:
+            dev = torch.device("cuda", bm.device)
+            to_dev = lambda a: a if is_cuda_tensor(a) else torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
+            image = to_dev(image)
+            reference = None if reference is None else to_dev(reference)
+        tw, th = self._calculate_target_size((int(image.shape[1]), int(image.shape[0])), cfg.target_resolution)
         half = bicubic_stub(image, (th // 2, tw // 2))  # the tiler works at half the target scale (SR doubles a tile)
         tiles: List[Tile] = self.tiling_module.split_array(half)
         out = self.tiling_module.output_size
@@ -113,16 +133,20 @@ class SuperResolutionPipeline:
             m = t.metadata
             up = self.upscaler(t.data, (out, out))
             infos.append(TileInfo(up, 2 * m.global_x, 2 * m.global_y, m.global_y // step, m.global_x // step))
-        canvas_hw = (2 * half.shape[0], 2 * half.shape[1])
-        if cfg.enable_qa:
+        canvas_hw = (2 * int(half.shape[0]), 2 * int(half.shape[1]))
+        fuse = bm.weighted_average_fusion if bm.method.value == "weighted" else bm.laplacian_fusion
+        report = None
+        if on_device:
+            canvas_d = fuse(infos, output_shape=canvas_hw)
+            if cfg.enable_qa:
+                ref = reference if reference is not None else bicubic_stub(image, canvas_hw)
+                report = self.quality_module.evaluate_full_reference(ref, canvas_d, scale_factor=2)
+            canvas = canvas_d.cpu().numpy()
+        elif cfg.enable_qa:
             ref = reference if reference is not None else bicubic_stub(image, canvas_hw)
             canvas, report = self.fuse_and_assess(infos, ref, canvas_hw)
         else:
-            bm = self.blending_module
-            if bm.method.value == "poisson":
-                raise NotImplementedError("blend_method='poisson' is outside the B200 hot path (SURVEY.md section 8)")
-            fuse = bm.weighted_average_fusion if bm.method.value == "weighted" else bm.laplacian_fusion
-            canvas, report = fuse(infos, output_shape=canvas_hw), None
+            canvas = fuse(infos, output_shape=canvas_hw)
         return {"canvas": canvas, "report": report, "tiles": len(tiles)}
 
     def fuse_and_assess(self, tile_infos: List[TileInfo], reference: np.ndarray, output_shape=None, out=None):

@@ -319,6 +319,21 @@ def test_pipeline_run_small(srs, oracle):
     assert res_w["report"]["psnr"] > res["report"]["psnr"] - 20
 
 
+def test_pipeline_device_resident_equals_host_upscaler(srs):
+    """run() with the built-in stub keeps every stage on the device; a user upscaler (cv2 on the host) takes the host
+    path -- the 2x bicubic up-scale is bit-identical, so both give the same canvas"""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(43)
+    src = synth(rng, 120, 200)
+    cfg = srs.PipelineConfig(block_size=128, overlap_ratio=0.2, target_resolution="800x480", num_pyramid_levels=5)
+    dev = srs.SuperResolutionPipeline(cfg).run(src)
+    host = srs.SuperResolutionPipeline(cfg, upscaler=lambda t, hw: cv2.resize(t, (hw[1], hw[0]), interpolation=cv2.INTER_CUBIC)).run(src)
+    assert dev["tiles"] == host["tiles"] and np.array_equal(dev["canvas"], host["canvas"])
+    assert {"psnr_structure_color", "ssim_high_frequency", "psnr", "ssim", "ms_ssim", "overall_score"} <= set(dev["report"])
+    assert dev["report"]["psnr"] == pytest.approx(host["report"]["psnr"], rel=1e-12)
+    assert dev["report"]["ms_ssim"] == pytest.approx(host["report"]["ms_ssim"], rel=1e-6)
+
+
 def test_fuse_and_assess_band_pipeline_equals_two_calls(srs):
     """the pipelined host entry point (several bands, three streams) returns the bytes and sums of the plain calls"""
     rng = np.random.default_rng(41)
