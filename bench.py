@@ -266,8 +266,10 @@ def run_b200(args, wl):
     roofline = {"bound": "hbm", "kernel": top["kernel"], "achieved": top["GBps"], "peak": peak, "unit": "GB/s",
                 "frac": top["frac_of_peak"], "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": top["algorithmic_GB_per_step"] * 1e9 / max(top["launches_per_step"], 1),
-                "note": "final_gather and psnr_ssim are instruction-issue bound (ncu: issue-active 65 % / 87 %, DRAM 15 % / 8 %): "
-                        "their DRAM traffic equals the algorithmic bytes, the gap to the HBM roofline is arithmetic, not re-reads",
+                "note": "final_gather and psnr_ssim are instruction / on-chip bound, not HBM bound (ncu, profiles/"
+                        "r01_ncu_full_final2_summary.txt: issue-active 59 % / 77 %, smem data pipe 55 % / FMA pipe 61 %, "
+                        "DRAM 20 % / 11 %): their DRAM traffic equals the algorithmic bytes, the gap to the HBM roofline is "
+                        "arithmetic, not re-reads",
                 "share_of_step": top["ms_per_step"] / (ms_prof / args.steps),
                 "whole_step": {"algorithmic_GB": (wl.tile_bytes + 3 * H * W + 6 * H * W) / 1e9,
                                "GBps": (wl.tile_bytes + 9 * H * W) / 1e9 / (ms_step / 1e3),

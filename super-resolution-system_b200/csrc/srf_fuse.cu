@@ -467,7 +467,8 @@ constexpr int DF_BW = 128, DF_ROWS = 32, DF_BATCH = 8;
 constexpr int DF_COLS = 2 * DF_BW + 8; // staged floats per row: columns [2*ox0 - 4, 2*ox0 + 260)
 
 template <bool WEIGHT>
-__global__ void __launch_bounds__(DF_BW) k_down_f32s(const TileDev *__restrict__ tiles, const int *__restrict__ tile_ids, GroupDev g, int l)
+__global__ void __launch_bounds__(DF_BW) k_down_f32s(const TileDev *__restrict__ tiles, const int *__restrict__ tile_ids, GroupDev g, int l,
+                                                     int rows_per_cta)
 {
     __shared__ __align__(128) float s_in[2][DF_BATCH][DF_COLS];
     __shared__ __align__(8) uint64_t s_bar[2];
@@ -494,10 +495,10 @@ __global__ void __launch_bounds__(DF_BW) k_down_f32s(const TileDev *__restrict__
         cn_ref = g.cn;
         xlim = t.gx1[l + 1];
     }
-    const int oy0 = r0 + blockIdx.y * DF_ROWS;
+    const int oy0 = r0 + blockIdx.y * rows_per_cta;
     const int ox0 = blockIdx.x * DF_BW;
     if (oy0 >= r1 || ox0 >= ow || ox0 >= xlim) return;
-    const int oy1 = min(oy0 + DF_ROWS, r1);
+    const int oy1 = min(oy0 + rows_per_cta, r1);
     const int in_y0 = 2 * oy0 - 2;
     const int in_x0 = 2 * ox0 - 4; // multiple of 4
     const int n_in_rows = 2 * (oy1 - oy0) + 3;
@@ -1324,6 +1325,16 @@ static PFN_encodeTiled srf_tensor_map_encoder()
     return fn;
 }
 
+// k_down_f32s streams DOWN rows_per_cta output rows per CTA.  32 rows amortise the 3-row vertical halo; a small level (or a
+// thin band of a big one) would then be a handful of long-running CTAs on a mostly idle GPU, so the rows are cut until
+// the grid fills the SMs a few times over -- the level then costs one short CTA lifetime instead of a long one
+static int df_rows_per_cta(const srf_ctx *ctx, int ctas_per_row_block, int rows)
+{
+    int rpc = DF_ROWS;
+    while (rpc > DF_BATCH && (long long)ctas_per_row_block * srf_ceil_div(rows, rpc) < 4LL * ctx->sm_count) rpc /= 2;
+    return rpc;
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------------------
@@ -1627,9 +1638,10 @@ int srf_fuse_device(srf_ctx *ctx, const srf_tile *tiles, int n_tiles, int C, int
         // weight pyramid (full planes; tiny next to the image work, and shared by the whole group)
         for (int l = 0; l + 1 < n && !w_valid[k]; ++l) {
             if (l >= 1) { // W_l -> W_{l+1}: the streaming kernel; W_0 -> W_1 reads the profile, not a plane
-                dim3 sgrid(srf_ceil_div(gw.lv[l + 1].w, DF_BW), srf_ceil_div(gw.lv[l + 1].h, DF_ROWS), 1);
+                const int rpc = df_rows_per_cta(ctx, srf_ceil_div(gw.lv[l + 1].w, DF_BW), gw.lv[l + 1].h);
+                dim3 sgrid(srf_ceil_div(gw.lv[l + 1].w, DF_BW), srf_ceil_div(gw.lv[l + 1].h, rpc), 1);
                 srf_launch_scope scope(ctx, "down_weight", 4.0 * ((double)gw.lv[l].h * gw.lv[l].w + (double)gw.lv[l + 1].h * gw.lv[l + 1].w), st);
-                k_down_f32s<true><<<sgrid, DF_BW, 0, st>>>(d_tiles, ids_k, gw, l);
+                k_down_f32s<true><<<sgrid, DF_BW, 0, st>>>(d_tiles, ids_k, gw, l, rpc);
                 continue;
             }
             dim3 grid(srf_ceil_div(gw.lv[l + 1].w, DN_BW), srf_ceil_div(gw.lv[l + 1].h, DN_BH), 1);
@@ -1653,11 +1665,12 @@ int srf_fuse_device(srf_ctx *ctx, const srf_tile *tiles, int n_tiles, int C, int
         for (int l = 1; l + 1 < n; ++l) {
             const int rows = max_rows(l + 1, false);
             if (rows <= 0) continue;
-            dim3 grid(srf_ceil_div(gi.lv[l + 1].w, DF_BW), srf_ceil_div(rows, DF_ROWS), nt * C);
+            const int rpc = df_rows_per_cta(ctx, srf_ceil_div(gi.lv[l + 1].w, DF_BW) * nt * C, rows);
+            dim3 grid(srf_ceil_div(gi.lv[l + 1].w, DF_BW), srf_ceil_div(rows, rpc), nt * C);
             double pxo = 0;
             for (int ti : groups[k].tiles) pxo += (double)(tdev[ti].g1[l + 1] - tdev[ti].g0[l + 1]) * std::min(gi.lv[l + 1].w, tdev[ti].gx1[l + 1]);
             srf_launch_scope scope(ctx, "down_f32", pxo * C * (16.0 + 4.0), st);
-            k_down_f32s<false><<<grid, DF_BW, 0, st>>>(d_tiles, ids_k, gi, l);
+            k_down_f32s<false><<<grid, DF_BW, 0, st>>>(d_tiles, ids_k, gi, l, rpc);
         }
         // up: l = n-2 .. 1
         for (int l = n - 2; l >= 1; --l) {
