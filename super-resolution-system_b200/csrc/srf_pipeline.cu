@@ -38,7 +38,9 @@ extern "C" int srf_fuse_assess_host(srf_ctx *ctx, const srf_tile *tiles, int n_t
     int rc = srf_check_fuse_args(ctx, tiles, n_tiles, channels, levels, luts, n_luts, out_h, out_w, h_canvas, canvas_pitch, row_begin, row_end);
     if (rc) return rc;
     // rows to FUSE: the requested band plus the SSIM halo (a rank of a band-sharded job needs its neighbours' 5 rows)
-    const int F0 = std::max(row_begin - 5, 0), F1 = (row_end > row_begin) ? std::min(row_end + 5, out_h) : F0;
+    // (the start is rounded down to an even row: tile origins are even in the pipeline, and the gather's predicate-free
+    // interior path needs blocks of even parity -- an odd band start would push every block onto the generic path)
+    const int F0 = std::max(row_begin - 5, 0) & ~1, F1 = (row_end > row_begin) ? std::min(row_end + 5, out_h) : F0;
     SRF_REQUIRE(ctx, h_reference && h_out, "srf_fuse_assess_host: null pointer");
     SRF_REQUIRE(ctx, reference_pitch >= (size_t)out_w * channels, "srf_fuse_assess_host: reference pitch < row bytes");
     SRF_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -68,7 +70,7 @@ extern "C" int srf_fuse_assess_host(srf_ctx *ctx, const srf_tile *tiles, int n_t
 
     // ---- bands ----
     const int nb = std::max(1, std::min(kMaxBands, (F1 - F0) / 1024));
-    const int per = std::max(1, (F1 - F0 + nb - 1) / nb);
+    const int per = (int)srf_align_up((size_t)std::max(1, (F1 - F0 + nb - 1) / nb), 16); // sub-bands start on even rows too
     auto band_lo = [&](int b) { return std::min(F0 + b * per, F1); };
     auto band_hi = [&](int b) { return std::min(F0 + (b + 1) * per, F1); };
     auto own_lo = [&](int b) { return std::max(band_lo(b), row_begin); }; // the part of a sub-band the caller asked for

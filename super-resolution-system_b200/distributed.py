@@ -22,23 +22,64 @@ def band(rank: int, world: int, rows: int) -> Tuple[int, int]:
     return min(rank * per, rows), min((rank + 1) * per, rows)
 
 
-def balanced_bands(world: int, rows: int, cols: int, positions_yx, sizes_hw) -> List[Tuple[int, int]]:
-    """Cut the canvas rows into `world` contiguous bands of equal COST rather than equal height.  A canvas row costs
-    one unit of per-pixel work (assessment + canvas write) plus one unit per covering tile (gather + that tile's
-    pyramid rows); with 20-30 % tile overlap the doubly covered rows are ~60 % dearer, and equal-height bands leave
-    the ranks that own an overlap zone ~20 % slower than the rest.  0.65 : 1 is the measured ratio of the two terms
-    on B200 (profiles/README.md)."""
+def balanced_bands(world: int, rows: int, cols: int, positions_yx, sizes_hw, row_cost: float = 2.5,
+                   tile_cost: float = 110.0) -> List[Tuple[int, int]]:
+    """Cut the canvas rows into `world` contiguous bands of equal COST rather than equal height.  Cost of a band, in
+    units of "one tile covering one full canvas row":
+        row_cost per canvas row        the per-pixel work: assessment, the canvas write and the gather's per-block part
+      + 1 per covering tile and row    the gather's per-tile work (scaled by the covered fraction of the row)
+      + tile_cost per tile touched     what a band pays for every tile it reaches at all, however few rows: that tile's
+                                       coarse pyramid levels and halo rows (scaled by tile width / 4096)
+    The constants are the per-rank kernel times of the 8-band 200 MP job measured with profiles/band_probe.py
+    (0.22 us per canvas row, 0.074 us per covered row, ~8 us per touched 4096-wide tile): at that band height the
+    pyramid kernels are launch-latency bound, i.e. a per-tile constant, not a per-row cost.  The cuts minimise the
+    most expensive band (binary search on the bound, greedy fill)."""
     import numpy as np
-    cost = np.full(rows, 0.65)
+    if world <= 1 or rows <= 0:
+        return [(0, max(rows, 0))] + [(max(rows, 0), max(rows, 0))] * (max(world, 1) - 1)
+    per_row = np.full(rows, float(row_cost))
+    tiles = []
     for (y, x), (h, w) in zip(positions_yx, sizes_hw):
-        wfrac = max(0, min(cols, x + w) - max(0, x)) / cols
-        cost[max(0, y):min(rows, y + h)] += wfrac
-    cum = np.concatenate([[0.0], np.cumsum(cost)])
-    cuts = [0]
-    for k in range(1, world):
-        cuts.append(max(int(np.searchsorted(cum, cum[-1] * k / world)), cuts[-1]))
-    cuts.append(rows)
-    return [(min(a, rows), min(b, rows)) for a, b in zip(cuts[:-1], cuts[1:])]
+        wc = max(0, min(cols, x + w) - max(0, x))
+        if wc == 0 or y >= rows or y + h <= 0:
+            continue
+        per_row[max(0, y):min(rows, y + h)] += wc / cols
+        tiles.append((y, y + h, tile_cost * wc / 4096.0))
+    cum = np.concatenate([[0.0], np.cumsum(per_row)])
+
+    def cost(r0, r1):
+        e0, e1 = r0 - IQA_HALO, r1 + IQA_HALO
+        return cum[r1] - cum[r0] + sum(f for (y0, y1, f) in tiles if y0 < e1 and y1 > e0)
+
+    def fill(bound):
+        """greedy: every band as tall as `bound` allows; None if more than `world` bands would be needed"""
+        cuts, s = [0], 0
+        for _ in range(world):
+            lo, hi = s, rows  # largest e with cost(s, e) <= bound (cost is monotone in e)
+            if cost(s, min(s + 1, rows)) > bound:
+                return None
+            while lo < hi:
+                mid = (lo + hi + 1) // 2
+                if cost(s, mid) <= bound:
+                    lo = mid
+                else:
+                    hi = mid - 1
+            s = lo
+            cuts.append(s)
+            if s >= rows:
+                break
+        return cuts if cuts[-1] >= rows else None
+
+    lo_b, hi_b = cost(0, rows) / world, cost(0, rows)
+    for _ in range(40):
+        mid = 0.5 * (lo_b + hi_b)
+        if fill(mid) is None:
+            lo_b = mid
+        else:
+            hi_b = mid
+    cuts = fill(hi_b)
+    cuts += [rows] * (world + 1 - len(cuts))
+    return [(a, b) for a, b in zip(cuts[:-1], cuts[1:])]
 
 
 def widen(band_rows: Tuple[int, int], rows: int) -> Tuple[int, int]:
@@ -46,7 +87,10 @@ def widen(band_rows: Tuple[int, int], rows: int) -> Tuple[int, int]:
     r0, r1 = band_rows
     if r0 >= r1:
         return r0, r0
-    return max(r0 - IQA_HALO, 0), min(r1 + IQA_HALO, rows)
+    # the start is rounded down to an even row: tile origins are even (2 x the low-resolution origin), and the gather
+    # kernel's predicate-free interior path needs canvas blocks of even parity relative to the tile -- an odd start
+    # puts every block of the band on the generic path (+60 % on that kernel)
+    return max(r0 - IQA_HALO, 0) & ~1, min(r1 + IQA_HALO, rows)
 
 
 def fuse_rows(rank: int, world: int, rows: int) -> Tuple[int, int]:
