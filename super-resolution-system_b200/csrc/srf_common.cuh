@@ -118,6 +118,26 @@ int srf_reserve_pinned(srf_ctx *ctx, size_t bytes);
 static inline int srf_ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline size_t srf_align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+#ifdef __CUDACC__
+// kernel launch with the programmatic-stream-serialization attribute (see pdl_enter): the launch latency and the ramp of a
+// kernel overlap the tail of its predecessor -- what the short, dependent launches of the pyramid levels are made of
+template <typename... KArgs, typename... Args>
+static inline cudaError_t srf_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#endif
+
 // ---- index maps -------------------------------------------------------------------------------------------
 // cv2 BORDER_REFLECT_101 with multi-bounce (index i on an axis of length n)
 __host__ __device__ __forceinline__ int srf_reflect101(int i, int n)
@@ -172,6 +192,16 @@ __device__ __forceinline__ float up_h_sample(int tx, int w, At at)
     if (i == 0) return up_even_left(p, at(1));
     if (i == w - 1) return up_even_right(at(i - 1), p);
     return up_even(at(i - 1), p, at(i + 1));
+}
+
+// ---- programmatic dependent launch: every kernel of the chain starts with pdl_enter().  launch_dependents lets the NEXT
+// kernel of the stream be scheduled while this grid is still running (its CTAs become resident as SMs drain);
+// griddepcontrol.wait then holds it until the PREVIOUS grid has completed and flushed its memory, so nothing before the
+// wait may touch global data.  Without the launch attribute both instructions are no-ops. ------------------------------
+__device__ __forceinline__ void pdl_enter()
+{
+    asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
+    asm volatile("griddepcontrol.wait;\n" ::: "memory");
 }
 
 // ---- cp.async (LDGSTS) helpers: 16-byte global -> shared copies that need no registers across the latency ------

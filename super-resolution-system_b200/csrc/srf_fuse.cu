@@ -120,6 +120,7 @@ __device__ __forceinline__ uint4 load_u8_chunk(const uint8_t *grow, int o, int v
 template <int C>
 __global__ void __launch_bounds__(128 * C) k_down_u8(const TileDev *__restrict__ tiles, const int *__restrict__ tile_ids, GroupDev g)
 {
+    pdl_enter(); // programmatic dependent launch: nothing above this line may touch global data
     __shared__ __align__(16) uint8_t s_pl[2][D8_BATCH][C][D8_PSTRIDE];
     constexpr int NT = 128 * C;
 
@@ -239,6 +240,7 @@ template <bool WEIGHT>
 __global__ void __launch_bounds__(kThreads) k_down_weight0(const TileDev *__restrict__ tiles, const int *__restrict__ tile_ids, GroupDev g,
                                                        int l /* source level */)
 {
+    pdl_enter(); // programmatic dependent launch: nothing above this line may touch global data
     __shared__ __align__(16) float s_in[DN_IN_ROWS][DN_IN_COLS_F32];
     __shared__ float s_h[DN_IN_ROWS][DN_BW];
 
@@ -362,6 +364,7 @@ __device__ __forceinline__ SrcWin src_window(int ty0, int ty1, int tx0, int h1)
 template <bool TOP>
 __global__ void __launch_bounds__(kThreads) k_up_level_top(const TileDev *__restrict__ tiles, const int *__restrict__ tile_ids, GroupDev g, int l)
 {
+    pdl_enter(); // programmatic dependent launch: nothing above this line may touch global data
     __shared__ __align__(16) float s_c[UP_SRC_ROWS][UP_SRC_COLS];
     __shared__ __align__(16) float s_g[UP_SRC_ROWS][UP_SRC_COLS];
     __shared__ __align__(16) float s_hc[UP_SRC_ROWS][UP_BW];
@@ -470,6 +473,7 @@ template <bool WEIGHT>
 __global__ void __launch_bounds__(DF_BW) k_down_f32s(const TileDev *__restrict__ tiles, const int *__restrict__ tile_ids, GroupDev g, int l,
                                                      int rows_per_cta)
 {
+    pdl_enter(); // programmatic dependent launch: nothing above this line may touch global data
     __shared__ __align__(128) float s_in[2][DF_BATCH][DF_COLS];
     __shared__ __align__(8) uint64_t s_bar[2];
 
@@ -627,6 +631,7 @@ __device__ __forceinline__ HPair2 up_pair_even_origin(float s0, float s1, float 
 
 __global__ void __launch_bounds__(UL_PAIRS) k_up_levels(const TileDev *__restrict__ tiles, const int *__restrict__ tile_ids, GroupDev g, int l)
 {
+    pdl_enter(); // programmatic dependent launch: nothing above this line may touch global data
     __shared__ __align__(16) float s_c[UL_SRC_ROWS][UL_SRC_COLS];
     __shared__ __align__(16) float s_g[UL_SRC_ROWS][UL_SRC_COLS];
 
@@ -1102,6 +1107,7 @@ __device__ __forceinline__ unsigned f2u8_trunc_sat(float v)
 template <int C>
 __global__ void __launch_bounds__(FB_PAIRS * C, (C == 3) ? FB_CTAS_3 : FB_CTAS_1) k_final(const __grid_constant__ FinalParams P, const __grid_constant__ FinalTmaps TM)
 {
+    pdl_enter(); // programmatic dependent launch: nothing above this line may touch global data
     extern __shared__ __align__(128) uint8_t smem_raw[];
     FinalSmem<C> &S = *reinterpret_cast<FinalSmem<C> *>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127); // +128 B are allocated
     constexpr int NT = FB_PAIRS * C;
@@ -1641,12 +1647,12 @@ int srf_fuse_device(srf_ctx *ctx, const srf_tile *tiles, int n_tiles, int C, int
                 const int rpc = df_rows_per_cta(ctx, srf_ceil_div(gw.lv[l + 1].w, DF_BW), gw.lv[l + 1].h);
                 dim3 sgrid(srf_ceil_div(gw.lv[l + 1].w, DF_BW), srf_ceil_div(gw.lv[l + 1].h, rpc), 1);
                 srf_launch_scope scope(ctx, "down_weight", 4.0 * ((double)gw.lv[l].h * gw.lv[l].w + (double)gw.lv[l + 1].h * gw.lv[l + 1].w), st);
-                k_down_f32s<true><<<sgrid, DF_BW, 0, st>>>(d_tiles, ids_k, gw, l, rpc);
+                srf_launch_pdl(k_down_f32s<true>, sgrid, dim3(DF_BW), 0, st, d_tiles, ids_k, gw, l, rpc);
                 continue;
             }
             dim3 grid(srf_ceil_div(gw.lv[l + 1].w, DN_BW), srf_ceil_div(gw.lv[l + 1].h, DN_BH), 1);
             srf_launch_scope scope(ctx, "down_weight", 4.0 * ((l ? (double)gw.lv[l].h * gw.lv[l].w : 0.0) + (double)gw.lv[l + 1].h * gw.lv[l + 1].w), st);
-            k_down_weight0<true><<<grid, kThreads, 0, st>>>(d_tiles, ids_k, gw, l);
+            srf_launch_pdl(k_down_weight0<true>, grid, dim3(kThreads), 0, st, d_tiles, ids_k, gw, l);
         }
         // image pyramids, down
         if (n >= 2) {
@@ -1657,9 +1663,9 @@ int srf_fuse_device(srf_ctx *ctx, const srf_tile *tiles, int n_tiles, int C, int
                 for (int ti : groups[k].tiles) px1 += (double)(tdev[ti].g1[1] - tdev[ti].g0[1]) * std::min(gi.lv[1].w, tdev[ti].gx1[1]);
                 srf_launch_scope scope(ctx, "down_u8", px1 * C * (4.0 /*u8 in*/ + 4.0 /*f32 out*/), st);
                 if (C == 3)
-                    k_down_u8<3><<<grid, 128 * 3, 0, st>>>(d_tiles, ids_k, gi);
+                    srf_launch_pdl(k_down_u8<3>, grid, dim3(128 * 3), 0, st, d_tiles, ids_k, gi);
                 else
-                    k_down_u8<1><<<grid, 128, 0, st>>>(d_tiles, ids_k, gi);
+                    srf_launch_pdl(k_down_u8<1>, grid, dim3(128), 0, st, d_tiles, ids_k, gi);
             }
         }
         for (int l = 1; l + 1 < n; ++l) {
@@ -1670,7 +1676,7 @@ int srf_fuse_device(srf_ctx *ctx, const srf_tile *tiles, int n_tiles, int C, int
             double pxo = 0;
             for (int ti : groups[k].tiles) pxo += (double)(tdev[ti].g1[l + 1] - tdev[ti].g0[l + 1]) * std::min(gi.lv[l + 1].w, tdev[ti].gx1[l + 1]);
             srf_launch_scope scope(ctx, "down_f32", pxo * C * (16.0 + 4.0), st);
-            k_down_f32s<false><<<grid, DF_BW, 0, st>>>(d_tiles, ids_k, gi, l, rpc);
+            srf_launch_pdl(k_down_f32s<false>, grid, dim3(DF_BW), 0, st, d_tiles, ids_k, gi, l, rpc);
         }
         // up: l = n-2 .. 1
         for (int l = n - 2; l >= 1; --l) {
@@ -1682,10 +1688,10 @@ int srf_fuse_device(srf_ctx *ctx, const srf_tile *tiles, int n_tiles, int C, int
             // per output element: G_l + W_l/C read, C_l written, C_{l+1} (or W_{l+1}/C) + G_{l+1} at quarter density
             srf_launch_scope scope(ctx, "up_level", pxo * C * (4.0 + 4.0 / C + 4.0 + 2.0), st);
             if (l == n - 2) {
-                k_up_level_top<true><<<grid, kThreads, 0, st>>>(d_tiles, ids_k, gi, l);
+                srf_launch_pdl(k_up_level_top<true>, grid, dim3(kThreads), 0, st, d_tiles, ids_k, gi, l);
             } else {
                 dim3 sgrid(srf_ceil_div(gi.lv[l].w, UL_W), srf_ceil_div(rows, UL_H), nt * C);
-                k_up_levels<<<sgrid, UL_PAIRS, 0, st>>>(d_tiles, ids_k, gi, l);
+                srf_launch_pdl(k_up_levels, sgrid, dim3(UL_PAIRS), 0, st, d_tiles, ids_k, gi, l);
             }
         }
     }
@@ -1745,12 +1751,12 @@ int srf_fuse_device(srf_ctx *ctx, const srf_tile *tiles, int n_tiles, int C, int
             const size_t sm = sizeof(FinalSmem<3>) + 128;
             SRF_CHECK_CUDA(ctx, cudaFuncSetAttribute(k_final<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
             SRF_CHECK_CUDA(ctx, cudaFuncSetAttribute(k_final<3>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-            k_final<3><<<grid, FB_PAIRS * 3, sm, st>>>(P, TM);
+            srf_launch_pdl(k_final<3>, grid, dim3(FB_PAIRS * 3), sm, st, P, TM);
         } else {
             const size_t sm = sizeof(FinalSmem<1>) + 128;
             SRF_CHECK_CUDA(ctx, cudaFuncSetAttribute(k_final<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
             SRF_CHECK_CUDA(ctx, cudaFuncSetAttribute(k_final<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-            k_final<1><<<grid, FB_PAIRS, sm, st>>>(P, TM);
+            srf_launch_pdl(k_final<1>, grid, dim3(FB_PAIRS), sm, st, P, TM);
         }
         SRF_CHECK_CUDA(ctx, cudaGetLastError());
     }

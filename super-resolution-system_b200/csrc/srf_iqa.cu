@@ -118,6 +118,7 @@ constexpr int IQ2_SROW = IQ2_PX + 6;                     // 272 (a, b) pairs per
 template <int C, bool ANYSCALE, int R>
 __global__ void __launch_bounds__(IQ_THREADS, 4) k_psnr_ssim(IqaParams P)
 {
+    pdl_enter(); // programmatic dependent launch: nothing above this line may touch global data
     __shared__ __align__(16) uint8_t s_raw[4][2][IQ2_RAW];
     __shared__ __align__(16) float2 s_ab[2][IQ2_SROW];
     __shared__ double s_red[IQ_THREADS / 32];
@@ -359,6 +360,7 @@ __global__ void __launch_bounds__(IQ_THREADS, 4) k_psnr_ssim(IqaParams P)
 // single CTA, fixed summation order: thread k sums partials k, k+256, ... then a shared-memory tree
 __global__ void __launch_bounds__(256) k_iqa_reduce(const IqaPartial *__restrict__ parts, int n, IqaPartial *__restrict__ out, double *__restrict__ dsum)
 {
+    pdl_enter(); // programmatic dependent launch: nothing above this line may touch global data
     __shared__ IqaPartial s[256];
     IqaPartial p;
     p.ssim = 0;
@@ -435,7 +437,7 @@ int srf_iqa_enqueue(srf_ctx *ctx, const uint8_t *a, size_t pa, const uint8_t *b,
         dim3 grid(gx, gy);
         srf_launch_scope scope(ctx, "psnr_ssim", 2.0 * (double)(row_end - row_begin) * w * C, st);
         const bool any = scale_a || scale_b; // the rare max() <= 1 rescale: generic instantiation
-#define IQ_LAUNCH(CC, ANY, RR) k_psnr_ssim<CC, ANY, RR><<<grid, IQ_THREADS, 0, st>>>(P)
+#define IQ_LAUNCH(CC, ANY, RR) srf_launch_pdl(k_psnr_ssim<CC, ANY, RR>, grid, dim3(IQ_THREADS), 0, st, P)
         if (window == 0) {
             if (C == 3) { if (any) IQ_LAUNCH(3, true, 5); else IQ_LAUNCH(3, false, 5); }
             else        { if (any) IQ_LAUNCH(1, true, 5); else IQ_LAUNCH(1, false, 5); }
@@ -447,7 +449,7 @@ int srf_iqa_enqueue(srf_ctx *ctx, const uint8_t *a, size_t pa, const uint8_t *b,
     }
     {
         srf_launch_scope scope(ctx, "iqa_reduce", 0.0, st);
-        k_iqa_reduce<<<1, 256, 0, st>>>(parts, (int)nparts, final_d, d_sums);
+        srf_launch_pdl(k_iqa_reduce, dim3(1), dim3(256), 0, st, (const IqaPartial *)parts, (int)nparts, final_d, d_sums);
     }
     SRF_CHECK_CUDA(ctx, cudaGetLastError());
     if (slot >= 0)
