@@ -629,27 +629,30 @@ __device__ __forceinline__ HPair2 up_pair_even_origin(float s0, float s1, float 
     return r;
 }
 
+template <int H> // output rows per CTA: 32 amortises the 2-row source halo; 8 keeps a small level (or a thin band) from
+                  // being a few long-running CTAs on an idle GPU
 __global__ void __launch_bounds__(UL_PAIRS) k_up_levels(const TileDev *__restrict__ tiles, const int *__restrict__ tile_ids, GroupDev g, int l)
 {
     pdl_enter(); // programmatic dependent launch: nothing above this line may touch global data
-    __shared__ __align__(16) float s_c[UL_SRC_ROWS][UL_SRC_COLS];
-    __shared__ __align__(16) float s_g[UL_SRC_ROWS][UL_SRC_COLS];
+    constexpr int STEPS = H / 2, SRC_ROWS = STEPS + 2;
+    __shared__ __align__(16) float s_c[SRC_ROWS][UL_SRC_COLS];
+    __shared__ __align__(16) float s_g[SRC_ROWS][UL_SRC_COLS];
 
     const int z = blockIdx.z;
     const TileDev &t = tiles[tile_ids[z / g.cn]];
     const int c = z % g.cn;
     const LevelGeom L0 = g.lv[l], L1 = g.lv[l + 1];
     const int h1 = L1.h, w1 = L1.w;
-    const int ty0 = t.c0[l] + blockIdx.y * UL_H;
+    const int ty0 = t.c0[l] + blockIdx.y * H;
     const int tx0 = blockIdx.x * UL_W;
     if (ty0 >= t.c1[l] || tx0 >= L0.w || tx0 >= t.cx1[l]) return;
-    const int ty1 = min(ty0 + UL_H, t.c1[l]);
+    const int ty1 = min(ty0 + H, t.c1[l]);
     const int ypar = ty0 & 1;
     const int i0 = (tx0 >> 1) - 1;           // window start column for pair 0 (tx0 is even)
     const int ws0 = (ty0 >> 1) - (1 - ypar); // window start row for step 0
     const int sx0 = max(i0, 0) & ~3;
     const int srow0 = max(min(ws0, h1 - 1), 0);
-    const int n_srows = max(min(ws0 + UL_STEPS + 1, h1 - 1), 0) - srow0 + 1; // <= 18
+    const int n_srows = max(min(ws0 + STEPS + 1, h1 - 1), 0) - srow0 + 1; // <= 18
     const float *G1 = t.G[l + 1] + (size_t)c * L1.plane;
     const float *C1 = t.C[l + 1] + (size_t)c * L1.plane;
 
@@ -726,7 +729,7 @@ __global__ void __launch_bounds__(UL_PAIRS) k_up_levels(const TileDev *__restric
     hrow(ws0, rc0, rg0);
     hrow(ws0 + 1, rc1, rg1);
 #pragma unroll 4
-    for (int k = 0; k < UL_STEPS; ++k) {
+    for (int k = 0; k < STEPS; ++k) {
         hrow(ws0 + k + 2, rc2, rg2);
         float uc[2][2], ug[2][2];
         if (ypar == 0) {
@@ -742,7 +745,7 @@ __global__ void __launch_bounds__(UL_PAIRS) k_up_levels(const TileDev *__restric
         }
         // this step's G_l / W_l were fetched one step ago; fetch the next step's now
         float2 gcur[2] = {gnext[0], gnext[1]}, wcur[2] = {wnext[0], wnext[1]};
-        if (k + 1 < UL_STEPS) fetch_gw(k + 1);
+        if (k + 1 < STEPS) fetch_gw(k + 1);
 #pragma unroll
         for (int a = 0; a < 2; ++a) {
             const int ty = ty0 + 2 * k + a;
@@ -1690,8 +1693,14 @@ int srf_fuse_device(srf_ctx *ctx, const srf_tile *tiles, int n_tiles, int C, int
             if (l == n - 2) {
                 srf_launch_pdl(k_up_level_top<true>, grid, dim3(kThreads), 0, st, d_tiles, ids_k, gi, l);
             } else {
-                dim3 sgrid(srf_ceil_div(gi.lv[l].w, UL_W), srf_ceil_div(rows, UL_H), nt * C);
-                srf_launch_pdl(k_up_levels, sgrid, dim3(UL_PAIRS), 0, st, d_tiles, ids_k, gi, l);
+                const int gx = srf_ceil_div(gi.lv[l].w, UL_W);
+                if ((long long)gx * srf_ceil_div(rows, UL_H) * nt * C >= 4LL * ctx->sm_count) {
+                    dim3 sgrid(gx, srf_ceil_div(rows, UL_H), nt * C);
+                    srf_launch_pdl(k_up_levels<UL_H>, sgrid, dim3(UL_PAIRS), 0, st, d_tiles, ids_k, gi, l);
+                } else { // small level / thin band: short CTAs
+                    dim3 sgrid(gx, srf_ceil_div(rows, 8), nt * C);
+                    srf_launch_pdl(k_up_levels<8>, sgrid, dim3(UL_PAIRS), 0, st, d_tiles, ids_k, gi, l);
+                }
             }
         }
     }
