@@ -146,6 +146,31 @@ typedef struct srf_iqa_sums {
     int32_t bits_b;     /*   the caller applies the reference's `image.max() <= 1.0` rescale rule (q.a.m:192-193) */
 } srf_iqa_sums;
 
+/* ---- merge_tiles: feathered weighted average of the processed tiles (tiling_module.py:1074-1135) -------------------
+ * out = astype(uint8)(sum_t tile_t * w_t / max(sum_t w_t, 1e-6)), float32, tiles in list order.  w_t is the map of
+ * _create_blend_weight (1137-1175): float32 ones multiplied in place by float64 linspace ramps, i.e.
+ * w(y, x) = f32(f32(wy[y] * wl[x]) * wr[x]) with float64 products -- the caller passes the three 1-D tables (HOST
+ * pointers; all NULL = weight 1, the reference's blending=False) and the full map is never built.  A tile whose stored
+ * size (h, w) differs from its canvas size (out_h, out_w) is first squashed with cv2.resize's default INTER_LINEAR, as
+ * the reference does for the padded edge tiles (1107-1109); enlarging is SRF_ERR_UNSUPPORTED. */
+typedef struct srf_merge_tile {
+    const uint8_t *data; /* (h, w, channels) uint8; host pointer for _host, device pointer otherwise */
+    size_t pitch;
+    int h, w;         /* stored size */
+    int out_h, out_w; /* size on the canvas (TileMetadata.output_h / output_w) */
+    int y, x;         /* canvas position: int(global_y * scale), int(global_x * scale) */
+    const float *wy;  /* out_h row factors (top and bottom ramps applied, float32) */
+    const double *wl; /* out_w left-ramp factors, 1.0 outside the ramp */
+    const double *wr; /* out_w right-ramp factors, 1.0 outside the ramp */
+} srf_merge_tile;
+int srf_merge_tiles(srf_ctx *ctx, const srf_merge_tile *tiles, int n_tiles, int channels, int out_h, int out_w,
+                    uint8_t *d_canvas, size_t canvas_pitch, void *stream);
+int srf_merge_tiles_host(srf_ctx *ctx, const srf_merge_tile *tiles, int n_tiles, int channels, int out_h, int out_w,
+                         uint8_t *h_canvas, size_t canvas_pitch);
+/* host only, exact: OpenCV's INTER_LINEAR taps for uint8 -- per destination index the source index pair and the two
+ * 11-bit coefficients (cvRound(frac * 2048)) */
+int srf_resize_linear_taps(int src, int dst, int *idx2, int *coef2);
+
 /* ---- bicubic resize: cv2.resize(img, (dst_w, dst_h), interpolation=cv2.INTER_CUBIC) on uint8 ---------------------
  * replaces QualityAssessmentModule.downsample_bicubic (quality_assessment_module.py:226-253) and upsample_bicubic
  * (255-275); _evaluate_downsample_comparison (518-555) applies it to both images at 0.1x / 0.2x / 0.4x before PSNR and

@@ -5,6 +5,8 @@ NumPy restatement of the reference tiler's geometry and padding:
   overlap metadata /root/reference/tiling_module.py:610-646  (_calculate_overlap_for_tile)
   bottom/right pad /root/reference/tiling_module.py:522-570, 718-724 (cv2.copyMakeBorder with
                    BORDER_REFLECT_101 / REPLICATE / REFLECT / CONSTANT(0); multi-bounce when pad > size-1)
+  merge_tiles      /root/reference/tiling_module.py:1074-1135 and _create_blend_weight 1137-1175: feathered weighted
+                   average of the processed tiles (linear ramps over the scaled overlap metadata)
 """
 from __future__ import annotations
 
@@ -69,3 +71,43 @@ def extract_tile(image: np.ndarray, x, y, w, h, block, mode):
         out[ys < 0] = 0
         out[:, xs < 0] = 0
     return out
+
+
+def blend_weight(out_h: int, out_w: int, ov_top: int, ov_bottom: int, ov_left: int, ov_right: int) -> np.ndarray:
+    """_create_blend_weight (tiling_module.py:1137-1175) for already scaled overlaps: float32 ones multiplied in place,
+    in this order, by float64 linspace ramps over the top rows, bottom rows, left columns, right columns"""
+    wgt = np.ones((out_h, out_w), np.float32)
+    if ov_top > 0:
+        wgt[:ov_top, :] *= np.linspace(0, 1, ov_top).reshape(-1, 1)
+    if ov_bottom > 0:
+        wgt[-ov_bottom:, :] *= np.linspace(1, 0, ov_bottom).reshape(-1, 1)
+    if ov_left > 0:
+        wgt[:, :ov_left] *= np.linspace(0, 1, ov_left).reshape(1, -1)
+    if ov_right > 0:
+        wgt[:, -ov_right:] *= np.linspace(1, 0, ov_right).reshape(1, -1)
+    return wgt
+
+
+def merge_tiles(tiles, output_width: int, output_height: int, scale: float = 2.0, blending: bool = True) -> np.ndarray:
+    """merge_tiles (tiling_module.py:1074-1135).  tiles: (data uint8 (h, w, 3), global_x, global_y, output_w, output_h,
+    (overlap_top, overlap_bottom, overlap_left, overlap_right)) in list order; data whose size differs from
+    (output_h, output_w) is squashed with cv2.resize's default INTER_LINEAR first, as the reference does"""
+    from .resize_oracle import resize_linear_u8
+
+    out = np.zeros((output_height, output_width, 3), np.float32)
+    wmap = np.zeros((output_height, output_width), np.float32)
+    for data, gx, gy, ow, oh, ov in tiles:
+        x, y = int(gx * scale), int(gy * scale)
+        if data.shape[0] != oh or data.shape[1] != ow:
+            data = resize_linear_u8(data, ow, oh)
+        td = data.astype(np.float32)
+        if blending:
+            wgt = blend_weight(oh, ow, *[int(v * scale) for v in ov])
+        else:
+            wgt = np.ones((oh, ow), np.float32)
+        y1, x1 = min(y + oh, output_height), min(x + ow, output_width)
+        th, tw = y1 - y, x1 - x
+        out[y:y1, x:x1] += td[:th, :tw] * wgt[:th, :tw, None]
+        wmap[y:y1, x:x1] += wgt[:th, :tw]
+    out = out / np.maximum(wmap, 1e-6)[:, :, None]
+    return out.astype(np.uint8)

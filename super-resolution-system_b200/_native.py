@@ -26,6 +26,11 @@ class srf_weight_lut(C.Structure):
     _fields_ = [("values", c_void_p), ("len", c_int)]
 
 
+class srf_merge_tile(C.Structure):
+    _fields_ = [("data", c_void_p), ("pitch", c_size_t), ("h", c_int), ("w", c_int), ("out_h", c_int), ("out_w", c_int),
+                ("y", c_int), ("x", c_int), ("wy", c_void_p), ("wl", c_void_p), ("wr", c_void_p)]
+
+
 class srf_profile_entry(C.Structure):
     _fields_ = [("name", C.c_char * 40), ("ms", C.c_float), ("bytes", C.c_double)]
 
@@ -74,6 +79,9 @@ SIGNATURES = {
     "srf_fuse_assess_host": (c_int, [c_void_p, P(srf_tile), c_int, c_int, c_int, P(srf_weight_lut), c_int, c_int, c_int,
                                      c_void_p, c_size_t, c_void_p, c_size_t, C.c_double, c_int, c_int, P(srf_iqa_sums)]),
     "srf_iqa_finish": (c_int, [P(srf_iqa_sums), C.c_double, P(C.c_double), P(C.c_double)]),
+    "srf_merge_tiles": (c_int, [c_void_p, P(srf_merge_tile), c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    "srf_merge_tiles_host": (c_int, [c_void_p, P(srf_merge_tile), c_int, c_int, c_int, c_int, c_void_p, c_size_t]),
+    "srf_resize_linear_taps": (c_int, [c_int, c_int, c_void_p, c_void_p]),
     "srf_resize_cubic_taps": (c_int, [c_int, c_int, c_void_p, c_void_p]),
     "srf_resize_cubic_u8": (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_int, c_int, c_void_p, c_size_t, c_int, c_int,
                                     c_void_p]),
@@ -121,6 +129,8 @@ def check(rc: int, ctx=None, exc=None):
         raise (exc or ValueError)(text)
     if rc == -4:
         raise MemoryError(text)
+    if rc == -5:
+        raise NotImplementedError(text)
     raise SrfError(f"libsrfuse status {rc}: {text}")
 
 

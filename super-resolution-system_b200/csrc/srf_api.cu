@@ -136,7 +136,7 @@ extern "C" void srf_destroy(srf_ctx *c)
     if (!c) return;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
-    srf_buffer *bs[] = {&c->ws_pyr, &c->ws_desc, &c->ws_stage_in, &c->ws_stage_out, &c->ws_iqa, &c->ws_tab};
+    srf_buffer *bs[] = {&c->ws_pyr, &c->ws_desc, &c->ws_stage_in, &c->ws_stage_out, &c->ws_iqa, &c->ws_tab, &c->ws_merge};
     for (srf_buffer *b : bs)
         if (b->ptr) cudaFree(b->ptr);
     if (c->fuse_graph) cudaGraphExecDestroy(c->fuse_graph);
@@ -173,7 +173,7 @@ extern "C" int srf_last_transfer_bytes(const srf_ctx *c, size_t *h2d, size_t *d2
 extern "C" size_t srf_workspace_bytes(const srf_ctx *c)
 {
     if (!c) return 0;
-    return c->ws_pyr.bytes + c->ws_desc.bytes + c->ws_stage_in.bytes + c->ws_stage_out.bytes + c->ws_iqa.bytes + c->ws_tab.bytes;
+    return c->ws_pyr.bytes + c->ws_desc.bytes + c->ws_stage_in.bytes + c->ws_stage_out.bytes + c->ws_iqa.bytes + c->ws_tab.bytes + c->ws_merge.bytes;
 }
 
 extern "C" int srf_profile_enable(srf_ctx *c, int on)

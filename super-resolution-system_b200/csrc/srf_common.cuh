@@ -50,6 +50,7 @@ struct srf_ctx {
     srf_buffer ws_stage_out;
     srf_buffer ws_iqa;      // IQA reduction partials
     srf_buffer ws_tab;      // per-axis tap tables of the bicubic resize
+    srf_buffer ws_merge;    // merge_tiles: tile descriptors, weight tables, squashed edge tiles
     void *pinned = nullptr; // small pinned host block for result read-back
     size_t pinned_bytes = 0;
     cudaStream_t own_stream = nullptr; // used by the *_host entry points

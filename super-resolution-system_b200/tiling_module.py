@@ -2,9 +2,10 @@
 
 Mirrors /root/reference/tiling_module.py: PaddingMode 40-45, TileStatus 48-54, TileMetadata 64-125, Tile 128-171,
 TilingModule.__init__ 446-504, _apply_padding 522-570, _calculate_tile_positions 572-608,
-_calculate_overlap_for_tile 610-646, split_image 671-784, neighbour bookkeeping 786-850.
+_calculate_overlap_for_tile 610-646, split_image 671-784, neighbour bookkeeping 786-850, merge_tiles 1074-1135,
+_create_blend_weight 1137-1175.
 Grid and overlap arithmetic run in libsrfuse's exact host functions; the crop + pad gather runs on the GPU
-(csrc/srf_api.cu: k_tile_extract_pad).  Out of scope: content analysis (Haar / MSER /
+(csrc/srf_api.cu: k_tile_extract_pad), and so does the feathered merge (csrc/srf_merge.cu).  Out of scope: content analysis (Haar / MSER /
 saliency), the L1/L2/L3 caches, JSON checkpoints and streaming -- metadata decoration and host bookkeeping.
 """
 from __future__ import annotations
@@ -247,6 +248,77 @@ class TilingModule:
             if tile is None:
                 return []
             return [self.tile_registry[n] for n in tile.metadata.neighbor_ids.values() if n and n in self.tile_registry]
+
+    # ------------------------------------------------------------------ merge (feathered weighted average)
+    def _blend_tables(self, tile: Tile):
+        """the three 1-D factor tables of _create_blend_weight (tiling_module.py:1137-1175).  The reference multiplies a
+        float32 map of ones IN PLACE by float64 linspace ramps over the top rows, bottom rows, left columns and right
+        columns (scaled overlap metadata): the first two only depend on the row, the last two on the column, so
+        map[y, x] = f32(f32(wy[y] * wl[x]) * wr[x]) with float64 products -- wy float32, wl / wr float64 (1 outside)."""
+        m = tile.metadata
+        h, w = int(m.output_h), int(m.output_w)
+        top, bottom = int(m.overlap_top * self.output_scale), int(m.overlap_bottom * self.output_scale)
+        left, right = int(m.overlap_left * self.output_scale), int(m.overlap_right * self.output_scale)
+        if max(top, bottom) > h or max(left, right) > w:
+            raise ValueError("scaled overlap exceeds the tile (the reference's ramp would not broadcast)")
+        wy = np.ones(h, np.float32)
+        if top > 0:
+            wy[:top] *= np.linspace(0, 1, top)
+        if bottom > 0:
+            wy[h - bottom:] *= np.linspace(1, 0, bottom)
+        wl, wr = np.ones(w, np.float64), np.ones(w, np.float64)
+        if left > 0:
+            wl[:left] = np.linspace(0, 1, left)
+        if right > 0:
+            wr[w - right:] = np.linspace(1, 0, right)
+        return wy, wl, wr
+
+    def _create_blend_weight(self, tile: Tile) -> np.ndarray:
+        """the reference's (output_h, output_w) float32 feather map, built from the same tables the GPU merge uses"""
+        wy, wl, wr = self._blend_tables(tile)
+        m = (wy[:, None].astype(np.float64) * wl[None, :]).astype(np.float32)
+        return (m.astype(np.float64) * wr[None, :]).astype(np.float32)
+
+    def merge_tiles(self, tiles: List[Tile], output_width: int, output_height: int, blending: bool = True):
+        """Feathered weighted average of the processed tiles (tiling_module.py:1074-1135) on the GPU: tile data at
+        int(global_x * scale), int(global_y * scale); data whose size is not (output_h, output_w) is squashed with
+        cv2.resize's default INTER_LINEAR first (the reference's treatment of the padded edge tiles); float32
+        accumulation in list order, / max(sum of weights, 1e-6), astype(uint8).  NumPy tiles -> NumPy canvas, CUDA
+        tensors -> CUDA tensor."""
+        live = [t for t in tiles if t.data is not None]
+        if not live:
+            return np.zeros((output_height, output_width, 3), np.uint8)
+        views = [ImageView(t.data, "tile.data") for t in live]
+        on_dev = views[0].on_device
+        if any(v.on_device != on_dev for v in views) or any(v.c != views[0].c for v in views):
+            raise ValueError("tiles must be all host or all device arrays with the same channel count")
+        ch = views[0].c
+        arr = (_native.srf_merge_tile * len(live))()
+        keep = []
+        for k, (t, v) in enumerate(zip(live, views)):
+            m = t.metadata
+            a = arr[k]
+            a.data, a.pitch, a.h, a.w = v.ptr, v.pitch, v.h, v.w
+            a.out_h, a.out_w = int(m.output_h), int(m.output_w)
+            a.y, a.x = int(m.global_y * self.output_scale), int(m.global_x * self.output_scale)
+            if blending:
+                wy, wl, wr = self._blend_tables(t)
+                keep.append((wy, wl, wr))
+                a.wy, a.wl, a.wr = wy.ctypes.data, wl.ctypes.data, wr.ctypes.data
+        lib = _native.load()
+        shape = (output_height, output_width) if (ch == 1 and len(live[0].data.shape) == 2) else (output_height, output_width, ch)
+        if on_dev:
+            dev = views[0].device
+            ctx = _native.context(dev)
+            canvas = torch.empty(shape, dtype=torch.uint8, device=views[0].keep.device)
+            rc = lib.srf_merge_tiles(ctx, arr, len(live), ch, output_height, output_width, canvas.data_ptr(), output_width * ch,
+                                     current_stream_ptr(dev))
+        else:
+            ctx = _native.context(self.device)
+            canvas = np.empty(shape, np.uint8)
+            rc = lib.srf_merge_tiles_host(ctx, arr, len(live), ch, output_height, output_width, canvas.ctypes.data, output_width * ch)
+        _native.check(rc, ctx)
+        return canvas
 
     def restore_from_cache(self, image_hash: str):
         """the reference's checkpoint restore (tiling_module.py:1040-1072) is host bookkeeping, out of scope"""

@@ -164,6 +164,26 @@ def main():
         if k_.startswith("psnr_"):
             out[f"dsc_{k_}"] = np.array(v_)
 
+    # ---- merge_tiles (row N3): the reference's own split_image -> (bicubic 2x stand-in) -> merge_tiles.  The right and
+    # bottom tiles are padded, so their processed data is larger than output_w x output_h and the reference squashes
+    # it with cv2.resize's default INTER_LINEAR before the feathered average.
+    ms = synth(rng, 100, 150)
+    cv2.imwrite("merge_src.png", ms[:, :, ::-1])
+    tmm = rt.TilingModule(block_size=64, overlap_ratio=0.25, padding_mode="mirror", output_scale=2.0,
+                          l2_cache_dir=tempfile.mkdtemp(), enable_content_aware=False)
+    mt = tmm.split_image("merge_src.png", save_metadata=False)
+    for t_ in mt:
+        t_.data = cv2.resize(t_.data, (128, 128), interpolation=cv2.INTER_CUBIC)
+    out["merge_n"] = np.array([len(mt), 64, 150, 100], np.int32)
+    out["merge_meta"] = np.array([[t_.metadata.global_x, t_.metadata.global_y, t_.metadata.input_w, t_.metadata.input_h,
+                                   t_.metadata.output_w, t_.metadata.output_h, t_.metadata.overlap_top,
+                                   t_.metadata.overlap_bottom, t_.metadata.overlap_left, t_.metadata.overlap_right] for t_ in mt], np.int32)
+    out["merge_tiles"] = np.stack([t_.data for t_ in mt])
+    out["merge_out_blend"] = tmm.merge_tiles(mt, 300, 200, blending=True)
+    out["merge_out_plain"] = tmm.merge_tiles(mt, 300, 200, blending=False)
+    out["merge_weight_4"] = tmm._create_blend_weight(mt[4])
+    out["merge_squash_2"] = cv2.resize(mt[2].data, (mt[2].metadata.output_w, mt[2].metadata.output_h))
+
     np.savez_compressed(os.path.join(HERE, "reference_vectors.npz"), **out)
     print("wrote", os.path.join(HERE, "reference_vectors.npz"), os.path.getsize(os.path.join(HERE, "reference_vectors.npz")) // 1024, "KiB")
     print("cv2", cv2.__version__, "numpy", np.__version__)

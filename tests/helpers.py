@@ -31,3 +31,10 @@ def canvas_agreement(a, b):
     """(max abs diff, fraction of exactly equal elements)"""
     d = np.abs(a.astype(np.int16) - b.astype(np.int16))
     return int(d.max()), float((d == 0).mean())
+
+
+def merge_case(golden):
+    """the reference's merge_tiles case: [(data, gx, gy, out_w, out_h, (top, bottom, left, right))], canvas (w, h)"""
+    meta, data = golden["merge_meta"], golden["merge_tiles"]
+    tiles = [(data[i], int(m[0]), int(m[1]), int(m[4]), int(m[5]), tuple(int(v) for v in m[6:10])) for i, m in enumerate(meta)]
+    return tiles, (300, 200)

@@ -154,3 +154,21 @@ def test_downsample_argument_errors(srs):
     for bad in (1.0, 0.0, -0.5, 1.5):
         with pytest.raises(ValueError):  # quality_assessment_module.py:240-241
             qa.downsample_bicubic(img, bad)
+
+
+def test_linear_tap_tables_and_blend_weight(srs, golden, oracle):
+    """host side of merge_tiles: OpenCV's bilinear tap tables (exact ints) and the feather map of _create_blend_weight"""
+    lib = srs._native.load()
+    for src, dst in [(128, 108), (128, 104), (4096, 1712), (4096, 930), (64, 64), (7, 3)]:
+        idx, co = np.zeros((dst, 2), np.int32), np.zeros((dst, 2), np.int32)
+        assert lib.srf_resize_linear_taps(src, dst, idx.ctypes.data, co.ctypes.data) == 0
+        i0, i1, a0, a1 = oracle.resize_oracle.linear_table(src, dst)
+        assert np.array_equal(idx[:, 0], i0) and np.array_equal(idx[:, 1], i1)
+        assert np.array_equal(co[:, 0], a0) and np.array_equal(co[:, 1], a1)
+    tm = srs.TilingModule(64, 0.25, "mirror", enable_content_aware=False)
+    m = golden["merge_meta"][4]
+    meta = srs.tiling_module.TileMetadata(global_x=int(m[0]), global_y=int(m[1]), input_w=int(m[2]), input_h=int(m[3]),
+                                          output_w=int(m[4]), output_h=int(m[5]), overlap_top=int(m[6]),
+                                          overlap_bottom=int(m[7]), overlap_left=int(m[8]), overlap_right=int(m[9]))
+    tile = srs.tiling_module.Tile(metadata=meta, data=None)
+    assert np.array_equal(tm._create_blend_weight(tile), golden["merge_weight_4"])

@@ -6,7 +6,7 @@ import ctypes as C
 import numpy as np
 import pytest
 
-from helpers import FUSE_CASES, canvas_agreement, fuse_case, synth
+from helpers import FUSE_CASES, canvas_agreement, fuse_case, merge_case, synth
 
 pytestmark = pytest.mark.gpu
 REL = 1e-4
@@ -260,6 +260,47 @@ def test_iqa_device_path_and_evaluate(srs, oracle):
     assert rep["ssim"] == pytest.approx(oracle.iqa_oracle.ssim_uniform(a, b), rel=REL)
     assert rep["overall_score"] == pytest.approx(np.mean([min(100, rep["psnr"]), rep["ms_ssim"] * 100]))
     assert len(qa.batch_evaluate([(a, b), (b, a)])) == 2
+
+
+# ------------------------------------------------------------------ merge_tiles (row N3)
+def _merge_tiles_objects(srs, tiles, to_device=False):
+    import torch
+    out = []
+    for data, gx, gy, ow, oh, ov in tiles:
+        meta = srs.tiling_module.TileMetadata(global_x=gx, global_y=gy, output_w=ow, output_h=oh, overlap_top=ov[0],
+                                              overlap_bottom=ov[1], overlap_left=ov[2], overlap_right=ov[3])
+        out.append(srs.tiling_module.Tile(metadata=meta, data=torch.from_numpy(data).cuda() if to_device else data))
+    return out
+
+
+def test_merge_tiles_bit_exact_vs_reference(srs, golden, oracle):
+    tiles, (w, h) = merge_case(golden)
+    tm = srs.TilingModule(64, 0.25, "mirror", enable_content_aware=False)
+    objs = _merge_tiles_objects(srs, tiles)
+    assert np.array_equal(tm.merge_tiles(objs, w, h, blending=True), golden["merge_out_blend"])
+    assert np.array_equal(tm.merge_tiles(objs, w, h, blending=False), golden["merge_out_plain"])
+    dev = tm.merge_tiles(_merge_tiles_objects(srs, tiles, to_device=True), w, h)
+    assert np.array_equal(dev.cpu().numpy(), golden["merge_out_blend"])
+    # a larger, oracle-checked case through the mirror's own split (block 256, 3 x 3 tiles, squashed right / bottom tiles)
+    rng = np.random.default_rng(81)
+    src = synth(rng, 600, 720)
+    tm2 = srs.TilingModule(256, 0.2, "mirror", enable_content_aware=False)
+    qa = srs.QualityAssessmentModule()
+    got_tiles, ref_tiles = [], []
+    for t in tm2.split_array(src):
+        t.data = qa.upsample_bicubic(t.data, (512, 512))
+        got_tiles.append(t)
+        m = t.metadata
+        ref_tiles.append((t.data, m.global_x, m.global_y, m.output_w, m.output_h,
+                          (m.overlap_top, m.overlap_bottom, m.overlap_left, m.overlap_right)))
+    want = oracle.tiling_oracle.merge_tiles(ref_tiles, 1440, 1200, 2.0, True)
+    assert np.array_equal(tm2.merge_tiles(got_tiles, 1440, 1200), want)
+    thin = [t for t in tm2.split_array(synth(rng, 300, 700))]  # last column 85 px wide: its scaled "overlap" (240) exceeds
+    with pytest.raises(ValueError):                             # the 170 px tile -- the reference's ramp fails to broadcast
+        tm2.merge_tiles(thin, 1400, 600)
+    big = srs.tiling_module.Tile(metadata=srs.tiling_module.TileMetadata(output_w=600, output_h=600), data=np.zeros((512, 512, 3), np.uint8))
+    with pytest.raises(NotImplementedError):
+        tm2.merge_tiles([big], 600, 600)  # enlarging a tile: cv2.resize's other INTER_LINEAR path, not built
 
 
 # ------------------------------------------------------------------ bicubic resize + down-sample comparison (row N1)

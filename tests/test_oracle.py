@@ -3,7 +3,7 @@ tests/golden/make_golden.py from the reference modules themselves) and against c
 import numpy as np
 import pytest
 
-from helpers import FUSE_CASES, fuse_case, synth
+from helpers import FUSE_CASES, fuse_case, merge_case, synth
 
 
 def test_pyr_c_matches_reference_pyramids(golden, oracle):
@@ -208,3 +208,23 @@ def test_downsample_comparison_psnr_matches_reference(golden, oracle):
     for name in ("structure_color", "mid_frequency", "high_frequency"):
         assert got[f"psnr_{name}"] == pytest.approx(float(golden[f"dsc_psnr_{name}"]), rel=1e-5)
         assert 0 < got[f"ssim_{name}"] <= 1
+
+
+# ------------------------------------------------------------------ merge_tiles (row N3)
+def test_merge_oracle_matches_reference(golden, oracle):
+    """split_image -> 2x stand-in -> merge_tiles run by the reference itself (edge tiles squashed with INTER_LINEAR)"""
+    tiles, (w, h) = merge_case(golden)
+    assert np.array_equal(oracle.tiling_oracle.merge_tiles(tiles, w, h, 2.0, True), golden["merge_out_blend"])
+    assert np.array_equal(oracle.tiling_oracle.merge_tiles(tiles, w, h, 2.0, False), golden["merge_out_plain"])
+    d, gx, gy, ow, oh, ov = tiles[4]
+    assert np.array_equal(oracle.tiling_oracle.blend_weight(oh, ow, *[2 * v for v in ov]), golden["merge_weight_4"])
+    d2, _, _, ow2, oh2, _ = tiles[2]
+    assert np.array_equal(oracle.resize_oracle.resize_linear_u8(d2, ow2, oh2), golden["merge_squash_2"])
+
+
+def test_linear_resize_oracle_vs_cv2_shrinking(oracle):
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(14)
+    for (h, w, c, dh, dw) in [(128, 128, 3, 104, 108), (256, 256, 3, 53, 256), (90, 77, 1, 31, 40), (64, 64, 3, 64, 64)]:
+        img = rng.integers(0, 256, (h, w, c) if c > 1 else (h, w), dtype=np.uint8)
+        assert np.array_equal(oracle.resize_oracle.resize_linear_u8(img, dw, dh), cv2.resize(img, (dw, dh))), (h, w, c, dh, dw)
