@@ -146,6 +146,20 @@ typedef struct srf_iqa_sums {
     int32_t bits_b;     /*   the caller applies the reference's `image.max() <= 1.0` rescale rule (q.a.m:192-193) */
 } srf_iqa_sums;
 
+/* ---- seam detection: the window scores of BlendingModule.detect_seams (blending_module.py:765-851) ------------------
+ * For a tile placed at (tile_x, tile_y) on the fused result: the whole-patch SSIM (_compute_ssim, 853-903; float64,
+ * gray by cv2.COLOR_BGR2GRAY on the stored channel order, tile first) of every window x window patch, stride `stride`,
+ * of the region the two share -- out[wy * nx + wx], ny x nx as srf_window_ssim_shape reports.  c1 = (k1 L)^2,
+ * c2 = (k2 L)^2.  Thresholding and the merging of neighbouring windows stay on the host. */
+int srf_window_ssim_shape(int result_h, int result_w, int tile_h, int tile_w, int tile_y, int tile_x, int window,
+                          int stride, int *ny, int *nx);
+int srf_window_ssim(srf_ctx *ctx, const uint8_t *d_result, size_t result_pitch, int result_h, int result_w,
+                    const uint8_t *d_tile, size_t tile_pitch, int tile_h, int tile_w, int channels, int tile_y, int tile_x,
+                    int window, int stride, double c1, double c2, double *d_out, void *stream);
+int srf_window_ssim_host(srf_ctx *ctx, const uint8_t *h_result, size_t result_pitch, int result_h, int result_w,
+                         const uint8_t *h_tile, size_t tile_pitch, int tile_h, int tile_w, int channels, int tile_y,
+                         int tile_x, int window, int stride, double c1, double c2, double *h_out);
+
 /* ---- merge_tiles: feathered weighted average of the processed tiles (tiling_module.py:1074-1135) -------------------
  * out = astype(uint8)(sum_t tile_t * w_t / max(sum_t w_t, 1e-6)), float32, tiles in list order.  w_t is the map of
  * _create_blend_weight (1137-1175): float32 ones multiplied in place by float64 linspace ramps, i.e.

@@ -93,3 +93,38 @@ def laplacian_fuse(tiles, positions_yx, out_hw, levels=6, kind="cosine", backend
     wacc = np.maximum(wacc, np.float32(1e-6))
     res = acc / (wacc[..., None] if ch else wacc)
     return np.clip(res, 0, 255).astype(np.uint8)
+
+
+# ---- seam detection (blending_module.py:765-968): per-window whole-patch SSIM -------------------------------------------
+def gray_bgr_order(img: np.ndarray) -> np.ndarray:
+    """cv2.cvtColor(img, cv2.COLOR_BGR2GRAY) for uint8 -- what the reference applies to its RGB arrays (channel 0 gets the
+    blue weight): (c0*3735 + c1*19235 + c2*9798 + 16384) >> 15"""
+    if img.ndim == 2:
+        return img
+    i = img.astype(np.int64)
+    return ((i[..., 0] * 3735 + i[..., 1] * 19235 + i[..., 2] * 9798 + 16384) >> 15).astype(np.uint8)
+
+
+def patch_ssim(img1: np.ndarray, img2: np.ndarray, k1=0.01, k2=0.03, L=255.0) -> float:
+    """_compute_ssim (blending_module.py:853-903), literally: float64 np.mean / np.var / covariance of the gray patches"""
+    a, b = gray_bgr_order(img1).astype(np.float64), gray_bgr_order(img2).astype(np.float64)
+    mu1, mu2 = np.mean(a), np.mean(b)
+    s1, s2 = np.var(a), np.var(b)
+    s12 = np.mean((a - mu1) * (b - mu2))
+    c1, c2 = (k1 * L) ** 2, (k2 * L) ** 2
+    return float(((2 * mu1 * mu2 + c1) * (2 * s12 + c2)) / ((mu1 ** 2 + mu2 ** 2 + c1) * (s1 + s2 + c2)))
+
+
+def window_ssim_map(result: np.ndarray, tile: np.ndarray, x: int, y: int, window=16, stride=8) -> np.ndarray:
+    """scores of detect_seams' sliding windows for one tile (blending_module.py:806-835), tile first"""
+    y2, x2 = min(y + tile.shape[0], result.shape[0]), min(x + tile.shape[1], result.shape[1])
+    if x2 <= x or y2 <= y:
+        return np.zeros((0, 0))
+    roi_r, roi_t = result[y:y2, x:x2], tile[:y2 - y, :x2 - x]
+    ys = range(0, roi_r.shape[0] - window + 1, stride)
+    xs = range(0, roi_r.shape[1] - window + 1, stride)
+    out = np.zeros((len(ys), len(xs)))
+    for j, wy in enumerate(ys):
+        for i, wx in enumerate(xs):
+            out[j, i] = patch_ssim(roi_t[wy:wy + window, wx:wx + window], roi_r[wy:wy + window, wx:wx + window])
+    return out

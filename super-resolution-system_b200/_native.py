@@ -79,6 +79,11 @@ SIGNATURES = {
     "srf_fuse_assess_host": (c_int, [c_void_p, P(srf_tile), c_int, c_int, c_int, P(srf_weight_lut), c_int, c_int, c_int,
                                      c_void_p, c_size_t, c_void_p, c_size_t, C.c_double, c_int, c_int, P(srf_iqa_sums)]),
     "srf_iqa_finish": (c_int, [P(srf_iqa_sums), C.c_double, P(C.c_double), P(C.c_double)]),
+    "srf_window_ssim_shape": (c_int, [c_int] * 8 + [P(c_int), P(c_int)]),
+    "srf_window_ssim": (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_int, c_void_p, c_size_t, c_int, c_int, c_int, c_int,
+                                c_int, c_int, c_int, C.c_double, C.c_double, c_void_p, c_void_p]),
+    "srf_window_ssim_host": (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_int, c_void_p, c_size_t, c_int, c_int, c_int,
+                                     c_int, c_int, c_int, c_int, C.c_double, C.c_double, c_void_p]),
     "srf_merge_tiles": (c_int, [c_void_p, P(srf_merge_tile), c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "srf_merge_tiles_host": (c_int, [c_void_p, P(srf_merge_tile), c_int, c_int, c_int, c_int, c_void_p, c_size_t]),
     "srf_resize_linear_taps": (c_int, [c_int, c_int, c_void_p, c_void_p]),

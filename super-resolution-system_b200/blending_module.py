@@ -47,6 +47,26 @@ class TileInfo:
     col: int
 
 
+@dataclass
+class Seam:
+    """a window (or a merged group of windows) where the fused result departs from a tile (blending_module.py:59-92)"""
+    x: int
+    y: int
+    width: int
+    height: int
+    ssim_score: float
+    severity: str = "low"
+    suggested_fix: str = ""
+
+    def __post_init__(self):
+        if self.ssim_score < 0.85:
+            self.severity, self.suggested_fix = "high", "poisson_refinement"
+        elif self.ssim_score < 0.92:
+            self.severity, self.suggested_fix = "medium", "increase_blend_width"
+        else:
+            self.severity, self.suggested_fix = "low", "none"
+
+
 class FusionPlan:
     """a marshalled tile list (see BlendingModule.plan_fusion)"""
 
@@ -313,5 +333,85 @@ class BlendingModule:
         return self.laplacian_fusion(tiles, output_shape=output_shape, weight_type=weight_type, row_range=row_range, out=out,
                                      _levels=1)
 
-    def detect_seams(self, *a, **k):
-        self._out_of_scope("detect_seams")
+    # ------------------------------------------------------------------ seam detection (blending_module.py:765-968)
+    def window_ssim_map(self, result, tile, x: int, y: int, window_size: int = 16, stride: int = 8,
+                        k1: float = 0.01, k2: float = 0.03, L: float = 255.0) -> np.ndarray:
+        """(ny, nx) float64 scores of every window of the region `tile` (placed at x, y) shares with `result`:
+        _compute_ssim(tile_window, result_window) of the reference for all windows at once (csrc/srf_seam.cu)"""
+        vr, vt = ImageView(result, "result"), ImageView(tile, "tile")
+        if vr.on_device != vt.on_device or vr.c != vt.c:
+            raise ValueError("result and tile must be both host or both device images with the same channel count")
+        lib = _native.load()
+        ny, nx = C.c_int(), C.c_int()
+        _native.check(lib.srf_window_ssim_shape(vr.h, vr.w, vt.h, vt.w, int(y), int(x), int(window_size), int(stride),
+                                                C.byref(ny), C.byref(nx)), None)
+        c1, c2 = (k1 * L) ** 2, (k2 * L) ** 2
+        if ny.value == 0 or nx.value == 0:
+            return np.zeros((ny.value, nx.value), np.float64)
+        if vr.on_device:
+            ctx = _native.context(vr.device)
+            out = torch.empty((ny.value, nx.value), dtype=torch.float64, device=vr.keep.device)
+            rc = lib.srf_window_ssim(ctx, vr.ptr, vr.pitch, vr.h, vr.w, vt.ptr, vt.pitch, vt.h, vt.w, vr.c, int(y), int(x),
+                                     int(window_size), int(stride), c1, c2, out.data_ptr(), current_stream_ptr(vr.device))
+            _native.check(rc, ctx)
+            return out.cpu().numpy()
+        ctx = self._ctx()
+        out = np.empty((ny.value, nx.value), np.float64)
+        rc = lib.srf_window_ssim_host(ctx, vr.ptr, vr.pitch, vr.h, vr.w, vt.ptr, vt.pitch, vt.h, vt.w, vr.c, int(y), int(x),
+                                      int(window_size), int(stride), c1, c2, out.ctypes.data)
+        _native.check(rc, ctx)
+        return out
+
+    def _compute_ssim(self, img1, img2, k1: float = 0.01, k2: float = 0.03, L: float = 255.0) -> float:
+        """whole-patch SSIM of two equally sized images (blending_module.py:853-903), gray by the reference's
+        COLOR_BGR2GRAY on the stored channel order"""
+        a, b = np.asarray(img1), np.asarray(img2)
+        if a.shape != b.shape or a.shape[0] != a.shape[1]:
+            raise ValueError("_compute_ssim on the GPU takes two equally sized square patches")
+        return float(self.window_ssim_map(b, a, 0, 0, window_size=a.shape[0], stride=a.shape[0], k1=k1, k2=k2, L=L)[0, 0])
+
+    def detect_seams(self, result, tiles, window_size: int = 16, stride: int = 8) -> List[Seam]:
+        """Windows of every tile whose SSIM against the fused result is below ssim_threshold, neighbours merged
+        (blending_module.py:765-851).  The result is uploaded once; every tile is one kernel launch."""
+        infos = [t if isinstance(t, TileInfo) else TileInfo(t, 0, 0, 0, 0) for t in tiles]
+        if not is_cuda_tensor(result) and torch is not None and torch.cuda.is_available():
+            result = torch.from_numpy(np.ascontiguousarray(result)).to(torch.device("cuda", self.device))
+        seams: List[Seam] = []
+        for info in infos:
+            img = info.image
+            if is_cuda_tensor(result) and not is_cuda_tensor(img):
+                img = torch.from_numpy(np.ascontiguousarray(img)).to(result.device)
+            if info.x >= result.shape[1] or info.y >= result.shape[0]:
+                continue
+            scores = self.window_ssim_map(result, img, info.x, info.y, window_size, stride)
+            ys, xs = np.nonzero(scores < self.ssim_threshold)  # row-major: y outer, x inner, as the reference's loops
+            for wy, wx in zip(ys.tolist(), xs.tolist()):
+                seams.append(Seam(x=info.x + wx * stride, y=info.y + wy * stride, width=window_size, height=window_size,
+                                  ssim_score=float(scores[wy, wx])))
+        seams = self._merge_adjacent_seams(seams, distance_threshold=window_size)
+        logger.info("Detected %d seams", len(seams))
+        return seams
+
+    def _merge_adjacent_seams(self, seams: List[Seam], distance_threshold: int = 16) -> List[Seam]:
+        """sort by (y, x), chain a seam to the current group while it lies closer than the threshold to the group's LAST
+        member, replace every group by its bounding box and mean score (blending_module.py:905-968)"""
+        if not seams:
+            return []
+        ordered = sorted(seams, key=lambda s: (s.y, s.x))
+        merged, group = [], [ordered[0]]
+        for s in ordered[1:]:
+            last = group[-1]
+            if np.sqrt((s.x - last.x) ** 2 + (s.y - last.y) ** 2) < distance_threshold:
+                group.append(s)
+            else:
+                merged.append(self._merge_seam_group(group))
+                group = [s]
+        merged.append(self._merge_seam_group(group))
+        return merged
+
+    def _merge_seam_group(self, group: List[Seam]) -> Seam:
+        if len(group) == 1:
+            return group[0]
+        x0, y0 = min(s.x for s in group), min(s.y for s in group)
+        x1, y1 = max(s.x + s.width for s in group), max(s.y + s.height for s in group)
+        return Seam(x=x0, y=y0, width=x1 - x0, height=y1 - y0, ssim_score=np.mean([s.ssim_score for s in group]))

@@ -184,6 +184,22 @@ def main():
     out["merge_weight_4"] = tmm._create_blend_weight(mt[4])
     out["merge_squash_2"] = cv2.resize(mt[2].data, (mt[2].metadata.output_w, mt[2].metadata.output_h))
 
+    # ---- detect_seams (row N4): the reference's window scores and merged seam list on the fused "grid" case; the result
+    # is disturbed in one corner so that some windows fall below the threshold
+    sg_tiles = [out[f"fuse_grid_t{i}"] for i in range(6)]
+    sg_pos = out["fuse_grid_pos"]
+    sg_res = out["fuse_grid_out"].copy()
+    sg_res[40:90, 100:170] = np.clip(sg_res[40:90, 100:170].astype(np.int16) + rng.integers(-60, 61, (50, 70, 3)), 0, 255).astype(np.uint8)
+    sbm = rb.BlendingModule(num_levels=5, ssim_threshold=0.9)
+    infos = [rb.TileInfo(t, int(x), int(y), 0, 0) for t, (y, x) in zip(sg_tiles, sg_pos)]
+    seams = sbm.detect_seams(sg_res, infos, window_size=16, stride=8)
+    out["seam_result"] = sg_res
+    out["seam_list"] = np.array([[s_.x, s_.y, s_.width, s_.height, s_.ssim_score] for s_ in seams], np.float64).reshape(-1, 5)
+    t1, (y1_, x1_) = sg_tiles[1], sg_pos[1]
+    roi = sg_res[int(y1_):int(y1_) + 128, int(x1_):int(x1_) + 128]
+    out["seam_scores_t1"] = np.array([[sbm._compute_ssim(t1[wy:wy + 16, wx:wx + 16], roi[wy:wy + 16, wx:wx + 16])
+                                       for wx in range(0, 113, 8)] for wy in range(0, 113, 8)])
+
     np.savez_compressed(os.path.join(HERE, "reference_vectors.npz"), **out)
     print("wrote", os.path.join(HERE, "reference_vectors.npz"), os.path.getsize(os.path.join(HERE, "reference_vectors.npz")) // 1024, "KiB")
     print("cv2", cv2.__version__, "numpy", np.__version__)

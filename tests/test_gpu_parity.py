@@ -262,6 +262,37 @@ def test_iqa_device_path_and_evaluate(srs, oracle):
     assert len(qa.batch_evaluate([(a, b), (b, a)])) == 2
 
 
+# ------------------------------------------------------------------ detect_seams (row N4)
+def test_window_ssim_and_seams_vs_reference(srs, golden, oracle):
+    import torch
+    bm = srs.BlendingModule(num_levels=5, ssim_threshold=0.9)
+    res = golden["seam_result"]
+    y1, x1 = (int(v) for v in golden["fuse_grid_pos"][1])
+    t1 = golden["fuse_grid_t1"]
+    host = bm.window_ssim_map(res, t1, x1, y1)
+    assert np.array_equal(host, golden["seam_scores_t1"])              # the reference's _compute_ssim loop, bit for bit
+    dev = bm.window_ssim_map(torch.from_numpy(res).cuda(), torch.from_numpy(t1).cuda(), x1, y1)
+    assert np.array_equal(dev, host)
+    assert bm._compute_ssim(t1[:16, :16], res[y1:y1 + 16, x1:x1 + 16]) == golden["seam_scores_t1"][0, 0]
+    infos = [srs.TileInfo(golden[f"fuse_grid_t{i}"], int(x), int(y), 0, 0) for i, (y, x) in enumerate(golden["fuse_grid_pos"])]
+    seams = bm.detect_seams(res, infos)
+    want = golden["seam_list"]
+    assert len(seams) == len(want)
+    for s, w in zip(seams, want):
+        assert (s.x, s.y, s.width, s.height) == tuple(int(v) for v in w[:4])
+        assert s.ssim_score == pytest.approx(w[4], rel=1e-13, abs=1e-15)
+    # other window sizes (n not a power of two: NumPy's two-pass variance differs in the last bits), gray, overhang
+    rng = np.random.default_rng(91)
+    a = synth(rng, 150, 170)
+    b = np.clip(a.astype(np.int16) + rng.integers(-30, 31, a.shape), 0, 255).astype(np.uint8)
+    for win, st, (x, y) in [(10, 5, (0, 0)), (16, 8, (37, 21)), (7, 3, (100, 90))]:
+        got = bm.window_ssim_map(b, a[:120, :110], x, y, win, st)
+        want_m = oracle.fusion_oracle.window_ssim_map(b, a[:120, :110], x, y, win, st)
+        assert got.shape == want_m.shape and np.allclose(got, want_m, rtol=1e-12, atol=1e-14)
+    g = bm.window_ssim_map(b[:, :, 0].copy(), a[:, :, 0].copy(), 0, 0)
+    assert np.array_equal(g, oracle.fusion_oracle.window_ssim_map(b[:, :, 0], a[:, :, 0], 0, 0))
+
+
 # ------------------------------------------------------------------ merge_tiles (row N3)
 def _merge_tiles_objects(srs, tiles, to_device=False):
     import torch

@@ -228,3 +228,42 @@ def test_linear_resize_oracle_vs_cv2_shrinking(oracle):
     for (h, w, c, dh, dw) in [(128, 128, 3, 104, 108), (256, 256, 3, 53, 256), (90, 77, 1, 31, 40), (64, 64, 3, 64, 64)]:
         img = rng.integers(0, 256, (h, w, c) if c > 1 else (h, w), dtype=np.uint8)
         assert np.array_equal(oracle.resize_oracle.resize_linear_u8(img, dw, dh), cv2.resize(img, (dw, dh))), (h, w, c, dh, dw)
+
+
+# ------------------------------------------------------------------ detect_seams (row N4)
+def test_seam_oracle_matches_reference(golden, oracle):
+    fo = oracle.fusion_oracle
+    y1, x1 = (int(v) for v in golden["fuse_grid_pos"][1])
+    got = fo.window_ssim_map(golden["seam_result"], golden["fuse_grid_t1"], x1, y1)
+    assert np.array_equal(got, golden["seam_scores_t1"])               # the reference's _compute_ssim, bit for bit
+    cv2 = pytest.importorskip("cv2")
+    img = golden["seam_result"]
+    assert np.array_equal(fo.gray_bgr_order(img), cv2.cvtColor(img, cv2.COLOR_BGR2GRAY))
+    # the integer form the kernel uses (exact sums; mu = S/n, var = (n Sxx - S^2)/n^2) equals NumPy's float64 path for 16x16
+    rng = np.random.default_rng(3)
+    for _ in range(50):
+        a = rng.integers(0, 256, (16, 16)).astype(np.int64)
+        b = np.clip(a + rng.integers(-40, 41, (16, 16)), 0, 255)
+        n = 256
+        s1, s2, s11, s22, s12 = a.sum(), b.sum(), (a * a).sum(), (b * b).sum(), (a * b).sum()
+        mu1, mu2 = float(s1) / n, float(s2) / n
+        v1, v2, cv = float(n * s11 - s1 * s1) / (n * n), float(n * s22 - s2 * s2) / (n * n), float(n * s12 - s1 * s2) / (n * n)
+        c1, c2 = (0.01 * 255.0) ** 2, (0.03 * 255.0) ** 2
+        mine = ((2.0 * mu1 * mu2 + c1) * (2.0 * cv + c2)) / ((mu1 * mu1 + mu2 * mu2 + c1) * (v1 + v2 + c2))
+        assert mine == fo.patch_ssim(a.astype(np.uint8), b.astype(np.uint8))
+
+
+def test_seam_merging_host_logic_matches_reference(srs, golden, oracle, monkeypatch):
+    """detect_seams' thresholding and neighbour merging (host side of the mirror) on the oracle's window scores"""
+    bm = srs.BlendingModule(num_levels=5, ssim_threshold=0.9)
+    monkeypatch.setattr(bm, "window_ssim_map",
+                        lambda result, tile, x, y, window_size=16, stride=8, **k: oracle.fusion_oracle.window_ssim_map(
+                            np.asarray(result), np.asarray(tile), x, y, window_size, stride))
+    infos = [srs.TileInfo(golden[f"fuse_grid_t{i}"], int(x), int(y), 0, 0) for i, (y, x) in enumerate(golden["fuse_grid_pos"])]
+    seams = bm.detect_seams(golden["seam_result"], infos)
+    want = golden["seam_list"]
+    assert len(seams) == len(want)
+    for s, w in zip(seams, want):
+        assert (s.x, s.y, s.width, s.height) == tuple(int(v) for v in w[:4])
+        assert s.ssim_score == pytest.approx(w[4], rel=1e-13, abs=1e-15)
+    assert seams[0].severity == "high" and seams[0].suggested_fix == "poisson_refinement"
