@@ -108,3 +108,26 @@ def test_balanced_bands_cover_and_balance(srs):
     b8 = d.balanced_bands(8, H, W, pos, sizes)
     assert b8[1][1] + 5 <= 3278                                    # band 1 stops short of grazing the second tile row
     assert d.balanced_bands(4, 3, 10, [(0, 0)], [(3, 10)])[-1][1] == 3  # more ranks than rows: empty bands allowed
+
+
+def test_band_starts_are_even_and_bands_random_layouts(srs):
+    """property checks of the band arithmetic on random tile layouts: the cuts tile the canvas, every fused range starts
+    on an even row (the gather's fast path), and a rank's tile selection contains every tile its rows intersect"""
+    d = srs.distributed
+    rng = np.random.default_rng(7)
+    for _ in range(40):
+        H, W = int(rng.integers(200, 9000)), int(rng.integers(200, 9000))
+        th, tw = int(rng.integers(64, 2048)), int(rng.integers(64, 2048))
+        sy, sx = max(1, int(th * rng.uniform(0.7, 0.9))), max(1, int(tw * rng.uniform(0.7, 0.9)))
+        pos = [(y, x) for y in range(0, H, sy) for x in range(0, W, sx)]
+        sizes = [(th, tw)] * len(pos)
+        for world in (1, 2, 3, 5, 8):
+            bands = d.balanced_bands(world, H, W, pos, sizes)
+            assert len(bands) == world and bands[0][0] == 0 and bands[-1][1] == H
+            assert all(a[1] == b[0] and a[0] <= a[1] for a, b in zip(bands, bands[1:]))
+            for b in bands:
+                e0, e1 = d.widen(b, H)
+                if b[1] > b[0]:
+                    assert e0 % 2 == 0 and e0 <= max(b[0] - 5, 0) and e1 == min(b[1] + 5, H)
+                    sel = d.tiles_for_rows(pos, [th] * len(pos), e0, e1)
+                    assert sel == [i for i, (y, _) in enumerate(pos) if y < e1 and y + th > e0]
