@@ -7,7 +7,9 @@
 //   k_up_levels     C_l = pyrUp(C_{l+1}) + (G_l - pyrUp(G_{l+1})) * W_l   l = n-3 .. 1, one streaming pass per level
 //   k_up_level_top  the same for l = n-2, with C_{n-1} = G_{n-1} * W_{n-1} formed on the fly (tiny planes)
 //   k_final         canvas gather: for every canvas pixel, in tile-list order, C_0 of each covering tile is rebuilt
-//                   from (C_1, G_1, the uint8 tile, W_0) and summed; divide by max(sum W_0, 1e-6), clip, truncate
+//                   from (C_1, G_1, the uint8 tile, W_0) and summed; divide by max(sum W_0, 1e-6), clip, truncate;
+//                   TMA tensor-map staging, packed FP32 interior path
+// Every kernel starts with pdl_enter() and is launched with programmatic stream serialization (srf_launch_pdl).
 //
 // Nothing canvas-sized is ever held in float32: the reference's two float accumulators (16 B per canvas pixel,
 // read-modify-written once per tile) become registers in k_final.
@@ -764,13 +766,16 @@ __global__ void __launch_bounds__(UL_PAIRS) k_up_levels(const TileDev *__restric
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// k_final: canvas gather.  One CTA per 256 x 16 canvas block, 128*C threads: thread (p, c) owns canvas columns
-// cx0+2p, cx0+2p+1 of channel c for all 16 rows -- 32 accumulators in registers; the sum of W_0 lives in smem.
-// Per covering tile (list order = the reference's accumulation order) the CTA stages the C_1 / G_1 source windows
-// (<= 11 rows x 136 cols per channel) and the uint8 tile block, then every thread slides DOWN the rows with a
-// 3-row register ring of horizontally up-sampled values: one new source row per canvas row pair, 3 LDS per array
-// for two columns, vertical pass + Laplacian weighting + accumulation straight from registers.
-// Tile origins of either parity are handled by shifting the window (xpar / ypar are uniform per CTA and tile).
+// k_final: canvas gather.  One CTA per FB_W x 16 canvas block (128 x 16 by default, 64*C threads, four CTAs per SM):
+// thread (p, c) owns canvas columns cx0+2p, cx0+2p+1 of channel c for all 16 rows -- 32 accumulators (16 packed float2)
+// in registers; the sum of W_0 lives in smem.  Per covering tile (list order = the reference's accumulation order) the
+// C_1 / G_1 source windows (10 rows x (FB_W/2 + 8) columns per channel) and the uint8 tile block arrive by TMA tensor
+// copies (one 3-D box per array, one 2-D box for the bytes; cp.async for 1- and 2-level tiles), double buffered across
+// tiles, then every thread slides DOWN the rows with a 3-row register ring of horizontally up-sampled values: one new
+// source row per canvas row pair, 3 LDS per array for two columns, vertical pass + Laplacian weighting + accumulation
+// straight from registers (packed FADD2 / FMUL2 / FFMA2 on the predicate-free interior path).
+// Tile origins of either parity are handled by shifting the window (xpar / ypar are uniform per CTA and tile); only even
+// parity takes the interior path.
 // MODE per tile: 0 = >= 3 levels (C_1 stored), 1 = exactly 2 levels (C_1 = G_1 * W_1 on the fly), 2 = single level
 // (C_0 = G_0 * W_0, no pyramid).
 // ------------------------------------------------------------------------------------------------------------
