@@ -1,0 +1,33 @@
+"""CPU suite, part 4: the bench.py contract -- the reference arm runs without a GPU and prints exactly ONE JSON line with
+the keys the driver reads; BASELINE.json's configs map to workloads the bench knows."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_reference_arm_prints_one_contract_line():
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [l for l in res.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, res.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "fused_canvas_megapixels_per_second" and d["unit"] == "MP/s"
+    assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["steps"] == 1 and d["vs_baseline"] is None
+    assert d["value"] > 0 and d["ms_per_step"] > 0 and d["gpu_launches"] == 0
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["config"]["workload"] == "cfg4_200mp" and d["config"]["tiles"] == 24 and d["config"]["levels"] == 7
+
+
+def test_workloads_cover_baseline_configs():
+    sys.path.insert(0, ROOT)
+    import workloads
+    names = set(workloads.CONFIGS) if hasattr(workloads, "CONFIGS") else set()
+    src = open(os.path.join(ROOT, "workloads.py")).read()
+    for name in ("cfg1_100mp_720p", "cfg2_100mp", "cfg3_150mp", "cfg4_200mp"):
+        assert name in names or name in src, name
