@@ -76,7 +76,8 @@ int seam_geometry(srf_ctx *ctx, int rh, int rw, int th, int tw, int C, int ty, i
 {
     SRF_REQUIRE(ctx, C == 1 || C == 3, "window_ssim: channels must be 1 or 3 (got %d)", C);
     SRF_REQUIRE(ctx, rh >= 1 && rw >= 1 && th >= 1 && tw >= 1, "window_ssim: empty image");
-    SRF_REQUIRE(ctx, window >= 1 && window <= 1024 && stride >= 1, "window_ssim: bad window %d / stride %d", window, stride);
+    // n * Sxx must stay below 2^53 for the integer form to be exact in float64: window <= 128 gives 2^14 * 2^30
+    SRF_REQUIRE(ctx, window >= 1 && window <= 128 && stride >= 1, "window_ssim: bad window %d (1..128) / stride %d", window, stride);
     SRF_REQUIRE(ctx, tx >= 0 && ty >= 0, "window_ssim: negative tile position (%d,%d)", ty, tx);
     *roi_h = std::max(0, std::min(ty + th, rh) - ty); // blending_module.py:809-814: the part of the tile inside the result
     *roi_w = std::max(0, std::min(tx + tw, rw) - tx);
