@@ -232,6 +232,12 @@ class TilingModule:
         self.processing_state[image_hash]["image_path"] = image_path
         return tiles
 
+    def create_tile_metadata(self, tile: Tile, global_x: int, global_y: int) -> TileMetadata:
+        """re-anchor a tile's metadata (tiling_module.py:648-669)"""
+        m = tile.metadata
+        m.global_x, m.global_y, m.updated_at = global_x, global_y, time.time()
+        return m
+
     def _build_neighbor_relationships(self, tiles: List[Tile]) -> None:
         at = {(t.metadata.global_x, t.metadata.global_y): t.metadata.block_id for t in tiles}
         step = self.block_size - self.overlap_pixels

@@ -172,3 +172,11 @@ def test_linear_tap_tables_and_blend_weight(srs, golden, oracle):
                                           overlap_bottom=int(m[7]), overlap_left=int(m[8]), overlap_right=int(m[9]))
     tile = srs.tiling_module.Tile(metadata=meta, data=None)
     assert np.array_equal(tm._create_blend_weight(tile), golden["merge_weight_4"])
+
+
+def test_create_tile_metadata_reanchors(srs):
+    tm = srs.TilingModule(64, 0.25, "mirror", enable_content_aware=False)
+    tile = srs.tiling_module.Tile(metadata=srs.tiling_module.TileMetadata(), data=None)
+    before = tile.metadata.updated_at
+    m = tm.create_tile_metadata(tile, 96, 48)  # tiling_module.py:648-669
+    assert m is tile.metadata and (m.global_x, m.global_y) == (96, 48) and m.updated_at >= before
