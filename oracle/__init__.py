@@ -11,10 +11,14 @@ Parity status (see DESIGN.md "Oracle"):
     (tests/golden/make_golden.py).
   * PSNR: PINNED against the reference's own manual formula (quality_assessment_module.py:313-318).
   * Gaussian SSIM: the arithmetic lives in scikit-image (requirements.txt:13, ">=0.21.0", not vendored, not
-    installed in this image).  Restated from its published algorithm; pinned to <=2e-5 relative against the
-    reference's own fallback `_calculate_ssim_simple` (quality_assessment_module.py:391-417) and exactly
-    against scipy.ndimage.gaussian_filter (what scikit-image calls) -- "parity pinned to the fallback, not to
-    scikit-image itself".
+    installed in this image), so in this image the reference itself returns its fallback `_calculate_ssim_simple`
+    (quality_assessment_module.py:391-417: same 11 taps, BORDER_REFLECT_101, mean over the full map).
+    iqa_oracle.ssim_simple restates that path (interior SSIM of the reflect-padded pair) and is PINNED to the
+    reference's own outputs to 1e-16 (tests/golden: iqa_ssim_fallback, iqa_demo_ssim_fallback); the GPU kernel matches
+    them to 1e-7 through QualityAssessmentModule._calculate_ssim_simple.  iqa_oracle.ssim (the scikit-image variant:
+    interior mean, no padding -- the oracle of record for calculate_ssim) is the same filter arithmetic without the
+    padding, restated from scikit-image's published algorithm and equal to scipy.ndimage.gaussian_filter (what
+    scikit-image calls) to 1e-12; its values differ from the fallback's by <= 3e-4 (border handling only).
   * bicubic resize (cv2.resize INTER_CUBIC, uint8): the opencv-python wheel calls Intel IPP (closed source); restated
     as the Keys cubic at float64 sample positions with half-to-even rounding.  PINNED against outputs of the
     reference's own downsample_bicubic / upsample_bicubic (tests/golden) and against cv2 directly: equal on all

@@ -111,3 +111,16 @@ def ssim_uniform(a, b, data_range=255.0) -> float:
     c1, c2 = (0.01 * data_range) ** 2, (0.03 * data_range) ** 2
     s = ((2 * ux * uy + c1) * (2 * vxy + c2)) / ((ux ** 2 + uy ** 2 + c1) * (vx + vy + c2))
     return float(s.mean(dtype=np.float64))
+
+
+def ssim_simple(a, b, data_range=255.0) -> float:
+    """_calculate_ssim_simple (/root/reference/quality_assessment_module.py:391-417), the path calculate_ssim takes when
+    scikit-image raises or is absent -- i.e. what the reference ACTUALLY returns in this image: cv2.GaussianBlur((11, 11),
+    1.5) in float64 with BORDER_REFLECT_101 and the mean over the FULL map.  Filtering with that border is filtering the
+    image reflect-padded by the window radius, so the full-map mean is the interior mean of the padded pair: equal to the
+    reference's own outputs (tests/golden: iqa_ssim_fallback, iqa_demo_ssim_fallback) to 1e-16."""
+    a, b = common_crop(preprocess(np.asarray(a)), preprocess(np.asarray(b)))
+    if min(a.shape[:2]) <= RADIUS:
+        raise ValueError("image smaller than the window radius")
+    pad = ((RADIUS, RADIUS), (RADIUS, RADIUS)) + (((0, 0),) if a.ndim == 3 else ())
+    return ssim(np.pad(a, pad, mode="reflect"), np.pad(b, pad, mode="reflect"), data_range)

@@ -2,7 +2,8 @@
 
 Mirrors /root/reference/quality_assessment_module.py: AssessmentLevel 35-41, QualityThresholds 44-75,
 ScaleConfig 78-86, QualityAssessmentModule.__init__ 107-133, _preprocess_image 169-195, calculate_psnr 277-320,
-downsample_bicubic 226-253, upsample_bicubic 255-275, calculate_ssim 322-389, evaluate_full_reference 467-516,
+downsample_bicubic 226-253, upsample_bicubic 255-275, calculate_ssim 322-389, _calculate_ssim_simple 391-417,
+evaluate_full_reference 467-516,
 _evaluate_downsample_comparison 518-555, _assess_* 557-588, _calculate_overall_score 590-609, batch_evaluate 1350-1371.
 The arithmetic (scikit-image's peak_signal_noise_ratio / structural_similarity) runs in csrc/srf_iqa.cu (both SSIM
 windows: 11x11 Gaussian and scikit-image's default 7x7 uniform); cv2.resize(INTER_CUBIC) runs in csrc/srf_resize.cu.
@@ -153,6 +154,26 @@ class QualityAssessmentModule:
         if sums.ssim_count <= 0:
             raise ValueError("image smaller than the SSIM window")
         return float(self.finish(sums, data_range)[1])
+
+    def _calculate_ssim_simple(self, img1, img2) -> float:
+        """The reference's fallback SSIM (q.a.m:391-417; what calculate_ssim returns wherever scikit-image is missing):
+        11x11 Gaussian filters with BORDER_REFLECT_101 and the mean over the FULL map.  Filtering with that border equals
+        filtering the image reflect-padded by the window radius, so this is the interior mean (the kernel's own) of the
+        padded pair -- the padding is a host / torch copy, the arithmetic stays in k_psnr_ssim."""
+        a, b = self._crop_common(self._preprocess_image(img1), self._preprocess_image(img2))
+        h, w = int(a.shape[0]), int(a.shape[1])
+        if min(h, w) <= 5:
+            raise ValueError("image smaller than the window radius")
+        if is_cuda_tensor(a) != is_cuda_tensor(b):
+            raise ValueError("image pair must be both host or both device")
+        if is_cuda_tensor(a):
+            iy = torch.tensor([abs(i) if i < h else 2 * (h - 1) - i for i in range(-5, h + 5)], device=a.device)
+            ix = torch.tensor([abs(i) if i < w else 2 * (w - 1) - i for i in range(-5, w + 5)], device=a.device)
+            a, b = (t.index_select(0, iy).index_select(1, ix).contiguous() for t in (a, b))
+        else:
+            pad = ((5, 5), (5, 5)) + (((0, 0),) if a.ndim == 3 else ())
+            a, b = np.pad(a, pad, mode="reflect"), np.pad(b, pad, mode="reflect")
+        return self.calculate_ssim(a, b, multiscale=True)
 
     def calculate_psnr_ssim(self, img1, img2, data_range: float = 255.0) -> Tuple[float, float]:
         """both metrics from ONE pass over the pair (extension; the reference makes two)"""

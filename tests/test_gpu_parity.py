@@ -262,6 +262,20 @@ def test_iqa_device_path_and_evaluate(srs, oracle):
     assert len(qa.batch_evaluate([(a, b), (b, a)])) == 2
 
 
+def test_fallback_ssim_equals_reference_outputs(srs, golden, oracle):
+    """_calculate_ssim_simple on the GPU against the numbers the reference itself produced (its fallback path)"""
+    import torch
+    qa = srs.QualityAssessmentModule()
+    a, b = golden["iqa_a"], golden["iqa_b"]
+    want = float(golden["iqa_ssim_fallback"])
+    assert qa._calculate_ssim_simple(a, b) == pytest.approx(want, rel=1e-5)
+    assert qa._calculate_ssim_simple(torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()) == pytest.approx(want, rel=1e-5)
+    np.random.seed(42)
+    hr = np.random.randint(0, 255, (512, 512, 3), dtype=np.uint8)
+    sr = np.clip(hr.astype(np.int16) + np.random.normal(0, 5, hr.shape).astype(np.int16), 0, 255).astype(np.uint8)
+    assert qa._calculate_ssim_simple(hr, sr) == pytest.approx(float(golden["iqa_demo_ssim_fallback"]), rel=1e-5)
+
+
 # ------------------------------------------------------------------ detect_seams (row N4)
 def test_window_ssim_and_seams_vs_reference(srs, golden, oracle):
     import torch

@@ -267,3 +267,14 @@ def test_seam_merging_host_logic_matches_reference(srs, golden, oracle, monkeypa
         assert (s.x, s.y, s.width, s.height) == tuple(int(v) for v in w[:4])
         assert s.ssim_score == pytest.approx(w[4], rel=1e-13, abs=1e-15)
     assert seams[0].severity == "high" and seams[0].suggested_fix == "poisson_refinement"
+
+
+def test_fallback_ssim_oracle_equals_reference_outputs(golden, oracle):
+    """the reference's ACTUAL SSIM outputs in this image (scikit-image absent -> _calculate_ssim_simple): reproduced to
+    the last bits by the interior SSIM of the reflect-padded pair"""
+    io = oracle.iqa_oracle
+    assert io.ssim_simple(golden["iqa_a"], golden["iqa_b"]) == pytest.approx(float(golden["iqa_ssim_fallback"]), rel=1e-13)
+    np.random.seed(42)  # the reference's own seeded demo (quality_assessment_module.py:1394-1400)
+    hr = np.random.randint(0, 255, (512, 512, 3), dtype=np.uint8)
+    sr = np.clip(hr.astype(np.int16) + np.random.normal(0, 5, hr.shape).astype(np.int16), 0, 255).astype(np.uint8)
+    assert io.ssim_simple(hr, sr) == pytest.approx(float(golden["iqa_demo_ssim_fallback"]), rel=1e-13)
