@@ -180,3 +180,24 @@ def test_create_tile_metadata_reanchors(srs):
     before = tile.metadata.updated_at
     m = tm.create_tile_metadata(tile, 96, 48)  # tiling_module.py:648-669
     assert m is tile.metadata and (m.global_x, m.global_y) == (96, 48) and m.updated_at >= before
+
+
+def test_blend_weight_tables_equal_the_reference_map_random(srs, oracle):
+    """the three 1-D tables the GPU merge uses reproduce _create_blend_weight's full map for any overlap geometry,
+    including ramps that overlap each other (top + bottom > height)"""
+    rng = np.random.default_rng(5)
+    tm = srs.TilingModule(64, 0.25, "mirror", enable_content_aware=False)
+    for _ in range(60):
+        h, w = int(rng.integers(4, 90)), int(rng.integers(4, 90))
+        ov = [int(rng.integers(0, h // 2 + 1)), int(rng.integers(0, h // 2 + 1)), int(rng.integers(0, w // 2 + 1)), int(rng.integers(0, w // 2 + 1))]
+        if rng.random() < 0.3:
+            ov[1] = int(rng.integers(0, h // 2 + 1)) + h // 2 - ov[0] // 2  # overlapping vertical ramps
+            ov[1] = min(ov[1], h // 2)
+        meta = srs.tiling_module.TileMetadata(output_w=w, output_h=h, overlap_top=ov[0], overlap_bottom=ov[1],
+                                              overlap_left=ov[2], overlap_right=ov[3])
+        tile = srs.tiling_module.Tile(metadata=meta, data=None)
+        want = oracle.tiling_oracle.blend_weight(h, w, *[2 * v for v in ov])
+        assert np.array_equal(tm._create_blend_weight(tile), want), (h, w, ov)
+    big = srs.tiling_module.Tile(metadata=srs.tiling_module.TileMetadata(output_w=10, output_h=10, overlap_top=8), data=None)
+    with pytest.raises(ValueError):  # 16 scaled ramp rows on a 10-row tile: the reference's ramp does not broadcast either
+        tm._create_blend_weight(big)
