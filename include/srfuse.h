@@ -91,6 +91,14 @@ int srf_tile_extract_pad(srf_ctx *ctx, const uint8_t *d_src, int height, int wid
 int srf_tile_extract_pad_host(srf_ctx *ctx, const uint8_t *h_src, int height, int width, int channels,
                               size_t pitch, const int *xywh, int n, int block, int border, uint8_t *h_tiles_out);
 
+/* replaces TilingModule._apply_padding (tiling_module.py:522-570) in full generality: cv2.copyMakeBorder(image, top,
+ * bottom, left, right, mode); dst is (h + top + bottom, w + left + right, channels), packed rows.  Padding may exceed
+ * the image size (multi-bounce reflection, as OpenCV). */
+int srf_copy_make_border(srf_ctx *ctx, const uint8_t *d_src, int h, int w, int channels, size_t pitch, int top, int bottom,
+                         int left, int right, int border, uint8_t *d_dst, void *stream);
+int srf_copy_make_border_host(srf_ctx *ctx, const uint8_t *h_src, int h, int w, int channels, size_t pitch, int top,
+                              int bottom, int left, int right, int border, uint8_t *h_dst);
+
 /* ---- pyramids (float32, HWC interleaved, packed rows -- the arrays the reference hands to cv2) ---------- */
 /* replaces cv2.pyrDown in BlendingModule.build_gaussian_pyramid (blending_module.py:263);
  * dst is ((h+1)/2, (w+1)/2, C) */
@@ -218,6 +226,24 @@ int srf_psnr_ssim_host(srf_ctx *ctx, const uint8_t *h_a, size_t pitch_a, const u
 int srf_psnr_ssim_enqueue(srf_ctx *ctx, const uint8_t *d_a, size_t pitch_a, const uint8_t *d_b, size_t pitch_b, int h,
                           int w, int channels, int scale_a, int scale_b, double data_range, int window, int row_begin,
                           int row_end, double *d_sums5, void *stream);
+/* replaces the PSNR / SSIM part of QualityAssessmentModule.batch_evaluate (quality_assessment_module.py:1350-1371: a serial
+ * loop of evaluate_full_reference over the pairs, one result per pair): n_pairs equally sized (h, w, channels) pairs
+ * scored by ONE kernel launch (grid.z = pair) and one reduction launch; out[i] holds pair i's sums over the whole image.
+ * The preprocess rule (an image whose max() <= 1 is rescaled) is reported through bits_a / bits_b: the caller re-scores
+ * such a pair with srf_psnr_ssim(scale_a / scale_b).  srf_psnr_ssim_batch synchronises `stream`; the _enqueue form writes
+ * 5 doubles per pair ({sq_err, ssim_sum, ssim_count, any byte of a > 1, of b > 1}, as srf_psnr_ssim_enqueue) to device
+ * memory and does not synchronise -- ranks that own different pairs all-gather / all-reduce that array. */
+typedef struct srf_image_pair {
+    const uint8_t *a; /* reference image ('original'); device pointer, host pointer for _host */
+    const uint8_t *b; /* assessed image ('upscaled') */
+    size_t pitch_a, pitch_b;
+} srf_image_pair;
+int srf_psnr_ssim_batch(srf_ctx *ctx, const srf_image_pair *pairs, int n_pairs, int h, int w, int channels, double data_range,
+                        int window, srf_iqa_sums *h_out, void *stream);
+int srf_psnr_ssim_batch_enqueue(srf_ctx *ctx, const srf_image_pair *pairs, int n_pairs, int h, int w, int channels,
+                                double data_range, int window, double *d_sums5n, void *stream);
+int srf_psnr_ssim_batch_host(srf_ctx *ctx, const srf_image_pair *pairs, int n_pairs, int h, int w, int channels,
+                             double data_range, int window, srf_iqa_sums *h_out);
 /* stage 3 + stage 4 of the reference pipeline in one call (main.py:347 laplacian_fusion, :369
  * evaluate_full_reference): host tiles -> fused canvas (host) + PSNR/SSIM sums of the canvas against a host
  * comparison image of the same size, for canvas rows [row_begin, row_end) (0, out_h for everything; a rank of a
@@ -228,6 +254,24 @@ int srf_fuse_assess_host(srf_ctx *ctx, const srf_tile *tiles, int n_tiles, int c
                          const srf_weight_lut *luts, int n_luts, int out_h, int out_w, uint8_t *h_canvas,
                          size_t canvas_pitch, const uint8_t *h_reference, size_t reference_pitch, double data_range,
                          int row_begin, int row_end, srf_iqa_sums *h_out);
+/* ---- multi-GPU: exchange of the additive sums over NVLink peer memory (one process per GPU) -----------------------
+ * The reference is a single-process CPU program and has no collectives; a band-sharded job sums
+ * srf_iqa_sums over its ranks.  Each rank: srf_comm_handle() -> 64-byte CUDA-IPC handle of its inbox; the host side
+ * gathers all ranks' handles (any transport: torch.distributed, MPI, a file) and passes the rank-ordered array to
+ * srf_comm_init(), which maps the peers' inboxes.  srf_allreduce_metrics() then replaces d_sums[0..n) by the sum over
+ * all ranks, in place, with ONE kernel per rank that writes to the peers' inboxes over NVLink and waits for theirs --
+ * enqueue only; totals are summed in rank order, so every rank holds bit-identical results.  srf_comm_result()
+ * synchronises `stream` and copies the totals of the last exchange from pinned host memory (the kernel wrote them
+ * there too): no separate device->host copy.  All ranks must call srf_allreduce_metrics the same number of times, each
+ * on its own GPU.  SRF_ERR_UNSUPPORTED from srf_comm_init = no peer access (the caller falls back to its own collective). */
+#define SRF_COMM_MAX_RANKS 16
+#define SRF_COMM_MAX_DOUBLES 128
+#define SRF_COMM_HANDLE_BYTES 64
+int srf_comm_handle(srf_ctx *ctx, void *handle64);
+int srf_comm_init(srf_ctx *ctx, int rank, int world, const void *handles);
+int srf_allreduce_metrics(srf_ctx *ctx, double *d_sums, int n, void *stream);
+int srf_comm_result(srf_ctx *ctx, double *h_out, int n, void *stream);
+
 /* final scalars from (all-reduced) sums: psnr = 10 log10(range^2 / (sq_err / n_elems)) (+inf if sq_err == 0),
  * ssim = ssim_sum / ssim_count */
 int srf_iqa_finish(const srf_iqa_sums *sums, double data_range, double *psnr, double *ssim);

@@ -18,6 +18,30 @@ def current_stream_ptr(device_index: int) -> int:
     return int(torch.cuda.current_stream(device_index).cuda_stream)
 
 
+_CAST_HELP = ("the GPU path computes on uint8 pixels (the tiles the pipeline produces); other dtypes are accepted when every "
+              "value is an integer in [0, 255] -- the reference's `astype(float32)` of such a tile (blending_module.py:440-441) "
+              "is then the same numbers")
+
+
+def _exact_u8_array(a: np.ndarray, what: str) -> np.ndarray:
+    """float32 / float64 / wider-integer pixels that ARE uint8 values -> uint8; anything else is a TypeError"""
+    if a.dtype == np.bool_ or not (np.issubdtype(a.dtype, np.floating) or np.issubdtype(a.dtype, np.integer)):
+        raise TypeError(f"{what}: expected uint8 pixels, got {a.dtype}; {_CAST_HELP}")
+    u = a.astype(np.uint8) if a.size == 0 else np.clip(a, 0, 255).astype(np.uint8)
+    if not np.array_equal(u, a):
+        raise TypeError(f"{what}: {a.dtype} pixels that are not exact uint8 values; {_CAST_HELP}")
+    return u
+
+
+def _exact_u8_tensor(t, what: str):
+    if not (t.dtype.is_floating_point or t.dtype in (torch.int16, torch.int32, torch.int64, torch.int8)):
+        raise TypeError(f"{what}: CUDA tensors must hold uint8 pixels (got {t.dtype}); {_CAST_HELP}")
+    u = t.clamp(0, 255).to(torch.uint8)
+    if not bool((u.to(t.dtype) == t).all()):
+        raise TypeError(f"{what}: {t.dtype} pixels that are not exact uint8 values; {_CAST_HELP}")
+    return u
+
+
 class ImageView:
     """uint8 (h, w) or (h, w, C) image with unit element stride inside a row."""
 
@@ -26,7 +50,7 @@ class ImageView:
     def __init__(self, img, what="image"):
         if is_cuda_tensor(img):
             if img.dtype != torch.uint8:
-                raise TypeError(f"{what}: CUDA tensors must be uint8 (got {img.dtype})")
+                img = _exact_u8_tensor(img, what)
             if img.dim() not in (2, 3):
                 raise ValueError(f"{what}: expected (H, W) or (H, W, C), got {tuple(img.shape)}")
             c = 1 if img.dim() == 2 else img.shape[2]
@@ -38,8 +62,8 @@ class ImageView:
         else:
             a = np.asarray(img)
             if a.dtype != np.uint8:
-                raise TypeError(f"{what}: expected uint8 pixels, got {a.dtype} "
-                                "(the GPU path computes on the uint8 tiles the pipeline produces)")
+                a = _exact_u8_array(a, what)
+            img = a
             if a.ndim not in (2, 3):
                 raise ValueError(f"{what}: expected (H, W) or (H, W, C), got {a.shape}")
             c = 1 if a.ndim == 2 else a.shape[2]

@@ -31,6 +31,10 @@ class srf_merge_tile(C.Structure):
                 ("y", c_int), ("x", c_int), ("wy", c_void_p), ("wl", c_void_p), ("wr", c_void_p)]
 
 
+class srf_image_pair(C.Structure):
+    _fields_ = [("a", c_void_p), ("b", c_void_p), ("pitch_a", c_size_t), ("pitch_b", c_size_t)]
+
+
 class srf_profile_entry(C.Structure):
     _fields_ = [("name", C.c_char * 40), ("ms", C.c_float), ("bytes", C.c_double)]
 
@@ -61,6 +65,10 @@ SIGNATURES = {
                                      c_void_p, c_void_p]),
     "srf_tile_extract_pad_host": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_size_t, c_void_p, c_int, c_int,
                                           c_int, c_void_p]),
+    "srf_copy_make_border": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_size_t, c_int, c_int, c_int, c_int, c_int, c_void_p,
+                                     c_void_p]),
+    "srf_copy_make_border_host": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_size_t, c_int, c_int, c_int, c_int, c_int,
+                                          c_void_p]),
     "srf_pyr_down_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "srf_pyr_up_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p]),
     "srf_pyr_down_f32_host": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
@@ -76,8 +84,18 @@ SIGNATURES = {
                                       C.c_double, c_int, c_int, c_int, c_void_p, c_void_p]),
     "srf_psnr_ssim_host": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, c_int, c_int, c_int, c_int, c_int,
                                    C.c_double, c_int, c_int, c_int, P(srf_iqa_sums)]),
+    "srf_psnr_ssim_batch": (c_int, [c_void_p, P(srf_image_pair), c_int, c_int, c_int, c_int, C.c_double, c_int, P(srf_iqa_sums),
+                                    c_void_p]),
+    "srf_psnr_ssim_batch_enqueue": (c_int, [c_void_p, P(srf_image_pair), c_int, c_int, c_int, c_int, C.c_double, c_int, c_void_p,
+                                            c_void_p]),
+    "srf_psnr_ssim_batch_host": (c_int, [c_void_p, P(srf_image_pair), c_int, c_int, c_int, c_int, C.c_double, c_int,
+                                         P(srf_iqa_sums)]),
     "srf_fuse_assess_host": (c_int, [c_void_p, P(srf_tile), c_int, c_int, c_int, P(srf_weight_lut), c_int, c_int, c_int,
                                      c_void_p, c_size_t, c_void_p, c_size_t, C.c_double, c_int, c_int, P(srf_iqa_sums)]),
+    "srf_comm_handle": (c_int, [c_void_p, c_void_p]),
+    "srf_comm_init": (c_int, [c_void_p, c_int, c_int, c_void_p]),
+    "srf_allreduce_metrics": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
+    "srf_comm_result": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
     "srf_iqa_finish": (c_int, [P(srf_iqa_sums), C.c_double, P(C.c_double), P(C.c_double)]),
     "srf_window_ssim_shape": (c_int, [c_int] * 8 + [P(c_int), P(c_int)]),
     "srf_window_ssim": (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_int, c_void_p, c_size_t, c_int, c_int, c_int, c_int,
@@ -97,10 +115,40 @@ SIGNATURES = {
 _lib = None
 _lock = threading.RLock()
 _ctx = {}
+_ctx_locks = {}  # srf_ctx address -> RLock: calls on one ctx must not overlap (include/srfuse.h), and ctypes drops the GIL
+
+# entry points that do NOT take an srf_ctx* first (nothing to serialise)
+_NO_CTX = {"srf_version", "srf_status_string", "srf_last_error", "srf_create", "srf_tile_positions", "srf_tile_overlaps",
+           "srf_weight_profile", "srf_iqa_finish", "srf_window_ssim_shape", "srf_resize_linear_taps", "srf_resize_cubic_taps"}
 
 
 def lib_path() -> str:
-    return _build.LIB_PATH
+    return os.environ.get("SRF_LIB") or _build.LIB_PATH
+
+
+def _guarded(fn):
+    """serialise every call on one srf_ctx: SuperResolutionPipeline.process runs run() on executor threads, and two
+    threads inside the library on the same workspaces would corrupt each other's staging buffers and descriptors"""
+    def call(ctx, *args):
+        lk = _ctx_locks.get(getattr(ctx, "value", ctx))
+        if lk is None:
+            return fn(ctx, *args)
+        with lk:
+            return fn(ctx, *args)
+    call.__name__ = fn.__name__
+    return call
+
+
+class _Library:
+    """the bound entry points of libsrfuse.so; those that take an srf_ctx hold that context's lock for the call"""
+
+    def __init__(self, cdll):
+        self._cdll = cdll
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(cdll, name)  # AttributeError if the export is missing
+            fn.restype = res
+            fn.argtypes = args
+            setattr(self, name, fn if name in _NO_CTX else _guarded(fn))
 
 
 def load():
@@ -112,12 +160,7 @@ def load():
             if not os.path.exists(path):
                 raise SrfError(f"{path} is missing -- run `python -c 'import __graft_entry__ as g; g.build()'` "
                                "(libsrfuse has no CPU fallback)")
-            lib = C.CDLL(path)
-            for name, (res, args) in SIGNATURES.items():
-                fn = getattr(lib, name)  # AttributeError if the export is missing
-                fn.restype = res
-                fn.argtypes = args
-            _lib = lib
+            _lib = _Library(C.CDLL(path))
     return _lib
 
 
@@ -149,7 +192,14 @@ def context(device: int = 0):
             if rc != 0:
                 raise SrfError(f"srf_create(device={device}) failed ({rc}): {last_error(None)}")
             _ctx[device] = h
+            _ctx_locks[h.value] = threading.RLock()
     return _ctx[device]
+
+
+def ctx_lock(ctx):
+    """the lock that serialises library calls on `ctx`: hold it across a call + the read of its side results
+    (last_transfer_bytes, last_device_ms) when several threads share the context"""
+    return _ctx_locks[getattr(ctx, "value", ctx)]
 
 
 def destroy_contexts():
@@ -158,6 +208,7 @@ def destroy_contexts():
         for h in _ctx.values():
             lib.srf_destroy(h)
         _ctx.clear()
+        _ctx_locks.clear()
 
 
 def last_transfer_bytes(ctx):

@@ -12,7 +12,7 @@ import sys
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libsrfuse.so")
-SOURCES = ["srf_api.cu", "srf_fuse.cu", "srf_iqa.cu", "srf_pipeline.cu", "srf_resize.cu", "srf_merge.cu", "srf_seam.cu"]
+SOURCES = ["srf_api.cu", "srf_fuse.cu", "srf_iqa.cu", "srf_pipeline.cu", "srf_resize.cu", "srf_merge.cu", "srf_seam.cu", "srf_comm.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

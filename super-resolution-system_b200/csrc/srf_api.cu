@@ -75,6 +75,27 @@ int srf_reserve_pinned(srf_ctx *ctx, size_t bytes)
     return SRF_OK;
 }
 
+int srf_note_device_work(srf_ctx *ctx, cudaStream_t st)
+{
+    if (st == ctx->own_stream) return SRF_OK; // a host entry point calling its device sibling: same stream, already ordered
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess) (void)cudaGetLastError();
+    if (cs != cudaStreamCaptureStatusNone) return SRF_OK; // the caller captures a graph: ordering is the caller's business
+    SRF_CHECK_CUDA(ctx, cudaEventRecord(ctx->ev_dev, st));
+    ctx->ev_dev_set = true;
+    return SRF_OK;
+}
+
+int srf_host_enter(srf_ctx *ctx)
+{
+    if (!ctx->ev_dev_set) return SRF_OK;
+    SRF_CHECK_CUDA(ctx, cudaStreamWaitEvent(ctx->own_stream, ctx->ev_dev, 0));
+    SRF_CHECK_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_dev, 0));
+    SRF_CHECK_CUDA(ctx, cudaStreamWaitEvent(ctx->down_stream, ctx->ev_dev, 0));
+    ctx->ev_dev_set = false;
+    return SRF_OK;
+}
+
 extern "C" int srf_version(void) { return SRF_VERSION; }
 
 extern "C" const char *srf_status_string(int s)
@@ -112,21 +133,36 @@ extern "C" int srf_create(int device, srf_ctx **out)
         srf_set_error((srf_ctx *)nullptr, "device %d out of range (have %d)", device, n);
         return SRF_ERR_ARG;
     }
-    cudaDeviceProp p;
-    if (cudaGetDeviceProperties(&p, device) != cudaSuccess || p.major < 10) {
+    cudaDeviceProp p = {};
+    e = cudaGetDeviceProperties(&p, device);
+    if (e != cudaSuccess) {
+        srf_set_error((srf_ctx *)nullptr, "cudaGetDeviceProperties(%d) failed: %s", device, cudaGetErrorString(e));
+        (void)cudaGetLastError();
+        return SRF_ERR_NO_DEVICE;
+    }
+    if (p.major < 10) {
         srf_set_error((srf_ctx *)nullptr, "device %d is sm_%d%d; libsrfuse is built for sm_100a only", device, p.major, p.minor);
         return SRF_ERR_NO_DEVICE;
     }
     srf_ctx *c = new srf_ctx();
     c->device = device;
     c->sm_count = p.multiProcessorCount;
-    SRF_CHECK_CUDA(c, cudaSetDevice(device));
-    SRF_CHECK_CUDA(c, cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
-    SRF_CHECK_CUDA(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-    SRF_CHECK_CUDA(c, cudaStreamCreateWithFlags(&c->down_stream, cudaStreamNonBlocking));
-    SRF_CHECK_CUDA(c, cudaEventCreate(&c->ev0));
-    SRF_CHECK_CUDA(c, cudaEventCreate(&c->ev1));
-    for (cudaEvent_t &e : c->ev_aux) SRF_CHECK_CUDA(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    const int rc = [&]() -> int { // any failure below destroys the half-built context (streams and events included)
+        SRF_CHECK_CUDA(c, cudaSetDevice(device));
+        SRF_CHECK_CUDA(c, cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+        SRF_CHECK_CUDA(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        SRF_CHECK_CUDA(c, cudaStreamCreateWithFlags(&c->down_stream, cudaStreamNonBlocking));
+        SRF_CHECK_CUDA(c, cudaEventCreate(&c->ev0));
+        SRF_CHECK_CUDA(c, cudaEventCreate(&c->ev1));
+        SRF_CHECK_CUDA(c, cudaEventCreateWithFlags(&c->ev_dev, cudaEventDisableTiming));
+        for (cudaEvent_t &ev : c->ev_aux) SRF_CHECK_CUDA(c, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        return SRF_OK;
+    }();
+    if (rc != SRF_OK) {
+        srf_set_error((srf_ctx *)nullptr, "srf_create: %s", c->last_error.c_str());
+        srf_destroy(c);
+        return rc;
+    }
     *out = c;
     return SRF_OK;
 }
@@ -136,6 +172,7 @@ extern "C" void srf_destroy(srf_ctx *c)
     if (!c) return;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
+    srf_comm_free(c);
     srf_buffer *bs[] = {&c->ws_pyr, &c->ws_desc, &c->ws_stage_in, &c->ws_stage_out, &c->ws_iqa, &c->ws_tab, &c->ws_merge};
     for (srf_buffer *b : bs)
         if (b->ptr) cudaFree(b->ptr);
@@ -146,6 +183,7 @@ extern "C" void srf_destroy(srf_ctx *c)
         if (e) cudaEventDestroy(e);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->ev_dev) cudaEventDestroy(c->ev_dev);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->down_stream) cudaStreamDestroy(c->down_stream);
@@ -279,63 +317,97 @@ extern "C" int srf_tile_overlaps(int x, int y, int w, int h, int width, int heig
 // ----------------------------------------------------------------------------------------------------------
 __host__ __device__ __forceinline__ int border_index(int i, int n, int mode)
 {
-    if (i < n) return i; // only bottom/right padding exists (tiling_module.py:718-724): i >= 0 always
+    if (i >= 0 && i < n) return i;
     if (mode == SRF_BORDER_CONSTANT) return -1;
-    if (mode == SRF_BORDER_REPLICATE) return n - 1;
+    if (mode == SRF_BORDER_REPLICATE) return i < 0 ? 0 : n - 1;
     if (n == 1) return 0;
-    const int delta = (mode == SRF_BORDER_MIRROR) ? 1 : 0;
+    const int delta = (mode == SRF_BORDER_MIRROR) ? 1 : 0; // REFLECT_101 skips the edge sample, REFLECT repeats it
     while (i < 0 || i >= n) i = (i < 0) ? (-i - 1 + delta) : (2 * n - 1 - i - delta);
     return i;
 }
 
-// One CTA per (tile row, tile).  The output row is block*C contiguous bytes; it is produced 16 B per thread
-// (output tiles are block*block*C bytes each, so rows are 16 B aligned whenever block*C % 16 == 0, which the
-// launcher checks; otherwise the byte-wise tail path handles everything).
+// cv2.copyMakeBorder of a crop: output tile t is (out_h, out_w, C); its pixel (r, px) is source pixel
+// (border_index(r - top, h), border_index(px - left, w)) of the crop src[y0:y0+h, x0:x0+w] (0 for BORDER_CONSTANT).
+// One CTA per (output row, tile); the row is out_w*C contiguous bytes produced 16 B per thread.  The BODY of the row (the
+// bytes copied verbatim from the source row) is read as five aligned 32-bit words per chunk and funnel-shifted into
+// place -- the crop's first byte sits at an arbitrary address -- so body traffic is word loads and 16-byte stores; only
+// the chunks that touch the border take the per-byte gather.  vec_ok: every output row is 16-byte aligned.
 template <int C>
 __global__ void __launch_bounds__(256) k_tile_extract_pad(const uint8_t *__restrict__ src, size_t pitch, const int4 *__restrict__ xywh,
-                                                          int block, int mode, uint8_t *__restrict__ out, int vec_ok)
+                                                          int out_h, int out_w, int top, int left, int mode, uint8_t *__restrict__ out, int vec_ok)
 {
     const int t = blockIdx.y;
     const int r = blockIdx.x;
     const int4 q = xywh[t];
     const int x0 = q.x, y0 = q.y, w = q.z, h = q.w;
-    const int sr = border_index(r, h, mode);
-    uint8_t *orow = out + ((size_t)t * block + r) * (size_t)block * C;
+    const int sr = border_index(r - top, h, mode);
+    uint8_t *orow = out + ((size_t)t * out_h + r) * (size_t)out_w * C;
     const uint8_t *srow = (sr >= 0) ? src + (size_t)(y0 + sr) * pitch + (size_t)x0 * C : nullptr;
-    const int nbytes = block * C;
-    const int body = w * C; // bytes copied verbatim from the source row
+    const int nbytes = out_w * C;
+    const int body0 = left * C, body1 = body0 + w * C; // output bytes [body0, body1) are source bytes [0, w*C) of srow
+    auto gather = [&](int byte) -> uint8_t {
+        if (!srow) return 0;
+        const int px = byte / C, c = byte - px * C;
+        const int sx = border_index(px - left, w, mode);
+        return (sx >= 0) ? srow[sx * C + c] : (uint8_t)0;
+    };
     if (vec_ok) {
         for (int k = threadIdx.x * 16; k < nbytes; k += blockDim.x * 16) {
-            uint32_t words[4];
-            uint8_t *b = reinterpret_cast<uint8_t *>(words);
+            uint4 v;
+            const uint8_t *p = srow + (k - body0);
+            const int sh = (int)(reinterpret_cast<uintptr_t>(p) & 3) * 8;
+            // a misaligned chunk reads a fifth word, i.e. up to 3 bytes beyond its own 16: allowed only while those
+            // still belong to the body of this row (the last chunk of a misaligned row takes the byte path instead)
+            if (srow && k >= body0 && k + 16 <= body1 && (sh == 0 || k + 20 <= body1)) {
+                const uint32_t *wp = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)3);
+                const uint32_t w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2), w3 = __ldg(wp + 3);
+                const uint32_t w4 = sh ? __ldg(wp + 4) : 0u;
+                v = make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
+            } else {
+                uint32_t words[4];
+                uint8_t *b = reinterpret_cast<uint8_t *>(words);
+                if (k + 16 <= nbytes) {
 #pragma unroll
-            for (int e = 0; e < 16; ++e) {
-                const int byte = k + e;
-                uint8_t v = 0;
-                if (srow) {
-                    if (byte < body) {
-                        v = srow[byte];
-                    } else {
-                        const int px = byte / C, c = byte - px * C;
-                        const int sx = border_index(px, w, mode);
-                        v = (sx >= 0) ? srow[sx * C + c] : 0;
+                    for (int e = 0; e < 16; ++e) {
+                        const int byte = k + e;
+                        b[e] = (srow && byte >= body0 && byte < body1) ? srow[byte - body0] : gather(byte);
                     }
+                    v = make_uint4(words[0], words[1], words[2], words[3]);
+                } else { // ragged end of a row whose length is not a multiple of 16 (cannot happen when vec_ok)
+                    for (int byte = k; byte < nbytes; ++byte) orow[byte] = gather(byte);
+                    continue;
                 }
-                b[e] = v;
             }
-            *reinterpret_cast<uint4 *>(orow + k) = make_uint4(words[0], words[1], words[2], words[3]);
+            *reinterpret_cast<uint4 *>(orow + k) = v;
         }
     } else {
-        for (int byte = threadIdx.x; byte < nbytes; byte += blockDim.x) {
-            uint8_t v = 0;
-            if (srow) {
-                const int px = byte / C, c = byte - px * C;
-                const int sx = border_index(px, w, mode);
-                v = (sx >= 0) ? srow[sx * C + c] : 0;
-            }
-            orow[byte] = v;
-        }
+        for (int byte = threadIdx.x; byte < nbytes; byte += blockDim.x) orow[byte] = gather(byte);
     }
+}
+
+static int launch_extract_pad(srf_ctx *ctx, const uint8_t *d_src, int channels, size_t pitch, const int *xywh, int n, int out_h, int out_w, int top,
+                              int left, int border, uint8_t *d_out, cudaStream_t st)
+{
+    {
+        const int rc = srf_reserve(ctx, ctx->ws_desc, (size_t)n * sizeof(int4));
+        if (rc) return rc;
+    }
+    ctx->desc_sig = 0; // ws_desc is shared with the fusion descriptors
+    ctx->fuse_sig = 0;
+    SRF_CHECK_CUDA(ctx, cudaMemcpyAsync(ctx->ws_desc.ptr, xywh, (size_t)n * sizeof(int4), cudaMemcpyHostToDevice, st));
+    const int vec_ok = ((out_w * channels) % 16 == 0) && (((uintptr_t)d_out) % 16 == 0);
+    dim3 grid(out_h, n);
+    {
+        double bytes = (double)n * out_h * out_w * channels;
+        for (int i = 0; i < n; ++i) bytes += (double)xywh[4 * i + 2] * xywh[4 * i + 3] * channels;
+        srf_launch_scope scope(ctx, "tile_extract_pad", bytes, st);
+        if (channels == 3)
+            k_tile_extract_pad<3><<<grid, 256, 0, st>>>(d_src, pitch, (const int4 *)ctx->ws_desc.ptr, out_h, out_w, top, left, border, d_out, vec_ok);
+        else
+            k_tile_extract_pad<1><<<grid, 256, 0, st>>>(d_src, pitch, (const int4 *)ctx->ws_desc.ptr, out_h, out_w, top, left, border, d_out, vec_ok);
+    }
+    SRF_CHECK_CUDA(ctx, cudaGetLastError());
+    return srf_note_device_work(ctx, st);
 }
 
 extern "C" int srf_tile_extract_pad(srf_ctx *ctx, const uint8_t *d_src, int height, int width, int channels, size_t pitch,
@@ -345,7 +417,7 @@ extern "C" int srf_tile_extract_pad(srf_ctx *ctx, const uint8_t *d_src, int heig
     SRF_REQUIRE(ctx, d_src && d_out && xywh, "srf_tile_extract_pad: null pointer");
     SRF_REQUIRE(ctx, channels == 1 || channels == 3, "srf_tile_extract_pad: channels must be 1 or 3 (got %d)", channels);
     SRF_REQUIRE(ctx, border >= 0 && border <= 3, "srf_tile_extract_pad: bad border mode %d", border);
-    SRF_REQUIRE(ctx, n >= 0 && block >= 1 && height >= 1 && width >= 1, "srf_tile_extract_pad: bad sizes");
+    SRF_REQUIRE(ctx, n >= 0 && block >= 1 && block <= 65535 && height >= 1 && width >= 1, "srf_tile_extract_pad: bad sizes");
     SRF_REQUIRE(ctx, pitch >= (size_t)width * channels, "srf_tile_extract_pad: pitch < row bytes");
     if (n == 0) return SRF_OK;
     for (int i = 0; i < n; ++i) {
@@ -353,37 +425,21 @@ extern "C" int srf_tile_extract_pad(srf_ctx *ctx, const uint8_t *d_src, int heig
         SRF_REQUIRE(ctx, x >= 0 && y >= 0 && w >= 1 && h >= 1 && x + w <= width && y + h <= height && w <= block && h <= block,
                     "srf_tile_extract_pad: tile %d (%d,%d,%d,%d) outside image %dx%d / block %d", i, x, y, w, h, width, height, block);
     }
-    cudaStream_t st = (cudaStream_t)stream;
     SRF_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
-    {
-        const int rc = srf_reserve(ctx, ctx->ws_desc, (size_t)n * sizeof(int4));
-        if (rc) return rc;
-    }
-    ctx->desc_sig = 0; // ws_desc is shared with the fusion descriptors
-    ctx->fuse_sig = 0;
-    SRF_CHECK_CUDA(ctx, cudaMemcpyAsync(ctx->ws_desc.ptr, xywh, (size_t)n * sizeof(int4), cudaMemcpyHostToDevice, st));
-    const int vec_ok = ((block * channels) % 16 == 0) && (((uintptr_t)d_out) % 16 == 0);
-    dim3 grid(block, n);
-    {
-        double bytes = (double)n * block * block * channels;
-        for (int i = 0; i < n; ++i) bytes += (double)xywh[4 * i + 2] * xywh[4 * i + 3] * channels;
-        srf_launch_scope scope(ctx, "tile_extract_pad", bytes, st);
-        if (channels == 3)
-            k_tile_extract_pad<3><<<grid, 256, 0, st>>>(d_src, pitch, (const int4 *)ctx->ws_desc.ptr, block, border, d_out, vec_ok);
-        else
-            k_tile_extract_pad<1><<<grid, 256, 0, st>>>(d_src, pitch, (const int4 *)ctx->ws_desc.ptr, block, border, d_out, vec_ok);
-    }
-    SRF_CHECK_CUDA(ctx, cudaGetLastError());
-    return SRF_OK;
+    return launch_extract_pad(ctx, d_src, channels, pitch, xywh, n, block, block, 0, 0, border, d_out, (cudaStream_t)stream);
 }
 
 extern "C" int srf_tile_extract_pad_host(srf_ctx *ctx, const uint8_t *h_src, int height, int width, int channels, size_t pitch,
                                          const int *xywh, int n, int block, int border, uint8_t *h_out)
 {
     if (!ctx) return SRF_ERR_ARG;
-    SRF_REQUIRE(ctx, h_src && h_out, "srf_tile_extract_pad_host: null pointer");
+    SRF_REQUIRE(ctx, h_src && h_out && xywh, "srf_tile_extract_pad_host: null pointer");
+    SRF_REQUIRE(ctx, channels == 1 || channels == 3, "srf_tile_extract_pad_host: channels must be 1 or 3 (got %d)", channels);
+    SRF_REQUIRE(ctx, n >= 0 && block >= 1 && height >= 1 && width >= 1, "srf_tile_extract_pad_host: bad sizes (n=%d block=%d image %dx%d)", n,
+                block, width, height);
     SRF_REQUIRE(ctx, pitch >= (size_t)width * channels, "srf_tile_extract_pad_host: pitch < row bytes");
     SRF_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (int hrc = srf_host_enter(ctx)) return hrc;
     const size_t dpitch = srf_align_up((size_t)width * channels, 256);
     const size_t out_bytes = (size_t)n * block * block * channels;
     int rc = srf_reserve(ctx, ctx->ws_stage_in, dpitch * height);
@@ -401,6 +457,58 @@ extern "C" int srf_tile_extract_pad_host(srf_ctx *ctx, const uint8_t *h_src, int
     ctx->ev_valid = true;
     if (out_bytes) SRF_CHECK_CUDA(ctx, cudaMemcpyAsync(h_out, ctx->ws_stage_out.ptr, out_bytes, cudaMemcpyDeviceToHost, st));
     SRF_CHECK_CUDA(ctx, cudaStreamSynchronize(st));
+    ctx->last_h2d = (size_t)width * channels * height;
+    ctx->last_d2h = out_bytes;
+    return SRF_OK;
+}
+
+// cv2.copyMakeBorder(image, top, bottom, left, right, mode) -- TilingModule._apply_padding in full generality
+// (tiling_module.py:522-570; split_image itself only ever pads bottom / right)
+static int check_border_args(srf_ctx *ctx, const void *s, const void *d, int h, int w, int C, size_t pitch, int top, int bottom, int left, int right,
+                             int border)
+{
+    SRF_REQUIRE(ctx, s && d, "srf_copy_make_border: null pointer");
+    SRF_REQUIRE(ctx, C == 1 || C == 3, "srf_copy_make_border: channels must be 1 or 3 (got %d)", C);
+    SRF_REQUIRE(ctx, h >= 1 && w >= 1 && pitch >= (size_t)w * C, "srf_copy_make_border: bad image %dx%d / pitch", w, h);
+    SRF_REQUIRE(ctx, top >= 0 && bottom >= 0 && left >= 0 && right >= 0, "srf_copy_make_border: negative padding");
+    SRF_REQUIRE(ctx, border >= 0 && border <= 3, "srf_copy_make_border: bad border mode %d", border);
+    SRF_REQUIRE(ctx, (long long)h + top + bottom <= 65535 * 32LL && (long long)w + left + right <= (1 << 28), "srf_copy_make_border: result too large");
+    return SRF_OK;
+}
+
+extern "C" int srf_copy_make_border(srf_ctx *ctx, const uint8_t *d_src, int h, int w, int channels, size_t pitch, int top, int bottom, int left,
+                                    int right, int border, uint8_t *d_dst, void *stream)
+{
+    if (!ctx) return SRF_ERR_ARG;
+    int rc = check_border_args(ctx, d_src, d_dst, h, w, channels, pitch, top, bottom, left, right, border);
+    if (rc) return rc;
+    SRF_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int xywh[4] = {0, 0, w, h};
+    return launch_extract_pad(ctx, d_src, channels, pitch, xywh, 1, h + top + bottom, w + left + right, top, left, border, d_dst, (cudaStream_t)stream);
+}
+
+extern "C" int srf_copy_make_border_host(srf_ctx *ctx, const uint8_t *h_src, int h, int w, int channels, size_t pitch, int top, int bottom,
+                                         int left, int right, int border, uint8_t *h_dst)
+{
+    if (!ctx) return SRF_ERR_ARG;
+    int rc = check_border_args(ctx, h_src, h_dst, h, w, channels, pitch, top, bottom, left, right, border);
+    if (rc) return rc;
+    SRF_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (int hrc = srf_host_enter(ctx)) return hrc;
+    const size_t dpitch = srf_align_up((size_t)w * channels, 256);
+    const size_t out_bytes = (size_t)(h + top + bottom) * (size_t)(w + left + right) * channels;
+    if ((rc = srf_reserve(ctx, ctx->ws_stage_in, dpitch * h))) return rc;
+    if ((rc = srf_reserve(ctx, ctx->ws_stage_out, out_bytes))) return rc;
+    cudaStream_t st = ctx->own_stream;
+    SRF_CHECK_CUDA(ctx, cudaMemcpy2DAsync(ctx->ws_stage_in.ptr, dpitch, h_src, pitch, (size_t)w * channels, h, cudaMemcpyHostToDevice, st));
+    const int xywh[4] = {0, 0, w, h};
+    if ((rc = launch_extract_pad(ctx, (const uint8_t *)ctx->ws_stage_in.ptr, channels, dpitch, xywh, 1, h + top + bottom, w + left + right, top, left,
+                                 border, (uint8_t *)ctx->ws_stage_out.ptr, st)))
+        return rc;
+    SRF_CHECK_CUDA(ctx, cudaMemcpyAsync(h_dst, ctx->ws_stage_out.ptr, out_bytes, cudaMemcpyDeviceToHost, st));
+    SRF_CHECK_CUDA(ctx, cudaStreamSynchronize(st));
+    ctx->last_h2d = (size_t)w * channels * h;
+    ctx->last_d2h = out_bytes;
     return SRF_OK;
 }
 
@@ -512,6 +620,7 @@ extern "C" int srf_pyr_down_f32_host(srf_ctx *ctx, const float *h_src, int h, in
     int rc = check_pyr_args(ctx, h_src, h_dst, h, w, cn, "srf_pyr_down_f32_host");
     if (rc) return rc;
     SRF_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (int hrc = srf_host_enter(ctx)) return hrc;
     const size_t ib = (size_t)h * w * cn * 4, ob = (size_t)((h + 1) / 2) * ((w + 1) / 2) * cn * 4;
     if ((rc = srf_reserve(ctx, ctx->ws_stage_in, ib))) return rc;
     if ((rc = srf_reserve(ctx, ctx->ws_stage_out, ob))) return rc;
@@ -531,6 +640,7 @@ extern "C" int srf_pyr_up_f32_host(srf_ctx *ctx, const float *h_src, int h, int 
     SRF_REQUIRE(ctx, (dh == 2 * h || dh == 2 * h - 1) && (dw == 2 * w || dw == 2 * w - 1) && dh >= 1 && dw >= 1,
                 "srf_pyr_up_f32_host: dst %dx%d must be 2n or 2n-1 of src %dx%d", dh, dw, h, w);
     SRF_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (int hrc = srf_host_enter(ctx)) return hrc;
     const size_t ib = (size_t)h * w * cn * 4, ob = (size_t)dh * dw * cn * 4;
     if ((rc = srf_reserve(ctx, ctx->ws_stage_in, ib))) return rc;
     if ((rc = srf_reserve(ctx, ctx->ws_stage_out, ob))) return rc;

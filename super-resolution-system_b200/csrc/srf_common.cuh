@@ -37,7 +37,11 @@ struct srf_buffer {
     size_t bytes = 0;
 };
 
+struct srf_comm; // srf_comm.cu: peer-memory inboxes of a multi-GPU job
+void srf_comm_free(struct srf_ctx *ctx);
+
 struct srf_ctx {
+    srf_comm *comm = nullptr;
     int device = 0;
     int sm_count = 148;
     std::string last_error;
@@ -63,6 +67,12 @@ struct srf_ctx {
     // weight pyramids of the previous fuse call still valid in ws_pyr: one key per shape group (srf_fuse.cu)
     std::vector<uint64_t> wcache_keys;
     const void *wcache_base = nullptr;
+    uint64_t wcache_epoch = ~0ull; // ws_epoch at which the cached weight pyramids were written (cudaFree + a larger cudaMalloc
+                                   // may hand back the same address, so the base pointer alone proves nothing)
+    // host entry points run on own_stream while device entry points enqueue on the caller's stream over the SAME
+    // workspaces: every device-path enqueue leaves an event here and every host entry point makes its streams wait on it
+    cudaEvent_t ev_dev = nullptr;
+    bool ev_dev_set = false;
     // CUDA-graph replay of a repeated srf_laplacian_fuse call (same tiles, canvas, band, stream): the second identical
     // call is captured, later ones are one cudaGraphLaunch.  Any workspace reallocation bumps ws_epoch and drops it.
     uint64_t fuse_sig = 0;        // signature of the last srf_laplacian_fuse call
@@ -115,6 +125,11 @@ void srf_set_error(srf_ctx *ctx, const char *fmt, ...);
 void srf_set_error(const srf_ctx *ctx, const char *fmt, ...);
 int srf_reserve(srf_ctx *ctx, srf_buffer &b, size_t bytes);
 int srf_reserve_pinned(srf_ctx *ctx, size_t bytes);
+// stream hygiene between the two families of entry points (they share the ctx workspaces):
+//   srf_note_device_work  a device-path entry point calls it after enqueuing on the caller's stream
+//   srf_host_enter        a *_host entry point calls it first: own / copy / down streams wait for that work
+int srf_note_device_work(srf_ctx *ctx, cudaStream_t st);
+int srf_host_enter(srf_ctx *ctx);
 
 static inline int srf_ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline size_t srf_align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }

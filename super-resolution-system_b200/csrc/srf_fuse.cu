@@ -1625,12 +1625,13 @@ int srf_fuse_device(srf_ctx *ctx, const srf_tile *tiles, int n_tiles, int C, int
         mix(w_off[k].data(), sizeof(size_t) * w_off[k].size());
         wkeys[k] = hsh;
     }
-    const bool wcache_hit_base = (ctx->wcache_base == ctx->ws_pyr.ptr);
+    const bool wcache_hit_base = (ctx->wcache_base == ctx->ws_pyr.ptr) && (ctx->wcache_epoch == ctx->ws_epoch);
     std::vector<bool> w_valid(groups.size(), false);
     for (size_t k = 0; k < groups.size(); ++k)
         w_valid[k] = wcache_hit_base && k < ctx->wcache_keys.size() && ctx->wcache_keys[k] == wkeys[k];
     ctx->wcache_keys = wkeys;
     ctx->wcache_base = ctx->ws_pyr.ptr;
+    ctx->wcache_epoch = ctx->ws_epoch;
 
     // ---- launches ----
     for (size_t k = 0; k < groups.size(); ++k) {
@@ -1820,7 +1821,7 @@ extern "C" int srf_laplacian_fuse(srf_ctx *ctx, const srf_tile *tiles, int n_til
         SRF_CHECK_CUDA(ctx, cudaGraphLaunch(ctx->fuse_graph, st));
         ctx->launches += ctx->fuse_graph_launches;
         ctx->ev_valid = false;
-        return SRF_OK;
+        return srf_note_device_work(ctx, st);
     }
     if (ctx->fuse_graph) {
         cudaGraphExecDestroy(ctx->fuse_graph);
@@ -1840,7 +1841,7 @@ extern "C" int srf_laplacian_fuse(srf_ctx *ctx, const srf_tile *tiles, int n_til
                 cudaGraphDestroy(graph);
                 SRF_CHECK_CUDA(ctx, cudaGraphLaunch(ctx->fuse_graph, st));
                 ctx->ev_valid = false;
-                return SRF_OK;
+                return srf_note_device_work(ctx, st);
             }
             if (graph) cudaGraphDestroy(graph);
             ctx->fuse_graph = nullptr;
@@ -1856,7 +1857,7 @@ extern "C" int srf_laplacian_fuse(srf_ctx *ctx, const srf_tile *tiles, int n_til
     if (rc) return rc;
     SRF_CHECK_CUDA(ctx, cudaEventRecord(ctx->ev1, st));
     ctx->ev_valid = true;
-    return SRF_OK;
+    return srf_note_device_work(ctx, st);
 }
 
 extern "C" int srf_laplacian_fuse_host(srf_ctx *ctx, const srf_tile *tiles, int n_tiles, int channels, int levels,
@@ -1867,6 +1868,7 @@ extern "C" int srf_laplacian_fuse_host(srf_ctx *ctx, const srf_tile *tiles, int 
     int rc = srf_check_fuse_args(ctx, tiles, n_tiles, channels, levels, luts, n_luts, out_h, out_w, h_canvas, canvas_pitch, row_begin, row_end);
     if (rc) return rc;
     SRF_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (int hrc = srf_host_enter(ctx)) return hrc;
     // device staging: every tile at a 256-byte aligned offset with a 16-byte-multiple pitch, then the canvas band
     std::vector<srf_tile> dt(tiles, tiles + n_tiles);
     std::vector<size_t> off(n_tiles);

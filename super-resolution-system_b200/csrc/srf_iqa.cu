@@ -42,9 +42,15 @@ struct IqaPartial {
     int max_a, max_b; // bitwise OR of every owned byte: <= 1 exactly when the image's max() <= 1
 };
 
+struct IqaPair { // one image pair of a batched launch (grid.z = pair)
+    const uint8_t *a, *b;
+    size_t pitch_a, pitch_b;
+};
+
 struct IqaParams {
     const uint8_t *a, *b;
     size_t pitch_a, pitch_b;
+    const IqaPair *pairs; // batched launch: pair blockIdx.z replaces (a, b, pitch_a, pitch_b); nullptr otherwise
     int h, w;
     int scale_a, scale_b;
     float c1, c2;
@@ -119,6 +125,15 @@ template <int C, bool ANYSCALE, int R>
 __global__ void __launch_bounds__(IQ_THREADS, 4) k_psnr_ssim(IqaParams P)
 {
     pdl_enter(); // programmatic dependent launch: nothing above this line may touch global data
+    const uint8_t *img_a = P.a, *img_b = P.b;
+    size_t pitch_a = P.pitch_a, pitch_b = P.pitch_b;
+    if (P.pairs != nullptr) { // batched launch (QualityAssessmentModule.batch_evaluate): every z-slice is its own image pair
+        const IqaPair q = P.pairs[blockIdx.z];
+        img_a = q.a;
+        img_b = q.b;
+        pitch_a = q.pitch_a;
+        pitch_b = q.pitch_b;
+    }
     __shared__ __align__(16) uint8_t s_raw[4][2][IQ2_RAW];
     __shared__ __align__(16) float2 s_ab[2][IQ2_SROW];
     __shared__ double s_red[IQ_THREADS / 32];
@@ -139,8 +154,8 @@ __global__ void __launch_bounds__(IQ_THREADS, 4) k_psnr_ssim(IqaParams P)
     constexpr int NCH = IQ2_RAW / 16;
     const bool loader = t < 2 * NCH;
     const int limg = (t >= NCH) ? 1 : 0, lchunk = t - limg * NCH;
-    const uint8_t *lbase = limg ? P.b : P.a;
-    const long long lpitch = (long long)(limg ? P.pitch_b : P.pitch_a);
+    const uint8_t *lbase = limg ? img_b : img_a;
+    const long long lpitch = (long long)(limg ? pitch_b : pitch_a);
     const int vr0 = max(P.row_begin - IQ_R, 0), vr1 = min(P.row_end + IQ_R, h);
     const uint8_t *llo = lbase + (long long)vr0 * lpitch;
     const uint8_t *lhi = lbase + (long long)(vr1 - 1) * lpitch + (long long)w * C;
@@ -174,9 +189,9 @@ __global__ void __launch_bounds__(IQ_THREADS, 4) k_psnr_ssim(IqaParams P)
 
     unsigned int sq = 0; // <= 266 rows * 4 px * 3 * 65025 < 2^32
     unsigned int bits_a = 0, bits_b = 0;
-    const int mis_a0 = (int)((reinterpret_cast<uintptr_t>(P.a) + (unsigned long long)col_off) & 15);
-    const int mis_b0 = (int)((reinterpret_cast<uintptr_t>(P.b) + (unsigned long long)col_off) & 15);
-    const int pa16 = (int)(P.pitch_a & 15), pb16 = (int)(P.pitch_b & 15);
+    const int mis_a0 = (int)((reinterpret_cast<uintptr_t>(img_a) + (unsigned long long)col_off) & 15);
+    const int mis_b0 = (int)((reinterpret_cast<uintptr_t>(img_b) + (unsigned long long)col_off) & 15);
+    const int pa16 = (int)(pitch_a & 15), pb16 = (int)(pitch_b & 15);
     // staged pixel i sits at image column cx0 - 5 + i; thread t converts the pairs (2t, 2t+1) and, t < 5, (256+2t, 257+2t).
     // byte masks of the pixels this CTA OWNS (columns [cx0, cx0 + 256) inside the image) within a pair's lo / hi words
     auto own = [&](int i) { const int colp = cx0 - IQ_R + i; return colp >= cx0 && colp < cx0 + IQ2_COLS && colp < w; };
@@ -353,7 +368,7 @@ __global__ void __launch_bounds__(IQ_THREADS, 4) k_psnr_ssim(IqaParams P)
             p.max_a |= s_mx[0][k];
             p.max_b |= s_mx[1][k];
         }
-        P.partials[blockIdx.y * gridDim.x + blockIdx.x] = p;
+        P.partials[(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = p;
     }
 }
 
@@ -362,6 +377,9 @@ __global__ void __launch_bounds__(256) k_iqa_reduce(const IqaPartial *__restrict
 {
     pdl_enter(); // programmatic dependent launch: nothing above this line may touch global data
     __shared__ IqaPartial s[256];
+    parts += (size_t)blockIdx.x * n; // batched: CTA z reduces the n partials of pair z
+    out += blockIdx.x;
+    if (dsum) dsum += 5 * blockIdx.x;
     IqaPartial p;
     p.ssim = 0;
     p.sq = 0;
@@ -404,8 +422,12 @@ __global__ void __launch_bounds__(256) k_iqa_reduce(const IqaPartial *__restrict
 
 } // namespace
 
-int srf_iqa_enqueue(srf_ctx *ctx, const uint8_t *a, size_t pa, const uint8_t *b, size_t pb, int h, int w, int C, int scale_a, int scale_b,
-                    double data_range, int row_begin, int row_end, cudaStream_t st, int slot, double *d_sums, int window)
+// one launch of k_psnr_ssim (+ the fixed-order reduction) over ONE pair (h_pairs == nullptr) or over n_pairs equally
+// sized pairs (grid.z = pair; h_pairs are the host copies of the descriptors).  Per-pair results: IqaPartial n_pairs x
+// at ws_iqa's tail (copied to ctx->pinned[slot ...] when slot >= 0) and, if d_sums != nullptr, 5 doubles per pair.
+static int iqa_launch(srf_ctx *ctx, const uint8_t *a, size_t pa, const uint8_t *b, size_t pb, const IqaPair *h_pairs, int n_pairs, int h, int w,
+                      int C, int scale_a, int scale_b, double data_range, int row_begin, int row_end, cudaStream_t st, int slot, double *d_sums,
+                      int window)
 {
     int rc;
     // S-map rows per CTA: tall CTAs amortise the vertical halo (2R rows re-filtered per CTA), but every CTA does the same
@@ -416,7 +438,7 @@ int srf_iqa_enqueue(srf_ctx *ctx, const uint8_t *a, size_t pa, const uint8_t *b,
     int rb = IQ_RB_MAX;
     long long best = -1;
     for (int cand = 32; cand <= 2 * IQ_RB_MAX; cand += 8) {
-        const long long ctas = (long long)gx * srf_ceil_div(row_end - row_begin, cand);
+        const long long ctas = (long long)gx * srf_ceil_div(row_end - row_begin, cand) * n_pairs;
         // fewer than three waves are charged as three: with one or two waves nothing overlaps the CTAs' fill and drain
         // (measured on 1 600-row bands: one wave of 208-row CTAs is slower than three waves of 64-row ones)
         const long long cost = (long long)(cand + 2 * IQ_R) * std::max<long long>((ctas + slots - 1) / slots, 3);
@@ -426,16 +448,22 @@ int srf_iqa_enqueue(srf_ctx *ctx, const uint8_t *a, size_t pa, const uint8_t *b,
         }
     }
     const int gy = srf_ceil_div(row_end - row_begin, rb);
-    const size_t nparts = (size_t)gx * gy;
-    if ((rc = srf_reserve(ctx, ctx->ws_iqa, (nparts + 1) * sizeof(IqaPartial)))) return rc;
-    if ((rc = srf_reserve_pinned(ctx, 4096))) return rc;
+    const size_t nparts = (size_t)gx * gy; // per pair
+    const size_t o_final = srf_align_up(nparts * n_pairs * sizeof(IqaPartial), 256);
+    const size_t o_pairs = o_final + srf_align_up((size_t)n_pairs * sizeof(IqaPartial), 256);
+    if ((rc = srf_reserve(ctx, ctx->ws_iqa, o_pairs + (size_t)n_pairs * sizeof(IqaPair)))) return rc;
+    if ((rc = srf_reserve_pinned(ctx, std::max<size_t>(4096, (size_t)(std::max(slot, 0) + n_pairs) * sizeof(IqaPartial))))) return rc;
     IqaPartial *parts = (IqaPartial *)ctx->ws_iqa.ptr;
-    IqaPartial *final_d = parts + nparts;
+    IqaPartial *final_d = (IqaPartial *)((uint8_t *)ctx->ws_iqa.ptr + o_final);
+    IqaPair *pairs_d = (IqaPair *)((uint8_t *)ctx->ws_iqa.ptr + o_pairs);
+    if (h_pairs) // pageable source: staged before the call returns
+        SRF_CHECK_CUDA(ctx, cudaMemcpyAsync(pairs_d, h_pairs, (size_t)n_pairs * sizeof(IqaPair), cudaMemcpyHostToDevice, st));
     IqaParams P;
     P.a = a;
     P.b = b;
     P.pitch_a = pa;
     P.pitch_b = pb;
+    P.pairs = h_pairs ? pairs_d : nullptr;
     P.h = h;
     P.w = w;
     P.scale_a = scale_a;
@@ -448,8 +476,8 @@ int srf_iqa_enqueue(srf_ctx *ctx, const uint8_t *a, size_t pa, const uint8_t *b,
     P.row_end = row_end;
     P.partials = parts;
     if (nparts > 0) {
-        dim3 grid(gx, gy);
-        srf_launch_scope scope(ctx, "psnr_ssim", 2.0 * (double)(row_end - row_begin) * w * C, st);
+        dim3 grid(gx, gy, n_pairs);
+        srf_launch_scope scope(ctx, "psnr_ssim", 2.0 * (double)(row_end - row_begin) * w * C * n_pairs, st);
         const bool any = scale_a || scale_b; // the rare max() <= 1 rescale: generic instantiation
 #define IQ_LAUNCH(CC, ANY, RR) srf_launch_pdl(k_psnr_ssim<CC, ANY, RR>, grid, dim3(IQ_THREADS), 0, st, P)
         if (window == 0) {
@@ -463,12 +491,18 @@ int srf_iqa_enqueue(srf_ctx *ctx, const uint8_t *a, size_t pa, const uint8_t *b,
     }
     {
         srf_launch_scope scope(ctx, "iqa_reduce", 0.0, st);
-        srf_launch_pdl(k_iqa_reduce, dim3(1), dim3(256), 0, st, (const IqaPartial *)parts, (int)nparts, final_d, d_sums);
+        srf_launch_pdl(k_iqa_reduce, dim3(n_pairs), dim3(256), 0, st, (const IqaPartial *)parts, (int)nparts, final_d, d_sums);
     }
     SRF_CHECK_CUDA(ctx, cudaGetLastError());
     if (slot >= 0)
-        SRF_CHECK_CUDA(ctx, cudaMemcpyAsync((IqaPartial *)ctx->pinned + slot, final_d, sizeof(IqaPartial), cudaMemcpyDeviceToHost, st));
+        SRF_CHECK_CUDA(ctx, cudaMemcpyAsync((IqaPartial *)ctx->pinned + slot, final_d, (size_t)n_pairs * sizeof(IqaPartial), cudaMemcpyDeviceToHost, st));
     return SRF_OK;
+}
+
+int srf_iqa_enqueue(srf_ctx *ctx, const uint8_t *a, size_t pa, const uint8_t *b, size_t pb, int h, int w, int C, int scale_a, int scale_b,
+                    double data_range, int row_begin, int row_end, cudaStream_t st, int slot, double *d_sums, int window)
+{
+    return iqa_launch(ctx, a, pa, b, pb, nullptr, 1, h, w, C, scale_a, scale_b, data_range, row_begin, row_end, st, slot, d_sums, window);
 }
 
 void srf_iqa_collect(srf_ctx *ctx, int w, int C, int row_begin, int row_end, srf_iqa_sums *out, int slot)
@@ -526,6 +560,7 @@ extern "C" int srf_psnr_ssim_host(srf_ctx *ctx, const uint8_t *h_a, size_t pitch
     int rc = check_iqa_args(ctx, h_a, pitch_a, h_b, pitch_b, h, w, channels, row_begin, row_end, h_out, window);
     if (rc) return rc;
     SRF_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (int hrc = srf_host_enter(ctx)) return hrc;
     // stage only the rows the band reads: [row_begin - 5, row_end + 5) clipped
     const int r0 = row_begin - IQ_R < 0 ? 0 : row_begin - IQ_R, r1 = row_end + IQ_R > h ? h : row_end + IQ_R;
     const size_t dp = srf_align_up((size_t)w * channels, 256);
@@ -548,6 +583,88 @@ extern "C" int srf_psnr_ssim_enqueue(srf_ctx *ctx, const uint8_t *d_a, size_t pi
     int rc = check_iqa_args(ctx, d_a, pitch_a, d_b, pitch_b, h, w, channels, row_begin, row_end, d_sums5, window);
     if (rc) return rc;
     SRF_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
-    return srf_iqa_enqueue(ctx, d_a, pitch_a, d_b, pitch_b, h, w, channels, scale_a, scale_b, data_range, row_begin, row_end,
-                           (cudaStream_t)stream, -1, d_sums5, window);
+    rc = srf_iqa_enqueue(ctx, d_a, pitch_a, d_b, pitch_b, h, w, channels, scale_a, scale_b, data_range, row_begin, row_end,
+                         (cudaStream_t)stream, -1, d_sums5, window);
+    return rc ? rc : srf_note_device_work(ctx, (cudaStream_t)stream);
+}
+
+// ---- batched pairs (QualityAssessmentModule.batch_evaluate, quality_assessment_module.py:1350-1371: one result per pair) ----
+static int check_batch_args(srf_ctx *ctx, const srf_image_pair *pairs, int n_pairs, int h, int w, int C, const void *out, int window)
+{
+    SRF_REQUIRE(ctx, pairs && out, "psnr_ssim_batch: null pointer");
+    SRF_REQUIRE(ctx, n_pairs >= 1 && n_pairs <= 65535, "psnr_ssim_batch: n_pairs must be 1..65535 (got %d)", n_pairs);
+    SRF_REQUIRE(ctx, C == 1 || C == 3, "psnr_ssim_batch: channels must be 1 or 3 (got %d)", C);
+    SRF_REQUIRE(ctx, h >= 1 && w >= 1, "psnr_ssim_batch: empty image");
+    SRF_REQUIRE(ctx, window == 0 || window == 1, "psnr_ssim_batch: window must be 0 (11x11 Gaussian) or 1 (7x7 uniform), got %d", window);
+    for (int i = 0; i < n_pairs; ++i) {
+        SRF_REQUIRE(ctx, pairs[i].a && pairs[i].b, "psnr_ssim_batch: pair %d has a null image", i);
+        SRF_REQUIRE(ctx, pairs[i].pitch_a >= (size_t)w * C && pairs[i].pitch_b >= (size_t)w * C, "psnr_ssim_batch: pair %d pitch < row bytes", i);
+    }
+    return SRF_OK;
+}
+
+static void batch_collect(srf_ctx *ctx, int n_pairs, int h, int w, int C, srf_iqa_sums *out)
+{
+    for (int i = 0; i < n_pairs; ++i) srf_iqa_collect(ctx, w, C, 0, h, out + i, i);
+}
+
+extern "C" int srf_psnr_ssim_batch(srf_ctx *ctx, const srf_image_pair *pairs, int n_pairs, int h, int w, int channels, double data_range,
+                                   int window, srf_iqa_sums *h_out, void *stream)
+{
+    if (!ctx) return SRF_ERR_ARG;
+    int rc = check_batch_args(ctx, pairs, n_pairs, h, w, channels, h_out, window);
+    if (rc) return rc;
+    SRF_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+    static_assert(sizeof(IqaPair) == sizeof(srf_image_pair), "descriptor layouts must agree");
+    std::vector<IqaPair> hp(n_pairs);
+    for (int i = 0; i < n_pairs; ++i) hp[i] = IqaPair{pairs[i].a, pairs[i].b, pairs[i].pitch_a, pairs[i].pitch_b};
+    cudaStream_t st = (cudaStream_t)stream;
+    if ((rc = iqa_launch(ctx, nullptr, 0, nullptr, 0, hp.data(), n_pairs, h, w, channels, 0, 0, data_range, 0, h, st, 0, nullptr, window))) return rc;
+    SRF_CHECK_CUDA(ctx, cudaStreamSynchronize(st));
+    batch_collect(ctx, n_pairs, h, w, channels, h_out);
+    return SRF_OK;
+}
+
+extern "C" int srf_psnr_ssim_batch_enqueue(srf_ctx *ctx, const srf_image_pair *pairs, int n_pairs, int h, int w, int channels, double data_range,
+                                           int window, double *d_sums5n, void *stream)
+{
+    if (!ctx) return SRF_ERR_ARG;
+    int rc = check_batch_args(ctx, pairs, n_pairs, h, w, channels, d_sums5n, window);
+    if (rc) return rc;
+    SRF_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+    std::vector<IqaPair> hp(n_pairs);
+    for (int i = 0; i < n_pairs; ++i) hp[i] = IqaPair{pairs[i].a, pairs[i].b, pairs[i].pitch_a, pairs[i].pitch_b};
+    rc = iqa_launch(ctx, nullptr, 0, nullptr, 0, hp.data(), n_pairs, h, w, channels, 0, 0, data_range, 0, h, (cudaStream_t)stream, -1, d_sums5n,
+                    window);
+    return rc ? rc : srf_note_device_work(ctx, (cudaStream_t)stream);
+}
+
+extern "C" int srf_psnr_ssim_batch_host(srf_ctx *ctx, const srf_image_pair *pairs, int n_pairs, int h, int w, int channels, double data_range,
+                                        int window, srf_iqa_sums *h_out)
+{
+    if (!ctx) return SRF_ERR_ARG;
+    int rc = check_batch_args(ctx, pairs, n_pairs, h, w, channels, h_out, window);
+    if (rc) return rc;
+    SRF_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (int hrc = srf_host_enter(ctx)) return hrc;
+    const size_t dp = srf_align_up((size_t)w * channels, 256), one = dp * (size_t)h;
+    if ((rc = srf_reserve(ctx, ctx->ws_stage_in, 2 * one * (size_t)n_pairs))) return rc;
+    cudaStream_t st = ctx->own_stream;
+    uint8_t *base = (uint8_t *)ctx->ws_stage_in.ptr;
+    std::vector<IqaPair> hp(n_pairs);
+    for (int i = 0; i < n_pairs; ++i) {
+        uint8_t *da = base + (size_t)(2 * i) * one, *db = da + one;
+        SRF_CHECK_CUDA(ctx, cudaMemcpy2DAsync(da, dp, pairs[i].a, pairs[i].pitch_a, (size_t)w * channels, h, cudaMemcpyHostToDevice, st));
+        SRF_CHECK_CUDA(ctx, cudaMemcpy2DAsync(db, dp, pairs[i].b, pairs[i].pitch_b, (size_t)w * channels, h, cudaMemcpyHostToDevice, st));
+        hp[i] = IqaPair{da, db, dp, dp};
+    }
+    SRF_CHECK_CUDA(ctx, cudaEventRecord(ctx->ev0, st));
+    if ((rc = iqa_launch(ctx, nullptr, 0, nullptr, 0, hp.data(), n_pairs, h, w, channels, 0, 0, data_range, 0, h, st, 0, nullptr, window))) return rc;
+    SRF_CHECK_CUDA(ctx, cudaEventRecord(ctx->ev1, st));
+    ctx->ev_valid = true;
+    SRF_CHECK_CUDA(ctx, cudaStreamSynchronize(st));
+    batch_collect(ctx, n_pairs, h, w, channels, h_out);
+    ctx->last_h2d = 2 * (size_t)w * channels * h * (size_t)n_pairs;
+    ctx->last_d2h = (size_t)n_pairs * sizeof(IqaPartial);
+    return SRF_OK;
 }

@@ -236,7 +236,8 @@ extern "C" int srf_merge_tiles(srf_ctx *ctx, const srf_merge_tile *tiles, int n_
     int rc = check_merge_args(ctx, tiles, n_tiles, channels, out_h, out_w, d_canvas, canvas_pitch);
     if (rc) return rc;
     SRF_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
-    return merge_device(ctx, tiles, n_tiles, channels, out_h, out_w, d_canvas, canvas_pitch, (cudaStream_t)stream);
+    rc = merge_device(ctx, tiles, n_tiles, channels, out_h, out_w, d_canvas, canvas_pitch, (cudaStream_t)stream);
+    return rc ? rc : srf_note_device_work(ctx, (cudaStream_t)stream);
 }
 
 extern "C" int srf_merge_tiles_host(srf_ctx *ctx, const srf_merge_tile *tiles, int n_tiles, int channels, int out_h, int out_w, uint8_t *h_canvas,
@@ -246,6 +247,7 @@ extern "C" int srf_merge_tiles_host(srf_ctx *ctx, const srf_merge_tile *tiles, i
     int rc = check_merge_args(ctx, tiles, n_tiles, channels, out_h, out_w, h_canvas, canvas_pitch);
     if (rc) return rc;
     SRF_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (int hrc = srf_host_enter(ctx)) return hrc;
     std::vector<srf_merge_tile> dt(tiles, tiles + n_tiles);
     std::vector<size_t> off(n_tiles);
     size_t total = 0, h2d = 0;

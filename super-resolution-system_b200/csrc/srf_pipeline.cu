@@ -44,6 +44,7 @@ extern "C" int srf_fuse_assess_host(srf_ctx *ctx, const srf_tile *tiles, int n_t
     SRF_REQUIRE(ctx, h_reference && h_out, "srf_fuse_assess_host: null pointer");
     SRF_REQUIRE(ctx, reference_pitch >= (size_t)out_w * channels, "srf_fuse_assess_host: reference pitch < row bytes");
     SRF_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (int hrc = srf_host_enter(ctx)) return hrc;
 
     // ---- device staging layout ----
     std::vector<srf_tile> dt(tiles, tiles + n_tiles);
@@ -87,12 +88,15 @@ extern "C" int srf_fuse_assess_host(srf_ctx *ctx, const srf_tile *tiles, int n_t
         ev_fused[b] = take_event(ctx);
         ev_ref[b] = take_event(ctx);
     }
+    size_t h2d = 0;
+    // everything that can fail runs inside `run`; whatever it returns, the single exit below drains the three streams
+    // (queued copies reference the caller's buffers and the staging workspaces) and hands the events back to the pool
+    auto run = [&]() -> int {
     // ---- upload stream: everything is queued now; the copy engine works through it in band order.  Tiles lead, the
     // comparison image's rows trail by one band: fusing (and downloading) a band only needs its tiles, the assessment
     // of band b-1 only needs comparison rows up to band b -- so the tail of the call is one small upload + one small
     // kernel, not a fuse + download.
     std::vector<char> uploaded(n_tiles, 0);
-    size_t h2d = 0;
     auto upload_ref = [&](int b) -> int {
         const int r0 = band_lo(b), r1 = band_hi(b);
         if (r1 > r0)
@@ -154,14 +158,20 @@ extern "C" int srf_fuse_assess_host(srf_ctx *ctx, const srf_tile *tiles, int n_t
         if (rc) return rc;
     }
     SRF_CHECK_CUDA(ctx, cudaEventRecord(ctx->ev1, st));
-    ctx->ev_valid = true;
-    SRF_CHECK_CUDA(ctx, cudaStreamSynchronize(st));
-    SRF_CHECK_CUDA(ctx, cudaStreamSynchronize(dn));
+    return SRF_OK;
+    };
+    rc = run();
+    const cudaError_t e_up = cudaStreamSynchronize(up), e_st = cudaStreamSynchronize(st), e_dn = cudaStreamSynchronize(dn);
     for (int b = 0; b < nb; ++b) {
         ctx->ev_pool.push_back(ev_up[b]);
         ctx->ev_pool.push_back(ev_fused[b]);
         ctx->ev_pool.push_back(ev_ref[b]);
     }
+    ctx->ev_valid = (rc == SRF_OK);
+    if (rc) return rc;
+    SRF_CHECK_CUDA(ctx, e_up);
+    SRF_CHECK_CUDA(ctx, e_st);
+    SRF_CHECK_CUDA(ctx, e_dn);
 
     srf_iqa_sums acc;
     acc.sq_err = 0;

@@ -141,7 +141,8 @@ extern "C" int srf_resize_cubic_u8(srf_ctx *ctx, const uint8_t *d_src, size_t sr
     int rc = check_resize_args(ctx, d_src, src_pitch, h, w, channels, d_dst, dst_pitch, dst_h, dst_w);
     if (rc) return rc;
     SRF_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
-    return resize_device(ctx, d_src, src_pitch, h, w, channels, d_dst, dst_pitch, dst_h, dst_w, (cudaStream_t)stream);
+    rc = resize_device(ctx, d_src, src_pitch, h, w, channels, d_dst, dst_pitch, dst_h, dst_w, (cudaStream_t)stream);
+    return rc ? rc : srf_note_device_work(ctx, (cudaStream_t)stream);
 }
 
 extern "C" int srf_resize_cubic_u8_host(srf_ctx *ctx, const uint8_t *h_src, size_t src_pitch, int h, int w, int channels, uint8_t *h_dst,
@@ -151,6 +152,7 @@ extern "C" int srf_resize_cubic_u8_host(srf_ctx *ctx, const uint8_t *h_src, size
     int rc = check_resize_args(ctx, h_src, src_pitch, h, w, channels, h_dst, dst_pitch, dst_h, dst_w);
     if (rc) return rc;
     SRF_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (int hrc = srf_host_enter(ctx)) return hrc;
     const size_t sp = srf_align_up((size_t)w * channels, 256), dp = srf_align_up((size_t)dst_w * channels, 256);
     if ((rc = srf_reserve(ctx, ctx->ws_stage_in, sp * (size_t)h))) return rc;
     if ((rc = srf_reserve(ctx, ctx->ws_stage_out, dp * (size_t)dst_h))) return rc;

@@ -152,6 +152,7 @@ extern "C" int srf_window_ssim_host(srf_ctx *ctx, const uint8_t *h_result, size_
     if (rc) return rc;
     if (ny == 0 || nx == 0) return SRF_OK;
     SRF_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (int hrc = srf_host_enter(ctx)) return hrc;
     // only the shared region travels: both images share one staging buffer, the scores the other
     const size_t dp = srf_align_up((size_t)roi_w * channels, 256), one = dp * (size_t)roi_h, ob = sizeof(double) * (size_t)ny * nx;
     if ((rc = srf_reserve(ctx, ctx->ws_stage_in, 2 * one))) return rc;

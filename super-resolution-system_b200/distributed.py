@@ -3,8 +3,10 @@
 The canvas is cut into `world` horizontal bands.  A rank fuses its band (plus a 5-row halo each side, so the 11x11
 SSIM window never needs a neighbour's pixels) from the tiles that reach it -- per-tile pyramids have tile-local
 borders, so a rank recomputes the pyramid rows its band depends on (libsrfuse derives those row ranges itself from
-`row_begin/row_end`) and the data path needs NO collective.  The only exchange is the all-reduce of the additive
-PSNR / SSIM partial sums (srf_iqa_sums): three numbers per rank, over NCCL on the GPUs (gloo in the CPU tests).
+`row_begin/row_end`).  The only exchange is the sum of the additive PSNR / SSIM partial sums (srf_iqa_sums): on the
+GPUs it is libsrfuse's own peer-memory exchange (SumsExchange -> srf_allreduce_metrics: one small kernel per rank that
+writes into every peer's inbox over NVLink, no NCCL call in the step); torch.distributed only carries the 64-byte IPC
+handles at start-up, and is the fallback collective where peer mapping is unavailable (and gloo in the CPU tests).
 """
 from __future__ import annotations
 
@@ -132,3 +134,105 @@ def allreduce_device_sums(d_sums, total_elems: int, group=None):
     s.sq_err, s.ssim_sum, s.ssim_count, s.n_elems = int(v[0]), v[1], int(v[2]), int(total_elems)
     s.bits_a, s.bits_b = (255 if v[3] > 0 else 1), (255 if v[4] > 0 else 1)
     return s
+
+
+class SumsExchange:
+    """Job-wide totals of the additive IQA sums, `slots` x 5 doubles {sq_err, ssim_sum, ssim_count, any byte of a > 1, of
+    b > 1} (slot 0 = the banded canvas pair; further slots = whole pairs owned by single ranks).
+
+    kind == "peer"  libsrfuse's NVLink exchange (include/srfuse.h: srf_comm_handle / srf_comm_init /
+                    srf_allreduce_metrics / srf_comm_result): enqueue-only kernel, totals land in pinned host memory
+    kind == "nccl"  torch.distributed all_reduce + one read-back (when the peers' memory cannot be mapped)
+    kind == "local" world size 1: only the read-back
+    `local` is the device tensor the IQA kernels write a rank's own sums into; reduce() leaves the totals in it."""
+
+    def __init__(self, device, group=None, slots: int = 1, allow_peer: bool = True):
+        import ctypes as C
+        import torch.distributed as dist
+        self.device, self.group, self.slots = device, group, int(slots)
+        self.local = torch.zeros(5 * self.slots, dtype=torch.float64, device=device)
+        self._scratch = None
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.kind = "local"
+        self._lib, self._ctx = _native.load(), _native.context(device.index)
+        self._host = (C.c_double * (5 * self.slots))()
+        if self.world == 1:
+            return
+        self.kind = "nccl"
+        if not allow_peer or 5 * self.slots > 128 or self.world > 16:
+            return
+        handle = (C.c_uint8 * 64)()
+        ok = self._lib.srf_comm_handle(self._ctx, handle) == 0
+        mine = torch.tensor(list(handle), dtype=torch.uint8, device=device)
+        every = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(every, mine, group=group)
+        if ok:
+            blob = bytes(torch.stack(every).cpu().numpy().tobytes())
+            ok = self._lib.srf_comm_init(self._ctx, self.rank, self.world, blob) == 0
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)  # all ranks or none: a mixed job would deadlock
+        if int(flag.item()) == 1:
+            self.kind = "peer"
+
+    # -- per-step ----------------------------------------------------------------------------------------------
+    def _totals(self):
+        """sum self.local over the ranks (in place) and return the 5 * slots totals as Python floats"""
+        if self.kind == "peer":
+            st = torch.cuda.current_stream(self.device).cuda_stream
+            _native.check(self._lib.srf_allreduce_metrics(self._ctx, self.local.data_ptr(), 5 * self.slots, st), self._ctx)
+            _native.check(self._lib.srf_comm_result(self._ctx, self._host, 5 * self.slots, st), self._ctx)
+            return list(self._host)
+        if self.kind == "nccl":
+            import torch.distributed as dist
+            dist.all_reduce(self.local, op=dist.ReduceOp.SUM, group=self.group)
+        return self.local.tolist()
+
+    @staticmethod
+    def _sums(v, total_elems):
+        s = _native.srf_iqa_sums()
+        s.sq_err, s.ssim_sum, s.ssim_count, s.n_elems = int(v[0]), v[1], int(v[2]), int(total_elems)
+        s.bits_a, s.bits_b = (255 if v[3] > 0 else 1), (255 if v[4] > 0 else 1)
+        return s
+
+    def reduce(self, total_elems: int):
+        """slot 0 only: the job-wide srf_iqa_sums of the banded pair"""
+        return self._sums(self._totals()[:5], total_elems)
+
+    def reduce_many(self, total_elems):
+        v = self._totals()
+        return [self._sums(v[5 * k:5 * k + 5], n) for k, n in enumerate(total_elems)]
+
+    def scratch(self, n: int):
+        """5 * n doubles for a batched launch's per-pair sums (scatter_scratch moves them to their slots)"""
+        if self._scratch is None or self._scratch.numel() < 5 * n:
+            self._scratch = torch.zeros(5 * n, dtype=torch.float64, device=self.device)
+        return self._scratch
+
+    def scatter_scratch(self, slot_ids):
+        key = tuple(slot_ids)
+        if getattr(self, "_idx_key", None) != key:
+            self._idx = torch.tensor([5 * k + j for k in key for j in range(5)], dtype=torch.long, device=self.device)
+            self._idx_key = key
+        self.local.index_copy_(0, self._idx, self._scratch[:self._idx.numel()])
+
+    def _load_host(self, slot_sums):
+        self.local.zero_()
+        if slot_sums:
+            vals = torch.zeros(5 * self.slots, dtype=torch.float64)
+            for k, s in slot_sums:
+                vals[5 * k:5 * k + 5] = torch.tensor([float(s.sq_err), s.ssim_sum, float(s.ssim_count), float(s.bits_a > 1), float(s.bits_b > 1)],
+                                                     dtype=torch.float64)
+            self.local.copy_(vals)
+
+    def reduce_host(self, sums, total_elems: int):
+        """host-side srf_iqa_sums of this rank's band -> job-wide sums (the e2e legs)"""
+        if self.world == 1:
+            sums.n_elems = int(total_elems)
+            return sums
+        self._load_host([(0, sums)])
+        return self.reduce(total_elems)
+
+    def reduce_many_host(self, slot_sums, total_elems):
+        self._load_host(slot_sums)
+        return self.reduce_many(total_elems)

@@ -143,8 +143,11 @@ class SuperResolutionPipeline:
                 report = self.quality_module.evaluate_full_reference(ref, canvas_d, scale_factor=2)
             canvas = canvas_d.cpu().numpy()
         elif cfg.enable_qa:
+            # host upscaler: same report schema as the device path (every evaluate_full_reference key), so the
+            # _qa_report.json does not depend on which upscaler was plugged in
             ref = reference if reference is not None else bicubic_stub(image, canvas_hw)
-            canvas, report = self.fuse_and_assess(infos, ref, canvas_hw)
+            canvas = fuse(infos, output_shape=canvas_hw)
+            report = self.quality_module.evaluate_full_reference(ref, canvas, scale_factor=2)
         else:
             canvas = fuse(infos, output_shape=canvas_hw)
         return {"canvas": canvas, "report": report, "tiles": len(tiles)}

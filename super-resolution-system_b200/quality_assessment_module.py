@@ -137,6 +137,25 @@ class QualityAssessmentModule:
         _native.check(rc, ctx)
         return out
 
+    def psnr_ssim_sums_device_rows(self, rows1, rows2, out, image_rows: int, first_row: int, data_range: float = 255.0,
+                                   row_range=None):
+        """psnr_ssim_sums_device for a rank that holds only a ROW SLICE of a tall pair: `rows1` / `rows2` are rows
+        [first_row, first_row + k) of two images with `image_rows` rows; `row_range` (image coordinates) must lie inside
+        the slice minus the 5-row window halo (except at the image's own top / bottom edge)."""
+        va, vb = ImageView(rows1, "rows1"), ImageView(rows2, "rows2")
+        if not (va.on_device and vb.on_device) or (va.h, va.w, va.c) != (vb.h, vb.w, vb.c):
+            raise ValueError("psnr_ssim_sums_device_rows takes two CUDA uint8 slices of equal shape")
+        r0, r1 = (first_row, first_row + va.h) if row_range is None else (int(row_range[0]), int(row_range[1]))
+        lo, hi = max(r0 - 5, 0), min(r1 + 5, int(image_rows))
+        if r1 > r0 and (lo < first_row or hi > first_row + va.h):
+            raise ValueError(f"rows [{r0}, {r1}) +- 5 are not inside the slice [{first_row}, {first_row + va.h})")
+        lib, ctx = _native.load(), _native.context(va.device)
+        # the kernel addresses rows of the whole image: shift the base pointers up by the rows the slice does not hold
+        rc = lib.srf_psnr_ssim_enqueue(ctx, va.ptr - first_row * va.pitch, va.pitch, vb.ptr - first_row * vb.pitch, vb.pitch, int(image_rows),
+                                       va.w, va.c, 0, 0, float(data_range), 0, r0, r1, out.data_ptr(), current_stream_ptr(va.device))
+        _native.check(rc, ctx)
+        return out
+
     @staticmethod
     def finish(sums, data_range: float = 255.0) -> Tuple[float, float]:
         p, s = C.c_double(), C.c_double()
@@ -272,5 +291,94 @@ class QualityAssessmentModule:
         metrics["overall_score"] = self._calculate_overall_score(metrics)
         return metrics
 
+    # ------------------------------------------------------------------ batched pairs
+    def batch_psnr_ssim_sums(self, image_pairs, data_range: float = 255.0, window: int = 0, out=None):
+        """srf_iqa_sums of MANY equally shaped pairs from ONE kernel launch (grid.z = pair): include/srfuse.h
+        srf_psnr_ssim_batch[_host | _enqueue].  Pairs are (original, upscaled) uint8 images, all NumPy (host path: the
+        library stages them) or all CUDA tensors.  With `out` (float64 CUDA tensor, 5 * n elements, device pairs only)
+        nothing is synchronised and `out` receives 5 additive doubles per pair -- the form ranks all-reduce."""
+        views = [(ImageView(a, f"pair {i} original"), ImageView(b, f"pair {i} upscaled")) for i, (a, b) in enumerate(image_pairs)]
+        if not views:
+            return []
+        va0 = views[0][0]
+        for va, vb in views:
+            if (va.h, va.w, va.c) != (va0.h, va0.w, va0.c) or (vb.h, vb.w, vb.c) != (va0.h, va0.w, va0.c):
+                raise ValueError("batch_psnr_ssim_sums: every image of the batch must have the same shape")
+            if va.on_device != va0.on_device or vb.on_device != va0.on_device:
+                raise ValueError("batch_psnr_ssim_sums: mix of host and device images")
+        n = len(views)
+        c_pairs = (_native.srf_image_pair * n)(*[_native.srf_image_pair(va.ptr, vb.ptr, va.pitch, vb.pitch) for va, vb in views])
+        lib, ctx = _native.load(), _native.context(va0.device if va0.on_device else self.device_index)
+        if out is not None:
+            if not va0.on_device or out.dtype != torch.float64 or out.numel() < 5 * n or not out.is_cuda:
+                raise ValueError("out needs device pairs and a float64 CUDA tensor with 5 elements per pair")
+            rc = lib.srf_psnr_ssim_batch_enqueue(ctx, c_pairs, n, va0.h, va0.w, va0.c, float(data_range), int(window), out.data_ptr(),
+                                                 current_stream_ptr(va0.device))
+            _native.check(rc, ctx)
+            return out
+        sums = (_native.srf_iqa_sums * n)()
+        if va0.on_device:
+            rc = lib.srf_psnr_ssim_batch(ctx, c_pairs, n, va0.h, va0.w, va0.c, float(data_range), int(window), sums,
+                                         current_stream_ptr(va0.device))
+        else:
+            rc = lib.srf_psnr_ssim_batch_host(ctx, c_pairs, n, va0.h, va0.w, va0.c, float(data_range), int(window), sums)
+        _native.check(rc, ctx)
+        return list(sums)
+
     def batch_evaluate(self, image_pairs, scale_factor: int = 4) -> List[Dict[str, float]]:
-        return [self.evaluate_full_reference(o, u, scale_factor) for o, u in image_pairs]
+        """one evaluate_full_reference dict per pair, in order (q.a.m:1350-1371; exceptions propagate as in the
+        reference's loop).  Pairs of equal shape are uploaded once and scored together: the 11x11-Gaussian pass (psnr,
+        ms_ssim) and the 7x7 pass (ssim) are ONE batched launch each over all of them (srf_psnr_ssim_batch, grid.z =
+        pair), and so is every scale of the down-sample comparison; odd-shaped pairs take the per-pair route."""
+        pairs = list(image_pairs)
+        results: List[Optional[Dict[str, float]]] = [None] * len(pairs)
+        groups: Dict[tuple, List[int]] = {}
+        prepared = {}
+        for i, (o, u) in enumerate(pairs):
+            a, b = self._crop_common(self._preprocess_image(o), self._preprocess_image(u))
+            if is_cuda_tensor(a) != is_cuda_tensor(b):
+                raise ValueError("image pair must be both host or both device")
+            if not is_cuda_tensor(a):
+                if torch is None or not torch.cuda.is_available():
+                    raise _native.SrfError("batch_evaluate needs a CUDA device (there is no CPU fallback)")
+                dev = torch.device("cuda", self.device_index)
+                a = torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+                b = torch.from_numpy(np.ascontiguousarray(b)).to(dev)
+            prepared[i] = (a.contiguous(), b.contiguous())
+            groups.setdefault((tuple(a.shape), a.device.index), []).append(i)
+
+        def degenerate(sums):  # the max() <= 1 rescale rule or an image below the window size: per-pair route
+            return any(s.bits_a <= 1 or s.bits_b <= 1 or s.ssim_count <= 0 for s in sums)
+
+        for idx in groups.values():
+            batch = [prepared[i] for i in idx]
+            mets = None
+            if len(idx) > 1:
+                full = self.batch_psnr_ssim_sums(batch, window=0)
+                uni = self.batch_psnr_ssim_sums(batch, window=1)
+                if not degenerate(list(full) + list(uni)):
+                    mets = [dict() for _ in idx]
+                    for scale in self.scale_config.scale_factors:
+                        name = self.scale_config.scale_names.get(scale, f"scale_{scale}")
+                        small = [(self.downsample_bicubic(b, scale), self.downsample_bicubic(a, scale)) for a, b in batch]
+                        small = [(hr, sr) for sr, hr in small]
+                        sg, su = self.batch_psnr_ssim_sums(small, window=0), self.batch_psnr_ssim_sums(small, window=1)
+                        if degenerate(list(sg) + list(su)):
+                            mets = None
+                            break
+                        for m, g1, u1 in zip(mets, sg, su):
+                            m[f"psnr_{name}"] = float(self.finish(g1)[0])
+                            m[f"ssim_{name}"] = float(self.finish(u1)[1])
+            if mets is None:
+                for k in idx:
+                    results[k] = self.evaluate_full_reference(*prepared[k], scale_factor)
+                continue
+            for k, m, g1, u1 in zip(idx, mets, full, uni):
+                m["psnr"] = float(self.finish(g1)[0])
+                m["psnr_level"] = self._assess_psnr(m["psnr"])
+                m["ssim"] = float(self.finish(u1)[1])
+                m["ms_ssim"] = float(self.finish(g1)[1])
+                m["ssim_level"] = self._assess_ssim(m["ms_ssim"])
+                m["overall_score"] = self._calculate_overall_score(m)
+                results[k] = m
+        return results

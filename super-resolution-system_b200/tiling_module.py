@@ -189,19 +189,25 @@ class TilingModule:
         _native.check(rc, ctx)
         return out
 
-    def _apply_padding(self, image: np.ndarray, pad_top: int, pad_bottom: int, pad_left: int, pad_right: int) -> np.ndarray:
-        """bottom/right padding of one crop on the GPU; split_image never pads top/left (tiling_module.py:718-724)"""
-        if pad_top or pad_left:
-            raise NotImplementedError("only bottom/right padding is on the tiling path")
-        h, w = image.shape[:2]
-        if h + pad_bottom != w + pad_right:
-            raise NotImplementedError("the GPU pad kernel produces square block_size tiles")
-        saved = self.block_size
-        try:
-            self.block_size = h + pad_bottom
-            return self._extract(image, [(0, 0, w, h)])[0]
-        finally:
-            self.block_size = saved
+    def _apply_padding(self, image, pad_top: int, pad_bottom: int, pad_left: int, pad_right: int):
+        """cv2.copyMakeBorder(image, top, bottom, left, right, <padding_mode>) on the GPU (tiling_module.py:522-570; any
+        combination of pads, padding larger than the image included).  NumPy in -> NumPy out, CUDA tensor in -> CUDA tensor out."""
+        pads = [int(pad_top), int(pad_bottom), int(pad_left), int(pad_right)]
+        if min(pads) < 0:
+            raise ValueError(f"negative padding {pads}")  # cv2.copyMakeBorder asserts on it
+        v = ImageView(image, "image")
+        oh, ow = v.h + pads[0] + pads[1], v.w + pads[2] + pads[3]
+        shape = (oh, ow) if v.keep.ndim == 2 else (oh, ow, v.c)
+        lib, ctx = _native.load(), _native.context(v.device if v.on_device else self.device)
+        mode = _BORDER_CODE[self.padding_mode]
+        if v.on_device:
+            out = torch.empty(shape, dtype=torch.uint8, device=v.keep.device)
+            rc = lib.srf_copy_make_border(ctx, v.ptr, v.h, v.w, v.c, v.pitch, *pads, mode, out.data_ptr(), current_stream_ptr(v.device))
+        else:
+            out = np.empty(shape, np.uint8)
+            rc = lib.srf_copy_make_border_host(ctx, v.ptr, v.h, v.w, v.c, v.pitch, *pads, mode, out.ctypes.data)
+        _native.check(rc, ctx)
+        return out
 
     # ------------------------------------------------------------------ public API
     def split_array(self, image, image_hash: str = "", save_metadata: bool = True) -> List[Tile]:

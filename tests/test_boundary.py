@@ -94,8 +94,10 @@ def test_fusion_argument_errors(srs):
         bm.laplacian_fusion([])
     with pytest.raises(ValueError):  # bare arrays without output_shape: the reference raises ValueError too
         bm.laplacian_fusion([np.zeros((64, 64, 3), np.uint8)])
+    with pytest.raises(TypeError):  # float tiles that are not uint8 values (exact ones are cast, as blending_module.py:440-441 would)
+        bm.laplacian_fusion([srs.TileInfo(np.full((64, 64, 3), 0.5, np.float32), 0, 0, 0, 0)], output_shape=(64, 64))
     with pytest.raises(TypeError):
-        bm.laplacian_fusion([srs.TileInfo(np.zeros((64, 64, 3), np.float32), 0, 0, 0, 0)], output_shape=(64, 64))
+        bm.laplacian_fusion([srs.TileInfo(np.full((64, 64, 3), 300, np.int32), 0, 0, 0, 0)], output_shape=(64, 64))
     with pytest.raises(ValueError):
         bm.laplacian_fusion([srs.TileInfo(np.zeros((4, 64, 3), np.uint8), 0, 0, 0, 0)], output_shape=(64, 64))
 

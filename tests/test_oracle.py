@@ -278,3 +278,51 @@ def test_fallback_ssim_oracle_equals_reference_outputs(golden, oracle):
     hr = np.random.randint(0, 255, (512, 512, 3), dtype=np.uint8)
     sr = np.clip(hr.astype(np.int16) + np.random.normal(0, 5, hr.shape).astype(np.int16), 0, 255).astype(np.uint8)
     assert io.ssim_simple(hr, sr) == pytest.approx(float(golden["iqa_demo_ssim_fallback"]), rel=1e-13)
+
+
+# ------------------------------------------------------------------ the reference itself (oracle/_ref) and the pinned configs
+def _ref_arm_or_skip():
+    from oracle import make_ref, ref_arm
+    if not make_ref.make():
+        pytest.skip("oracle/_ref is absent and /root/reference is not here to build it from")
+    ref_arm.load()
+    return ref_arm
+
+
+def test_reference_modules_equal_the_oracle_restatement(oracle):
+    """oracle/_ref (verbatim reference modules) vs the restatement: same canvas bytes, same PSNR, same fallback SSIM"""
+    ref_arm = _ref_arm_or_skip()
+    rng = np.random.default_rng(91)
+    tiles = [synth(rng, 200, 240) for _ in range(4)]
+    pos = [(0, 0), (0, 180), (150, 0), (150, 180)]
+    out_hw = (330, 400)
+    for levels in (1, 4, 6):
+        got = ref_arm.laplacian_fuse(tiles, pos, out_hw, levels)
+        want = oracle.fusion_oracle.laplacian_fuse(tiles, pos, out_hw, levels, "cosine", "c")
+        assert np.array_equal(got, want), levels
+    cmp_img = synth(rng, *out_hw)
+    assert ref_arm.psnr(cmp_img, got) == pytest.approx(oracle.iqa_oracle.psnr(cmp_img, got), rel=1e-12)
+    stubs = ref_arm.load()[3]
+    if "skimage" in stubs:  # no scikit-image in this image: the reference returns its own fallback
+        assert ref_arm.ssim(cmp_img, got) == pytest.approx(oracle.iqa_oracle.ssim_simple(cmp_img, got), rel=1e-12)
+    else:
+        assert ref_arm.ssim(cmp_img, got) == pytest.approx(oracle.iqa_oracle.ssim(cmp_img, got), rel=1e-10)
+
+
+def test_pinned_config_constants_are_self_consistent():
+    import json
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "config_constants.json")
+    doc = json.load(open(path))
+    assert {"cfg2_100mp", "cfg3_150mp", "cfg4_200mp"} <= set(doc)
+    import workloads
+    for name, c in doc.items():
+        (tw, th), _, levels = workloads.CONFIGS[name]
+        assert c["canvas_hw"] == [2 * (th // 2), 2 * (tw // 2)] and c["levels"] == levels
+        assert c["n_elems"] == c["canvas_hw"][0] * c["canvas_hw"][1] * 3
+        assert c["psnr"] == pytest.approx(10 * np.log10(255.0 ** 2 * c["n_elems"] / c["sq_err"]), rel=1e-14)
+        assert c["ref_psnr"] == pytest.approx(c["psnr"], rel=1e-12)          # the reference's manual formula == the exact integer form
+        assert abs(c["ref_ssim"] - c["ssim"]) / c["ssim"] < 5e-4              # fallback vs scikit-image variant: border rows only
+        bs = np.array(c["block_sums"])
+        assert bs.shape == (-(-c["canvas_hw"][0] // c["block"]), -(-c["canvas_hw"][1] // c["block"]), 3)
+    assert doc["cfg4_200mp"]["sq_err"] == 96026474500

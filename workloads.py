@@ -67,6 +67,46 @@ def stub_sr(img: np.ndarray, size_hw) -> np.ndarray:
     return cv2.resize(img, (int(size_hw[1]), int(size_hw[0])), interpolation=cv2.INTER_CUBIC)
 
 
+@dataclass
+class IqaWorkload:
+    """BASELINE.json configs[4]: full-reference IQA sweep"""
+    name: str
+    big_a: np.ndarray                  # uint8 (H, W, 3): the 200 MP comparison canvas of cfg4
+    big_b: np.ndarray                  # the same + N(0, 5), re-clipped (seed 1)
+    pairs: List[Tuple[np.ndarray, np.ndarray]]  # 16 x (2048, 2048, 3) pairs, seeds 2 .. 17
+
+    @property
+    def megapixels(self) -> float:
+        return (self.big_a.shape[0] * self.big_a.shape[1] + sum(a.shape[0] * a.shape[1] for a, _ in self.pairs)) / 1e6
+
+
+def perturb(img: np.ndarray, seed: int, sigma: float = 5.0) -> np.ndarray:
+    """img + N(0, sigma) re-clipped to uint8, in row strips (a 200 MP image would need 5 GB of float64 at once)"""
+    rng = np.random.default_rng(seed)
+    out = np.empty_like(img)
+    for r in range(0, img.shape[0], 512):
+        blk = img[r:r + 512].astype(np.float32)
+        blk += rng.normal(0, sigma, blk.shape).astype(np.float32)
+        out[r:r + 512] = np.clip(blk, 0, 255).astype(np.uint8)
+    return out
+
+
+def build_iqa(name: str = "cfg5_iqa", big_rows: int = 0, n_pairs: int = 16, pair_size: int = 2048) -> IqaWorkload:
+    """big_rows > 0 keeps only the first rows of the 200 MP pair (bounded CPU samples / small tests)"""
+    (tw, th), _, _ = CONFIGS["cfg4_200mp"]
+    src = synthetic_source(seed=0)
+    half_h, half_w = th // 2, tw // 2
+    big_a = np.ascontiguousarray(stub_sr(src, (2 * half_h, 2 * half_w)))
+    if big_rows:
+        big_a = np.ascontiguousarray(big_a[:big_rows])
+    big_b = perturb(big_a, seed=1)
+    pairs = []
+    for k in range(n_pairs):
+        a = synthetic_source(pair_size, pair_size, seed=2 + k)
+        pairs.append((a, perturb(a, seed=100 + k)))
+    return IqaWorkload(name, big_a, big_b, pairs)
+
+
 def build(name: str = "cfg4_200mp", seed: int = 0, max_tiles: int = 0) -> Workload:
     import cv2
     (tw, th), ratio, levels = CONFIGS[name]
