@@ -572,6 +572,8 @@ extern "C" int srf_psnr_ssim_host(srf_ctx *ctx, const uint8_t *h_a, size_t pitch
         SRF_CHECK_CUDA(ctx, cudaMemcpy2DAsync(da, dp, h_a + (size_t)r0 * pitch_a, pitch_a, (size_t)w * channels, r1 - r0, cudaMemcpyHostToDevice, st));
         SRF_CHECK_CUDA(ctx, cudaMemcpy2DAsync(db, dp, h_b + (size_t)r0 * pitch_b, pitch_b, (size_t)w * channels, r1 - r0, cudaMemcpyHostToDevice, st));
     }
+    ctx->last_h2d = 2 * (size_t)w * channels * (size_t)(r1 > r0 ? r1 - r0 : 0);
+    ctx->last_d2h = sizeof(IqaPartial);
     return iqa_device(ctx, da - (size_t)r0 * dp, dp, db - (size_t)r0 * dp, dp, h, w, channels, scale_a, scale_b, data_range, row_begin, row_end, h_out, st, true, window);
 }
 
