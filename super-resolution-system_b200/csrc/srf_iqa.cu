@@ -135,7 +135,15 @@ __global__ void __launch_bounds__(IQ_THREADS, 4) k_psnr_ssim(IqaParams P)
         pitch_b = q.pitch_b;
     }
     __shared__ __align__(16) uint8_t s_raw[4][2][IQ2_RAW];
-    __shared__ __align__(16) float2 s_ab[2][IQ2_SROW];
+    __shared__ __align__(16) float2 s_ab[2][IQ2_SROW]; // (a, b) = gray - 128 of both images, per staged pixel
+#ifndef SRF_IQ_SP_SMEM
+#define SRF_IQ_SP_SMEM 0 // 1: (a^2 + b^2, a b) formed once per pixel and staged in a second smem row -- 12 % fewer instructions,
+                         // twice the LDS.128 of the horizontal pass: measured EQUAL (1.425 ms), the warps then wait on the
+                         // shared-memory pipe (61 % busy, short-scoreboard stalls x3) instead of on issue slots
+#endif
+#if SRF_IQ_SP_SMEM
+    __shared__ __align__(16) float2 s_sp[2][IQ2_SROW]; // (a^2 + b^2, a b) of the same pixel
+#endif
     __shared__ double s_red[IQ_THREADS / 32];
     __shared__ unsigned long long s_sq[IQ_THREADS / 32];
     __shared__ unsigned long long s_cnt[IQ_THREADS / 32];
@@ -208,6 +216,7 @@ __global__ void __launch_bounds__(IQ_THREADS, 4) k_psnr_ssim(IqaParams P)
     unsigned mlo0, mhi0, mlo1 = 0u, mhi1 = 0u;
     pair_masks(2 * t, mlo0, mhi0);
     if (t < IQ_R) pair_masks(IQ2_COLS + 2 * t, mlo1, mhi1);
+    asm volatile("" : "+r"(mlo0), "+r"(mhi0)); // per-thread constants: keep them, do not re-derive them from the thread index every row
     auto G = [&](int r) {
         const int buf = r & 1;
         float4 o0 = make_float4(0.f, 0.f, 0.f, 0.f), o1 = o0; // (a, b) of the pair's two pixels
@@ -237,8 +246,17 @@ __global__ void __launch_bounds__(IQ_THREADS, 4) k_psnr_ssim(IqaParams P)
             pair(2 * t, mlo0, mhi0, o0);
             if (t < IQ_R) pair(IQ2_COLS + 2 * t, mlo1, mhi1, o1);
         }
+        auto second = [](const float4 &o) { // (a0, b0, a1, b1) -> (a0^2 + b0^2, a0 b0, a1^2 + b1^2, a1 b1)
+            return make_float4(fmaf(o.x, o.x, o.y * o.y), o.x * o.y, fmaf(o.z, o.z, o.w * o.w), o.z * o.w);
+        };
         *reinterpret_cast<float4 *>(&s_ab[buf][2 * t]) = o0;
         if (t < IQ_R) *reinterpret_cast<float4 *>(&s_ab[buf][IQ2_COLS + 2 * t]) = o1;
+#if SRF_IQ_SP_SMEM
+        *reinterpret_cast<float4 *>(&s_sp[buf][2 * t]) = second(o0);
+        if (t < IQ_R) *reinterpret_cast<float4 *>(&s_sp[buf][IQ2_COLS + 2 * t]) = second(o1);
+#else
+        (void)second;
+#endif
     };
 
     // open output rows: A[q][0][j] = partial (a, b) sums, A[q][1][j] = partial (a^2+b^2, ab) sums of S-map column q
@@ -274,16 +292,25 @@ __global__ void __launch_bounds__(IQ_THREADS, 4) k_psnr_ssim(IqaParams P)
             // staged pixels 2t + (5 - R) .. + TAPS (TAPS + 1 of them, two per LDS.128): column 0 takes samples
             // 0 .. TAPS-1, column 1 samples 1 .. TAPS, both with taps 0 .. TAPS-1
             const float4 *pv = reinterpret_cast<const float4 *>(&s_ab[buf][2 * t + (IQ_R - R)]);
+#if SRF_IQ_SP_SMEM
+            const float4 *pw = reinterpret_cast<const float4 *>(&s_sp[buf][2 * t + (IQ_R - R)]);
+#endif
             static_assert(((IQ_R - R) & 1) == 0 && ((TAPS + 1) & 1) == 0, "pairs must stay 16-byte aligned");
 #pragma unroll
             for (int j = 0; j < (TAPS + 1) / 2; ++j) {
                 const float4 v = pv[j];
+#if SRF_IQ_SP_SMEM
+                const float4 u = pw[j];
+#endif
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     const int k = 2 * j + e;
-                    const float a = e ? v.z : v.x, b = e ? v.w : v.y;
-                    const float2 ab = make_float2(a, b);
-                    const float2 sp = make_float2(fmaf(a, a, b * b), a * b);
+                    const float2 ab = e ? make_float2(v.z, v.w) : make_float2(v.x, v.y);
+#if SRF_IQ_SP_SMEM
+                    const float2 sp = e ? make_float2(u.z, u.w) : make_float2(u.x, u.y);
+#else
+                    const float2 sp = make_float2(fmaf(ab.x, ab.x, ab.y * ab.y), ab.x * ab.y);
+#endif
                     if (k == 0) {
                         hn[0][0] = f2mul(ab, iq_tap<R>(0));
                         hn[0][1] = f2mul(sp, iq_tap<R>(0));
@@ -315,13 +342,22 @@ __global__ void __launch_bounds__(IQ_THREADS, 4) k_psnr_ssim(IqaParams P)
                 A[q][s][TAPS - 2] = f2mul(hn[q][s], iq_tap<R>(0));
             }
             if (emit) {
-                const float ua = f[0].x, ub = f[0].y;
-                const float ux = ua + 128.f, uy = ub + 128.f;
-                const float vsum = P.cov_norm * (f[1].x - fmaf(ua, ua, ub * ub));
-                const float vxy = P.cov_norm * (f[1].y - ua * ub);
-                const float A1 = fmaf(2.f * ux, uy, C1), A2 = fmaf(2.f, vxy, C2);
-                const float B1 = fmaf(ux, ux, fmaf(uy, uy, C1)), B2 = vsum + C2;
-                const float S = __fdividef(A1 * A2, B1 * B2);
+                // the filtered signals are means of (x - 128): variances and the covariance do not see the offset, the
+                // luminance term needs the true means (ux, uy).  Packed where the (a, b) pairing allows it.
+                const float2 u = f[0];                                          // (ua, ub)
+                const float2 m = __fadd2_rn(u, make_float2(128.f, 128.f));      // (ux, uy)
+                const float2 uu = __fmul2_rn(u, u), mm = __fmul2_rn(m, m);
+                constexpr float COV = (R == 3) ? (float)(49.0 / 48.0) : 1.f;   // sample covariance for the 7x7 uniform window
+                float vsum = f[1].x - (uu.x + uu.y), vxy = fmaf(-u.x, u.y, f[1].y);
+                if (R == 3) {
+                    vsum *= COV;
+                    vxy *= COV;
+                }
+                const float A1 = fmaf(m.x + m.x, m.y, C1), A2 = fmaf(2.f, vxy, C2);
+                const float B1 = (mm.x + mm.y) + C1, B2 = vsum + C2;
+                float inv;
+                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(B1 * B2)); // B1 B2 >= C1 C2 = 380: no range handling needed
+                const float S = (A1 * A2) * inv;
                 if (row_ok && (q ? ci1 : ci0)) {
                     ssum += S;
                     scount++;
