@@ -155,6 +155,11 @@ extern "C" int srf_create(int device, srf_ctx **out)
         SRF_CHECK_CUDA(c, cudaEventCreate(&c->ev0));
         SRF_CHECK_CUDA(c, cudaEventCreate(&c->ev1));
         SRF_CHECK_CUDA(c, cudaEventCreateWithFlags(&c->ev_dev, cudaEventDisableTiming));
+        SRF_CHECK_CUDA(c, cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+        for (int i = 0; i < srf_ctx::kForkStreams; ++i) {
+            SRF_CHECK_CUDA(c, cudaStreamCreateWithFlags(&c->fork_stream[i], cudaStreamNonBlocking));
+            SRF_CHECK_CUDA(c, cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming));
+        }
         for (cudaEvent_t &ev : c->ev_aux) SRF_CHECK_CUDA(c, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         return SRF_OK;
     }();
@@ -184,6 +189,11 @@ extern "C" void srf_destroy(srf_ctx *c)
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->ev_dev) cudaEventDestroy(c->ev_dev);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    for (int i = 0; i < srf_ctx::kForkStreams; ++i) {
+        if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]);
+        if (c->fork_stream[i]) cudaStreamDestroy(c->fork_stream[i]);
+    }
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->down_stream) cudaStreamDestroy(c->down_stream);

@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <algorithm>
 #include <string>
 #include <vector>
@@ -73,6 +74,10 @@ struct srf_ctx {
     // workspaces: every device-path enqueue leaves an event here and every host entry point makes its streams wait on it
     cudaEvent_t ev_dev = nullptr;
     bool ev_dev_set = false;
+    // the gather's class launches write disjoint canvas blocks: they fork onto these streams and join back (srf_fuse.cu)
+    static const int kForkStreams = 5;
+    cudaStream_t fork_stream[kForkStreams] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[kForkStreams] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     // CUDA-graph replay of a repeated srf_laplacian_fuse call (same tiles, canvas, band, stream): the second identical
     // call is captured, later ones are one cudaGraphLaunch.  Any workspace reallocation bumps ws_epoch and drops it.
     uint64_t fuse_sig = 0;        // signature of the last srf_laplacian_fuse call
@@ -95,7 +100,8 @@ struct srf_launch_scope {
     srf_ctx *ctx;
     cudaStream_t st;
     cudaEvent_t e1 = nullptr;
-    srf_launch_scope(srf_ctx *c, const char *name, double bytes, cudaStream_t s) : ctx(c), st(s)
+    const char *name;
+    srf_launch_scope(srf_ctx *c, const char *name_, double bytes, cudaStream_t s) : ctx(c), st(s), name(name_)
     {
         ctx->launches++;
         if (!ctx->profile) return;
@@ -118,6 +124,11 @@ struct srf_launch_scope {
     ~srf_launch_scope()
     {
         if (e1) cudaEventRecord(e1, st);
+        static const bool debug_sync = getenv("SRF_DEBUG_SYNC") != nullptr; // bring-up aid: name the kernel that faults
+        if (debug_sync) {
+            const cudaError_t e = cudaStreamSynchronize(st);
+            if (e != cudaSuccess) fprintf(stderr, "[srfuse] kernel '%s' (launch %lld): %s\n", name, (long long)ctx->launches, cudaGetErrorString(e));
+        }
     }
 };
 

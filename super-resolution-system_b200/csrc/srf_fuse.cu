@@ -49,6 +49,12 @@ struct GroupDev {
     const float *lut;        // device copy of the weight profile
     LevelGeom lv[SRF_MAX_LEVELS];
     float *W[SRF_MAX_LEVELS]; // W[l], l >= 1 (single plane); W[0] unused
+    // G_1 = pyrDown(uint8 tile) is an exact integer / 256 (<= 65280): when the row-outer gather runs (its kernels read it as
+    // such) it is stored as that integer in uint16 planes -- half the bytes of the level every big kernel touches.  TileDev::G[1]
+    // then points at uint16 data with its own pitch / plane size (in ELEMENTS); every other level stays float32.
+    int g1_u16;
+    int g1_pitch;
+    size_t g1_plane;
 };
 
 struct TileDev {
@@ -119,7 +125,7 @@ __device__ __forceinline__ uint4 load_u8_chunk(const uint8_t *grow, int o, int v
     return v;
 }
 
-template <int C>
+template <int C, bool U16>
 __global__ void __launch_bounds__(128 * C) k_down_u8(const TileDev *__restrict__ tiles, const int *__restrict__ tile_ids, GroupDev g)
 {
     pdl_enter(); // programmatic dependent launch: nothing above this line may touch global data
@@ -198,6 +204,7 @@ __global__ void __launch_bounds__(128 * C) k_down_u8(const TileDev *__restrict__
         ti[k] = max(min(q, D8_PSTRIDE - 1), 0);
     }
     float *dst = t.G[1] + (size_t)c * L1.plane;
+    unsigned short *dst16 = reinterpret_cast<unsigned short *>(t.G[1]) + (size_t)c * g.g1_plane;
 
     int h0 = 0, h1 = 0, h2 = 0, h3 = 0, h4 = 0;
     stage_load(0);
@@ -223,7 +230,10 @@ __global__ void __launch_bounds__(128 * C) k_down_u8(const TileDev *__restrict__
                 const int oy = oy0 + ((r - 4) >> 1);
                 if (oy < oy1 && ox < ow) {
                     const int v = h0 + h4 + 4 * (h1 + h3) + 6 * h2;
-                    dst[(size_t)oy * L1.pitch + ox] = __fmul_rn((float)v, 1.f / 256.f);
+                    if (U16)
+                        dst16[(size_t)oy * g.g1_pitch + ox] = (unsigned short)v; // G_1 * 256, exact
+                    else
+                        dst[(size_t)oy * L1.pitch + ox] = __fmul_rn((float)v, 1.f / 256.f);
                 }
             }
         }
@@ -441,7 +451,15 @@ __global__ void __launch_bounds__(kThreads) k_up_level_top(const TileDev *__rest
             ug[0] = up_even(mg.x, pg.x, ng.x); ug[1] = up_even(mg.y, pg.y, ng.y); ug[2] = up_even(mg.z, pg.z, ng.z); ug[3] = up_even(mg.w, pg.w, ng.w);
         }
         const size_t off = (size_t)ty * L0.pitch + tx;
-        const float4 g0 = load_f32_chunk(G0 + (size_t)ty * L0.pitch, tx, L0.w);
+        float4 g0;
+        if (l == 1 && g.g1_u16) { // the uint16 level: four values (x 256) in one aligned 8-byte word (tx is a multiple of 4)
+            const unsigned short *row = reinterpret_cast<const unsigned short *>(t.G[1]) + (size_t)c * g.g1_plane + (size_t)ty * g.g1_pitch;
+            const uint2 v = *reinterpret_cast<const uint2 *>(row + tx);
+            g0 = make_float4(__fmul_rn((float)(v.x & 0xFFFFu), 1.f / 256.f), __fmul_rn((float)(v.x >> 16), 1.f / 256.f),
+                             __fmul_rn((float)(v.y & 0xFFFFu), 1.f / 256.f), __fmul_rn((float)(v.y >> 16), 1.f / 256.f));
+        } else {
+            g0 = load_f32_chunk(G0 + (size_t)ty * L0.pitch, tx, L0.w);
+        }
         const float4 w0 = load_f32_chunk(W0 + (size_t)ty * L0.pitch, tx, L0.w);
         const float gg[4] = {g0.x, g0.y, g0.z, g0.w}, ww[4] = {w0.x, w0.y, w0.z, w0.w};
         float o[4];
@@ -610,6 +628,134 @@ __global__ void __launch_bounds__(DF_BW) k_down_f32s(const TileDev *__restrict__
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// k_down_u16: G_1 (uint16 planes, value * 256) -> G_2 (float32).  Everything up to G_2 is EXACT in float32: G_1 * 256 <= 65280,
+// a horizontal 5-tap sum <= 16 * 65280 < 2^20 and the full 5 x 5 sum <= 256 * 65280 < 2^24 are integers, so cv2.pyrDown's
+// float32 result is that integer * 2^-16 whatever its op order -- the level is computed in integer arithmetic (two DP2A per
+// horizontal tap row) from half the bytes.  Same streaming structure as k_down_f32s: thread = output column, rows staged 8
+// at a time by TMA bulk copies (cp.async-free edge strips are zero-filled by hand), 5-deep register ring, one output row
+// per two input rows.  grid = (ceil(ow/128), ceil(rows/rows_per_cta), planes)
+// ------------------------------------------------------------------------------------------------------------
+constexpr int D16_COLS = 2 * DF_BW + 16; // staged uint16 per row: columns [2*ox0 - 8, 2*ox0 + 264): 544 bytes, 16-byte aligned start
+
+__global__ void __launch_bounds__(DF_BW) k_down_u16(const TileDev *__restrict__ tiles, const int *__restrict__ tile_ids, GroupDev g, int rows_per_cta)
+{
+    pdl_enter(); // programmatic dependent launch: nothing above this line may touch global data
+    __shared__ __align__(128) unsigned short s_in[2][DF_BATCH][D16_COLS];
+    __shared__ __align__(8) uint64_t s_bar[2];
+
+    const LevelGeom Ld = g.lv[2];
+    const int h = g.lv[1].h, w = g.lv[1].w, ow = Ld.w;
+    const int z = blockIdx.z;
+    const TileDev &t = tiles[tile_ids[z / g.cn]];
+    const int c = z % g.cn;
+    const unsigned short *src = reinterpret_cast<const unsigned short *>(t.G[1]) + (size_t)c * g.g1_plane;
+    float *dst = t.G[2] + (size_t)c * Ld.plane;
+    const int r0 = t.g0[2], r1 = t.g1[2], xlim = t.gx1[2];
+    const int oy0 = r0 + blockIdx.y * rows_per_cta;
+    const int ox0 = blockIdx.x * DF_BW;
+    if (oy0 >= r1 || ox0 >= ow || ox0 >= xlim) return;
+    const int oy1 = min(oy0 + rows_per_cta, r1);
+    const int in_y0 = 2 * oy0 - 2;
+    const int in_x0 = 2 * ox0 - 8; // multiple of 8 elements = 16 bytes
+    const int n_in_rows = 2 * (oy1 - oy0) + 3;
+    const int n_batches = (n_in_rows + DF_BATCH - 1) / DF_BATCH;
+    const int pitch = g.g1_pitch;
+
+    const bool use_tma = (in_x0 >= 0) && (in_x0 + D16_COLS <= pitch);
+    if (use_tma) {
+        if (threadIdx.x == 0) {
+            mbar_init(&s_bar[0], 1);
+            mbar_init(&s_bar[1], 1);
+            mbar_fence_init();
+        }
+        __syncthreads();
+    }
+    auto stage_tma = [&](int b) {
+        if (threadIdx.x == 0) {
+            uint64_t *bar = &s_bar[b & 1];
+            mbar_expect_tx(bar, DF_BATCH * D16_COLS * (unsigned)sizeof(unsigned short));
+#pragma unroll
+            for (int j = 0; j < DF_BATCH; ++j) {
+                const int gy = srf_reflect101(in_y0 + b * DF_BATCH + j, h);
+                tma_bulk_g2s(&s_in[b & 1][j][0], src + (size_t)gy * pitch + in_x0, D16_COLS * (unsigned)sizeof(unsigned short), bar);
+            }
+        }
+    };
+    // edge strips: 34 lanes own one 16-byte chunk (8 elements) each; chunks outside the padded row are zero
+    const int sch = threadIdx.x;
+    const int sc0 = in_x0 + sch * 8;
+    const bool s_on = sch < D16_COLS / 8;
+    const bool s_ok = s_on && sc0 >= 0 && sc0 + 8 <= pitch;
+    auto stage = [&](int b) {
+        unsigned short(*buf)[D16_COLS] = s_in[b & 1];
+        if (s_on) {
+#pragma unroll
+            for (int j = 0; j < DF_BATCH; ++j) {
+                const int gy = srf_reflect101(in_y0 + b * DF_BATCH + j, h); // uniform
+                unsigned short *d = &buf[j][sch * 8];
+                if (s_ok)
+                    cp_async_16(d, src + (size_t)gy * pitch + sc0);
+                else
+                    *reinterpret_cast<uint4 *>(d) = make_uint4(0, 0, 0, 0);
+            }
+        }
+        cp_async_commit();
+    };
+
+    const int x = threadIdx.x;
+    const int ox = ox0 + x;
+    const bool x_edge = (ox0 == 0) || (2 * (ox0 + DF_BW - 1) + 2 >= w); // some tap of this strip is reflected
+    int ti[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        const int q = srf_reflect101(2 * min(ox, ow - 1) + k - 2, w) - in_x0;
+        ti[k] = max(min(q, D16_COLS - 1), 0);
+    }
+
+    int h0 = 0, h1 = 0, h2 = 0, h3 = 0, h4 = 0;
+    if (use_tma) {
+        stage_tma(0);
+    } else {
+        stage(0);
+        cp_async_wait<0>();
+        __syncthreads();
+    }
+    for (int b = 0; b < n_batches; ++b) {
+        if (b + 1 < n_batches) {
+            if (use_tma)
+                stage_tma(b + 1);
+            else
+                stage(b + 1);
+        }
+        if (use_tma) mbar_wait(&s_bar[b & 1], (b >> 1) & 1); // batch b has landed
+        const unsigned short(*buf)[D16_COLS] = s_in[b & 1];
+#pragma unroll
+        for (int j = 0; j < DF_BATCH; ++j) {
+            const unsigned short *row = buf[j];
+            int hv;
+            if (!x_edge) { // taps at staged columns 2x+6 .. 2x+10: two aligned 32-bit words + one halfword
+                const unsigned w0 = *reinterpret_cast<const unsigned *>(row + 2 * x + 6);
+                const unsigned w1 = *reinterpret_cast<const unsigned *>(row + 2 * x + 8);
+                hv = (int)__dp2a_lo(w0, 0x0401u, __dp2a_lo(w1, 0x0406u, (unsigned)row[2 * x + 10]));
+            } else {
+                hv = (int)row[ti[0]] + (int)row[ti[4]] + 4 * ((int)row[ti[1]] + (int)row[ti[3]]) + 6 * (int)row[ti[2]];
+            }
+            h0 = h1; h1 = h2; h2 = h3; h3 = h4; h4 = hv;
+            const int r = b * DF_BATCH + j; // stream position; rows r-4..r are in the ring
+            if ((j & 1) == 0 && r >= 4) {
+                const int oy = oy0 + ((r - 4) >> 1);
+                if (oy < oy1 && ox < ow) {
+                    const int v = h0 + h4 + 4 * (h1 + h3) + 6 * h2; // <= 256 * 65280 < 2^24: exact in float32
+                    dst[(size_t)oy * Ld.pitch + ox] = __fmul_rn((float)v, 1.f / 65536.f);
+                }
+            }
+        }
+        if (!use_tma) cp_async_wait<0>();
+        __syncthreads(); // everyone is done with buffer b & 1 before batch b + 2 is copied over it
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // k_up_levels: C_l = pyrUp(C_{l+1}) + (G_l - pyrUp(G_{l+1})) * W_l with C_{l+1} stored (every level but the top one).  One CTA = 256 x 32 outputs of
 // one plane, 128 threads: thread p owns output columns 2p, 2p+1 and slides down the rows with a 3-row register ring
 // of horizontally up-sampled (C_{l+1}, G_{l+1}) pairs, exactly like k_final; the <= 19 x 136 source windows arrive by
@@ -631,8 +777,8 @@ __device__ __forceinline__ HPair2 up_pair_even_origin(float s0, float s1, float 
     return r;
 }
 
-template <int H> // output rows per CTA: 32 amortises the 2-row source halo; 8 keeps a small level (or a thin band) from
-                  // being a few long-running CTAs on an idle GPU
+template <int H, bool G0U16 = false> // H: output rows per CTA (32 amortises the 2-row source halo; 8 keeps a small level or a thin band
+                                      // from being a few long-running CTAs on an idle GPU); G0U16: G_l is the uint16 level 1
 __global__ void __launch_bounds__(UL_PAIRS) k_up_levels(const TileDev *__restrict__ tiles, const int *__restrict__ tile_ids, GroupDev g, int l)
 {
     pdl_enter(); // programmatic dependent launch: nothing above this line may touch global data
@@ -678,6 +824,7 @@ __global__ void __launch_bounds__(UL_PAIRS) k_up_levels(const TileDev *__restric
     const bool hfast = (i0 >= 0) && (i0 + UL_PAIRS + 1 <= w1 - 1) && (w1 > 1);
     const int scol = i0 + p - sx0;
     const float *G0 = t.G[l] + (size_t)c * L0.plane;
+    const unsigned short *G0h = reinterpret_cast<const unsigned short *>(t.G[l]) + (size_t)c * g.g1_plane; // G0U16 only
     const float *W0 = g.W[l];
     float *C0 = t.C[l] + (size_t)c * L0.plane;
 
@@ -704,15 +851,24 @@ __global__ void __launch_bounds__(UL_PAIRS) k_up_levels(const TileDev *__restric
 
     // software prefetch of the per-output operands (G_l, W_l): one step (two rows) ahead, in registers
     float2 gnext[2], wnext[2];
+    unsigned graw[2] = {0u, 0u}; // G0U16: the raw pair stays in flight; it is converted where it is used, not where it is loaded
     auto fetch_gw = [&](int k) {
 #pragma unroll
         for (int a = 0; a < 2; ++a) {
             const int ty = ty0 + 2 * k + a;
             gnext[a] = make_float2(0.f, 0.f);
             wnext[a] = make_float2(0.f, 0.f);
+            if (G0U16) graw[a] = 0u;
             if (ty < ty1 && ina) {
                 const size_t off = (size_t)ty * L0.pitch + txa;
-                if (inb) {
+                if (G0U16) { // two uint16 (value * 256) in one aligned 32-bit word: txa is even, the plane pitch a multiple of 8
+                    graw[a] = __ldg(reinterpret_cast<const unsigned *>(G0h + (size_t)ty * g.g1_pitch + txa));
+                    if (inb) {
+                        wnext[a] = __ldg(reinterpret_cast<const float2 *>(W0 + off));
+                    } else {
+                        wnext[a].x = __ldg(W0 + off);
+                    }
+                } else if (inb) {
                     gnext[a] = __ldg(reinterpret_cast<const float2 *>(G0 + off));
                     wnext[a] = __ldg(reinterpret_cast<const float2 *>(W0 + off));
                 } else {
@@ -747,6 +903,11 @@ __global__ void __launch_bounds__(UL_PAIRS) k_up_levels(const TileDev *__restric
         }
         // this step's G_l / W_l were fetched one step ago; fetch the next step's now
         float2 gcur[2] = {gnext[0], gnext[1]}, wcur[2] = {wnext[0], wnext[1]};
+        if (G0U16) {
+#pragma unroll
+            for (int a = 0; a < 2; ++a)
+                gcur[a] = make_float2(__fmul_rn((float)(graw[a] & 0xFFFFu), 1.f / 256.f), __fmul_rn((float)(graw[a] >> 16), 1.f / 256.f));
+        }
         if (k + 1 < STEPS) fetch_gw(k + 1);
 #pragma unroll
         for (int a = 0; a < 2; ++a) {
@@ -878,6 +1039,7 @@ __device__ __forceinline__ void mbar_wait_or_trap(uint64_t *bar, unsigned parity
             : "memory");
         if (ok) return;
     }
+    if ((threadIdx.x & 31) == 0) printf("[srfuse] mbarrier wait timed out: block (%d,%d,%d) warp %d parity %u\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x >> 5, parity);
     __trap();
 }
 
@@ -1361,9 +1523,20 @@ struct GatherParams {
     size_t canvas_pitch;
     int row_begin, row_end;
 };
+// A TMA box must start on a 16-byte boundary of the innermost dimension (any other start faults as an illegal instruction):
+// the float32 C_1 window starts at a multiple of 4 columns, the uint16 G_1 window at a multiple of 8 and is up to 4 columns
+// wider for it (66 columns needed + up to 7 of slack, rounded to whole 16 bytes)
+constexpr int FB_G_COLS = 80;
+template <int C>
+struct alignas(128) GatherStage { // everything the row-outer gather reads of ONE covering tile: three dense TMA boxes
+    alignas(128) float sc[C][FB_SRC_ROWS][FB_SRC_COLS];          // C_1 window
+    alignas(128) unsigned short sg[C][FB_SRC_ROWS][FB_G_COLS];   // G_1 window, uint16 (value * 256); starts at a multiple of 8 columns
+    alignas(128) uint8_t u8[FB_H][FB_U8_STRIDE];                 // uint8 tile block
+    float nwy[FB_H];                                             // -W_0 profile of the block's 16 rows
+};
 template <int C, int TMAX>
 struct alignas(128) GatherSmem {
-    FinalStage<C> st[TMAX];
+    GatherStage<C> st[TMAX];
     alignas(16) uint8_t out[FB_H][FB_U8_STRIDE]; // finished rows, bytes congruent (mod 16) with the canvas rows
 };
 #ifndef SRF_GATHER_UNROLL
@@ -1416,18 +1589,26 @@ extern __shared__ __align__(128) uint8_t g_gather_smem[];
 __device__ __forceinline__ float gs_f32(int off) { return *reinterpret_cast<const float *>(g_gather_smem + off); }
 __device__ __forceinline__ float2 gs_f32x2(int off) { return *reinterpret_cast<const float2 *>(g_gather_smem + off); }
 __device__ __forceinline__ float gs_u8f(int off) { return __int2float_rn((int)g_gather_smem[off]); }
+__device__ __forceinline__ int gs_u16(int off) { return (int)*reinterpret_cast<const unsigned short *>(g_gather_smem + off); }
+// horizontal pyrUp of the uint16 G_1 window for columns (2i, 2i+1), i = window centre, UN-NORMALISED and still x 256: exact
+// integers (<= 8 * 65280), so the float op order of the reference does not matter here; the 2^-8 is folded into the pixel
+// stage (x 2^-8 commutes with every rounding)
+__device__ __forceinline__ float2 g16_pair_even_origin(int g0, int g1, int g2)
+{
+    return make_float2(__int2float_rn(6 * g1 + g0 + g2), __int2float_rn(4 * (g1 + g2)));
+}
 
 template <int C, int TMAX>
 __global__ void __launch_bounds__(FB_PAIRS *C, (TMAX <= 2) ? SRF_GATHER_CTAS : 2)
     k_gather(const __grid_constant__ GatherParams P, const __grid_constant__ GatherTiles GT, const __grid_constant__ FinalTmaps TM)
 {
     pdl_enter(); // programmatic dependent launch: nothing above this line may touch global data
-    using Stage = FinalStage<C>;
+    using Stage = GatherStage<C>;
     constexpr int NT = FB_PAIRS * C;
     constexpr int O_SC = (int)offsetof(Stage, sc), O_SG = (int)offsetof(Stage, sg), O_U8 = (int)offsetof(Stage, u8), O_NWY = (int)offsetof(Stage, nwy);
     constexpr int STAGE = (int)sizeof(Stage), O_OUT = TMAX * STAGE;
-    constexpr int ROWB = FB_SRC_COLS * 4; // bytes per staged source row
-    constexpr int CHB = FB_SRC_ROWS * ROWB; // bytes per staged channel plane
+    constexpr int ROWB = FB_SRC_COLS * 4, CHB = FB_SRC_ROWS * ROWB;  // bytes per staged C_1 row / channel plane
+    constexpr int ROWG = FB_G_COLS * 2, CHG = FB_SRC_ROWS * ROWG;    // the same for the uint16 G_1 window
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ FinalGeo s_geo[TMAX];
     const int base = (int)((128u - (smem_u32(g_gather_smem) & 127u)) & 127u); // the TMA boxes want 128-byte aligned destinations
@@ -1470,7 +1651,7 @@ __global__ void __launch_bounds__(FB_PAIRS *C, (TMAX <= 2) ? SRF_GATHER_CTAS : 2
         const int sb = base + s * STAGE;
         if (threadIdx.x == 0) {
             tma_tensor_3d_g2s(g_gather_smem + sb + O_SC, &TM.m[ti][0], q.sx0, q.srow0, 0, &s_bar);
-            tma_tensor_3d_g2s(g_gather_smem + sb + O_SG, &TM.m[ti][1], q.sx0, q.srow0, 0, &s_bar);
+            tma_tensor_3d_g2s(g_gather_smem + sb + O_SG, &TM.m[ti][1], (q.i0 >> 3) * 8, q.srow0, 0, &s_bar);
             tma_tensor_2d_g2s(g_gather_smem + sb + O_U8, &TM.m[ti][2], q.u8_a0 >> 2, cy0 - gt.y, &s_bar);
             s_geo[s] = q;
         }
@@ -1491,14 +1672,15 @@ __global__ void __launch_bounds__(FB_PAIRS *C, (TMAX <= 2) ? SRF_GATHER_CTAS : 2
     // ---- per-slot state: a 3-row ring of horizontally up-sampled (C_1, G_1) pairs, the column weights, smem cursors ----
     float2 rc0[TMAX], rg0[TMAX], rc1[TMAX], rg1[TMAX]; // .x / .y = the thread's two columns
     float wxa[TMAX], wxb[TMAX];                        // column weights; NEGATED for full slots (see k_final's FULL path)
-    int o_src[TMAX], o_u8[TMAX];                       // byte offsets: next source row (full slots), the thread's first pixel byte
-    unsigned flags[TMAX];                              // generic slots: bit 0 ina, 1 inb, 2 spa, 3 spb
+    int o_src[TMAX], o_g[TMAX], o_u8[TMAX];            // byte offsets: next C_1 / G_1 source row (full slots), the thread's first pixel byte
+    unsigned flags[TMAX] = {};                         // generic slots: bit 0 ina, 1 inb, 2 spa, 3 spb
 
-    auto hrow_fast = [&](int o, float2 &oc, float2 &og) { // interior form: columns (2i, 2i+1), i = window centre
-        const float c0 = gs_f32(o + O_SC), c1 = gs_f32(o + O_SC + 4), c2 = gs_f32(o + O_SC + 8);
-        const float g0 = gs_f32(o + O_SG), g1 = gs_f32(o + O_SG + 4), g2 = gs_f32(o + O_SG + 8);
+    // `o` / `oh` address the first of the three C_1 / G_1 samples (byte offsets inside the stage's sc / sg arrays).  G values
+    // are x 256 (see g16_pair_even_origin) all the way to the pixel stage.
+    auto hrow_fast = [&](int sb, int o, int oh, float2 &oc, float2 &og) { // interior form: columns (2i, 2i+1), i = window centre
+        const float c0 = gs_f32(sb + O_SC + o), c1 = gs_f32(sb + O_SC + o + 4), c2 = gs_f32(sb + O_SC + o + 8);
         oc = make_float2(up_even(c0, c1, c2), up_odd(c1, c2));
-        og = make_float2(up_even(g0, g1, g2), up_odd(g1, g2));
+        og = g16_pair_even_origin(gs_u16(sb + O_SG + oh), gs_u16(sb + O_SG + oh + 2), gs_u16(sb + O_SG + oh + 4));
     };
     auto hrow_generic = [&](int s, int r_logical, float2 &oc, float2 &og) {
         const GatherTile &gt = GT.t[tiles_of[s]];
@@ -1506,16 +1688,22 @@ __global__ void __launch_bounds__(FB_PAIRS *C, (TMAX <= 2) ? SRF_GATHER_CTAS : 2
         const int h1 = gt.h1, w1 = gt.w1;
         int r = (r_logical == -1) ? min(1, h1 - 1) : max(min(r_logical, h1 - 1), 0);
         r = max(min(r - q.srow0, q.n_srows - 1), 0);
-        const int row = base + s * STAGE + c * CHB + r * ROWB; // + O_SC / O_SG
+        const int sb = base + s * STAGE;
+        const int row = c * CHB + r * ROWB; // byte offset of the staged C_1 row inside sc
         const int o = row + 4 * (q.i0 + p - q.sx0);
-        const HPair hc = h_pair_fast(gs_f32(o + O_SC), gs_f32(o + O_SC + 4), gs_f32(o + O_SC + 8), q.xpar);
-        const HPair hg = h_pair_fast(gs_f32(o + O_SG), gs_f32(o + O_SG + 4), gs_f32(o + O_SG + 8), q.xpar);
+        const int sxg = (q.i0 >> 3) * 8;    // first staged column of the G_1 window
+        const int rowg = sb + O_SG + c * CHG + r * ROWG;
+        // integer-valued floats below 2^24: every pyrUp formula is exact on them, so the float forms serve the uint16 level too
+        auto g16 = [&](int col) { return (float)gs_u16(rowg + 2 * (col - sxg)); };
+        const int i0p = q.i0 + p;
+        const HPair hc = h_pair_fast(gs_f32(sb + O_SC + o), gs_f32(sb + O_SC + o + 4), gs_f32(sb + O_SC + o + 8), q.xpar);
+        const HPair hg = h_pair_fast(g16(i0p), g16(i0p + 1), g16(i0p + 2), q.xpar);
         oc = make_float2(hc.a, hc.b);
         og = make_float2(hg.a, hg.b);
         if (flags[s] & 12u) { // edge formulas (tile column 0, the last source column, a 1-wide source)
             const int txa = cx0 - gt.x + 2 * p, txb = txa + 1;
-            auto atc = [&](int ii) { return gs_f32(row + O_SC + 4 * (ii - q.sx0)); };
-            auto atg = [&](int ii) { return gs_f32(row + O_SG + 4 * (ii - q.sx0)); };
+            auto atc = [&](int ii) { return gs_f32(sb + O_SC + row + 4 * (ii - q.sx0)); };
+            auto atg = [&](int ii) { return g16(ii); };
             if (flags[s] & 4u) {
                 oc.x = up_h_sample(txa, w1, atc);
                 og.x = up_h_sample(txa, w1, atg);
@@ -1539,17 +1727,19 @@ __global__ void __launch_bounds__(FB_PAIRS *C, (TMAX <= 2) ? SRF_GATHER_CTAS : 2
             wxa[s] = -wa;
             wxb[s] = -wb;
             flags[s] = 0;
-            o_src[s] = base + s * STAGE + c * CHB + 4 * (q.i0 + p - q.sx0); // staged row 0 is logical row ws0
-            hrow_fast(o_src[s], rc0[s], rg0[s]);
-            hrow_fast(o_src[s] + ROWB, rc1[s], rg1[s]);
+            o_src[s] = c * CHB + 4 * (q.i0 + p - q.sx0); // relative to the stage's sc array; staged row 0 is logical row ws0
+            o_g[s] = c * CHG + 2 * (q.i0 + p - (q.i0 >> 3) * 8);
+            hrow_fast(base + s * STAGE, o_src[s], o_g[s], rc0[s], rg0[s]);
+            hrow_fast(base + s * STAGE, o_src[s] + ROWB, o_g[s] + ROWG, rc1[s], rg1[s]);
             o_src[s] += 2 * ROWB;
+            o_g[s] += 2 * ROWG;
         } else {
             wxa[s] = wa;
             wxb[s] = wb;
             const bool ina = (cx0 + 2 * p >= q.ix0) && (cx0 + 2 * p < q.ix1), inb = (cx0 + 2 * p + 1 >= q.ix0) && (cx0 + 2 * p + 1 < q.ix1);
             const bool spa = ina && ((txa <= 0) || ((txa >> 1) >= gt.w1 - 1)), spb = inb && ((txb <= 0) || ((txb >> 1) >= gt.w1 - 1));
             flags[s] = (ina ? 1u : 0u) | (inb ? 2u : 0u) | (spa ? 4u : 0u) | (spb ? 8u : 0u);
-            o_src[s] = 0;
+            o_src[s] = o_g[s] = 0;
             hrow_generic(s, q.ws0, rc0[s], rg0[s]);
             hrow_generic(s, q.ws0 + 1, rc1[s], rg1[s]);
         }
@@ -1573,9 +1763,10 @@ __global__ void __launch_bounds__(FB_PAIRS *C, (TMAX <= 2) ? SRF_GATHER_CTAS : 2
                 // multiply into a following packed add even for .rn, so every INEXACT product that feeds an add (6 p, d * w)
                 // is a scalar FMUL.  nd = fma(g, -64, up64G) = -(64 g - up64G), nw = -w0: their product is the reference's.
                 float2 rc2, rg2;
-                hrow_fast(o_src[s], rc2, rg2);
+                hrow_fast(sb, o_src[s], o_g[s], rc2, rg2);
                 o_src[s] += ROWB;
-                float2 uc[2], ug[2]; // x64, tile rows (2j, 2j+1): even uses the whole ring, odd its last two rows
+                o_g[s] += ROWG;
+                float2 uc[2], ug[2]; // x64 (ug also x256), tile rows (2j, 2j+1): even uses the whole ring, odd its last two rows
                 uc[0] = up_even2(rc0[s], rc1[s], rc2); ug[0] = up_even2(rg0[s], rg1[s], rg2);
                 uc[1] = up_odd2(rc1[s], rc2);          ug[1] = up_odd2(rg1[s], rg2);
                 const float2 nwy2 = gs_f32x2(sb + O_NWY + 8 * k);
@@ -1584,9 +1775,11 @@ __global__ void __launch_bounds__(FB_PAIRS *C, (TMAX <= 2) ? SRF_GATHER_CTAS : 2
                     const float nwy = a ? nwy2.y : nwy2.x;
                     const int ob = o_u8[s] + (2 * k + a) * FB_U8_STRIDE;
                     const float2 nw = make_float2(fmaxf(nwy, wxa[s]), fmaxf(nwy, wxb[s])); // -min(wy, wx)
-                    const float2 nd = __ffma2_rn(make_float2(gs_u8f(ob), gs_u8f(ob + C)), make_float2(-64.f, -64.f), ug[a]);
+                    // nd = -256 (64 g - up64G): integers below 2^24, exact; dw = 256 x the reference's product (the scale commutes
+                    // with its rounding); the last FMA takes the 2^-8 out again: fma(dw, 2^-8, uc) == uc + dw / 256 rounded once
+                    const float2 nd = __ffma2_rn(make_float2(gs_u8f(ob), gs_u8f(ob + C)), make_float2(-16384.f, -16384.f), ug[a]);
                     const float2 dw = make_float2(__fmul_rn(nd.x, nw.x), __fmul_rn(nd.y, nw.y));
-                    v[a] = __fadd2_rn(uc[a], dw);
+                    v[a] = __ffma2_rn(dw, make_float2(1.f / 256.f, 1.f / 256.f), uc[a]);
                     w[a] = make_float2(-nw.x, -nw.y);
                 }
                 rc0[s] = rc1[s]; rg0[s] = rg1[s]; rc1[s] = rc2; rg1[s] = rg2;
@@ -1617,13 +1810,13 @@ __global__ void __launch_bounds__(FB_PAIRS *C, (TMAX <= 2) ? SRF_GATHER_CTAS : 2
                     v[a] = w[a] = make_float2(0.f, 0.f);
                     if (row_in && (flags[s] & 1u)) {
                         const float w0 = fminf(wy, wxa[s]);
-                        // fma(g, 64, -up64G) == 64 g - up64G rounded once: 64 g is exact, so this IS the reference's subtraction
-                        v[a].x = __fadd_rn(uc[a].x, __fmul_rn(__fmaf_rn(gs_u8f(ob), 64.f, -ug[a].x), w0));
+                        // fma(g, 16384, -256 up64G) == 256 (64 g - up64G), exact; the product carries the x 256 through its rounding
+                        v[a].x = __fmaf_rn(__fmul_rn(__fmaf_rn(gs_u8f(ob), 16384.f, -ug[a].x), w0), 1.f / 256.f, uc[a].x);
                         w[a].x = w0;
                     }
                     if (row_in && (flags[s] & 2u)) {
                         const float w0 = fminf(wy, wxb[s]);
-                        v[a].y = __fadd_rn(uc[a].y, __fmul_rn(__fmaf_rn(gs_u8f(ob + C), 64.f, -ug[a].y), w0));
+                        v[a].y = __fmaf_rn(__fmul_rn(__fmaf_rn(gs_u8f(ob + C), 16384.f, -ug[a].y), w0), 1.f / 256.f, uc[a].y);
                         w[a].y = w0;
                     }
                 }
@@ -1699,11 +1892,12 @@ __global__ void __launch_bounds__(FB_PAIRS *C, (TMAX == 1) ? 6 : ((TMAX == 2) ? 
     k_gather_full(const __grid_constant__ GatherParams P, const __grid_constant__ GatherTiles GT, const __grid_constant__ FinalTmaps TM)
 {
     pdl_enter(); // programmatic dependent launch: nothing above this line may touch global data
-    using Stage = FinalStage<C>;
+    using Stage = GatherStage<C>;
     constexpr int NT = FB_PAIRS * C;
     constexpr int O_SC = (int)offsetof(Stage, sc), O_SG = (int)offsetof(Stage, sg), O_U8 = (int)offsetof(Stage, u8), O_NWY = (int)offsetof(Stage, nwy);
     constexpr int STAGE = (int)sizeof(Stage), O_OUT = TMAX * STAGE;
-    constexpr int ROWB = FB_SRC_COLS * 4, CHB = FB_SRC_ROWS * ROWB;
+    constexpr int ROWB = FB_SRC_COLS * 4, CHB = FB_SRC_ROWS * ROWB; // bytes per staged C_1 row / channel plane
+    constexpr int ROWG = FB_G_COLS * 2, CHG = FB_SRC_ROWS * ROWG;   // the same for the uint16 G_1 window
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ __align__(8) int s_rowoff[FB_H]; // r * FB_U8_STRIDE + misalignment of canvas row r: where a finished row is staged
     const int base = (int)((128u - (smem_u32(g_gather_smem) & 127u)) & 127u);
@@ -1738,7 +1932,7 @@ __global__ void __launch_bounds__(FB_PAIRS *C, (TMAX == 1) ? 6 : ((TMAX == 2) ? 
         const int r = (int)threadIdx.x - 64;
         s_rowoff[r] = r * FB_U8_STRIDE + ((mis0 + r * pit16) & 15);
     }
-    int o_src[TMAX], o_u8[TMAX];
+    int o_src[TMAX], o_g[TMAX], o_u8[TMAX];
     float nwxa[TMAX], nwxb[TMAX];
 #pragma unroll
     for (int s = 0; s < TMAX; ++s) {
@@ -1750,11 +1944,12 @@ __global__ void __launch_bounds__(FB_PAIRS *C, (TMAX == 1) ? 6 : ((TMAX == 2) ? 
         const int sb = base + s * STAGE;
         if (threadIdx.x == 0) {
             tma_tensor_3d_g2s(g_gather_smem + sb + O_SC, &TM.m[ti][0], sx0, ws0, 0, &s_bar);
-            tma_tensor_3d_g2s(g_gather_smem + sb + O_SG, &TM.m[ti][1], sx0, ws0, 0, &s_bar);
+            tma_tensor_3d_g2s(g_gather_smem + sb + O_SG, &TM.m[ti][1], (i0 >> 3) * 8, ws0, 0, &s_bar);
             tma_tensor_2d_g2s(g_gather_smem + sb + O_U8, &TM.m[ti][2], u8_a0 >> 2, tyf, &s_bar);
         }
         const int txa = txf + 2 * p;
-        o_src[s] = sb + c * CHB + 4 * (i0 + p - sx0);
+        o_src[s] = c * CHB + 4 * (i0 + p - sx0); // first C_1 sample, relative to the stage's sc array
+        o_g[s] = c * CHG + 2 * (i0 + p - (i0 >> 3) * 8); // first G_1 sample, relative to sg
         o_u8[s] = sb + O_U8 + txa * C + c - u8_a0;
         if (!UNIT) {
             if (threadIdx.x >= 32 && threadIdx.x < 32 + FB_H) { // -W_0 row profile of the block
@@ -1771,18 +1966,18 @@ __global__ void __launch_bounds__(FB_PAIRS *C, (TMAX == 1) ? 6 : ((TMAX == 2) ? 
     mbar_wait_or_trap(&s_bar, 0);
 
     float2 rc0[TMAX], rg0[TMAX], rc1[TMAX], rg1[TMAX];
-    auto hrow = [&](int o, float2 &oc, float2 &og) { // columns (2i, 2i+1), i = window centre: even form, odd form
-        const float c0 = gs_f32(o + O_SC), c1 = gs_f32(o + O_SC + 4), c2 = gs_f32(o + O_SC + 8);
-        const float g0 = gs_f32(o + O_SG), g1 = gs_f32(o + O_SG + 4), g2 = gs_f32(o + O_SG + 8);
+    auto hrow = [&](int sb, int o, int oh, float2 &oc, float2 &og) { // columns (2i, 2i+1), i = window centre: even form, odd form
+        const float c0 = gs_f32(sb + O_SC + o), c1 = gs_f32(sb + O_SC + o + 4), c2 = gs_f32(sb + O_SC + o + 8);
         oc = make_float2(up_even(c0, c1, c2), up_odd(c1, c2));
-        og = make_float2(up_even(g0, g1, g2), up_odd(g1, g2));
+        og = g16_pair_even_origin(gs_u16(sb + O_SG + oh), gs_u16(sb + O_SG + oh + 2), gs_u16(sb + O_SG + oh + 4)); // x 256, exact
     };
 #pragma unroll
     for (int s = 0; s < TMAX; ++s) {
         if (s >= T) break;
-        hrow(o_src[s], rc0[s], rg0[s]);
-        hrow(o_src[s] + ROWB, rc1[s], rg1[s]);
+        hrow(base + s * STAGE, o_src[s], o_g[s], rc0[s], rg0[s]);
+        hrow(base + s * STAGE, o_src[s] + ROWB, o_g[s] + ROWG, rc1[s], rg1[s]);
         o_src[s] += 2 * ROWB;
+        o_g[s] += 2 * ROWG;
     }
     auto up_even2 = [](float2 m, float2 p6, float2 n) {
         return __fadd2_rn(__fadd2_rn(make_float2(__fmul_rn(p6.x, 6.f), __fmul_rn(p6.y, 6.f)), m), n);
@@ -1798,9 +1993,10 @@ __global__ void __launch_bounds__(FB_PAIRS *C, (TMAX == 1) ? 6 : ((TMAX == 2) ? 
         for (int s = 0; s < TMAX; ++s) {
             if (s >= T) break;
             float2 rc2, rg2;
-            hrow(o_src[s], rc2, rg2);
+            hrow(base + s * STAGE, o_src[s], o_g[s], rc2, rg2);
             o_src[s] += ROWB;
-            float2 uc[2], ug[2]; // x64, tile rows (2j, 2j+1): even uses the whole ring, odd its last two rows
+            o_g[s] += ROWG;
+            float2 uc[2], ug[2]; // x64 (ug also x256), tile rows (2j, 2j+1): even uses the whole ring, odd its last two rows
             uc[0] = up_even2(rc0[s], rc1[s], rc2); ug[0] = up_even2(rg0[s], rg1[s], rg2);
             uc[1] = up_odd2(rc1[s], rc2);          ug[1] = up_odd2(rg1[s], rg2);
             float2 v[2], w[2];
@@ -1809,15 +2005,16 @@ __global__ void __launch_bounds__(FB_PAIRS *C, (TMAX == 1) ? 6 : ((TMAX == 2) ? 
 #pragma unroll
             for (int a = 0; a < 2; ++a) {
                 const int ob = o_u8[s] + (2 * k + a) * FB_U8_STRIDE;
-                // nd = fma(g, -64, up64G) = -(64 g - up64G), rounded once: 64 g is exact, so this IS the reference's subtraction
-                const float2 nd = __ffma2_rn(make_float2(gs_u8f(ob), gs_u8f(ob + C)), make_float2(-64.f, -64.f), ug[a]);
+                // nd = -256 (64 g - up64G): integers below 2^24, exact -- the reference's subtraction, scaled by a power of two
+                const float2 nd = __ffma2_rn(make_float2(gs_u8f(ob), gs_u8f(ob + C)), make_float2(-16384.f, -16384.f), ug[a]);
                 if (UNIT) {
-                    v[a] = __fadd2_rn(uc[a], make_float2(-nd.x, -nd.y)); // (64 g - up64G) * 1.0f is exact
+                    v[a] = __ffma2_rn(nd, make_float2(-1.f / 256.f, -1.f / 256.f), uc[a]); // (64 g - up64G) * 1.0f is exact: uc + that, rounded once
                 } else {
                     const float nwy = a ? nwy2.y : nwy2.x;
                     const float2 nw = make_float2(fmaxf(nwy, nwxa[s]), fmaxf(nwy, nwxb[s])); // -min(wy, wx)
-                    const float2 dw = make_float2(__fmul_rn(nd.x, nw.x), __fmul_rn(nd.y, nw.y)); // scalar: must not fuse into the add
-                    v[a] = __fadd2_rn(uc[a], dw);
+                    // dw = 256 x the reference's product (the scale commutes with its rounding); scalar so it cannot fuse into an add
+                    const float2 dw = make_float2(__fmul_rn(nd.x, nw.x), __fmul_rn(nd.y, nw.y));
+                    v[a] = __ffma2_rn(dw, make_float2(1.f / 256.f, 1.f / 256.f), uc[a]); // uc + dw / 256, rounded once
                     w[a] = make_float2(-nw.x, -nw.y);
                 }
             }
@@ -2069,18 +2266,12 @@ int srf_fuse_device(srf_ctx *ctx, const srf_tile *tiles, int n_tiles, int C, int
             ++n;
         }
         g.n_levels = n;
-        w_off[k].assign(SRF_MAX_LEVELS, 0);
-        for (int l = 1; l < n; ++l) w_off[k][l] = take(g.lv[l].plane);
+        g.g1_u16 = 0;
+        g.g1_pitch = n >= 2 ? (int)srf_align_up((size_t)g.lv[1].w, 8) : 0; // uint16 elements: 16-byte rows
+        g.g1_plane = n >= 2 ? srf_align_up((size_t)g.g1_pitch * g.lv[1].h, 64) : 0;
     }
     std::vector<TileDev> tdev(n_tiles);
-    std::vector<std::vector<size_t>> g_off(n_tiles, std::vector<size_t>(SRF_MAX_LEVELS, 0)), c_off = g_off;
-    for (int i = 0; i < n_tiles; ++i) {
-        const GroupDev &g = groups[tile_group[i]].dev;
-        for (int l = 1; l < g.n_levels; ++l) g_off[i][l] = take(g.lv[l].plane * C);
-        for (int l = 1; l <= g.n_levels - 2; ++l) c_off[i][l] = take(g.lv[l].plane * C);
-    }
     int rc;
-    if ((rc = srf_reserve(ctx, ctx->ws_pyr, pyr_floats * sizeof(float) + 256))) return rc;
     // ---- cells of the row-outer gather (k_gather / k_gather_full): rectangles of blocks that share one ordered tile list
     // and one class (what can be proven about every block of the cell) ----
     const int rb = std::max(row_begin, 0), re = std::min(row_end, out_h);
@@ -2216,6 +2407,25 @@ int srf_fuse_device(srf_ctx *ctx, const srf_tile *tiles, int n_tiles, int C, int
             }
         }
     }
+    // the row-outer gather also needs a TMA descriptor per tile: 16-byte aligned rows, and the driver's encoder
+    for (int i = 0; i < n_tiles && cells_ok; ++i) cells_ok = (tiles[i].pitch % 16 == 0) && (((uintptr_t)tiles[i].data & 15) == 0);
+    if (cells_ok && srf_tensor_map_encoder() == nullptr) cells_ok = false;
+    const bool g1_u16 = cells_ok; // the row-outer gather kernels read G_1 as uint16 (x 256); k_final reads float32
+    for (size_t k = 0; k < groups.size(); ++k) groups[k].dev.g1_u16 = g1_u16 ? 1 : 0;
+    // ---- workspace plan: weight pyramids first (their offsets key the cross-call cache), then per tile G_l and C_l ----
+    for (size_t k = 0; k < groups.size(); ++k) {
+        const GroupDev &g = groups[k].dev;
+        w_off[k].assign(SRF_MAX_LEVELS, 0);
+        for (int l = 1; l < g.n_levels; ++l) w_off[k][l] = take(g.lv[l].plane);
+    }
+    std::vector<std::vector<size_t>> g_off(n_tiles, std::vector<size_t>(SRF_MAX_LEVELS, 0)), c_off = g_off;
+    for (int i = 0; i < n_tiles; ++i) {
+        const GroupDev &g = groups[tile_group[i]].dev;
+        for (int l = 1; l < g.n_levels; ++l)
+            g_off[i][l] = take((l == 1 && g1_u16) ? (g.g1_plane * C + 1) / 2 : g.lv[l].plane * C); // uint16 plane: half the floats
+        for (int l = 1; l <= g.n_levels - 2; ++l) c_off[i][l] = take(g.lv[l].plane * C);
+    }
+    if ((rc = srf_reserve(ctx, ctx->ws_pyr, pyr_floats * sizeof(float) + 256))) return rc;
     size_t n_cells_all = 0, cell_off[GC_CLASSES];
     for (int k = 0; k < GC_CLASSES; ++k) {
         cell_off[k] = n_cells_all;
@@ -2376,11 +2586,18 @@ int srf_fuse_device(srf_ctx *ctx, const srf_tile *tiles, int n_tiles, int C, int
                 dim3 grid(srf_ceil_div(gi.lv[1].w, D8_BW), srf_ceil_div(rows, D8_ROWS), nt);
                 double px1 = 0; // level-1 pixels produced
                 for (int ti : groups[k].tiles) px1 += (double)(tdev[ti].g1[1] - tdev[ti].g0[1]) * std::min(gi.lv[1].w, tdev[ti].gx1[1]);
-                srf_launch_scope scope(ctx, "down_u8", px1 * C * (4.0 /*u8 in*/ + 4.0 /*f32 out*/), st);
-                if (C == 3)
-                    srf_launch_pdl(k_down_u8<3>, grid, dim3(128 * 3), 0, st, d_tiles, ids_k, gi);
-                else
-                    srf_launch_pdl(k_down_u8<1>, grid, dim3(128), 0, st, d_tiles, ids_k, gi);
+                srf_launch_scope scope(ctx, "down_u8", px1 * C * (4.0 /*u8 in*/ + (g1_u16 ? 2.0 : 4.0) /*G_1 out*/), st);
+                if (C == 3) {
+                    if (g1_u16)
+                        srf_launch_pdl(k_down_u8<3, true>, grid, dim3(128 * 3), 0, st, d_tiles, ids_k, gi);
+                    else
+                        srf_launch_pdl(k_down_u8<3, false>, grid, dim3(128 * 3), 0, st, d_tiles, ids_k, gi);
+                } else {
+                    if (g1_u16)
+                        srf_launch_pdl(k_down_u8<1, true>, grid, dim3(128), 0, st, d_tiles, ids_k, gi);
+                    else
+                        srf_launch_pdl(k_down_u8<1, false>, grid, dim3(128), 0, st, d_tiles, ids_k, gi);
+                }
             }
         }
         for (int l = 1; l + 1 < n; ++l) {
@@ -2390,6 +2607,11 @@ int srf_fuse_device(srf_ctx *ctx, const srf_tile *tiles, int n_tiles, int C, int
             dim3 grid(srf_ceil_div(gi.lv[l + 1].w, DF_BW), srf_ceil_div(rows, rpc), nt * C);
             double pxo = 0;
             for (int ti : groups[k].tiles) pxo += (double)(tdev[ti].g1[l + 1] - tdev[ti].g0[l + 1]) * std::min(gi.lv[l + 1].w, tdev[ti].gx1[l + 1]);
+            if (l == 1 && g1_u16) { // the exact integer level: uint16 in (4 x 2 B per output), float32 out
+                srf_launch_scope scope(ctx, "down_f32", pxo * C * (8.0 + 4.0), st);
+                srf_launch_pdl(k_down_u16, grid, dim3(DF_BW), 0, st, d_tiles, ids_k, gi, rpc);
+                continue;
+            }
             srf_launch_scope scope(ctx, "down_f32", pxo * C * (16.0 + 4.0), st);
             srf_launch_pdl(k_down_f32s<false>, grid, dim3(DF_BW), 0, st, d_tiles, ids_k, gi, l, rpc);
         }
@@ -2401,17 +2623,24 @@ int srf_fuse_device(srf_ctx *ctx, const srf_tile *tiles, int n_tiles, int C, int
             double pxo = 0;
             for (int ti : groups[k].tiles) pxo += (double)(tdev[ti].c1[l] - tdev[ti].c0[l]) * std::min(gi.lv[l].w, tdev[ti].cx1[l]);
             // per output element: G_l + W_l/C read, C_l written, C_{l+1} (or W_{l+1}/C) + G_{l+1} at quarter density
-            srf_launch_scope scope(ctx, "up_level", pxo * C * (4.0 + 4.0 / C + 4.0 + 2.0), st);
+            srf_launch_scope scope(ctx, "up_level", pxo * C * ((l == 1 && g1_u16 ? 2.0 : 4.0) + 4.0 / C + 4.0 + 2.0), st);
             if (l == n - 2) {
                 srf_launch_pdl(k_up_level_top<true>, grid, dim3(kThreads), 0, st, d_tiles, ids_k, gi, l);
             } else {
                 const int gx = srf_ceil_div(gi.lv[l].w, UL_W);
+                const bool g16 = (l == 1) && g1_u16;
                 if ((long long)gx * srf_ceil_div(rows, UL_H) * nt * C >= 4LL * ctx->sm_count) {
                     dim3 sgrid(gx, srf_ceil_div(rows, UL_H), nt * C);
-                    srf_launch_pdl(k_up_levels<UL_H>, sgrid, dim3(UL_PAIRS), 0, st, d_tiles, ids_k, gi, l);
+                    if (g16)
+                        srf_launch_pdl(k_up_levels<UL_H, true>, sgrid, dim3(UL_PAIRS), 0, st, d_tiles, ids_k, gi, l);
+                    else
+                        srf_launch_pdl(k_up_levels<UL_H, false>, sgrid, dim3(UL_PAIRS), 0, st, d_tiles, ids_k, gi, l);
                 } else { // small level / thin band: short CTAs
                     dim3 sgrid(gx, srf_ceil_div(rows, 8), nt * C);
-                    srf_launch_pdl(k_up_levels<8>, sgrid, dim3(UL_PAIRS), 0, st, d_tiles, ids_k, gi, l);
+                    if (g16)
+                        srf_launch_pdl(k_up_levels<8, true>, sgrid, dim3(UL_PAIRS), 0, st, d_tiles, ids_k, gi, l);
+                    else
+                        srf_launch_pdl(k_up_levels<8, false>, sgrid, dim3(UL_PAIRS), 0, st, d_tiles, ids_k, gi, l);
                 }
             }
         }
@@ -2451,14 +2680,19 @@ int srf_fuse_device(srf_ctx *ctx, const srf_tile *tiles, int n_tiles, int C, int
                 const cuuint64_t dims3[3] = {(cuuint64_t)L1.pitch, (cuuint64_t)L1.h, (cuuint64_t)C};
                 const cuuint64_t str3[2] = {(cuuint64_t)L1.pitch * sizeof(float), (cuuint64_t)L1.plane * sizeof(float)};
                 const cuuint32_t box3[3] = {FB_SRC_COLS, FB_SRC_ROWS, (cuuint32_t)C}, one3[3] = {1, 1, 1};
+                const cuuint64_t dims16[3] = {(cuuint64_t)g.g1_pitch, (cuuint64_t)L1.h, (cuuint64_t)C}; // the uint16 G_1 planes
+                const cuuint32_t box16[3] = {FB_G_COLS, FB_SRC_ROWS, (cuuint32_t)C};
+                const cuuint64_t str16[2] = {(cuuint64_t)g.g1_pitch * sizeof(unsigned short), (cuuint64_t)g.g1_plane * sizeof(unsigned short)};
                 const cuuint64_t dims2[2] = {(cuuint64_t)(t.pitch / 4), (cuuint64_t)t.h};
                 const cuuint64_t str2[1] = {(cuuint64_t)t.pitch};
                 const cuuint32_t box2[2] = {FB_U8_STRIDE / 4, FB_H}, one2[2] = {1, 1};
                 const bool ok =
                     enc(&TM.m[i][0], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, t.C[1], dims3, str3, box3, one3, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS &&
-                    enc(&TM.m[i][1], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, t.G[1], dims3, str3, box3, one3, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS &&
+                    (g1_u16 ? enc(&TM.m[i][1], CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, t.G[1], dims16, str16, box16, one3, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE)
+                            : enc(&TM.m[i][1], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, t.G[1], dims3, str3, box3, one3, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE)) == CUDA_SUCCESS &&
                     enc(&TM.m[i][2], CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<uint8_t *>(t.src), dims2, str2, box2, one2,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
@@ -2473,8 +2707,24 @@ int srf_fuse_device(srf_ctx *ctx, const srf_tile *tiles, int n_tiles, int C, int
                 GT.t[i].lut = groups[tile_group[i]].dev.lut;
             }
             const GatherCell *d_cells = (const GatherCell *)(dbase + o_cells);
+            // The classes write disjoint blocks of the canvas, so their launches are independent: the biggest stays on the
+            // caller's stream, the others fork onto side streams and join back -- short launches then fill each other's
+            // ramps and tails instead of queueing (a band of an 8-rank job is six launches of a few hundred CTAs each).
+            // Under stream capture the fork / join events become graph edges.  Serial while per-kernel timing is on.
+            int main_cls = 0;
+            for (int cls = 1; cls < GC_CLASSES; ++cls)
+                if (class_blocks[cls] > class_blocks[main_cls]) main_cls = cls;
+            const bool fork = !ctx->profile && getenv("SRF_GATHER_SERIAL") == nullptr;
+            const cudaStream_t st_main = st;
+            int n_forked = 0;
+            if (fork) SRF_CHECK_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st_main));
             for (int cls = 0; cls < GC_CLASSES; ++cls) {
                 if (class_blocks[cls] == 0) continue;
+                cudaStream_t st = st_main; // shadows the caller's stream for this launch
+                if (fork && cls != main_cls) {
+                    st = ctx->fork_stream[n_forked];
+                    SRF_CHECK_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_fork, 0));
+                }
                 GatherParams GP;
                 GP.cells = d_cells + cell_off[cls];
                 GP.n_cells = (int)cells[cls].size();
@@ -2512,9 +2762,18 @@ int srf_fuse_device(srf_ctx *ctx, const srf_tile *tiles, int n_tiles, int C, int
                     }
                 }
 #undef SRF_GATHER_LAUNCH
+                if (fork && cls != main_cls) {
+                    SRF_CHECK_CUDA(ctx, cudaEventRecord(ctx->ev_join[n_forked], st));
+                    ++n_forked;
+                }
             }
+            for (int i = 0; i < n_forked; ++i) SRF_CHECK_CUDA(ctx, cudaStreamWaitEvent(st_main, ctx->ev_join[i], 0));
             SRF_CHECK_CUDA(ctx, cudaGetLastError());
             return SRF_OK;
+        }
+        if (g1_u16) { // G_1 was written as uint16 for the row-outer gather: k_final cannot read it
+            srf_set_error(ctx, "laplacian_fuse: cuTensorMapEncodeTiled failed for a tile the gather was planned for");
+            return SRF_ERR_CUDA;
         }
         // ---- general gather (1- / 2-level tiles, tiles without a TMA descriptor, more than four tiles over a block) ----
         dim3 grid(srf_ceil_div(out_w, FB_W), srf_ceil_div(re - rb, FB_H), 1);
