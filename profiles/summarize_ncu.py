@@ -1,0 +1,69 @@
+#!/usr/bin/env python
+"""Turn an `ncu --set full` report into the text summary kept under profiles/ and (with --traffic) into
+profiles/ncu_traffic.json: DRAM bytes per bench-table kernel name for ONE step, stamped with the digest of the CUDA
+sources they were captured from (bench.py only attaches them while that digest still matches).
+
+    python profiles/summarize_ncu.py gpurun_out/r02_ncu_full.ncu-rep profiles/r02_ncu_full_summary.txt [--traffic profiles/ncu_traffic.json]
+"""
+import csv
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+WANT = ["launch__grid_size", "launch__block_size", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__occupancy_limit_registers",
+        "launch__occupancy_limit_shared_mem", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+        "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "smsp__inst_executed.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+        "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed"]
+NAMES = [("k_gather", "final_gather"), ("k_final", "final_gather"), ("k_psnr_ssim", "psnr_ssim"), ("k_down_u8", "down_u8"),
+         ("k_down_u16", "down_f32"), ("k_down_f32s", "down_f32"), ("k_up_level", "up_level"), ("k_iqa_reduce", "iqa_reduce")]
+UNIT = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "msecond": 1.0, "usecond": 1e-3, "second": 1e3, "nsecond": 1e-6}
+
+
+def main():
+    rep, out_txt = sys.argv[1], sys.argv[2]
+    traffic_path = sys.argv[sys.argv.index("--traffic") + 1] if "--traffic" in sys.argv else None
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    head, units, body = rows[0], rows[1], rows[2:]
+    col = {h: i for i, h in enumerate(head)}
+    stalls = [h for h in head if "issue_stalled" in h and "per_issue_active" in h]
+    lines, traffic = [], {}
+    for r in body:
+        name = r[col["Kernel Name"]]
+        lines.append(f"Kernel Name = {name}")
+        for w in WANT + stalls:
+            if w in col:
+                lines.append(f"{w} = {r[col[w]]} {units[col[w]]}")
+        lines.append("-----")
+        table = next((t for k, t in NAMES if k in name), None)
+        if table:
+            def val(metric):
+                return float(r[col[metric]].replace(",", "")) * UNIT.get(units[col[metric]], 1.0)
+            t = traffic.setdefault(table, {"dram_bytes_per_step": 0.0, "ncu_time_ms": 0.0, "launches": 0})
+            t["dram_bytes_per_step"] += val("dram__bytes_read.sum") + val("dram__bytes_write.sum")
+            t["ncu_time_ms"] += val("gpu__time_duration.sum")
+            t["launches"] += 1
+    with open(out_txt, "w") as f:
+        f.write("\n".join(lines) + "\n")
+    print(f"{out_txt}: {len(body)} launches")
+    if traffic_path:
+        import bench
+        doc = {"source": f"{os.path.basename(out_txt)}: dram__bytes_read.sum + dram__bytes_write.sum summed over the launches of ONE step that the bench table "
+                         "files under each name (ncu --set full --clock-control none, cfg4_200mp, 1 GPU)",
+               "workload": "cfg4_200mp", "csrc_digest": bench.csrc_digest(), "kernels": traffic}
+        with open(traffic_path, "w") as f:
+            json.dump(doc, f, indent=1)
+        print(f"{traffic_path}: digest {doc['csrc_digest']}, {list(traffic)}")
+
+
+if __name__ == "__main__":
+    main()

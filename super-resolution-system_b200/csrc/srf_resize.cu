@@ -54,6 +54,70 @@ __global__ void __launch_bounds__(RS_BX *RS_BY) k_resize_cubic(const uint8_t *__
     for (int c = 0; c < C; ++c) out[c] = (uint8_t)min(max(__float2int_rn(o[c]), 0), 255); // rint, then saturate
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// k_resize_cubic_up: the same arithmetic for ENLARGING resizes (the bicubic SR stand-in: 2048^2 -> 4096^2 per tile), tiled.
+// The general kernel above gathers 16 source bytes per output value straight from global memory and repeats the column
+// sums of a source column for every output pixel that taps it (8 times at 2x).  Here a CTA stages the source patch of its
+// 128 x 16 output block in shared memory once, and per output row forms the COLUMN sums T[sx] = sum_j src[yi_j][sx] * yw_j
+// once per source column (the first, "rows first" half of the reference order), then every thread combines four of them
+// with its x weights -- the identical products and sums, in the identical order, so the bytes equal the general kernel's.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int RU_W = 128, RU_H = 16;             // output block
+constexpr int RU_SW = RU_W + 8, RU_SH = RU_H + 8; // source patch capacity (scale >= 1: at most block + 4 taps, rounded up)
+
+template <int C>
+__global__ void __launch_bounds__(RU_W) k_resize_cubic_up(const uint8_t *__restrict__ src, size_t spitch, uint8_t *__restrict__ dst, size_t dpitch,
+                                                           int dh, int dw, const ResizeTap *__restrict__ tx, const ResizeTap *__restrict__ ty)
+{
+    __shared__ uint8_t s_src[RU_SH][RU_SW * C];
+    __shared__ float s_t[RU_SW * C];
+    const int x0 = blockIdx.x * RU_W, y0 = blockIdx.y * RU_H;
+    const int x1 = min(x0 + RU_W, dw), y1 = min(y0 + RU_H, dh);
+    // source patch: taps are clamped and monotone, so the first tap of the first output and the last tap of the last bound it
+    const int sx0 = tx[x0].i[0], sx1 = tx[x1 - 1].i[3], sy0 = ty[y0].i[0], sy1 = ty[y1 - 1].i[3];
+    const int ncols = sx1 - sx0 + 1, nrows = sy1 - sy0 + 1; // <= RU_SW, RU_SH for every scale >= 1 (checked by the launcher)
+    const int nbytes = ncols * C;
+    for (int r = 0; r < nrows; ++r) {
+        const uint8_t *g = src + (size_t)(sy0 + r) * spitch + (size_t)sx0 * C;
+        for (int b = threadIdx.x; b < nbytes; b += RU_W) s_src[r][b] = __ldg(g + b);
+    }
+    const int x = x0 + threadIdx.x;
+    int4 xi = make_int4(0, 0, 0, 0);
+    float4 xw = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (x < dw) {
+        xi = *reinterpret_cast<const int4 *>(tx[x].i);
+        xw = *reinterpret_cast<const float4 *>(tx[x].w);
+    }
+    const int xo[4] = {(xi.x - sx0) * C, (xi.y - sx0) * C, (xi.z - sx0) * C, (xi.w - sx0) * C};
+    const float wx[4] = {xw.x, xw.y, xw.z, xw.w};
+    __syncthreads();
+    for (int y = y0; y < y1; ++y) {
+        const int4 yi = *reinterpret_cast<const int4 *>(ty[y].i); // uniform
+        const float4 yw = *reinterpret_cast<const float4 *>(ty[y].w);
+        const uint8_t *r0 = s_src[yi.x - sy0], *r1 = s_src[yi.y - sy0], *r2 = s_src[yi.z - sy0], *r3 = s_src[yi.w - sy0];
+        for (int b = threadIdx.x; b < nbytes; b += RU_W) { // rows first: the column sum of every source column, once
+            float t = __fmul_rn((float)r0[b], yw.x);
+            t = __fadd_rn(t, __fmul_rn((float)r1[b], yw.y));
+            t = __fadd_rn(t, __fmul_rn((float)r2[b], yw.z));
+            t = __fadd_rn(t, __fmul_rn((float)r3[b], yw.w));
+            s_t[b] = t;
+        }
+        __syncthreads();
+        if (x < dw) {
+            uint8_t *out = dst + (size_t)y * dpitch + (size_t)x * C;
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                float o = __fmul_rn(s_t[xo[0] + c], wx[0]);
+                o = __fadd_rn(o, __fmul_rn(s_t[xo[1] + c], wx[1]));
+                o = __fadd_rn(o, __fmul_rn(s_t[xo[2] + c], wx[2]));
+                o = __fadd_rn(o, __fmul_rn(s_t[xo[3] + c], wx[3]));
+                out[c] = (uint8_t)min(max(__float2int_rn(o), 0), 255); // rint, then saturate
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // OpenCV interpolateCubic (a = -0.75) in float64, the operation order of oracle/resize_oracle.py::cubic_weights
 void cubic_weights(double x, float *w)
 {
@@ -110,7 +174,13 @@ int resize_device(srf_ctx *ctx, const uint8_t *d_src, size_t spitch, int h, int 
         // every source pixel a tap can reach is read once from HBM (the 16-tap gathers overlap in L1/L2) + the output
         const double src_px = (double)(dw < w ? std::min((double)w, 4.0 * dw) : w) * (double)(dh < h ? std::min((double)h, 4.0 * dh) : h);
         srf_launch_scope scope(ctx, "resize_cubic", C * (src_px + (double)dw * dh), st);
-        if (C == 3)
+        if (dw >= w && dh >= h) { // enlarging (the SR stand-in): the tiled kernel -- same bytes, a quarter of the instructions
+            dim3 ugrid(srf_ceil_div(dw, RU_W), srf_ceil_div(dh, RU_H));
+            if (C == 3)
+                k_resize_cubic_up<3><<<ugrid, RU_W, 0, st>>>(d_src, spitch, d_dst, dpitch, dh, dw, tx, ty);
+            else
+                k_resize_cubic_up<1><<<ugrid, RU_W, 0, st>>>(d_src, spitch, d_dst, dpitch, dh, dw, tx, ty);
+        } else if (C == 3)
             k_resize_cubic<3><<<grid, block, 0, st>>>(d_src, spitch, d_dst, dpitch, dh, dw, tx, ty);
         else
             k_resize_cubic<1><<<grid, block, 0, st>>>(d_src, spitch, d_dst, dpitch, dh, dw, tx, ty);

@@ -304,3 +304,18 @@ def test_float_and_wide_integer_tiles_are_cast_like_the_reference(srs, oracle):
     got = bm.laplacian_fusion([srs.TileInfo(torch.from_numpy(t.astype(np.float32)).cuda(), x, y, 0, 0) for t, (y, x) in zip(tiles, pos)],
                               output_shape=out_hw)
     assert np.array_equal(got.cpu().numpy(), want)
+
+
+def test_enlarging_bicubic_tiled_kernel_bit_equals_oracle(srs, oracle):
+    """the SR stand-in's tiled kernel (enlarging resizes): same bytes as the restatement for 2x (bit-equal to cv2), for
+    non-integer and anisotropic factors, for scale 1, for gray images and for sizes that do not fill its 128 x 16 blocks"""
+    import torch
+    rng = np.random.default_rng(61)
+    qa = srs.QualityAssessmentModule()
+    ro = oracle.resize_oracle
+    for shape, (dh, dw) in [((300, 410, 3), (600, 820)), ((257, 131, 3), (701, 301)), ((64, 64, 3), (64, 64)), ((90, 200), (181, 777)),
+                            ((33, 17, 3), (99, 18)), ((512, 512, 3), (1024, 1024))]:
+        img = synth(rng, shape[0], shape[1], shape[2] if len(shape) == 3 else 1)
+        want = ro.resize_cubic_u8(img, dw, dh)
+        assert np.array_equal(qa.upsample_bicubic(img, (dh, dw)), want), (shape, dh, dw)
+        assert np.array_equal(qa.upsample_bicubic(torch.from_numpy(img).cuda(), (dh, dw)).cpu().numpy(), want), (shape, dh, dw)
