@@ -105,6 +105,9 @@ __device__ __forceinline__ float lut_weight(const float *__restrict__ lut, int l
 // register shift ring and every second row emits one output row (coalesced 128-byte stores per warp).
 // grid = (ceil(ow/128), ceil(rows/32), tiles in group)
 // ------------------------------------------------------------------------------------------------------------
+#ifndef SRF_D8_CTAS
+#define SRF_D8_CTAS 3 // resident CTAs per SM the register allocation of k_down_u8<3> is held to (2 at the compiler's own choice: +20 % time)
+#endif
 constexpr int D8_BW = 128, D8_ROWS = 32, D8_BATCH = 8;
 constexpr int D8_GROUPS = 18;           // 16-pixel groups staged per row: pixels [2*ox0-16, 2*ox0+272)
 constexpr int D8_PSTRIDE = D8_GROUPS * 16;
@@ -126,7 +129,7 @@ __device__ __forceinline__ uint4 load_u8_chunk(const uint8_t *grow, int o, int v
 }
 
 template <int C, bool U16>
-__global__ void __launch_bounds__(128 * C) k_down_u8(const TileDev *__restrict__ tiles, const int *__restrict__ tile_ids, GroupDev g)
+__global__ void __launch_bounds__(128 * C, (C == 3) ? SRF_D8_CTAS : 8) k_down_u8(const TileDev *__restrict__ tiles, const int *__restrict__ tile_ids, GroupDev g)
 {
     pdl_enter(); // programmatic dependent launch: nothing above this line may touch global data
     __shared__ __align__(16) uint8_t s_pl[2][D8_BATCH][C][D8_PSTRIDE];
@@ -203,8 +206,12 @@ __global__ void __launch_bounds__(128 * C) k_down_u8(const TileDev *__restrict__
         int q = srf_reflect101(2 * min(ox, ow - 1) + k - 2, w) - px_g0;
         ti[k] = max(min(q, D8_PSTRIDE - 1), 0);
     }
-    float *dst = t.G[1] + (size_t)c * L1.plane;
-    unsigned short *dst16 = reinterpret_cast<unsigned short *>(t.G[1]) + (size_t)c * g.g1_plane;
+    // output rows of a batch leave through a running pointer: row oy0 + 4 b - 2 + (j / 2) at even j of batch b
+    const bool col_ok = ox < ow;
+    const ptrdiff_t row_stride = U16 ? (ptrdiff_t)g.g1_pitch : (ptrdiff_t)L1.pitch;
+    float *po32 = t.G[1] + (size_t)c * L1.plane + ((ptrdiff_t)oy0 - 2) * row_stride + ox;
+    unsigned short *po16 = reinterpret_cast<unsigned short *>(t.G[1]) + (size_t)c * g.g1_plane + ((ptrdiff_t)oy0 - 2) * row_stride + ox;
+    int oyb = oy0 - 2;
 
     int h0 = 0, h1 = 0, h2 = 0, h3 = 0, h4 = 0;
     stage_load(0);
@@ -225,18 +232,20 @@ __global__ void __launch_bounds__(128 * C) k_down_u8(const TileDev *__restrict__
                 hv = (int)row[ti[0]] + (int)row[ti[4]] + 4 * ((int)row[ti[1]] + (int)row[ti[3]]) + 6 * (int)row[ti[2]];
             }
             h0 = h1; h1 = h2; h2 = h3; h3 = h4; h4 = hv;
-            const int r = b * D8_BATCH + j; // stream position; rows r-4..r are in the ring
-            if ((j & 1) == 0 && r >= 4) {
-                const int oy = oy0 + ((r - 4) >> 1);
-                if (oy < oy1 && ox < ow) {
+            if ((j & 1) == 0) { // stream position r = 8 b + j holds input rows r-4 .. r in the ring: output row oy0 + (r - 4) / 2
+                const int oy = oyb + (j >> 1);
+                if (oy >= oy0 && oy < oy1 && col_ok) {
                     const int v = h0 + h4 + 4 * (h1 + h3) + 6 * h2;
                     if (U16)
-                        dst16[(size_t)oy * g.g1_pitch + ox] = (unsigned short)v; // G_1 * 256, exact
+                        po16[(j >> 1) * row_stride] = (unsigned short)v; // G_1 * 256, exact
                     else
-                        dst[(size_t)oy * L1.pitch + ox] = __fmul_rn((float)v, 1.f / 256.f);
+                        po32[(j >> 1) * row_stride] = __fmul_rn((float)v, 1.f / 256.f);
                 }
             }
         }
+        oyb += D8_BATCH / 2;
+        po16 += (D8_BATCH / 2) * row_stride;
+        po32 += (D8_BATCH / 2) * row_stride;
         if (b + 1 < n_batches) stage_store(buf ^ 1);
         __syncthreads();
     }

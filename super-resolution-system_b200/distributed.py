@@ -24,18 +24,19 @@ def band(rank: int, world: int, rows: int) -> Tuple[int, int]:
     return min(rank * per, rows), min((rank + 1) * per, rows)
 
 
-def balanced_bands(world: int, rows: int, cols: int, positions_yx, sizes_hw, row_cost: float = 2.5,
-                   tile_cost: float = 110.0) -> List[Tuple[int, int]]:
+def balanced_bands(world: int, rows: int, cols: int, positions_yx, sizes_hw, row_cost: float = 1.13,
+                   tile_cost: float = 100.0) -> List[Tuple[int, int]]:
     """Cut the canvas rows into `world` contiguous bands of equal COST rather than equal height.  Cost of a band, in
     units of "one tile covering one full canvas row":
         row_cost per canvas row        the per-pixel work: assessment, the canvas write and the gather's per-block part
       + 1 per covering tile and row    the gather's per-tile work (scaled by the covered fraction of the row)
       + tile_cost per tile touched     what a band pays for every tile it reaches at all, however few rows: that tile's
                                        coarse pyramid levels and halo rows (scaled by tile width / 4096)
-    The constants are the per-rank kernel times of the 8-band 200 MP job measured with profiles/band_probe.py
-    (0.22 us per canvas row, 0.074 us per covered row, ~8 us per touched 4096-wide tile): at that band height the
-    pyramid kernels are launch-latency bound, i.e. a per-tile constant, not a per-row cost.  The cuts minimise the
-    most expensive band (binary search on the bound, greedy fill)."""
+    The constants are a least-squares fit to the per-rank kernel times of the 8-band 200 MP job measured with
+    profiles/band_probe.py on the round-2 kernels (0.177 us per canvas row, 0.157 us per covered row, 15.8 us per
+    touched 4096-wide tile; the fit reproduces every rank's time to 2 %): at that band height the pyramid kernels are
+    launch-latency and halo bound, i.e. a per-tile constant, not a per-row cost.  The cuts minimise the most expensive
+    band (binary search on the bound, greedy fill)."""
     import numpy as np
     if world <= 1 or rows <= 0:
         return [(0, max(rows, 0))] + [(max(rows, 0), max(rows, 0))] * (max(world, 1) - 1)
