@@ -143,6 +143,13 @@ int srf_laplacian_fuse_host(srf_ctx *ctx, const srf_tile *tiles, int n_tiles, in
                             const srf_weight_lut *luts, int n_luts, int out_h, int out_w, uint8_t *h_canvas,
                             size_t canvas_pitch, int row_begin, int row_end);
 
+/* host only, exact: the rows [row0, row1) and columns [0, cols) of a tile (h, w at canvas position y, x) that canvas rows
+ * [row_begin, row_end) of an out_h x out_w fusion with `levels` pyramid levels can depend on -- the dependency cone the
+ * host entry points upload, exposed so a band-sharded caller can upload each tile row to ONE rank and ship the few halo
+ * rows GPU to GPU (distributed.BandedHostFuser).  row0 == row1: the tile does not reach those rows. */
+int srf_fuse_input_rows(int tile_h, int tile_w, int tile_y, int tile_x, int levels, int out_h, int out_w, int row_begin,
+                        int row_end, int *row0, int *row1, int *cols);
+
 /* ---- full-reference IQA -------------------------------------------------------------------------------- */
 /* partial sums of one image pair over a row band; additive across bands / ranks */
 typedef struct srf_iqa_sums {

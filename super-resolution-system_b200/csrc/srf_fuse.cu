@@ -2169,8 +2169,8 @@ static void srf_propagate_need(int a0, int b0, const int *dim, int n, RowRange *
     }
 }
 
-// rows / columns [0, rows) x [0, cols) of an input tile that canvas rows [row_begin, row_end) can depend on
-void srf_fuse_input_extent(const srf_tile &t, int levels, int out_h, int out_w, int row_begin, int row_end, int *rows, int *cols)
+// rows [row0, rows) x columns [0, cols) of an input tile that canvas rows [row_begin, row_end) can depend on
+void srf_fuse_input_extent(const srf_tile &t, int levels, int out_h, int out_w, int row_begin, int row_end, int *rows, int *cols, int *row0)
 {
     int hs[SRF_MAX_LEVELS], ws[SRF_MAX_LEVELS], n = 1;
     hs[0] = t.h;
@@ -2188,6 +2188,21 @@ void srf_fuse_input_extent(const srf_tile &t, int levels, int out_h, int out_w, 
     srf_propagate_need(live ? xa0 : 0, live ? xb0 : 0, ws, n, cc, cg);
     *rows = ng[0].b;
     *cols = cg[0].b;
+    if (row0) *row0 = ng[0].a;
+}
+
+extern "C" int srf_fuse_input_rows(int tile_h, int tile_w, int tile_y, int tile_x, int levels, int out_h, int out_w, int row_begin, int row_end,
+                                   int *row0, int *row1, int *cols)
+{
+    if (tile_h < 1 || tile_w < 1 || levels < 1 || levels > SRF_MAX_LEVELS || !row0 || !row1 || !cols) return SRF_ERR_ARG;
+    srf_tile t;
+    memset(&t, 0, sizeof t);
+    t.h = tile_h;
+    t.w = tile_w;
+    t.y = tile_y;
+    t.x = tile_x;
+    srf_fuse_input_extent(t, levels, out_h, out_w, row_begin, row_end, row1, cols, row0);
+    return SRF_OK;
 }
 
 static uint64_t fuse_signature(const srf_tile *tiles, int n_tiles, int C, int levels, const srf_weight_lut *luts, int n_luts, int out_h,
@@ -2914,12 +2929,12 @@ extern "C" int srf_laplacian_fuse_host(srf_ctx *ctx, const srf_tile *tiles, int 
     size_t h2d = 0;
     for (int i = 0; i < n_tiles; ++i) {
         dt[i].data = din + off[i];
-        int rows = 0, cols = 0; // only the part of the tile the requested canvas rows can depend on travels
-        srf_fuse_input_extent(tiles[i], levels, out_h, out_w, row_begin, row_end, &rows, &cols);
-        if (rows > 0 && cols > 0) {
-            h2d += (size_t)cols * channels * rows;
-            SRF_CHECK_CUDA(ctx, cudaMemcpy2DAsync(din + off[i], dt[i].pitch, tiles[i].data, tiles[i].pitch, (size_t)cols * channels, rows,
-                                                  cudaMemcpyHostToDevice, st));
+        int rows = 0, cols = 0, row0 = 0; // only the part of the tile the requested canvas rows can depend on travels
+        srf_fuse_input_extent(tiles[i], levels, out_h, out_w, row_begin, row_end, &rows, &cols, &row0);
+        if (rows > row0 && cols > 0) {
+            h2d += (size_t)cols * channels * (rows - row0);
+            SRF_CHECK_CUDA(ctx, cudaMemcpy2DAsync(din + off[i] + (size_t)row0 * dt[i].pitch, dt[i].pitch, tiles[i].data + (size_t)row0 * tiles[i].pitch,
+                                                  tiles[i].pitch, (size_t)cols * channels, rows - row0, cudaMemcpyHostToDevice, st));
         }
     }
     ctx->last_h2d = h2d;

@@ -110,11 +110,12 @@ extern "C" int srf_fuse_assess_host(srf_ctx *ctx, const srf_tile *tiles, int n_t
         for (int i = 0; i < n_tiles; ++i) {
             if (uploaded[i] || !touches(i, r0, r1)) continue;
             uploaded[i] = 1;
-            int rows = 0, cols = 0; // only the part of the tile the canvas can depend on travels (exact dependency cone)
-            srf_fuse_input_extent(tiles[i], levels, out_h, out_w, F0, F1, &rows, &cols);
-            if (rows > 0 && cols > 0) {
-                h2d += (size_t)cols * channels * rows;
-                SRF_CHECK_CUDA(ctx, cudaMemcpy2DAsync(din + off[i], dt[i].pitch, tiles[i].data, tiles[i].pitch, (size_t)cols * channels, rows,
+            int rows = 0, cols = 0, row0 = 0; // only the part of the tile the canvas can depend on travels (exact dependency cone)
+            srf_fuse_input_extent(tiles[i], levels, out_h, out_w, F0, F1, &rows, &cols, &row0);
+            if (rows > row0 && cols > 0) {
+                h2d += (size_t)cols * channels * (rows - row0);
+                SRF_CHECK_CUDA(ctx, cudaMemcpy2DAsync(din + off[i] + (size_t)row0 * dt[i].pitch, dt[i].pitch,
+                                                      tiles[i].data + (size_t)row0 * tiles[i].pitch, tiles[i].pitch, (size_t)cols * channels, rows - row0,
                                                       cudaMemcpyHostToDevice, up));
             }
         }

@@ -58,6 +58,21 @@ def main():
     tot = results[-1]
     assert all((r.sq_err, r.ssim_count, r.ssim_sum) == (tot.sq_err, tot.ssim_count, tot.ssim_sum) for r in results)
 
+    # the host-memory variant: own rows uploaded once, halo rows shipped GPU -> GPU, same bytes and sums
+    import torch as _t
+    pinned = [_t.from_numpy(t).pin_memory().numpy() for t in tiles]
+    h_infos = [srs.TileInfo(pinned[i], pos[i][1], pos[i][0], 0, 0) for i in range(len(tiles))]
+    h_out = _t.zeros((H, W, 3), dtype=_t.uint8).pin_memory().numpy()
+    fuser = D.BandedHostFuser(bm, qa, h_infos, _t.from_numpy(ref).pin_memory().numpy(), (H, W), bands, rank, world, dev, exchange=ex)
+    for _ in range(2):
+        ftot = fuser.step(h_out)
+    fuser_ok = (ftot.sq_err, ftot.ssim_count, ftot.ssim_sum) == (tot.sq_err, tot.ssim_count, tot.ssim_sum) and \
+        bool(np.array_equal(h_out[r0:r1], canvas[r0:r1].cpu().numpy()))
+    ok_t = torch.tensor([1 if fuser_ok else 0], dtype=torch.int32, device=dev)
+    dist.all_reduce(ok_t, op=dist.ReduceOp.MIN)
+    total_h2d = torch.tensor([float(fuser.h2d_bytes), float(fuser.p2p_bytes)], dtype=torch.float64, device=dev)
+    dist.all_reduce(total_h2d)
+
     # every rank must hold the same totals: gather them (plumbing) and compare on rank 0
     mine_t = torch.tensor([float(tot.sq_err), tot.ssim_sum, float(tot.ssim_count)], dtype=torch.float64, device=dev)
     every = [torch.empty_like(mine_t) for _ in range(world)]
@@ -74,7 +89,9 @@ def main():
                "canvas_equal": bool(torch.equal(full, own)),
                "sq_err_equal": int(tot.sq_err) == int(s1.sq_err) and int(tot.ssim_count) == int(s1.ssim_count),
                "ssim_rel_err": abs(tot.ssim_sum - s1.ssim_sum) / abs(s1.ssim_sum),
-               "all_ranks_agree": all(bool(torch.equal(e, every[0])) for e in every)}
+               "all_ranks_agree": all(bool(torch.equal(e, every[0])) for e in every),
+               "host_fuser_equal": bool(ok_t.item() == 1), "host_fuser_h2d_bytes": total_h2d[0].item(), "host_fuser_p2p_bytes": total_h2d[1].item(),
+               "tile_bytes_plus_reference": float(sum(t.nbytes for t in tiles) + ref.nbytes)}
         print(json.dumps(rep), flush=True)
     dist.barrier()
     dist.destroy_process_group()

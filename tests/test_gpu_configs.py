@@ -265,6 +265,8 @@ def test_multi_rank_bands_equal_single_rank_canvas(srs, world):
     assert rep["world"] == world and rep["canvas_equal"] and rep["sq_err_equal"] and rep["ssim_rel_err"] <= 1e-9
     assert rep["exchange"] in ("peer", "nccl")
     assert rep["all_ranks_agree"]
+    # host-memory variant (BandedHostFuser): same bytes and sums, and no tile row crosses PCIe twice
+    assert rep["host_fuser_equal"] and rep["host_fuser_h2d_bytes"] <= rep["tile_bytes_plus_reference"] * 1.02 + 4e6
 
 
 # ------------------------------------------------------------------ boundary completeness (round-1 review, "small API holes")
