@@ -473,7 +473,7 @@ static int iqa_launch(srf_ctx *ctx, const uint8_t *a, size_t pa, const uint8_t *
     const long long slots = 4LL * ctx->sm_count;
     int rb = IQ_RB_MAX;
     long long best = -1;
-    for (int cand = 32; cand <= 2 * IQ_RB_MAX; cand += 8) {
+    for (int cand = 32; cand <= 2 * IQ_RB_MAX; cand += 2) {
         const long long ctas = (long long)gx * srf_ceil_div(row_end - row_begin, cand) * n_pairs;
         // fewer than three waves are charged as three: with one or two waves nothing overlaps the CTAs' fill and drain
         // (measured on 1 600-row bands: one wave of 208-row CTAs is slower than three waves of 64-row ones)
