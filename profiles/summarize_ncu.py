@@ -45,6 +45,8 @@ def main():
                 lines.append(f"{w} = {r[col[w]]} {units[col[w]]}")
         lines.append("-----")
         table = next((t for k, t in NAMES if k in name), None)
+        if "k_down_f32s<1>" in name.replace("(bool)", "").replace(" ", ""):
+            table = None  # weight-pyramid launches: first call only (cached afterwards), not part of a steady-state step
         if table:
             def val(metric):
                 return float(r[col[metric]].replace(",", "")) * UNIT.get(units[col[metric]], 1.0)

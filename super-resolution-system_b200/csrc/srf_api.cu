@@ -38,6 +38,7 @@ int srf_reserve(srf_ctx *ctx, srf_buffer &b, size_t bytes)
 {
     if (bytes <= b.bytes) return SRF_OK;
     ctx->ws_epoch++; // pointers handed to captured graphs / cached descriptors are about to change
+    if (&b == &ctx->ws_pyr) ctx->pyr_epoch++;
     ctx->desc_sig = 0;
     if (b.ptr) {
         SRF_CHECK_CUDA(ctx, cudaDeviceSynchronize());
@@ -72,6 +73,41 @@ int srf_reserve_pinned(srf_ctx *ctx, size_t bytes)
     }
     SRF_CHECK_CUDA(ctx, cudaMallocHost(&ctx->pinned, bytes));
     ctx->pinned_bytes = bytes;
+    return SRF_OK;
+}
+
+// one warp per row: 16-byte loads from the mapped host pointer while both ends are 16-byte aligned, bytes for the tail
+__global__ void __launch_bounds__(256) k_copy_rows_from_host(uint8_t *__restrict__ dst, size_t dpitch, const uint8_t *__restrict__ src, size_t spitch,
+                                                             unsigned width, unsigned rows)
+{
+    const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31, nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (unsigned r = warp; r < rows; r += nwarps) {
+        const uint8_t *s = src + (size_t)r * spitch;
+        uint8_t *d = dst + (size_t)r * dpitch;
+        unsigned body = 0;
+        if ((((uintptr_t)s | (uintptr_t)d) & 15) == 0) {
+            body = width & ~15u;
+            for (unsigned o = lane * 16; o < body; o += 32 * 16) *reinterpret_cast<uint4 *>(d + o) = *reinterpret_cast<const uint4 *>(s + o);
+        }
+        for (unsigned o = body + lane; o < width; o += 32) d[o] = s[o];
+    }
+}
+
+int srf_copy2d_h2d(srf_ctx *ctx, void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t rows, cudaStream_t st)
+{
+    if (width == 0 || rows == 0) return SRF_OK;
+    if (rows >= 64 && width * 2 <= spitch && width < (1u << 31) && rows < (1u << 31)) { // narrow region: is the source mapped pinned memory?
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, src) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer != nullptr) {
+            const unsigned blocks = (unsigned)std::min<size_t>((rows + 7) / 8, 2048);
+            k_copy_rows_from_host<<<blocks, 256, 0, st>>>((uint8_t *)dst, dpitch, (const uint8_t *)at.devicePointer, spitch, (unsigned)width, (unsigned)rows);
+            SRF_CHECK_CUDA(ctx, cudaGetLastError());
+            ctx->launches++;
+            return SRF_OK;
+        }
+        (void)cudaGetLastError(); // pageable memory: not an error, the copy engine takes it
+    }
+    SRF_CHECK_CUDA(ctx, cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, rows, cudaMemcpyHostToDevice, st));
     return SRF_OK;
 }
 

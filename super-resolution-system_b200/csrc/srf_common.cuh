@@ -83,6 +83,7 @@ struct srf_ctx {
     uint64_t fuse_sig = 0;        // signature of the last srf_laplacian_fuse call
     uint64_t desc_sig = 0;        // signature whose descriptors currently sit in ws_desc
     uint64_t ws_epoch = 0, graph_epoch = 0;
+    uint64_t pyr_epoch = 0; // bumped only when ws_pyr itself is re-allocated (the weight cache lives there)
     cudaGraphExec_t fuse_graph = nullptr;
     int64_t fuse_graph_launches = 0;
     // per-kernel profiling (srf_profile_enable)
@@ -139,6 +140,11 @@ int srf_reserve_pinned(srf_ctx *ctx, size_t bytes);
 // stream hygiene between the two families of entry points (they share the ctx workspaces):
 //   srf_note_device_work  a device-path entry point calls it after enqueuing on the caller's stream
 //   srf_host_enter        a *_host entry point calls it first: own / copy / down streams wait for that work
+// host -> device copy of `rows` rows of `width` bytes (the *_host entry points' tile uploads).  The copy engine moves a
+// 2-D region whose rows are much shorter than the pitch at a fifth of the link rate (measured: 2 790-byte rows of a
+// 12 288-byte pitch, 11 GB/s against 51 GB/s for whole rows), so a narrow region of PINNED host memory is pulled by a
+// kernel instead (16-byte loads through the mapped pointer); everything else stays a cudaMemcpy2DAsync.
+int srf_copy2d_h2d(srf_ctx *ctx, void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t rows, cudaStream_t st);
 int srf_note_device_work(srf_ctx *ctx, cudaStream_t st);
 int srf_host_enter(srf_ctx *ctx);
 

@@ -2565,13 +2565,13 @@ int srf_fuse_device(srf_ctx *ctx, const srf_tile *tiles, int n_tiles, int C, int
         mix(w_off[k].data(), sizeof(size_t) * w_off[k].size());
         wkeys[k] = hsh;
     }
-    const bool wcache_hit_base = (ctx->wcache_base == ctx->ws_pyr.ptr) && (ctx->wcache_epoch == ctx->ws_epoch);
+    const bool wcache_hit_base = (ctx->wcache_base == ctx->ws_pyr.ptr) && (ctx->wcache_epoch == ctx->pyr_epoch);
     std::vector<bool> w_valid(groups.size(), false);
     for (size_t k = 0; k < groups.size(); ++k)
         w_valid[k] = wcache_hit_base && k < ctx->wcache_keys.size() && ctx->wcache_keys[k] == wkeys[k];
     ctx->wcache_keys = wkeys;
     ctx->wcache_base = ctx->ws_pyr.ptr;
-    ctx->wcache_epoch = ctx->ws_epoch;
+    ctx->wcache_epoch = ctx->pyr_epoch;
 
     // ---- launches ----
     for (size_t k = 0; k < groups.size(); ++k) {
@@ -2933,8 +2933,9 @@ extern "C" int srf_laplacian_fuse_host(srf_ctx *ctx, const srf_tile *tiles, int 
         srf_fuse_input_extent(tiles[i], levels, out_h, out_w, row_begin, row_end, &rows, &cols, &row0);
         if (rows > row0 && cols > 0) {
             h2d += (size_t)cols * channels * (rows - row0);
-            SRF_CHECK_CUDA(ctx, cudaMemcpy2DAsync(din + off[i] + (size_t)row0 * dt[i].pitch, dt[i].pitch, tiles[i].data + (size_t)row0 * tiles[i].pitch,
-                                                  tiles[i].pitch, (size_t)cols * channels, rows - row0, cudaMemcpyHostToDevice, st));
+            if ((rc = srf_copy2d_h2d(ctx, din + off[i] + (size_t)row0 * dt[i].pitch, dt[i].pitch, tiles[i].data + (size_t)row0 * tiles[i].pitch,
+                                     tiles[i].pitch, (size_t)cols * channels, rows - row0, st)))
+                return rc;
         }
     }
     ctx->last_h2d = h2d;

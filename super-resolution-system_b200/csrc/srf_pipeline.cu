@@ -114,9 +114,9 @@ extern "C" int srf_fuse_assess_host(srf_ctx *ctx, const srf_tile *tiles, int n_t
             srf_fuse_input_extent(tiles[i], levels, out_h, out_w, F0, F1, &rows, &cols, &row0);
             if (rows > row0 && cols > 0) {
                 h2d += (size_t)cols * channels * (rows - row0);
-                SRF_CHECK_CUDA(ctx, cudaMemcpy2DAsync(din + off[i] + (size_t)row0 * dt[i].pitch, dt[i].pitch,
-                                                      tiles[i].data + (size_t)row0 * tiles[i].pitch, tiles[i].pitch, (size_t)cols * channels, rows - row0,
-                                                      cudaMemcpyHostToDevice, up));
+                if ((rc = srf_copy2d_h2d(ctx, din + off[i] + (size_t)row0 * dt[i].pitch, dt[i].pitch, tiles[i].data + (size_t)row0 * tiles[i].pitch,
+                                         tiles[i].pitch, (size_t)cols * channels, rows - row0, up)))
+                    return rc;
             }
         }
         SRF_CHECK_CUDA(ctx, cudaEventRecord(ev_up[b], up));
