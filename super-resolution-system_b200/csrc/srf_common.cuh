@@ -75,9 +75,9 @@ struct srf_ctx {
     cudaEvent_t ev_dev = nullptr;
     bool ev_dev_set = false;
     // the gather's class launches write disjoint canvas blocks: they fork onto these streams and join back (srf_fuse.cu)
-    static const int kForkStreams = 5;
-    cudaStream_t fork_stream[kForkStreams] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-    cudaEvent_t ev_fork = nullptr, ev_join[kForkStreams] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    static const int kForkStreams = 8; // >= the gather's classes - 1
+    cudaStream_t fork_stream[kForkStreams] = {};
+    cudaEvent_t ev_fork = nullptr, ev_join[kForkStreams] = {};
     // CUDA-graph replay of a repeated srf_laplacian_fuse call (same tiles, canvas, band, stream): the second identical
     // call is captured, later ones are one cudaGraphLaunch.  Any workspace reallocation bumps ws_epoch and drops it.
     uint64_t fuse_sig = 0;        // signature of the last srf_laplacian_fuse call

@@ -961,7 +961,7 @@ __global__ void __launch_bounds__(UL_PAIRS) k_up_levels(const TileDev *__restric
 constexpr int FB_W = SRF_FB_W, FB_H = SRF_FB_H, FB_PAIRS = FB_W / 2, FB_STEPS = FB_H / 2;
 constexpr int FB_CTAS_3 = SRF_FB_CTAS, FB_CTAS_1 = 2 * SRF_FB_CTAS; // resident CTAs per SM the smem / registers allow
 constexpr int FB_SRC_ROWS = FB_STEPS + 2;   // 10
-constexpr int FB_SRC_COLS = FB_PAIRS + 8;   // 136
+constexpr int FB_SRC_COLS = FB_PAIRS + 8;   // 72
 constexpr int FB_U8_STRIDE = FB_W * 3 + 16; // payload + up to 15 B misalignment, a multiple of 16
 
 template <int C>
@@ -1589,7 +1589,17 @@ enum { GC_U1 = 0,  // one tile, interior, W_0 == 1 everywhere in the cell: out =
        GC_F4 = 3,  // three or four tiles, all interior
        GC_G2 = 4,  // anything else with <= 2 tiles: tile edges, canvas edges, odd parity, no tile at all
        GC_G4 = 5,  // anything else with 3 or 4 tiles
-       GC_CLASSES = 6 };
+       GC_E2 = 6,  // <= 2 tiles, at least one of them with an edge inside the cell (or the canvas edge), even geometry: the
+                   // lean kernel with border fix-ups of the staged windows and 0 / 1 coverage masks (k_gather_full<.., EDGE>)
+       GC_E4 = 7,  // the same with 3 or 4 tiles
+       GC_CLASSES = 8 };
+// what GC_E2 / GC_E4 ask of every covering tile: even offsets between block grid and tile (cx0 is a multiple of FB_W, cy0 of
+// FB_H from row_begin) and a level-1 plane of exactly half the size, at least 2 x 2 (so the pyrUp border rules are the plain
+// "column -1 := column 1" and "column n := column n - 1", with no duplicated or truncated last row / column)
+__host__ __device__ __forceinline__ bool gather_slot_edge_ok(const GatherTile &t, int cy0, int cx0)
+{
+    return (((cx0 - t.x) & 1) == 0) && (((cy0 - t.y) & 1) == 0) && t.w == 2 * t.w1 && t.h == 2 * t.h1 && t.w1 >= 2 && t.h1 >= 2;
+}
 
 // All shared-memory traffic of k_gather goes through byte offsets into the extern array itself (never through pointers
 // kept in registers across the rolled loop): the compiler then knows the address space and emits LDS / STS with 32-bit
@@ -1896,7 +1906,7 @@ __global__ void __launch_bounds__(FB_PAIRS *C, (TMAX <= 2) ? SRF_GATHER_CTAS : 2
 // products, the sum of W_0 is exactly 1 and the quotient is acc itself (a power-of-two divisor: see k_final's epilogue) --
 // the epilogue is a scale, a truncating conversion and a byte store.
 // ------------------------------------------------------------------------------------------------------------
-template <int C, int TMAX, bool UNIT>
+template <int C, int TMAX, bool UNIT, bool EDGE = false>
 __global__ void __launch_bounds__(FB_PAIRS *C, (TMAX == 1) ? 6 : ((TMAX == 2) ? 4 : 2))
     k_gather_full(const __grid_constant__ GatherParams P, const __grid_constant__ GatherTiles GT, const __grid_constant__ FinalTmaps TM)
 {
@@ -1909,6 +1919,7 @@ __global__ void __launch_bounds__(FB_PAIRS *C, (TMAX == 1) ? 6 : ((TMAX == 2) ? 
     constexpr int ROWG = FB_G_COLS * 2, CHG = FB_SRC_ROWS * ROWG;   // the same for the uint16 G_1 window
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ __align__(8) int s_rowoff[FB_H]; // r * FB_U8_STRIDE + misalignment of canvas row r: where a finished row is staged
+    __shared__ __align__(8) unsigned s_mrow[EDGE ? TMAX : 1][FB_H]; // EDGE: all ones where the tile covers the block's row, else 0
     const int base = (int)((128u - (smem_u32(g_gather_smem) & 127u)) & 127u);
 
     int lo = 0, hi = P.n_cells - 1;
@@ -1923,7 +1934,7 @@ __global__ void __launch_bounds__(FB_PAIRS *C, (TMAX == 1) ? 6 : ((TMAX == 2) ? 
     const int4 ca = __ldg(reinterpret_cast<const int4 *>(&P.cells[lo]));
     const int4 cb = __ldg(reinterpret_cast<const int4 *>(&P.cells[lo]) + 1);
     const int4 cc = __ldg(reinterpret_cast<const int4 *>(&P.cells[lo]) + 2);
-    const int T = (TMAX <= 2) ? TMAX : min(cb.y, TMAX);
+    const int T = (TMAX <= 2 && !EDGE) ? TMAX : min(cb.y, TMAX);
     const int tiles_of[GC_MAX_T] = {cb.z, cb.w, cc.x, cc.y};
     const int local = bid - cb.x;
     const int by = ca.y + local / ca.z, bx = ca.x + local % ca.z;
@@ -1937,18 +1948,21 @@ __global__ void __launch_bounds__(FB_PAIRS *C, (TMAX == 1) ? 6 : ((TMAX == 2) ? 
         mbar_fence_init();
         mbar_expect_tx(&s_bar, (unsigned)(T * (sizeof(Stage::sc) + sizeof(Stage::sg) + sizeof(Stage::u8))));
     }
-    if (threadIdx.x >= 64 && threadIdx.x < 64 + FB_H) {
-        const int r = (int)threadIdx.x - 64;
+    if (threadIdx.x >= NT - FB_H) { // the CTA's last 16 threads (a 1-channel CTA has only 64)
+        const int r = (int)threadIdx.x - (NT - FB_H);
         s_rowoff[r] = r * FB_U8_STRIDE + ((mis0 + r * pit16) & 15);
     }
     int o_src[TMAX], o_g[TMAX], o_u8[TMAX];
     float nwxa[TMAX], nwxb[TMAX];
+    unsigned mcola[EDGE ? TMAX : 1], mcolb[EDGE ? TMAX : 1]; // EDGE: all ones / 0 for the thread's two columns
 #pragma unroll
     for (int s = 0; s < TMAX; ++s) {
         if (s >= T) break;
         const int ti = tiles_of[s];
         const GatherTile &gt = GT.t[ti];
-        const int tyf = cy0 - gt.y, txf = cx0 - gt.x; // even, >= 2
+        // even; >= 2 unless EDGE, where they may be negative (the tile starts inside the block: the TMA boxes then start at
+        // negative coordinates and everything outside the planes arrives as zeros) or reach past the tile's far edge
+        const int tyf = cy0 - gt.y, txf = cx0 - gt.x;
         const int i0 = (txf >> 1) - 1, ws0 = (tyf >> 1) - 1, sx0 = (i0 >> 2) * 4, u8_a0 = (txf * C) & ~15;
         const int sb = base + s * STAGE;
         if (threadIdx.x == 0) {
@@ -1963,16 +1977,94 @@ __global__ void __launch_bounds__(FB_PAIRS *C, (TMAX == 1) ? 6 : ((TMAX == 2) ? 
         if (!UNIT) {
             if (threadIdx.x >= 32 && threadIdx.x < 32 + FB_H) { // -W_0 row profile of the block
                 const int ty = tyf + (int)threadIdx.x - 32;
-                *reinterpret_cast<float *>(g_gather_smem + sb + O_NWY + 4 * ((int)threadIdx.x - 32)) =
-                    -__ldg(gt.lut + max(min(min(ty, gt.h - 1 - ty), gt.lut_len - 1), 0));
+                float nwy = -__ldg(gt.lut + max(min(min(ty, gt.h - 1 - ty), gt.lut_len - 1), 0));
+                if (EDGE) { // rows the tile does not cover: weight 0 and mask 0
+                    const bool in = ty >= 0 && ty < gt.h;
+                    nwy = in ? nwy : 0.f;
+                    s_mrow[EDGE ? s : 0][(int)threadIdx.x - 32] = in ? 0xFFFFFFFFu : 0u;
+                }
+                *reinterpret_cast<float *>(g_gather_smem + sb + O_NWY + 4 * ((int)threadIdx.x - 32)) = nwy;
             }
             const int lmax = gt.lut_len - 1, txb = txa + 1;
             nwxa[s] = -__ldg(gt.lut + max(min(min(txa, gt.w - 1 - txa), lmax), 0));
             nwxb[s] = -__ldg(gt.lut + max(min(min(txb, gt.w - 1 - txb), lmax), 0));
+            if (EDGE) {
+                const bool ina = txa >= 0 && txa < gt.w, inb = txb >= 0 && txb < gt.w;
+                nwxa[s] = ina ? nwxa[s] : 0.f;
+                nwxb[s] = inb ? nwxb[s] : 0.f;
+                mcola[EDGE ? s : 0] = ina ? 0xFFFFFFFFu : 0u;
+                mcolb[EDGE ? s : 0] = inb ? 0xFFFFFFFFu : 0u;
+            }
         }
     }
     __syncthreads(); // barrier initialised; row profiles and staging offsets visible
     mbar_wait_or_trap(&s_bar, 0);
+    if (EDGE) {
+        // pyrUp's border rules, applied to the staged level-1 windows in place: source column -1 := column 1 and column
+        // w1 := column w1 - 1 (cv2.pyrUp: reflect-101 at the low edge, replicate at the high edge), then the same for rows
+        // (after the columns, so the corners come out as the separable rule has them).  Everything else outside the planes
+        // is TMA zero fill or plane padding, and only ever lies under pixels whose mask is 0.
+        bool fix_cols = false, fix_rows = false;
+#pragma unroll
+        for (int s = 0; s < TMAX; ++s) {
+            if (s >= T) break;
+            const GatherTile &gt = GT.t[tiles_of[s]];
+            const int i0 = ((cx0 - gt.x) >> 1) - 1, ws0 = ((cy0 - gt.y) >> 1) - 1;
+            fix_cols |= (i0 <= -1) || (i0 + FB_PAIRS + 1 >= gt.w1);
+            fix_rows |= (ws0 <= -1) || (ws0 + FB_SRC_ROWS - 1 >= gt.h1);
+            // (the second halves of the need* tests below only keep the indices inside the windows if a listed tile should
+            // ever miss the block altogether -- its masks are all 0 then)
+        }
+        if (fix_cols) { // block-uniform
+#pragma unroll
+            for (int s = 0; s < TMAX; ++s) {
+                if (s >= T) break;
+                const GatherTile &gt = GT.t[tiles_of[s]];
+                const int i0 = ((cx0 - gt.x) >> 1) - 1, sx0 = (i0 >> 2) * 4, gx0 = (i0 >> 3) * 8;
+                const bool needl = i0 <= -1 && i0 >= -(FB_PAIRS + 1), needr = i0 + FB_PAIRS + 1 >= gt.w1 && i0 <= gt.w1 - 1;
+                const int sb = base + s * STAGE;
+                for (int i = threadIdx.x; i < C * FB_SRC_ROWS; i += NT) {
+                    float *rowc = reinterpret_cast<float *>(g_gather_smem + sb + O_SC + i * ROWB); // planes are contiguous: i = c * rows + r
+                    unsigned short *rowg = reinterpret_cast<unsigned short *>(g_gather_smem + sb + O_SG + i * ROWG);
+                    if (needl) {
+                        rowc[-1 - sx0] = rowc[1 - sx0];
+                        rowg[-1 - gx0] = rowg[1 - gx0];
+                    }
+                    if (needr) {
+                        rowc[gt.w1 - sx0] = rowc[gt.w1 - 1 - sx0];
+                        rowg[gt.w1 - gx0] = rowg[gt.w1 - 1 - gx0];
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        if (fix_rows) {
+#pragma unroll
+            for (int s = 0; s < TMAX; ++s) {
+                if (s >= T) break;
+                const GatherTile &gt = GT.t[tiles_of[s]];
+                const int ws0 = ((cy0 - gt.y) >> 1) - 1;
+                const bool needt = ws0 <= -1 && ws0 >= -(FB_SRC_ROWS - 2), needb = ws0 + FB_SRC_ROWS - 1 >= gt.h1 && ws0 <= gt.h1 - 1;
+                const int sb = base + s * STAGE;
+                constexpr int FIX_COLS = FB_G_COLS > FB_SRC_COLS ? FB_G_COLS : FB_SRC_COLS; // the wider of the two windows
+                for (int i = threadIdx.x; i < C * FIX_COLS; i += NT) {
+                    const int ch = i / FIX_COLS, col = i - ch * FIX_COLS;
+                    float *pc = reinterpret_cast<float *>(g_gather_smem + sb + O_SC + ch * CHB) + col;
+                    unsigned short *pg = reinterpret_cast<unsigned short *>(g_gather_smem + sb + O_SG + ch * CHG) + col;
+                    const bool c_col = col < FB_SRC_COLS, g_col = col < FB_G_COLS;
+                    if (needt) {
+                        if (c_col) pc[(-1 - ws0) * FB_SRC_COLS] = pc[(1 - ws0) * FB_SRC_COLS];
+                        if (g_col) pg[(-1 - ws0) * FB_G_COLS] = pg[(1 - ws0) * FB_G_COLS];
+                    }
+                    if (needb) {
+                        if (c_col) pc[(gt.h1 - ws0) * FB_SRC_COLS] = pc[(gt.h1 - 1 - ws0) * FB_SRC_COLS];
+                        if (g_col) pg[(gt.h1 - ws0) * FB_G_COLS] = pg[(gt.h1 - 1 - ws0) * FB_G_COLS];
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
 
     float2 rc0[TMAX], rg0[TMAX], rc1[TMAX], rg1[TMAX];
     auto hrow = [&](int sb, int o, int oh, float2 &oc, float2 &og) { // columns (2i, 2i+1), i = window centre: even form, odd form
@@ -2010,7 +2102,9 @@ __global__ void __launch_bounds__(FB_PAIRS *C, (TMAX == 1) ? 6 : ((TMAX == 2) ? 
             uc[1] = up_odd2(rc1[s], rc2);          ug[1] = up_odd2(rg1[s], rg2);
             float2 v[2], w[2];
             float2 nwy2 = make_float2(0.f, 0.f);
+            uint2 mrow2 = make_uint2(0u, 0u);
             if (!UNIT) nwy2 = gs_f32x2(base + s * STAGE + O_NWY + 8 * k);
+            if (EDGE) mrow2 = *reinterpret_cast<const uint2 *>(&s_mrow[EDGE ? s : 0][2 * k]);
 #pragma unroll
             for (int a = 0; a < 2; ++a) {
                 const int ob = o_u8[s] + (2 * k + a) * FB_U8_STRIDE;
@@ -2025,6 +2119,12 @@ __global__ void __launch_bounds__(FB_PAIRS *C, (TMAX == 1) ? 6 : ((TMAX == 2) ? 
                     const float2 dw = make_float2(__fmul_rn(nd.x, nw.x), __fmul_rn(nd.y, nw.y));
                     v[a] = __ffma2_rn(dw, make_float2(1.f / 256.f, 1.f / 256.f), uc[a]); // uc + dw / 256, rounded once
                     w[a] = make_float2(-nw.x, -nw.y);
+                    if (EDGE) { // pixels the tile does not cover add exactly +0 to both sums (their weight is already 0), whatever
+                                // lies under them in the staged windows (plane padding is not zero-filled and need not be finite)
+                        const unsigned mr = a ? mrow2.y : mrow2.x;
+                        v[a].x = __uint_as_float(__float_as_uint(v[a].x) & mcola[EDGE ? s : 0] & mr);
+                        v[a].y = __uint_as_float(__float_as_uint(v[a].y) & mcolb[EDGE ? s : 0] & mr);
+                    }
                 }
             }
             rc0[s] = rc1[s]; rg0[s] = rg1[s]; rc1[s] = rc2; rg1[s] = rg2;
@@ -2061,10 +2161,11 @@ __global__ void __launch_bounds__(FB_PAIRS *C, (TMAX == 1) ? 6 : ((TMAX == 2) ? 
     }
     __syncthreads();
 
-    // ---- copy the 16 finished rows out (the block is whole: FB_W * C payload bytes per row) ----
-    constexpr int ROW_BYTES = FB_W * C;
-    constexpr int kChunks = (ROW_BYTES + 15 + 15) / 16;
-    for (int i = threadIdx.x; i < FB_H * kChunks; i += NT) {
+    // ---- copy the finished rows out (unless EDGE the block is whole: 16 rows of FB_W * C payload bytes) ----
+    const int n_rows = EDGE ? min(FB_H, P.row_end - cy0) : FB_H;
+    const int ROW_BYTES = EDGE ? min(FB_W, P.out_w - cx0) * C : FB_W * C;
+    constexpr int kChunks = (FB_W * C + 15 + 15) / 16;
+    for (int i = threadIdx.x; i < n_rows * kChunks; i += NT) {
         const int r = i / kChunks, ch = i - r * kChunks;
         uint8_t *grow = P.canvas + (size_t)(cy0 + r) * P.canvas_pitch + (size_t)cx0 * C;
         const int mis = (int)(reinterpret_cast<uintptr_t>(grow) & 15);
@@ -2220,7 +2321,10 @@ static uint64_t fuse_signature(const srf_tile *tiles, int n_tiles, int C, int le
         mix(v, sizeof v);
     }
     for (int k = 0; k < n_luts; ++k) mix(luts[k].values, sizeof(float) * luts[k].len);
-    const int geo[7] = {n_tiles, C, levels, out_h, out_w, row_begin, row_end};
+    // the tuning switches change which kernels a call plans: part of the signature (a cached plan must not outlive a flip)
+    const int switches = (getenv("SRF_GATHER_ONE_CLASS") ? 1 : 0) | (getenv("SRF_GATHER_NO_EDGE") ? 2 : 0) | (getenv("SRF_LEGACY_GATHER") ? 4 : 0) |
+                         (getenv("SRF_GATHER_SERIAL") ? 8 : 0);
+    const int geo[8] = {n_tiles, C, levels, out_h, out_w, row_begin, row_end, switches};
     mix(geo, sizeof geo);
     mix(&canvas, sizeof canvas);
     mix(&canvas_pitch, sizeof canvas_pitch);
@@ -2300,8 +2404,8 @@ int srf_fuse_device(srf_ctx *ctx, const srf_tile *tiles, int n_tiles, int C, int
     // and one class (what can be proven about every block of the cell) ----
     const int rb = std::max(row_begin, 0), re = std::min(row_end, out_h);
     std::vector<GatherCell> cells[GC_CLASSES];
-    int class_blocks[GC_CLASSES] = {0, 0, 0, 0, 0, 0};
-    double class_bytes[GC_CLASSES] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    int class_blocks[GC_CLASSES] = {};
+    double class_bytes[GC_CLASSES] = {};
     std::vector<GatherTile> gtiles(n_tiles);
     for (int i = 0; i < n_tiles; ++i) {
         const GroupDev &g = groups[tile_group[i]].dev;
@@ -2384,7 +2488,10 @@ int srf_fuse_device(srf_ctx *ctx, const srf_tile *tiles, int n_tiles, int C, int
                                (gt.y + gt.h - 1 - (y1 - 1) >= F);
                     }
                 }
-                rc.cls = !all_full ? (T <= 2 ? GC_G2 : GC_G4) : (T == 1 ? (unit ? GC_U1 : GC_F1) : (T == 2 ? GC_F2 : GC_F4));
+                bool edge_ok = classify && T >= 1 && getenv("SRF_GATHER_NO_EDGE") == nullptr; // block-independent conditions
+                for (int s = 0; s < T && edge_ok; ++s) edge_ok = gather_slot_edge_ok(gtiles[cell.tile[s]], y0, x0);
+                rc.cls = all_full ? (T == 1 ? (unit ? GC_U1 : GC_F1) : (T == 2 ? GC_F2 : GC_F4))
+                                  : (edge_ok ? (T <= 2 ? GC_E2 : GC_E4) : (T <= 2 ? GC_G2 : GC_G4));
                 raw.push_back(rc);
             }
         if (cells_ok) {
@@ -2735,6 +2842,7 @@ int srf_fuse_device(srf_ctx *ctx, const srf_tile *tiles, int n_tiles, int C, int
             // caller's stream, the others fork onto side streams and join back -- short launches then fill each other's
             // ramps and tails instead of queueing (a band of an 8-rank job is six launches of a few hundred CTAs each).
             // Under stream capture the fork / join events become graph edges.  Serial while per-kernel timing is on.
+            static_assert(GC_CLASSES - 1 <= srf_ctx::kForkStreams, "one side stream per class but the biggest");
             int main_cls = 0;
             for (int cls = 1; cls < GC_CLASSES; ++cls)
                 if (class_blocks[cls] > class_blocks[main_cls]) main_cls = cls;
@@ -2773,6 +2881,8 @@ int srf_fuse_device(srf_ctx *ctx, const srf_tile *tiles, int n_tiles, int C, int
                     case GC_F2: SRF_GATHER_LAUNCH((k_gather_full<3, 2, false>), 2, 3); break;
                     case GC_F4: SRF_GATHER_LAUNCH((k_gather_full<3, 4, false>), 4, 3); break;
                     case GC_G2: SRF_GATHER_LAUNCH((k_gather<3, 2>), 2, 3); break;
+                    case GC_E2: SRF_GATHER_LAUNCH((k_gather_full<3, 2, false, true>), 2, 3); break;
+                    case GC_E4: SRF_GATHER_LAUNCH((k_gather_full<3, 4, false, true>), 4, 3); break;
                     default: SRF_GATHER_LAUNCH((k_gather<3, 4>), 4, 3); break;
                     }
                 } else {
@@ -2782,6 +2892,8 @@ int srf_fuse_device(srf_ctx *ctx, const srf_tile *tiles, int n_tiles, int C, int
                     case GC_F2: SRF_GATHER_LAUNCH((k_gather_full<1, 2, false>), 2, 1); break;
                     case GC_F4: SRF_GATHER_LAUNCH((k_gather_full<1, 4, false>), 4, 1); break;
                     case GC_G2: SRF_GATHER_LAUNCH((k_gather<1, 2>), 2, 1); break;
+                    case GC_E2: SRF_GATHER_LAUNCH((k_gather_full<1, 2, false, true>), 2, 1); break;
+                    case GC_E4: SRF_GATHER_LAUNCH((k_gather_full<1, 4, false, true>), 4, 1); break;
                     default: SRF_GATHER_LAUNCH((k_gather<1, 4>), 4, 1); break;
                     }
                 }

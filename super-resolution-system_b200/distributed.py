@@ -18,6 +18,38 @@ from ._arrays import torch
 IQA_HALO = 5  # radius of the 11-tap SSIM window
 
 
+def _cpulist(text: str) -> set:
+    cpus = set()
+    for part in text.strip().split(","):
+        if part:
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_host_to_device_node(device_index: int, sysfs: str = "/sys/bus/pci/devices"):
+    """Pin the calling process to the host cores next to GPU `device_index` (its PCIe root's NUMA node), so that the
+    pinned buffers it allocates afterwards are first-touched on that node and host<->device copies do not cross the
+    socket interconnect.  Call before allocating pinned memory.  Returns {"node", "cpus"} or None when the box gives
+    no locality (single node, no sysfs entry, or the allowed cpu set does not reach that node) -- then nothing changes."""
+    import os
+    try:
+        p = torch.cuda.get_device_properties(device_index)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        with open(f"{sysfs}/{bdf}/numa_node") as f:
+            node = int(f.read())
+        with open(f"{sysfs}/{bdf}/local_cpulist") as f:
+            local = _cpulist(f.read())
+        allowed = os.sched_getaffinity(0)
+        use = local & allowed
+        if node < 0 or not use or use == allowed:
+            return None
+        os.sched_setaffinity(0, use)
+        return {"node": node, "cpus": len(use)}
+    except (OSError, ValueError, AttributeError):
+        return None
+
+
 def band(rank: int, world: int, rows: int) -> Tuple[int, int]:
     """canvas rows [r0, r1) owned by `rank`: ceil(rows / world) rows each, the last band takes what is left"""
     per = -(-rows // world)

@@ -114,6 +114,28 @@ def test_fusion_vs_oracle_levels(srs, oracle, levels):
     assert mx <= 1 and exact >= 0.999, (levels, mx, exact)
 
 
+@pytest.mark.parametrize("c", [1, 3])
+def test_fusion_every_gather_class(srs, oracle, c):
+    """tiles wide enough for whole interior blocks (128 x 16 pixels) on an even grid: unit-weight cores, 1 / 2 / 4-tile interior
+    cells, and the edge cells (tile edges inside a block, the canvas edge) all go through the lean gather kernels, gray and RGB"""
+    rng = np.random.default_rng(40 + c)
+    tiles, pos = _grid_case(rng, 640, 704, 2, 2, 500, 520, c=c)
+    out_hw = (1100, 1190)  # bottom / right tiles overhang the canvas
+    infos = [srs.TileInfo(t, x, y, 0, 0) for t, (y, x) in zip(tiles, pos)]
+    for levels, kind in ((3, "cosine"), (5, "sigmoid")):  # sigmoid: the weight at a tile's border is not 0
+        got = srs.BlendingModule(num_levels=levels).laplacian_fusion(infos, output_shape=out_hw, weight_type=srs.WeightType(kind))
+        want = oracle.fusion_oracle.laplacian_fuse(tiles, pos, out_hw, levels, kind, "c")
+        mx, exact = canvas_agreement(got, want)
+        assert mx <= 1 and exact >= 0.999, (c, levels, kind, mx, exact)
+    import os
+    os.environ["SRF_GATHER_ONE_CLASS"] = "1"  # the same bytes through the generic kernel alone
+    try:
+        generic = srs.BlendingModule(num_levels=5).laplacian_fusion(infos, output_shape=out_hw, weight_type=srs.WeightType("sigmoid"))
+    finally:
+        del os.environ["SRF_GATHER_ONE_CLASS"]
+    assert np.array_equal(generic, got)
+
+
 def test_fusion_odd_positions_and_sizes(srs, oracle):
     """odd tile origins flip the pyrUp phase relative to the canvas blocks; odd sizes hit the 2n-1 pyrUp case"""
     rng = np.random.default_rng(21)
