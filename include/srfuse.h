@@ -59,6 +59,8 @@ void srf_destroy(srf_ctx *ctx);
 int srf_sync(srf_ctx *ctx, void *stream);
 /* number of kernels this ctx has launched since creation (bench.py's gpu_launches) */
 int64_t srf_launch_count(const srf_ctx *ctx);
+/* how many srf_laplacian_fuse calls were served by launching the captured CUDA graph of an identical earlier call */
+int64_t srf_graph_replays(const srf_ctx *ctx);
 /* bytes the last *_host entry point copied host->device / device->host (image data only) */
 int srf_last_transfer_bytes(const srf_ctx *ctx, size_t *h2d, size_t *d2h);
 /* bytes of device workspace currently held */

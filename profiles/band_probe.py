@@ -60,6 +60,15 @@ def main():
         b.record()
         torch.cuda.synchronize()
         ms = a.elapsed_time(b) / args.steps
+        # the same steps with the bench's per-step read-back of the sums (a host round trip every step): the difference is
+        # the launch latency a step exposes once the host waits for its result before enqueueing the next one
+        a.record()
+        for _ in range(args.steps):
+            step()
+            d_sums.tolist()
+        b.record()
+        torch.cuda.synchronize()
+        ms_synced = a.elapsed_time(b) / args.steps
         native.profile_enable(ctx, True)
         native.profile_read(ctx)
         for _ in range(args.steps):
@@ -69,7 +78,7 @@ def main():
         for name, t, _ in native.profile_read(ctx):
             agg[name] = agg.get(name, 0.0) + t / args.steps
         native.profile_enable(ctx, False)
-        rec = {"rank": rank, "band": [r0, r1], "rows": r1 - r0, "tiles": len(mine), "ms": round(ms, 4),
+        rec = {"rank": rank, "band": [r0, r1], "rows": r1 - r0, "tiles": len(mine), "ms": round(ms, 4), "ms_with_per_step_readback": round(ms_synced, 4),
                "kernels": {k: round(v, 4) for k, v in sorted(agg.items(), key=lambda kv: -kv[1])}}
         out.append(rec)
         print(json.dumps(rec), flush=True)

@@ -54,6 +54,7 @@ SIGNATURES = {
     "srf_destroy": (None, [c_void_p]),
     "srf_sync": (c_int, [c_void_p, c_void_p]),
     "srf_launch_count": (c_int64, [c_void_p]),
+    "srf_graph_replays": (c_int64, [c_void_p]),
     "srf_workspace_bytes": (c_size_t, [c_void_p]),
     "srf_last_transfer_bytes": (c_int, [c_void_p, P(c_size_t), P(c_size_t)]),
     "srf_last_device_ms": (C.c_float, [c_void_p]),

@@ -245,6 +245,7 @@ extern "C" int srf_sync(srf_ctx *ctx, void *stream)
 }
 
 extern "C" int64_t srf_launch_count(const srf_ctx *ctx) { return ctx ? ctx->launches : -1; }
+extern "C" int64_t srf_graph_replays(const srf_ctx *ctx) { return ctx ? ctx->graph_replays : -1; }
 
 extern "C" int srf_last_transfer_bytes(const srf_ctx *c, size_t *h2d, size_t *d2h)
 {

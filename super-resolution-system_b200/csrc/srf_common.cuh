@@ -47,6 +47,7 @@ struct srf_ctx {
     int sm_count = 148;
     std::string last_error;
     int64_t launches = 0;
+    int64_t graph_replays = 0;
     size_t last_h2d = 0, last_d2h = 0; // bytes the last *_host entry point moved over PCIe
     // grow-only device workspaces, by role
     srf_buffer ws_pyr;      // per-tile G/C pyramids + weight pyramids

@@ -482,6 +482,44 @@ def test_fusion_plan_reuse_and_misaligned_device_tiles(srs):
     assert np.array_equal(bm.laplacian_fusion(hplan), host)
 
 
+def test_repeated_fuse_call_is_served_by_the_captured_graph(srs):
+    """consecutive identical device calls on a real stream: the second is captured, the later ones are one graph launch each
+    (srf_graph_replays counts them -- a signature that never repeats would silently re-plan every call), and a replay
+    reads the tiles' CURRENT pixels"""
+    import torch
+    rng = np.random.default_rng(44)
+    tiles, pos = _grid_case(rng, 320, 384, 2, 2, 250, 300)
+    out_hw = (570, 684)
+    bm = srs.BlendingModule(num_levels=5)
+    dev_tiles = [torch.from_numpy(t).cuda() for t in tiles]
+    plan = bm.plan_fusion([srs.TileInfo(d, x, y, 0, 0) for d, (y, x) in zip(dev_tiles, pos)], output_shape=out_hw)
+    out = torch.empty(out_hw + (3,), dtype=torch.uint8, device="cuda")
+    lib, ctx = srs._native.load(), srs._native.context(0)
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        r0 = lib.srf_graph_replays(ctx)
+        for _ in range(5):
+            bm.laplacian_fusion(plan, out=out)
+        side.synchronize()
+        assert lib.srf_graph_replays(ctx) - r0 >= 3
+        first = out.cpu().numpy().copy()
+        for d, t in zip(dev_tiles, tiles):  # new pixels behind the same pointers
+            d.copy_(torch.from_numpy(np.ascontiguousarray(t[::-1, ::-1])), non_blocking=False)
+        r1 = lib.srf_graph_replays(ctx)
+        bm.laplacian_fusion(plan, out=out)
+        side.synchronize()
+        assert lib.srf_graph_replays(ctx) == r1 + 1
+        second = out.cpu().numpy().copy()
+        r2 = lib.srf_graph_replays(ctx)
+        bm.laplacian_fusion(plan, row_range=(100, 400), out=out)  # another band: a new plan, not a replay
+        side.synchronize()
+        assert lib.srf_graph_replays(ctx) == r2
+    infos = [srs.TileInfo(t, x, y, 0, 0) for t, (y, x) in zip(tiles, pos)]
+    assert np.array_equal(first, bm.laplacian_fusion(infos, output_shape=out_hw))
+    flipped = [srs.TileInfo(np.ascontiguousarray(t[::-1, ::-1]), x, y, 0, 0) for t, (y, x) in zip(tiles, pos)]
+    assert np.array_equal(second, bm.laplacian_fusion(flipped, output_shape=out_hw))
+
+
 def test_fusion_graph_replay_and_device_sums(srs):
     """a repeated device call on a side stream is captured into a CUDA graph and replayed; it must track the tile
     CONTENTS (same addresses, new pixels) and agree with the host path; the enqueue-only IQA agrees with the sync one"""
