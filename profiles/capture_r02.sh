@@ -10,6 +10,6 @@ python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/r02
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r02_ncu_launches.csv \
     python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/r02_ncu_launches.log 2>&1
 # full sections of every launch of ONE step (the first call's weight-pyramid launches are skipped by the -k filter)
-ncu --set full --clock-control none --import-source on -k regex:"k_gather|k_final|k_psnr_ssim|k_down_u8|k_down_u16|k_up_level|k_down_f32s" -c 27 -f \
+ncu --set full --clock-control none --import-source on -k regex:"k_gather|k_final|k_psnr_ssim|k_down_u8|k_down_u16|k_up_level|k_down_f32s" -c 30 -f \
     -o gpurun_out/r02_ncu_full python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/r02_ncu_full.log 2>&1
 ls -la gpurun_out/r02_*

@@ -37,8 +37,11 @@ def main():
     col = {h: i for i, h in enumerate(head)}
     stalls = [h for h in head if "issue_stalled" in h and "per_issue_active" in h]
     lines, traffic = [], {}
+    steps_seen = 0  # a step starts with k_down_u8: the traffic table sums the FIRST step only (the capture may run into the next)
     for r in body:
         name = r[col["Kernel Name"]]
+        if "k_down_u8" in name:
+            steps_seen += 1
         lines.append(f"Kernel Name = {name}")
         for w in WANT + stalls:
             if w in col:
@@ -47,7 +50,7 @@ def main():
         table = next((t for k, t in NAMES if k in name), None)
         if "k_down_f32s<1>" in name.replace("(bool)", "").replace(" ", ""):
             table = None  # weight-pyramid launches: first call only (cached afterwards), not part of a steady-state step
-        if table:
+        if table and steps_seen <= 1:
             def val(metric):
                 return float(r[col[metric]].replace(",", "")) * UNIT.get(units[col[metric]], 1.0)
             t = traffic.setdefault(table, {"dram_bytes_per_step": 0.0, "ncu_time_ms": 0.0, "launches": 0})
