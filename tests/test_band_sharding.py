@@ -131,3 +131,41 @@ def test_band_starts_are_even_and_bands_random_layouts(srs):
                     assert e0 % 2 == 0 and e0 <= max(b[0] - 5, 0) and e1 == min(b[1] + 5, H)
                     sel = d.tiles_for_rows(pos, [th] * len(pos), e0, e1)
                     assert sel == [i for i, (y, _) in enumerate(pos) if y < e1 and y + th > e0]
+
+
+def test_fuse_input_rows_is_a_sufficient_cone(srs, oracle):
+    """srf_fuse_input_rows (host arithmetic behind BandedHostFuser: which tile rows a band's ranks must hold): scrambling
+    every tile pixel OUTSIDE the rows / columns it returns must not change one byte of the band in the reference algorithm,
+    and the cone must stay near the reach SURVEY section 8c measured (about 3.25 * 2^(levels-1) rows a side; the planner
+    rounds to whole rows of the coarsest level and to its kernels' row batches, so allow 6 * 2^(levels-1) + 8)"""
+    import ctypes as C
+    lib = srs._native.load()
+    rng = np.random.default_rng(11)
+    from helpers import synth
+    for case in range(10):
+        levels = int(rng.integers(2, 6))
+        th, tw = int(rng.integers(90, 200)) & ~1, int(rng.integers(90, 200)) & ~1
+        sy, sx = int(th * rng.uniform(0.6, 0.9)), int(tw * rng.uniform(0.6, 0.9))
+        pos = [(j * sy, i * sx) for j in range(3) for i in range(2)]
+        H, W = 2 * sy + th - int(rng.integers(0, 30)), sx + tw - int(rng.integers(0, 30))  # last row / column overhangs
+        tiles = [synth(rng, th, tw) for _ in pos]
+        rb = int(rng.integers(0, H - 20))
+        re = int(rng.integers(rb + 1, H + 1))
+        want = oracle.fusion_oracle.laplacian_fuse(tiles, pos, (H, W), levels, "cosine", "c")
+        scrambled = []
+        for t, (y, x) in zip(tiles, pos):
+            a, b, c = C.c_int(), C.c_int(), C.c_int()
+            assert lib.srf_fuse_input_rows(th, tw, y, x, levels, H, W, rb, re, C.byref(a), C.byref(b), C.byref(c)) == 0
+            r0, r1, cols = a.value, b.value, c.value
+            assert 0 <= r0 <= r1 <= th and 0 <= cols <= tw
+            s = rng.integers(0, 256, t.shape, dtype=np.uint8)
+            if r1 > r0:
+                s[r0:r1, :cols] = t[r0:r1, :cols]
+                lo, hi = max(rb, y) - y, min(re, y + th, H) - y  # the tile rows the band itself covers
+                reach = 6 * 2 ** (levels - 1) + 8
+                assert r0 >= lo - reach and r1 <= hi + reach, (case, levels, r0, r1, lo, hi)
+            else:
+                assert y >= re or y + th <= rb or x >= W
+            scrambled.append(s)
+        got = oracle.fusion_oracle.laplacian_fuse(scrambled, pos, (H, W), levels, "cosine", "c")
+        assert np.array_equal(got[rb:re], want[rb:re]), (case, levels, rb, re)
