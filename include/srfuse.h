@@ -152,6 +152,18 @@ int srf_laplacian_fuse_host(srf_ctx *ctx, const srf_tile *tiles, int n_tiles, in
 int srf_fuse_input_rows(int tile_h, int tile_w, int tile_y, int tile_x, int levels, int out_h, int out_w, int row_begin,
                         int row_end, int *row0, int *row1, int *cols);
 
+/* diagnostic, host only, no context, no device work: the plan the canvas gather of srf_laplacian_fuse uses for this
+ * geometry -- the band's 128 x 16-pixel blocks (rows counted from max(row_begin, 0)) cut into rectangular cells that share
+ * one ordered list of covering tiles and one class.  Writes min(*n_cells, cap) records of 12 ints
+ * {class, bx0, by0, nbx, nby, T, tile0, tile1, tile2, tile3, first, 0} and the number of cells.  Classes: 0 one tile,
+ * interior, unit weight; 1 one tile interior; 2 two tiles interior; 3 three / four tiles interior; 4 / 5 anything else
+ * with <= 2 / <= 4 tiles (generic arithmetic); 6 / 7 cells with a tile, canvas or band edge inside them that still run
+ * the interior arithmetic (<= 2 / <= 4 tiles).  SRF_ERR_UNSUPPORTED when the call would take the general kernel instead
+ * (more than 48 tiles, a tile with fewer than 3 pyramid levels, more than 4 tiles over one block, an empty band).
+ * tiles[i].data is not read. */
+int srf_gather_plan(const srf_tile *tiles, int n_tiles, int channels, int levels, const srf_weight_lut *luts, int n_luts,
+                    int out_h, int out_w, int row_begin, int row_end, int *cells, int cap, int *n_cells);
+
 /* ---- full-reference IQA -------------------------------------------------------------------------------- */
 /* partial sums of one image pair over a row band; additive across bands / ranks */
 typedef struct srf_iqa_sums {

@@ -80,6 +80,7 @@ SIGNATURES = {
     "srf_laplacian_fuse_host": (c_int, [c_void_p, P(srf_tile), c_int, c_int, c_int, P(srf_weight_lut), c_int, c_int,
                                         c_int, c_void_p, c_size_t, c_int, c_int]),
     "srf_fuse_input_rows": (c_int, [c_int] * 9 + [P(c_int), P(c_int), P(c_int)]),
+    "srf_gather_plan": (c_int, [P(srf_tile), c_int, c_int, c_int, P(srf_weight_lut), c_int, c_int, c_int, c_int, c_int, P(c_int), c_int, P(c_int)]),
     "srf_psnr_ssim": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, c_int, c_int, c_int, c_int, c_int,
                               C.c_double, c_int, c_int, c_int, P(srf_iqa_sums), c_void_p]),
     "srf_psnr_ssim_enqueue": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, c_int, c_int, c_int, c_int, c_int,
@@ -120,7 +121,7 @@ _ctx = {}
 _ctx_locks = {}  # srf_ctx address -> RLock: calls on one ctx must not overlap (include/srfuse.h), and ctypes drops the GIL
 
 # entry points that do NOT take an srf_ctx* first (nothing to serialise)
-_NO_CTX = {"srf_fuse_input_rows", "srf_version", "srf_status_string", "srf_last_error", "srf_create", "srf_tile_positions", "srf_tile_overlaps",
+_NO_CTX = {"srf_fuse_input_rows", "srf_gather_plan", "srf_version", "srf_status_string", "srf_last_error", "srf_create", "srf_tile_positions", "srf_tile_overlaps",
            "srf_weight_profile", "srf_iqa_finish", "srf_window_ssim_shape", "srf_resize_linear_taps", "srf_resize_cubic_taps"}
 
 

@@ -309,6 +309,37 @@ class BlendingModule:
         _native.check(rc, ctx)
         return canvas, sums
 
+    def gather_plan(self, sizes_hw, positions_yx, output_shape, weight_type: WeightType = WeightType.COSINE, row_range=None,
+                    channels: int = 3, levels: Optional[int] = None):
+        """Diagnostic (host arithmetic only, no GPU): the cells the canvas gather of laplacian_fusion would use for tiles of
+        these sizes at these positions -- a list of dicts {cls, bx0, by0, nbx, nby, tiles, first} in 128 x 16-pixel block
+        units (rows counted from the band's first row), or None when the call would take the general kernel
+        (include/srfuse.h: srf_gather_plan)."""
+        n = len(sizes_hw)
+        lut_index, luts = {}, []
+        c_tiles = (_native.srf_tile * n)()
+        for i, ((h, w), (y, x)) in enumerate(zip(sizes_hw, positions_yx)):
+            prof = self._profile(int(h), int(w), weight_type)
+            if id(prof) not in lut_index:
+                lut_index[id(prof)] = len(luts)
+                luts.append(prof)
+            c_tiles[i] = _native.srf_tile(None, int(w) * channels, int(h), int(w), int(y), int(x), lut_index[id(prof)])
+        c_luts = (_native.srf_weight_lut * len(luts))(*[_native.srf_weight_lut(p.ctypes.data, len(p)) for p in luts])
+        out_h, out_w = int(output_shape[0]), int(output_shape[1])
+        r0, r1 = (0, out_h) if row_range is None else (int(row_range[0]), int(row_range[1]))
+        lib = _native.load()
+        count = C.c_int(0)
+        lv = self.num_levels if levels is None else int(levels)
+        rc = lib.srf_gather_plan(c_tiles, n, channels, lv, c_luts, len(luts), out_h, out_w, r0, r1, None, 0, C.byref(count))
+        if rc == -5:  # SRF_ERR_UNSUPPORTED: the general kernel takes this geometry
+            return None
+        _native.check(rc, None)
+        buf = (C.c_int * (12 * max(count.value, 1)))()
+        _native.check(lib.srf_gather_plan(c_tiles, n, channels, lv, c_luts, len(luts), out_h, out_w, r0, r1, buf, count.value, C.byref(count)), None)
+        rec = np.frombuffer(buf, dtype=np.int32).reshape(-1, 12)[: count.value]
+        return [{"cls": int(r[0]), "bx0": int(r[1]), "by0": int(r[2]), "nbx": int(r[3]), "nby": int(r[4]),
+                 "tiles": [int(t) for t in r[6:6 + min(int(r[5]), 4)]], "first": int(r[10])} for r in rec]
+
     # ------------------------------------------------------------------ explicitly out of scope
     def _out_of_scope(self, name):
         raise NotImplementedError(f"BlendingModule.{name} is outside the B200 hot path (SURVEY.md section 8); "

@@ -2308,6 +2308,189 @@ extern "C" int srf_fuse_input_rows(int tile_h, int tile_w, int tile_y, int tile_
     return SRF_OK;
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// The gather's plan (host only, no device work): the band's blocks cut into cells, each with its ordered tile list and
+// its class.  Returns false when some block has more than GC_MAX_T covering tiles (the general kernel takes the call).
+// Shared by srf_fuse_device and by the diagnostic entry point srf_gather_plan (tests check the plan on the CPU).
+// ------------------------------------------------------------------------------------------------------------
+static bool srf_build_gather_cells(const srf_tile *tiles, int n_tiles, const std::vector<GatherTile> &gtiles, const srf_weight_lut *luts, int C,
+                                   int out_w, int rb, int re, std::vector<GatherCell> (&cells)[GC_CLASSES], int (&class_blocks)[GC_CLASSES],
+                                   double (&class_bytes)[GC_CLASSES])
+{
+    bool cells_ok = true;
+    {
+        const bool classify = getenv("SRF_GATHER_ONE_CLASS") == nullptr; // tuning switch: everything through the generic kernel
+        const int nbx = srf_ceil_div(out_w, FB_W), nby = srf_ceil_div(re - rb, FB_H);
+        std::vector<int> xs = {0, nbx}, ys = {0, nby};
+        auto add_edge = [](std::vector<int> &v, long long e, int org, int lim, int blk, int nmax) {
+            long long rel = std::min<long long>(std::max<long long>(e, org), lim) - org; // clipped to the band / canvas
+            v.push_back((int)std::min<long long>(rel / blk, nmax));
+            v.push_back((int)std::min<long long>((rel + blk - 1) / blk, nmax));
+        };
+        for (int i = 0; i < n_tiles; ++i) {
+            // tile edges (the tile list changes there), the 2-pixel margins inside them (the source windows of the first /
+            // last interior block must not poke out of the level-1 plane) and the feather width (inside it W_0 == 1).
+            // Superfluous cuts are merged away below; a missing cut only sends a cell to the generic class.
+            const long long x0 = tiles[i].x, x1 = x0 + tiles[i].w, y0 = tiles[i].y, y1 = y0 + tiles[i].h, F = luts[tiles[i].lut].len - 1;
+            for (long long e : {x0, x0 + 2, x0 + F, x1 - F, x1 - 2, x1}) add_edge(xs, e, 0, out_w, FB_W, nbx);
+            for (long long e : {y0, y0 + 2, y0 + F, y1 - F, y1 - 2, y1}) add_edge(ys, e, rb, re, FB_H, nby);
+        }
+        std::sort(xs.begin(), xs.end());
+        xs.erase(std::unique(xs.begin(), xs.end()), xs.end());
+        std::sort(ys.begin(), ys.end());
+        ys.erase(std::unique(ys.begin(), ys.end()), ys.end());
+        struct RawCell {
+            GatherCell c;
+            int cls;
+        };
+        std::vector<RawCell> raw;
+        for (size_t j = 0; j + 1 < ys.size() && cells_ok; ++j)
+            for (size_t i = 0; i + 1 < xs.size(); ++i) {
+                const int y0 = rb + ys[j] * FB_H, y1 = std::min(rb + ys[j + 1] * FB_H, re);
+                const int x0 = xs[i] * FB_W, x1 = std::min(xs[i + 1] * FB_W, out_w);
+                RawCell rc;
+                memset(&rc, 0, sizeof rc);
+                GatherCell &cell = rc.c;
+                cell.bx0 = xs[i];
+                cell.by0 = ys[j];
+                cell.nbx = xs[i + 1] - xs[i];
+                cell.nby = ys[j + 1] - ys[j];
+                int T = 0;
+                for (int t = 0; t < n_tiles; ++t)
+                    if (tiles[t].y < y1 && tiles[t].y + tiles[t].h > y0 && tiles[t].x < x1 && tiles[t].x + tiles[t].w > x0) {
+                        if (T < GC_MAX_T) cell.tile[T] = t;
+                        ++T;
+                    }
+                if (T > GC_MAX_T) { // more than four tiles over one block: the general kernel takes the whole call
+                    cells_ok = false;
+                    break;
+                }
+                cell.T = T;
+                // interior for every tile?  The conditions are intervals per axis, so the cell's four corner blocks decide.
+                bool all_full = classify && T >= 1, unit = classify && T == 1;
+                for (int s = 0; s < T && all_full; ++s) {
+                    const GatherTile &gt = gtiles[cell.tile[s]];
+                    for (int cy = 0; cy < 2 && all_full; ++cy)
+                        for (int cx = 0; cx < 2 && all_full; ++cx) {
+                            const int by = cy ? cell.by0 + cell.nby - 1 : cell.by0, bx = cx ? cell.bx0 + cell.nbx - 1 : cell.bx0;
+                            const int cy0 = rb + by * FB_H, cx0 = bx * FB_W;
+                            const FinalGeo q = gather_geo(gt, cy0, std::min(cy0 + FB_H, re), cx0, std::min(cx0 + FB_W, out_w), C);
+                            all_full = gather_slot_full(gt, q, cy0, cx0);
+                        }
+                    if (unit) { // W_0 == 1.0f over the whole cell: every pixel at least feather-width inside, and the profile ends at 1
+                        const srf_weight_lut &L = luts[tiles[cell.tile[s]].lut];
+                        const int F = L.len - 1;
+                        unit = L.values[F] == 1.0f && (x0 - gt.x >= F) && (gt.x + gt.w - 1 - (x1 - 1) >= F) && (y0 - gt.y >= F) &&
+                               (gt.y + gt.h - 1 - (y1 - 1) >= F);
+                    }
+                }
+                bool edge_ok = classify && T >= 1 && getenv("SRF_GATHER_NO_EDGE") == nullptr; // block-independent conditions
+                for (int s = 0; s < T && edge_ok; ++s) edge_ok = gather_slot_edge_ok(gtiles[cell.tile[s]], y0, x0);
+                rc.cls = all_full ? (T == 1 ? (unit ? GC_U1 : GC_F1) : (T == 2 ? GC_F2 : GC_F4))
+                                  : (edge_ok ? (T <= 2 ? GC_E2 : GC_E4) : (T <= 2 ? GC_G2 : GC_G4));
+                raw.push_back(rc);
+            }
+        if (cells_ok) {
+            auto same_list = [](const GatherCell &a, const GatherCell &b) {
+                return a.T == b.T && a.tile[0] == b.tile[0] && a.tile[1] == b.tile[1] && a.tile[2] == b.tile[2] && a.tile[3] == b.tile[3];
+            };
+            // merge horizontally (cells arrive row by row, left to right), then vertically
+            std::vector<RawCell> rows;
+            for (const RawCell &rc : raw) {
+                if (rc.c.nbx <= 0 || rc.c.nby <= 0) continue;
+                if (!rows.empty()) {
+                    RawCell &pr = rows.back();
+                    if (pr.cls == rc.cls && pr.c.by0 == rc.c.by0 && pr.c.nby == rc.c.nby && pr.c.bx0 + pr.c.nbx == rc.c.bx0 && same_list(pr.c, rc.c)) {
+                        pr.c.nbx += rc.c.nbx;
+                        continue;
+                    }
+                }
+                rows.push_back(rc);
+            }
+            std::vector<RawCell> merged;
+            std::vector<char> used(rows.size(), 0);
+            for (size_t i = 0; i < rows.size(); ++i) {
+                if (used[i]) continue;
+                RawCell cur = rows[i];
+                for (size_t k = i + 1; k < rows.size(); ++k) {
+                    if (used[k]) continue;
+                    const RawCell &nx = rows[k];
+                    if (nx.c.by0 > cur.c.by0 + cur.c.nby) break; // rows are ordered by by0: nothing further down can touch
+                    if (nx.cls == cur.cls && nx.c.by0 == cur.c.by0 + cur.c.nby && nx.c.bx0 == cur.c.bx0 && nx.c.nbx == cur.c.nbx && same_list(nx.c, cur.c)) {
+                        cur.c.nby += nx.c.nby;
+                        used[k] = 1;
+                    }
+                }
+                merged.push_back(cur);
+            }
+            for (RawCell &rc : merged) {
+                const int cls = rc.cls;
+                const int y0 = rb + rc.c.by0 * FB_H, y1 = std::min(rb + (rc.c.by0 + rc.c.nby) * FB_H, re);
+                const int x0 = rc.c.bx0 * FB_W, x1 = std::min((rc.c.bx0 + rc.c.nbx) * FB_W, out_w);
+                rc.c.first = class_blocks[cls];
+                class_blocks[cls] += rc.c.nbx * rc.c.nby;
+                class_bytes[cls] += (double)(y1 - y0) * (x1 - x0) * C * (3.0 * rc.c.T + 1.0);
+                cells[cls].push_back(rc.c);
+            }
+        }
+    }
+    return cells_ok;
+}
+
+extern "C" int srf_gather_plan(const srf_tile *tiles, int n_tiles, int channels, int levels, const srf_weight_lut *luts, int n_luts, int out_h,
+                               int out_w, int row_begin, int row_end, int *cells_out, int cap, int *n_cells)
+{
+    if (!tiles || n_tiles < 1 || !luts || n_luts < 1 || !n_cells || (channels != 1 && channels != 3) || levels < 1 || out_h < 1 || out_w < 1 ||
+        cap < 0 || (cap > 0 && !cells_out))
+        return SRF_ERR_ARG;
+    *n_cells = 0;
+    const int rb = std::max(row_begin, 0), re = std::min(row_end, out_h);
+    if (rb >= re || n_tiles > FINAL_TMA_TILES) return SRF_ERR_UNSUPPORTED;
+    std::vector<GatherTile> gtiles(n_tiles);
+    for (int i = 0; i < n_tiles; ++i) {
+        if (tiles[i].lut < 0 || tiles[i].lut >= n_luts || tiles[i].h < 1 || tiles[i].w < 1 || !luts[tiles[i].lut].values || luts[tiles[i].lut].len < 1)
+            return SRF_ERR_ARG;
+        int h = tiles[i].h, w = tiles[i].w, n = 1, h1 = 0, w1 = 0;
+        while (n < levels && h >= 2 && w >= 2) { // the pyramid of srf_fuse_device: stops when a side reaches 1
+            h = (h + 1) / 2;
+            w = (w + 1) / 2;
+            if (n == 1) {
+                h1 = h;
+                w1 = w;
+            }
+            ++n;
+        }
+        if (n < 3) return SRF_ERR_UNSUPPORTED; // 1- / 2-level tiles take the general kernel
+        GatherTile &gt = gtiles[i];
+        gt.y = tiles[i].y;
+        gt.x = tiles[i].x;
+        gt.h = tiles[i].h;
+        gt.w = tiles[i].w;
+        gt.h1 = h1;
+        gt.w1 = w1;
+        gt.lut_len = luts[tiles[i].lut].len;
+        gt.pad = 0;
+        gt.lut = nullptr;
+    }
+    std::vector<GatherCell> cells[GC_CLASSES];
+    int class_blocks[GC_CLASSES] = {};
+    double class_bytes[GC_CLASSES] = {};
+    if (!srf_build_gather_cells(tiles, n_tiles, gtiles, luts, channels, out_w, rb, re, cells, class_blocks, class_bytes)) return SRF_ERR_UNSUPPORTED;
+    int n = 0;
+    for (int cls = 0; cls < GC_CLASSES; ++cls)
+        for (const GatherCell &c : cells[cls]) {
+            if (n < cap) {
+                int *o = cells_out + (size_t)n * 12;
+                o[0] = cls; o[1] = c.bx0; o[2] = c.by0; o[3] = c.nbx; o[4] = c.nby; o[5] = c.T;
+                o[6] = c.tile[0]; o[7] = c.tile[1]; o[8] = c.tile[2]; o[9] = c.tile[3];
+                o[10] = c.first; o[11] = 0;
+            }
+            ++n;
+        }
+    *n_cells = n;
+    return SRF_OK;
+}
+
 static uint64_t fuse_signature(const srf_tile *tiles, int n_tiles, int C, int levels, const srf_weight_lut *luts, int n_luts, int out_h,
                                int out_w, const void *canvas, size_t canvas_pitch, int row_begin, int row_end, const void *stream)
 {
@@ -2424,122 +2607,7 @@ int srf_fuse_device(srf_ctx *ctx, const srf_tile *tiles, int n_tiles, int C, int
     }
     bool cells_ok = (rb < re) && n_tiles <= FINAL_TMA_TILES && getenv("SRF_LEGACY_GATHER") == nullptr;
     for (size_t k = 0; k < groups.size() && cells_ok; ++k) cells_ok = groups[k].dev.n_levels >= 3;
-    if (cells_ok) {
-        const bool classify = getenv("SRF_GATHER_ONE_CLASS") == nullptr; // tuning switch: everything through the generic kernel
-        const int nbx = srf_ceil_div(out_w, FB_W), nby = srf_ceil_div(re - rb, FB_H);
-        std::vector<int> xs = {0, nbx}, ys = {0, nby};
-        auto add_edge = [](std::vector<int> &v, long long e, int org, int lim, int blk, int nmax) {
-            long long rel = std::min<long long>(std::max<long long>(e, org), lim) - org; // clipped to the band / canvas
-            v.push_back((int)std::min<long long>(rel / blk, nmax));
-            v.push_back((int)std::min<long long>((rel + blk - 1) / blk, nmax));
-        };
-        for (int i = 0; i < n_tiles; ++i) {
-            // tile edges (the tile list changes there), the 2-pixel margins inside them (the source windows of the first /
-            // last interior block must not poke out of the level-1 plane) and the feather width (inside it W_0 == 1).
-            // Superfluous cuts are merged away below; a missing cut only sends a cell to the generic class.
-            const long long x0 = tiles[i].x, x1 = x0 + tiles[i].w, y0 = tiles[i].y, y1 = y0 + tiles[i].h, F = luts[tiles[i].lut].len - 1;
-            for (long long e : {x0, x0 + 2, x0 + F, x1 - F, x1 - 2, x1}) add_edge(xs, e, 0, out_w, FB_W, nbx);
-            for (long long e : {y0, y0 + 2, y0 + F, y1 - F, y1 - 2, y1}) add_edge(ys, e, rb, re, FB_H, nby);
-        }
-        std::sort(xs.begin(), xs.end());
-        xs.erase(std::unique(xs.begin(), xs.end()), xs.end());
-        std::sort(ys.begin(), ys.end());
-        ys.erase(std::unique(ys.begin(), ys.end()), ys.end());
-        struct RawCell {
-            GatherCell c;
-            int cls;
-        };
-        std::vector<RawCell> raw;
-        for (size_t j = 0; j + 1 < ys.size() && cells_ok; ++j)
-            for (size_t i = 0; i + 1 < xs.size(); ++i) {
-                const int y0 = rb + ys[j] * FB_H, y1 = std::min(rb + ys[j + 1] * FB_H, re);
-                const int x0 = xs[i] * FB_W, x1 = std::min(xs[i + 1] * FB_W, out_w);
-                RawCell rc;
-                memset(&rc, 0, sizeof rc);
-                GatherCell &cell = rc.c;
-                cell.bx0 = xs[i];
-                cell.by0 = ys[j];
-                cell.nbx = xs[i + 1] - xs[i];
-                cell.nby = ys[j + 1] - ys[j];
-                int T = 0;
-                for (int t = 0; t < n_tiles; ++t)
-                    if (tiles[t].y < y1 && tiles[t].y + tiles[t].h > y0 && tiles[t].x < x1 && tiles[t].x + tiles[t].w > x0) {
-                        if (T < GC_MAX_T) cell.tile[T] = t;
-                        ++T;
-                    }
-                if (T > GC_MAX_T) { // more than four tiles over one block: the general kernel takes the whole call
-                    cells_ok = false;
-                    break;
-                }
-                cell.T = T;
-                // interior for every tile?  The conditions are intervals per axis, so the cell's four corner blocks decide.
-                bool all_full = classify && T >= 1, unit = classify && T == 1;
-                for (int s = 0; s < T && all_full; ++s) {
-                    const GatherTile &gt = gtiles[cell.tile[s]];
-                    for (int cy = 0; cy < 2 && all_full; ++cy)
-                        for (int cx = 0; cx < 2 && all_full; ++cx) {
-                            const int by = cy ? cell.by0 + cell.nby - 1 : cell.by0, bx = cx ? cell.bx0 + cell.nbx - 1 : cell.bx0;
-                            const int cy0 = rb + by * FB_H, cx0 = bx * FB_W;
-                            const FinalGeo q = gather_geo(gt, cy0, std::min(cy0 + FB_H, re), cx0, std::min(cx0 + FB_W, out_w), C);
-                            all_full = gather_slot_full(gt, q, cy0, cx0);
-                        }
-                    if (unit) { // W_0 == 1.0f over the whole cell: every pixel at least feather-width inside, and the profile ends at 1
-                        const srf_weight_lut &L = luts[tiles[cell.tile[s]].lut];
-                        const int F = L.len - 1;
-                        unit = L.values[F] == 1.0f && (x0 - gt.x >= F) && (gt.x + gt.w - 1 - (x1 - 1) >= F) && (y0 - gt.y >= F) &&
-                               (gt.y + gt.h - 1 - (y1 - 1) >= F);
-                    }
-                }
-                bool edge_ok = classify && T >= 1 && getenv("SRF_GATHER_NO_EDGE") == nullptr; // block-independent conditions
-                for (int s = 0; s < T && edge_ok; ++s) edge_ok = gather_slot_edge_ok(gtiles[cell.tile[s]], y0, x0);
-                rc.cls = all_full ? (T == 1 ? (unit ? GC_U1 : GC_F1) : (T == 2 ? GC_F2 : GC_F4))
-                                  : (edge_ok ? (T <= 2 ? GC_E2 : GC_E4) : (T <= 2 ? GC_G2 : GC_G4));
-                raw.push_back(rc);
-            }
-        if (cells_ok) {
-            auto same_list = [](const GatherCell &a, const GatherCell &b) {
-                return a.T == b.T && a.tile[0] == b.tile[0] && a.tile[1] == b.tile[1] && a.tile[2] == b.tile[2] && a.tile[3] == b.tile[3];
-            };
-            // merge horizontally (cells arrive row by row, left to right), then vertically
-            std::vector<RawCell> rows;
-            for (const RawCell &rc : raw) {
-                if (rc.c.nbx <= 0 || rc.c.nby <= 0) continue;
-                if (!rows.empty()) {
-                    RawCell &pr = rows.back();
-                    if (pr.cls == rc.cls && pr.c.by0 == rc.c.by0 && pr.c.nby == rc.c.nby && pr.c.bx0 + pr.c.nbx == rc.c.bx0 && same_list(pr.c, rc.c)) {
-                        pr.c.nbx += rc.c.nbx;
-                        continue;
-                    }
-                }
-                rows.push_back(rc);
-            }
-            std::vector<RawCell> merged;
-            std::vector<char> used(rows.size(), 0);
-            for (size_t i = 0; i < rows.size(); ++i) {
-                if (used[i]) continue;
-                RawCell cur = rows[i];
-                for (size_t k = i + 1; k < rows.size(); ++k) {
-                    if (used[k]) continue;
-                    const RawCell &nx = rows[k];
-                    if (nx.c.by0 > cur.c.by0 + cur.c.nby) break; // rows are ordered by by0: nothing further down can touch
-                    if (nx.cls == cur.cls && nx.c.by0 == cur.c.by0 + cur.c.nby && nx.c.bx0 == cur.c.bx0 && nx.c.nbx == cur.c.nbx && same_list(nx.c, cur.c)) {
-                        cur.c.nby += nx.c.nby;
-                        used[k] = 1;
-                    }
-                }
-                merged.push_back(cur);
-            }
-            for (RawCell &rc : merged) {
-                const int cls = rc.cls;
-                const int y0 = rb + rc.c.by0 * FB_H, y1 = std::min(rb + (rc.c.by0 + rc.c.nby) * FB_H, re);
-                const int x0 = rc.c.bx0 * FB_W, x1 = std::min((rc.c.bx0 + rc.c.nbx) * FB_W, out_w);
-                rc.c.first = class_blocks[cls];
-                class_blocks[cls] += rc.c.nbx * rc.c.nby;
-                class_bytes[cls] += (double)(y1 - y0) * (x1 - x0) * C * (3.0 * rc.c.T + 1.0);
-                cells[cls].push_back(rc.c);
-            }
-        }
-    }
+    if (cells_ok) cells_ok = srf_build_gather_cells(tiles, n_tiles, gtiles, luts, C, out_w, rb, re, cells, class_blocks, class_bytes);
     // the row-outer gather also needs a TMA descriptor per tile: 16-byte aligned rows, and the driver's encoder
     for (int i = 0; i < n_tiles && cells_ok; ++i) cells_ok = (tiles[i].pitch % 16 == 0) && (((uintptr_t)tiles[i].data & 15) == 0);
     if (cells_ok && srf_tensor_map_encoder() == nullptr) cells_ok = false;

@@ -203,3 +203,98 @@ def test_blend_weight_tables_equal_the_reference_map_random(srs, oracle):
     big = srs.tiling_module.Tile(metadata=srs.tiling_module.TileMetadata(output_w=10, output_h=10, overlap_top=8), data=None)
     with pytest.raises(ValueError):  # 16 scaled ramp rows on a 10-row tile: the reference's ramp does not broadcast either
         tm._create_blend_weight(big)
+
+
+def _check_gather_plan(srs, sizes, pos, out_hw, levels, kind, row_range):
+    """independent restatement of what every class of the gather's plan PROMISES about each block of a cell"""
+    FB_W, FB_H = 128, 16
+    H, W = out_hw
+    bm = srs.BlendingModule(num_levels=levels)
+    plan = bm.gather_plan(sizes, pos, out_hw, weight_type=srs.WeightType(kind), row_range=row_range)
+    rb, re = (0, H) if row_range is None else (max(row_range[0], 0), min(row_range[1], H))
+    nbx, nby = -(-W // FB_W), -(-(re - rb) // FB_H)
+    lv1 = [((h + 1) // 2, (w + 1) // 2) for h, w in sizes]
+    if plan is None:
+        return None
+    seen = np.zeros((nby, nbx), np.int32)
+    for c in plan:
+        seen[c["by0"]:c["by0"] + c["nby"], c["bx0"]:c["bx0"] + c["nbx"]] += 1
+        T, cls = len(c["tiles"]), c["cls"]
+        assert {0: T == 1, 1: T == 1, 2: T == 2, 3: T in (3, 4), 4: T <= 2, 5: T in (3, 4), 6: 1 <= T <= 2, 7: T in (3, 4)}[cls], c
+        # the corner blocks and a few inner ones decide (every condition is an interval per axis)
+        bys = sorted({c["by0"], c["by0"] + c["nby"] - 1, c["by0"] + c["nby"] // 2})
+        bxs = sorted({c["bx0"], c["bx0"] + c["nbx"] - 1, c["bx0"] + c["nbx"] // 2})
+        for by in bys:
+            for bx in bxs:
+                cy0, cx0 = rb + by * FB_H, bx * FB_W
+                cy1, cx1 = min(cy0 + FB_H, re), min(cx0 + FB_W, W)
+                cover = [t for t, ((h, w), (y, x)) in enumerate(zip(sizes, pos)) if y < cy1 and y + h > cy0 and x < cx1 and x + w > cx0]
+                assert cover == c["tiles"], (c, by, bx, cover)
+                for t in cover:
+                    (h, w), (y, x), (h1, w1) = sizes[t], pos[t], lv1[t]
+                    tyf, txf = cy0 - y, cx0 - x
+                    even = tyf % 2 == 0 and txf % 2 == 0
+                    if cls <= 3:  # interior: whole block inside the tile, every level-1 window strictly inside the plane
+                        assert even and cy1 == cy0 + FB_H and cx1 == cx0 + FB_W, (c, t)
+                        assert tyf >= 2 and txf >= 2 and y + h >= cy0 + FB_H and x + w >= cx0 + FB_W, (c, t)
+                        assert txf // 2 + FB_W // 2 + 1 <= w1 and tyf // 2 + FB_H // 2 + 1 <= h1, (c, t)
+                    if cls == 0:  # unit weight over the whole block
+                        F = min(h, w) // 8
+                        assert tyf >= F and txf >= F and (y + h - 1) - (cy1 - 1) >= F and (x + w - 1) - (cx1 - 1) >= F, (c, t)
+                        assert kind != "sigmoid"  # its profile never reaches exactly 1.0
+                    if cls in (6, 7):  # edge cells on the interior arithmetic: even geometry, half-size level-1 plane
+                        assert even and h == 2 * h1 and w == 2 * w1 and h1 >= 2 and w1 >= 2, (c, t)
+    assert (seen == 1).all(), "every block of the band belongs to exactly one cell"
+    firsts = {}
+    for c in plan:  # `first` numbers the blocks of a class consecutively (a CTA finds its cell by searching it)
+        firsts.setdefault(c["cls"], []).append((c["first"], c["nbx"] * c["nby"]))
+    for cls, lst in firsts.items():
+        nxt = 0
+        for first, n in lst:
+            assert first == nxt, (cls, lst)
+            nxt += n
+    return plan
+
+
+def test_gather_plan_keeps_its_promises_on_random_geometry(srs):
+    """the host-side planner of the canvas gather (include/srfuse.h: srf_gather_plan; no GPU involved): on random grids,
+    bands, tile sizes and parities every block is in exactly one cell, a cell's tile list is the block's coverage in list
+    order, and a cell's class never claims more than holds for its blocks"""
+    rng = np.random.default_rng(5)
+    classes = set()
+    for case in range(60):
+        th, tw = int(rng.integers(300, 1500)), int(rng.integers(300, 1500))
+        if case % 3:
+            th, tw = th & ~1, tw & ~1
+        ny, nx = int(rng.integers(1, 4)), int(rng.integers(1, 4))
+        sy, sx = int(th * rng.uniform(0.6, 1.0)), int(tw * rng.uniform(0.6, 1.0))
+        if case % 2:
+            sy, sx = sy & ~1, sx & ~1
+        oy, ox = (0, 0) if case % 4 else (int(rng.integers(0, 40)), int(rng.integers(0, 300)))
+        pos = [(oy + j * sy, ox + i * sx) for j in range(ny) for i in range(nx)]
+        sizes = [(th, tw)] * len(pos)
+        H = oy + (ny - 1) * sy + th - int(rng.integers(0, 60))
+        W = ox + (nx - 1) * sx + tw - int(rng.integers(0, 60))
+        band = None
+        if case % 5 == 0:
+            a = int(rng.integers(0, H - 1)) & ~1
+            band = (a, int(rng.integers(a + 1, H + 1)))
+        plan = _check_gather_plan(srs, sizes, pos, (H, W), int(rng.integers(3, 7)), ["cosine", "linear", "sigmoid"][case % 3], band)
+        if plan:
+            classes |= {c["cls"] for c in plan}
+    assert classes >= {0, 1, 2, 3, 4, 6, 7}, classes  # the random cases reach every class but the rare generic 3/4-tile one
+
+
+def test_gather_plan_of_the_200mp_config(srs):
+    import collections
+    pos = [(y, x) for y in (0, 3278, 6556, 9834) for x in range(0, 6 * 3278, 3278)]
+    plan = _check_gather_plan(srs, [(4096, 4096)] * 24, pos, (11546, 17320), 7, "cosine", None)
+    blocks = collections.Counter()
+    for c in plan:
+        blocks[c["cls"]] += c["nbx"] * c["nby"]
+    # DESIGN.md section 5: unit-weight cores, interior 1 / 2 / 4-tile cells, edge cells; nothing is left to the generic kernel
+    assert dict(blocks) == {0: 50635, 1: 4637, 2: 29364, 3: 3900, 6: 7940, 7: 1716}
+    assert sum(blocks.values()) == -(-17320 // 128) * -(-11546 // 16)
+    band = _check_gather_plan(srs, [(4096, 4096)] * 24, pos, (11546, 17320), 7, "cosine", (4438, 6212))  # a band of an 8-rank job
+    assert band and not any(c["cls"] in (4, 5) for c in band)
+    assert srs.BlendingModule(num_levels=2).gather_plan([(256, 256)], [(0, 0)], (256, 256)) is None  # 2 levels: general kernel
