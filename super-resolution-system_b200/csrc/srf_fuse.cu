@@ -1619,6 +1619,34 @@ __device__ __forceinline__ float2 g16_pair_even_origin(int g0, int g1, int g2)
     return make_float2(__int2float_rn(6 * g1 + g0 + g2), __int2float_rn(4 * (g1 + g2)));
 }
 
+// The cell whose block range [first, first + nbx * nby) holds block `bid` (cells are sorted by `first`, which starts at
+// 0).  Every warp searches for itself, 32 probes at a time: two dependent loads for up to 1024 cells instead of the ten
+// of a binary search -- the search is the first thing a CTA does and nothing can start before it ends.
+__device__ __forceinline__ int gather_find_cell(const GatherCell *__restrict__ cells, int n, int bid)
+{
+    if (n <= 1024) {
+        const int lane = (int)(threadIdx.x & 31u);
+        const int stride = (n + 31) >> 5; // <= 32
+        int idx = lane * stride;
+        int f = idx < n ? __ldg(&cells[idx].first) : 0x7fffffff;
+        unsigned m = __ballot_sync(0xffffffffu, f <= bid); // ascending: a prefix of ones, lane 0 always set
+        const int base = (31 - __clz((int)m)) * stride;
+        idx = base + lane;
+        f = (lane < stride && idx < n) ? __ldg(&cells[idx].first) : 0x7fffffff;
+        m = __ballot_sync(0xffffffffu, f <= bid);
+        return base + 31 - __clz((int)m);
+    }
+    int lo = 0, hi = n - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (__ldg(&cells[mid].first) <= bid)
+            lo = mid;
+        else
+            hi = mid - 1;
+    }
+    return lo;
+}
+
 template <int C, int TMAX>
 __global__ void __launch_bounds__(FB_PAIRS *C, (TMAX <= 2) ? SRF_GATHER_CTAS : 2)
     k_gather(const __grid_constant__ GatherParams P, const __grid_constant__ GatherTiles GT, const __grid_constant__ FinalTmaps TM)
@@ -1635,15 +1663,8 @@ __global__ void __launch_bounds__(FB_PAIRS *C, (TMAX <= 2) ? SRF_GATHER_CTAS : 2
     const int base = (int)((128u - (smem_u32(g_gather_smem) & 127u)) & 127u); // the TMA boxes want 128-byte aligned destinations
 
     // ---- which cell, which block ----
-    int lo = 0, hi = P.n_cells - 1;
     const int bid = blockIdx.x;
-    while (lo < hi) {
-        const int mid = (lo + hi + 1) >> 1;
-        if (__ldg(&P.cells[mid].first) <= bid)
-            lo = mid;
-        else
-            hi = mid - 1;
-    }
+    const int lo = gather_find_cell(P.cells, P.n_cells, bid);
     const int4 ca = __ldg(reinterpret_cast<const int4 *>(&P.cells[lo]));
     const int4 cb = __ldg(reinterpret_cast<const int4 *>(&P.cells[lo]) + 1);
     const int4 cc = __ldg(reinterpret_cast<const int4 *>(&P.cells[lo]) + 2);
@@ -1924,15 +1945,8 @@ __global__ void __launch_bounds__(FB_PAIRS *C, (TMAX == 1) ? 6 : ((TMAX == 2) ? 
     __shared__ __align__(8) unsigned s_mrow[EDGE ? TMAX : 1][FB_H]; // EDGE: all ones where the tile covers the block's row, else 0
     const int base = (int)((128u - (smem_u32(g_gather_smem) & 127u)) & 127u);
 
-    int lo = 0, hi = P.n_cells - 1;
     const int bid = blockIdx.x;
-    while (lo < hi) {
-        const int mid = (lo + hi + 1) >> 1;
-        if (__ldg(&P.cells[mid].first) <= bid)
-            lo = mid;
-        else
-            hi = mid - 1;
-    }
+    const int lo = gather_find_cell(P.cells, P.n_cells, bid);
     const int4 ca = __ldg(reinterpret_cast<const int4 *>(&P.cells[lo]));
     const int4 cb = __ldg(reinterpret_cast<const int4 *>(&P.cells[lo]) + 1);
     const int4 cc = __ldg(reinterpret_cast<const int4 *>(&P.cells[lo]) + 2);
