@@ -194,8 +194,8 @@ int srf_window_ssim_host(srf_ctx *ctx, const uint8_t *h_result, size_t result_pi
  * _create_blend_weight (1137-1175): float32 ones multiplied in place by float64 linspace ramps, i.e.
  * w(y, x) = f32(f32(wy[y] * wl[x]) * wr[x]) with float64 products -- the caller passes the three 1-D tables (HOST
  * pointers; all NULL = weight 1, the reference's blending=False) and the full map is never built.  A tile whose stored
- * size (h, w) differs from its canvas size (out_h, out_w) is first squashed with cv2.resize's default INTER_LINEAR, as
- * the reference does for the padded edge tiles (1107-1109); enlarging is SRF_ERR_UNSUPPORTED. */
+ * size (h, w) differs from its canvas size (out_h, out_w) is first resized with cv2.resize's default INTER_LINEAR, as
+ * the reference does (1107-1109: shrinking for the padded edge tiles, enlarging when the upscaler returned less). */
 typedef struct srf_merge_tile {
     const uint8_t *data; /* (h, w, channels) uint8; host pointer for _host, device pointer otherwise */
     size_t pitch;
@@ -210,9 +210,34 @@ int srf_merge_tiles(srf_ctx *ctx, const srf_merge_tile *tiles, int n_tiles, int 
                     uint8_t *d_canvas, size_t canvas_pitch, void *stream);
 int srf_merge_tiles_host(srf_ctx *ctx, const srf_merge_tile *tiles, int n_tiles, int channels, int out_h, int out_w,
                          uint8_t *h_canvas, size_t canvas_pitch);
+/* ---- weighted_average_fusion with custom weight maps (blending_module.py:661-760, the `weights=` argument) -----------
+ * out = astype(uint8)(clip(sum_t tile_t * w_t / max(sum_t w_t, 1e-6), 0, 255)), float32 accumulators, tiles in list order,
+ * every tile cropped to the canvas.  w_t is an (weight_h, weight_w) plane of float32 or float64 (weight_f64 != 0) at least
+ * as large as the tile's part of the canvas (top-left aligned); NumPy's mixed-precision rules are reproduced: a float64 map
+ * makes the products and the in-place sums run in float64 before they are stored as float32.  Without custom maps the call
+ * is srf_laplacian_fuse with levels = 1.  `srf_weighted_average` takes DEVICE pointers in data / weight and only enqueues on
+ * `stream`; `_host` takes host pointers and returns the finished canvas. */
+typedef struct srf_wavg_tile {
+    const uint8_t *data; /* (h, w, channels) uint8 */
+    size_t pitch;
+    int h, w;
+    int y, x; /* position on the canvas, >= 0 */
+    const void *weight; /* (weight_h, weight_w) float32 or float64 */
+    size_t weight_pitch; /* bytes */
+    int weight_h, weight_w;
+    int weight_f64;
+    int reserved;
+} srf_wavg_tile;
+int srf_weighted_average(srf_ctx *ctx, const srf_wavg_tile *tiles, int n_tiles, int channels, int out_h, int out_w,
+                         uint8_t *d_canvas, size_t canvas_pitch, void *stream);
+int srf_weighted_average_host(srf_ctx *ctx, const srf_wavg_tile *tiles, int n_tiles, int channels, int out_h, int out_w,
+                              uint8_t *h_canvas, size_t canvas_pitch);
 /* host only, exact: OpenCV's INTER_LINEAR taps for uint8 -- per destination index the source index pair and the two
  * 11-bit coefficients (cvRound(frac * 2048)) */
 int srf_resize_linear_taps(int src, int dst, int *idx2, int *coef2);
+/* the same per axis: vertical != 0 gives the table of OpenCV's vertical pass (fraction kept past the first / last source
+ * row, the two row indices clamped separately -- differs from the horizontal table only when enlarging) */
+int srf_resize_linear_taps_axis(int src, int dst, int vertical, int *idx2, int *coef2);
 
 /* ---- bicubic resize: cv2.resize(img, (dst_w, dst_h), interpolation=cv2.INTER_CUBIC) on uint8 ---------------------
  * replaces QualityAssessmentModule.downsample_bicubic (quality_assessment_module.py:226-253) and upsample_bicubic

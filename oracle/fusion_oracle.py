@@ -95,6 +95,40 @@ def laplacian_fuse(tiles, positions_yx, out_hw, levels=6, kind="cosine", backend
     return np.clip(res, 0, 255).astype(np.uint8)
 
 
+def weighted_average_custom(tiles, positions_yx, weights, out_hw=None, kind="cosine"):
+    """weighted_average_fusion WITH the `weights=` argument (/root/reference/blending_module.py:688-757), every NumPy
+    promotion written out: a float32 map multiplies and accumulates in float32; a float64 map makes the product float64
+    and the in-place `+=` on the float32 accumulators run in float64 before the result is stored back as float32.
+    Tiles past the end of `weights` get the generated distance map (float32).  (h, w, 1) maps count as planes."""
+    if out_hw is None:
+        out_hw = (max(y + t.shape[0] for t, (y, x) in zip(tiles, positions_yx)), max(x + t.shape[1] for t, (y, x) in zip(tiles, positions_yx)))
+    H, W = out_hw
+    ch = tiles[0].shape[2:]
+    acc = np.zeros((H, W) + ch, np.float32)
+    wacc = np.zeros((H, W), np.float32)
+    for i, (img, (y, x)) in enumerate(zip(tiles, positions_yx)):
+        h, w = img.shape[:2]
+        wm = np.asarray(weights[i]) if i < len(weights) else weight_map(h, w, kind)
+        ye, xe = min(y + h, H), min(x + w, W)
+        if ye <= y or xe <= x:
+            continue
+        t = img[:ye - y, :xe - x].astype(np.float32)
+        m = wm[:ye - y, :xe - x]
+        m = m.reshape(m.shape[:2])
+        wide = np.result_type(np.float32, m.dtype) == np.float64
+        m = m.astype(np.float64 if wide else np.float32)
+        mc = m[..., None] if ch else m
+        if wide:
+            acc[y:ye, x:xe] = (acc[y:ye, x:xe].astype(np.float64) + t.astype(np.float64) * mc).astype(np.float32)
+            wacc[y:ye, x:xe] = (wacc[y:ye, x:xe].astype(np.float64) + m).astype(np.float32)
+        else:
+            acc[y:ye, x:xe] = acc[y:ye, x:xe] + t * mc
+            wacc[y:ye, x:xe] = wacc[y:ye, x:xe] + m
+    wacc = np.maximum(wacc, np.float32(1e-6))
+    res = acc / (wacc[..., None] if ch else wacc)
+    return np.clip(res, 0, 255).astype(np.uint8)
+
+
 # ---- seam detection (blending_module.py:765-968): per-window whole-patch SSIM -------------------------------------------
 def gray_bgr_order(img: np.ndarray) -> np.ndarray:
     """cv2.cvtColor(img, cv2.COLOR_BGR2GRAY) for uint8 -- what the reference applies to its RGB arrays (channel 0 gets the

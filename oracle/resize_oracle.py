@@ -66,37 +66,41 @@ def resize_cubic_u8(img: np.ndarray, dw: int, dh: int) -> np.ndarray:
     return out[:, :, 0] if squeeze else out
 
 
-def linear_table(src: int, dst: int):
+def linear_table(src: int, dst: int, vertical: bool = False):
     """OpenCV's fixed-point bilinear taps (imgproc resize, INTER_LINEAR, uint8): source index pair and the two 11-bit
-    coefficients per destination index; the sample position is float32 here, clamped at both ends"""
+    coefficients per destination index; the sample position is float32.  The two axes treat the ends differently:
+    the HORIZONTAL table resets the fraction to 0 where the sample falls before the first or on / after the last source
+    column; the VERTICAL pass keeps the fraction and clamps each of the two row indices on its own, so above the first
+    (below the last) source row both taps read the same row with coefficients a0 + a1 = 2048 -- and each product is
+    truncated separately, which is visible in the last bit.  Only enlarging reaches those rows."""
     inv = dst / src
     scale = 1.0 / inv
     d = np.arange(dst, dtype=np.float64)
     f = ((d + 0.5) * scale - 0.5).astype(np.float32)
     s = np.floor(f).astype(np.int64)
     fr = (f - s.astype(np.float32)).astype(np.float32)
-    lo, hi = s < 0, s >= src - 1
-    fr[lo | hi] = 0
-    s[lo] = 0
-    s[hi] = src - 1
+    if not vertical:
+        lo, hi = s < 0, s >= src - 1
+        fr[lo | hi] = 0
+        s[lo] = 0
+        s[hi] = src - 1
     a1 = np.rint(fr * np.float32(2048)).astype(np.int32)                    # saturate_cast<short>(cvRound)
     a0 = np.rint((np.float32(1) - fr) * np.float32(2048)).astype(np.int32)
-    return s, np.minimum(s + 1, src - 1), a0, a1
+    return np.clip(s, 0, src - 1), np.clip(s + 1, 0, src - 1), a0, a1
 
 
 def resize_linear_u8(img: np.ndarray, dw: int, dh: int) -> np.ndarray:
-    """cv2.resize(img, (dw, dh)) (INTER_LINEAR, the default) for uint8 when SHRINKING or keeping a size -- the case
-    TilingModule.merge_tiles hits (/root/reference/tiling_module.py:1107-1109).  OpenCV's own integer code (IPP is not
-    used for 8-bit linear unless its "not exact" mode is on): horizontal pass in int32 with 11-bit coefficients,
-    vertical pass ((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2.  Bit-exact against cv2 4.13 for
-    every shrinking case probed; 2x enlargements take another OpenCV path and are NOT covered."""
+    """cv2.resize(img, (dw, dh)) (INTER_LINEAR, the default) for uint8, shrinking or enlarging -- what
+    TilingModule.merge_tiles applies to a tile whose data is not (output_h, output_w)
+    (/root/reference/tiling_module.py:1107-1109).  OpenCV's own integer code (IPP is not used for 8-bit linear unless
+    its "not exact" mode is on): horizontal pass in int32 with 11-bit coefficients, vertical pass
+    ((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2.  Bit-exact against cv2 4.13 on 1 500 random shapes
+    in every direction (tests/test_oracle.py)."""
     if img.dtype != np.uint8:
         raise TypeError("uint8 only")
     h, w = img.shape[:2]
-    if dw > w or dh > h:
-        raise ValueError("resize_linear_u8 restates the shrinking path only")
     x0, x1, ax0, ax1 = linear_table(w, dw)
-    y0, y1, ay0, ay1 = linear_table(h, dh)
+    y0, y1, ay0, ay1 = linear_table(h, dh, vertical=True)
     im = (img[:, :, None] if img.ndim == 2 else img).astype(np.int32)
     hz = im[:, x0, :] * ax0[None, :, None] + im[:, x1, :] * ax1[None, :, None]
     s0, s1 = hz[y0], hz[y1]

@@ -31,6 +31,12 @@ class srf_merge_tile(C.Structure):
                 ("y", c_int), ("x", c_int), ("wy", c_void_p), ("wl", c_void_p), ("wr", c_void_p)]
 
 
+class srf_wavg_tile(C.Structure):
+    _fields_ = [("data", c_void_p), ("pitch", c_size_t), ("h", c_int), ("w", c_int), ("y", c_int), ("x", c_int),
+                ("weight", c_void_p), ("weight_pitch", c_size_t), ("weight_h", c_int), ("weight_w", c_int),
+                ("weight_f64", c_int), ("reserved", c_int)]
+
+
 class srf_image_pair(C.Structure):
     _fields_ = [("a", c_void_p), ("b", c_void_p), ("pitch_a", c_size_t), ("pitch_b", c_size_t)]
 
@@ -107,7 +113,10 @@ SIGNATURES = {
                                      c_int, c_int, c_int, c_int, C.c_double, C.c_double, c_void_p]),
     "srf_merge_tiles": (c_int, [c_void_p, P(srf_merge_tile), c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "srf_merge_tiles_host": (c_int, [c_void_p, P(srf_merge_tile), c_int, c_int, c_int, c_int, c_void_p, c_size_t]),
+    "srf_weighted_average": (c_int, [c_void_p, P(srf_wavg_tile), c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    "srf_weighted_average_host": (c_int, [c_void_p, P(srf_wavg_tile), c_int, c_int, c_int, c_int, c_void_p, c_size_t]),
     "srf_resize_linear_taps": (c_int, [c_int, c_int, c_void_p, c_void_p]),
+    "srf_resize_linear_taps_axis": (c_int, [c_int, c_int, c_int, c_void_p, c_void_p]),
     "srf_resize_cubic_taps": (c_int, [c_int, c_int, c_void_p, c_void_p]),
     "srf_resize_cubic_u8": (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_int, c_int, c_void_p, c_size_t, c_int, c_int,
                                     c_void_p]),
@@ -122,7 +131,7 @@ _ctx_locks = {}  # srf_ctx address -> RLock: calls on one ctx must not overlap (
 
 # entry points that do NOT take an srf_ctx* first (nothing to serialise)
 _NO_CTX = {"srf_fuse_input_rows", "srf_gather_plan", "srf_version", "srf_status_string", "srf_last_error", "srf_create", "srf_tile_positions", "srf_tile_overlaps",
-           "srf_weight_profile", "srf_iqa_finish", "srf_window_ssim_shape", "srf_resize_linear_taps", "srf_resize_cubic_taps"}
+           "srf_weight_profile", "srf_iqa_finish", "srf_window_ssim_shape", "srf_resize_linear_taps", "srf_resize_linear_taps_axis", "srf_resize_cubic_taps"}
 
 
 def lib_path() -> str:

@@ -354,15 +354,95 @@ class BlendingModule:
         sum_t tile_t * W_0^t / max(sum_t W_0^t, 1e-6), clip, truncate -- which is exactly the Laplacian fusion with a
         single pyramid level (no pyramid at all), so it runs the same gather kernel.  Bare-array tiles always get the
         sqrt-grid layout here (the reference does not require output_shape for them).  Custom per-tile weight maps
-        (`weights=`) are not supported on the GPU path."""
+        (`weights=`, float32 or float64 planes at least as large as the tile's part of the canvas; tiles past the end of
+        the list get the generated map) run `srf_weighted_average`, which reproduces NumPy's mixed-precision sums."""
         if weights is not None:
-            raise NotImplementedError("weighted_average_fusion(weights=...): custom weight maps are not on the GPU path")
+            if row_range is not None or out is not None:
+                raise ValueError("weighted_average_fusion(weights=...) produces the whole canvas: row_range / out are not supported")
+            return self._weighted_average_custom(list(tiles), list(weights), weight_type, output_shape)
         tiles = list(tiles)
         if tiles and not any(isinstance(t, TileInfo) for t in tiles):
             grid = int(np.ceil(np.sqrt(len(tiles))))
             tiles = [TileInfo(t, (i % grid) * t.shape[1], (i // grid) * t.shape[0], i // grid, i % grid) for i, t in enumerate(tiles)]
         return self.laplacian_fusion(tiles, output_shape=output_shape, weight_type=weight_type, row_range=row_range, out=out,
                                      _levels=1)
+
+    def _weighted_average_custom(self, tiles, weights, weight_type, output_shape):
+        """blending_module.py:688-757 with `weights` given: positions as in the reference (TileInfo or sqrt-grid), the
+        canvas the maximum extent unless output_shape says otherwise, every tile cropped to it"""
+        if not tiles:
+            raise ValueError("no tiles")
+        images, pos = [], []
+        grid = int(np.ceil(np.sqrt(len(tiles))))
+        for i, t in enumerate(tiles):
+            if isinstance(t, TileInfo):
+                images.append(t.image)
+                pos.append((int(t.y), int(t.x)))
+            else:
+                images.append(t)
+                pos.append(((i // grid) * int(t.shape[0]), (i % grid) * int(t.shape[1])))
+        views = [ImageView(im, f"tile {i}") for i, im in enumerate(images)]
+        on_dev, chans = views[0].on_device, views[0].c
+        if any(v.on_device != on_dev or v.c != chans for v in views):
+            raise ValueError("tiles must be all host or all device images with the same channel count")
+        if output_shape is None:
+            out_h = max(y + v.h for v, (y, x) in zip(views, pos))
+            out_w = max(x + v.w for v, (y, x) in zip(views, pos))
+        else:
+            out_h, out_w = int(output_shape[0]), int(output_shape[1])
+        arr = (_native.srf_wavg_tile * len(views))()
+        keep = []
+        for i, (v, (y, x)) in enumerate(zip(views, pos)):
+            wm = weights[i] if i < len(weights) else self._create_distance_weight_map(v.h, v.w, weight_type)
+            if is_cuda_tensor(wm):
+                if not on_dev:
+                    wm = wm.cpu().numpy()
+            if not is_cuda_tensor(wm):
+                wm = np.asarray(wm)
+            if wm.ndim == 3 and wm.shape[2] == 1 and chans > 1:
+                wm = wm[:, :, 0]  # the reference squeezes such a map for its weight accumulator
+            if wm.ndim != 2:
+                raise ValueError(f"weight map {i}: expected an (H, W) plane, got {tuple(wm.shape)}")
+            ch, cw = max(min(y + v.h, out_h) - y, 0), max(min(x + v.w, out_w) - x, 0)
+            if wm.shape[0] < ch or wm.shape[1] < cw:  # NumPy would refuse to broadcast tile[:ch, :cw] * weight[:ch, :cw]
+                raise ValueError(f"weight map {i} is {tuple(wm.shape)}, smaller than the tile's part of the canvas ({ch}, {cw})")
+            if is_cuda_tensor(wm):
+                f64 = wm.dtype == torch.float64
+                if not f64 and wm.dtype != torch.float32:
+                    f64 = torch.promote_types(torch.float32, wm.dtype) == torch.float64
+                    wm = wm.to(torch.float64 if f64 else torch.float32)
+                if wm.stride(1) != 1:
+                    wm = wm.contiguous()
+                wptr, wpitch = wm.data_ptr(), wm.stride(0) * wm.element_size()
+            else:
+                f64 = np.result_type(np.float32, wm.dtype) == np.float64  # what `float32 tile * map` computes in
+                wm = wm.astype(np.float64 if f64 else np.float32, copy=False)
+                if wm.strides[1] != wm.itemsize or wm.strides[0] < wm.shape[1] * wm.itemsize:
+                    wm = np.ascontiguousarray(wm)
+                if on_dev:
+                    wm = torch.from_numpy(np.ascontiguousarray(wm)).to(views[0].keep.device)
+                    wptr, wpitch = wm.data_ptr(), wm.stride(0) * wm.element_size()
+                else:
+                    wptr, wpitch = wm.ctypes.data, wm.strides[0] if wm.shape[0] > 1 else wm.shape[1] * wm.itemsize
+            keep.append(wm)
+            a = arr[i]
+            a.data, a.pitch, a.h, a.w, a.y, a.x = v.ptr, v.pitch, v.h, v.w, y, x
+            a.weight, a.weight_pitch, a.weight_h, a.weight_w, a.weight_f64 = wptr, wpitch, int(wm.shape[0]), int(wm.shape[1]), int(f64)
+        lib = _native.load()
+        shape = (out_h, out_w) if views[0].keep.ndim == 2 else (out_h, out_w, chans)
+        if on_dev:
+            dev = views[0].device
+            ctx = _native.context(dev)
+            canvas = torch.empty(shape, dtype=torch.uint8, device=views[0].keep.device)
+            rc = lib.srf_weighted_average(ctx, arr, len(views), chans, out_h, out_w, canvas.data_ptr(), out_w * chans, current_stream_ptr(dev))
+            _native.check(rc, ctx)
+            torch.cuda.current_stream(dev).synchronize()  # the uploaded maps in `keep` must outlive the kernel
+            return canvas
+        ctx = self._ctx()
+        canvas = np.empty(shape, np.uint8)
+        rc = lib.srf_weighted_average_host(ctx, arr, len(views), chans, out_h, out_w, canvas.ctypes.data, out_w * chans)
+        _native.check(rc, ctx)
+        return canvas
 
     # ------------------------------------------------------------------ seam detection (blending_module.py:765-968)
     def window_ssim_map(self, result, tile, x: int, y: int, window_size: int = 16, stride: int = 8,

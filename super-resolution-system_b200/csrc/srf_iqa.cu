@@ -71,7 +71,7 @@ template <int C, bool ANYSCALE>
 __device__ __forceinline__ void iq_load_pair(const uint8_t *row, int byte_off, int scale, unsigned &lo, unsigned &hi)
 {
     const unsigned *wp = reinterpret_cast<const unsigned *>(row) + (byte_off >> 2);
-    const int sh = (byte_off & 3) * 8;
+    const int sh = byte_off * 8; // the funnel shift uses the low five bits: (byte_off & 3) * 8
     const unsigned w0 = wp[0], w1 = wp[1];
     lo = __funnelshift_r(w0, w1, sh);
     hi = 0u;
@@ -85,20 +85,32 @@ __device__ __forceinline__ void iq_load_pair(const uint8_t *row, int byte_off, i
 // gray - 128 of both pixels.  cv2 COLOR_RGB2GRAY (uint8): (R*9798 + G*19235 + B*3735 + 16384) >> 15; the coefficients
 // are split into byte halves so that two IDP.4A per pixel form the sum; the -128 rides in the rounding constant
 // (128 << 15 is a multiple of the shift, so the arithmetic shift gives gray - 128 exactly)
+#ifndef SRF_IQ_DP2A
+#define SRF_IQ_DP2A 0
+#endif
 template <int C>
-__device__ __forceinline__ void iq_gray_pair(unsigned lo, unsigned hi, float &g0, float &g1)
+__device__ __forceinline__ void iq_gray_pair(unsigned lo, unsigned hi, int &g0, int &g1)
 {
     if (C == 3) {
         constexpr unsigned CLO = 70u | (35u << 8) | (151u << 16), CHI = 38u | (75u << 8) | (14u << 16);
         constexpr unsigned K = 16384u - (128u << 15);
         const unsigned p1 = __funnelshift_r(lo, hi, 24);
+#if SRF_IQ_DP2A
+        // 16-bit coefficients against the bytes: (R, G) with the low byte pair, (B, -) with the high one -- no shift-add
+        constexpr unsigned CRG = 9798u | (19235u << 16), CB = 3735u;
+        const int x0 = (int)__dp2a_hi(CB, lo, __dp2a_lo(CRG, lo, K));
+        const int x1 = (int)__dp2a_hi(CB, p1, __dp2a_lo(CRG, p1, K));
+        (void)CLO;
+        (void)CHI;
+#else
         const int x0 = (int)(__dp4a(lo, CLO, K) + (__dp4a(lo, CHI, 0u) << 8));
         const int x1 = (int)(__dp4a(p1, CLO, K) + (__dp4a(p1, CHI, 0u) << 8));
-        g0 = (float)(x0 >> 15);
-        g1 = (float)(x1 >> 15);
+#endif
+        g0 = x0 >> 15;
+        g1 = x1 >> 15;
     } else {
-        g0 = (float)((int)(lo & 0xFFu) - 128);
-        g1 = (float)((int)((lo >> 8) & 0xFFu) - 128);
+        g0 = (int)(lo & 0xFFu) - 128;
+        g1 = (int)((lo >> 8) & 0xFFu) - 128;
     }
 }
 
@@ -135,15 +147,14 @@ __global__ void __launch_bounds__(IQ_THREADS, 4) k_psnr_ssim(IqaParams P)
         pitch_b = q.pitch_b;
     }
     __shared__ __align__(16) uint8_t s_raw[4][2][IQ2_RAW];
-    __shared__ __align__(16) float2 s_ab[2][IQ2_SROW]; // (a, b) = gray - 128 of both images, per staged pixel
-#ifndef SRF_IQ_SP_SMEM
-#define SRF_IQ_SP_SMEM 0 // 1: (a^2 + b^2, a b) formed once per pixel and staged in a second smem row -- 12 % fewer instructions,
-                         // twice the LDS.128 of the horizontal pass: measured EQUAL (1.425 ms), the warps then wait on the
-                         // shared-memory pipe (61 % busy, short-scoreboard stalls x3) instead of on issue slots
+    __shared__ __align__(16) float2 s_ab[2][IQ2_SROW]; // (s, d) = (a + b, a - b), a / b = gray - 128 of the two images, per staged pixel
+#ifndef SRF_IQ_BULK
+#define SRF_IQ_BULK 0 // 1: rows that cannot touch either end of the readable range arrive as two 832-byte TMA bulk copies issued by ONE
+                      // thread (mbarrier per stage) instead of 104 threads' 16-byte cp.async chunks; 0: chunks only.  MEASURED SLOWER
+                      // (200 MP: 1.416 ms against 1.287): every thread polls the stage's mbarrier and the issuing warp runs a
+                      // 50-instruction elect / R2UR sequence per row inside a loop that is barrier-coupled already
 #endif
-#if SRF_IQ_SP_SMEM
-    __shared__ __align__(16) float2 s_sp[2][IQ2_SROW]; // (a^2 + b^2, a b) of the same pixel
-#endif
+    __shared__ __align__(8) uint64_t s_full[4];
     __shared__ double s_red[IQ_THREADS / 32];
     __shared__ unsigned long long s_sq[IQ_THREADS / 32];
     __shared__ unsigned long long s_cnt[IQ_THREADS / 32];
@@ -172,10 +183,39 @@ __global__ void __launch_bounds__(IQ_THREADS, 4) k_psnr_ssim(IqaParams P)
     const long long over = col_off + IQ2_RAW - (long long)w * C;
     const int safe_lo = vr0 + (int)((32 + lpitch - 1) / lpitch);
     const int safe_hi = vr1 - 1 - (over > 0 ? (int)((over + lpitch - 1) / lpitch) : 0);
-    // L is called for consecutive rows starting at r_first: l_ptr tracks the thread's chunk of the next row
-    const uint8_t *l_ptr = lbase + (long long)r_first * lpitch + col_off + 16 * lchunk;
+    // rows every chunk of BOTH images may be copied blindly (uniform over the CTA): those travel as bulk copies
+    auto safe_range = [&](long long pitch, int &lo, int &hi) {
+        lo = vr0 + (int)((32 + pitch - 1) / pitch);
+        hi = vr1 - 1 - (over > 0 ? (int)((over + pitch - 1) / pitch) : 0);
+    };
+    int sla, sha, slb, shb;
+    safe_range((long long)pitch_a, sla, sha);
+    safe_range((long long)pitch_b, slb, shb);
+    const int bulk_lo = SRF_IQ_BULK ? max(max(sla, slb), r_first) : 0x7fffffff, bulk_hi = min(min(sha, shb), r_last - 1);
+    if (SRF_IQ_BULK) {
+        if (t == 0) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) mbar_init(&s_full[i], 1);
+            mbar_fence_init();
+        }
+        __syncthreads();
+    }
+    constexpr int BULK_T = 96; // the issuing thread: lane 0 of the last warp (warp 0 converts the extra halo pairs)
+    // bulk rows are consecutive: the issuing thread tracks its two source pointers, nobody else carries loader state
+    const uint8_t *ba_ptr = img_a + (long long)bulk_lo * (long long)pitch_a + col_off;
+    const uint8_t *bb_ptr = img_b + (long long)bulk_lo * (long long)pitch_b + col_off;
     auto L = [&](int r) {
-        if (loader && r >= vr0 && r < vr1 && r < r_last) {
+        if (SRF_IQ_BULK && r >= bulk_lo && r <= bulk_hi) {
+            if (t == BULK_T) {
+                const int st = (r - r_first) & 3;
+                mbar_expect_tx(&s_full[st], 2 * IQ2_RAW);
+                tma_bulk_g2s(&s_raw[st][0][0], ba_ptr - (reinterpret_cast<uintptr_t>(ba_ptr) & 15), IQ2_RAW, &s_full[st]);
+                tma_bulk_g2s(&s_raw[st][1][0], bb_ptr - (reinterpret_cast<uintptr_t>(bb_ptr) & 15), IQ2_RAW, &s_full[st]);
+                ba_ptr += pitch_a;
+                bb_ptr += pitch_b;
+            }
+        } else if (loader && r >= vr0 && r < vr1 && r < r_last) { // the few rows next to an end of the readable range: guarded chunks
+            const uint8_t *l_ptr = lbase + (long long)r * lpitch + col_off + 16 * lchunk;
             const uint8_t *q = l_ptr - (reinterpret_cast<uintptr_t>(l_ptr) & 15);
             uint8_t *dst = &s_raw[(r - r_first) & 3][limg][16 * lchunk];
             if (r >= safe_lo && r <= safe_hi) {
@@ -191,8 +231,12 @@ __global__ void __launch_bounds__(IQ_THREADS, 4) k_psnr_ssim(IqaParams P)
                 *reinterpret_cast<uint4 *>(dst) = v;
             }
         }
-        l_ptr += lpitch;
         cp_async_commit();
+    };
+    // a row that travelled as bulk copies is complete when its stage's mbarrier flips: bulk rows are consecutive, so the
+    // k-th of them is the (k / 4)-th use of its stage
+    auto wait_row = [&](int r) {
+        if (SRF_IQ_BULK && r >= bulk_lo && r <= bulk_hi) mbar_wait(&s_full[(r - r_first) & 3], (unsigned)(((r - bulk_lo) >> 2) & 1));
     };
 
     unsigned int sq = 0; // <= 266 rows * 4 px * 3 * 65025 < 2^32
@@ -219,8 +263,9 @@ __global__ void __launch_bounds__(IQ_THREADS, 4) k_psnr_ssim(IqaParams P)
     asm volatile("" : "+r"(mlo0), "+r"(mhi0)); // per-thread constants: keep them, do not re-derive them from the thread index every row
     auto G = [&](int r) {
         const int buf = r & 1;
-        float4 o0 = make_float4(0.f, 0.f, 0.f, 0.f), o1 = o0; // (a, b) of the pair's two pixels
+        float4 o0 = make_float4(0.f, 0.f, 0.f, 0.f), o1 = o0; // (s, d) of the pair's two pixels
         if (r >= 0 && r < h) {
+            wait_row(r);
             const int st = (r - r_first) & 3;
             const int ma = (mis_a0 + r * pa16) & 15, mb = (mis_b0 + r * pb16) & 15;
             const bool rown = r >= ry0 && r < ry1;
@@ -228,8 +273,10 @@ __global__ void __launch_bounds__(IQ_THREADS, 4) k_psnr_ssim(IqaParams P)
                 unsigned alo, ahi, blo, bhi;
                 iq_load_pair<C, ANYSCALE>(s_raw[st][0], ma + i * C, P.scale_a, alo, ahi);
                 iq_load_pair<C, ANYSCALE>(s_raw[st][1], mb + i * C, P.scale_b, blo, bhi);
-                iq_gray_pair<C>(alo, ahi, o.x, o.z);
-                iq_gray_pair<C>(blo, bhi, o.y, o.w);
+                int a0, a1, b0, b1;
+                iq_gray_pair<C>(alo, ahi, a0, a1);
+                iq_gray_pair<C>(blo, bhi, b0, b1);
+                o = make_float4((float)(a0 + b0), (float)(a0 - b0), (float)(a1 + b1), (float)(a1 - b1));
                 if (rown) {
                     const unsigned dlo = __vabsdiffu4(alo, blo) & mlo;
                     sq = __dp4a(dlo, dlo, sq);
@@ -246,20 +293,11 @@ __global__ void __launch_bounds__(IQ_THREADS, 4) k_psnr_ssim(IqaParams P)
             pair(2 * t, mlo0, mhi0, o0);
             if (t < IQ_R) pair(IQ2_COLS + 2 * t, mlo1, mhi1, o1);
         }
-        auto second = [](const float4 &o) { // (a0, b0, a1, b1) -> (a0^2 + b0^2, a0 b0, a1^2 + b1^2, a1 b1)
-            return make_float4(fmaf(o.x, o.x, o.y * o.y), o.x * o.y, fmaf(o.z, o.z, o.w * o.w), o.z * o.w);
-        };
         *reinterpret_cast<float4 *>(&s_ab[buf][2 * t]) = o0;
         if (t < IQ_R) *reinterpret_cast<float4 *>(&s_ab[buf][IQ2_COLS + 2 * t]) = o1;
-#if SRF_IQ_SP_SMEM
-        *reinterpret_cast<float4 *>(&s_sp[buf][2 * t]) = second(o0);
-        if (t < IQ_R) *reinterpret_cast<float4 *>(&s_sp[buf][IQ2_COLS + 2 * t]) = second(o1);
-#else
-        (void)second;
-#endif
     };
 
-    // open output rows: A[q][0][j] = partial (a, b) sums, A[q][1][j] = partial (a^2+b^2, ab) sums of S-map column q
+    // open output rows: A[q][0][j] = partial (s, d) sums, A[q][1][j] = partial (s^2, d^2) sums of S-map column q
     float2 A[2][2][TAPS - 1];
 #pragma unroll
     for (int q = 0; q < 2; ++q)
@@ -269,10 +307,14 @@ __global__ void __launch_bounds__(IQ_THREADS, 4) k_psnr_ssim(IqaParams P)
             for (int k = 0; k < TAPS - 1; ++k) A[q][s][k] = make_float2(0.f, 0.f);
 
     float ssum = 0.f;
-    unsigned int scount = 0;
     const int col0 = cx0 + 2 * t; // this thread's two S-map columns: col0, col0 + 1
     const bool ci0 = col0 >= R && col0 < w - R, ci1 = col0 + 1 >= R && col0 + 1 < w - R;
-    const float C1 = P.c1, C2 = P.c2;
+    // rows outside the map skip the pointwise stage altogether, columns outside it are skipped by a per-thread flag (a
+    // predicated FFMA: S of a column outside the image need not be finite when the caller's data_range makes C1, C2 tiny);
+    // the COUNT of accumulated values is rows x columns -- nothing is counted inside the loop
+    int cf0 = ci0 ? 1 : 0, cf1 = ci1 ? 1 : 0;
+    asm volatile("" : "+r"(cf0), "+r"(cf1)); // per-thread constants: kept in registers, not re-derived every row
+    const float K1 = 2.f * P.c1, K2 = 2.f * P.c2;
 
     L(r_first);
     L(r_first + 1);
@@ -287,81 +329,68 @@ __global__ void __launch_bounds__(IQ_THREADS, 4) k_psnr_ssim(IqaParams P)
     for (int r_in = r_first; r_in < r_last; ++r_in) {
         const int buf = r_in & 1;
         L(r_in + 4);
-        float2 hn[2][2]; // this row's horizontal sums: [q][(a, b) | (a^2+b^2, ab)]
+        float2 hn[2][2]; // this row's horizontal sums: [q][(s, d) | (s^2, d^2)]
         {
             // staged pixels 2t + (5 - R) .. + TAPS (TAPS + 1 of them, two per LDS.128): column 0 takes samples
-            // 0 .. TAPS-1, column 1 samples 1 .. TAPS, both with taps 0 .. TAPS-1
+            // 0 .. TAPS-1, column 1 samples 1 .. TAPS, both with taps 0 .. TAPS-1.  The second-order signals of a sample are
+            // ONE packed multiply (s^2, d^2): a^2 + b^2 = (s^2 + d^2) / 2 and a b = (s^2 - d^2) / 4 are taken after the
+            // filters, which are linear
             const float4 *pv = reinterpret_cast<const float4 *>(&s_ab[buf][2 * t + (IQ_R - R)]);
-#if SRF_IQ_SP_SMEM
-            const float4 *pw = reinterpret_cast<const float4 *>(&s_sp[buf][2 * t + (IQ_R - R)]);
-#endif
             static_assert(((IQ_R - R) & 1) == 0 && ((TAPS + 1) & 1) == 0, "pairs must stay 16-byte aligned");
 #pragma unroll
             for (int j = 0; j < (TAPS + 1) / 2; ++j) {
                 const float4 v = pv[j];
-#if SRF_IQ_SP_SMEM
-                const float4 u = pw[j];
-#endif
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     const int k = 2 * j + e;
-                    const float2 ab = e ? make_float2(v.z, v.w) : make_float2(v.x, v.y);
-#if SRF_IQ_SP_SMEM
-                    const float2 sp = e ? make_float2(u.z, u.w) : make_float2(u.x, u.y);
-#else
-                    const float2 sp = make_float2(fmaf(ab.x, ab.x, ab.y * ab.y), ab.x * ab.y);
-#endif
+                    const float2 sd = e ? make_float2(v.z, v.w) : make_float2(v.x, v.y);
+                    const float2 sq2 = __fmul2_rn(sd, sd);
                     if (k == 0) {
-                        hn[0][0] = f2mul(ab, iq_tap<R>(0));
-                        hn[0][1] = f2mul(sp, iq_tap<R>(0));
+                        hn[0][0] = f2mul(sd, iq_tap<R>(0));
+                        hn[0][1] = f2mul(sq2, iq_tap<R>(0));
                     } else if (k < TAPS) {
-                        hn[0][0] = f2fma(ab, iq_tap<R>(k), hn[0][0]);
-                        hn[0][1] = f2fma(sp, iq_tap<R>(k), hn[0][1]);
+                        hn[0][0] = f2fma(sd, iq_tap<R>(k), hn[0][0]);
+                        hn[0][1] = f2fma(sq2, iq_tap<R>(k), hn[0][1]);
                     }
                     if (k == 1) {
-                        hn[1][0] = f2mul(ab, iq_tap<R>(0));
-                        hn[1][1] = f2mul(sp, iq_tap<R>(0));
+                        hn[1][0] = f2mul(sd, iq_tap<R>(0));
+                        hn[1][1] = f2mul(sq2, iq_tap<R>(0));
                     } else if (k > 1) {
-                        hn[1][0] = f2fma(ab, iq_tap<R>(k - 1), hn[1][0]);
-                        hn[1][1] = f2fma(sp, iq_tap<R>(k - 1), hn[1][1]);
+                        hn[1][0] = f2fma(sd, iq_tap<R>(k - 1), hn[1][0]);
+                        hn[1][1] = f2fma(sq2, iq_tap<R>(k - 1), hn[1][1]);
                     }
                 }
             }
         }
         const int r = r_in - R;
-        const bool emit = r >= ry0;
-        const bool row_ok = r >= R && r < h - R;
+        float2 f[2][2];
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
-            float2 f[2];
 #pragma unroll
             for (int s = 0; s < 2; ++s) {
-                f[s] = f2fma(hn[q][s], iq_tap<R>(TAPS - 1), A[q][s][0]);
+                f[q][s] = f2fma(hn[q][s], iq_tap<R>(TAPS - 1), A[q][s][0]);
 #pragma unroll
                 for (int j = 0; j < TAPS - 2; ++j) A[q][s][j] = f2fma(hn[q][s], iq_tap<R>(TAPS - 2 - j), A[q][s][j + 1]);
                 A[q][s][TAPS - 2] = f2mul(hn[q][s], iq_tap<R>(0));
             }
-            if (emit) {
-                // the filtered signals are means of (x - 128): variances and the covariance do not see the offset, the
-                // luminance term needs the true means (ux, uy).  Packed where the (a, b) pairing allows it.
-                const float2 u = f[0];                                          // (ua, ub)
-                const float2 m = __fadd2_rn(u, make_float2(128.f, 128.f));      // (ux, uy)
-                const float2 uu = __fmul2_rn(u, u), mm = __fmul2_rn(m, m);
-                constexpr float COV = (R == 3) ? (float)(49.0 / 48.0) : 1.f;   // sample covariance for the 7x7 uniform window
-                float vsum = f[1].x - (uu.x + uu.y), vxy = fmaf(-u.x, u.y, f[1].y);
-                if (R == 3) {
-                    vsum *= COV;
-                    vxy *= COV;
-                }
-                const float A1 = fmaf(m.x + m.x, m.y, C1), A2 = fmaf(2.f, vxy, C2);
-                const float B1 = (mm.x + mm.y) + C1, B2 = vsum + C2;
+        }
+        if (r >= ry0 && r >= R && r < h - R) { // uniform: an S-map row this CTA owns
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                // With u = (mean s, mean d) and e = (mean s^2, mean d^2) of the (x - 128) signals:
+                //   ux + uy = u.s + 256, ux - uy = u.d;  2 ux uy = (p.s^2 - p.d^2) / 2, ux^2 + uy^2 = (p.s^2 + p.d^2) / 2
+                //   v = e - u^2 = (var s, var d);       2 vxy = (v.s - v.d) / 2,     vx + vy = (v.s + v.d) / 2
+                // The four factors of S are used DOUBLED (the 2s cancel in the quotient), so the constants enter as 2 C1, 2 C2.
+                const float2 u = f[q][0];
+                const float2 pp0 = __fadd2_rn(u, make_float2(256.f, 0.f));
+                const float2 pp = __fmul2_rn(pp0, pp0);
+                float2 v = __ffma2_rn(make_float2(-u.x, -u.y), u, f[q][1]);
+                if (R == 3) v = f2mul(v, (float)(49.0 / 48.0)); // sample covariance for the 7x7 uniform window
+                const float t1 = pp.x + K1, t2 = v.x + K2;
+                const float A1 = t1 - pp.y, B1 = t1 + pp.y, A2 = t2 - v.y, B2 = t2 + v.y;
                 float inv;
-                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(B1 * B2)); // B1 B2 >= C1 C2 = 380: no range handling needed
-                const float S = (A1 * A2) * inv;
-                if (row_ok && (q ? ci1 : ci0)) {
-                    ssum += S;
-                    scount++;
-                }
+                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(B1 * B2)); // B1 B2 >= 4 C1 C2 = 1521: no range handling needed
+                if (q ? cf1 : cf0) ssum = fmaf(A1 * A2, inv, ssum);
             }
         }
         if (r_in + 1 < r_last) G(r_in + 1);
@@ -371,7 +400,8 @@ __global__ void __launch_bounds__(IQ_THREADS, 4) k_psnr_ssim(IqaParams P)
     cp_async_wait<0>();
 
     double ds = (double)ssum;
-    unsigned long long dsq = sq, dcnt = scount;
+    const int own_rows = max(min(ry1, h - R) - max(ry0, R), 0); // S-map rows this CTA accumulated
+    unsigned long long dsq = sq, dcnt = (unsigned long long)own_rows * (unsigned)((ci0 ? 1 : 0) + (ci1 ? 1 : 0));
     int mxa = (int)((bits_a | (bits_a >> 8) | (bits_a >> 16) | (bits_a >> 24)) & 0xFFu);
     int mxb = (int)((bits_b | (bits_b >> 8) | (bits_b >> 16) | (bits_b >> 24)) & 0xFFu);
 #pragma unroll

@@ -8,10 +8,13 @@
 // A tile whose stored size differs from its canvas size is first squashed with cv2.resize's default INTER_LINEAR, as
 // the reference does for the padded edge tiles (1107-1109): OpenCV's own 11-bit fixed-point bilinear code for uint8
 // (IPP is not used for 8-bit linear), restated in oracle/resize_oracle.py::resize_linear_u8 and bit-exact against
-// cv2 4.13 for shrinking, the only direction merge_tiles can take (enlarging returns SRF_ERR_UNSUPPORTED).
+// cv2 4.13 in both directions (the vertical pass keeps the fraction above the first / below the last source row and clamps
+// its two row indices separately -- only enlarging reaches those rows).
 #include "srf_common.cuh"
 
 #include <math.h>
+
+#include <algorithm>
 
 namespace {
 
@@ -79,9 +82,59 @@ __global__ void __launch_bounds__(MG_BX *MG_BY) k_merge_tiles(const MergeTileDev
     for (int c = 0; c < C; ++c) o[c] = (uint8_t)min(max(__float2int_rz(__fdiv_rn(acc[c], den)), 0), 255); // astype(uint8): truncation
 }
 
-// OpenCV's INTER_LINEAR taps for uint8 (oracle/resize_oracle.py::linear_table): float32 sample position, clamped ends,
-// coefficients = cvRound(frac * 2048) as shorts
-void linear_table(int src, int dst, LinTap *tab)
+// ---- BlendingModule.weighted_average_fusion with CUSTOM weight maps (/root/reference/blending_module.py:661-760, the
+// `weights=` argument): per tile an (h, w) plane of float32 or float64 weights.  NumPy's arithmetic for the two cases:
+//   float32 map: acc += f32(tile) * w          -> float32 product, float32 sum
+//   float64 map: acc += f32(tile) * w          -> float64 product, the in-place add runs in float64 and is stored as float32
+// and the same for the weight accumulator; then acc / max(wsum, 1e-6), clip(0, 255), astype(uint8).  (Without custom maps
+// the call is the gather kernel with one pyramid level -- srf_laplacian_fuse(levels = 1).)
+struct WavgTileDev {
+    const uint8_t *data;
+    size_t pitch;
+    int h, w, y, x; // extent already cropped to the canvas
+    const void *wgt;
+    size_t wpitch; // bytes
+    int f64;
+};
+
+template <int C>
+__global__ void __launch_bounds__(MG_BX *MG_BY) k_weighted_average(const WavgTileDev *__restrict__ tiles, int n_tiles, uint8_t *__restrict__ canvas,
+                                                                    size_t pitch, int out_h, int out_w)
+{
+    pdl_enter();
+    const int px = blockIdx.x * MG_BX + threadIdx.x, py = blockIdx.y * MG_BY + threadIdx.y;
+    if (px >= out_w || py >= out_h) return;
+    float acc[C], wsum = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) acc[c] = 0.f;
+    for (int i = 0; i < n_tiles; ++i) { // list order = the reference's accumulation order
+        const WavgTileDev &t = tiles[i];
+        const int tx = px - t.x, ty = py - t.y;
+        if (tx < 0 || ty < 0 || tx >= t.w || ty >= t.h) continue;
+        const uint8_t *p = t.data + (size_t)ty * t.pitch + (size_t)tx * C;
+        const char *wrow = (const char *)t.wgt + (size_t)ty * t.wpitch;
+        if (t.f64) {
+            const double w = __ldg((const double *)wrow + tx);
+#pragma unroll
+            for (int c = 0; c < C; ++c) acc[c] = (float)__dadd_rn((double)acc[c], __dmul_rn((double)__ldg(p + c), w));
+            wsum = (float)__dadd_rn((double)wsum, w);
+        } else {
+            const float w = __ldg((const float *)wrow + tx);
+#pragma unroll
+            for (int c = 0; c < C; ++c) acc[c] = __fadd_rn(acc[c], __fmul_rn((float)__ldg(p + c), w));
+            wsum = __fadd_rn(wsum, w);
+        }
+    }
+    const float den = fmaxf(wsum, 1e-6f);
+    uint8_t *o = canvas + (size_t)py * pitch + (size_t)px * C;
+#pragma unroll
+    for (int c = 0; c < C; ++c) o[c] = (uint8_t)__float2int_rz(fminf(fmaxf(__fdiv_rn(acc[c], den), 0.f), 255.f)); // clip, then astype(uint8)
+}
+
+// OpenCV's INTER_LINEAR taps for uint8 (oracle/resize_oracle.py::linear_table): float32 sample position, coefficients =
+// cvRound(frac * 2048) as shorts.  Horizontal table: fraction reset to 0 at the clamped ends.  Vertical pass: fraction
+// kept, the two row indices clamped one by one (both taps then read the same row, each product truncated on its own).
+void linear_table(int src, int dst, LinTap *tab, bool vertical)
 {
     const double inv = (double)dst / (double)src;
     const double scale = 1.0 / inv;
@@ -89,16 +142,18 @@ void linear_table(int src, int dst, LinTap *tab)
         float f = (float)(((double)d + 0.5) * scale - 0.5);
         int s = (int)floorf(f);
         float fr = f - (float)s;
-        if (s < 0) {
-            fr = 0.f;
-            s = 0;
+        if (!vertical) {
+            if (s < 0) {
+                fr = 0.f;
+                s = 0;
+            }
+            if (s >= src - 1) {
+                fr = 0.f;
+                s = src - 1;
+            }
         }
-        if (s >= src - 1) {
-            fr = 0.f;
-            s = src - 1;
-        }
-        tab[d].i0 = s;
-        tab[d].i1 = s + 1 < src ? s + 1 : src - 1;
+        tab[d].i0 = std::min(std::max(s, 0), src - 1);
+        tab[d].i1 = std::min(std::max(s + 1, 0), src - 1);
         tab[d].a1 = (int)lrintf(fr * 2048.f);
         tab[d].a0 = (int)lrintf((1.f - fr) * 2048.f);
     }
@@ -108,8 +163,8 @@ int resize_linear_device(srf_ctx *ctx, const uint8_t *d_src, size_t spitch, int 
                          LinTap *d_tab, cudaStream_t st)
 {
     std::vector<LinTap> tab((size_t)dw + dh);
-    linear_table(w, dw, tab.data());
-    linear_table(h, dh, tab.data() + dw);
+    linear_table(w, dw, tab.data(), false);
+    linear_table(h, dh, tab.data() + dw, true);
     SRF_CHECK_CUDA(ctx, cudaMemcpyAsync(d_tab, tab.data(), tab.size() * sizeof(LinTap), cudaMemcpyHostToDevice, st));
     dim3 grid(srf_ceil_div(dw, MG_BX), srf_ceil_div(dh, MG_BY)), block(MG_BX, MG_BY);
     srf_launch_scope scope(ctx, "resize_linear", (double)C * ((double)h * w + (double)dh * dw), st);
@@ -134,14 +189,6 @@ int check_merge_args(srf_ctx *ctx, const srf_merge_tile *tiles, int n, int C, in
         SRF_REQUIRE(ctx, t.y >= 0 && t.x >= 0, "merge_tiles: tile %d has a negative position (%d,%d)", i, t.y, t.x);
         SRF_REQUIRE(ctx, (t.wy == nullptr) == (t.wl == nullptr) && (t.wl == nullptr) == (t.wr == nullptr),
                     "merge_tiles: tile %d needs all three weight tables or none", i);
-        if (t.out_h != t.h || t.out_w != t.w) {
-            if (t.out_h > t.h || t.out_w > t.w) {
-                srf_set_error(ctx, "merge_tiles: tile %d would be ENLARGED (%dx%d -> %dx%d); only the shrinking INTER_LINEAR path of "
-                                   "cv2.resize is implemented",
-                              i, t.w, t.h, t.out_w, t.out_h);
-                return SRF_ERR_UNSUPPORTED;
-            }
-        }
     }
     return SRF_OK;
 }
@@ -213,13 +260,123 @@ int merge_device(srf_ctx *ctx, const srf_merge_tile *tiles, int n, int C, int ou
     return SRF_OK;
 }
 
+int check_wavg_args(srf_ctx *ctx, const srf_wavg_tile *tiles, int n, int C, int out_h, int out_w, const void *canvas, size_t pitch)
+{
+    SRF_REQUIRE(ctx, tiles && n >= 1, "weighted_average: no tiles");
+    SRF_REQUIRE(ctx, C == 1 || C == 3, "weighted_average: channels must be 1 or 3 (got %d)", C);
+    SRF_REQUIRE(ctx, out_h >= 1 && out_w >= 1 && canvas, "weighted_average: empty canvas");
+    SRF_REQUIRE(ctx, pitch >= (size_t)out_w * C, "weighted_average: canvas pitch < row bytes");
+    for (int i = 0; i < n; ++i) {
+        const srf_wavg_tile &t = tiles[i];
+        SRF_REQUIRE(ctx, t.data && t.weight && t.h >= 1 && t.w >= 1, "weighted_average: tile %d is empty", i);
+        SRF_REQUIRE(ctx, t.pitch >= (size_t)t.w * C, "weighted_average: tile %d pitch < row bytes", i);
+        SRF_REQUIRE(ctx, t.y >= 0 && t.x >= 0, "weighted_average: tile %d has a negative position (%d,%d)", i, t.y, t.x);
+        const int ch = std::max(std::min(t.y + t.h, out_h) - t.y, 0), cw = std::max(std::min(t.x + t.w, out_w) - t.x, 0);
+        // the reference multiplies tile[:ch, :cw] by weight[:ch, :cw]: a smaller map does not broadcast (ValueError there)
+        SRF_REQUIRE(ctx, t.weight_h >= ch && t.weight_w >= cw, "weighted_average: weight map %d is %dx%d, the tile's part of the canvas %dx%d", i,
+                    t.weight_w, t.weight_h, cw, ch);
+        SRF_REQUIRE(ctx, t.weight_pitch >= (size_t)t.weight_w * (t.weight_f64 ? 8 : 4), "weighted_average: weight map %d pitch < row bytes", i);
+    }
+    return SRF_OK;
+}
+
+// tiles[i].data / .weight are DEVICE pointers here
+int wavg_device(srf_ctx *ctx, const srf_wavg_tile *tiles, int n, int C, int out_h, int out_w, uint8_t *d_canvas, size_t pitch, cudaStream_t st)
+{
+    int rc;
+    if ((rc = srf_reserve(ctx, ctx->ws_merge, sizeof(WavgTileDev) * (size_t)n))) return rc;
+    std::vector<WavgTileDev> dev(n);
+    double cov = 0;
+    for (int i = 0; i < n; ++i) {
+        const srf_wavg_tile &t = tiles[i];
+        WavgTileDev &d = dev[i];
+        d.data = t.data;
+        d.pitch = t.pitch;
+        d.y = t.y;
+        d.x = t.x;
+        d.h = std::max(std::min(t.y + t.h, out_h) - t.y, 0);
+        d.w = std::max(std::min(t.x + t.w, out_w) - t.x, 0);
+        d.wgt = t.weight;
+        d.wpitch = t.weight_pitch;
+        d.f64 = t.weight_f64;
+        cov += (double)d.h * d.w * (C + (t.weight_f64 ? 8 : 4));
+    }
+    SRF_CHECK_CUDA(ctx, cudaMemcpyAsync(ctx->ws_merge.ptr, dev.data(), sizeof(WavgTileDev) * n, cudaMemcpyHostToDevice, st));
+    dim3 grid(srf_ceil_div(out_w, MG_BX), srf_ceil_div(out_h, MG_BY)), block(MG_BX, MG_BY);
+    srf_launch_scope scope(ctx, "weighted_average", cov + (double)C * out_h * out_w, st);
+    if (C == 3)
+        srf_launch_pdl(k_weighted_average<3>, grid, block, 0, st, (const WavgTileDev *)ctx->ws_merge.ptr, n, d_canvas, pitch, out_h, out_w);
+    else
+        srf_launch_pdl(k_weighted_average<1>, grid, block, 0, st, (const WavgTileDev *)ctx->ws_merge.ptr, n, d_canvas, pitch, out_h, out_w);
+    SRF_CHECK_CUDA(ctx, cudaGetLastError());
+    return SRF_OK;
+}
+
 } // namespace
 
-extern "C" int srf_resize_linear_taps(int src, int dst, int *idx2, int *coef2)
+extern "C" int srf_weighted_average(srf_ctx *ctx, const srf_wavg_tile *tiles, int n_tiles, int channels, int out_h, int out_w, uint8_t *d_canvas,
+                                    size_t canvas_pitch, void *stream)
+{
+    if (!ctx) return SRF_ERR_ARG;
+    int rc = check_wavg_args(ctx, tiles, n_tiles, channels, out_h, out_w, d_canvas, canvas_pitch);
+    if (rc) return rc;
+    SRF_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+    rc = wavg_device(ctx, tiles, n_tiles, channels, out_h, out_w, d_canvas, canvas_pitch, (cudaStream_t)stream);
+    return rc ? rc : srf_note_device_work(ctx, (cudaStream_t)stream);
+}
+
+extern "C" int srf_weighted_average_host(srf_ctx *ctx, const srf_wavg_tile *tiles, int n_tiles, int channels, int out_h, int out_w,
+                                         uint8_t *h_canvas, size_t canvas_pitch)
+{
+    if (!ctx) return SRF_ERR_ARG;
+    int rc = check_wavg_args(ctx, tiles, n_tiles, channels, out_h, out_w, h_canvas, canvas_pitch);
+    if (rc) return rc;
+    SRF_CHECK_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (int hrc = srf_host_enter(ctx)) return hrc;
+    std::vector<srf_wavg_tile> dt(tiles, tiles + n_tiles);
+    std::vector<size_t> off(n_tiles), woff(n_tiles);
+    size_t total = 0, h2d = 0;
+    for (int i = 0; i < n_tiles; ++i) { // only the part of a tile (and of its map) that lies on the canvas travels
+        const int ch = std::max(std::min(tiles[i].y + tiles[i].h, out_h) - tiles[i].y, 0), cw = std::max(std::min(tiles[i].x + tiles[i].w, out_w) - tiles[i].x, 0);
+        dt[i].h = std::max(ch, 1);
+        dt[i].w = std::max(cw, 1);
+        off[i] = total;
+        dt[i].pitch = srf_align_up((size_t)dt[i].w * channels, 16);
+        total += srf_align_up(dt[i].pitch * dt[i].h, 256);
+        woff[i] = total;
+        dt[i].weight_pitch = srf_align_up((size_t)dt[i].w * (tiles[i].weight_f64 ? 8 : 4), 16);
+        dt[i].weight_h = dt[i].h;
+        dt[i].weight_w = dt[i].w;
+        total += srf_align_up(dt[i].weight_pitch * dt[i].h, 256);
+    }
+    const size_t cpitch = srf_align_up((size_t)out_w * channels, 256);
+    if ((rc = srf_reserve(ctx, ctx->ws_stage_in, total))) return rc;
+    if ((rc = srf_reserve(ctx, ctx->ws_stage_out, cpitch * (size_t)out_h))) return rc;
+    cudaStream_t st = ctx->own_stream;
+    uint8_t *din = (uint8_t *)ctx->ws_stage_in.ptr, *dcanvas = (uint8_t *)ctx->ws_stage_out.ptr;
+    for (int i = 0; i < n_tiles; ++i) {
+        const size_t esz = tiles[i].weight_f64 ? 8 : 4;
+        dt[i].data = din + off[i];
+        dt[i].weight = din + woff[i];
+        SRF_CHECK_CUDA(ctx, cudaMemcpy2DAsync(din + off[i], dt[i].pitch, tiles[i].data, tiles[i].pitch, (size_t)dt[i].w * channels, dt[i].h,
+                                              cudaMemcpyHostToDevice, st));
+        SRF_CHECK_CUDA(ctx, cudaMemcpy2DAsync(din + woff[i], dt[i].weight_pitch, tiles[i].weight, tiles[i].weight_pitch, (size_t)dt[i].w * esz, dt[i].h,
+                                              cudaMemcpyHostToDevice, st));
+        h2d += (size_t)dt[i].w * dt[i].h * (channels + esz);
+    }
+    if ((rc = wavg_device(ctx, dt.data(), n_tiles, channels, out_h, out_w, dcanvas, cpitch, st))) return rc;
+    SRF_CHECK_CUDA(ctx, cudaMemcpy2DAsync(h_canvas, canvas_pitch, dcanvas, cpitch, (size_t)out_w * channels, out_h, cudaMemcpyDeviceToHost, st));
+    SRF_CHECK_CUDA(ctx, cudaStreamSynchronize(st));
+    ctx->last_h2d = h2d;
+    ctx->last_d2h = (size_t)out_w * channels * out_h;
+    return SRF_OK;
+}
+
+static int linear_taps_out(int src, int dst, bool vertical, int *idx2, int *coef2)
 {
     if (src < 1 || dst < 1 || !idx2 || !coef2) return SRF_ERR_ARG;
     std::vector<LinTap> tab((size_t)dst);
-    linear_table(src, dst, tab.data());
+    linear_table(src, dst, tab.data(), vertical);
     for (int d = 0; d < dst; ++d) {
         idx2[2 * d] = tab[d].i0;
         idx2[2 * d + 1] = tab[d].i1;
@@ -227,6 +384,13 @@ extern "C" int srf_resize_linear_taps(int src, int dst, int *idx2, int *coef2)
         coef2[2 * d + 1] = tab[d].a1;
     }
     return SRF_OK;
+}
+
+extern "C" int srf_resize_linear_taps(int src, int dst, int *idx2, int *coef2) { return linear_taps_out(src, dst, false, idx2, coef2); }
+
+extern "C" int srf_resize_linear_taps_axis(int src, int dst, int vertical, int *idx2, int *coef2)
+{
+    return linear_taps_out(src, dst, vertical != 0, idx2, coef2);
 }
 
 extern "C" int srf_merge_tiles(srf_ctx *ctx, const srf_merge_tile *tiles, int n_tiles, int channels, int out_h, int out_w, uint8_t *d_canvas,

@@ -200,6 +200,38 @@ def main():
     out["seam_scores_t1"] = np.array([[sbm._compute_ssim(t1[wy:wy + 16, wx:wx + 16], roi[wy:wy + 16, wx:wx + 16])
                                        for wx in range(0, 113, 8)] for wy in range(0, 113, 8)])
 
+    # ---- appended in round 2 (after every earlier draw, so the vectors above do not move) ----
+    # merge_tiles on tiles that come back SMALLER than output_w x output_h (a 1.5x stand-in under output_scale 2): the
+    # reference enlarges them with cv2.resize's default INTER_LINEAR (tiling_module.py:1107-1109)
+    for t_ in mt:
+        t_.data = cv2.resize(out["merge_tiles"][mt.index(t_)], (96, 96), interpolation=cv2.INTER_AREA)
+    out["merge_up_tiles"] = np.stack([t_.data for t_ in mt])
+    out["merge_up_out_blend"] = tmm.merge_tiles(mt, 300, 200, blending=True)
+    out["merge_up_out_plain"] = tmm.merge_tiles(mt, 300, 200, blending=False)
+
+    # weighted_average_fusion with CUSTOM weight maps (blending_module.py:661-760, `weights=`): float32 maps, float64
+    # maps, a list shorter than the tile list (the last tile gets the generated cosine map), maps larger than the tile,
+    # a tile that overhangs the canvas, RGB and gray
+    wq_tiles = [synth(rng, 64, 80), synth(rng, 64, 80), synth(rng, 48, 96), synth(rng, 64, 64)]
+    wq_pos = [(0, 0), (0, 60), (40, 10), (50, 90)]  # (y, x)
+    wq_w32 = [rng.random((64, 80), dtype=np.float32), (rng.random((70, 90), dtype=np.float32) * 3).astype(np.float32),
+              rng.random((48, 96, 1), dtype=np.float32)]
+    wq_w64 = [rng.random((64, 80)), rng.random((64, 80)) * 1e-3, rng.random((48, 96)) + 0.5, rng.random((64, 64))]
+    wbm = rb.BlendingModule(num_levels=5)
+    infos = [rb.TileInfo(t, int(x), int(y), 0, 0) for t, (y, x) in zip(wq_tiles, wq_pos)]
+    for i, t in enumerate(wq_tiles):
+        out[f"wcus_t{i}"] = t
+    out["wcus_pos"] = np.array(wq_pos, np.int32)
+    for i, m in enumerate(wq_w32):
+        out[f"wcus_w32_{i}"] = m
+    for i, m in enumerate(wq_w64):
+        out[f"wcus_w64_{i}"] = m
+    out["wcus_out32"] = wbm.weighted_average_fusion(infos, weights=wq_w32, output_shape=(100, 150))
+    out["wcus_out64"] = wbm.weighted_average_fusion(infos, weights=wq_w64)
+    out["wcus_mixed"] = wbm.weighted_average_fusion(infos, weights=[wq_w32[0], wq_w64[1]], weight_type=rb.WeightType.LINEAR)
+    ginfos = [rb.TileInfo(t[:, :, 1].copy(), int(x), int(y), 0, 0) for t, (y, x) in zip(wq_tiles, wq_pos)]
+    out["wcus_gray64"] = wbm.weighted_average_fusion(ginfos, weights=[wq_w64[0], wq_w32[1]], output_shape=(110, 140))
+
     np.savez_compressed(os.path.join(HERE, "reference_vectors.npz"), **out)
     print("wrote", os.path.join(HERE, "reference_vectors.npz"), os.path.getsize(os.path.join(HERE, "reference_vectors.npz")) // 1024, "KiB")
     print("cv2", cv2.__version__, "numpy", np.__version__)

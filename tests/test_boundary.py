@@ -167,6 +167,12 @@ def test_linear_tap_tables_and_blend_weight(srs, golden, oracle):
         i0, i1, a0, a1 = oracle.resize_oracle.linear_table(src, dst)
         assert np.array_equal(idx[:, 0], i0) and np.array_equal(idx[:, 1], i1)
         assert np.array_equal(co[:, 0], a0) and np.array_equal(co[:, 1], a1)
+    for src, dst, vertical in [(96, 128, 1), (96, 128, 0), (64, 128, 1), (7, 30, 1), (128, 104, 1), (1, 9, 1), (300, 301, 1)]:
+        idx, co = np.zeros((dst, 2), np.int32), np.zeros((dst, 2), np.int32)
+        assert lib.srf_resize_linear_taps_axis(src, dst, vertical, idx.ctypes.data, co.ctypes.data) == 0
+        i0, i1, a0, a1 = oracle.resize_oracle.linear_table(src, dst, vertical=bool(vertical))
+        assert np.array_equal(idx[:, 0], i0) and np.array_equal(idx[:, 1], i1)
+        assert np.array_equal(co[:, 0], a0) and np.array_equal(co[:, 1], a1)
     tm = srs.TilingModule(64, 0.25, "mirror", enable_content_aware=False)
     m = golden["merge_meta"][4]
     meta = srs.tiling_module.TileMetadata(global_x=int(m[0]), global_y=int(m[1]), input_w=int(m[2]), input_h=int(m[3]),

@@ -365,9 +365,18 @@ def test_merge_tiles_bit_exact_vs_reference(srs, golden, oracle):
     thin = [t for t in tm2.split_array(synth(rng, 300, 700))]  # last column 85 px wide: its scaled "overlap" (240) exceeds
     with pytest.raises(ValueError):                             # the 170 px tile -- the reference's ramp fails to broadcast
         tm2.merge_tiles(thin, 1400, 600)
-    big = srs.tiling_module.Tile(metadata=srs.tiling_module.TileMetadata(output_w=600, output_h=600), data=np.zeros((512, 512, 3), np.uint8))
-    with pytest.raises(NotImplementedError):
-        tm2.merge_tiles([big], 600, 600)  # enlarging a tile: cv2.resize's other INTER_LINEAR path, not built
+    # tiles the upscaler returned SMALLER than their canvas size are enlarged (cv2.resize INTER_LINEAR, tiling_module.py:1107-1109):
+    # the reference's own output for 1.5x data under output_scale 2 (golden), then mixed directions against the oracle
+    up_tiles = [(d, *t[1:]) for d, t in zip(golden["merge_up_tiles"], tiles)]
+    assert np.array_equal(tm.merge_tiles(_merge_tiles_objects(srs, up_tiles), w, h, blending=True), golden["merge_up_out_blend"])
+    dev_up = tm.merge_tiles(_merge_tiles_objects(srs, up_tiles, to_device=True), w, h, blending=False)
+    assert np.array_equal(dev_up.cpu().numpy(), golden["merge_up_out_plain"])
+    mixed = []
+    for k, t in enumerate(ref_tiles):
+        hh, ww = [(300, 512), (512, 333), (700, 640), (512, 512), (97, 1201)][k % 5]
+        mixed.append((synth(rng, hh, ww), *t[1:]))
+    want = oracle.tiling_oracle.merge_tiles(mixed, 1440, 1200, 2.0, True)
+    assert np.array_equal(tm2.merge_tiles(_merge_tiles_objects(srs, mixed), 1440, 1200), want)
 
 
 # ------------------------------------------------------------------ bicubic resize + down-sample comparison (row N1)
@@ -601,8 +610,42 @@ def test_weighted_average_fusion_vs_reference_golden(srs, golden):
     assert np.array_equal(got, golden["wavg_ragged_out"])
     t4 = [np.ascontiguousarray(golden[f"fuse_linear6_t{i}"]) for i in range(4)]
     assert np.array_equal(bm.weighted_average_fusion(t4), golden["wavg_grid_out"])  # bare arrays: sqrt-grid, max extents
-    with pytest.raises(NotImplementedError):
-        bm.weighted_average_fusion(t4, weights=[np.ones((64, 64), np.float32)] * 4)
+    # unit maps given explicitly == a plain average of the tiles where they overlap (here they do not): same canvas as
+    # the reference computes for weights of ones
+    ones = bm.weighted_average_fusion(t4, weights=[np.ones((64, 64), np.float32)] * 4)
+    assert np.array_equal(ones, np.vstack([np.hstack([t4[0], t4[1]]), np.hstack([t4[2], t4[3]])]))
+
+
+def test_weighted_average_custom_maps_vs_reference_golden(srs, golden, oracle):
+    """weighted_average_fusion(weights=...) through srf_weighted_average[_host]: the reference's own outputs for float32,
+    float64 and mixed map lists, RGB and gray, host arrays and CUDA tensors; then a larger random case against the oracle"""
+    import torch
+    tiles = [np.ascontiguousarray(golden[f"wcus_t{i}"]) for i in range(4)]
+    pos = [tuple(int(v) for v in p) for p in golden["wcus_pos"]]
+    w32 = [golden[f"wcus_w32_{i}"] for i in range(3)]
+    w64 = [golden[f"wcus_w64_{i}"] for i in range(4)]
+    bm = srs.BlendingModule(num_levels=5)
+    infos = [srs.TileInfo(t, x, y, 0, 0) for t, (y, x) in zip(tiles, pos)]
+    assert np.array_equal(bm.weighted_average_fusion(infos, weights=w32, output_shape=(100, 150)), golden["wcus_out32"])
+    assert np.array_equal(bm.weighted_average_fusion(infos, weights=w64), golden["wcus_out64"])
+    assert np.array_equal(bm.weighted_average_fusion(infos, weights=[w32[0], w64[1]], weight_type=srs.WeightType.LINEAR), golden["wcus_mixed"])
+    ginfos = [srs.TileInfo(np.ascontiguousarray(t[:, :, 1]), x, y, 0, 0) for t, (y, x) in zip(tiles, pos)]
+    assert np.array_equal(bm.weighted_average_fusion(ginfos, weights=[w64[0], w32[1]], output_shape=(110, 140)), golden["wcus_gray64"])
+    dinfos = [srs.TileInfo(torch.from_numpy(t).cuda(), x, y, 0, 0) for t, (y, x) in zip(tiles, pos)]
+    dev = bm.weighted_average_fusion(dinfos, weights=[torch.from_numpy(w64[0]).cuda(), w64[1], w64[2], w64[3]])
+    assert dev.is_cuda and np.array_equal(dev.cpu().numpy(), golden["wcus_out64"])
+    rng = np.random.default_rng(77)
+    big = [synth(rng, 300, 420) for _ in range(5)]
+    bpos = [(0, 0), (0, 380), (250, 100), (260, 500), (500, 0)]
+    maps = [rng.random((300, 420)) if k % 2 else rng.random((300, 420), dtype=np.float32) for k in range(5)]
+    maps[3] = -maps[3]  # negative weights: the denominator clamps at 1e-6, the quotient clips
+    want = oracle.fusion_oracle.weighted_average_custom(big, bpos, maps, (700, 900))
+    got = bm.weighted_average_fusion([srs.TileInfo(t, x, y, 0, 0) for t, (y, x) in zip(big, bpos)], weights=maps, output_shape=(700, 900))
+    assert np.array_equal(got, want)
+    with pytest.raises(ValueError):  # a map smaller than its tile does not broadcast in the reference either
+        bm.weighted_average_fusion(infos, weights=[np.ones((10, 10), np.float32)])
+    with pytest.raises(ValueError):
+        bm.weighted_average_fusion(infos, weights=w32, row_range=(0, 10))
 
 
 def test_config_sized_two_tile_fuse_and_iqa_vs_oracle(srs, oracle):

@@ -112,3 +112,60 @@ def test_vertical_accumulate_form_keeps_the_summation_order():
         for k in range(1, 2 * R + 1):
             v = fma(h[r - R + k], taps[k], v)
         assert outs[r] == v
+
+
+def test_sum_difference_form_of_ssim_in_float32_matches_the_float64_oracle():
+    """k_psnr_ssim filters the packed signal (s, d) = (a + b, a - b) of the centred grays and its square (s^2, d^2) -- one
+    packed multiply per sample instead of a^2 + b^2 and a b -- and rebuilds S from the four filtered values with every
+    factor doubled:  2 ux uy + C1 ~ p.s^2 - p.d^2 + 2 C1,  ux^2 + uy^2 + C1 ~ p.s^2 + p.d^2 + 2 C1  (p = (u.s + 256, u.d)),
+    2 vxy + C2 ~ v.s - v.d + 2 C2,  vx + vy + C2 ~ v.s + v.d + 2 C2  (v = e - u^2).  Emulated here in float32 (horizontal
+    pass, then the vertical one, as the kernel) on textured, flat, saturated and anti-correlated pairs."""
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+    from oracle import iqa_oracle
+    from helpers import synth
+
+    taps64 = iqa_oracle.gaussian_taps()
+    taps = taps64.astype(f32)
+    R = 5
+
+    def filt(x):  # float32, horizontal then vertical, mul + add in tap order
+        h, w = x.shape
+        t = np.zeros((h, w - 2 * R), f32)
+        for k in range(2 * R + 1):
+            t = (t + x[:, k:k + w - 2 * R] * taps[k]).astype(f32)
+        o = np.zeros((h - 2 * R, w - 2 * R), f32)
+        for k in range(2 * R + 1):
+            o = (o + t[k:k + h - 2 * R] * taps[k]).astype(f32)
+        return o
+
+    def kernel_ssim(ga, gb, data_range=255.0):
+        a, b = ga.astype(np.int32) - 128, gb.astype(np.int32) - 128
+        s, d = (a + b).astype(f32), (a - b).astype(f32)
+        us, ud = filt(s), filt(d)
+        es, ed = filt((s * s).astype(f32)), filt((d * d).astype(f32))
+        k1, k2 = f32(2) * f32((0.01 * data_range) ** 2), f32(2) * f32((0.03 * data_range) ** 2)
+        ps = (us + f32(256)).astype(f32)
+        pps, ppd = (ps * ps).astype(f32), (ud * ud).astype(f32)
+        vs, vd = (es - us * us).astype(f32), (ed - ud * ud).astype(f32)
+        t1, t2 = (pps + k1).astype(f32), (vs + k2).astype(f32)
+        a1, b1, a2, b2 = t1 - ppd, t1 + ppd, t2 - vd, t2 + vd
+        smap = ((a1 * a2).astype(f32) / (b1 * b2).astype(f32)).astype(f32)
+        return float(smap.astype(np.float64).mean())
+
+    rng = np.random.default_rng(11)
+    x = synth(rng, 96, 160, 1)
+    noisy = np.clip(x.astype(np.int32) + rng.integers(-12, 13, x.shape), 0, 255).astype(np.uint8)
+    cases = {
+        "textured": (x, noisy),
+        "flat bright": (np.full_like(x, 255), np.full_like(x, 254)),
+        "flat dark": (np.zeros_like(x), np.ones_like(x)),
+        "saturated halves": (np.where(np.arange(160) < 80, 255, 0).astype(np.uint8)[None].repeat(96, 0), noisy),
+        "negative": (x, 255 - x),
+        "identical": (x, x.copy()),
+        "checkerboard": ((np.indices(x.shape).sum(0) % 2 * 255).astype(np.uint8), x),
+    }
+    for name, (ga, gb) in cases.items():
+        want = float(iqa_oracle.ssim_map_interior(ga, gb).mean(dtype=np.float64))
+        got = kernel_ssim(ga, gb)
+        assert abs(got - want) <= 2e-6 * max(1.0, abs(want)), (name, got, want)

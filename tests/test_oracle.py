@@ -157,6 +157,30 @@ def test_weighted_average_is_single_level_fusion(golden, oracle):
     assert np.array_equal(got, golden["wavg_grid_out"])
 
 
+def _wcus_case(golden):
+    tiles = [golden[f"wcus_t{i}"] for i in range(4)]
+    pos = [tuple(int(v) for v in p) for p in golden["wcus_pos"]]
+    w32 = [golden[f"wcus_w32_{i}"] for i in range(3)]
+    w64 = [golden[f"wcus_w64_{i}"] for i in range(4)]
+    return tiles, pos, w32, w64
+
+
+def test_weighted_average_with_custom_maps_matches_reference(golden, oracle):
+    """weighted_average_fusion(weights=...) run by the reference itself: float32 maps (one larger than its tile, one
+    (h, w, 1), the last tile on the generated map, a tile cropped by output_shape), float64 maps (float64 products and
+    sums stored back as float32), a mixed list, gray tiles"""
+    tiles, pos, w32, w64 = _wcus_case(golden)
+    fo = oracle.fusion_oracle
+    assert np.array_equal(fo.weighted_average_custom(tiles, pos, w32, (100, 150)), golden["wcus_out32"])
+    assert np.array_equal(fo.weighted_average_custom(tiles, pos, w64), golden["wcus_out64"])
+    assert np.array_equal(fo.weighted_average_custom(tiles, pos, [w32[0], w64[1]], kind="linear"), golden["wcus_mixed"])
+    gray = [t[:, :, 1].copy() for t in tiles]
+    assert np.array_equal(fo.weighted_average_custom(gray, pos, [w64[0], w32[1]], (110, 140)), golden["wcus_gray64"])
+    # the two precisions really differ on this input: the float64 rules are not decoration
+    narrow = fo.weighted_average_custom(tiles, pos, [m.astype(np.float32) for m in w64])
+    assert not np.array_equal(narrow, golden["wcus_out64"])
+
+
 # ------------------------------------------------------------------ bicubic resize (cv2.resize INTER_CUBIC; row N1)
 def _resize_agreement(got, want):
     d = np.abs(got.astype(np.int16) - want.astype(np.int16))
@@ -222,12 +246,28 @@ def test_merge_oracle_matches_reference(golden, oracle):
     assert np.array_equal(oracle.resize_oracle.resize_linear_u8(d2, ow2, oh2), golden["merge_squash_2"])
 
 
-def test_linear_resize_oracle_vs_cv2_shrinking(oracle):
+def test_linear_resize_oracle_vs_cv2_every_direction(oracle):
+    """cv2.resize's default INTER_LINEAR on uint8, shrinking and enlarging (the vertical pass treats the rows above the
+    first / below the last source row differently from the horizontal table -- only enlarging sees it)"""
     cv2 = pytest.importorskip("cv2")
     rng = np.random.default_rng(14)
-    for (h, w, c, dh, dw) in [(128, 128, 3, 104, 108), (256, 256, 3, 53, 256), (90, 77, 1, 31, 40), (64, 64, 3, 64, 64)]:
+    cases = [(128, 128, 3, 104, 108), (256, 256, 3, 53, 256), (90, 77, 1, 31, 40), (64, 64, 3, 64, 64), (96, 96, 3, 128, 128),
+             (64, 64, 3, 128, 128), (300, 400, 3, 700, 900), (33, 47, 1, 66, 94), (8, 16, 1, 20, 13), (1, 1, 3, 5, 7), (50, 3, 3, 49, 200)]
+    for _ in range(150):
+        h, w = (int(v) for v in rng.integers(1, 90, 2))
+        cases.append((h, w, int(rng.choice([1, 3])), int(rng.integers(1, 260)), int(rng.integers(1, 260))))
+    for (h, w, c, dh, dw) in cases:
         img = rng.integers(0, 256, (h, w, c) if c > 1 else (h, w), dtype=np.uint8)
         assert np.array_equal(oracle.resize_oracle.resize_linear_u8(img, dw, dh), cv2.resize(img, (dw, dh))), (h, w, c, dh, dw)
+
+
+def test_merge_oracle_enlarges_like_the_reference(golden, oracle):
+    """the reference's own merge_tiles on tiles the stand-in upscaled by 1.5x only (output_scale 2): interior tiles are
+    enlarged 96 -> 128, the padded edge tiles enlarged or squashed per axis"""
+    tiles, (w, h) = merge_case(golden)
+    up = [(d, *t[1:]) for d, t in zip(golden["merge_up_tiles"], tiles)]
+    assert np.array_equal(oracle.tiling_oracle.merge_tiles(up, w, h, 2.0, True), golden["merge_up_out_blend"])
+    assert np.array_equal(oracle.tiling_oracle.merge_tiles(up, w, h, 2.0, False), golden["merge_up_out_plain"])
 
 
 # ------------------------------------------------------------------ detect_seams (row N4)
