@@ -86,7 +86,7 @@ __device__ __forceinline__ void iq_load_pair(const uint8_t *row, int byte_off, i
 // are split into byte halves so that two IDP.4A per pixel form the sum; the -128 rides in the rounding constant
 // (128 << 15 is a multiple of the shift, so the arithmetic shift gives gray - 128 exactly)
 #ifndef SRF_IQ_DP2A
-#define SRF_IQ_DP2A 0
+#define SRF_IQ_DP2A 1 // gray from two IDP.2A (16-bit coefficients) instead of two IDP.4A + shift-add: 1.287 -> 1.280 ms at 200 MP
 #endif
 template <int C>
 __device__ __forceinline__ void iq_gray_pair(unsigned lo, unsigned hi, int &g0, int &g1)
@@ -325,45 +325,40 @@ __global__ void __launch_bounds__(IQ_THREADS, 4) k_psnr_ssim(IqaParams P)
     G(r_first);
     __syncthreads();
 
-#pragma unroll 1
-    for (int r_in = r_first; r_in < r_last; ++r_in) {
-        const int buf = r_in & 1;
-        L(r_in + 4);
-        float2 hn[2][2]; // this row's horizontal sums: [q][(s, d) | (s^2, d^2)]
-        {
-            // staged pixels 2t + (5 - R) .. + TAPS (TAPS + 1 of them, two per LDS.128): column 0 takes samples
-            // 0 .. TAPS-1, column 1 samples 1 .. TAPS, both with taps 0 .. TAPS-1.  The second-order signals of a sample are
-            // ONE packed multiply (s^2, d^2): a^2 + b^2 = (s^2 + d^2) / 2 and a b = (s^2 - d^2) / 4 are taken after the
-            // filters, which are linear
-            const float4 *pv = reinterpret_cast<const float4 *>(&s_ab[buf][2 * t + (IQ_R - R)]);
-            static_assert(((IQ_R - R) & 1) == 0 && ((TAPS + 1) & 1) == 0, "pairs must stay 16-byte aligned");
+    // ---- the stages of one row as lambdas; the loop below orders them ----
+    // H: staged pixels 2t + (5 - R) .. + TAPS (TAPS + 1 of them, two per LDS.128): column 0 takes samples 0 .. TAPS-1,
+    // column 1 samples 1 .. TAPS, both with taps 0 .. TAPS-1.  The second-order signals of a sample are ONE packed multiply
+    // (s^2, d^2): a^2 + b^2 = (s^2 + d^2) / 2 and a b = (s^2 - d^2) / 4 are taken after the filters, which are linear
+    auto H = [&](int buf, float2 (&hn)[2][2]) {
+        const float4 *pv = reinterpret_cast<const float4 *>(&s_ab[buf][2 * t + (IQ_R - R)]);
+        static_assert(((IQ_R - R) & 1) == 0 && ((TAPS + 1) & 1) == 0, "pairs must stay 16-byte aligned");
 #pragma unroll
-            for (int j = 0; j < (TAPS + 1) / 2; ++j) {
-                const float4 v = pv[j];
+        for (int j = 0; j < (TAPS + 1) / 2; ++j) {
+            const float4 v = pv[j];
 #pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int k = 2 * j + e;
-                    const float2 sd = e ? make_float2(v.z, v.w) : make_float2(v.x, v.y);
-                    const float2 sq2 = __fmul2_rn(sd, sd);
-                    if (k == 0) {
-                        hn[0][0] = f2mul(sd, iq_tap<R>(0));
-                        hn[0][1] = f2mul(sq2, iq_tap<R>(0));
-                    } else if (k < TAPS) {
-                        hn[0][0] = f2fma(sd, iq_tap<R>(k), hn[0][0]);
-                        hn[0][1] = f2fma(sq2, iq_tap<R>(k), hn[0][1]);
-                    }
-                    if (k == 1) {
-                        hn[1][0] = f2mul(sd, iq_tap<R>(0));
-                        hn[1][1] = f2mul(sq2, iq_tap<R>(0));
-                    } else if (k > 1) {
-                        hn[1][0] = f2fma(sd, iq_tap<R>(k - 1), hn[1][0]);
-                        hn[1][1] = f2fma(sq2, iq_tap<R>(k - 1), hn[1][1]);
-                    }
+            for (int e = 0; e < 2; ++e) {
+                const int k = 2 * j + e;
+                const float2 sd = e ? make_float2(v.z, v.w) : make_float2(v.x, v.y);
+                const float2 sq2 = __fmul2_rn(sd, sd);
+                if (k == 0) {
+                    hn[0][0] = f2mul(sd, iq_tap<R>(0));
+                    hn[0][1] = f2mul(sq2, iq_tap<R>(0));
+                } else if (k < TAPS) {
+                    hn[0][0] = f2fma(sd, iq_tap<R>(k), hn[0][0]);
+                    hn[0][1] = f2fma(sq2, iq_tap<R>(k), hn[0][1]);
+                }
+                if (k == 1) {
+                    hn[1][0] = f2mul(sd, iq_tap<R>(0));
+                    hn[1][1] = f2mul(sq2, iq_tap<R>(0));
+                } else if (k > 1) {
+                    hn[1][0] = f2fma(sd, iq_tap<R>(k - 1), hn[1][0]);
+                    hn[1][1] = f2fma(sq2, iq_tap<R>(k - 1), hn[1][1]);
                 }
             }
         }
-        const int r = r_in - R;
-        float2 f[2][2];
+    };
+    // V: vertical pass in accumulate form; f = the output row that closes with this input row
+    auto V = [&](const float2 (&hn)[2][2], float2 (&f)[2][2]) {
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
 #pragma unroll
@@ -374,24 +369,37 @@ __global__ void __launch_bounds__(IQ_THREADS, 4) k_psnr_ssim(IqaParams P)
                 A[q][s][TAPS - 2] = f2mul(hn[q][s], iq_tap<R>(0));
             }
         }
-        if (r >= ry0 && r >= R && r < h - R) { // uniform: an S-map row this CTA owns
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                // With u = (mean s, mean d) and e = (mean s^2, mean d^2) of the (x - 128) signals:
-                //   ux + uy = u.s + 256, ux - uy = u.d;  2 ux uy = (p.s^2 - p.d^2) / 2, ux^2 + uy^2 = (p.s^2 + p.d^2) / 2
-                //   v = e - u^2 = (var s, var d);       2 vxy = (v.s - v.d) / 2,     vx + vy = (v.s + v.d) / 2
-                // The four factors of S are used DOUBLED (the 2s cancel in the quotient), so the constants enter as 2 C1, 2 C2.
-                const float2 u = f[q][0];
-                const float2 pp0 = __fadd2_rn(u, make_float2(256.f, 0.f));
-                const float2 pp = __fmul2_rn(pp0, pp0);
-                float2 v = __ffma2_rn(make_float2(-u.x, -u.y), u, f[q][1]);
-                if (R == 3) v = f2mul(v, (float)(49.0 / 48.0)); // sample covariance for the 7x7 uniform window
-                const float t1 = pp.x + K1, t2 = v.x + K2;
-                const float A1 = t1 - pp.y, B1 = t1 + pp.y, A2 = t2 - v.y, B2 = t2 + v.y;
-                float inv;
-                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(B1 * B2)); // B1 B2 >= 4 C1 C2 = 1521: no range handling needed
-                if (q ? cf1 : cf0) ssum = fmaf(A1 * A2, inv, ssum);
-            }
+    };
+    // PW: S of one column, accumulated when `take` is set.  With u = (mean s, mean d) and e = (mean s^2, mean d^2) of the
+    // (x - 128) signals:
+    //   ux + uy = u.s + 256, ux - uy = u.d;  2 ux uy = (p.s^2 - p.d^2) / 2, ux^2 + uy^2 = (p.s^2 + p.d^2) / 2
+    //   v = e - u^2 = (var s, var d);       2 vxy = (v.s - v.d) / 2,     vx + vy = (v.s + v.d) / 2
+    // The four factors of S are used DOUBLED (the 2s cancel in the quotient), so the constants enter as 2 C1, 2 C2.
+    auto PW = [&](const float2 (&fq)[2], int take) {
+        const float2 u = fq[0];
+        const float2 pp0 = __fadd2_rn(u, make_float2(256.f, 0.f));
+        const float2 pp = __fmul2_rn(pp0, pp0);
+        float2 v = __ffma2_rn(make_float2(-u.x, -u.y), u, fq[1]);
+        if (R == 3) v = f2mul(v, (float)(49.0 / 48.0)); // sample covariance for the 7x7 uniform window
+        const float t1 = pp.x + K1, t2 = v.x + K2;
+        const float A1 = t1 - pp.y, B1 = t1 + pp.y, A2 = t2 - v.y, B2 = t2 + v.y;
+        float inv;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(B1 * B2)); // B1 B2 >= 4 C1 C2 = 1521: no range handling needed
+        if (take) ssum = fmaf(A1 * A2, inv, ssum);
+    };
+
+#pragma unroll 1
+    for (int r_in = r_first; r_in < r_last; ++r_in) {
+        const int buf = r_in & 1;
+        L(r_in + 4);
+        float2 hn[2][2], f[2][2]; // this row's horizontal sums [q][(s, d) | (s^2, d^2)] and the output row they close
+        const int r = r_in - R;
+        const bool emit = r >= ry0 && r >= R && r < h - R; // uniform: an S-map row this CTA owns
+        H(buf, hn);
+        V(hn, f);
+        if (emit) {
+            PW(f[0], cf0);
+            PW(f[1], cf1);
         }
         if (r_in + 1 < r_last) G(r_in + 1);
         cp_async_wait<2>();

@@ -61,6 +61,10 @@ def test_gray_from_packed_bytes_is_cv2_gray():
     g = ((x + (y << np.uint32(8))).astype(np.uint32).view(np.int32) >> 15).astype(np.int64)
     want = ((rgb[:, 0].astype(np.int64) * 9798 + rgb[:, 1].astype(np.int64) * 19235 + rgb[:, 2].astype(np.int64) * 3735 + 16384) >> 15) - 128
     assert np.array_equal(g, want)
+    # the shipped form: two IDP.2A with the 16-bit coefficients -- (R, G) against the low byte pair, (B, next byte x 0) against the
+    # high one -- accumulate the same 32-bit sum without the shift-add
+    g2 = ((p[:, 0] * 9798 + p[:, 1] * 19235 + k).astype(np.uint32) + (p[:, 2] * 3735).astype(np.uint32)).astype(np.uint32).view(np.int32) >> 15
+    assert np.array_equal(g2.astype(np.int64), want)
     if cv2_ok:
         assert np.array_equal(cv2.cvtColor(rgb[None], cv2.COLOR_RGB2GRAY)[0].astype(np.int64) - 128, want)
 
