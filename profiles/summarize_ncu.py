@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Turn an `ncu --set full` report into the text summary kept under profiles/ and (with --traffic) into
-profiles/ncu_traffic.json: DRAM bytes per bench-table kernel name for ONE step, stamped with the digest of the CUDA
-sources they were captured from (bench.py only attaches them while that digest still matches).
+profiles/ncu_traffic.json: DRAM bytes per bench-table kernel name for ONE step, each stamped with the digest of the CUDA
+sources that kernel is compiled from (bench.py only attaches a figure while its digest still matches; kernels absent from a
+partial re-capture keep their entry as long as their own sources did not move).
 
     python profiles/summarize_ncu.py gpurun_out/r02_ncu_full.ncu-rep profiles/r02_ncu_full_summary.txt [--traffic profiles/ncu_traffic.json]
 """
@@ -62,13 +63,23 @@ def main():
     print(f"{out_txt}: {len(body)} launches")
     if traffic_path:
         import bench
-        doc = {"source": f"{os.path.basename(out_txt)}: dram__bytes_read.sum + dram__bytes_write.sum summed over the launches of ONE step that the bench table "
-                         "files under each name (ncu --set full --clock-control none, cfg4_200mp, 1 GPU)",
-               "workload": "cfg4_200mp", "csrc_digest": bench.csrc_digest(), "kernels": traffic}
+        # every kernel carries the digest of ITS sources; entries of an earlier capture are kept while theirs still matches
+        # (a partial re-capture after a change to one translation unit), and say which summary they come from
+        doc = {"kernels": {}}
+        if os.path.exists(traffic_path):
+            with open(traffic_path) as f:
+                doc = json.load(f)
+        kept = {k: v for k, v in doc.get("kernels", {}).items() if k not in traffic and v.get("src_digest") == bench.csrc_digest(k)}
+        for k, v in traffic.items():
+            v["src_digest"] = bench.csrc_digest(k)
+            v["summary"] = os.path.basename(out_txt)
+        doc = {"source": "dram__bytes_read.sum + dram__bytes_write.sum summed over the launches of ONE step that the bench table files under each "
+                         "name (ncu --set full --clock-control none, cfg4_200mp, 1 GPU); per kernel: the summary file it was read from and the "
+                         "digest of the sources it is compiled from",
+               "workload": "cfg4_200mp", "kernels": {**kept, **traffic}}
         with open(traffic_path, "w") as f:
             json.dump(doc, f, indent=1)
-        print(f"{traffic_path}: digest {doc['csrc_digest']}, {list(traffic)}")
-
+        print(f"{traffic_path}: captured {list(traffic)}, kept {list(kept)}")
 
 if __name__ == "__main__":
     main()
