@@ -69,6 +69,20 @@ def main():
         b.record()
         torch.cuda.synchronize()
         ms_synced = a.elapsed_time(b) / args.steps
+        # the two-deep pipeline of bench.py's default loop (assess of step k overlaps fuse of step k + 1, two contexts)
+        pipe = D.PipelinedFuseAssess(pkg, infos, (H, W), wl.levels, 0, d_ref, (r0, r1), (e0, e1), D.SumsExchange(dev))
+        for _ in range(8):
+            pipe.submit()
+        pipe.join()
+        torch.cuda.synchronize()
+        a.record(pipe.s_fuse)
+        for _ in range(args.steps):
+            pipe.submit()
+        pipe.join()
+        b.record()
+        torch.cuda.synchronize()
+        ms_pipe = a.elapsed_time(b) / args.steps
+        del pipe
         native.profile_enable(ctx, True)
         native.profile_read(ctx)
         for _ in range(args.steps):
@@ -78,12 +92,13 @@ def main():
         for name, t, _ in native.profile_read(ctx):
             agg[name] = agg.get(name, 0.0) + t / args.steps
         native.profile_enable(ctx, False)
-        rec = {"rank": rank, "band": [r0, r1], "rows": r1 - r0, "tiles": len(mine), "ms": round(ms, 4), "ms_with_per_step_readback": round(ms_synced, 4),
+        rec = {"rank": rank, "band": [r0, r1], "rows": r1 - r0, "tiles": len(mine), "ms": round(ms, 4), "ms_with_per_step_readback": round(ms_synced, 4), "ms_pipelined": round(ms_pipe, 4),
                "kernels": {k: round(v, 4) for k, v in sorted(agg.items(), key=lambda kv: -kv[1])}}
         out.append(rec)
         print(json.dumps(rec), flush=True)
     worst = max(r["ms"] for r in out)
-    print(json.dumps({"gpus": args.gpus, "max_ms": worst, "mean_ms": round(sum(r["ms"] for r in out) / len(out), 4),
+    print(json.dumps({"gpus": args.gpus, "max_ms": worst, "max_ms_pipelined": max(r["ms_pipelined"] for r in out),
+                      "max_ms_with_per_step_readback": max(r["ms_with_per_step_readback"] for r in out), "mean_ms": round(sum(r["ms"] for r in out) / len(out), 4),
                       "sum_ms": round(sum(r["ms"] for r in out), 4)}))
 
 

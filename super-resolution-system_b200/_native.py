@@ -194,18 +194,21 @@ def check(rc: int, ctx=None, exc=None):
     raise SrfError(f"libsrfuse status {rc}: {text}")
 
 
-def context(device: int = 0):
-    """one srf_ctx per (process, device); raises SrfError when no sm_100 device is usable."""
+def context(device: int = 0, slot: int = 0):
+    """one srf_ctx per (process, device, slot); raises SrfError when no sm_100 device is usable.  Slot 0 is the context
+    every mirror class uses; further slots are independent contexts on the same device (own workspaces, own captured
+    graph) for callers that keep two fusions in flight (distributed.PipelinedFuseAssess)."""
     lib = load()
+    key = device if slot == 0 else (device, int(slot))
     with _lock:
-        if device not in _ctx:
+        if key not in _ctx:
             h = c_void_p()
             rc = lib.srf_create(device, C.byref(h))
             if rc != 0:
                 raise SrfError(f"srf_create(device={device}) failed ({rc}): {last_error(None)}")
-            _ctx[device] = h
+            _ctx[key] = h
             _ctx_locks[h.value] = threading.RLock()
-    return _ctx[device]
+    return _ctx[key]
 
 
 def ctx_lock(ctx):

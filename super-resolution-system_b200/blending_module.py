@@ -93,18 +93,19 @@ def weight_profile(feather_width: int, weight_type: WeightType) -> np.ndarray:
 
 class BlendingModule:
     def __init__(self, method: str = "laplacian", num_levels: int = 6, ssim_threshold: float = 0.95,
-                 use_cuda: bool = False, device: int = 0):
+                 use_cuda: bool = False, device: int = 0, context_slot: int = 0):
         self.method = FusionMethod(method)  # ValueError on an unknown method, like the reference
         self.num_levels = num_levels
         self.ssim_threshold = ssim_threshold
         self.use_cuda = True  # the only path there is; the reference's flag selected cv2.cuda and is accepted for compatibility
         self.device = int(device)
+        self.context_slot = int(context_slot)  # extension: an independent library context on the same device (see _native.context)
         self._profiles = {}
         logger.info("BlendingModule (libsrfuse, sm_100a): method=%s levels=%d device=%d", method, num_levels, self.device)
 
     # ------------------------------------------------------------------ pyramids (API-compat helpers)
     def _ctx(self):
-        return _native.context(self.device)
+        return _native.context(self.device, self.context_slot)
 
     def _pyr_down(self, img: np.ndarray) -> np.ndarray:
         lib = _native.load()

@@ -221,6 +221,25 @@ class SumsExchange:
             dist.all_reduce(self.local, op=dist.ReduceOp.SUM, group=self.group)
         return self.local.tolist()
 
+    def enqueue(self):
+        """the exchange alone, on the current stream, nothing read: sums self.local over the ranks in place (and, for the
+        peer kind, into pinned host memory); fetch() reads the totals of the LAST enqueued exchange"""
+        if self.kind == "peer":
+            st = torch.cuda.current_stream(self.device).cuda_stream
+            _native.check(self._lib.srf_allreduce_metrics(self._ctx, self.local.data_ptr(), 5 * self.slots, st), self._ctx)
+        elif self.kind == "nccl":
+            import torch.distributed as dist
+            dist.all_reduce(self.local, op=dist.ReduceOp.SUM, group=self.group)
+
+    def fetch(self, total_elems: int, stream=None):
+        """slot 0 of the last enqueue()d exchange, after synchronising `stream` (default: the current one)"""
+        st = torch.cuda.current_stream(self.device) if stream is None else stream
+        if self.kind == "peer":
+            _native.check(self._lib.srf_comm_result(self._ctx, self._host, 5 * self.slots, st.cuda_stream), self._ctx)
+            return self._sums(list(self._host)[:5], total_elems)
+        st.synchronize()
+        return self._sums(self.local.tolist()[:5], total_elems)
+
     @staticmethod
     def _sums(v, total_elems):
         s = _native.srf_iqa_sums()
@@ -482,3 +501,58 @@ class BandedHostFuser:
         self.h2d_bytes, self.p2p_bytes = h2d, p2p
         self.d2h_bytes = max(self.r1 - self.r0, 0) * self.W * nch
         return total
+
+
+class PipelinedFuseAssess:
+    """Steady-state (fuse band -> assess band) loop, two steps deep: the assessment of step k runs on its own stream while
+    the fusion of step k + 1 is already building its pyramids -- the two stress different pipes (FP32 filters against
+    byte / integer streaming) and, on the short bands of a many-rank job, the one fills the SMs the other's small launches
+    leave idle.  Two library contexts (each with its own workspaces and captured CUDA graph) fuse into two canvases in turn;
+    a canvas is overwritten only after the assessment that read it has finished (events).  Every step does the whole work
+    of the serial loop -- same kernels, same bytes; only the host no longer waits for a step's sums before it enqueues the
+    next (they land in `reducer` / pinned host memory; result() returns those of the last step)."""
+
+    def __init__(self, pkg, tiles, canvas_hw, levels: int, device_index: int, reference, band, fuse_rows, reducer, channels: int = 3):
+        self.dev = torch.device("cuda", device_index)
+        self.H, self.W = canvas_hw
+        self.band, self.fuse_rows, self.reducer, self.reference = band, fuse_rows, reducer, reference
+        self.bm = [pkg.BlendingModule(num_levels=levels, device=device_index, context_slot=s) for s in (0, 1)]
+        self.qa = pkg.QualityAssessmentModule(device=f"cuda:{device_index}")
+        self.plan = [b.plan_fusion(tiles, output_shape=canvas_hw) for b in self.bm]
+        shape = (self.H, self.W, channels) if channels > 1 else (self.H, self.W)
+        self.canvas = [torch.zeros(shape, dtype=torch.uint8, device=self.dev) for _ in (0, 1)]
+        self.s_fuse, self.s_iqa = torch.cuda.Stream(device=self.dev), torch.cuda.Stream(device=self.dev)
+        self.fused = [torch.cuda.Event() for _ in (0, 1)]
+        self.read = [torch.cuda.Event() for _ in (0, 1)]
+        self.k = 0
+        cur = torch.cuda.current_stream(self.dev)
+        self.s_fuse.wait_stream(cur)  # inputs uploaded on the caller's stream
+        self.s_iqa.wait_stream(cur)
+        for e in self.read:
+            e.record(self.s_iqa)
+
+    def submit(self):
+        c = self.k & 1
+        self.k += 1
+        with torch.cuda.stream(self.s_fuse):
+            self.s_fuse.wait_event(self.read[c])  # the assessment two steps back has finished with this canvas
+            self.bm[c].laplacian_fusion(self.plan[c], row_range=self.fuse_rows, out=self.canvas[c])
+            self.fused[c].record(self.s_fuse)
+        with torch.cuda.stream(self.s_iqa):
+            self.s_iqa.wait_event(self.fused[c])
+            self.qa.psnr_ssim_sums_device(self.reference, self.canvas[c], self.reducer.local, row_range=self.band)
+            self.read[c].record(self.s_iqa)
+            self.reducer.enqueue()
+
+    def result(self):
+        """srf_iqa_sums of the last submitted step (synchronises the assessment stream)"""
+        return self.reducer.fetch(self.H * self.W * (self.canvas[0].shape[2] if self.canvas[0].dim() == 3 else 1), stream=self.s_iqa)
+
+    def join(self):
+        """make the caller's current stream wait for everything submitted"""
+        cur = torch.cuda.current_stream(self.dev)
+        cur.wait_stream(self.s_fuse)
+        cur.wait_stream(self.s_iqa)
+
+    def last_canvas(self):
+        return self.canvas[(self.k - 1) & 1]

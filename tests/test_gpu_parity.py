@@ -529,6 +529,62 @@ def test_repeated_fuse_call_is_served_by_the_captured_graph(srs):
     assert np.array_equal(second, bm.laplacian_fusion(flipped, output_shape=out_hw))
 
 
+def test_pipelined_fuse_assess_equals_the_serial_loop(srs):
+    """distributed.PipelinedFuseAssess (bench.py's default loop): the assess of step k on its own stream while a second
+    library context fuses step k + 1 into the other canvas.  Both canvases hold the serial call's bytes, the sums of the
+    last step are the serial sums, both contexts replay their captured graphs, and new pixels behind the same tile
+    pointers show up in the next steps (nothing is cached across steps)"""
+    import torch
+    rng = np.random.default_rng(45)
+    tiles, pos = _grid_case(rng, 320, 384, 2, 3, 250, 300)
+    out_hw = (570, 984)
+    ref = synth(rng, *out_hw)
+    bm = srs.BlendingModule(num_levels=5)
+    qa = srs.QualityAssessmentModule()
+    want = bm.laplacian_fusion([srs.TileInfo(t, x, y, 0, 0) for t, (y, x) in zip(tiles, pos)], output_shape=out_hw)
+    s_want = qa.psnr_ssim_sums(ref, want)
+    dev = torch.device("cuda", 0)
+    dev_tiles = [torch.from_numpy(t).to(dev) for t in tiles]
+    infos = [srs.TileInfo(d, x, y, 0, 0) for d, (y, x) in zip(dev_tiles, pos)]
+    D = srs.distributed
+    lib = srs._native.load()
+    pipe = D.PipelinedFuseAssess(srs, infos, out_hw, 5, 0, torch.from_numpy(ref).to(dev), (0, out_hw[0]), (0, out_hw[0]), D.SumsExchange(dev))
+    c0, c1 = srs._native.context(0), srs._native.context(0, 1)
+    assert c0.value != c1.value
+    g0 = lib.srf_graph_replays(c0) + lib.srf_graph_replays(c1)
+    for _ in range(9):
+        pipe.submit()
+    got = pipe.result()
+    assert lib.srf_graph_replays(c0) + lib.srf_graph_replays(c1) - g0 >= 5
+    pipe.join()
+    torch.cuda.synchronize()
+    for cv in pipe.canvas:
+        assert np.array_equal(cv.cpu().numpy(), want)
+    assert (got.sq_err, got.ssim_count, got.n_elems) == (s_want.sq_err, s_want.ssim_count, s_want.n_elems)
+    assert got.ssim_sum == s_want.ssim_sum  # same kernel, same bytes, same fixed-order reduction
+    for d, t in zip(dev_tiles, tiles):
+        d.copy_(torch.from_numpy(np.ascontiguousarray(t[::-1, ::-1])))
+    torch.cuda.synchronize()
+    flipped = bm.laplacian_fusion([srs.TileInfo(np.ascontiguousarray(t[::-1, ::-1]), x, y, 0, 0) for t, (y, x) in zip(tiles, pos)], output_shape=out_hw)
+    for _ in range(2):
+        pipe.submit()
+    got2 = pipe.result()
+    pipe.join()
+    torch.cuda.synchronize()
+    for cv in pipe.canvas:
+        assert np.array_equal(cv.cpu().numpy(), flipped)
+    assert got2.sq_err == qa.psnr_ssim_sums(ref, flipped).sq_err
+    # a band: only the band's rows are fused and assessed, the sums are the band's share
+    pipe_b = D.PipelinedFuseAssess(srs, infos, out_hw, 5, 0, torch.from_numpy(ref).to(dev), (200, 400), (194, 405), D.SumsExchange(dev))
+    for _ in range(4):
+        pipe_b.submit()
+    band = pipe_b.result()
+    pipe_b.join()
+    torch.cuda.synchronize()
+    assert np.array_equal(pipe_b.last_canvas().cpu().numpy()[194:405], flipped[194:405])
+    assert band.sq_err == int(((flipped[200:400].astype(np.int64) - ref[200:400].astype(np.int64)) ** 2).sum())
+
+
 def test_fusion_graph_replay_and_device_sums(srs):
     """a repeated device call on a side stream is captured into a CUDA graph and replayed; it must track the tile
     CONTENTS (same addresses, new pixels) and agree with the host path; the enqueue-only IQA agrees with the sync one"""
