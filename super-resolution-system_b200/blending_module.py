@@ -409,8 +409,8 @@ class BlendingModule:
                 raise ValueError(f"weight map {i} is {tuple(wm.shape)}, smaller than the tile's part of the canvas ({ch}, {cw})")
             if is_cuda_tensor(wm):
                 f64 = wm.dtype == torch.float64
-                if not f64 and wm.dtype != torch.float32:
-                    f64 = torch.promote_types(torch.float32, wm.dtype) == torch.float64
+                if not f64 and wm.dtype != torch.float32:  # NumPy's promotion against float32, not torch's: 32 / 64-bit integers widen
+                    f64 = wm.dtype in (torch.int32, torch.int64)
                     wm = wm.to(torch.float64 if f64 else torch.float32)
                 if wm.stride(1) != 1:
                     wm = wm.contiguous()
