@@ -12,7 +12,9 @@
  *     result is in the caller's buffer; the others take DEVICE pointers, enqueue on `stream`
  *     (a cudaStream_t passed as void*, NULL = the legacy default stream) and do not synchronise;
  *   - the library owns only the workspace inside srf_ctx; callers own every buffer they pass;
- *   - one srf_ctx per device per host thread; calls on one ctx must not overlap;
+ *   - one srf_ctx per device per host thread; calls on one ctx must not overlap.  Several contexts on one device are
+ *     fine and independent (own workspaces, own captured graph): a caller that keeps two fusions in flight -- the fuse of
+ *     step k + 1 while step k is still being assessed on another stream -- gives each its own context;
  *   - there is NO CPU fallback: without a usable sm_100-class device srf_create fails.
  */
 #ifndef SRFUSE_H_
