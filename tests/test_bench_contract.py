@@ -34,3 +34,33 @@ def test_workloads_cover_baseline_configs():
     src = open(os.path.join(ROOT, "workloads.py")).read()
     for name in ("cfg1_100mp_720p", "cfg2_100mp", "cfg3_150mp", "cfg4_200mp"):
         assert name in names or name in src, name
+
+
+def test_traffic_figures_are_tied_to_the_sources_of_their_own_kernel(tmp_path, monkeypatch):
+    """bench.traffic_for attaches a committed ncu DRAM figure only while the digest of THAT kernel's translation units is the
+    one recorded with the figure: a change to srf_iqa.cu drops the SSIM figure and keeps the fuse kernels', a change to the
+    shared header drops all of them; launch counts that differ from the capture's drop the figure too"""
+    sys.path.insert(0, ROOT)
+    import shutil
+    import bench
+    with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+        tj = json.load(f)
+    assert set(tj["kernels"]) >= {"psnr_ssim", "final_gather", "up_level", "down_u8", "down_f32"}
+    for name, k in tj["kernels"].items():  # the committed table matches the committed sources
+        assert k["src_digest"] == bench.csrc_digest(name), name
+        got, dig = bench.traffic_for(name, "cfg4_200mp", 1, k["launches"])
+        assert got == k["dram_bytes_per_step"] and dig == k["src_digest"]
+        assert bench.traffic_for(name, "cfg4_200mp", 1, k["launches"] + 1)[0] is None
+        assert bench.traffic_for(name, "cfg4_200mp", 2, k["launches"])[0] is None  # per-rank traffic of a band is another number
+    # a scratch copy of the tree: touch one translation unit at a time
+    root2 = tmp_path / "repo"
+    shutil.copytree(os.path.join(ROOT, "super-resolution-system_b200", "csrc"), root2 / "super-resolution-system_b200" / "csrc")
+    shutil.copytree(os.path.join(ROOT, "profiles"), root2 / "profiles", ignore=shutil.ignore_patterns("*.csv", "*.txt", "scratch"))
+    monkeypatch.setattr(bench, "ROOT", str(root2))
+    with open(root2 / "super-resolution-system_b200" / "csrc" / "srf_iqa.cu", "a") as f:
+        f.write("// touched\n")
+    assert bench.traffic_for("psnr_ssim", "cfg4_200mp", 1, 1)[0] is None
+    assert bench.traffic_for("final_gather", "cfg4_200mp", 1, tj["kernels"]["final_gather"]["launches"])[0] is not None
+    with open(root2 / "super-resolution-system_b200" / "csrc" / "srf_common.cuh", "a") as f:
+        f.write("// touched\n")
+    assert bench.traffic_for("final_gather", "cfg4_200mp", 1, tj["kernels"]["final_gather"]["launches"])[0] is None
