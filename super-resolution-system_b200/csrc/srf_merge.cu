@@ -338,8 +338,9 @@ extern "C" int srf_weighted_average_host(srf_ctx *ctx, const srf_wavg_tile *tile
     size_t total = 0, h2d = 0;
     for (int i = 0; i < n_tiles; ++i) { // only the part of a tile (and of its map) that lies on the canvas travels
         const int ch = std::max(std::min(tiles[i].y + tiles[i].h, out_h) - tiles[i].y, 0), cw = std::max(std::min(tiles[i].x + tiles[i].w, out_w) - tiles[i].x, 0);
-        dt[i].h = std::max(ch, 1);
-        dt[i].w = std::max(cw, 1);
+        const bool on_canvas = ch > 0 && cw > 0; // a tile that lies entirely off the canvas contributes nothing and is not staged
+        dt[i].h = on_canvas ? ch : 0;
+        dt[i].w = on_canvas ? cw : 0;
         off[i] = total;
         dt[i].pitch = srf_align_up((size_t)dt[i].w * channels, 16);
         total += srf_align_up(dt[i].pitch * dt[i].h, 256);
@@ -350,7 +351,7 @@ extern "C" int srf_weighted_average_host(srf_ctx *ctx, const srf_wavg_tile *tile
         total += srf_align_up(dt[i].weight_pitch * dt[i].h, 256);
     }
     const size_t cpitch = srf_align_up((size_t)out_w * channels, 256);
-    if ((rc = srf_reserve(ctx, ctx->ws_stage_in, total))) return rc;
+    if ((rc = srf_reserve(ctx, ctx->ws_stage_in, std::max<size_t>(total, 256)))) return rc;
     if ((rc = srf_reserve(ctx, ctx->ws_stage_out, cpitch * (size_t)out_h))) return rc;
     cudaStream_t st = ctx->own_stream;
     uint8_t *din = (uint8_t *)ctx->ws_stage_in.ptr, *dcanvas = (uint8_t *)ctx->ws_stage_out.ptr;
@@ -358,6 +359,7 @@ extern "C" int srf_weighted_average_host(srf_ctx *ctx, const srf_wavg_tile *tile
         const size_t esz = tiles[i].weight_f64 ? 8 : 4;
         dt[i].data = din + off[i];
         dt[i].weight = din + woff[i];
+        if (dt[i].h == 0) continue;
         SRF_CHECK_CUDA(ctx, cudaMemcpy2DAsync(din + off[i], dt[i].pitch, tiles[i].data, tiles[i].pitch, (size_t)dt[i].w * channels, dt[i].h,
                                               cudaMemcpyHostToDevice, st));
         SRF_CHECK_CUDA(ctx, cudaMemcpy2DAsync(din + woff[i], dt[i].weight_pitch, tiles[i].weight, tiles[i].weight_pitch, (size_t)dt[i].w * esz, dt[i].h,

@@ -698,6 +698,15 @@ def test_weighted_average_custom_maps_vs_reference_golden(srs, golden, oracle):
     want = oracle.fusion_oracle.weighted_average_custom(big, bpos, maps, (700, 900))
     got = bm.weighted_average_fusion([srs.TileInfo(t, x, y, 0, 0) for t, (y, x) in zip(big, bpos)], weights=maps, output_shape=(700, 900))
     assert np.array_equal(got, want)
+    # a tile that lies entirely off the canvas contributes nothing (host and device paths)
+    off = big + [synth(rng, 64, 64)]
+    opos = bpos + [(900, 50)]
+    omaps = maps + [np.ones((64, 64), np.float32)]
+    assert np.array_equal(bm.weighted_average_fusion([srs.TileInfo(t, x, y, 0, 0) for t, (y, x) in zip(off, opos)], weights=omaps,
+                                                     output_shape=(700, 900)), want)
+    dev_off = bm.weighted_average_fusion([srs.TileInfo(torch.from_numpy(t).cuda(), x, y, 0, 0) for t, (y, x) in zip(off, opos)], weights=omaps,
+                                         output_shape=(700, 900))
+    assert np.array_equal(dev_off.cpu().numpy(), want)
     with pytest.raises(ValueError):  # a map smaller than its tile does not broadcast in the reference either
         bm.weighted_average_fusion(infos, weights=[np.ones((10, 10), np.float32)])
     with pytest.raises(ValueError):
