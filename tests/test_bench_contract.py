@@ -64,3 +64,35 @@ def test_traffic_figures_are_tied_to_the_sources_of_their_own_kernel(tmp_path, m
     with open(root2 / "super-resolution-system_b200" / "csrc" / "srf_common.cuh", "a") as f:
         f.write("// touched\n")
     assert bench.traffic_for("final_gather", "cfg4_200mp", 1, tj["kernels"]["final_gather"]["launches"])[0] is None
+
+
+def test_cpu_sample_is_a_two_by_two_block_scaled_per_tile():
+    """the bounded CPU sample: tiles 0, 1 and the two below them (every overlap kind), and the value scales the fusion per
+    tile and the assessment per megapixel to the whole workload"""
+    sys.path.insert(0, ROOT)
+    import numpy as np
+    import bench
+
+    class WL:
+        grid = (6, 4)
+        canvas_hw = (11546, 17320)
+        tiles = [np.zeros((8, 8, 3), np.uint8) for _ in range(24)]
+        positions_yx = [(3482 * (i // 6), 3278 * (i % 6)) for i in range(24)]
+        reference = np.zeros((11546, 17320, 1), np.uint8)
+
+    tiles, pos, hw, ref = bench.cpu_sample(WL)
+    assert pos == [(0, 0), (0, 3278), (3482, 0), (3482, 3278)] and hw == (3490, 3286) and ref.shape[:2] == hw
+    WL.tiles, WL.positions_yx = WL.tiles[:2], WL.positions_yx[:2]
+    assert len(bench.cpu_sample(WL)[0]) == 2  # not enough tiles for a block: the first two
+    calls = {"fuse": 0}
+
+    def fuse(t, p, hw_, levels):
+        calls["fuse"] += 1
+        return np.zeros(hw_ + (3,), np.uint8)
+
+    backend = ("port", fuse, lambda a, b: 30.0, lambda a, b: 0.9, "stub")
+    a = np.zeros((64, 64, 3), np.uint8)
+    v, tf, tq, mpf, mpq, p, s = bench.cpu_step(backend, [a, a, a, a], [(0, 0)] * 4, (64, 64), np.zeros((64, 64, 3), np.uint8), 3,
+                                               iqa_rows=32, whole=(24, 200.0))
+    assert calls["fuse"] == 1 and (p, s) == (30.0, 0.9) and mpq == 32 * 64 / 1e6
+    assert v == 200.0 / (tf / 4 * 24 + tq / mpq * 200.0)
